@@ -1,0 +1,201 @@
+/*
+ * spectralkernels_b200.h -- C ABI of the B200 (sm_100a) evaluator for the K(r) hot path of
+ * pbeckman/SpectralKernels.jl.
+ *
+ * Plain C: `extern "C"`, pointers and sizes only, no torch / CUDA types in any signature.
+ * Every function returns an int status (SK_OK == 0, negative == error), never throws, and
+ * never calls back into the host language.  All host buffers are owned by the caller and
+ * must stay alive for the duration of the call; all device memory is owned by the sk_ctx.
+ * One sk_ctx must be used by one host thread at a time (the reference's config is not
+ * re-entrant either: src/adaptive.jl:17-21, src/quadrature.jl:170).
+ *
+ * There are two levels.  Each entry point cites the reference interface it replaces
+ * (paths are into the reference repository).
+ *
+ *   Level 0  sk_nufft1d3            == finufft1d3(w, s, x)             src/utils.jl:10
+ *   Level 1  device-resident session that absorbs every O(N) pass of
+ *            kernel_values / _kernel_values / fourier_integrate_interval /
+ *            fourier_integrate_panel / updatequadbufs!; the host keeps only the scalar
+ *            control flow of src/adaptive.jl:149-200 and src/quadrature.jl:181-272.
+ *
+ * INTEGRATION.md shows the Julia `ccall` bindings for each entry point.
+ */
+#ifndef SPECTRALKERNELS_B200_H
+#define SPECTRALKERNELS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SK_ABI_VERSION 1
+
+/* status codes */
+#define SK_OK 0
+#define SK_ERR_CUDA (-1)        /* a CUDA runtime call failed (sk_last_error has the text)      */
+#define SK_ERR_ARG (-2)         /* invalid argument                                            */
+#define SK_ERR_STATE (-3)       /* call sequence violated (e.g. sub-interval before targets)   */
+#define SK_ERR_NAN (-4)         /* NaN in the 2m-rule panel integral, src/quadrature.jl:165     */
+#define SK_ERR_SPLIT (-5)       /* b - a <= 1e-16, src/utils.jl:28-36 (check_subdivide_failure) */
+#define SK_ERR_ALLOC (-6)       /* out of device / pinned memory                               */
+#define SK_ERR_CUFFT (-7)       /* cuFFT failure                                               */
+#define SK_ERR_UNSUPPORTED (-8) /* a reference branch this build does not cover                */
+#define SK_ERR_INPUT (-9)       /* targets contain NaN / negative / non-finite values          */
+
+/* integral kernels, src/quadrature.jl:176-180 and :130-136 */
+#define SK_KERNEL_COS 0
+#define SK_KERNEL_SIN 1
+
+/* convergence criteria, src/adaptive.jl:12, :231-233 */
+#define SK_CRIT_PANEL 0
+#define SK_CRIT_TAILS 1
+#define SK_CRIT_BOTH 2
+
+/* built-in spectral-density families (evaluated on the device) */
+#define SK_SDF_HOST 0        /* strengths are supplied by the host (sk_subinterval_host)               */
+#define SK_SDF_MATERN 1      /* params (phi, rho, nu, d): phi*(rho^2+w^2)^(-nu-d/2), scripts/matern_pair.jl:17 */
+#define SK_SDF_EXPONENTIAL 2 /* params (phi, alpha):      phi*exp(-alpha*|w|), test/derivatives/jacobian.jl:5 */
+
+typedef struct sk_ctx sk_ctx;
+
+typedef struct sk_target_info {
+  int64_t n_in;      /* number of input distances                                          */
+  int64_t n_unique;  /* number of unique distances (length of the sorted unique set)       */
+  int32_t has_zero;  /* 1 if the smallest unique distance is 0 (src/adaptive.jl:133)       */
+  int32_t _pad;
+  double r_min_pos;  /* smallest strictly positive distance (0 if none)                    */
+  double r_max;      /* largest distance                                                   */
+} sk_target_info;
+
+typedef struct sk_subinterval_opts {
+  double cmul;       /* config.c, src/adaptive.jl:43-45, applied at src/quadrature.jl:250-251        */
+  double p;          /* config.p, src/adaptive.jl:42                                                */
+  int32_t kernel;    /* SK_KERNEL_COS / SK_KERNEL_SIN, src/quadrature.jl:177                        */
+  int32_t logw;      /* config.logw: multiply the integrand by log(w), src/quadrature.jl:242        */
+} sk_subinterval_opts;
+
+typedef struct sk_scan_args {
+  double trunc_a;    /* -c/(d+dim)*b^(d+dim), first bound of src/adaptive.jl:225-228 (target independent) */
+  double trunc_num;  /* c*b^(d+(dim-1)/2), numerator of the second bound                                 */
+  double xpow;       /* (dim+1)/2, exponent of x in the second bound                                     */
+  double tau;        /* config.tol*abs(k0)/2, src/adaptive.jl:191                                        */
+  int32_t criteria;  /* SK_CRIT_*; the host switches to PANEL after a NaN tail fit (src/adaptive.jl:170-175) */
+  int32_t _pad;
+} sk_scan_args;
+
+typedef struct sk_stats {
+  int64_t n_subintervals;   /* sub-intervals evaluated since sk_run_begin                     */
+  int64_t n_accepted;
+  int64_t n_panels;         /* outer panels committed                                         */
+  int64_t units;            /* sum over sub-intervals of N_active  (SURVEY section 8d "unit")  */
+  int64_t n_fast;           /* sub-intervals that took the NUFFT branch                        */
+  int64_t n_direct;         /* sub-intervals that took the direct-summation branch             */
+  int64_t kernel_launches;  /* kernels of this library launched since sk_run_begin             */
+  int64_t last_nf;          /* spread-grid size of the last NUFFT                              */
+  int64_t last_nf2;         /* FFT size of the last NUFFT                                      */
+  double interp_ms;         /* device time in the interpolation kernel since sk_run_begin      */
+  double source_ms;         /* device time in node/strength/spread/FFT since sk_run_begin      */
+  int32_t timing_enabled;
+  int32_t _pad;
+} sk_stats;
+
+/* ---- library --------------------------------------------------------------------------------- */
+int sk_abi_version(void);
+const char *sk_error_string(int code);
+const char *sk_last_error(const sk_ctx *ctx);            /* detail of the last failure on ctx        */
+
+int sk_ctx_create(int device, sk_ctx **out);
+int sk_ctx_destroy(sk_ctx *ctx);
+int sk_ctx_set_timing(sk_ctx *ctx, int enabled);          /* per-stage cudaEvent timers (NVTX-like)   */
+int sk_ctx_set_nufft_eps(sk_ctx *ctx, double eps);        /* default 1e-15, as hard-wired in src/utils.jl:10 */
+int sk_ctx_synchronize(sk_ctx *ctx);
+/* the CUDA stream of the context as an opaque handle (cudaStream_t), for event timing by the caller */
+int sk_ctx_stream(sk_ctx *ctx, void **stream_out);
+
+/* pinned host memory for callers that want full PCIe rate (Julia: unsafe_wrap the pointer) */
+int sk_host_alloc(size_t bytes, void **out);
+int sk_host_free(void *ptr);
+
+/* ---- Level 0: drop-in for finufft1d3(w, s, x), src/utils.jl:10 -------------------------------- */
+/* out[j] = sum_k s[k] * exp(+i * 2*pi * x[j] * w[k]);  s and out are interleaved (re, im);        */
+/* all pointers are HOST pointers; synchronous.  eps <= 0 selects the context default.             */
+int sk_nufft1d3(sk_ctx *ctx, int64_t M, const double *w, const double *s, int64_t N, const double *x,
+                double *out, double eps);
+
+/* ---- Level 1: quadrature rules, QuadRule src/quadrature.jl:27-47 ------------------------------- */
+/* (m, k) = quadspec; p = config.p.  Node/weight pointers are HOST arrays of length m (…1) and    */
+/* 2m (…2) on [-1,1], ascending; pass NULL for all eight to let the library generate them          */
+/* (Gauss-Legendre, and Gauss-Jacobi(0,p) when p != 0).                                            */
+int sk_rule_set(sk_ctx *ctx, int32_t m, int32_t k, double p,
+                const double *leg_no1, const double *leg_wt1, const double *leg_no2, const double *leg_wt2,
+                const double *jac_no1, const double *jac_wt1, const double *jac_no2, const double *jac_wt2);
+/* which: 0 legendre m, 1 legendre 2m, 2 jacobi m, 3 jacobi 2m; copies to HOST arrays */
+int sk_rule_get(sk_ctx *ctx, int32_t which, double *no, double *wt);
+
+/* ---- Level 1: integrand ------------------------------------------------------------------------ */
+/* deriv_index 0 = S itself; j >= 1 = dS/dparams[j-1] (the integrands of src/derivatives.jl:63-72) */
+int sk_sdf_builtin(sk_ctx *ctx, int32_t family, const double *params, int32_t nparams, int32_t deriv_index);
+
+/* ---- Level 1: targets, replaces unique/sort/Dict of src/adaptive.jl:99-107, :113-120 ----------- */
+int sk_targets_set(sk_ctx *ctx, const double *xs_host, int64_t n_in, sk_target_info *info);
+int sk_targets_set_device(sk_ctx *ctx, const double *xs_dev, int64_t n_in, sk_target_info *info);
+/* sorted unique value at 1-based index idx */
+int sk_target_value(sk_ctx *ctx, int64_t idx, double *out);
+
+/* ---- Level 1: the adaptive loop's device steps ------------------------------------------------- */
+/* ks = errs = 0 (src/adaptive.jl:122) and reset statistics */
+int sk_run_begin(sk_ctx *ctx);
+/* ks[1] = value, errs[1] = NaN when the first unique distance is 0 (src/adaptive.jl:133-146) */
+int sk_zero_lag_set(sk_ctx *ctx, double value);
+/* start an outer panel over the 1-based inclusive index range [ix1, hi] (src/adaptive.jl:157-159,
+ * src/quadrature.jl:174-175: I = err = 0); returns the smallest / largest active distance */
+int sk_panel_begin(sk_ctx *ctx, int64_t ix1, int64_t hi, double *r_lo, double *r_hi);
+/* override the distance range the transform geometry is built for (default: the panel's own
+ * [r_lo, r_hi]).  A target-sharded multi-GPU run passes the GLOBAL range so that every rank uses the
+ * same grids and per-target results do not depend on the sharding. */
+int sk_panel_set_range(sk_ctx *ctx, double r_lo, double r_hi);
+/* one pass of the bisection loop body, src/quadrature.jl:183-258: build both rules on [a,b]
+ * (updatequadbufs!, :49-95) from the built-in S, transform (fast or direct, :105-128), select
+ * Re/Im, scale by cmul, stage I2 and |I2-I1|, and return max|I2-I1| (NaN if any is NaN). */
+int sk_subinterval(sk_ctx *ctx, double a, double b, const sk_subinterval_opts *opts, double *max_abs_diff);
+/* same with host-evaluated nodes and (real) strengths: no1/buf1 length m*k, no2/buf2 length 2*m*k
+ * (the buffers of src/adaptive.jl:50-53 after updatequadbufs!) */
+int sk_subinterval_host(sk_ctx *ctx, double a, double b, const double *no1, const double *buf1,
+                        const double *no2, const double *buf2, const sk_subinterval_opts *opts,
+                        double *max_abs_diff);
+/* copy the nodes / strengths the last sk_subinterval generated to HOST arrays (parity tests) */
+int sk_sources_get(sk_ctx *ctx, int32_t rule /*0: m-rule, 1: 2m-rule*/, double *no, double *buf);
+/* I += I2; err += |I2-I1| for the staged sub-interval, src/quadrature.jl:260-262 */
+int sk_subinterval_accept(sk_ctx *ctx);
+/* ks += I; errs += err over the panel range, src/adaptive.jl:163-164 */
+int sk_panel_commit(sk_ctx *ctx);
+/* convergence scan from hi downwards, src/adaptive.jl:183-199, search part: returns the highest
+ * unconverged 1-based index (ix1-1 if every active target converged) and the distance at that index
+ * (0 if none).  No side effects. */
+int sk_converge_scan(sk_ctx *ctx, const sk_scan_args *args, int64_t *new_hi, double *r_at_new_hi);
+/* side-effect part: errs[ix] += 2*trunc_err for new_hi < ix <= hi (src/adaptive.jl:194) and close the
+ * panel.  Single GPU: pass the new_hi sk_converge_scan returned.  Target-sharded multi-GPU: pass the
+ * local index of the GLOBAL stopping distance (sk_target_upper_index of the max over ranks). */
+int sk_converge_apply(sk_ctx *ctx, const sk_scan_args *args, int64_t new_hi);
+/* largest 1-based index whose sorted unique distance is <= r (0 if none) */
+int sk_target_upper_index(sk_ctx *ctx, double r, int64_t *idx);
+/* values and errors in the ORIGINAL input order, duplicates included (src/adaptive.jl:105-107);
+ * HOST arrays of length n_in; errs may be NULL */
+int sk_results_get(sk_ctx *ctx, double *vals, double *errs);
+/* same into DEVICE arrays (no PCIe traffic) */
+int sk_results_get_device(sk_ctx *ctx, double *vals_dev, double *errs_dev);
+int sk_stats_get(sk_ctx *ctx, sk_stats *out);
+
+/* ---- host-side plan helpers exported for tests (no GPU needed) --------------------------------- */
+/* Gauss-Legendre (p == 0) / Gauss-Jacobi(0,p) on [-1,1], ascending; 0 on success */
+int sk_host_gauss_rule(int32_t n, double p, double *no, double *wt);
+/* exp-of-semicircle plan: tap polynomial coefficients coef[w/2][2][nc/2] (even, odd parts in s^2,
+ * s = 2x), Chebyshev coefficients qc[nq] of (2/w)/phihat(xi) in tau = 2 (xi/ximax)^2 - 1 */
+int sk_host_es_plan(int32_t w, double *beta, int32_t *nc, double *coef, int32_t *nq, double *qc, double *ximax);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECTRALKERNELS_B200_H */

@@ -1,0 +1,22 @@
+"""
+spectralkernels.jl_b200 -- B200 (sm_100a) evaluator for the K(r) hot path of pbeckman/SpectralKernels.jl.
+
+    csrc/                 CUDA kernels + the C ABI (include/spectralkernels_b200.h) -> libsk_b200.so
+    _capi.py              ctypes binding of that ABI (what Julia binds with ccall)
+    adaptive.py           host mirror of AdaptiveKernelConfig / kernel_values (scalar control flow only)
+    sdf.py                built-in spectral-density families with device generators
+    sharded.py            scalar reductions for a target-sharded multi-GPU run (torch.distributed)
+
+The directory name contains a dot, so import it through the loader module at the repository root:
+
+    import spectralkernels_jl_b200 as sk
+"""
+from . import _capi, sdf
+from ._capi import PinnedArray, Session, SkError, host_gauss_rule, load
+from .adaptive import (AdaptiveKernelConfig, compute_k0, estimate_tail_decay, gen_derivative_config,
+                       gen_new_sdf_config, kernel_values)
+from .sdf import Exponential, Matern
+
+__all__ = ["AdaptiveKernelConfig", "kernel_values", "compute_k0", "estimate_tail_decay", "gen_derivative_config",
+           "gen_new_sdf_config", "Matern", "Exponential", "Session", "SkError", "PinnedArray", "host_gauss_rule",
+           "load", "sdf"]

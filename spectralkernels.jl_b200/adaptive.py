@@ -1,0 +1,364 @@
+"""
+Host side of the K(r) path: the reference's public API for this path with the same names, argument
+meaning and error behaviour --
+
+    AdaptiveKernelConfig(f; df, dim, alpha, tol, derivative, logw, convergence_criteria, tail, quadspec)
+                                                                         (src/adaptive.jl:2-59)
+    kernel_values(cfg, xs; k0, param_derivative, verbose) -> (values, errors)   (src/adaptive.jl:95-108)
+
+-- keeping only the scalar control flow of the adaptive panel driver (src/adaptive.jl:149-200) and of
+the bisection loop (src/quadrature.jl:181-272).  Every O(N) pass runs on the GPU behind the C ABI of
+include/spectralkernels_b200.h (ctypes here, `ccall` in Julia: INTEGRATION.md).  This module is what
+the Julia host does, written in Python because the image has no Julia.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import SK_CRIT, SK_KERNEL_COS, SK_KERNEL_SIN, ScanArgs, Session, SkError
+from .sdf import is_builtin
+
+_CRITERIA = ("panel", "tails", "both")
+
+
+def _sym(s) -> str:
+    return str(s).lstrip(":")
+
+
+class AdaptiveKernelConfig:
+    """Mirror of `AdaptiveKernelConfig` (src/adaptive.jl:2-59).
+
+    `f` is a callable S(w) accepting numpy arrays, or a built-in family from `sdf` (device-evaluated).
+    Extra, optional keywords (reference-compatible defaults): `device` (CUDA ordinal), `nufft_eps`
+    (the reference hard-wires 1e-15 in src/utils.jl:10), `engine` (an object implementing the Session
+    interface; used by the multi-process tests)."""
+
+    def __init__(self, f: Callable, *, df: Optional[Callable] = None, dim: int = 1, alpha: float = 0.0,
+                 tol: float = 1e-8, derivative: bool = False, logw: bool = False,
+                 convergence_criteria="both", tail: Optional[float] = None,
+                 quadspec: Tuple[int, int] = (2 ** 12, 2 ** 4), device: int = 0, nufft_eps: float = 1e-15,
+                 engine=None):
+        crit = _sym(convergence_criteria)
+        if crit not in _CRITERIA:                                              # adaptive.jl:29-31
+            raise ValueError("Argument convergence_criteria must be one of :panel, :tails, :both.")
+        if alpha >= dim:                                                       # adaptive.jl:33-35
+            raise ValueError("alpha must be less than dim to be integrable.")
+        quadspec = (int(quadspec[0]), int(quadspec[1]))
+        if tol < 1e-12 and quadspec[0] * quadspec[1] > 2 ** 12:                # adaptive.jl:37-40
+            warnings.warn("Tolerances ε < 1e-12 are not recommended. Switching to a smaller quadrature rule for "
+                          "higher accuracy (but slower) computations.")
+            quadspec = (2 ** 12, 1)
+        self.f, self.df = f, df
+        self.dim, self.alpha, self.tol = int(dim), float(alpha), float(tol)
+        self.derivative, self.logw = bool(derivative), bool(logw)
+        self.convergence_criteria, self.tail, self.quadspec = crit, tail, quadspec
+        self.p = -self.alpha + (0 if self.dim == 1 else self.dim / 2) + (1 if self.derivative else 0)   # :42
+        c = 2.0 if self.dim == 1 else 2 * math.pi                               # :43
+        if self.derivative:
+            c *= -2 * math.pi                                                   # :44
+        if self.logw:
+            c *= -1                                                             # :45
+        self.c = c
+        self.device, self.nufft_eps = int(device), float(nufft_eps)
+        self._engine = engine
+        self._rules = None       # host copies of the canonical rules (for host-evaluated integrands)
+
+    # -- the config owns its device scratch, like cfg.buffers / cfg.splittingheap (adaptive.jl:17-21) --
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = Session(self.device)
+            if self.nufft_eps != 1e-15:
+                self._engine.set_nufft_eps(self.nufft_eps)
+        return self._engine
+
+    @property
+    def quadsz(self) -> int:                                                    # adaptive.jl:93
+        return self.quadspec[0] * self.quadspec[1]
+
+    def _kw(self):
+        return dict(df=self.df, dim=self.dim, alpha=self.alpha, tol=self.tol, derivative=self.derivative,
+                    logw=self.logw, convergence_criteria=self.convergence_criteria, tail=self.tail,
+                    quadspec=self.quadspec, device=self.device, nufft_eps=self.nufft_eps)
+
+
+def gen_derivative_config(cfg: AdaptiveKernelConfig) -> AdaptiveKernelConfig:   # adaptive.jl:61-66
+    kw = cfg._kw()
+    kw["derivative"] = True
+    out = AdaptiveKernelConfig(cfg.f, **kw)
+    out._engine = cfg._engine
+    return out
+
+
+def gen_new_sdf_config(cfg: AdaptiveKernelConfig, new_f, alpha=None) -> AdaptiveKernelConfig:   # adaptive.jl:69-72
+    out = AdaptiveKernelConfig(new_f, df=cfg.df, dim=cfg.dim, alpha=cfg.alpha if alpha is None else alpha,
+                               tol=cfg.tol, device=cfg.device, nufft_eps=cfg.nufft_eps)
+    out._engine = cfg._engine
+    return out
+
+
+def _f_scalar(f, w: float) -> float:
+    return float(np.asarray(f(np.asarray([w], dtype=np.float64)))[0])
+
+
+def compute_k0(cfg: AdaptiveKernelConfig) -> float:
+    """src/adaptive.jl:74-91 (host scalar work, stays on the host as in the reference).  QuadGK's
+    quadgk(f, 0, Inf; atol=0, rtol=min(1e-8, 1e-2 tol)) becomes QUADPACK qagi with the same tolerances."""
+    from scipy import integrate, special
+    f, p = cfg.f, cfg.p
+    L = 1.0
+    while L ** p * abs(_f_scalar(f, L)) > abs(_f_scalar(f, 0.0)) / 2:          # :78-80
+        L *= 2
+    if cfg.dim == 1:
+        pref = lambda w: 1.0
+    else:
+        nu = cfg.dim / 2 - 1 + (1 if cfg.derivative else 0)                     # :85
+        pref = lambda w: (math.pi * w) ** nu / special.gamma(nu + 1)
+
+    def integrand(w):                                                          # :82 / :86
+        wl = w * L
+        if wl == 0.0 and (p < 0 or cfg.logw):
+            return 0.0
+        return pref(w) * wl ** p * (math.log(wl) if cfg.logw else 1.0) * _f_scalar(f, wl) * L
+
+    rtol = min(1e-8, 1e-2 * cfg.tol)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        val = integrate.quad(integrand, 0.0, np.inf, epsabs=0.0, epsrel=max(rtol, 5e-14), limit=400)[0]
+    return cfg.c * val                                                         # :88-90
+
+
+def estimate_tail_decay(cfg: AdaptiveKernelConfig, a: float, b: float, d=None):
+    """src/adaptive.jl:204-220, including its quirk: `range(a + (b-a), stop=b, length=1000)` is 1000
+    copies of b, so the least-squares fit is rank one and Julia's `\\` returns the minimum-norm solution."""
+    nf = 1000
+    start = a + (b - a)
+    ws = np.full(nf, b) if start == b else np.linspace(start, b, nf)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        fw = np.abs(np.asarray(cfg.f(ws), dtype=np.float64))
+        if d is None:
+            tmp = np.log(fw)                                                   # :213
+            if not np.all(np.isfinite(tmp)):
+                d = float("nan")
+            else:
+                A = np.stack([np.ones(nf), np.log(ws)], axis=1)
+                d = float(np.linalg.lstsq(A, tmp, rcond=None)[0][1])           # :214
+        d = d - cfg.alpha                                                      # :216
+        c = float(np.sum(ws ** d * fw) / np.sum(ws ** (2 * d)))                # :218
+    return c, d
+
+
+def _scan_args(cfg, b, c, d, tau, crit) -> ScanArgs:
+    """The target-independent pieces of truncation_error_estimate (src/adaptive.jl:222-229)."""
+    dim = cfg.dim
+    if crit == "panel":
+        ta = tn = 0.0
+    else:
+        with np.errstate(all="ignore"):
+            ta = float(-c / (d + dim) * np.float64(b) ** (d + dim))
+            tn = float(c * np.float64(b) ** (d + (dim - 1) / 2))
+    return ScanArgs(ta, tn, (dim + 1) / 2, float(tau), SK_CRIT[crit], 0)
+
+
+class _NoComm:
+    """Single-process stand-in for the scalar reductions of a target-sharded run."""
+    world_size = 1
+
+    def max(self, vals: Sequence[float]) -> List[float]:
+        return list(vals)
+
+    def min(self, vals: Sequence[float]) -> List[float]:
+        return list(vals)
+
+
+def _host_rules(cfg: AdaptiveKernelConfig, eng):
+    if cfg._rules is None:
+        leg = eng.rule_get(0) + eng.rule_get(1)
+        jac = (eng.rule_get(2) + eng.rule_get(3)) if cfg.p != 0.0 else leg
+        cfg._rules = (leg, jac)
+    return cfg._rules
+
+
+def _subpanel_edges(a: float, b: float, k: int) -> np.ndarray:
+    """range(a, b, length=k+1), src/quadrature.jl:56 (twice-precision step: one rounding per element)."""
+    al, bl = np.longdouble(a), np.longdouble(b)
+    e = (al + np.arange(k + 1, dtype=np.longdouble) * ((bl - al) / np.longdouble(k))).astype(np.float64)
+    e[0], e[-1] = a, b
+    return e
+
+
+def _host_strengths(cfg: AdaptiveKernelConfig, eng, a: float, b: float, origin: bool):
+    """updatequadbufs! (src/quadrature.jl:49-95) on the host for an arbitrary callable S."""
+    m, k = cfg.quadspec
+    (ln1, lw1, ln2, lw2), (jn1, jw1, jn2, jw2) = _host_rules(cfg, eng)
+    p, f = cfg.p, cfg.f
+    if origin:
+        g = f
+        pw = lambda no: np.ones_like(no) if p == 0 else np.power(no, p)
+    else:                                                                        # quadrature.jl:240-247
+        lg = (lambda w: np.log(w)) if cfg.logw else (lambda w: 1.0)
+        g = lambda w: (np.ones_like(w) if p == 0 else np.power(w, p)) * lg(w) * f(w)
+        pw = lambda no: np.ones_like(no)
+    edges = _subpanel_edges(a, b, k)
+    out = []
+    for mm, ln, lw, jn, jw in ((m, ln1, lw1, jn1, jw1), (2 * m, ln2, lw2, jn2, jw2)):
+        no = np.empty(mm * k)
+        buf = np.empty(mm * k)
+        first = 0
+        if origin:                                                               # :61-78
+            bm, bp = (edges[1] - edges[0]) / 2, (edges[1] + edges[0]) / 2
+            no[:mm] = bm * jn + bp
+            buf[:mm] = jw * bm ** (p + 1) * g(no[:mm])
+            first = 1
+        for i in range(first, k):                                                # :82-92
+            bm, bp = (edges[i + 1] - edges[i]) / 2, (edges[i + 1] + edges[i]) / 2
+            sl = slice(i * mm, (i + 1) * mm)
+            no[sl] = bm * ln + bp
+            buf[sl] = lw * bm * pw(no[sl]) * g(no[sl])
+        out += [no, buf]
+    return out
+
+
+def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: float, k0: float, comm, active: bool,
+                               verbose: bool = False, trace: Optional[list] = None):
+    """Scalar control flow of src/quadrature.jl:169-275: LIFO bisection, accept test against
+    config.tol*k0 (not the split tolerance), 9:1 tolerance split at the origin.  The per-target work of
+    every pass happens inside sk_subinterval / sk_subinterval_accept."""
+    if cfg.dim != 1:
+        raise NotImplementedError("dim > 1 (Hankel kernel, src/quadrature.jl:137-161) is not built yet")
+    kernel = SK_KERNEL_SIN if cfg.derivative else SK_KERNEL_COS                  # :177
+    stack = [(a, b, cfg.tol)]                                                    # :173
+    builtin = is_builtin(cfg.f)
+    while stack:
+        _a, _b, _tol = stack.pop()                                               # :183
+        origin = (_a == 0.0 and cfg.p != 0.0)                                    # :185
+        if origin and cfg.logw:
+            raise NotImplementedError("log-weighted origin sub-interval (src/quadrature.jl:186-228)")
+        if abs(_b - _a) <= 1e-16:                                                # utils.jl:28-36
+            raise RuntimeError(f"The sub-interval (a, b) = ({_a}, {_b}) has been split too many times "
+                               f"(b - a < 1e-16). Exiting to avoid infinite splitting.")
+        if active:
+            if builtin:
+                mx = eng.subinterval(_a, _b, cfg.c, cfg.p, kernel, cfg.logw)
+            else:
+                no1, buf1, no2, buf2 = _host_strengths(cfg, eng, _a, _b, origin)
+                mx = eng.subinterval_host(_a, _b, no1, buf1, no2, buf2, cfg.c, cfg.p, kernel, cfg.logw)
+        else:
+            mx = 0.0
+        # max over all ranks; NaN travels as +inf (both fail the accept test, quadrature.jl:260)
+        mx_g = comm.max([math.inf if math.isnan(mx) else mx])[0]
+        accepted = mx_g < cfg.tol * k0                                           # :260
+        if verbose:
+            word = "converged" if mx_g / k0 <= _tol else "did not converge"
+            print(f"\tsubpanel w ∈ [{_a:.2e}, {_b:.2e}] {word} to tolerance {_tol:.2e} with max error {mx_g / k0:.2e}")
+        if trace is not None:
+            trace.append({"kind": "subinterval", "a": float(_a), "b": float(_b), "rel_err": float(mx_g / k0),
+                          "accepted": bool(accepted)})
+        if accepted:
+            if active:
+                eng.subinterval_accept()                                         # :261-262
+        else:                                                                    # :268-270
+            tl, tr = (9 * _tol / 10, _tol / 10) if _a == 0 else (_tol / 2, _tol / 2)
+            mid = (_a + _b) / 2
+            stack.append((_a, mid, tl))
+            stack.append((mid, _b, tr))
+
+
+def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, param_derivative: bool = False,
+                  verbose: bool = False, trace: Optional[list] = None, comm=None, want_errors: bool = True,
+                  out_vals=None, out_errs=None, xs_device: Optional[Tuple[int, int]] = None,
+                  out_device: Optional[Tuple[int, int]] = None):
+    """`kernel_values(config, xs; k0, param_derivative, verbose)` (src/adaptive.jl:95-108): returns
+    (values, errors) in the order of `xs`, duplicates included.
+
+    Optional extras: `trace` (list, receives the panel trace), `comm` (scalar reductions of a
+    target-sharded multi-GPU run: every rank passes its own chunk of the distances), `xs_device` /
+    `out_device` ((pointer, n) / (vals_ptr, errs_ptr): device-resident input and output, no PCIe)."""
+    eng = cfg.engine
+    comm = comm or _NoComm()
+    if k0 is None:
+        k0 = compute_k0(cfg)                                                     # :97
+    m, k = cfg.quadspec
+    eng.rule_set(m, k, cfg.p)
+    if is_builtin(cfg.f):
+        eng.sdf_builtin(cfg.f.family, cfg.f.params, cfg.f.deriv)
+    # unique + sort + inverse map on the device (adaptive.jl:99, :113-120)
+    if xs_device is not None:
+        info = eng.targets_set_device(*xs_device)
+        n_in = int(xs_device[1])
+    else:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n_in = xs.size
+        info = eng.targets_set(xs)
+    if verbose:
+        print(f"Reducing {info.n_in} to {info.n_unique} unique lags for evaluation...")
+    eng.run_begin()
+    n = int(info.n_unique)
+    ix1 = 1
+    if info.has_zero:                                                            # :133-146
+        ix1 = 2
+        if cfg.derivative:
+            eng.zero_lag_set(0.0)
+        elif param_derivative:
+            eng.zero_lag_set(compute_k0(cfg))
+        else:
+            eng.zero_lag_set(k0)
+    hi = n                                                                       # :123
+    quadm = cfg.quadsz
+    crit = cfg.convergence_criteria
+    a = b = 0.0
+    # global distance range over all ranks (scalars only)
+    r_hi_local = info.r_max if (n >= ix1) else 0.0
+    r_lo_g = comm.min([info.r_min_pos if info.r_min_pos > 0 else math.inf])[0]
+    r_hi_g = comm.max([r_hi_local])[0]
+    ipanel = 0
+    tau = cfg.tol * abs(k0) / 2                                                  # :191
+    while r_hi_g > 0:                                                            # :149 (hi > 0 && xs[hi] > 0)
+        a, b = b, b + quadm / (2 * r_hi_g)                                       # :152
+        active = hi >= ix1
+        if verbose:
+            print(f"\nintegrating panel w ∈ [{a:.2e}, {b:.2e}] (length {b - a:.2e}) to resolve {hi} points "
+                  f"x ≤ {r_hi_g:.2e} ")
+        if active:
+            eng.panel_begin(ix1, hi)
+            if comm.world_size > 1:
+                eng.panel_set_range(r_lo_g, r_hi_g)
+        fourier_integrate_interval(cfg, eng, a, b, abs(k0), comm, active, verbose=verbose, trace=trace)   # :157-159
+        if active:
+            eng.panel_commit()                                                   # :163-164
+        if crit == "panel":                                                      # :168
+            c = d = float("nan")
+        else:
+            c, d = estimate_tail_decay(cfg, a, b, d=cfg.tail)
+        if (math.isnan(c) or math.isnan(d)) and crit != "panel":                 # :170-175
+            if verbose:
+                print("\talgebraic tail estimate failed -- using convergence_criteria = :panel")
+            crit = "panel"
+        elif crit != "panel" and verbose:
+            print(f"\talgebraic tail estimate S(w) ≈ {c:.2e} * w^({d:.2f})")
+        sargs = _scan_args(cfg, b, c, d, tau, crit)
+        hi_before = hi
+        if active:
+            new_hi, r_stop = eng.converge_scan(sargs)                            # :183-198
+        else:
+            new_hi, r_stop = hi, 0.0
+        r_stop_g = comm.max([r_stop])[0]
+        if comm.world_size > 1 and active and r_stop_g > r_stop:
+            new_hi = eng.target_upper_index(r_stop_g)
+        if active:
+            eng.converge_apply(sargs, new_hi)                                    # :194
+        hi = new_hi
+        r_hi_g = r_stop_g
+        if trace is not None:
+            trace.append({"kind": "panel", "index": ipanel, "a": float(a), "b": float(b), "hi_before": int(hi_before),
+                          "hi_after": int(hi), "ix1": int(ix1), "c": float(c), "d": float(d), "criteria": crit})
+        ipanel += 1
+    if out_device is not None:
+        eng.results_get_device(*out_device)
+        return None, None
+    return eng.results_get(n_in, want_errors=want_errors, out_vals=out_vals, out_errs=out_errs)   # :105-107

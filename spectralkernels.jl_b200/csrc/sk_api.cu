@@ -1,0 +1,851 @@
+// sk_api.cu -- the C ABI (include/spectralkernels_b200.h) over the sm_100a kernels.
+//
+// One sk_ctx owns one CUDA stream, the exp-of-semicircle plan, the quadrature rules, the sorted
+// unique targets and every O(N) work array of the adaptive loop.  Only scalars cross the ABI per
+// sub-interval (a, b in; max|I2-I1| out) and per outer panel (new highest unconverged index out).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cufft.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/spectralkernels_b200.h"
+#include "sk_host_util.h"
+#include "sk_kernels.cuh"
+
+namespace {
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct HostScalars {          // pinned mirror of SkReduceOut plus two doubles
+  SkReduceOut red;
+  double r[2];
+};
+
+}  // namespace
+
+struct sk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string errmsg;
+  double eps = 1e-15;
+  SkEsPlan plan;
+  std::map<std::pair<long long, int>, cufftHandle> fft_plans;
+
+  // rules
+  int m = 0, k = 0;
+  double p = 0.0;
+  bool have_rule = false, have_jac = false;
+  DevBuf<double> leg_no1, leg_wt1, leg_no2, leg_wt2, jac_no1, jac_wt1, jac_no2, jac_wt2;
+  std::vector<double> h_rule[8];
+
+  // integrand
+  int family = SK_SDF_HOST, deriv = 0, nparam = 0;
+  double params[SK_NPARAM_MAX] = {0};
+
+  // sources of the current sub-interval
+  DevBuf<double> no1, buf1, no2, buf2, pos_hi1, pos_lo1, pos_hi2, pos_lo2, imz;
+  DevBuf<sk_cplx> cs1, cs2, fft, dsum;
+  bool have_sources = false;
+
+  // targets
+  long long n_in = 0, n_unique = 0;
+  bool has_zero = false;
+  DevBuf<double> in, uxs, ks, errs, I, err, stage_i, stage_e, out_v, out_e;
+  DevBuf<unsigned long long> keys, keys_alt;
+  DevBuf<unsigned int> idx, idx_alt, head, uid, inv;
+  DevBuf<unsigned char> cub_tmp;
+  DevBuf<unsigned int> badflag;
+  bool have_targets = false;
+
+  // panel state (0-based half-open [lo, hi))
+  long long lo = 0, hi = 0;
+  double r_lo = 0, r_hi = 0;
+  bool in_panel = false, staged = false, first_accept = true;
+
+  SkReduceOut *d_red = nullptr;
+  HostScalars *h_scal = nullptr;  // pinned
+
+  // stats / timing
+  sk_stats stats;
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+int fail(sk_ctx *c, int code, const char *fmt, ...) {
+  if (c) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    c->errmsg = buf;
+  }
+  return code;
+}
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(c, e_ == cudaErrorMemoryAllocation ? SK_ERR_ALLOC : SK_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                        \
+  } while (0)
+
+#define LAUNCH_CHECK()                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                                        \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(c, SK_ERR_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    c->stats.kernel_launches++;                                                                 \
+  } while (0)
+
+inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
+
+int width_from_eps(double eps) {
+  int w = (int)std::ceil(-std::log10(eps / 10.0));
+  if (w & 1) ++w;
+  if (w < 4) w = 4;
+  if (w > SK_WMAX) w = SK_WMAX;
+  return w;
+}
+
+int get_fft_plan(sk_ctx *c, long long nf2, int batch, cufftHandle *out) {
+  auto key = std::make_pair(nf2, batch);
+  auto it = c->fft_plans.find(key);
+  if (it != c->fft_plans.end()) {
+    *out = it->second;
+    return SK_OK;
+  }
+  cufftHandle h;
+  int n[1] = {(int)nf2};
+  int embed[1] = {(int)nf2};
+  // interleaved batch: element l of transform r lives at [l*batch + r]
+  cufftResult r = cufftPlanMany(&h, 1, n, embed, batch, 1, embed, batch, 1, CUFFT_Z2Z, batch);
+  if (r != CUFFT_SUCCESS) return fail(c, SK_ERR_CUFFT, "cufftPlanMany(n=%lld, batch=%d) failed: %d", nf2, batch, (int)r);
+  r = cufftSetStream(h, c->stream);
+  if (r != CUFFT_SUCCESS) return fail(c, SK_ERR_CUFFT, "cufftSetStream failed: %d", (int)r);
+  c->fft_plans[key] = h;
+  *out = h;
+  return SK_OK;
+}
+
+template <int W>
+void launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long long n, double cmul, int ksin) {
+  k_interp_session<W><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage_i.p + c->lo,
+                                                           c->stage_e.p + c->lo, c->d_red);
+}
+template <int W>
+void launch_interp_cplx(sk_ctx *c, const SkGeom &G, const double *x, long long n, sk_cplx *out) {
+  k_interp_cplx<W><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, x, n, c->fft.p, out);
+}
+
+#define DISPATCH_W(w, CALL)                \
+  switch (w) {                             \
+    case 4: CALL(4); break;                \
+    case 6: CALL(6); break;                \
+    case 8: CALL(8); break;                \
+    case 10: CALL(10); break;              \
+    case 12: CALL(12); break;              \
+    case 14: CALL(14); break;              \
+    default: CALL(16); break;              \
+  }
+
+// Source side of one transform pair: prep + spread/deconvolve/pad + FFT.  nrule = 1 or 2.
+int run_source_side(sk_ctx *c, const SkGeom &G, int nrule, long long M1, const double *im1, long long M2) {
+  const size_t need = (size_t)G.nf2 * nrule;
+  CK(c->fft.ensure(need));
+  CK(c->pos_hi1.ensure(M1));
+  CK(c->pos_lo1.ensure(M1));
+  CK(c->cs1.ensure(M1));
+  k_prep_sources<<<nblk(M1, 256), 256, 0, c->stream>>>(G, M1, c->no1.p, c->buf1.p, im1, c->pos_hi1.p, c->pos_lo1.p, c->cs1.p);
+  LAUNCH_CHECK();
+  SkSpreadSrc src;
+  std::memset(&src, 0, sizeof(src));
+  src.pos_hi[0] = c->pos_hi1.p; src.pos_lo[0] = c->pos_lo1.p; src.cs[0] = c->cs1.p; src.M[0] = M1;
+  if (nrule == 2) {
+    CK(c->pos_hi2.ensure(M2));
+    CK(c->pos_lo2.ensure(M2));
+    CK(c->cs2.ensure(M2));
+    k_prep_sources<<<nblk(M2, 256), 256, 0, c->stream>>>(G, M2, c->no2.p, c->buf2.p, nullptr, c->pos_hi2.p, c->pos_lo2.p, c->cs2.p);
+    LAUNCH_CHECK();
+    src.pos_hi[1] = c->pos_hi2.p; src.pos_lo[1] = c->pos_lo2.p; src.cs[1] = c->cs2.p; src.M[1] = M2;
+  }
+  dim3 grid(nblk(G.nf2, 128), nrule);
+  k_spread_modes<<<grid, 128, 0, c->stream>>>(c->plan, G, src, nrule, c->fft.p);
+  LAUNCH_CHECK();
+  cufftHandle h;
+  int rc = get_fft_plan(c, G.nf2, nrule, &h);
+  if (rc != SK_OK) return rc;
+  cufftResult fr = cufftExecZ2Z(h, (cufftDoubleComplex *)c->fft.p, (cufftDoubleComplex *)c->fft.p, CUFFT_INVERSE);
+  if (fr != CUFFT_SUCCESS) return fail(c, SK_ERR_CUFFT, "cufftExecZ2Z failed: %d", (int)fr);
+  c->stats.kernel_launches++;
+  c->stats.last_nf = G.nf;
+  c->stats.last_nf2 = G.nf2;
+  return SK_OK;
+}
+
+// transform + stage for the sub-interval whose sources are in no1/buf1/no2/buf2
+int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, double *max_abs_diff) {
+  const long long n_act = c->hi - c->lo;
+  const long long M1 = (long long)c->m * c->k, M2 = 2 * M1;
+  const int ksin = o->kernel == SK_KERNEL_SIN;
+  CK(cudaMemsetAsync(c->d_red, 0, sizeof(SkReduceOut), c->stream));
+  // fast = nufft_quad_size_cutoff(length(no2), length(xs)) && length(xs) > 1   (src/quadrature.jl:105, src/utils.jl:39)
+  const bool fast = (M2 * n_act > (1LL << 18)) && n_act > 1;
+  if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+  if (fast) {
+    SkGeom G;
+    if (sk_make_geom(c->plan, a, b, c->r_lo, c->r_hi, &G) != 0)
+      return fail(c, SK_ERR_ARG, "type-3 grid too large for [a,b]=[%g,%g], r in [%g,%g]", a, b, c->r_lo, c->r_hi);
+    int rc = run_source_side(c, G, 2, M1, nullptr, M2);
+    if (rc != SK_OK) return rc;
+    if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
+#define CALL(WW) launch_interp_session<WW>(c, G, c->uxs.p + c->lo, n_act, o->cmul, ksin)
+    DISPATCH_W(c->plan.w, CALL)
+#undef CALL
+    LAUNCH_CHECK();
+    if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
+    c->stats.n_fast++;
+  } else {
+    CK(c->dsum.ensure((size_t)n_act * 2));
+    dim3 grid((unsigned int)n_act, 2);
+    k_direct<<<grid, 256, 0, c->stream>>>(c->no1.p, c->buf1.p, M1, c->no2.p, c->buf2.p, M2, c->uxs.p + c->lo, c->dsum.p);
+    LAUNCH_CHECK();
+    k_direct_finish<<<1, 256, 0, c->stream>>>(c->dsum.p, n_act, o->cmul, ksin, c->stage_i.p + c->lo, c->stage_e.p + c->lo, c->d_red);
+    LAUNCH_CHECK();
+    c->stats.n_direct++;
+  }
+  CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->timing && fast) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->stats.source_ms += ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+    c->stats.interp_ms += ms;
+  }
+  const unsigned int fl = c->h_scal->red.flags;
+  double mx;
+  std::memcpy(&mx, &c->h_scal->red.maxbits, sizeof(double));
+  if (fl & SK_FLAG_NAND) mx = std::nan("");
+  *max_abs_diff = mx;
+  c->staged = true;
+  c->stats.n_subintervals++;
+  c->stats.units += n_act;
+  // any(isnan, int1) || any(isnan, int2) && throw(...)   (src/quadrature.jl:165)
+  if (!(fl & SK_FLAG_NAN1) && (fl & SK_FLAG_NAN2)) return fail(c, SK_ERR_NAN, "NaN detected in panel integral...");
+  return SK_OK;
+}
+
+int upload_rule(sk_ctx *c, DevBuf<double> &dst, const double *src, int n) {
+  CK(dst.ensure(n));
+  CK(cudaMemcpyAsync(dst.p, src, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  return SK_OK;
+}
+
+int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info) {
+  // c->in holds the n_in raw distances
+  c->have_targets = false;
+  if (n_in > 0xfffffff0LL) return fail(c, SK_ERR_ARG, "n_in too large");
+  CK(c->keys.ensure(n_in));
+  CK(c->keys_alt.ensure(n_in));
+  CK(c->idx.ensure(n_in));
+  CK(c->idx_alt.ensure(n_in));
+  CK(c->head.ensure(n_in));
+  CK(c->uid.ensure(n_in));
+  CK(c->inv.ensure(n_in));
+  CK(c->badflag.ensure(1));
+  CK(cudaMemsetAsync(c->badflag.p, 0, sizeof(unsigned int), c->stream));
+  k_make_keys<<<nblk(n_in, 256), 256, 0, c->stream>>>(c->in.p, n_in, c->keys.p, c->idx.p, c->badflag.p);
+  LAUNCH_CHECK();
+  cub::DoubleBuffer<unsigned long long> dk(c->keys.p, c->keys_alt.p);
+  cub::DoubleBuffer<unsigned int> dv(c->idx.p, c->idx_alt.p);
+  size_t tmp_bytes = 0, tmp2 = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n_in, 0, 64, c->stream));
+  CK(cub::DeviceScan::InclusiveSum(nullptr, tmp2, c->head.p, c->uid.p, (int)n_in, c->stream));
+  CK(c->cub_tmp.ensure(std::max(tmp_bytes, tmp2)));
+  tmp_bytes = tmp2 = c->cub_tmp.cap;
+  // positive doubles below 2^63: the top bit is always clear, sort the low 63 bits
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, 0, 63, c->stream));
+  c->stats.kernel_launches += 8;
+  const unsigned long long *skeys = dk.Current();
+  const unsigned int *sidx = dv.Current();
+  k_flag_heads<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, n_in, c->head.p);
+  LAUNCH_CHECK();
+  CK(cub::DeviceScan::InclusiveSum(c->cub_tmp.p, tmp2, c->head.p, c->uid.p, (int)n_in, c->stream));
+  c->stats.kernel_launches += 2;
+  unsigned int h_last = 0, h_bad = 0;
+  CK(cudaMemcpyAsync(&c->h_scal->red.flags, c->uid.p + (n_in - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&c->h_scal->red._pad, c->badflag.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  h_last = c->h_scal->red.flags;
+  h_bad = c->h_scal->red._pad;
+  if (h_bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
+  const long long nu = h_last;
+  CK(c->uxs.ensure(nu));
+  k_scatter_unique<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, sidx, c->head.p, c->uid.p, n_in, c->uxs.p, c->inv.p);
+  LAUNCH_CHECK();
+  CK(c->ks.ensure(nu));
+  CK(c->errs.ensure(nu));
+  CK(c->I.ensure(nu));
+  CK(c->err.ensure(nu));
+  CK(c->stage_i.ensure(nu));
+  CK(c->stage_e.ensure(nu));
+  // smallest / second smallest / largest unique distance
+  double h3[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(&c->h_scal->r[0], c->uxs.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&c->h_scal->r[1], c->uxs.p + (nu - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  h3[0] = c->h_scal->r[0];
+  h3[2] = c->h_scal->r[1];
+  c->n_in = n_in;
+  c->n_unique = nu;
+  c->has_zero = (h3[0] == 0.0);
+  double rminpos = h3[0];
+  if (c->has_zero) {
+    rminpos = 0.0;
+    if (nu > 1) {
+      CK(cudaMemcpyAsync(&c->h_scal->r[0], c->uxs.p + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      rminpos = c->h_scal->r[0];
+    }
+  }
+  c->have_targets = true;
+  c->in_panel = false;
+  c->staged = false;
+  if (info) {
+    info->n_in = n_in;
+    info->n_unique = nu;
+    info->has_zero = c->has_zero ? 1 : 0;
+    info->_pad = 0;
+    info->r_min_pos = rminpos;
+    info->r_max = h3[2];
+  }
+  return SK_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int sk_abi_version(void) { return SK_ABI_VERSION; }
+
+const char *sk_error_string(int code) {
+  switch (code) {
+    case SK_OK: return "ok";
+    case SK_ERR_CUDA: return "CUDA runtime error";
+    case SK_ERR_ARG: return "invalid argument";
+    case SK_ERR_STATE: return "invalid call sequence";
+    case SK_ERR_NAN: return "NaN detected in panel integral...";
+    case SK_ERR_SPLIT: return "sub-interval split too many times (b - a < 1e-16)";
+    case SK_ERR_ALLOC: return "out of memory";
+    case SK_ERR_CUFFT: return "cuFFT error";
+    case SK_ERR_UNSUPPORTED: return "unsupported reference branch";
+    case SK_ERR_INPUT: return "invalid distances";
+    default: return "unknown error";
+  }
+}
+
+const char *sk_last_error(const sk_ctx *ctx) { return ctx ? ctx->errmsg.c_str() : "null context"; }
+
+int sk_ctx_create(int device, sk_ctx **out) {
+  if (!out) return SK_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SK_ERR_CUDA;  // no CPU fallback: fail loudly
+  if (device < 0 || device >= ndev) return SK_ERR_ARG;
+  sk_ctx *c = new sk_ctx();
+  c->device = device;
+  std::memset(&c->stats, 0, sizeof(c->stats));
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc((void **)&c->d_red, sizeof(SkReduceOut)) != cudaSuccess ||
+      cudaMallocHost((void **)&c->h_scal, sizeof(HostScalars)) != cudaSuccess) {
+    delete c;
+    return SK_ERR_CUDA;
+  }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
+  if (sk_plan_make_es(width_from_eps(c->eps), &c->plan) != 0) {
+    delete c;
+    return SK_ERR_ARG;
+  }
+  *out = c;
+  return SK_OK;
+}
+
+int sk_ctx_destroy(sk_ctx *c) {
+  if (!c) return SK_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto &kv : c->fft_plans) cufftDestroy(kv.second);
+  DevBuf<double> *dbl[] = {&c->leg_no1, &c->leg_wt1, &c->leg_no2, &c->leg_wt2, &c->jac_no1, &c->jac_wt1, &c->jac_no2,
+                           &c->jac_wt2, &c->no1, &c->buf1, &c->no2, &c->buf2, &c->pos_hi1, &c->pos_lo1, &c->pos_hi2,
+                           &c->pos_lo2, &c->imz, &c->in, &c->uxs, &c->ks, &c->errs, &c->I, &c->err, &c->stage_i,
+                           &c->stage_e, &c->out_v, &c->out_e};
+  for (auto *b : dbl) b->release();
+  c->cs1.release(); c->cs2.release(); c->fft.release(); c->dsum.release();
+  c->keys.release(); c->keys_alt.release(); c->idx.release(); c->idx_alt.release();
+  c->head.release(); c->uid.release(); c->inv.release(); c->cub_tmp.release(); c->badflag.release();
+  if (c->d_red) cudaFree(c->d_red);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return SK_OK;
+}
+
+int sk_ctx_set_timing(sk_ctx *c, int enabled) {
+  if (!c) return SK_ERR_ARG;
+  c->timing = enabled != 0;
+  c->stats.timing_enabled = enabled != 0;
+  return SK_OK;
+}
+
+int sk_ctx_set_nufft_eps(sk_ctx *c, double eps) {
+  if (!c || !(eps > 0) || !(eps < 1)) return fail(c, SK_ERR_ARG, "eps must be in (0,1)");
+  c->eps = eps;
+  if (sk_plan_make_es(width_from_eps(eps), &c->plan) != 0) return fail(c, SK_ERR_ARG, "cannot plan for eps=%g", eps);
+  return SK_OK;
+}
+
+int sk_ctx_synchronize(sk_ctx *c) {
+  if (!c) return SK_ERR_ARG;
+  CK(cudaStreamSynchronize(c->stream));
+  return SK_OK;
+}
+
+int sk_ctx_stream(sk_ctx *c, void **stream_out) {
+  if (!c || !stream_out) return SK_ERR_ARG;
+  *stream_out = (void *)c->stream;
+  return SK_OK;
+}
+
+int sk_host_alloc(size_t bytes, void **out) {
+  if (!out) return SK_ERR_ARG;
+  return cudaMallocHost(out, bytes) == cudaSuccess ? SK_OK : SK_ERR_ALLOC;
+}
+int sk_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? SK_OK : SK_ERR_CUDA; }
+
+// ---- Level 0 ------------------------------------------------------------------------------------------
+int sk_nufft1d3(sk_ctx *c, int64_t M, const double *w, const double *s, int64_t N, const double *x, double *out,
+                double eps) {
+  if (!c || M < 0 || N < 0 || (M > 0 && (!w || !s)) || (N > 0 && (!x || !out))) return fail(c, SK_ERR_ARG, "bad pointers/sizes");
+  if (N == 0) return SK_OK;
+  if (M == 0) { std::memset(out, 0, sizeof(double) * 2 * N); return SK_OK; }
+  CK(cudaSetDevice(c->device));
+  SkEsPlan saved = c->plan;
+  if (eps > 0 && eps != c->eps && sk_plan_make_es(width_from_eps(eps), &c->plan) != 0) return fail(c, SK_ERR_ARG, "bad eps");
+  // the gather spread needs ascending sources
+  std::vector<long long> perm(M);
+  std::iota(perm.begin(), perm.end(), 0LL);
+  if (!std::is_sorted(w, w + M)) std::sort(perm.begin(), perm.end(), [&](long long a, long long b) { return w[a] < w[b]; });
+  std::vector<double> hw(M), hre(M), him(M);
+  for (long long i = 0; i < M; ++i) { hw[i] = w[perm[i]]; hre[i] = s[2 * perm[i]]; him[i] = s[2 * perm[i] + 1]; }
+  double xmin = x[0], xmax = x[0];
+  for (long long j = 1; j < N; ++j) { xmin = std::min(xmin, x[j]); xmax = std::max(xmax, x[j]); }
+  SkGeom G;
+  int rc = SK_OK;
+  if (sk_make_geom(c->plan, hw.front(), hw.back(), xmin, xmax, &G) != 0) rc = fail(c, SK_ERR_ARG, "type-3 grid too large");
+  auto body = [&]() -> int {
+    CK(c->no1.ensure(M)); CK(c->buf1.ensure(M)); CK(c->imz.ensure(M));
+    CK(c->in.ensure(N)); CK(c->dsum.ensure(N));
+    CK(cudaMemcpyAsync(c->no1.p, hw.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->buf1.p, hre.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->imz.p, him.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->in.p, x, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
+    int r2 = run_source_side(c, G, 1, M, c->imz.p, 0);
+    if (r2 != SK_OK) return r2;
+#define CALL(WW) launch_interp_cplx<WW>(c, G, c->in.p, N, c->dsum.p)
+    DISPATCH_W(c->plan.w, CALL)
+#undef CALL
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(out, c->dsum.p, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SK_OK;
+  };
+  if (rc == SK_OK) rc = body();
+  c->plan = saved;
+  c->have_sources = false;
+  c->have_targets = false;  // the target buffer was reused
+  return rc;
+}
+
+// ---- rules ------------------------------------------------------------------------------------------------
+int sk_rule_set(sk_ctx *c, int32_t m, int32_t k, double p, const double *leg_no1, const double *leg_wt1,
+                const double *leg_no2, const double *leg_wt2, const double *jac_no1, const double *jac_wt1,
+                const double *jac_no2, const double *jac_wt2) {
+  if (!c || m < 1 || k < 1) return fail(c, SK_ERR_ARG, "quadspec must be positive");
+  if (k > SK_KMAX) return fail(c, SK_ERR_UNSUPPORTED, "k = %d sub-panels > %d", k, SK_KMAX);
+  if (p != 0.0 && !(p > -1.0)) return fail(c, SK_ERR_ARG, "p needs to be in (-1.0, Inf) to be integrable");  // quadrature.jl:40
+  CK(cudaSetDevice(c->device));
+  const bool given_leg = leg_no1 && leg_wt1 && leg_no2 && leg_wt2;
+  const bool given_jac = jac_no1 && jac_wt1 && jac_no2 && jac_wt2;
+  const int sizes[8] = {m, m, 2 * m, 2 * m, m, m, 2 * m, 2 * m};
+  for (int i = 0; i < 8; ++i) c->h_rule[i].assign(sizes[i], 0.0);
+  if (given_leg) {
+    const double *src[4] = {leg_no1, leg_wt1, leg_no2, leg_wt2};
+    for (int i = 0; i < 4; ++i) std::copy(src[i], src[i] + sizes[i], c->h_rule[i].begin());
+  } else {
+    if (sk_plan_gauss_rule(m, 0.0, c->h_rule[0].data(), c->h_rule[1].data()) != 0 ||
+        sk_plan_gauss_rule(2 * m, 0.0, c->h_rule[2].data(), c->h_rule[3].data()) != 0)
+      return fail(c, SK_ERR_ARG, "Gauss-Legendre generation failed for m=%d", m);
+  }
+  c->have_jac = (p != 0.0);
+  if (c->have_jac) {
+    if (given_jac) {
+      const double *src[4] = {jac_no1, jac_wt1, jac_no2, jac_wt2};
+      for (int i = 0; i < 4; ++i) std::copy(src[i], src[i] + sizes[4 + i], c->h_rule[4 + i].begin());
+    } else {
+      if (sk_plan_gauss_rule(m, p, c->h_rule[4].data(), c->h_rule[5].data()) != 0 ||
+          sk_plan_gauss_rule(2 * m, p, c->h_rule[6].data(), c->h_rule[7].data()) != 0)
+        return fail(c, SK_ERR_ARG, "Gauss-Jacobi generation failed for m=%d p=%g", m, p);
+    }
+  } else {
+    for (int i = 0; i < 4; ++i) c->h_rule[4 + i] = c->h_rule[i];  // jacrule = legrule, src/adaptive.jl:49
+  }
+  DevBuf<double> *dst[8] = {&c->leg_no1, &c->leg_wt1, &c->leg_no2, &c->leg_wt2, &c->jac_no1, &c->jac_wt1, &c->jac_no2, &c->jac_wt2};
+  for (int i = 0; i < 8; ++i) {
+    int rc = upload_rule(c, *dst[i], c->h_rule[i].data(), sizes[i]);
+    if (rc != SK_OK) return rc;
+  }
+  const long long M1 = (long long)m * k;
+  CK(c->no1.ensure(M1)); CK(c->buf1.ensure(M1)); CK(c->no2.ensure(2 * M1)); CK(c->buf2.ensure(2 * M1));
+  CK(cudaStreamSynchronize(c->stream));
+  c->m = m; c->k = k; c->p = p;
+  c->have_rule = true;
+  return SK_OK;
+}
+
+int sk_rule_get(sk_ctx *c, int32_t which, double *no, double *wt) {
+  if (!c || which < 0 || which > 3 || !no || !wt) return fail(c, SK_ERR_ARG, "bad arguments");
+  if (!c->have_rule) return fail(c, SK_ERR_STATE, "no rule set");
+  const std::vector<double> &a = c->h_rule[2 * which], &b = c->h_rule[2 * which + 1];
+  std::copy(a.begin(), a.end(), no);
+  std::copy(b.begin(), b.end(), wt);
+  return SK_OK;
+}
+
+int sk_sdf_builtin(sk_ctx *c, int32_t family, const double *params, int32_t nparams, int32_t deriv_index) {
+  if (!c) return SK_ERR_ARG;
+  int want = family == SK_SDF_MATERN ? 4 : family == SK_SDF_EXPONENTIAL ? 2 : family == SK_SDF_HOST ? 0 : -1;
+  if (want < 0) return fail(c, SK_ERR_ARG, "unknown family %d", family);
+  if (nparams != want || (want > 0 && !params)) return fail(c, SK_ERR_ARG, "family %d takes %d parameters", family, want);
+  if (deriv_index < 0 || deriv_index > want - (family == SK_SDF_MATERN ? 1 : 0)) return fail(c, SK_ERR_ARG, "bad deriv_index");
+  c->family = family;
+  c->nparam = nparams;
+  c->deriv = deriv_index;
+  for (int i = 0; i < nparams; ++i) c->params[i] = params[i];
+  return SK_OK;
+}
+
+// ---- targets -------------------------------------------------------------------------------------------
+int sk_targets_set(sk_ctx *c, const double *xs_host, int64_t n_in, sk_target_info *info) {
+  if (!c || !xs_host || n_in < 1) return fail(c, SK_ERR_ARG, "need at least one distance");
+  CK(cudaSetDevice(c->device));
+  CK(c->in.ensure(n_in));
+  CK(cudaMemcpyAsync(c->in.p, xs_host, sizeof(double) * n_in, cudaMemcpyHostToDevice, c->stream));
+  return targets_from_device_buffer(c, n_in, info);
+}
+
+int sk_targets_set_device(sk_ctx *c, const double *xs_dev, int64_t n_in, sk_target_info *info) {
+  if (!c || !xs_dev || n_in < 1) return fail(c, SK_ERR_ARG, "need at least one distance");
+  CK(cudaSetDevice(c->device));
+  CK(c->in.ensure(n_in));
+  CK(cudaMemcpyAsync(c->in.p, xs_dev, sizeof(double) * n_in, cudaMemcpyDeviceToDevice, c->stream));
+  return targets_from_device_buffer(c, n_in, info);
+}
+
+int sk_target_value(sk_ctx *c, int64_t idx, double *out) {
+  if (!c || !out) return SK_ERR_ARG;
+  if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
+  if (idx < 1 || idx > c->n_unique) return fail(c, SK_ERR_ARG, "index out of range");
+  CK(cudaMemcpyAsync(&c->h_scal->r[0], c->uxs.p + (idx - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *out = c->h_scal->r[0];
+  return SK_OK;
+}
+
+// ---- adaptive loop steps -----------------------------------------------------------------------------------
+int sk_run_begin(sk_ctx *c) {
+  if (!c) return SK_ERR_ARG;
+  if (!c->have_targets) return fail(c, SK_ERR_STATE, "sk_targets_set first");
+  CK(cudaSetDevice(c->device));
+  const bool t = c->timing;
+  std::memset(&c->stats, 0, sizeof(c->stats));
+  c->stats.timing_enabled = t;
+  CK(cudaMemsetAsync(c->ks.p, 0, sizeof(double) * c->n_unique, c->stream));     // zeros, src/adaptive.jl:122
+  CK(cudaMemsetAsync(c->errs.p, 0, sizeof(double) * c->n_unique, c->stream));
+  c->in_panel = false;
+  c->staged = false;
+  return SK_OK;
+}
+
+int sk_zero_lag_set(sk_ctx *c, double value) {
+  if (!c) return SK_ERR_ARG;
+  if (!c->have_targets) return fail(c, SK_ERR_STATE, "sk_targets_set first");
+  if (!c->has_zero) return SK_OK;
+  k_fill<<<1, 32, 0, c->stream>>>(c->ks.p, 1, value);
+  LAUNCH_CHECK();
+  k_fill<<<1, 32, 0, c->stream>>>(c->errs.p, 1, std::nan(""));
+  LAUNCH_CHECK();
+  return SK_OK;
+}
+
+int sk_panel_begin(sk_ctx *c, int64_t ix1, int64_t hi, double *r_lo, double *r_hi) {
+  if (!c) return SK_ERR_ARG;
+  if (!c->have_targets) return fail(c, SK_ERR_STATE, "sk_targets_set first");
+  if (ix1 < 1 || hi < ix1 || hi > c->n_unique) return fail(c, SK_ERR_ARG, "bad index range [%lld,%lld]", (long long)ix1, (long long)hi);
+  CK(cudaSetDevice(c->device));
+  c->lo = ix1 - 1;
+  c->hi = hi;
+  CK(cudaMemcpyAsync(&c->h_scal->r[0], c->uxs.p + c->lo, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&c->h_scal->r[1], c->uxs.p + (c->hi - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->r_lo = c->h_scal->r[0];
+  c->r_hi = c->h_scal->r[1];
+  if (r_lo) *r_lo = c->r_lo;
+  if (r_hi) *r_hi = c->r_hi;
+  c->in_panel = true;
+  c->staged = false;
+  c->first_accept = true;
+  return SK_OK;
+}
+
+int sk_panel_set_range(sk_ctx *c, double r_lo, double r_hi) {
+  if (!c) return SK_ERR_ARG;
+  if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
+  if (!(r_lo <= c->r_lo) || !(r_hi >= c->r_hi)) return fail(c, SK_ERR_ARG, "range must contain the panel's targets");
+  c->r_lo = r_lo;
+  c->r_hi = r_hi;
+  return SK_OK;
+}
+
+static int subinterval_prologue(sk_ctx *c, double a, double b, const sk_subinterval_opts *o) {
+  if (!c || !o) return SK_ERR_ARG;
+  if (!c->have_rule) return fail(c, SK_ERR_STATE, "sk_rule_set first");
+  if (!c->in_panel) return fail(c, SK_ERR_STATE, "sk_panel_begin first");
+  if (o->kernel != SK_KERNEL_COS && o->kernel != SK_KERNEL_SIN) return fail(c, SK_ERR_UNSUPPORTED, "kernel %d", o->kernel);
+  // check_subdivide_failure, src/utils.jl:28-36
+  if (!(std::fabs(b - a) > 1e-16))
+    return fail(c, SK_ERR_SPLIT,
+                "The sub-interval (a, b) = (%.17g, %.17g) has been split too many times (b - a < 1e-16). "
+                "Exiting to avoid infinite splitting.", a, b);
+  CK(cudaSetDevice(c->device));
+  return SK_OK;
+}
+
+int sk_subinterval(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, double *max_abs_diff) {
+  int rc = subinterval_prologue(c, a, b, o);
+  if (rc != SK_OK) return rc;
+  if (!max_abs_diff) return fail(c, SK_ERR_ARG, "null output");
+  if (c->family == SK_SDF_HOST) return fail(c, SK_ERR_STATE, "no built-in spectral density set: use sk_subinterval_host");
+  if (o->p != c->p) return fail(c, SK_ERR_ARG, "opts.p (%g) differs from the rule's p (%g)", o->p, c->p);
+  const bool origin = (a == 0.0 && c->p != 0.0);                    // src/quadrature.jl:185
+  if (origin && o->logw) return fail(c, SK_ERR_UNSUPPORTED, "log-weighted origin sub-interval (src/quadrature.jl:186-228)");
+  SkPanelSpec S;
+  std::memset(&S, 0, sizeof(S));
+  S.m = c->m; S.k = c->k;
+  S.origin_jacobi = origin ? 1 : 0;
+  S.weight_in_f = origin ? 0 : 1;                                   // :230-238 vs :240-247
+  S.logw = o->logw ? 1 : 0;
+  S.family = c->family; S.deriv = c->deriv; S.nparam = c->nparam;
+  S.p = c->p;
+  for (int i = 0; i < c->nparam; ++i) S.params[i] = c->params[i];
+  sk_fill_subpanels(a, b, c->k, S.bmad2, S.bpad2);
+  S.jac_scale = std::pow(S.bmad2[0], c->p + 1);
+  const long long M1 = (long long)c->m * c->k;
+  if (c->timing) CK(cudaEventRecord(c->ev[3], c->stream));
+  k_gen_sources<<<nblk(3 * M1, 256), 256, 0, c->stream>>>(S, c->leg_no1.p, c->leg_wt1.p, c->leg_no2.p, c->leg_wt2.p,
+                                                          c->jac_no1.p, c->jac_wt1.p, c->jac_no2.p, c->jac_wt2.p,
+                                                          c->no1.p, c->buf1.p, c->no2.p, c->buf2.p);
+  LAUNCH_CHECK();
+  c->have_sources = true;
+  return transform_and_stage(c, a, b, o, max_abs_diff);
+}
+
+int sk_subinterval_host(sk_ctx *c, double a, double b, const double *no1, const double *buf1, const double *no2,
+                        const double *buf2, const sk_subinterval_opts *o, double *max_abs_diff) {
+  int rc = subinterval_prologue(c, a, b, o);
+  if (rc != SK_OK) return rc;
+  if (!no1 || !buf1 || !no2 || !buf2 || !max_abs_diff) return fail(c, SK_ERR_ARG, "null pointer");
+  const long long M1 = (long long)c->m * c->k;
+  CK(cudaMemcpyAsync(c->no1.p, no1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->buf1.p, buf1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->no2.p, no2, sizeof(double) * 2 * M1, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->buf2.p, buf2, sizeof(double) * 2 * M1, cudaMemcpyHostToDevice, c->stream));
+  c->have_sources = true;
+  return transform_and_stage(c, a, b, o, max_abs_diff);
+}
+
+int sk_sources_get(sk_ctx *c, int32_t rule, double *no, double *buf) {
+  if (!c || !no || !buf || rule < 0 || rule > 1) return SK_ERR_ARG;
+  if (!c->have_sources) return fail(c, SK_ERR_STATE, "no sub-interval evaluated yet");
+  const long long M = (long long)c->m * c->k * (rule ? 2 : 1);
+  CK(cudaMemcpyAsync(no, rule ? c->no2.p : c->no1.p, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(buf, rule ? c->buf2.p : c->buf1.p, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return SK_OK;
+}
+
+int sk_subinterval_accept(sk_ctx *c) {
+  if (!c) return SK_ERR_ARG;
+  if (!c->staged) return fail(c, SK_ERR_STATE, "no staged sub-interval");
+  const long long n = c->hi - c->lo;
+  k_accept<<<nblk(n, 256), 256, 0, c->stream>>>(c->I.p + c->lo, c->err.p + c->lo, c->stage_i.p + c->lo, c->stage_e.p + c->lo, n,
+                                                c->first_accept ? 1 : 0);
+  LAUNCH_CHECK();
+  c->first_accept = false;
+  c->staged = false;
+  c->stats.n_accepted++;
+  return SK_OK;
+}
+
+int sk_panel_commit(sk_ctx *c) {
+  if (!c) return SK_ERR_ARG;
+  if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
+  const long long n = c->hi - c->lo;
+  if (c->first_accept) {  // nothing was accepted: I = err = 0
+    CK(cudaMemsetAsync(c->I.p + c->lo, 0, sizeof(double) * n, c->stream));
+    CK(cudaMemsetAsync(c->err.p + c->lo, 0, sizeof(double) * n, c->stream));
+  }
+  k_commit<<<nblk(n, 256), 256, 0, c->stream>>>(c->ks.p + c->lo, c->errs.p + c->lo, c->I.p + c->lo, c->err.p + c->lo, n);
+  LAUNCH_CHECK();
+  c->stats.n_panels++;
+  return SK_OK;
+}
+
+int sk_converge_scan(sk_ctx *c, const sk_scan_args *a, int64_t *new_hi, double *r_at_new_hi) {
+  if (!c || !a || !new_hi) return SK_ERR_ARG;
+  if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
+  if (a->criteria < 0 || a->criteria > 2) return fail(c, SK_ERR_ARG, "bad criteria");
+  const long long n = c->hi - c->lo;
+  SkReduceOut init;
+  std::memset(&init, 0, sizeof(init));
+  init.max_unconv = c->lo - 1;
+  c->h_scal->red = init;
+  CK(cudaMemcpyAsync(c->d_red, &c->h_scal->red, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  k_scan<<<nblk(n, 256), 256, 0, c->stream>>>(c->uxs.p + c->lo, c->I.p + c->lo, n, c->lo, a->trunc_a, a->trunc_num, a->xpow, a->tau,
+                                              a->criteria, c->d_red);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const long long top = c->h_scal->red.max_unconv;      // 0-based index of the highest unconverged target, or lo-1
+  *new_hi = top + 1;                                      // 1-based
+  double r = 0.0;
+  if (top >= c->lo) {
+    CK(cudaMemcpyAsync(&c->h_scal->r[0], c->uxs.p + top, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    r = c->h_scal->r[0];
+  }
+  if (r_at_new_hi) *r_at_new_hi = r;
+  return SK_OK;
+}
+
+int sk_converge_apply(sk_ctx *c, const sk_scan_args *a, int64_t new_hi) {
+  if (!c || !a) return SK_ERR_ARG;
+  if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
+  if (new_hi < c->lo || new_hi > c->hi) return fail(c, SK_ERR_ARG, "new_hi outside the panel range");
+  const long long nconv = c->hi - new_hi;                 // 0-based indices new_hi .. hi-1
+  if (nconv > 0 && a->criteria != SK_CRIT_PANEL) {
+    k_scan_add<<<nblk(nconv, 256), 256, 0, c->stream>>>(c->uxs.p + new_hi, c->errs.p + new_hi, nconv, a->trunc_a, a->trunc_num,
+                                                        a->xpow, a->criteria);
+    LAUNCH_CHECK();
+  }
+  c->in_panel = false;
+  return SK_OK;
+}
+
+int sk_target_upper_index(sk_ctx *c, double r, int64_t *idx) {
+  if (!c || !idx) return SK_ERR_ARG;
+  if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
+  k_upper_bound<<<1, 1, 0, c->stream>>>(c->uxs.p, c->n_unique, r, &c->d_red->max_unconv);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *idx = c->h_scal->red.max_unconv;
+  return SK_OK;
+}
+
+int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
+  if (!c || !vals_dev) return SK_ERR_ARG;
+  if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
+  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->ks.p, c->errs.p, c->n_in, vals_dev, errs_dev);
+  LAUNCH_CHECK();
+  CK(cudaStreamSynchronize(c->stream));
+  return SK_OK;
+}
+
+int sk_results_get(sk_ctx *c, double *vals, double *errs) {
+  if (!c || !vals) return SK_ERR_ARG;
+  if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
+  CK(cudaSetDevice(c->device));
+  CK(c->out_v.ensure(c->n_in));
+  if (errs) CK(c->out_e.ensure(c->n_in));
+  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->ks.p, c->errs.p, c->n_in, c->out_v.p, errs ? c->out_e.p : nullptr);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(vals, c->out_v.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
+  if (errs) CK(cudaMemcpyAsync(errs, c->out_e.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return SK_OK;
+}
+
+int sk_stats_get(sk_ctx *c, sk_stats *out) {
+  if (!c || !out) return SK_ERR_ARG;
+  *out = c->stats;
+  return SK_OK;
+}
+
+// ---- host-side helpers exported for tests ---------------------------------------------------------------
+int sk_host_gauss_rule(int32_t n, double p, double *no, double *wt) {
+  if (!no || !wt) return SK_ERR_ARG;
+  return sk_plan_gauss_rule(n, p, no, wt) == 0 ? SK_OK : SK_ERR_ARG;
+}
+
+int sk_host_es_plan(int32_t w, double *beta, int32_t *nc, double *coef, int32_t *nq, double *qc, double *ximax) {
+  SkEsPlan P;
+  if (sk_plan_make_es(w, &P) != 0) return SK_ERR_ARG;
+  if (beta) *beta = P.beta;
+  if (nc) *nc = SK_NC;
+  if (nq) *nq = P.nq;
+  if (ximax) *ximax = P.ximax;
+  if (coef)
+    for (int i = 0; i < w / 2; ++i)
+      for (int q = 0; q < SK_NC / 2; ++q) {
+        coef[(i * 2 + 0) * (SK_NC / 2) + q] = P.E[i][q];
+        coef[(i * 2 + 1) * (SK_NC / 2) + q] = P.O[i][q];
+      }
+  if (qc) std::memcpy(qc, P.qc, sizeof(double) * P.nq);
+  return SK_OK;
+}
+
+}  // extern "C"

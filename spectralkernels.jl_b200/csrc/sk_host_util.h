@@ -1,0 +1,71 @@
+// sk_host_util.h -- host-side geometry / panel bookkeeping shared by the C-ABI translation unit and
+// the host-emulation test harness.
+#pragma once
+#include "sk_math.h"
+
+#include <cmath>
+
+static inline long long sk_next235even(long long n) {
+  if (n <= 2) return 2;
+  if (n & 1) ++n;
+  for (;; n += 2) {
+    long long m = n;
+    while (m % 2 == 0) m /= 2;
+    while (m % 3 == 0) m /= 3;
+    while (m % 5 == 0) m /= 5;
+    if (m == 1) return n;
+  }
+}
+
+// Geometry of one type-3 transform: sources in [w_lo, w_hi], targets in [r_lo, r_hi].
+// sigma = 2 for both the spread and the inner type-2 step.
+// Returns 0, or -1 if the grid would be unreasonably large.
+static inline int sk_make_geom(const SkEsPlan &P, double w_lo, double w_hi, double r_lo, double r_hi, SkGeom *G) {
+  const double sigma = 2.0;
+  const double PI = 3.14159265358979323846;
+  double X = 0.5 * (w_hi - w_lo);
+  G->wc = 0.5 * (w_lo + w_hi);
+  double S;
+  // centre the targets only when they form a narrow band away from the origin; otherwise keep
+  // D = 0 (no pre-phase, r - D exact) -- the adaptive driver's targets always start near 0.
+  if (r_lo > 0.5 * r_hi && r_lo > 0.0) {
+    G->D = 0.5 * (r_lo + r_hi);
+    S = 0.5 * (r_hi - r_lo);
+  } else if (r_hi < 0.0 && r_hi < 0.5 * r_lo) {
+    G->D = 0.5 * (r_lo + r_hi);
+    S = 0.5 * (r_hi - r_lo);
+  } else {
+    G->D = 0.0;
+    S = std::fmax(std::fabs(r_lo), std::fabs(r_hi));
+  }
+  // keep the space-bandwidth product >= O(1) so that the grids never degenerate
+  if (!(X > 0.0) && !(S > 0.0)) { X = 1.0; S = 1.0; }
+  else if (!(X > 0.0)) X = 1.0 / (16.0 * S);
+  if (S * X < 0.0625) S = 0.0625 / X;
+  G->inv_hu = 2.0 * sigma * S;
+  const double cells = 2.0 * X * G->inv_hu;
+  if (!(cells < 2.0e8)) return -1;
+  long long nf = (long long)std::ceil(cells) + P.w + 2;
+  if (nf & 1) ++nf;
+  if (nf < 2 * P.w) nf = 2 * P.w;
+  G->nf = nf;
+  G->nf2 = sk_next235even((long long)std::ceil(sigma * (double)nf));
+  const double n2 = (double)G->nf2;
+  G->kap_hi = n2 / G->inv_hu;
+  G->kap_lo = -std::fma(G->kap_hi, G->inv_hu, -n2) / G->inv_hu;
+  G->t_cell = (PI * P.w / n2) / P.ximax;
+  return 0;
+}
+
+// range(a, b, length=k+1) (src/quadrature.jl:56): Julia's StepRangeLen keeps the step in twice
+// precision, i.e. element i is a + i (b-a)/k rounded once; long double reproduces that.
+static inline void sk_fill_subpanels(double a, double b, int k, double *bmad2, double *bpad2) {
+  const long double al = a, bl = b;
+  double prev = a;
+  for (int i = 1; i <= k; ++i) {
+    double e = (i == k) ? b : (double)(al + (long double)i * ((bl - al) / (long double)k));
+    bmad2[i - 1] = (e - prev) / 2;   // src/quadrature.jl:63,83
+    bpad2[i - 1] = (e + prev) / 2;
+    prev = e;
+  }
+}

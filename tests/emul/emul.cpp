@@ -1,0 +1,58 @@
+// emul.cpp -- TEST HARNESS ONLY.  Compiles the product's per-element arithmetic
+// (spectralkernels.jl_b200/csrc/sk_math.h, sk_host_util.h, sk_plan_host.cpp) with g++ and runs it in
+// plain loops, so that the index arithmetic of the CUDA kernels can be checked against the oracle on
+// a machine without a GPU.  It is not a product path: nothing in spectralkernels.jl_b200/ loads it.
+#include "sk_host_util.h"
+
+#include <cstring>
+#include <vector>
+
+extern "C" {
+
+int emul_es_plan(int w, SkEsPlan *out) { return sk_plan_make_es(w, out); }
+
+int emul_geom(const SkEsPlan *P, double w_lo, double w_hi, double r_lo, double r_hi, SkGeom *G) {
+  return sk_make_geom(*P, w_lo, w_hi, r_lo, r_hi, G);
+}
+
+// spread + deconvolve + zero-pad: fills fft_in[nf2] (interleaved complex) for one rule
+void emul_spread(const SkEsPlan *P, const SkGeom *G, long long M, const double *no, const double *c /*interleaved*/,
+                 double *fft_in) {
+  std::vector<double> ph(M), pl(M);
+  std::vector<sk_cplx> cs(M);
+  for (long long k = 0; k < M; ++k) sk_source_prep(*G, no[k], c[2 * k], c[2 * k + 1], &ph[k], &pl[k], &cs[k].x, &cs[k].y);
+#pragma omp parallel for schedule(static)
+  for (long long j = 0; j < G->nf2; ++j)
+    sk_spread_mode(*P, *G, j, ph.data(), pl.data(), cs.data(), M, &fft_in[2 * j], &fft_in[2 * j + 1]);
+}
+
+// interpolate one grid (interleaved complex, nf2 entries) at N targets
+void emul_interp(const SkEsPlan *P, const SkGeom *G, long long N, const double *r, const double *grid, double *out) {
+  std::vector<sk_cplx> g(G->nf2);
+  std::memcpy(g.data(), grid, sizeof(sk_cplx) * G->nf2);
+#pragma omp parallel for schedule(static)
+  for (long long j = 0; j < N; ++j) sk_interp_point<16, 1>(*P, *G, r[j], g.data(), &out[2 * j], &out[2 * j + 1]);
+}
+
+// updatequadbufs! on the "device" generator
+void emul_gen_sources(int m, int k, double a, double b, double p, int origin_jacobi, int weight_in_f, int logw,
+                      int family, int deriv, const double *params, int nparam, const double *leg_no1,
+                      const double *leg_wt1, const double *leg_no2, const double *leg_wt2, const double *jac_no1,
+                      const double *jac_wt1, const double *jac_no2, const double *jac_wt2, double *no1, double *buf1,
+                      double *no2, double *buf2) {
+  SkPanelSpec S;
+  std::memset(&S, 0, sizeof(S));
+  S.m = m; S.k = k; S.origin_jacobi = origin_jacobi; S.weight_in_f = weight_in_f; S.logw = logw;
+  S.family = family; S.deriv = deriv; S.nparam = nparam; S.p = p;
+  for (int i = 0; i < nparam; ++i) S.params[i] = params[i];
+  sk_fill_subpanels(a, b, k, S.bmad2, S.bpad2);
+  S.jac_scale = std::pow(S.bmad2[0], p + 1);
+  for (long long i = 0; i < (long long)m * k; ++i) sk_gen_source(S, 0, i, leg_no1, leg_wt1, jac_no1, jac_wt1, &no1[i], &buf1[i]);
+  for (long long i = 0; i < 2LL * m * k; ++i) sk_gen_source(S, 1, i, leg_no2, leg_wt2, jac_no2, jac_wt2, &no2[i], &buf2[i]);
+}
+
+int emul_gauss_rule(int n, double p, double *no, double *wt) { return sk_plan_gauss_rule(n, p, no, wt); }
+
+double emul_trunc_err(double ta, double tn, double xpow, double x, int panel) { return sk_trunc_err(ta, tn, xpow, x, panel); }
+int emul_converged(double te, double pk, double tau, int crit) { return sk_converged(te, pk, tau, crit) ? 1 : 0; }
+}
