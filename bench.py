@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the K(r) hot path (BASELINE.json):
+
+    K(r) evals/sec at tol = 1e-8 (Matern S, 1e7 r), 1/2/4/8 B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, restated (oracle port)
+
+A "step" is one kernel_values(cfg, rs) call over one batch of synthetic distances:
+Matern nu = 1.5, rho = 1, phi such that K(0) = 1; rs ~ U(0,1), seed = rank, unsorted as drawn;
+tol = 1e-8, convergence_criteria = :both, quadspec = (2^12, 2^4)  (BASELINE config 2).
+
+value : whole-job K(r) evals/s with the distances already resident in HBM (device pointers in,
+        device pointers out), timed with CUDA events on the library's stream, max over ranks.
+e2e   : the same metric through the public kernel_values call with HOST (pinned) buffers: the H2D copy
+        of the distances and the D2H copy of values and errors are inside the timed region.
+N > 1 : every rank evaluates its own batch of n distances (weak scaling); the ranks run ONE adaptive
+        loop in lock step through scalar NCCL all-reduces (spectralkernels.jl_b200/sharded.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# algorithmic work per unit = one (active target, sub-interval) pair
+FLOPS_PER_UNIT_FUSED = 764      # ES taps shared by the m- and 2m-rule grids (our kernel is fused)
+BYTES_PER_UNIT_K4 = 24          # interpolation kernel: read r (8) + write I2 and |I2-I1| (16)
+BYTES_PER_UNIT_STEP = 40        # SURVEY 8(d) figure for the whole sub-interval (r + RMW of value and error)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000, help="distances per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="distances in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_sdf_params():
+    return (1.0 / (np.pi / 2), 1.0, 1.5)            # K(0) = 1 (pattern of scripts/figures/speed_test_plot.jl:27-28)
+
+
+def make_distances(n: int, rank: int) -> np.ndarray:
+    return np.random.default_rng(rank).uniform(0.0, 1.0, n)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_cpu_run(n_sample: int, steps: int, warmup: int):
+    """The reference's CPU path restated (oracle port): numpy driver + from-scratch CPU type-3 NUFFT
+    with all host threads, on a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sk_oracle as so
+    phi, rho, nu = workload_sdf_params()
+    S = lambda w: phi * (rho ** 2 + w ** 2) ** (-nu - 0.5)
+    cfg = so.OracleConfig(S)
+    xs = make_distances(10_000_000, 0)[:n_sample]
+    for _ in range(warmup):
+        so.kernel_values(cfg, xs[: max(1000, n_sample // 50)], k0=1.0, transform="nufft")
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        vals, _ = so.kernel_values(cfg, xs, k0=1.0, transform="nufft")
+    dt = time.perf_counter() - t0
+    true = (1 + 2 * np.pi * xs) * np.exp(-2 * np.pi * xs)
+    return {"evals_per_s": n_sample * steps / dt, "seconds": dt, "threads": so.num_threads(),
+            "max_err": float(np.max(np.abs(vals - true)))}
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    r = oracle_cpu_run(args.cpu_sample, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "K(r) evals/sec at tol=1e-8 (Matern S, 1e7 r)", "value": r["evals_per_s"],
+        "unit": "evals/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "matern nu=1.5 rho=1 K(0)=1, r~U(0,1) seed 0, tol=1e-8, quadspec (4096,16), :both",
+                   "n_per_step": args.cpu_sample, "full_n": 10_000_000,
+                   "note": "reference (Julia+FINUFFT) cannot run in this image; this is the oracle port of its CPU "
+                           "path (CPU restatement, not FINUFFT), all host threads, bounded sample per step"},
+        "cpu_baseline": {"value": r["evals_per_s"], "unit": "evals/s", "cores": r["threads"], "kind": "port",
+                         "sample": f"{args.cpu_sample} of the 1e7 distances per step"},
+        "e2e": {"value": r["evals_per_s"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "max_abs_err_vs_closed_form": r["max_err"],
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import spectralkernels_jl_b200 as sk
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from spectralkernels_jl_b200.sharded import TorchComm
+        comm = TorchComm(device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.n
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    phi, rho, nu = workload_sdf_params()
+    cfg = sk.AdaptiveKernelConfig(sk.Matern(phi, rho, nu), device=local_rank)
+    eng = cfg.engine
+    k0 = 1.0
+
+    # synthetic distances: pinned host copy (e2e) and device copy (resident)
+    host_in = sk.PinnedArray(n)
+    host_in.array[:] = make_distances(n, rank)
+    host_v, host_e = sk.PinnedArray(n), sk.PinnedArray(n)
+    d_in = torch.from_numpy(host_in.array).to(f"cuda:{local_rank}")
+    d_v = torch.empty(n, dtype=torch.float64, device=d_in.device)
+    d_e = torch.empty(n, dtype=torch.float64, device=d_in.device)
+    torch.cuda.synchronize()
+
+    def step_resident(trace=None):
+        sk.kernel_values(cfg, None, k0=k0, xs_device=(d_in.data_ptr(), n), out_device=(d_v.data_ptr(), d_e.data_ptr()),
+                         comm=comm, trace=trace)
+
+    def step_e2e():
+        sk.kernel_values(cfg, host_in.array, k0=k0, comm=comm, out_vals=host_v.array, out_errs=host_e.array)
+
+    # ---- device-resident: warm-up, then K timed steps ------------------------------------------------
+    trace = []
+    step_resident(trace)
+    for _ in range(W - 1):
+        step_resident()
+    eng.set_timing(True)
+    sampler = ClockSampler(local_rank)
+    agg = {"units": 0, "interp_ms": 0.0, "source_ms": 0.0, "launches": 0, "subintervals": 0}
+    barrier()
+    sampler.start()
+    eng.timer_begin()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_resident()
+        st = eng.stats()
+        agg["units"] += st["units"]; agg["interp_ms"] += st["interp_ms"]; agg["source_ms"] += st["source_ms"]
+        agg["launches"] += st["kernel_launches"]; agg["subintervals"] += st["n_subintervals"]
+    dev_ms = eng.timer_end()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    eng.set_timing(False)
+    res_ms = max(dev_ms, 0.0)
+
+    # ---- end to end (host buffers) ---------------------------------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([res_ms, e2e_ms, wall_ms], dtype=torch.float64, device=d_in.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res_ms, e2e_ms, wall_ms = t.tolist()
+
+    # parity spot check of the timed configuration (closed form of Matern nu = 3/2)
+    true = (1 + 2 * np.pi * host_in.array) * np.exp(-2 * np.pi * host_in.array)
+    max_err = float(np.max(np.abs(host_v.array - true)))
+    same = bool(torch.equal(d_v.cpu(), torch.from_numpy(host_v.array)))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        fp64_tf, _ = eng.fp64_peak()
+        n_launch = max(1, agg["subintervals"])
+        units_per_launch = agg["units"] / n_launch
+        k4_ms = agg["interp_ms"] / n_launch
+        ach_tf = units_per_launch * FLOPS_PER_UNIT_FUSED / (k4_ms * 1e-3) / 1e12 if k4_ms > 0 else None
+        ach_gbs = units_per_launch * BYTES_PER_UNIT_K4 / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else None
+        line = {
+            "metric": "K(r) evals/sec at tol=1e-8 (Matern S, 1e7 r)",
+            "value": world * n * K / (res_ms * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": res_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "matern nu=1.5 rho=1 K(0)=1, r~U(0,1) seed=rank unsorted, tol=1e-8, "
+                                   "quadspec (4096,16), :both (BASELINE config 2)",
+                       "n_per_gpu": n, "k0": "passed (=1.0) in both arms", "nufft_eps": 1e-15,
+                       "l2": "inputs + work arrays (>1 GB per step) exceed the 126 MB L2; no explicit flush",
+                       "parallelism": "target-sharded, scalar NCCL all-reduces only" if world > 1 else "single GPU",
+                       "panels": [(t["a"], t["b"], t["hi_before"], t["hi_after"]) for t in trace if t["kind"] == "panel"]},
+            "e2e": {"value": world * n * K / (e2e_ms * 1e-3), "unit": "evals/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 16 * n,
+                    "note": "kernel_values with pinned host buffers; values and errors both copied back"},
+            "gpu_launches": int(agg["launches"]),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "kernel": "k_interp_session<16>", "achieved": ach_tf, "peak": fp64_tf,
+                         "unit": "TFLOP/s", "frac": (ach_tf / fp64_tf) if ach_tf else None, "traffic": None,
+                         "flops_per_unit": FLOPS_PER_UNIT_FUSED, "units_per_launch": units_per_launch,
+                         "avg_launch_ms": k4_ms, "kernel_share_of_step": agg["interp_ms"] / res_ms,
+                         "peak_source": "measured live: sk_fp64_peak DFMA micro-benchmark (MEASURED_PEAKS.json has no FP64 figure)",
+                         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": (ach_gbs / hbm_peak) if ach_gbs else None, "bytes_per_unit": BYTES_PER_UNIT_K4,
+                                 "peak_source": hbm_src}},
+            "source_side_ms_per_step": agg["source_ms"] / K, "interp_ms_per_step": agg["interp_ms"] / K,
+            "units_per_step": agg["units"] / K, "wall_ms_per_step": wall_ms / K,
+            "parity": {"max_abs_err_vs_closed_form": max_err, "resident_equals_e2e_bitwise": same},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = oracle_cpu_run(args.cpu_sample, 1, 1)
+            line["cpu_baseline"] = {"value": r["evals_per_s"], "unit": "evals/s", "cores": r["threads"], "kind": "port",
+                                    "sample": f"first {args.cpu_sample} of the 1e7 distances, 1 pass "
+                                              f"({r['seconds']:.1f} s); oracle port (CPU restatement, not FINUFFT)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,6 +114,14 @@ int sk_ctx_synchronize(sk_ctx *ctx);
 /* the CUDA stream of the context as an opaque handle (cudaStream_t), for event timing by the caller */
 int sk_ctx_stream(sk_ctx *ctx, void **stream_out);
 
+/* device-side stopwatch on the context's stream (cudaEvent pair), the equivalent of the reference's
+ * TimerOutputs sections (src/SpectralKernels.jl:14): begin records, end records + waits + returns ms */
+int sk_timer_begin(sk_ctx *ctx);
+int sk_timer_end(sk_ctx *ctx, double *ms);
+/* measured FP64 FMA throughput of this GPU (dependent-chain DFMA micro-benchmark, TFLOP/s); the
+ * denominator of the FP64 roofline, which MEASURED_PEAKS.json does not contain */
+int sk_fp64_peak(sk_ctx *ctx, double *tflops, double *ms);
+
 /* pinned host memory for callers that want full PCIe rate (Julia: unsafe_wrap the pointer) */
 int sk_host_alloc(size_t bytes, void **out);
 int sk_host_free(void *ptr);

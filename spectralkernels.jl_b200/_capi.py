@@ -66,6 +66,9 @@ SIGNATURES = {
     "sk_ctx_set_nufft_eps": (c_int, [c_void_p, c_double]),
     "sk_ctx_synchronize": (c_int, [c_void_p]),
     "sk_ctx_stream": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "sk_timer_begin": (c_int, [c_void_p]),
+    "sk_timer_end": (c_int, [c_void_p, _dp]),
+    "sk_fp64_peak": (c_int, [c_void_p, _dp, _dp]),
     "sk_host_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "sk_host_free": (c_int, [c_void_p]),
     "sk_nufft1d3": (c_int, [c_void_p, c_int64, _dp, _dp, c_int64, _dp, _dp, c_double]),
@@ -184,6 +187,22 @@ class Session:
         s = c_void_p()
         self._ck(self._L.sk_ctx_stream(self._h, byref(s)))
         return s.value or 0
+
+    def timer_begin(self):
+        self._ck(self._L.sk_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = c_double()
+        self._ck(self._L.sk_timer_end(self._h, byref(ms)))
+        return ms.value
+
+    def fp64_peak(self):
+        tf, ms = c_double(), c_double()
+        self._ck(self._L.sk_fp64_peak(self._h, byref(tf), byref(ms)))
+        return tf.value, ms.value
+
+    def set_timing(self, on: bool):
+        self._ck(self._L.sk_ctx_set_timing(self._h, 1 if on else 0))
 
     def set_nufft_eps(self, eps: float):
         self._ck(self._L.sk_ctx_set_nufft_eps(self._h, float(eps)))

@@ -97,6 +97,7 @@ struct sk_ctx {
   sk_stats stats;
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_user[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -395,6 +396,7 @@ int sk_ctx_create(int device, sk_ctx **out) {
     return SK_ERR_CUDA;
   }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
+  for (int i = 0; i < 2; ++i) cudaEventCreate(&c->ev_user[i]);
   if (sk_plan_make_es(width_from_eps(c->eps), &c->plan) != 0) {
     delete c;
     return SK_ERR_ARG;
@@ -419,6 +421,7 @@ int sk_ctx_destroy(sk_ctx *c) {
   if (c->d_red) cudaFree(c->d_red);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2; ++i) if (c->ev_user[i]) cudaEventDestroy(c->ev_user[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return SK_OK;
@@ -447,6 +450,45 @@ int sk_ctx_synchronize(sk_ctx *c) {
 int sk_ctx_stream(sk_ctx *c, void **stream_out) {
   if (!c || !stream_out) return SK_ERR_ARG;
   *stream_out = (void *)c->stream;
+  return SK_OK;
+}
+
+int sk_timer_begin(sk_ctx *c) {
+  if (!c) return SK_ERR_ARG;
+  CK(cudaEventRecord(c->ev_user[0], c->stream));
+  return SK_OK;
+}
+
+int sk_timer_end(sk_ctx *c, double *ms) {
+  if (!c || !ms) return SK_ERR_ARG;
+  CK(cudaEventRecord(c->ev_user[1], c->stream));
+  CK(cudaEventSynchronize(c->ev_user[1]));
+  float f = 0;
+  CK(cudaEventElapsedTime(&f, c->ev_user[0], c->ev_user[1]));
+  *ms = f;
+  return SK_OK;
+}
+
+int sk_fp64_peak(sk_ctx *c, double *tflops, double *ms_out) {
+  if (!c || !tflops) return SK_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  CK(c->dsum.ensure(16));
+  const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+  double best = 1e30;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(c->ev_user[0], c->stream));
+    k_dfma_peak<<<blocks, 256, 0, c->stream>>>((double *)c->dsum.p, iters, 0.999999, 1e-9);
+    CK(cudaEventRecord(c->ev_user[1], c->stream));
+    CK(cudaEventSynchronize(c->ev_user[1]));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, c->ev_user[0], c->ev_user[1]));
+    if (rep > 0 && f < best) best = f;
+  }
+  const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
   return SK_OK;
 }
 

@@ -296,3 +296,19 @@ __global__ void k_fill(double *__restrict__ a, long long n, double v) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) a[j] = v;
 }
+
+// ---- FP64 pipe micro-benchmark (roofline denominator) -------------------------------------------------
+// 8 independent dependent-FMA chains per thread; 2 flops per DFMA.
+__global__ void __launch_bounds__(256) k_dfma_peak(double *__restrict__ out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+      x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
+}

@@ -1,0 +1,42 @@
+"""
+Scalar reductions for a target-sharded multi-GPU run of kernel_values.
+
+Every rank passes its own chunk of the distances (no exchange of targets).  The adaptive loop stays in
+lock step through three kinds of scalar all-reduces: max of the largest unconverged distance (panel
+choice, src/adaptive.jl:152), max of max|I2-I1| (accept test, src/quadrature.jl:258-260) and max of the
+stopping distance of the convergence scan (src/adaptive.jl:183-198).  Because every rank builds the
+same transform geometry (sk_panel_set_range) the per-target arithmetic does not depend on the sharding:
+the values are bit-identical to a single-GPU run over the union of the chunks.
+
+Backend: torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+
+class TorchComm:
+    def __init__(self, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._torch, self._dist, self._group = torch, dist, group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if device is None:
+            device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        self.device = device
+        self.n_reductions = 0
+
+    def _reduce(self, vals: Sequence[float], op) -> List[float]:
+        t = self._torch.tensor(list(vals), dtype=self._torch.float64, device=self.device)
+        self._dist.all_reduce(t, op=op, group=self._group)
+        self.n_reductions += 1
+        return t.cpu().tolist()
+
+    def max(self, vals):
+        return self._reduce(vals, self._dist.ReduceOp.MAX)
+
+    def min(self, vals):
+        return self._reduce(vals, self._dist.ReduceOp.MIN)
