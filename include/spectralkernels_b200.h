@@ -110,6 +110,9 @@ int sk_ctx_create(int device, sk_ctx **out);
 int sk_ctx_destroy(sk_ctx *ctx);
 int sk_ctx_set_timing(sk_ctx *ctx, int enabled);          /* per-stage cudaEvent timers (NVTX-like)   */
 int sk_ctx_set_nufft_eps(sk_ctx *ctx, double eps);        /* default 1e-15, as hard-wired in src/utils.jl:10 */
+/* interpolation kernel: 0 (default) = cell polynomials in shared memory (k_interp_cells); 1 = per-target
+ * exp-of-semicircle taps, the textbook evaluation (k_interp_session), kept for A/B measurements */
+int sk_ctx_set_interp_mode(sk_ctx *ctx, int mode);
 int sk_ctx_synchronize(sk_ctx *ctx);
 /* the CUDA stream of the context as an opaque handle (cudaStream_t), for event timing by the caller */
 int sk_ctx_stream(sk_ctx *ctx, void **stream_out);

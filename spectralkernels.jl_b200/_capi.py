@@ -64,6 +64,7 @@ SIGNATURES = {
     "sk_ctx_destroy": (c_int, [c_void_p]),
     "sk_ctx_set_timing": (c_int, [c_void_p, c_int]),
     "sk_ctx_set_nufft_eps": (c_int, [c_void_p, c_double]),
+    "sk_ctx_set_interp_mode": (c_int, [c_void_p, c_int]),
     "sk_ctx_synchronize": (c_int, [c_void_p]),
     "sk_ctx_stream": (c_int, [c_void_p, POINTER(c_void_p)]),
     "sk_timer_begin": (c_int, [c_void_p]),
@@ -203,6 +204,9 @@ class Session:
 
     def set_timing(self, on: bool):
         self._ck(self._L.sk_ctx_set_timing(self._h, 1 if on else 0))
+
+    def set_interp_mode(self, mode: int):
+        self._ck(self._L.sk_ctx_set_interp_mode(self._h, int(mode)))
 
     def set_nufft_eps(self, eps: float):
         self._ck(self._L.sk_ctx_set_nufft_eps(self._h, float(eps)))

@@ -44,8 +44,9 @@ struct DevBuf {
   }
 };
 
-struct HostScalars {          // pinned mirror of SkReduceOut plus two doubles
+struct HostScalars {          // pinned mirror of the device scalars
   SkReduceOut red;
+  SkTargetSummary sum;
   double r[2];
 };
 
@@ -78,7 +79,8 @@ struct sk_ctx {
   // targets
   long long n_in = 0, n_unique = 0;
   bool has_zero = false;
-  DevBuf<double> in, uxs, ks, errs, I, err, stage_i, stage_e, out_v, out_e;
+  DevBuf<double> in, uxs, out_v, out_e;
+  DevBuf<sk_cplx> res, pan, stage;   // (ks, errs), (I, err), (I2, |I2-I1|) per unique target
   DevBuf<unsigned long long> keys, keys_alt;
   DevBuf<unsigned int> idx, idx_alt, head, uid, inv;
   DevBuf<unsigned char> cub_tmp;
@@ -88,7 +90,13 @@ struct sk_ctx {
   // panel state (0-based half-open [lo, hi))
   long long lo = 0, hi = 0;
   double r_lo = 0, r_hi = 0;
-  bool in_panel = false, staged = false, first_accept = true;
+  bool in_panel = false, staged = false, first_accept = true, commit_pending = false;
+  long long pend_lo = 0, pend_hi = 0;        // range of the pending (lazy) commit
+  double r0 = 0, r1 = 0, r_last = 0;         // smallest, second smallest, largest unique distance
+  long long scan_hi = -1;                    // 1-based index / distance returned by the last scan
+  double scan_r = 0;
+  int interp_mode = 0;                       // 0: cell polynomials (default), 1: per-target taps
+  SkTargetSummary *d_sum = nullptr;
 
   SkReduceOut *d_red = nullptr;
   HostScalars *h_scal = nullptr;  // pinned
@@ -161,9 +169,23 @@ int get_fft_plan(sk_ctx *c, long long nf2, int batch, cufftHandle *out) {
 }
 
 template <int W>
-void launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long long n, double cmul, int ksin) {
-  k_interp_session<W><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage_i.p + c->lo,
-                                                           c->stage_e.p + c->lo, c->d_red);
+int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long long n, double cmul, int ksin) {
+  if (c->interp_mode == 1) {
+    k_interp_session<W><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage.p + c->lo, c->d_red);
+    return 0;
+  }
+  // cells the active targets span -> average targets per cell -> how many cells a block may hold
+  const double span = (c->r_hi - c->r_lo) * G.kap_hi + 1.0;
+  const double per_block = span * (double)SK_TPB / (double)n;
+  const int cmax = per_block <= 24.0 ? 32 : 96;
+  const size_t smem = sizeof(double) * (size_t)(2 * (W / 2) * (SK_NC / 2) + (cmax + W) * 4 + cmax * SK_NC * 4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_interp_cells<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_set = true;
+  }
+  k_interp_cells<W><<<nblk(n, SK_TPB), 256, smem, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, cmax, c->stage.p + c->lo, c->d_red);
+  return 0;
 }
 template <int W>
 void launch_interp_cplx(sk_ctx *c, const SkGeom &G, const double *x, long long n, sk_cplx *out) {
@@ -242,7 +264,7 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
     dim3 grid((unsigned int)n_act, 2);
     k_direct<<<grid, 256, 0, c->stream>>>(c->no1.p, c->buf1.p, M1, c->no2.p, c->buf2.p, M2, c->uxs.p + c->lo, c->dsum.p);
     LAUNCH_CHECK();
-    k_direct_finish<<<1, 256, 0, c->stream>>>(c->dsum.p, n_act, o->cmul, ksin, c->stage_i.p + c->lo, c->stage_e.p + c->lo, c->d_red);
+    k_direct_finish<<<1, 256, 0, c->stream>>>(c->dsum.p, n_act, o->cmul, ksin, c->stage.p + c->lo, c->d_red);
     LAUNCH_CHECK();
     c->stats.n_direct++;
   }
@@ -305,53 +327,47 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info) 
   LAUNCH_CHECK();
   CK(cub::DeviceScan::InclusiveSum(c->cub_tmp.p, tmp2, c->head.p, c->uid.p, (int)n_in, c->stream));
   c->stats.kernel_launches += 2;
-  unsigned int h_last = 0, h_bad = 0;
-  CK(cudaMemcpyAsync(&c->h_scal->red.flags, c->uid.p + (n_in - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&c->h_scal->red._pad, c->badflag.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  h_last = c->h_scal->red.flags;
-  h_bad = c->h_scal->red._pad;
-  if (h_bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
-  const long long nu = h_last;
-  CK(c->uxs.ensure(nu));
+  // unique table sized for the worst case (n_unique <= n_in): no host round trip before the scatter
+  CK(c->uxs.ensure(n_in));
   k_scatter_unique<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, sidx, c->head.p, c->uid.p, n_in, c->uxs.p, c->inv.p);
   LAUNCH_CHECK();
-  CK(c->ks.ensure(nu));
-  CK(c->errs.ensure(nu));
-  CK(c->I.ensure(nu));
-  CK(c->err.ensure(nu));
-  CK(c->stage_i.ensure(nu));
-  CK(c->stage_e.ensure(nu));
-  // smallest / second smallest / largest unique distance
-  double h3[3] = {0, 0, 0};
-  CK(cudaMemcpyAsync(&c->h_scal->r[0], c->uxs.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&c->h_scal->r[1], c->uxs.p + (nu - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  k_target_summary<<<1, 1, 0, c->stream>>>(c->uxs.p, c->uid.p, n_in, c->badflag.p, c->d_sum);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
+  CK(c->res.ensure(n_in));
+  CK(c->pan.ensure(n_in));
+  CK(c->stage.ensure(n_in));
   CK(cudaStreamSynchronize(c->stream));
-  h3[0] = c->h_scal->r[0];
-  h3[2] = c->h_scal->r[1];
+  const SkTargetSummary sm = c->h_scal->sum;
+  if (sm.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
+  const long long nu = sm.n_unique;
   c->n_in = n_in;
   c->n_unique = nu;
-  c->has_zero = (h3[0] == 0.0);
-  double rminpos = h3[0];
-  if (c->has_zero) {
-    rminpos = 0.0;
-    if (nu > 1) {
-      CK(cudaMemcpyAsync(&c->h_scal->r[0], c->uxs.p + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      rminpos = c->h_scal->r[0];
-    }
-  }
+  c->r0 = sm.r0; c->r1 = sm.r1; c->r_last = sm.r_last;
+  c->has_zero = (sm.r0 == 0.0);
   c->have_targets = true;
   c->in_panel = false;
   c->staged = false;
+  c->commit_pending = false;
+  c->scan_hi = -1;
   if (info) {
     info->n_in = n_in;
     info->n_unique = nu;
     info->has_zero = c->has_zero ? 1 : 0;
     info->_pad = 0;
-    info->r_min_pos = rminpos;
-    info->r_max = h3[2];
+    info->r_min_pos = c->has_zero ? sm.r1 : sm.r0;
+    info->r_max = sm.r_last;
   }
+  return SK_OK;
+}
+
+// the lazy commit of the last panel, when no scan consumed it
+int flush_commit(sk_ctx *c) {
+  if (!c->commit_pending) return SK_OK;
+  const long long n = c->pend_hi - c->pend_lo;
+  k_commit<<<nblk(n, 256), 256, 0, c->stream>>>(c->pan.p + c->pend_lo, c->res.p + c->pend_lo, n);
+  LAUNCH_CHECK();
+  c->commit_pending = false;
   return SK_OK;
 }
 
@@ -391,6 +407,7 @@ int sk_ctx_create(int device, sk_ctx **out) {
   std::memset(&c->stats, 0, sizeof(c->stats));
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc((void **)&c->d_red, sizeof(SkReduceOut)) != cudaSuccess ||
+      cudaMalloc((void **)&c->d_sum, sizeof(SkTargetSummary)) != cudaSuccess ||
       cudaMallocHost((void **)&c->h_scal, sizeof(HostScalars)) != cudaSuccess) {
     delete c;
     return SK_ERR_CUDA;
@@ -412,10 +429,11 @@ int sk_ctx_destroy(sk_ctx *c) {
   for (auto &kv : c->fft_plans) cufftDestroy(kv.second);
   DevBuf<double> *dbl[] = {&c->leg_no1, &c->leg_wt1, &c->leg_no2, &c->leg_wt2, &c->jac_no1, &c->jac_wt1, &c->jac_no2,
                            &c->jac_wt2, &c->no1, &c->buf1, &c->no2, &c->buf2, &c->pos_hi1, &c->pos_lo1, &c->pos_hi2,
-                           &c->pos_lo2, &c->imz, &c->in, &c->uxs, &c->ks, &c->errs, &c->I, &c->err, &c->stage_i,
-                           &c->stage_e, &c->out_v, &c->out_e};
+                           &c->pos_lo2, &c->imz, &c->in, &c->uxs, &c->out_v, &c->out_e};
   for (auto *b : dbl) b->release();
   c->cs1.release(); c->cs2.release(); c->fft.release(); c->dsum.release();
+  c->res.release(); c->pan.release(); c->stage.release();
+  if (c->d_sum) cudaFree(c->d_sum);
   c->keys.release(); c->keys_alt.release(); c->idx.release(); c->idx_alt.release();
   c->head.release(); c->uid.release(); c->inv.release(); c->cub_tmp.release(); c->badflag.release();
   if (c->d_red) cudaFree(c->d_red);
@@ -645,10 +663,11 @@ int sk_run_begin(sk_ctx *c) {
   const bool t = c->timing;
   std::memset(&c->stats, 0, sizeof(c->stats));
   c->stats.timing_enabled = t;
-  CK(cudaMemsetAsync(c->ks.p, 0, sizeof(double) * c->n_unique, c->stream));     // zeros, src/adaptive.jl:122
-  CK(cudaMemsetAsync(c->errs.p, 0, sizeof(double) * c->n_unique, c->stream));
+  CK(cudaMemsetAsync(c->res.p, 0, sizeof(sk_cplx) * c->n_unique, c->stream));   // ks = errs = 0, src/adaptive.jl:122
   c->in_panel = false;
   c->staged = false;
+  c->commit_pending = false;
+  c->scan_hi = -1;
   return SK_OK;
 }
 
@@ -656,9 +675,7 @@ int sk_zero_lag_set(sk_ctx *c, double value) {
   if (!c) return SK_ERR_ARG;
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "sk_targets_set first");
   if (!c->has_zero) return SK_OK;
-  k_fill<<<1, 32, 0, c->stream>>>(c->ks.p, 1, value);
-  LAUNCH_CHECK();
-  k_fill<<<1, 32, 0, c->stream>>>(c->errs.p, 1, std::nan(""));
+  k_set_zero_lag<<<1, 1, 0, c->stream>>>(c->res.p, value);
   LAUNCH_CHECK();
   return SK_OK;
 }
@@ -668,13 +685,24 @@ int sk_panel_begin(sk_ctx *c, int64_t ix1, int64_t hi, double *r_lo, double *r_h
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "sk_targets_set first");
   if (ix1 < 1 || hi < ix1 || hi > c->n_unique) return fail(c, SK_ERR_ARG, "bad index range [%lld,%lld]", (long long)ix1, (long long)hi);
   CK(cudaSetDevice(c->device));
+  int rc = flush_commit(c);
+  if (rc != SK_OK) return rc;
   c->lo = ix1 - 1;
   c->hi = hi;
-  CK(cudaMemcpyAsync(&c->h_scal->r[0], c->uxs.p + c->lo, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&c->h_scal->r[1], c->uxs.p + (c->hi - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  c->r_lo = c->h_scal->r[0];
-  c->r_hi = c->h_scal->r[1];
+  // the end points are normally known on the host already (target summary / last scan): no D2H
+  bool need_lo = true, need_hi = true;
+  if (ix1 == 1) { c->r_lo = c->r0; need_lo = false; }
+  else if (ix1 == 2) { c->r_lo = c->r1; need_lo = false; }
+  if (hi == c->n_unique) { c->r_hi = c->r_last; need_hi = false; }
+  else if (hi == c->scan_hi) { c->r_hi = c->scan_r; need_hi = false; }
+  else if (hi == 1) { c->r_hi = c->r0; need_hi = false; }
+  if (need_lo || need_hi) {
+    CK(cudaMemcpyAsync(&c->h_scal->r[0], c->uxs.p + c->lo, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->h_scal->r[1], c->uxs.p + (c->hi - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->r_lo = c->h_scal->r[0];
+    c->r_hi = c->h_scal->r[1];
+  }
   if (r_lo) *r_lo = c->r_lo;
   if (r_hi) *r_hi = c->r_hi;
   c->in_panel = true;
@@ -763,9 +791,14 @@ int sk_subinterval_accept(sk_ctx *c) {
   if (!c) return SK_ERR_ARG;
   if (!c->staged) return fail(c, SK_ERR_STATE, "no staged sub-interval");
   const long long n = c->hi - c->lo;
-  k_accept<<<nblk(n, 256), 256, 0, c->stream>>>(c->I.p + c->lo, c->err.p + c->lo, c->stage_i.p + c->lo, c->stage_e.p + c->lo, n,
-                                                c->first_accept ? 1 : 0);
-  LAUNCH_CHECK();
+  if (c->first_accept) {
+    // I = 0 + I2, err = 0 + |I2-I1| exactly (src/quadrature.jl:174-175, :261-262): the staging buffer
+    // becomes the panel buffer, no pass over the data
+    std::swap(c->pan, c->stage);
+  } else {
+    k_accept_add<<<nblk(n, 256), 256, 0, c->stream>>>(c->pan.p + c->lo, c->stage.p + c->lo, n);
+    LAUNCH_CHECK();
+  }
   c->first_accept = false;
   c->staged = false;
   c->stats.n_accepted++;
@@ -776,12 +809,13 @@ int sk_panel_commit(sk_ctx *c) {
   if (!c) return SK_ERR_ARG;
   if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
   const long long n = c->hi - c->lo;
-  if (c->first_accept) {  // nothing was accepted: I = err = 0
-    CK(cudaMemsetAsync(c->I.p + c->lo, 0, sizeof(double) * n, c->stream));
-    CK(cudaMemsetAsync(c->err.p + c->lo, 0, sizeof(double) * n, c->stream));
-  }
-  k_commit<<<nblk(n, 256), 256, 0, c->stream>>>(c->ks.p + c->lo, c->errs.p + c->lo, c->I.p + c->lo, c->err.p + c->lo, n);
-  LAUNCH_CHECK();
+  if (c->first_accept)   // nothing was accepted: I = err = 0
+    CK(cudaMemsetAsync(c->pan.p + c->lo, 0, sizeof(sk_cplx) * n, c->stream));
+  // ks += I; errs += err (src/adaptive.jl:163-164) is deferred and fused with the convergence scan
+  // (k_commit_scan); any other consumer flushes it first.
+  c->commit_pending = true;
+  c->pend_lo = c->lo;
+  c->pend_hi = c->hi;
   c->stats.n_panels++;
   return SK_OK;
 }
@@ -796,20 +830,24 @@ int sk_converge_scan(sk_ctx *c, const sk_scan_args *a, int64_t *new_hi, double *
   init.max_unconv = c->lo - 1;
   c->h_scal->red = init;
   CK(cudaMemcpyAsync(c->d_red, &c->h_scal->red, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-  k_scan<<<nblk(n, 256), 256, 0, c->stream>>>(c->uxs.p + c->lo, c->I.p + c->lo, n, c->lo, a->trunc_a, a->trunc_num, a->xpow, a->tau,
-                                              a->criteria, c->d_red);
+  const int do_commit = (c->commit_pending && c->pend_lo == c->lo && c->pend_hi == c->hi) ? 1 : 0;
+  if (c->commit_pending && !do_commit) {
+    int rc = flush_commit(c);
+    if (rc != SK_OK) return rc;
+  }
+  k_commit_scan<<<nblk(n, 256), 256, 0, c->stream>>>(c->uxs.p + c->lo, c->pan.p + c->lo, c->res.p + c->lo, n, c->lo, do_commit,
+                                                     a->trunc_a, a->trunc_num, a->xpow, a->tau, a->criteria, c->d_red);
   LAUNCH_CHECK();
+  c->commit_pending = false;
   CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   const long long top = c->h_scal->red.max_unconv;      // 0-based index of the highest unconverged target, or lo-1
-  *new_hi = top + 1;                                      // 1-based
   double r = 0.0;
-  if (top >= c->lo) {
-    CK(cudaMemcpyAsync(&c->h_scal->r[0], c->uxs.p + top, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    r = c->h_scal->r[0];
-  }
+  if (top >= c->lo) std::memcpy(&r, &c->h_scal->red.rbits, sizeof(double));
+  *new_hi = top + 1;                                      // 1-based
   if (r_at_new_hi) *r_at_new_hi = r;
+  c->scan_hi = top + 1;
+  c->scan_r = r;
   return SK_OK;
 }
 
@@ -817,9 +855,11 @@ int sk_converge_apply(sk_ctx *c, const sk_scan_args *a, int64_t new_hi) {
   if (!c || !a) return SK_ERR_ARG;
   if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
   if (new_hi < c->lo || new_hi > c->hi) return fail(c, SK_ERR_ARG, "new_hi outside the panel range");
+  int rc = flush_commit(c);
+  if (rc != SK_OK) return rc;
   const long long nconv = c->hi - new_hi;                 // 0-based indices new_hi .. hi-1
   if (nconv > 0 && a->criteria != SK_CRIT_PANEL) {
-    k_scan_add<<<nblk(nconv, 256), 256, 0, c->stream>>>(c->uxs.p + new_hi, c->errs.p + new_hi, nconv, a->trunc_a, a->trunc_num,
+    k_scan_add<<<nblk(nconv, 256), 256, 0, c->stream>>>(c->uxs.p + new_hi, c->res.p + new_hi, nconv, a->trunc_a, a->trunc_num,
                                                         a->xpow, a->criteria);
     LAUNCH_CHECK();
   }
@@ -841,7 +881,9 @@ int sk_target_upper_index(sk_ctx *c, double r, int64_t *idx) {
 int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
   if (!c || !vals_dev) return SK_ERR_ARG;
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
-  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->ks.p, c->errs.p, c->n_in, vals_dev, errs_dev);
+  int rc = flush_commit(c);
+  if (rc != SK_OK) return rc;
+  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, vals_dev, errs_dev);
   LAUNCH_CHECK();
   CK(cudaStreamSynchronize(c->stream));
   return SK_OK;
@@ -851,13 +893,21 @@ int sk_results_get(sk_ctx *c, double *vals, double *errs) {
   if (!c || !vals) return SK_ERR_ARG;
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
   CK(cudaSetDevice(c->device));
+  int rc = flush_commit(c);
+  if (rc != SK_OK) return rc;
   CK(c->out_v.ensure(c->n_in));
   if (errs) CK(c->out_e.ensure(c->n_in));
-  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->ks.p, c->errs.p, c->n_in, c->out_v.p, errs ? c->out_e.p : nullptr);
+  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, c->out_v.p, errs ? c->out_e.p : nullptr);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(vals, c->out_v.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
   if (errs) CK(cudaMemcpyAsync(errs, c->out_e.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  return SK_OK;
+}
+
+int sk_ctx_set_interp_mode(sk_ctx *c, int mode) {
+  if (!c || mode < 0 || mode > 1) return SK_ERR_ARG;
+  c->interp_mode = mode;
   return SK_OK;
 }
 

@@ -1,18 +1,23 @@
 // sk_kernels.cuh -- sm_100a kernels of the K(r) path.  Each kernel is a launch wrapper around the
-// per-element functions of sk_math.h plus the block-level cooperation (reductions, atomics).
+// per-element functions of sk_math.h plus the block-level cooperation (shared memory, reductions).
 //
-//   K1  k_gen_sources      updatequadbufs!                      src/quadrature.jl:49-95
-//   K2  k_prep_sources     source positions / pre-phase         (inside nufft1d3, src/utils.jl:10)
-//       k_spread_modes     ES spread (deterministic gather) + mode deconvolution + zero-pad
-//   K3  cuFFT Z2Z          (sk_api.cu)
-//   K4  k_interp_session   ES interpolation at the targets, target-side deconvolution, post-phase,
-//                          Re/Im select, *c, |I2-I1|, block max     src/quadrature.jl:130-136, :250-258
-//       k_interp_cplx      same, complex output (Level-0 sk_nufft1d3)
-//   K5  k_accept           I += I2; err += |I2-I1|              src/quadrature.jl:260-262
-//       k_commit           ks += I; errs += err                 src/adaptive.jl:163-164
-//   K6  k_scan, k_scan_add convergence scan                     src/adaptive.jl:183-199
-//   K7  k_direct           direct Fourier summation             src/quadrature.jl:113-128
-//   K8  k_make_keys, k_flag_heads, k_scatter_unique, k_gather   unique/sort/scatter, src/adaptive.jl:99-120
+//   K1  k_gen_sources       updatequadbufs!                       src/quadrature.jl:49-95
+//   K2  k_prep_sources      source positions / pre-phase          (inside nufft1d3, src/utils.jl:10)
+//       k_spread_modes      ES spread (deterministic gather, 8 lanes per grid point) + mode
+//                           deconvolution + zero-pad
+//   K3  cuFFT Z2Z           (sk_api.cu)
+//   K4  k_interp_cells      targets -> cell polynomials in shared memory -> Horner; target-side
+//                           deconvolution, post-phase, Re/Im select, *c, |I2-I1|, block max
+//                                                                 src/quadrature.jl:130-136, :250-258
+//       k_interp_session    per-target ES taps (reference-style evaluation; A/B and sparse fallback)
+//       k_interp_cplx       complex output (Level-0 sk_nufft1d3)
+//   K5  k_accept_add        I += I2; err += |I2-I1|               src/quadrature.jl:260-262
+//   K6  k_commit_scan       ks += I; errs += err fused with the convergence predicate
+//                                                                 src/adaptive.jl:163-164, :183-199
+//       k_scan_add          errs += 2 trunc_err for the converged tail   src/adaptive.jl:194
+//   K7  k_direct            direct Fourier summation              src/quadrature.jl:113-128
+//   K8  k_make_keys, k_flag_heads, k_scatter_unique, k_target_summary, k_gather
+//                           unique/sort/scatter                   src/adaptive.jl:99-120
 #pragma once
 #include <cuda_runtime.h>
 
@@ -27,12 +32,55 @@ struct SkReduceOut {            // device scalars written by the reductions
   unsigned int flags;
   unsigned int _pad;
   long long max_unconv;         // highest non-converged 0-based index, or lo-1
+  unsigned long long rbits;     // bit pattern of the distance at that index (0 if none)
+};
+
+struct SkTargetSummary {        // written by k_target_summary
+  long long n_unique;
+  double r0, r1, r_last;        // smallest, second smallest and largest unique distance
+  unsigned int bad;
+  unsigned int _pad;
 };
 
 __device__ __forceinline__ double sk_warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// block max of |I2-I1| (src/quadrature.jl:258) and NaN flags -> device scalars
+__device__ __forceinline__ void sk_block_reduce_maxflags(double d, unsigned int fl, SkReduceOut *red) {
+  __shared__ double smax[32];
+  __shared__ unsigned int sfl[32];
+  d = sk_warp_max(d);
+  fl = __reduce_or_sync(0xffffffffu, fl);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { smax[wid] = d; sfl[wid] = fl; }
+  __syncthreads();
+  if (wid == 0) {
+    d = lane < nw ? smax[lane] : 0.0;
+    fl = lane < nw ? sfl[lane] : 0u;
+    d = sk_warp_max(d);
+    fl = __reduce_or_sync(0xffffffffu, fl);
+    if (lane == 0) {
+      atomicMax(&red->maxbits, (unsigned long long)__double_as_longlong(d));
+      if (fl) atomicOr(&red->flags, fl);
+    }
+  }
+}
+
+// staging of one target: I2 and |I2-I1| (src/quadrature.jl:250-257) as one 16-byte store
+__device__ __forceinline__ void sk_stage(double f1, double f2, double cmul, sk_cplx *dst, double &d, unsigned int &fl) {
+  const double i1 = f1 * cmul, i2 = f2 * cmul;
+  double dd = fabs(i2 - i1);
+  if (i1 != i1) fl |= SK_FLAG_NAN1;
+  if (i2 != i2) fl |= SK_FLAG_NAN2;
+  sk_cplx o;
+  o.x = i2;
+  o.y = dd;
+  *dst = o;
+  if (dd != dd) { fl |= SK_FLAG_NAND; dd = 0.0; }
+  d = fmax(d, dd);
 }
 
 // ---- K1 ---------------------------------------------------------------------------------------------
@@ -64,31 +112,77 @@ __global__ void k_prep_sources(const __grid_constant__ SkGeom G, long long M, co
   cs[k] = c;
 }
 
-// One thread per FFT-input element j of rule blockIdx.y.  Gather: each element sums, in source
-// order, the sources whose kernel support covers it -- bitwise reproducible, no atomics.
+// Spread + mode deconvolution + zero-pad.  Gather: every FFT-input element sums the sources whose
+// kernel support covers it -- no atomics, bitwise reproducible.  Gauss nodes cluster at the sub-panel
+// ends (hundreds of sources within one kernel width there), so SK_SPREAD_LANES lanes share one element:
+// lane t takes sources a+t, a+t+L, ... and the partial sums are combined in a fixed butterfly order.
+#define SK_SPREAD_LANES 8
 struct SkSpreadSrc {
   const double *pos_hi[2];
   const double *pos_lo[2];
   const sk_cplx *cs[2];
   long long M[2];
 };
-__global__ void k_spread_modes(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G,
-                               const __grid_constant__ SkSpreadSrc src, int nrule, sk_cplx *__restrict__ fft_io) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+k_spread_modes(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G,
+               const __grid_constant__ SkSpreadSrc src, int nrule, sk_cplx *__restrict__ fft_io) {
+  const int sub = threadIdx.x & (SK_SPREAD_LANES - 1);
+  long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / SK_SPREAD_LANES;
   const int r = blockIdx.y;
-  if (j >= G.nf2) return;
-  sk_cplx o;
-  sk_spread_mode(P, G, j, src.pos_hi[r], src.pos_lo[r], src.cs[r], src.M[r], &o.x, &o.y);
-  fft_io[j * nrule + r] = o;
+  const bool in_range = j < G.nf2;                          // whole lane groups agree; keep all lanes for the shuffles
+  if (!in_range) j = G.nf2 - 1;
+  const long long n = (j < G.nf2 / 2) ? j : j - G.nf2;      // signed mode index
+  double ar = 0.0, ai = 0.0;
+  const bool live = in_range && !(n < -(G.nf / 2) || n >= G.nf / 2);
+  if (live) {
+    const double *__restrict__ ph = src.pos_hi[r];
+    const double *__restrict__ pl = src.pos_lo[r];
+    const sk_cplx *__restrict__ cs = src.cs[r];
+    const long long M = src.M[r];
+    const double ctr = (double)n, half = 0.5 * P.w;
+    const double lo_edge = ctr - half - 1e-6, hi_edge = ctr + half + 1e-6;
+    long long a = 0, b = M;
+    while (a < b) {                                         // first source with pos >= lo_edge
+      const long long mid = (a + b) >> 1;
+      if (ph[mid] < lo_edge) a = mid + 1; else b = mid;
+    }
+    const double inv_half = 1.0 / half;
+    for (long long k = a + sub; k < M; k += SK_SPREAD_LANES) {
+      const double p = ph[k];
+      if (p > hi_edge) break;
+      const double z = ((ctr - p) - pl[k]) * inv_half;
+      const double wgt = sk_es_direct(z, P.beta);
+      const sk_cplx c = cs[k];
+      ar = sk_fma(wgt, c.x, ar);
+      ai = sk_fma(wgt, c.y, ai);
+    }
+  }
+#pragma unroll
+  for (int o = SK_SPREAD_LANES / 2; o > 0; o >>= 1) {       // fixed-order butterfly inside the lane group
+    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+  }
+  if (sub == 0 && in_range) {
+    sk_cplx o;
+    o.x = 0.0;
+    o.y = 0.0;
+    if (live) {
+      double q = sk_deconv(P, G.t_cell * fabs((double)n));
+      if (n & 1) q = -q;                                    // shifts the FFT output by nf2/2
+      o.x = ar * q;
+      o.y = ai * q;
+    }
+    fft_io[j * nrule + r] = o;
+  }
 }
 
-// ---- K4 ---------------------------------------------------------------------------------------------
-// Session interpolation: both rules share the taps.  grid layout [nf2][2] (m-rule, 2m-rule).
+// ---- K4 (reference-style per-target taps) -------------------------------------------------------------
+// grid layout [nf2][2] (m-rule, 2m-rule); stage[j] = (I2, |I2-I1|)
 template <int W>
 __global__ void __launch_bounds__(256)
 k_interp_session(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G, const double *__restrict__ xs,
                  long long n, const sk_cplx *__restrict__ grid, double cmul, int kernel_sin,
-                 double *__restrict__ stage_i, double *__restrict__ stage_e, SkReduceOut *__restrict__ red) {
+                 sk_cplx *__restrict__ stage, SkReduceOut *__restrict__ red) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double d = 0.0;
   unsigned int fl = 0;
@@ -96,33 +190,91 @@ k_interp_session(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkG
     double fre[2], fim[2];
     sk_interp_point<W, 2>(P, G, xs[j], grid, fre, fim);
     // kernel == :cos -> real part, :sin -> imaginary part (src/quadrature.jl:130-136); then *c (:250-251)
-    const double i1 = (kernel_sin ? fim[0] : fre[0]) * cmul;
-    const double i2 = (kernel_sin ? fim[1] : fre[1]) * cmul;
-    d = fabs(i2 - i1);                                          // :257
-    if (i1 != i1) fl |= SK_FLAG_NAN1;
-    if (i2 != i2) fl |= SK_FLAG_NAN2;
-    if (d != d) { fl |= SK_FLAG_NAND; d = 0.0; }
-    stage_i[j] = i2;
-    stage_e[j] = d;
+    sk_stage(kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, &stage[j], d, fl);
   }
-  // block max of |I2-I1| (src/quadrature.jl:258) and NaN flags
-  __shared__ double smax[8];
-  __shared__ unsigned int sfl[8];
-  d = sk_warp_max(d);
-  fl = __reduce_or_sync(0xffffffffu, fl);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) { smax[wid] = d; sfl[wid] = fl; }
-  __syncthreads();
-  if (wid == 0) {
-    d = lane < (blockDim.x >> 5) ? smax[lane] : 0.0;
-    fl = lane < (blockDim.x >> 5) ? sfl[lane] : 0u;
-    d = sk_warp_max(d);
-    fl = __reduce_or_sync(0xffffffffu, fl);
-    if (lane == 0) {
-      atomicMax(&red->maxbits, (unsigned long long)__double_as_longlong(d));
-      if (fl) atomicOr(&red->flags, fl);
+  sk_block_reduce_maxflags(d, fl, red);
+}
+
+// ---- K4 (cell polynomials) -----------------------------------------------------------------------------
+// One block = SK_TPB consecutive sorted targets.  Sorted targets touch a contiguous run of fine-grid
+// cells; when the run is short enough (ncell <= cmax) the block
+//   A. stages the grid window [l_first, l_last + W) of both rules in shared memory (coalesced),
+//   B. turns it into SK_NC polynomial coefficients x 4 components (re/im x two rules) per cell,
+//   C. evaluates every target by Horner from shared memory (broadcast reads inside a cell).
+// Otherwise (sparse targets) it falls back to per-target taps straight from L2.
+#define SK_TPT 4
+#define SK_TPB (256 * SK_TPT)
+template <int W>
+__global__ void __launch_bounds__(256, 3)
+k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G, const double *__restrict__ xs,
+               long long n, const sk_cplx *__restrict__ grid, double cmul, int kernel_sin, int cmax,
+               sk_cplx *__restrict__ stage, SkReduceOut *__restrict__ red) {
+  extern __shared__ __align__(16) double smem[];
+  double *sE = smem;                                   // [W/2][SK_NC/2]
+  double *sO = sE + (W / 2) * (SK_NC / 2);
+  double *sWin = sO + (W / 2) * (SK_NC / 2);            // [(cmax + W)][4]
+  double *sCoef = sWin + (size_t)(cmax + W) * 4;        // [cmax][SK_NC][4]
+  const long long j0 = (long long)blockIdx.x * SK_TPB;
+  const int cnt = (int)((n - j0) < (long long)SK_TPB ? (n - j0) : (long long)SK_TPB);
+  const long long l_first = sk_target_coord<W>(G, xs[j0]).l0;
+  const long long l_last = sk_target_coord<W>(G, xs[j0 + cnt - 1]).l0;
+  const long long ncell_ll = l_last - l_first + 1;
+  double d = 0.0;
+  unsigned int fl = 0;
+  if (ncell_ll >= 1 && ncell_ll <= (long long)cmax) {
+    const int ncell = (int)ncell_ll;
+    for (int t = threadIdx.x; t < (W / 2) * (SK_NC / 2); t += blockDim.x) {
+      sE[t] = P.E[t / (SK_NC / 2)][t % (SK_NC / 2)];
+      sO[t] = P.O[t / (SK_NC / 2)][t % (SK_NC / 2)];
+    }
+    // A: window of (ncell + W - 1) grid points x 2 rules, 32 bytes per point
+    const double4 *gsrc = reinterpret_cast<const double4 *>(grid + (size_t)l_first * 2);
+    double4 *wdst = reinterpret_cast<double4 *>(sWin);
+    for (int t = threadIdx.x; t < ncell + W - 1; t += blockDim.x) wdst[t] = gsrc[t];
+    __syncthreads();
+    // B: coefficient (cell, q, comp) = W/2 FMAs
+    for (int t = threadIdx.x; t < ncell * SK_NC * 4; t += blockDim.x) {
+      const int comp = t & 3, q = (t >> 2) & (SK_NC - 1), cell = t / (SK_NC * 4);
+      sCoef[t] = sk_cell_coef<W>(sE, sO, sWin + cell * 4 + comp, 4, q);
+    }
+    __syncthreads();
+    // C: Horner per target
+#pragma unroll
+    for (int u = 0; u < SK_TPT; ++u) {
+      const int t = threadIdx.x + u * 256;
+      if (t < cnt) {
+        const double r = xs[j0 + t];
+        const SkTargetCoord tc = sk_target_coord<W>(G, r);
+        int cell = (int)(tc.l0 - l_first);
+        cell = cell < 0 ? 0 : (cell >= ncell ? ncell - 1 : cell);
+        double a[4];
+        sk_cell_horner<4>(sCoef + (size_t)cell * SK_NC * 4, tc.s, a);
+        const double qf = sk_deconv(P, G.t_cell * tc.yabs);
+        double sn, cs;
+        sk_post_phase(G, r, &sn, &cs);
+        double f1, f2;
+        if (kernel_sin) {
+          f1 = qf * (a[0] * sn + a[1] * cs);
+          f2 = qf * (a[2] * sn + a[3] * cs);
+        } else {
+          f1 = qf * (a[0] * cs - a[1] * sn);
+          f2 = qf * (a[2] * cs - a[3] * sn);
+        }
+        sk_stage(f1, f2, cmul, &stage[j0 + t], d, fl);
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int u = 0; u < SK_TPT; ++u) {
+      const int t = threadIdx.x + u * 256;
+      if (t < cnt) {
+        double fre[2], fim[2];
+        sk_interp_point<W, 2>(P, G, xs[j0 + t], grid, fre, fim);
+        sk_stage(kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, &stage[j0 + t], d, fl);
+      }
     }
   }
+  sk_block_reduce_maxflags(d, fl, red);
 }
 
 template <int W>
@@ -164,82 +316,95 @@ k_direct(const double *__restrict__ no1, const double *__restrict__ buf1, long l
   if (threadIdx.x == 0) { sk_cplx o; o.x = sr[0]; o.y = si[0]; sums[(long long)blockIdx.x * 2 + r] = o; }
 }
 
-// epilogue of the direct branch: same staging as k_interp_session (single block, n is tiny)
+// epilogue of the direct branch: same staging as the interpolation kernels (single block, n is tiny)
 __global__ void k_direct_finish(const sk_cplx *__restrict__ sums, long long n, double cmul, int kernel_sin,
-                                double *__restrict__ stage_i, double *__restrict__ stage_e,
-                                SkReduceOut *__restrict__ red) {
+                                sk_cplx *__restrict__ stage, SkReduceOut *__restrict__ red) {
+  double d = 0.0;
+  unsigned int fl = 0;
   for (long long j = threadIdx.x; j < n; j += blockDim.x) {
     const sk_cplx f1 = sums[2 * j], f2 = sums[2 * j + 1];
-    const double i1 = (kernel_sin ? f1.y : f1.x) * cmul;
-    const double i2 = (kernel_sin ? f2.y : f2.x) * cmul;
-    double d = fabs(i2 - i1);
-    unsigned int fl = 0;
-    if (i1 != i1) fl |= SK_FLAG_NAN1;
-    if (i2 != i2) fl |= SK_FLAG_NAN2;
-    if (d != d) { fl |= SK_FLAG_NAND; d = 0.0; }
-    stage_i[j] = i2;
-    stage_e[j] = d;
-    atomicMax(&red->maxbits, (unsigned long long)__double_as_longlong(d));
-    if (fl) atomicOr(&red->flags, fl);
+    sk_stage(kernel_sin ? f1.y : f1.x, kernel_sin ? f2.y : f2.x, cmul, &stage[j], d, fl);
   }
+  sk_block_reduce_maxflags(d, fl, red);
 }
 
 // ---- K5 ---------------------------------------------------------------------------------------------
-__global__ void k_accept(double *__restrict__ I, double *__restrict__ err, const double *__restrict__ stage_i,
-                         const double *__restrict__ stage_e, long long n, int first) {
+// pan = (I, err), stage = (I2, |I2-I1|):  I += I2; err += |I2-I1|   (src/quadrature.jl:261-262).
+// The first accepted sub-interval of a panel is not added at all: the staging buffer BECOMES the panel
+// buffer (pointer swap on the host; 0 + x == x exactly).
+__global__ void k_accept_add(sk_cplx *__restrict__ pan, const sk_cplx *__restrict__ stage, long long n) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  if (first) {            // I = 0 + I2 exactly (I, err start at zero: src/quadrature.jl:174-175)
-    I[j] = stage_i[j];
-    err[j] = stage_e[j];
-  } else {
-    I[j] += stage_i[j];   // :261
-    err[j] += stage_e[j]; // :262
-  }
-}
-
-__global__ void k_commit(double *__restrict__ ks, double *__restrict__ errs, const double *__restrict__ I,
-                         const double *__restrict__ err, long long n) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  ks[j] += I[j];        // src/adaptive.jl:163
-  errs[j] += err[j];    // :164
+  sk_cplx p = pan[j];
+  const sk_cplx s = stage[j];
+  p.x += s.x;
+  p.y += s.y;
+  pan[j] = p;
 }
 
 // ---- K6 ---------------------------------------------------------------------------------------------
-// The reference walks ix = hi, hi-1, ... while converged (src/adaptive.jl:185-197).  Equivalent:
-// new_hi = the largest index whose predicate is false.  lo0 is the 0-based global index of element 0.
+// res = (ks, errs) += pan = (I, err)  (src/adaptive.jl:163-164), fused with the convergence predicate of
+// src/adaptive.jl:185-197 on panel_ks = I.  The reference walks ix = hi, hi-1, ... while converged;
+// equivalently new_hi is the largest index whose predicate is false.  lo0 = global 0-based index of
+// element 0.  do_commit = 0 runs the scan only.
 __global__ void __launch_bounds__(256)
-k_scan(const double *__restrict__ xs, const double *__restrict__ I, long long n, long long lo0, double trunc_a,
-       double trunc_num, double xpow, double tau, int criteria, SkReduceOut *__restrict__ red) {
+k_commit_scan(const double *__restrict__ xs, const sk_cplx *__restrict__ pan, sk_cplx *__restrict__ res, long long n,
+              long long lo0, int do_commit, double trunc_a, double trunc_num, double xpow, double tau, int criteria,
+              SkReduceOut *__restrict__ red) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long bad = -1;
+  unsigned long long rb = 0;
   if (j < n) {
-    const double te = sk_trunc_err(trunc_a, trunc_num, xpow, xs[j], criteria == 0);
-    if (!sk_converged(te, I[j], tau, criteria)) bad = lo0 + j;
+    const sk_cplx p = pan[j];
+    if (do_commit) {
+      sk_cplx r = res[j];
+      r.x += p.x;
+      r.y += p.y;
+      res[j] = r;
+    }
+    const double x = xs[j];
+    const double te = sk_trunc_err(trunc_a, trunc_num, xpow, x, criteria == 0);
+    if (!sk_converged(te, p.x, tau, criteria)) { bad = lo0 + j; rb = (unsigned long long)__double_as_longlong(x); }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    const long long other = __shfl_xor_sync(0xffffffffu, bad, o);
-    bad = other > bad ? other : bad;
+    const long long ob = __shfl_xor_sync(0xffffffffu, bad, o);
+    const unsigned long long orb = __shfl_xor_sync(0xffffffffu, rb, o);
+    if (ob > bad) { bad = ob; rb = orb; }
   }
   __shared__ long long sb[8];
+  __shared__ unsigned long long srb[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) sb[wid] = bad;
+  if (lane == 0) { sb[wid] = bad; srb[wid] = rb; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) bad = sb[w] > bad ? sb[w] : bad;
-    if (bad >= 0) atomicMax(&red->max_unconv, bad);
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (sb[w] > bad) { bad = sb[w]; rb = srb[w]; }
+    if (bad >= 0) {                       // sorted unique distances: max index <=> max distance
+      atomicMax(&red->max_unconv, bad);
+      atomicMax(&red->rbits, rb);
+    }
   }
 }
 
+// plain commit (no scan follows, e.g. a flush before reading results)
+__global__ void k_commit(const sk_cplx *__restrict__ pan, sk_cplx *__restrict__ res, long long n) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  sk_cplx r = res[j];
+  const sk_cplx p = pan[j];
+  r.x += p.x;
+  r.y += p.y;
+  res[j] = r;
+}
+
 // errs[ix] += 2*trunc_err for the converged tail (src/adaptive.jl:194)
-__global__ void k_scan_add(const double *__restrict__ xs, double *__restrict__ errs, long long n, double trunc_a,
+__global__ void k_scan_add(const double *__restrict__ xs, sk_cplx *__restrict__ res, long long n, double trunc_a,
                            double trunc_num, double xpow, int criteria) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const double te = sk_trunc_err(trunc_a, trunc_num, xpow, xs[j], criteria == 0);
-  errs[j] += 2 * te;
+  res[j].y += 2 * te;
 }
 
 // ---- K8 ---------------------------------------------------------------------------------------------
@@ -272,14 +437,24 @@ __global__ void k_scatter_unique(const unsigned long long *__restrict__ keys, co
   inv[idx[j]] = u;
 }
 
-__global__ void k_gather(const unsigned int *__restrict__ inv, const double *__restrict__ ks,
-                         const double *__restrict__ errs, long long n, double *__restrict__ out_v,
-                         double *__restrict__ out_e) {
+__global__ void k_target_summary(const double *__restrict__ uxs, const unsigned int *__restrict__ uid_incl, long long n,
+                                 const unsigned int *__restrict__ bad, SkTargetSummary *__restrict__ out) {
+  const long long nu = uid_incl[n - 1];
+  out->n_unique = nu;
+  out->r0 = uxs[0];
+  out->r1 = nu > 1 ? uxs[1] : 0.0;
+  out->r_last = uxs[nu - 1];
+  out->bad = *bad;
+}
+
+// values and errors in the original input order from res = (ks, errs): one 16-byte random read per target
+__global__ void k_gather(const unsigned int *__restrict__ inv, const sk_cplx *__restrict__ res, long long n,
+                         double *__restrict__ out_v, double *__restrict__ out_e) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const unsigned int u = inv[j];
-  out_v[j] = ks[u];
-  if (out_e) out_e[j] = errs[u];
+  const sk_cplx r = res[inv[j]];
+  out_v[j] = r.x;
+  if (out_e) out_e[j] = r.y;
 }
 
 // number of sorted values <= r (== the largest 1-based index with xs[idx] <= r)
@@ -292,9 +467,9 @@ __global__ void k_upper_bound(const double *__restrict__ xs, long long n, double
   *out = a;
 }
 
-__global__ void k_fill(double *__restrict__ a, long long n, double v) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) a[j] = v;
+__global__ void k_set_zero_lag(sk_cplx *__restrict__ res, double v) {
+  res[0].x = v;
+  res[0].y = nan("");
 }
 
 // ---- FP64 pipe micro-benchmark (roofline denominator) -------------------------------------------------

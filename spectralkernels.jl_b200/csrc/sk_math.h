@@ -312,6 +312,39 @@ SK_HD void sk_interp_point(const SkEsPlan &P, const SkGeom &G, double r, const s
   }
 }
 
+// ---- cell polynomials ---------------------------------------------------------------------------------
+// All targets whose w-wide window starts at the same fine-grid index ("cell") see the same w grid
+// values, so  sum_i tap_i(s) g_i = sum_q C_q s^q  with coefficients that depend on the cell only:
+//   C_{2q'}   = sum_{i<w/2} E_i[q'] (g_i + g_{w-1-i}),   C_{2q'+1} = sum_{i<w/2} O_i[q'] (g_i - g_{w-1-i}).
+// With many targets per cell (N >> nf2: 1e7 targets on ~6.6e4 used cells) the per-target work drops
+// from w tap polynomials + w complex MACs to one degree-(SK_NC-1) Horner per component.
+// g: window of W points, `stride` doubles between consecutive points, component `comp` selected by offset.
+template <int W>
+SK_HD double sk_cell_coef(const double *E, const double *O, const double *g, int stride, int q) {
+  const int qh = q >> 1;
+  const bool odd = q & 1;
+  const double *T = odd ? O : E;   // flattened [W/2][SK_NC/2]
+  double acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < W / 2; ++i) {
+    const double a = g[i * stride], b = g[(W - 1 - i) * stride];
+    acc = sk_fma(T[i * (SK_NC / 2) + qh], odd ? (a - b) : (a + b), acc);
+  }
+  return acc;
+}
+
+// Horner in s on NCOMP interleaved components; coef layout [SK_NC][NCOMP]
+template <int NCOMP>
+SK_HD void sk_cell_horner(const double *coef, double s, double *out) {
+#pragma unroll
+  for (int c = 0; c < NCOMP; ++c) out[c] = coef[(SK_NC - 1) * NCOMP + c];
+#pragma unroll
+  for (int q = SK_NC - 2; q >= 0; --q) {
+#pragma unroll
+    for (int c = 0; c < NCOMP; ++c) out[c] = sk_fma(out[c], s, coef[q * NCOMP + c]);
+  }
+}
+
 // ---- convergence predicate, src/adaptive.jl:222-233 -------------------------------------------------
 // trunc_a, trunc_num are computed on the host (they do not depend on the target).
 SK_HD double sk_trunc_err(double trunc_a, double trunc_num, double xpow, double x, int criteria_panel) {

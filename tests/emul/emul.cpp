@@ -4,6 +4,7 @@
 // a machine without a GPU.  It is not a product path: nothing in spectralkernels.jl_b200/ loads it.
 #include "sk_host_util.h"
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -32,6 +33,69 @@ void emul_interp(const SkEsPlan *P, const SkGeom *G, long long N, const double *
   std::memcpy(g.data(), grid, sizeof(sk_cplx) * G->nf2);
 #pragma omp parallel for schedule(static)
   for (long long j = 0; j < N; ++j) sk_interp_point<16, 1>(*P, *G, r[j], g.data(), &out[2 * j], &out[2 * j + 1]);
+}
+
+// the block algorithm of k_interp_cells (csrc/sk_kernels.cuh) in plain loops: two interleaved grids
+// (layout [nf2][2]), sorted targets, blocks of `tpb` targets, cell polynomials when a block spans at
+// most cmax cells, per-target taps otherwise.  out: [N][2] complex (rule 0, rule 1).  Returns the
+// number of blocks that took the cell-polynomial path.
+long long emul_interp_cells(const SkEsPlan *P, const SkGeom *G, long long N, const double *r, const double *grid2,
+                            int tpb, int cmax, double *out) {
+  const int W = 16;
+  std::vector<sk_cplx> g((size_t)G->nf2 * 2);
+  std::memcpy(g.data(), grid2, sizeof(sk_cplx) * G->nf2 * 2);
+  std::vector<double> E(8 * 8), O(8 * 8);
+  for (int i = 0; i < 8; ++i) for (int q = 0; q < 8; ++q) { E[i * 8 + q] = P->E[i][q]; O[i * 8 + q] = P->O[i][q]; }
+  long long npoly = 0;
+  for (long long j0 = 0; j0 < N; j0 += tpb) {
+    const int cnt = (int)std::min<long long>(tpb, N - j0);
+    const long long lf = sk_target_coord<W>(*G, r[j0]).l0, ll = sk_target_coord<W>(*G, r[j0 + cnt - 1]).l0;
+    const long long ncell = ll - lf + 1;
+    if (ncell >= 1 && ncell <= cmax) {
+      ++npoly;
+      const double *win = reinterpret_cast<const double *>(g.data() + (size_t)lf * 2);   // [ncell+W-1][4]
+      std::vector<double> coef((size_t)ncell * SK_NC * 4);
+      for (long long t = 0; t < ncell * SK_NC * 4; ++t) {
+        const int comp = t & 3, q = (t >> 2) & (SK_NC - 1);
+        const long long cell = t / (SK_NC * 4);
+        coef[t] = sk_cell_coef<W>(E.data(), O.data(), win + cell * 4 + comp, 4, q);
+      }
+      for (int t = 0; t < cnt; ++t) {
+        const double rr = r[j0 + t];
+        const SkTargetCoord tc = sk_target_coord<W>(*G, rr);
+        long long cell = tc.l0 - lf;
+        double a[4];
+        sk_cell_horner<4>(coef.data() + (size_t)cell * SK_NC * 4, tc.s, a);
+        const double qf = sk_deconv(*P, G->t_cell * tc.yabs);
+        double sn, cs;
+        sk_post_phase(*G, rr, &sn, &cs);
+        double *o = out + (j0 + t) * 4;
+        o[0] = qf * (a[0] * cs - a[1] * sn); o[1] = qf * (a[0] * sn + a[1] * cs);
+        o[2] = qf * (a[2] * cs - a[3] * sn); o[3] = qf * (a[2] * sn + a[3] * cs);
+      }
+    } else {
+      for (int t = 0; t < cnt; ++t) {
+        double fre[2], fim[2];
+        sk_interp_point<W, 2>(*P, *G, r[j0 + t], g.data(), fre, fim);
+        double *o = out + (j0 + t) * 4;
+        o[0] = fre[0]; o[1] = fim[0]; o[2] = fre[1]; o[3] = fim[1];
+      }
+    }
+  }
+  return npoly;
+}
+
+// per-target taps on two interleaved grids (the k_interp_session body)
+void emul_interp2(const SkEsPlan *P, const SkGeom *G, long long N, const double *r, const double *grid2, double *out) {
+  std::vector<sk_cplx> g((size_t)G->nf2 * 2);
+  std::memcpy(g.data(), grid2, sizeof(sk_cplx) * G->nf2 * 2);
+#pragma omp parallel for schedule(static)
+  for (long long j = 0; j < N; ++j) {
+    double fre[2], fim[2];
+    sk_interp_point<16, 2>(*P, *G, r[j], g.data(), fre, fim);
+    double *o = out + j * 4;
+    o[0] = fre[0]; o[1] = fim[0]; o[2] = fre[1]; o[3] = fim[1];
+  }
 }
 
 // updatequadbufs! on the "device" generator

@@ -89,6 +89,46 @@ def test_type3_math_general_geometry(emul):
     assert np.max(np.abs(f - so.direct_cis(np.array([7.0]), np.array([1.0 + 2j]), np.array([0.25, 0.5])))) < 1e-13
 
 
+def test_cell_polynomial_interpolation(emul):
+    """k_interp_cells' block algorithm (cell polynomials in place of per-target taps) against the
+    per-target evaluation and against direct sums, for dense, clustered and sparse sorted targets."""
+    L, P = emul
+    L.emul_interp_cells.restype = ctypes.c_longlong
+    L.emul_interp_cells.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, dp, dp, ctypes.c_int,
+                                    ctypes.c_int, dp]
+    L.emul_interp2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, dp, dp, dp]
+    rng = np.random.default_rng(2)
+    cfg = so.OracleConfig(lambda w: (1 + w ** 2) ** -2)
+    no1, buf1, no2, buf2 = so.updatequadbufs(cfg, cfg.f, 0.0, 32768.0)
+    for name, x in (("dense", np.sort(rng.uniform(0.3, 0.3005, 4000))),
+                    ("mixed", np.sort(np.concatenate([rng.uniform(0, 1, 1500), rng.uniform(0.6, 0.6002, 2500)]))),
+                    ("sparse", np.sort(rng.uniform(1e-4, 1.0, 700)))):
+        x[-1] = 1.0
+        G = Geom()
+        assert L.emul_geom(ctypes.byref(P), 0.0, 32768.0, x.min(), x.max(), ctypes.byref(G)) == 0
+        grid2 = np.zeros((G.nf2, 2), dtype=complex)
+        for rule, (no, buf) in enumerate(((no1, buf1), (no2, buf2))):
+            fin = np.zeros(G.nf2, dtype=complex)
+            cc = np.ascontiguousarray(buf.astype(complex))
+            L.emul_spread(ctypes.byref(P), ctypes.byref(G), no.size, _ptr(no), _ptr(cc.view(float)), _ptr(fin.view(float)))
+            grid2[:, rule] = np.fft.ifft(fin) * G.nf2
+        grid2 = np.ascontiguousarray(grid2)
+        ref = np.zeros((x.size, 2), dtype=complex)
+        L.emul_interp2(ctypes.byref(P), ctypes.byref(G), x.size, _ptr(x), _ptr(grid2.view(float)), _ptr(ref.view(float)))
+        out = np.zeros((x.size, 2), dtype=complex)
+        npoly = L.emul_interp_cells(ctypes.byref(P), ctypes.byref(G), x.size, _ptr(x), _ptr(grid2.view(float)), 1024, 32,
+                                    _ptr(out.view(float)))
+        nblocks = -(-x.size // 1024)
+        if name == "dense":
+            assert npoly >= nblocks - 1      # the last block also holds x = 1.0
+        if name == "sparse":
+            assert npoly == 0
+        scale = np.sum(np.abs(buf2))
+        assert np.max(np.abs(out - ref)) <= 4e-15 * scale, name
+        sub = slice(None, None, 40)
+        assert np.max(np.abs(out[sub, 1] - so.direct_cis(no2, buf2, x[sub]))) <= 5e-13 * scale
+
+
 def test_device_source_generator_matches_updatequadbufs(emul):
     """sk_gen_source (the K1 body) against the oracle's updatequadbufs (quadrature.jl:49-95)."""
     L, _ = emul

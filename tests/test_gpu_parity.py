@@ -88,7 +88,10 @@ def test_device_sources_match_updatequadbufs(sk, sess, alpha, a, b):
     S = sk.Matern(*parms)
     ocfg = so.OracleConfig(lambda w: cf.matern_sdf(w, parms), alpha=alpha)
     p = ocfg.p
-    sess.rule_set(4096, 16, p)
+    # the host passes its own rules (as the Julia host passes FastGaussQuadrature's), so that the
+    # comparison isolates the device generator
+    lr, jr = ocfg.legrule, ocfg.jacrule
+    sess.rule_set(4096, 16, p, leg=(lr.no1, lr.wt1, lr.no2, lr.wt2), jac=(jr.no1, jr.wt1, jr.no2, jr.wt2))
     sess.sdf_builtin(S.family, S.params, 0)
     sess.targets_set(np.linspace(0.01, 1.0, 50))
     sess.run_begin()
@@ -102,8 +105,7 @@ def test_device_sources_match_updatequadbufs(sk, sess, alpha, a, b):
     for rule in (0, 1):
         no, buf = sess.sources_get(rule)
         assert np.array_equal(no, ref[2 * rule])                                   # nodes bit-exact
-        assert np.max(np.abs(buf - ref[2 * rule + 1])) <= 4e-14 * np.max(np.abs(ref[2 * rule + 1]))   # pow() ulps
-        assert np.max(np.abs(buf / ref[2 * rule + 1] - 1)) <= 1e-13
+        assert np.max(np.abs(buf / ref[2 * rule + 1] - 1)) <= 2e-15                 # pow() ulps only
 
 
 # ---- end to end against the oracle: values and panel traces ---------------------------------------------------
@@ -171,6 +173,23 @@ def test_singular_matern_golden_and_oracle(sk, golden, tol):
     assert np.all(np.abs(vg - golden["sing_K"][i]) / k0 <= 10 * tol)
     assert np.max(np.abs(vg - vo)) <= 1e-11 * k0
     assert _trace_key(tg) == _trace_key(to)
+
+
+def test_interp_modes_agree(sk):
+    """k_interp_cells (cell polynomials) against k_interp_session (per-target taps): same polynomial,
+    reassociated -- agreement at rounding level; same traces."""
+    rng = np.random.default_rng(11)
+    xs = np.concatenate([rng.uniform(0, 1, 200_000), rng.uniform(0.25, 0.2501, 100_000), 10 ** rng.uniform(-6, 0, 3000)])
+    out = []
+    for mode in (0, 1):
+        cfg = sk.AdaptiveKernelConfig(sk.Matern(1.0, 1.0, 1.5))
+        cfg.engine.set_interp_mode(mode)
+        tr = []
+        v, e = sk.kernel_values(cfg, xs, k0=np.pi / 2, trace=tr)
+        out.append((v, e, tr))
+    assert np.max(np.abs(out[0][0] - out[1][0])) <= 1e-14 * (np.pi / 2)
+    assert _trace_key(out[0][2]) == _trace_key(out[1][2])
+    assert np.max(np.abs(out[0][0] - cf.readme_cov(xs))) <= 1e-8 * (np.pi / 2)
 
 
 def test_host_callable_equals_builtin(sk, golden):

@@ -1,0 +1,108 @@
+"""
+world_size-2 gloo tests of the host logic of a target-sharded kernel_values run: every rank holds its
+own chunk of the distances, the adaptive loop runs in lock step through scalar all-reduces
+(spectralkernels.jl_b200/sharded.py), and the result equals the single-process run over the union --
+values bit-for-bit, panel traces identical.  Per-target work is done by tests/fake_engine.py (oracle
+direct sums) because there is no GPU here; the driver under test is the product's.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, chunks, kw, ret):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    import spectralkernels_jl_b200 as sk
+    from spectralkernels_jl_b200.sharded import TorchComm
+    from fake_engine import FakeEngine
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        S = lambda w: np.exp(-np.abs(w)) if kw.get("sdf") == "exp" else (0.25 + w ** 2) ** -1.05
+        cfg = sk.AdaptiveKernelConfig(S, engine=FakeEngine(), quadspec=(256, 4), **kw.get("cfg", {}))
+        comm = TorchComm()
+        trace = []
+        vals, errs = sk.kernel_values(cfg, chunks[rank], k0=kw["k0"], comm=comm, trace=trace)
+        ret[rank] = (vals, errs, trace, comm.n_reductions)
+    finally:
+        dist.destroy_process_group()
+
+
+def _single(xs, kw):
+    import spectralkernels_jl_b200 as sk
+    from fake_engine import FakeEngine
+    S = lambda w: np.exp(-np.abs(w)) if kw.get("sdf") == "exp" else (0.25 + w ** 2) ** -1.05
+    cfg = sk.AdaptiveKernelConfig(S, engine=FakeEngine(), quadspec=(256, 4), **kw.get("cfg", {}))
+    trace = []
+    vals, errs = sk.kernel_values(cfg, xs, k0=kw["k0"], trace=trace)
+    return vals, errs, trace
+
+
+def _key(trace, with_hi=False):
+    subs = [(t["a"], t["b"], t["accepted"]) for t in trace if t["kind"] == "subinterval"]
+    pans = [(t["a"], t["b"], t["criteria"]) + ((t["hi_before"], t["hi_after"]) if with_hi else ())
+            for t in trace if t["kind"] == "panel"]
+    return subs, pans
+
+
+@pytest.mark.parametrize("case", ["slow_decay_logspaced", "exp_with_zero_and_empty_rank_tail"])
+def test_two_rank_gloo_equals_single(case):
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(5)
+    if case == "slow_decay_logspaced":
+        xs = 10 ** rng.uniform(-3, 0, 90)
+        chunks = [xs[:50], xs[50:]]
+        kw = {"k0": 5.9, "sdf": "matern"}
+    else:
+        # rank 1 only holds small distances: its active set empties panels before rank 0's does
+        xs = np.concatenate([rng.uniform(0.5, 3.0, 30), [0.0, 0.0], rng.uniform(1e-3, 2e-2, 25)])
+        chunks = [xs[:32], xs[32:]]
+        kw = {"k0": 2.0, "sdf": "exp"}
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, chunks, kw, ret), nprocs=2, join=True)
+    v1, e1, t1 = _single(xs, kw)
+    v2 = np.concatenate([ret[0][0], ret[1][0]])
+    e2 = np.concatenate([ret[0][1], ret[1][1]])
+    assert np.array_equal(v1, v2)                                  # bit-identical values
+    assert np.array_equal(np.isnan(e1), np.isnan(e2)) and np.array_equal(np.nan_to_num(e1), np.nan_to_num(e2))
+    assert _key(ret[0][2]) == _key(ret[1][2]) == _key(t1)          # same panels and accept decisions on every rank
+    assert ret[0][3] == ret[1][3] > 0                              # same number of scalar reductions
+    # the active counts add up to the single-process ones
+    p0 = [t for t in ret[0][2] if t["kind"] == "panel"]
+    p1 = [t for t in ret[1][2] if t["kind"] == "panel"]
+    ps = [t for t in t1 if t["kind"] == "panel"]
+    off0 = 1 if np.any(chunks[0] == 0) else 0
+    off1 = 1 if np.any(chunks[1] == 0) else 0
+    offs = 1 if np.any(xs == 0) else 0
+    for a, b, s in zip(p0, p1, ps):
+        dup = 0
+        assert (a["hi_after"] - off0) + (b["hi_after"] - off1) - dup == s["hi_after"] - offs
+
+
+def test_driver_with_fake_engine_matches_oracle_driver():
+    """The product's host driver (adaptive.py) against the oracle's independent restatement
+    (oracle/sk_oracle.py) when both use the same per-target arithmetic: identical values and traces."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import sk_oracle as so
+    import spectralkernels_jl_b200 as sk
+    from fake_engine import FakeEngine
+    S = lambda w: (0.25 + w ** 2) ** -1.05
+    xs = np.concatenate([[0.0, 0.7, 0.7], 10 ** np.linspace(-3, 0, 40)])
+    for kw in ({}, {"derivative": True}, {"alpha": 0.4}, {"convergence_criteria": "tails"},
+               {"convergence_criteria": "panel"}, {"tol": 1e-5}):
+        cfg = sk.AdaptiveKernelConfig(S, engine=FakeEngine(), quadspec=(256, 4), **kw)
+        ocfg = so.OracleConfig(S, quadspec=(256, 4), **kw)
+        tg, to = [], []
+        vg, eg = sk.kernel_values(cfg, xs, k0=5.9, trace=tg)
+        vo, eo = so.kernel_values(ocfg, xs, k0=5.9, trace=to)
+        assert np.array_equal(vg, vo), kw
+        assert np.array_equal(np.nan_to_num(eg, nan=-1.0), np.nan_to_num(eo, nan=-1.0)), kw
+        assert _key(tg, True) == _key(to, True), kw
