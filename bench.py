@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=10_000_000, help="distances per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="distances in the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=10_000_000, help="distances in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

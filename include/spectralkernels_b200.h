@@ -98,7 +98,7 @@ typedef struct sk_stats {
   double interp_ms;         /* device time in the interpolation kernel since sk_run_begin      */
   double source_ms;         /* device time in node/strength/spread/FFT since sk_run_begin      */
   int32_t timing_enabled;
-  int32_t _pad;
+  int32_t sort_two_level;   /* 1 if the last sk_targets_set used the 4-pass + run-rank sort, 0 = full 8-pass sort */
 } sk_stats;
 
 /* ---- library --------------------------------------------------------------------------------- */
@@ -176,6 +176,14 @@ int sk_subinterval(sk_ctx *ctx, double a, double b, const sk_subinterval_opts *o
 int sk_subinterval_host(sk_ctx *ctx, double a, double b, const double *no1, const double *buf1,
                         const double *no2, const double *buf2, const sk_subinterval_opts *opts,
                         double *max_abs_diff);
+/* the log-weighted origin sub-interval (config.logw && a == 0 && p != 0, src/quadrature.jl:186-228, dim = 1):
+ * integration by parts with two :cis transforms per rule.  bufa* = wt * (f + w log w f')(no*), bufb* =
+ * wt * (w log w f)(no*) built by updatequadbufs! with p = config.p (Jacobi first sub-panel);
+ * i0_coef = b^(dim/2+1-alpha) * log(b) * f(b), denom = dim - alpha.  Stages
+ * I_k = (I0 - Re A_k + 2 pi x Im B_k) / denom * cmul like sk_subinterval. */
+int sk_subinterval_logw_host(sk_ctx *ctx, double a, double b, const double *no1, const double *bufa1,
+                             const double *bufb1, const double *no2, const double *bufa2, const double *bufb2,
+                             const sk_subinterval_opts *opts, double i0_coef, double denom, double *max_abs_diff);
 /* copy the nodes / strengths the last sk_subinterval generated to HOST arrays (parity tests) */
 int sk_sources_get(sk_ctx *ctx, int32_t rule /*0: m-rule, 1: 2m-rule*/, double *no, double *buf);
 /* I += I2; err += |I2-I1| for the staged sub-interval, src/quadrature.jl:260-262 */

@@ -122,6 +122,7 @@ function kernel_values_b200(config::AdaptiveKernelConfig, xs::AbstractVector{Flo
         ck(c, ccall((:sk_subinterval_accept, libsk), Cint, (Ptr{Cvoid},), c.h))
       else                                                                 # quadrature.jl:268-270
         (tl, tr) = (_a == 0) ? (9_tol/10, _tol/10) : (_tol/2, _tol/2)
+        (_a < (_a + _b)/2 < _b) || error("sub-interval ($_a, $_b) cannot be split any further")
         push!(stack, (_a, (_a + _b)/2, tl)); push!(stack, ((_a + _b)/2, _b, tr))
       end
     end

@@ -73,6 +73,23 @@ def readme_cov(r):
 
 
 # --- singular Matern: scripts/matern_pair.jl:20-33 --------------------------------------
+def sing_matern_cov_mp(t, params, d=1):
+    """scalar mpmath version of sing_matern_cov (params may hold mpf values; used for d/d alpha)."""
+    import mpmath as mp
+    phi, a, b, p = [mp.mpf(x) for x in params]
+    dd = mp.mpf(d)
+    tt = mp.mpf(t) + mp.mpf("1e-30")
+    z = a ** 2 * mp.pi ** 2 * tt ** 2
+    o = mp.pi ** p * (a * tt) ** p * mp.gamma((dd + p) / 2) * \
+        mp.hyp1f2((dd + p) / 2, dd / 2, (2 - 2 * b + p) / 2, z) / (mp.gamma(dd / 2) * mp.gamma((2 - 2 * b + p) / 2))
+    o -= mp.pi ** (2 * b) * (a * tt) ** (2 * b) * mp.gamma(b + dd / 2) * \
+        mp.hyp1f2(b + dd / 2, 1 + b - p / 2, b + dd / 2 - p / 2, z) / \
+        (mp.gamma(1 + b - p / 2) * mp.gamma(b + dd / 2 - p / 2))
+    o *= phi * a ** (-2 * b) * mp.pi ** (1 + dd / 2 - p) * tt ** (-p) * mp.csc(b * mp.pi - p * mp.pi / 2) / \
+        mp.gamma(b + dd / 2)
+    return o
+
+
 def sing_matern_cov(t, params, d=1, dps=40):
     """params = (phi, a, b, p) with p = -alpha (matern_pair.jl:33); evaluated in mpmath."""
     import mpmath as mp

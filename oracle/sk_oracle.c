@@ -267,17 +267,43 @@ int sko_nufft1d3(int64_t M, const double *w, const double *s, int64_t N, const d
   phihat_t ph;
   phihat_init(&ph, beta, nsp);
   const double half = 0.5 * nsp;
-  /* step A: pre-phase and spread (serial: M is small on this path) */
-  for (int64_t k = 0; k < M; ++k) {
-    double u = w[k] - wc;
-    double ang = 2.0 * M_PI * (u * D);
-    dc c = (s[2 * k] + I * s[2 * k + 1]) * (cos(ang) + I * sin(ang));
-    double pos = u / hu + 0.5 * (double)nf;
-    int64_t l0 = (int64_t)ceil(pos - half);
-    for (int i = 0; i < nsp; ++i) {
-      int64_t l = l0 + i;
-      if (l < 0 || l >= nf) continue;
-      b[l] += c * es_kernel(((double)l - pos) / half, beta);
+  /* step A: pre-phase and spread; sources are split over the threads, each with a private grid */
+  {
+    int nth = sko_num_threads();
+    if (nth > 32) nth = 32;
+    if (M < 4096) nth = 1;
+    dc *priv = nth > 1 ? (dc *)calloc((size_t)nf * (size_t)nth, sizeof(dc)) : NULL;
+    if (nth > 1 && !priv) nth = 1;
+#pragma omp parallel num_threads(nth)
+    {
+#ifdef _OPENMP
+      int tid = omp_get_thread_num();
+#else
+      int tid = 0;
+#endif
+      dc *bb = nth > 1 ? priv + (size_t)tid * (size_t)nf : b;
+#pragma omp for schedule(static)
+      for (int64_t k = 0; k < M; ++k) {
+        double u = w[k] - wc;
+        double ang = 2.0 * M_PI * (u * D);
+        dc c = (s[2 * k] + I * s[2 * k + 1]) * (cos(ang) + I * sin(ang));
+        double pos = u / hu + 0.5 * (double)nf;
+        int64_t l0 = (int64_t)ceil(pos - half);
+        for (int i = 0; i < nsp; ++i) {
+          int64_t l = l0 + i;
+          if (l < 0 || l >= nf) continue;
+          bb[l] += c * es_kernel(((double)l - pos) / half, beta);
+        }
+      }
+    }
+    if (nth > 1) {
+#pragma omp parallel for schedule(static)
+      for (int64_t l = 0; l < nf; ++l) {
+        dc acc = 0;
+        for (int t = 0; t < nth; ++t) acc += priv[(size_t)t * (size_t)nf + l];
+        b[l] = acc;
+      }
+      free(priv);
     }
   }
   /* step B: deconvolve the modes n = l - nf/2, modulate by (-1)^n (output shift nf2/2), zero-pad */

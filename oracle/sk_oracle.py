@@ -439,14 +439,10 @@ def kernel_values(cfg: OracleConfig, xs, k0=None, param_derivative=False, trace:
     # unique(xs) keeps first occurrences (:99); values are scattered back through
     # a Dict keyed by x (:105-107).  Order of the unique set is irrelevant for the
     # result because _kernel_values sorts it (:113-120).
-    uxs, inv = np.unique(xs, return_inverse=True)
-    first = np.sort(np.unique(xs, return_index=True)[1])
-    uxs_first = xs[first]                                                 # first-occurrence order, as Julia
-    uvals, uerrs = _kernel_values(cfg, uxs_first, k0, param_derivative=param_derivative, trace=trace,
+    uxs, inv = np.unique(xs, return_inverse=True)                         # sorted unique
+    uvals, uerrs = _kernel_values(cfg, uxs, k0, param_derivative=param_derivative, trace=trace,
                                   transform=transform)
-    order = np.argsort(uxs_first, kind="stable")
-    sv, se = uvals[order], uerrs[order]
-    return sv[inv], se[inv]
+    return uvals[inv], uerrs[inv]
 
 
 def _kernel_values(cfg: OracleConfig, xs, k0, param_derivative=False, trace=None, transform="direct"):
@@ -489,18 +485,22 @@ def _kernel_values(cfg: OracleConfig, xs, k0, param_derivative=False, trace=None
             conv_crit = "panel"
         tau = cfg.tol * abs(k0) / 2                                       # :191
         hi_before = hi
-        ix = hi
-        conv = True
         if conv_crit == "panel":
             te = np.zeros(hi - ix1 + 1)
         else:
             te = truncation_error_estimate(b, xs[sl], c, d, cfg.dim)
-        while conv and ix >= ix1:                                         # :185-197
-            trunc_err = te[ix - ix1]
-            conv = check_convergence(trunc_err, pk[ix - ix1], tau, criteria=conv_crit)
-            if conv:
-                errs[ix - 1] += 2 * trunc_err
-                ix -= 1
+        # :185-197 -- walk ix = hi, hi-1, ... while converged.  Vectorised: the walk stops at the
+        # largest index whose predicate is false; everything above it gets errs += 2*trunc_err.
+        pk_abs = np.abs(pk)
+        ok = np.ones(hi - ix1 + 1, dtype=bool)
+        if conv_crit != "panel":
+            ok &= te < tau                                                # check_convergence, :231-233
+        if conv_crit != "tails":
+            ok &= pk_abs < tau
+        bad = np.nonzero(~ok)[0]
+        ix = ix1 - 1 if bad.size == 0 else ix1 + int(bad[-1])
+        if ix < hi:
+            errs[ix:hi] += 2 * te[ix - ix1 + 1:]
         hi = ix                                                           # :198
         if trace is not None:
             trace.append({"kind": "panel", "index": ipanel, "a": float(a), "b": float(b),

@@ -47,7 +47,7 @@ class Stats(ctypes.Structure):
     _fields_ = [("n_subintervals", c_int64), ("n_accepted", c_int64), ("n_panels", c_int64), ("units", c_int64),
                 ("n_fast", c_int64), ("n_direct", c_int64), ("kernel_launches", c_int64), ("last_nf", c_int64),
                 ("last_nf2", c_int64), ("interp_ms", c_double), ("source_ms", c_double),
-                ("timing_enabled", c_int32), ("_pad", c_int32)]
+                ("timing_enabled", c_int32), ("sort_two_level", c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
@@ -85,6 +85,8 @@ SIGNATURES = {
     "sk_panel_set_range": (c_int, [c_void_p, c_double, c_double]),
     "sk_subinterval": (c_int, [c_void_p, c_double, c_double, POINTER(SubintervalOpts), _dp]),
     "sk_subinterval_host": (c_int, [c_void_p, c_double, c_double, _dp, _dp, _dp, _dp, POINTER(SubintervalOpts), _dp]),
+    "sk_subinterval_logw_host": (c_int, [c_void_p, c_double, c_double, _dp, _dp, _dp, _dp, _dp, _dp,
+                                         POINTER(SubintervalOpts), c_double, c_double, _dp]),
     "sk_sources_get": (c_int, [c_void_p, c_int32, _dp, _dp]),
     "sk_subinterval_accept": (c_int, [c_void_p]),
     "sk_panel_commit": (c_int, [c_void_p]),
@@ -293,6 +295,14 @@ class Session:
         no1, buf1, no2, buf2 = _f64(no1), _f64(buf1), _f64(no2), _f64(buf2)
         self._ck(self._L.sk_subinterval_host(self._h, float(a), float(b), _p(no1), _p(buf1), _p(no2), _p(buf2),
                                              byref(o), byref(out)))
+        return out.value
+
+    def subinterval_logw_host(self, a, b, no1, bufa1, bufb1, no2, bufa2, bufb2, cmul, p, i0_coef, denom) -> float:
+        o = SubintervalOpts(float(cmul), float(p), SK_KERNEL_COS, 1)
+        out = c_double()
+        arrs = [_f64(x) for x in (no1, bufa1, bufb1, no2, bufa2, bufb2)]
+        self._ck(self._L.sk_subinterval_logw_host(self._h, float(a), float(b), *[_p(x) for x in arrs], byref(o),
+                                                  float(i0_coef), float(denom), byref(out)))
         return out.value
 
     def sources_get(self, rule: int):

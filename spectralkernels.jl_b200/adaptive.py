@@ -138,7 +138,23 @@ def estimate_tail_decay(cfg: AdaptiveKernelConfig, a: float, b: float, d=None):
     copies of b, so the least-squares fit is rank one and Julia's `\\` returns the minimum-norm solution."""
     nf = 1000
     start = a + (b - a)
-    ws = np.full(nf, b) if start == b else np.linspace(start, b, nf)
+    if start == b:
+        # all 1000 abscissae equal b: the design matrix [1 log b] has identical rows, and the minimum-norm
+        # least-squares solution is (1, L) t / (1 + L^2) with L = log b, t = log|f(b)|;  the ratio of sums
+        # in :218 collapses to |f(b)| b^d / b^(2d).
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            fb = abs(_f_scalar(cfg.f, b))
+            if d is None:
+                t = math.log(fb) if fb > 0 else -math.inf
+                L = math.log(b)
+                d = (L * t / (1.0 + L * L)) if math.isfinite(t) else float("nan")      # :213-214
+            d = d - cfg.alpha                                                          # :216
+            try:
+                c = float((b ** d * fb) / (b ** (2 * d)))                              # :218
+            except (OverflowError, ZeroDivisionError):
+                c = float("nan")
+        return c, d
+    ws = np.linspace(start, b, nf)
     with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
         fw = np.abs(np.asarray(cfg.f(ws), dtype=np.float64))
         if d is None:
@@ -192,11 +208,11 @@ def _subpanel_edges(a: float, b: float, k: int) -> np.ndarray:
     return e
 
 
-def _host_strengths(cfg: AdaptiveKernelConfig, eng, a: float, b: float, origin: bool):
+def _host_strengths(cfg: AdaptiveKernelConfig, eng, a: float, b: float, origin: bool, integrand=None):
     """updatequadbufs! (src/quadrature.jl:49-95) on the host for an arbitrary callable S."""
     m, k = cfg.quadspec
     (ln1, lw1, ln2, lw2), (jn1, jw1, jn2, jw2) = _host_rules(cfg, eng)
-    p, f = cfg.p, cfg.f
+    p, f = cfg.p, (integrand if integrand is not None else cfg.f)
     if origin:
         g = f
         pw = lambda no: np.ones_like(no) if p == 0 else np.power(no, p)
@@ -237,13 +253,22 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
     while stack:
         _a, _b, _tol = stack.pop()                                               # :183
         origin = (_a == 0.0 and cfg.p != 0.0)                                    # :185
-        if origin and cfg.logw:
-            raise NotImplementedError("log-weighted origin sub-interval (src/quadrature.jl:186-228)")
         if abs(_b - _a) <= 1e-16:                                                # utils.jl:28-36
             raise RuntimeError(f"The sub-interval (a, b) = ({_a}, {_b}) has been split too many times "
                                f"(b - a < 1e-16). Exiting to avoid infinite splitting.")
         if active:
-            if builtin:
+            if origin and cfg.logw:                                              # :186-228, integration by parts
+                f, df = cfg.f, cfg.df
+                if df is None:
+                    raise TypeError("logw=true needs df (the derivative of the spectral density)")
+                ga = lambda w: f(w) + w * np.log(w) * df(w)                      # :192, :210
+                gb = lambda w: w * np.log(w) * f(w)                              # :198, :216
+                no1, ba1, no2, ba2 = _host_strengths(cfg, eng, _a, _b, True, integrand=ga)
+                _, bb1, _, bb2 = _host_strengths(cfg, eng, _a, _b, True, integrand=gb)
+                i0 = _b ** (cfg.dim / 2 + 1 - cfg.alpha) * math.log(_b) * _f_scalar(f, _b)      # :189
+                mx = eng.subinterval_logw_host(_a, _b, no1, ba1, bb1, no2, ba2, bb2, cfg.c, cfg.p, i0,
+                                               cfg.dim - cfg.alpha)
+            elif builtin:
                 mx = eng.subinterval(_a, _b, cfg.c, cfg.p, kernel, cfg.logw)
             else:
                 no1, buf1, no2, buf2 = _host_strengths(cfg, eng, _a, _b, origin)
@@ -265,6 +290,11 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
         else:                                                                    # :268-270
             tl, tr = (9 * _tol / 10, _tol / 10) if _a == 0 else (_tol / 2, _tol / 2)
             mid = (_a + _b) / 2
+            if not (_a < mid < _b):
+                # the reference would push the same interval again and loop forever once (a+b)/2 rounds
+                # to an end point (its guard only fires for b - a <= 1e-16, src/utils.jl:28-36)
+                raise RuntimeError(f"The sub-interval (a, b) = ({_a}, {_b}) cannot be split any further. "
+                                   f"Exiting to avoid infinite splitting.")
             stack.append((_a, mid, tl))
             stack.append((mid, _b, tr))
 

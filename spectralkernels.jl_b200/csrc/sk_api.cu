@@ -73,7 +73,8 @@ struct sk_ctx {
 
   // sources of the current sub-interval
   DevBuf<double> no1, buf1, no2, buf2, pos_hi1, pos_lo1, pos_hi2, pos_lo2, imz;
-  DevBuf<sk_cplx> cs1, cs2, fft, dsum;
+  DevBuf<sk_cplx> cs1, cs2, fft, fftB, dsum, dsumB;
+  DevBuf<double> bufb1, bufb2;               // second integrand of the log-weighted origin sub-interval
   bool have_sources = false;
 
   // targets
@@ -204,13 +205,16 @@ void launch_interp_cplx(sk_ctx *c, const SkGeom &G, const double *x, long long n
   }
 
 // Source side of one transform pair: prep + spread/deconvolve/pad + FFT.  nrule = 1 or 2.
-int run_source_side(sk_ctx *c, const SkGeom &G, int nrule, long long M1, const double *im1, long long M2) {
+// re1/im1 (rule 0) and re2 (rule 1) are the strengths over the nodes c->no1 / c->no2; fft_out receives
+// the interleaved grids [nf2][nrule].
+int run_source_side(sk_ctx *c, const SkGeom &G, int nrule, long long M1, const double *re1, const double *im1,
+                    long long M2, const double *re2, DevBuf<sk_cplx> &fft_out) {
   const size_t need = (size_t)G.nf2 * nrule;
-  CK(c->fft.ensure(need));
+  CK(fft_out.ensure(need));
   CK(c->pos_hi1.ensure(M1));
   CK(c->pos_lo1.ensure(M1));
   CK(c->cs1.ensure(M1));
-  k_prep_sources<<<nblk(M1, 256), 256, 0, c->stream>>>(G, M1, c->no1.p, c->buf1.p, im1, c->pos_hi1.p, c->pos_lo1.p, c->cs1.p);
+  k_prep_sources<<<nblk(M1, 256), 256, 0, c->stream>>>(G, M1, c->no1.p, re1, im1, c->pos_hi1.p, c->pos_lo1.p, c->cs1.p);
   LAUNCH_CHECK();
   SkSpreadSrc src;
   std::memset(&src, 0, sizeof(src));
@@ -219,17 +223,17 @@ int run_source_side(sk_ctx *c, const SkGeom &G, int nrule, long long M1, const d
     CK(c->pos_hi2.ensure(M2));
     CK(c->pos_lo2.ensure(M2));
     CK(c->cs2.ensure(M2));
-    k_prep_sources<<<nblk(M2, 256), 256, 0, c->stream>>>(G, M2, c->no2.p, c->buf2.p, nullptr, c->pos_hi2.p, c->pos_lo2.p, c->cs2.p);
+    k_prep_sources<<<nblk(M2, 256), 256, 0, c->stream>>>(G, M2, c->no2.p, re2, nullptr, c->pos_hi2.p, c->pos_lo2.p, c->cs2.p);
     LAUNCH_CHECK();
     src.pos_hi[1] = c->pos_hi2.p; src.pos_lo[1] = c->pos_lo2.p; src.cs[1] = c->cs2.p; src.M[1] = M2;
   }
-  dim3 grid(nblk(G.nf2, 128), nrule);
-  k_spread_modes<<<grid, 128, 0, c->stream>>>(c->plan, G, src, nrule, c->fft.p);
+  dim3 grid(nblk(G.nf2 * SK_SPREAD_LANES, 256), nrule);   // SK_SPREAD_LANES lanes per FFT-input element
+  k_spread_modes<<<grid, 256, 0, c->stream>>>(c->plan, G, src, nrule, fft_out.p);
   LAUNCH_CHECK();
   cufftHandle h;
   int rc = get_fft_plan(c, G.nf2, nrule, &h);
   if (rc != SK_OK) return rc;
-  cufftResult fr = cufftExecZ2Z(h, (cufftDoubleComplex *)c->fft.p, (cufftDoubleComplex *)c->fft.p, CUFFT_INVERSE);
+  cufftResult fr = cufftExecZ2Z(h, (cufftDoubleComplex *)fft_out.p, (cufftDoubleComplex *)fft_out.p, CUFFT_INVERSE);
   if (fr != CUFFT_SUCCESS) return fail(c, SK_ERR_CUFFT, "cufftExecZ2Z failed: %d", (int)fr);
   c->stats.kernel_launches++;
   c->stats.last_nf = G.nf;
@@ -250,7 +254,7 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
     SkGeom G;
     if (sk_make_geom(c->plan, a, b, c->r_lo, c->r_hi, &G) != 0)
       return fail(c, SK_ERR_ARG, "type-3 grid too large for [a,b]=[%g,%g], r in [%g,%g]", a, b, c->r_lo, c->r_hi);
-    int rc = run_source_side(c, G, 2, M1, nullptr, M2);
+    int rc = run_source_side(c, G, 2, M1, c->buf1.p, nullptr, M2, c->buf2.p, c->fft);
     if (rc != SK_OK) return rc;
     if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
 #define CALL(WW) launch_interp_session<WW>(c, G, c->uxs.p + c->lo, n_act, o->cmul, ksin)
@@ -296,10 +300,10 @@ int upload_rule(sk_ctx *c, DevBuf<double> &dst, const double *src, int n) {
   return SK_OK;
 }
 
-int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info) {
+int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, bool two_level = true) {
   // c->in holds the n_in raw distances
   c->have_targets = false;
-  if (n_in > 0xfffffff0LL) return fail(c, SK_ERR_ARG, "n_in too large");
+  if (n_in > 0x7ffffff0LL) return fail(c, SK_ERR_ARG, "n_in too large");
   CK(c->keys.ensure(n_in));
   CK(c->keys_alt.ensure(n_in));
   CK(c->idx.ensure(n_in));
@@ -307,8 +311,8 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info) 
   CK(c->head.ensure(n_in));
   CK(c->uid.ensure(n_in));
   CK(c->inv.ensure(n_in));
-  CK(c->badflag.ensure(1));
-  CK(cudaMemsetAsync(c->badflag.p, 0, sizeof(unsigned int), c->stream));
+  CK(c->badflag.ensure(2));
+  CK(cudaMemsetAsync(c->badflag.p, 0, 2 * sizeof(unsigned int), c->stream));
   k_make_keys<<<nblk(n_in, 256), 256, 0, c->stream>>>(c->in.p, n_in, c->keys.p, c->idx.p, c->badflag.p);
   LAUNCH_CHECK();
   cub::DoubleBuffer<unsigned long long> dk(c->keys.p, c->keys_alt.p);
@@ -318,13 +322,26 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info) 
   CK(cub::DeviceScan::InclusiveSum(nullptr, tmp2, c->head.p, c->uid.p, (int)n_in, c->stream));
   CK(c->cub_tmp.ensure(std::max(tmp_bytes, tmp2)));
   tmp_bytes = tmp2 = c->cub_tmp.cap;
-  // positive doubles below 2^63: the top bit is always clear, sort the low 63 bits
-  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, 0, 63, c->stream));
-  c->stats.kernel_launches += 8;
-  const unsigned long long *skeys = dk.Current();
-  const unsigned int *sidx = dv.Current();
-  k_flag_heads<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, n_in, c->head.p);
-  LAUNCH_CHECK();
+  const unsigned long long *skeys;
+  const unsigned int *sidx;
+  if (two_level) {
+    // keys are non-negative doubles (< 2^63): order by the high word (bits 32..62) with 4 radix passes,
+    // then finish inside the short runs of equal high words (k_run_rank)
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, 32, 63, c->stream));
+    c->stats.kernel_launches += 5;
+    k_run_rank<<<nblk(n_in, 256), 256, 0, c->stream>>>(dk.Current(), dv.Current(), n_in, 128, dk.Alternate(), dv.Alternate(),
+                                                       c->head.p, c->badflag.p + 1);
+    LAUNCH_CHECK();
+    skeys = dk.Alternate();
+    sidx = dv.Alternate();
+  } else {
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, 0, 63, c->stream));
+    c->stats.kernel_launches += 9;
+    skeys = dk.Current();
+    sidx = dv.Current();
+    k_flag_heads<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, n_in, c->head.p);
+    LAUNCH_CHECK();
+  }
   CK(cub::DeviceScan::InclusiveSum(c->cub_tmp.p, tmp2, c->head.p, c->uid.p, (int)n_in, c->stream));
   c->stats.kernel_launches += 2;
   // unique table sized for the worst case (n_unique <= n_in): no host round trip before the scatter
@@ -340,6 +357,7 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info) 
   CK(cudaStreamSynchronize(c->stream));
   const SkTargetSummary sm = c->h_scal->sum;
   if (sm.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
+  if (two_level && sm.overflow) return targets_from_device_buffer(c, n_in, info, false);   // heavily clustered input
   const long long nu = sm.n_unique;
   c->n_in = n_in;
   c->n_unique = nu;
@@ -350,6 +368,7 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info) 
   c->staged = false;
   c->commit_pending = false;
   c->scan_hi = -1;
+  c->stats.sort_two_level = two_level ? 1 : 0;
   if (info) {
     info->n_in = n_in;
     info->n_unique = nu;
@@ -433,6 +452,7 @@ int sk_ctx_destroy(sk_ctx *c) {
   for (auto *b : dbl) b->release();
   c->cs1.release(); c->cs2.release(); c->fft.release(); c->dsum.release();
   c->res.release(); c->pan.release(); c->stage.release();
+  c->fftB.release(); c->dsumB.release(); c->bufb1.release(); c->bufb2.release();
   if (c->d_sum) cudaFree(c->d_sum);
   c->keys.release(); c->keys_alt.release(); c->idx.release(); c->idx_alt.release();
   c->head.release(); c->uid.release(); c->inv.release(); c->cub_tmp.release(); c->badflag.release();
@@ -543,7 +563,7 @@ int sk_nufft1d3(sk_ctx *c, int64_t M, const double *w, const double *s, int64_t 
     CK(cudaMemcpyAsync(c->buf1.p, hre.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->imz.p, him.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->in.p, x, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
-    int r2 = run_source_side(c, G, 1, M, c->imz.p, 0);
+    int r2 = run_source_side(c, G, 1, M, c->buf1.p, c->imz.p, 0, nullptr, c->fft);
     if (r2 != SK_OK) return r2;
 #define CALL(WW) launch_interp_cplx<WW>(c, G, c->in.p, N, c->dsum.p)
     DISPATCH_W(c->plan.w, CALL)
@@ -661,8 +681,10 @@ int sk_run_begin(sk_ctx *c) {
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "sk_targets_set first");
   CK(cudaSetDevice(c->device));
   const bool t = c->timing;
+  const int two = c->stats.sort_two_level;
   std::memset(&c->stats, 0, sizeof(c->stats));
   c->stats.timing_enabled = t;
+  c->stats.sort_two_level = two;
   CK(cudaMemsetAsync(c->res.p, 0, sizeof(sk_cplx) * c->n_unique, c->stream));   // ks = errs = 0, src/adaptive.jl:122
   c->in_panel = false;
   c->staged = false;
@@ -741,7 +763,8 @@ int sk_subinterval(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, 
   if (c->family == SK_SDF_HOST) return fail(c, SK_ERR_STATE, "no built-in spectral density set: use sk_subinterval_host");
   if (o->p != c->p) return fail(c, SK_ERR_ARG, "opts.p (%g) differs from the rule's p (%g)", o->p, c->p);
   const bool origin = (a == 0.0 && c->p != 0.0);                    // src/quadrature.jl:185
-  if (origin && o->logw) return fail(c, SK_ERR_UNSUPPORTED, "log-weighted origin sub-interval (src/quadrature.jl:186-228)");
+  if (origin && o->logw)
+    return fail(c, SK_ERR_UNSUPPORTED, "log-weighted origin sub-interval needs df: use sk_subinterval_logw_host (src/quadrature.jl:186-228)");
   SkPanelSpec S;
   std::memset(&S, 0, sizeof(S));
   S.m = c->m; S.k = c->k;
@@ -775,6 +798,73 @@ int sk_subinterval_host(sk_ctx *c, double a, double b, const double *no1, const 
   CK(cudaMemcpyAsync(c->buf2.p, buf2, sizeof(double) * 2 * M1, cudaMemcpyHostToDevice, c->stream));
   c->have_sources = true;
   return transform_and_stage(c, a, b, o, max_abs_diff);
+}
+
+// Log-weighted origin sub-interval (src/quadrature.jl:186-228, dim = 1): the host evaluates both
+// integrands of the integration by parts (it owns f and df) and the boundary-term coefficient.
+int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, const double *bufa1, const double *bufb1,
+                             const double *no2, const double *bufa2, const double *bufb2, const sk_subinterval_opts *o,
+                             double i0_coef, double denom, double *max_abs_diff) {
+  int rc = subinterval_prologue(c, a, b, o);
+  if (rc != SK_OK) return rc;
+  if (!no1 || !bufa1 || !bufb1 || !no2 || !bufa2 || !bufb2 || !max_abs_diff) return fail(c, SK_ERR_ARG, "null pointer");
+  if (a != 0.0) return fail(c, SK_ERR_ARG, "the integration-by-parts branch applies to a == 0 only");
+  const long long M1 = (long long)c->m * c->k, M2 = 2 * M1;
+  const long long n_act = c->hi - c->lo;
+  CK(c->bufb1.ensure(M1));
+  CK(c->bufb2.ensure(M2));
+  CK(cudaMemcpyAsync(c->no1.p, no1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->buf1.p, bufa1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->bufb1.p, bufb1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->no2.p, no2, sizeof(double) * M2, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->buf2.p, bufa2, sizeof(double) * M2, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->bufb2.p, bufb2, sizeof(double) * M2, cudaMemcpyHostToDevice, c->stream));
+  c->have_sources = true;
+  CK(cudaMemsetAsync(c->d_red, 0, sizeof(SkReduceOut), c->stream));
+  SkLogwArgs L;
+  L.i0_coef = i0_coef;
+  L.denom = denom;
+  L.b = b;
+  const bool fast = (M2 * n_act > (1LL << 18)) && n_act > 1;          // src/quadrature.jl:105
+  if (fast) {
+    SkGeom G;
+    if (sk_make_geom(c->plan, a, b, c->r_lo, c->r_hi, &G) != 0) return fail(c, SK_ERR_ARG, "type-3 grid too large");
+    rc = run_source_side(c, G, 2, M1, c->buf1.p, nullptr, M2, c->buf2.p, c->fft);
+    if (rc != SK_OK) return rc;
+    rc = run_source_side(c, G, 2, M1, c->bufb1.p, nullptr, M2, c->bufb2.p, c->fftB);
+    if (rc != SK_OK) return rc;
+#define CALL(WW)                                                                                                     \
+  k_interp_logw<WW><<<nblk(n_act, 256), 256, 0, c->stream>>>(c->plan, G, c->uxs.p + c->lo, n_act, c->fft.p, c->fftB.p, \
+                                                             o->cmul, L, c->stage.p + c->lo, c->d_red)
+    DISPATCH_W(c->plan.w, CALL)
+#undef CALL
+    LAUNCH_CHECK();
+    c->stats.n_fast++;
+  } else {
+    CK(c->dsum.ensure((size_t)n_act * 2));
+    CK(c->dsumB.ensure((size_t)n_act * 2));
+    dim3 grid((unsigned int)n_act, 2);
+    k_direct<<<grid, 256, 0, c->stream>>>(c->no1.p, c->buf1.p, M1, c->no2.p, c->buf2.p, M2, c->uxs.p + c->lo, c->dsum.p);
+    LAUNCH_CHECK();
+    k_direct<<<grid, 256, 0, c->stream>>>(c->no1.p, c->bufb1.p, M1, c->no2.p, c->bufb2.p, M2, c->uxs.p + c->lo, c->dsumB.p);
+    LAUNCH_CHECK();
+    k_direct_finish_logw<<<1, 256, 0, c->stream>>>(c->dsum.p, c->dsumB.p, c->uxs.p + c->lo, n_act, o->cmul, L,
+                                                   c->stage.p + c->lo, c->d_red);
+    LAUNCH_CHECK();
+    c->stats.n_direct++;
+  }
+  CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const unsigned int fl = c->h_scal->red.flags;
+  double mx;
+  std::memcpy(&mx, &c->h_scal->red.maxbits, sizeof(double));
+  if (fl & SK_FLAG_NAND) mx = std::nan("");
+  *max_abs_diff = mx;
+  c->staged = true;
+  c->stats.n_subintervals++;
+  c->stats.units += n_act;
+  if (!(fl & SK_FLAG_NAN1) && (fl & SK_FLAG_NAN2)) return fail(c, SK_ERR_NAN, "NaN detected in panel integral...");
+  return SK_OK;
 }
 
 int sk_sources_get(sk_ctx *c, int32_t rule, double *no, double *buf) {

@@ -39,7 +39,7 @@ struct SkTargetSummary {        // written by k_target_summary
   long long n_unique;
   double r0, r1, r_last;        // smallest, second smallest and largest unique distance
   unsigned int bad;
-  unsigned int _pad;
+  unsigned int overflow;        // a run of equal high words was too long for the two-level sort
 };
 
 __device__ __forceinline__ double sk_warp_max(double v) {
@@ -238,6 +238,14 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       sCoef[t] = sk_cell_coef<W>(sE, sO, sWin + cell * 4 + comp, 4, q);
     }
     __syncthreads();
+    // B': fold the target-side deconvolution (a cubic per cell) into the coefficients
+    for (int t = threadIdx.x; t < ncell * 4; t += blockDim.x) {
+      const int comp = t & 3, cell = t >> 2;
+      double a[4];
+      sk_cell_deconv_cubic(P, G, (double)(l_first + cell - G.nf2 / 2) + (0.5 * W - 0.5), a);
+      sk_cell_fold(sCoef + (size_t)cell * SK_NC * 4 + comp, 4, a);
+    }
+    __syncthreads();
     // C: Horner per target
 #pragma unroll
     for (int u = 0; u < SK_TPT; ++u) {
@@ -249,16 +257,15 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
         cell = cell < 0 ? 0 : (cell >= ncell ? ncell - 1 : cell);
         double a[4];
         sk_cell_horner<4>(sCoef + (size_t)cell * SK_NC * 4, tc.s, a);
-        const double qf = sk_deconv(P, G.t_cell * tc.yabs);
         double sn, cs;
         sk_post_phase(G, r, &sn, &cs);
         double f1, f2;
         if (kernel_sin) {
-          f1 = qf * (a[0] * sn + a[1] * cs);
-          f2 = qf * (a[2] * sn + a[3] * cs);
+          f1 = a[0] * sn + a[1] * cs;
+          f2 = a[2] * sn + a[3] * cs;
         } else {
-          f1 = qf * (a[0] * cs - a[1] * sn);
-          f2 = qf * (a[2] * cs - a[3] * sn);
+          f1 = a[0] * cs - a[1] * sn;
+          f2 = a[2] * cs - a[3] * sn;
         }
         sk_stage(f1, f2, cmul, &stage[j0 + t], d, fl);
       }
@@ -273,6 +280,61 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
         sk_stage(kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, &stage[j0 + t], d, fl);
       }
     }
+  }
+  sk_block_reduce_maxflags(d, fl, red);
+}
+
+// ---- K4 (log-weighted origin sub-interval, src/quadrature.jl:186-228, dim = 1) --------------------------
+// Integration by parts: two :cis transforms per rule, A with integrand f + w log w f' (real part used) and
+// B with w log w f (imaginary part used);  I_k = (I0 - Re A_k + 2 pi x Im B_k) / (dim - alpha) with the
+// boundary term I0 = b^(dim/2+1-alpha) log(b) f(b) J_{-1/2}(2 pi b x),  J_{-1/2}(z) = sqrt(2/(pi z)) cos z.
+struct SkLogwArgs {
+  double i0_coef;   // b^(dim/2 + 1 - alpha) * log(b) * f(b)
+  double denom;     // dim - alpha
+  double b;         // right end of the sub-interval
+};
+template <int W>
+__global__ void __launch_bounds__(256)
+k_interp_logw(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G, const double *__restrict__ xs,
+              long long n, const sk_cplx *__restrict__ gridA, const sk_cplx *__restrict__ gridB, double cmul,
+              const __grid_constant__ SkLogwArgs L, sk_cplx *__restrict__ stage, SkReduceOut *__restrict__ red) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double d = 0.0;
+  unsigned int fl = 0;
+  if (j < n) {
+    const double x = xs[j];
+    double are[2], aim[2], bre[2], bim[2];
+    sk_interp_point<W, 2>(P, G, x, gridA, are, aim);
+    sk_interp_point<W, 2>(P, G, x, gridB, bre, bim);
+    double sn, cs;
+    sincospi(2.0 * sk_frac_prod(L.b, x, 0.0), &sn, &cs);            // cos(2 pi b x) with the product exact
+    const double z = 6.283185307179586 * (L.b * x);
+    const double i0 = L.i0_coef * sqrt(2.0 / (3.141592653589793 * z)) * cs;
+    const double tx = 6.283185307179586 * x;
+    const double f1 = ((i0 - are[0]) + tx * bim[0]) / L.denom;      // src/quadrature.jl:226-227
+    const double f2 = ((i0 - are[1]) + tx * bim[1]) / L.denom;
+    sk_stage(f1, f2, cmul, &stage[j], d, fl);
+  }
+  sk_block_reduce_maxflags(d, fl, red);
+}
+
+// direct-summation twin of k_interp_logw: sumsA / sumsB hold the :cis sums of both rules per target
+__global__ void k_direct_finish_logw(const sk_cplx *__restrict__ sumsA, const sk_cplx *__restrict__ sumsB,
+                                     const double *__restrict__ xs, long long n, double cmul,
+                                     const __grid_constant__ SkLogwArgs L, sk_cplx *__restrict__ stage,
+                                     SkReduceOut *__restrict__ red) {
+  double d = 0.0;
+  unsigned int fl = 0;
+  for (long long j = threadIdx.x; j < n; j += blockDim.x) {
+    const double x = xs[j];
+    double sn, cs;
+    sincospi(2.0 * sk_frac_prod(L.b, x, 0.0), &sn, &cs);
+    const double z = 6.283185307179586 * (L.b * x);
+    const double i0 = L.i0_coef * sqrt(2.0 / (3.141592653589793 * z)) * cs;
+    const double tx = 6.283185307179586 * x;
+    const double f1 = ((i0 - sumsA[2 * j].x) + tx * sumsB[2 * j].y) / L.denom;
+    const double f2 = ((i0 - sumsA[2 * j + 1].x) + tx * sumsB[2 * j + 1].y) / L.denom;
+    sk_stage(f1, f2, cmul, &stage[j], d, fl);
   }
   sk_block_reduce_maxflags(d, fl, red);
 }
@@ -420,6 +482,42 @@ __global__ void k_make_keys(const double *__restrict__ xs, long long n, unsigned
   idx[j] = (unsigned int)j;
 }
 
+// Second half of the two-level sort.  The radix sort ordered the pairs by the HIGH 32 bits of the key
+// only (4 digit passes instead of 8, stable).  Runs of equal high words are short for real distance
+// sets (a few elements), so every element finds its run by walking left/right and ranks itself inside
+// it on the full 64-bit key (ties: earlier position first => stable).  It writes itself to its final
+// sorted position together with its "first of its value" flag.  Runs longer than lmax raise
+// *overflow and the caller falls back to the full 8-pass sort.
+__global__ void __launch_bounds__(256)
+k_run_rank(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ idx, long long n, int lmax,
+           unsigned long long *__restrict__ keys_out, unsigned int *__restrict__ idx_out, unsigned int *__restrict__ head_out,
+           unsigned int *__restrict__ overflow) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  const unsigned int hw = (unsigned int)(k >> 32);
+  long long rank = 0;
+  bool first = true;
+  long long s = i;
+  while (s > 0 && (unsigned int)(keys[s - 1] >> 32) == hw) {
+    --s;
+    const unsigned long long o = keys[s];
+    if (o <= k) ++rank;                  // earlier position wins ties
+    if (o == k) first = false;
+    if (i - s > lmax) { atomicOr(overflow, 1u); return; }
+  }
+  long long e = i + 1;
+  while (e < n && (unsigned int)(keys[e] >> 32) == hw) {
+    if (keys[e] < k) ++rank;
+    ++e;
+    if (e - i > lmax) { atomicOr(overflow, 1u); return; }
+  }
+  const long long pos = s + rank;
+  keys_out[pos] = k;
+  idx_out[pos] = idx[i];
+  head_out[pos] = first ? 1u : 0u;
+}
+
 __global__ void k_flag_heads(const unsigned long long *__restrict__ keys, long long n, unsigned int *__restrict__ head) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -433,13 +531,17 @@ __global__ void k_scatter_unique(const unsigned long long *__restrict__ keys, co
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const unsigned int u = uid_incl[j] - 1u;
-  if (head[j]) uxs[u] = __longlong_as_double((long long)keys[j]);
-  inv[idx[j]] = u;
+  // the guards only matter when the two-level sort overflowed and left garbage behind (the caller then
+  // redoes the sort): never write out of bounds
+  if (head[j] && (long long)u < n) uxs[u] = __longlong_as_double((long long)keys[j]);
+  if ((long long)idx[j] < n) inv[idx[j]] = u;
 }
 
 __global__ void k_target_summary(const double *__restrict__ uxs, const unsigned int *__restrict__ uid_incl, long long n,
                                  const unsigned int *__restrict__ bad, SkTargetSummary *__restrict__ out) {
-  const long long nu = uid_incl[n - 1];
+  out->overflow = bad[1];
+  long long nu = uid_incl[n - 1];
+  if (nu < 1 || nu > n) nu = 1;          // only after an overflowed two-level sort
   out->n_unique = nu;
   out->r0 = uxs[0];
   out->r1 = nu > 1 ? uxs[1] : 0.0;

@@ -253,6 +253,7 @@ SK_HD void sk_spread_mode(const SkEsPlan &P, const SkGeom &G, long long j, const
 // ---- target side ----------------------------------------------------------------------------------
 struct SkTargetCoord {
   long long l0;   // first fine-grid index of the w-wide window (already shifted by nf2/2, clamped)
+                  // (the cell centre s = 0 sits at y = l0 - nf2/2 + w/2 - 1/2)
   double s;       // 2x, x in [-1/2, 1/2) the offset inside the window
   double yabs;    // |y| for the deconvolution argument
 };
@@ -342,6 +343,41 @@ SK_HD void sk_cell_horner(const double *coef, double s, double *out) {
   for (int q = SK_NC - 2; q >= 0; --q) {
 #pragma unroll
     for (int c = 0; c < NCOMP; ++c) out[c] = sk_fma(out[c], s, coef[q * NCOMP + c]);
+  }
+}
+
+// The target-side deconvolution factor q(y) = (2/w)/phihat(pi w y / nf2) changes by ~1e-4 relative across
+// one cell, so inside a cell it is a cubic in s to ~1e-17 (interpolated at the 4 Chebyshev nodes).  Folding
+// that cubic into the cell polynomial (a truncated polynomial product: the dropped degree-16..18 terms are
+// ~1e-4 * 1e-16) makes the deconvolution free per target.  ymid = y at s = 0 (the cell centre), y = ymid - s/2.
+SK_HD void sk_cell_deconv_cubic(const SkEsPlan &P, const SkGeom &G, double ymid, double *a) {
+  const double n0 = 0.9238795325112867, n1 = 0.3826834323650898;   // cos(pi/8), cos(3 pi/8)
+  const double q0 = sk_deconv(P, G.t_cell * fabs(ymid - 0.5 * n0));
+  const double q1 = sk_deconv(P, G.t_cell * fabs(ymid - 0.5 * n1));
+  const double q2 = sk_deconv(P, G.t_cell * fabs(ymid + 0.5 * n1));
+  const double q3 = sk_deconv(P, G.t_cell * fabs(ymid + 0.5 * n0));
+  // Chebyshev coefficients of the interpolant: c_j = (2/4) sum_k q_k T_j(s_k), c_0 halved
+  const double t2a = 2.0 * n0 * n0 - 1.0, t2b = 2.0 * n1 * n1 - 1.0;               // T2 at +-n0, +-n1
+  const double t3a = (4.0 * n0 * n0 - 3.0) * n0, t3b = (4.0 * n1 * n1 - 3.0) * n1; // T3 at n0, n1 (odd)
+  const double c0 = 0.25 * ((q0 + q3) + (q1 + q2));
+  const double c1 = 0.5 * (n0 * (q0 - q3) + n1 * (q1 - q2));
+  const double c2 = 0.5 * (t2a * (q0 + q3) + t2b * (q1 + q2));
+  const double c3 = 0.5 * (t3a * (q0 - q3) + t3b * (q1 - q2));
+  a[0] = c0 - c2;          // T0 = 1, T1 = s, T2 = 2 s^2 - 1, T3 = 4 s^3 - 3 s
+  a[1] = c1 - 3.0 * c3;
+  a[2] = 2.0 * c2;
+  a[3] = 4.0 * c3;
+}
+
+// in-place product of one coefficient column (stride doubles apart) with the cubic a, truncated at SK_NC
+SK_HD void sk_cell_fold(double *col, int stride, const double *a) {
+#pragma unroll
+  for (int q = SK_NC - 1; q >= 0; --q) {
+    double v = a[0] * col[q * stride];
+    if (q >= 1) v = sk_fma(a[1], col[(q - 1) * stride], v);
+    if (q >= 2) v = sk_fma(a[2], col[(q - 2) * stride], v);
+    if (q >= 3) v = sk_fma(a[3], col[(q - 3) * stride], v);
+    col[q * stride] = v;
   }
 }
 

@@ -47,6 +47,14 @@ class Matern:
     def derivative(self, j: int) -> "Matern":
         return Matern(self.phi, self.rho, self.nu, self.d, j)
 
+    def dw(self, w):
+        """dS/dw, the `df` keyword of AdaptiveKernelConfig (needed by logw=true, src/quadrature.jl:192)."""
+        if self.deriv != 0:
+            raise ValueError("dw is provided for the density itself only")
+        w = np.asarray(w, dtype=np.float64)
+        ex = -self.nu - self.d / 2
+        return self.phi * ex * (self.rho ** 2 + w ** 2) ** (ex - 1.0) * 2.0 * w
+
 
 @dataclass(frozen=True)
 class Exponential:
@@ -74,6 +82,12 @@ class Exponential:
 
     def derivative(self, j: int) -> "Exponential":
         return Exponential(self.phi, self.alpha, j)
+
+    def dw(self, w):
+        if self.deriv != 0:
+            raise ValueError("dw is provided for the density itself only")
+        w = np.asarray(w, dtype=np.float64)
+        return -self.alpha * np.sign(w) * self.phi * np.exp(-self.alpha * np.abs(w))
 
 
 def is_builtin(f) -> bool:

@@ -60,18 +60,24 @@ long long emul_interp_cells(const SkEsPlan *P, const SkGeom *G, long long N, con
         const long long cell = t / (SK_NC * 4);
         coef[t] = sk_cell_coef<W>(E.data(), O.data(), win + cell * 4 + comp, 4, q);
       }
+      for (long long t = 0; t < ncell * 4; ++t) {
+        const int comp = t & 3;
+        const long long cell = t >> 2;
+        double a[4];
+        sk_cell_deconv_cubic(*P, *G, (double)(lf + cell - G->nf2 / 2) + (0.5 * W - 0.5), a);
+        sk_cell_fold(coef.data() + (size_t)cell * SK_NC * 4 + comp, 4, a);
+      }
       for (int t = 0; t < cnt; ++t) {
         const double rr = r[j0 + t];
         const SkTargetCoord tc = sk_target_coord<W>(*G, rr);
         long long cell = tc.l0 - lf;
         double a[4];
         sk_cell_horner<4>(coef.data() + (size_t)cell * SK_NC * 4, tc.s, a);
-        const double qf = sk_deconv(*P, G->t_cell * tc.yabs);
         double sn, cs;
         sk_post_phase(*G, rr, &sn, &cs);
         double *o = out + (j0 + t) * 4;
-        o[0] = qf * (a[0] * cs - a[1] * sn); o[1] = qf * (a[0] * sn + a[1] * cs);
-        o[2] = qf * (a[2] * cs - a[3] * sn); o[3] = qf * (a[2] * sn + a[3] * cs);
+        o[0] = a[0] * cs - a[1] * sn; o[1] = a[0] * sn + a[1] * cs;
+        o[2] = a[2] * cs - a[3] * sn; o[3] = a[2] * sn + a[3] * cs;
       }
     } else {
       for (int t = 0; t < cnt; ++t) {

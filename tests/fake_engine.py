@@ -68,6 +68,17 @@ class FakeEngine:
         self._stage = (i2, np.abs(i2 - i1))
         return float(np.max(self._stage[1]))
 
+    def subinterval_logw_host(self, a, b, no1, bufa1, bufb1, no2, bufa2, bufb2, cmul, p, i0_coef, denom):
+        from scipy import special
+        x = self.uxs[self.lo:self.hi]
+        i0 = i0_coef * special.jv(-0.5, 2 * np.pi * b * x)
+        out = []
+        for no, ba, bb in ((no1, bufa1, bufb1), (no2, bufa2, bufb2)):
+            fa, fb = so.direct_cis(no, ba, x), so.direct_cis(no, bb, x)
+            out.append(((i0 - fa.real) + 2 * np.pi * x * fb.imag) / denom * cmul)
+        self._stage = (out[1], np.abs(out[1] - out[0]))
+        return float(np.max(self._stage[1]))
+
     def subinterval(self, *a, **k):
         raise AssertionError("built-in S needs the CUDA engine")
 

@@ -51,6 +51,17 @@ def main():
     out["sing_r"] = r11
     out["sing_alpha"] = np.array(0.5)
     out["sing_K"] = cf.sing_matern_cov(r11, (*parms, -0.5), d=1)
+    # d/d alpha of the singular kernel (test/matern_sdf.jl:66-86; ForwardDiff there, mpmath.diff here),
+    # on every 5th point of the grid (the points the parity tests use)
+    import mpmath as mp_
+    idx = np.unique(np.append(np.arange(0, 1000, 5), 999))[1:]
+    dka = []
+    with mp_.workdps(40):
+        for t in r11[idx]:
+            fun = lambda a_: mp_.mpf(float(cf.sing_matern_cov_mp(float(t), (*parms, -a_), d=1)))
+            dka.append(float(mp_.diff(lambda a_: cf.sing_matern_cov_mp(float(t), (*parms, -a_), d=1), mp_.mpf("0.5"))))
+    out["sing_dalpha_idx"] = idx
+    out["sing_dalpha"] = np.array(dka)
     rr = 10 ** np.linspace(-6, 0, 1000)
     out["readme_r"] = rr
     out["readme_K"] = cf.readme_cov(rr)

@@ -192,6 +192,29 @@ def test_interp_modes_agree(sk):
     assert np.max(np.abs(out[0][0] - cf.readme_cov(xs))) <= 1e-8 * (np.pi / 2)
 
 
+def test_singularity_derivative_logw(sk, golden):
+    """dK/d alpha through logw=true (test/matern_sdf.jl:66-86, dim = 1): the integration-by-parts origin
+    sub-interval (sk_subinterval_logw_host) and the log-weighted Legendre sub-intervals on the device."""
+    idx = golden["sing_dalpha_idx"][::2]
+    parms = tuple(golden["matern_parms"])
+    xs = golden["sing_r"][idx]
+    S = sk.Matern(*parms)
+    Sh = lambda w: cf.matern_sdf(w, parms)
+    k0 = so.compute_k0(so.OracleConfig(Sh, alpha=0.5))
+    cfg = sk.AdaptiveKernelConfig(S, df=S.dw, alpha=0.5, logw=True)
+    ocfg = so.OracleConfig(Sh, df=S.dw, alpha=0.5, logw=True)
+    tg, to = [], []
+    vg, eg = sk.kernel_values(cfg, xs, k0=k0, param_derivative=True, trace=tg)
+    vo, eo = so.kernel_values(ocfg, xs, k0=k0, param_derivative=True, trace=to)
+    assert np.all(np.abs(vg - golden["sing_dalpha"][::2]) / k0 <= 10 * 1e-8)
+    assert np.max(np.abs(vg - vo)) <= 1e-11 * k0
+    assert _trace_key(tg) == _trace_key(to)
+    # direct-summation twin (two targets)
+    v2, _ = sk.kernel_values(cfg, xs[[3, 40]], k0=k0, param_derivative=True)
+    o2, _ = so.kernel_values(ocfg, xs[[3, 40]], k0=k0, param_derivative=True)
+    assert np.max(np.abs(v2 - o2)) <= 1e-11 * k0
+
+
 def test_host_callable_equals_builtin(sk, golden):
     """Arbitrary closures are evaluated on the host and uploaded (sk_subinterval_host)."""
     xs = golden["readme_r"][::7]
@@ -223,6 +246,31 @@ def test_duplicates_unsorted_zero_and_direct_branch(sk):
     assert abs(v1[0] - cf.exponential_cov(0.77)) <= 1e-8 * k0
     v0, e0 = sk.kernel_values(cfg, np.zeros(4), k0=k0)
     assert np.all(v0 == k0) and np.all(np.isnan(e0))
+
+
+def test_sort_paths(sk):
+    """K8: the two-level sort (4 radix passes on the high key word + k_run_rank) and its fallback to the
+    full sort for heavily clustered inputs give the same unique/sort/scatter as numpy."""
+    rng = np.random.default_rng(4)
+    S = sk.Exponential(1.0, 1.0)
+    cfg = sk.AdaptiveKernelConfig(S)
+    spread = rng.uniform(0, 2.0, 5000)
+    spread[100:200] = spread[0:100]                                    # exact duplicates
+    clustered = 0.5 + rng.uniform(0, 1e-9, 3000)                       # one high word: > 128 per run -> fallback
+    clustered[::7] = clustered[0]
+    for xs, two_level in ((spread, 1), (np.concatenate([spread, clustered]), 0)):
+        info = cfg.engine.targets_set(xs)
+        assert info.n_unique == np.unique(xs).size
+        assert cfg.engine.stats()["sort_two_level"] == two_level
+        ux = np.unique(xs)
+        for i in (1, 2, ux.size // 2, ux.size):
+            assert cfg.engine.target_value(i) == ux[i - 1]
+        v, e = sk.kernel_values(cfg, xs, k0=2.0)
+        assert np.max(np.abs(v - cf.exponential_cov(xs))) <= 1e-8 * 2.0
+        _, inv = np.unique(xs, return_inverse=True)
+        first = {}
+        for j, u in enumerate(inv):
+            assert v[j] == v[first.setdefault(u, j)]                   # equal distances -> identical values
 
 
 def test_shrinking_active_set_trace(sk):

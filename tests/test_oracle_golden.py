@@ -61,6 +61,25 @@ def test_singular_matern_1d(golden, tol):
     assert np.all(np.abs(vals - true) / k0 <= 10 * tol)
 
 
+def test_singularity_derivative_logw(golden):
+    """test/matern_sdf.jl:66-86, dim = 1: dK/d alpha through the logw=true config (integration by parts at
+    the origin, src/quadrature.jl:186-228).  Sign/scale: kernel_singularity_derivative (src/derivatives.jl:74-81)
+    returns d/d alpha of int |w|^-alpha S cos = -int log(w) w^-alpha S cos, which is what c *= -1 encodes
+    (src/adaptive.jl:45)."""
+    idx = golden["sing_dalpha_idx"][::4]
+    parms = tuple(golden["matern_parms"])
+    r = golden["sing_r"][idx]
+    true = golden["sing_dalpha"][::4]
+    S = lambda w: cf.matern_sdf(w, parms)
+    ex = -parms[2] - 0.5
+    dS = lambda w: parms[0] * ex * (parms[1] ** 2 + w ** 2) ** (ex - 1) * 2 * w
+    cfg0 = so.OracleConfig(S, alpha=0.5)
+    k0 = so.compute_k0(cfg0)
+    cfg = so.OracleConfig(S, df=dS, alpha=0.5, logw=True, tol=1e-8)
+    vals, _ = so.kernel_values(cfg, r, k0=k0, param_derivative=True)
+    assert np.all(np.abs(vals - true) / k0 <= 10 * 1e-8)
+
+
 def test_readme_demo_and_trace(golden):
     """README.md:19-33; the trace shape (2 outer panels, no bisection) is the oracle's own
     output -- there is no reference-side fixture for traces ("parity unpinned" for traces)."""
