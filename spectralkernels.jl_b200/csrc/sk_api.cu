@@ -47,6 +47,7 @@ struct DevBuf {
 struct HostScalars {          // pinned mirror of the device scalars
   SkReduceOut red;
   SkTargetSummary sum;
+  SkKeyBits kb;
   double r[2];
 };
 
@@ -83,9 +84,10 @@ struct sk_ctx {
   DevBuf<double> in, uxs, out_v, out_e;
   DevBuf<sk_cplx> res, pan, stage;   // (ks, errs), (I, err), (I2, |I2-I1|) per unique target
   DevBuf<unsigned long long> keys, keys_alt;
-  DevBuf<unsigned int> idx, idx_alt, head, uid, inv;
+  DevBuf<unsigned int> idx, idx_alt, head, uid;
   DevBuf<unsigned char> cub_tmp;
-  DevBuf<unsigned int> badflag;
+  SkKeyBits *d_kb = nullptr;
+  const unsigned int *sidx = nullptr;        // sorted position -> original position (one of idx / idx_alt)
   bool have_targets = false;
 
   // panel state (0-based half-open [lo, hi))
@@ -227,7 +229,8 @@ int run_source_side(sk_ctx *c, const SkGeom &G, int nrule, long long M1, const d
     LAUNCH_CHECK();
     src.pos_hi[1] = c->pos_hi2.p; src.pos_lo[1] = c->pos_lo2.p; src.cs[1] = c->cs2.p; src.M[1] = M2;
   }
-  dim3 grid(nblk(G.nf2 * SK_SPREAD_LANES, 256), nrule);   // SK_SPREAD_LANES lanes per FFT-input element
+  CK(cudaMemsetAsync(fft_out.p, 0, sizeof(sk_cplx) * need, c->stream));   // zero-padding of the modes
+  dim3 grid(nblk(G.nf, SK_SPREAD_CELLS), nrule);          // SK_SPREAD_LANES lanes per spread-grid cell
   k_spread_modes<<<grid, 256, 0, c->stream>>>(c->plan, G, src, nrule, fft_out.p);
   LAUNCH_CHECK();
   cufftHandle h;
@@ -310,10 +313,11 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   CK(c->idx_alt.ensure(n_in));
   CK(c->head.ensure(n_in));
   CK(c->uid.ensure(n_in));
-  CK(c->inv.ensure(n_in));
-  CK(c->badflag.ensure(2));
-  CK(cudaMemsetAsync(c->badflag.p, 0, 2 * sizeof(unsigned int), c->stream));
-  k_make_keys<<<nblk(n_in, 256), 256, 0, c->stream>>>(c->in.p, n_in, c->keys.p, c->idx.p, c->badflag.p);
+  SkKeyBits kb0;
+  kb0.bits_or = 0ull; kb0.bits_and = ~0ull; kb0.bad = 0; kb0.overflow = 0;
+  c->h_scal->kb = kb0;
+  CK(cudaMemcpyAsync(c->d_kb, &c->h_scal->kb, sizeof(SkKeyBits), cudaMemcpyHostToDevice, c->stream));
+  k_make_keys<<<nblk(n_in, 256), 256, 0, c->stream>>>(c->in.p, n_in, c->keys.p, c->idx.p, c->d_kb);
   LAUNCH_CHECK();
   cub::DoubleBuffer<unsigned long long> dk(c->keys.p, c->keys_alt.p);
   cub::DoubleBuffer<unsigned int> dv(c->idx.p, c->idx_alt.p);
@@ -325,12 +329,21 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   const unsigned long long *skeys;
   const unsigned int *sidx;
   if (two_level) {
-    // keys are non-negative doubles (< 2^63): order by the high word (bits 32..62) with 4 radix passes,
-    // then finish inside the short runs of equal high words (k_run_rank)
-    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, 32, 63, c->stream));
-    c->stats.kernel_launches += 5;
-    k_run_rank<<<nblk(n_in, 256), 256, 0, c->stream>>>(dk.Current(), dv.Current(), n_in, 128, dk.Alternate(), dv.Alternate(),
-                                                       c->head.p, c->badflag.p + 1);
+    // Which key bits differ at all?  (one 24-byte read-back; the keys are non-negative doubles, so the
+    // sign bit never varies and for a distance set spanning a few binades neither do the top exponent bits)
+    CK(cudaMemcpyAsync(&c->h_scal->kb, c->d_kb, sizeof(SkKeyBits), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->h_scal->kb.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
+    const unsigned long long varying = c->h_scal->kb.bits_or ^ c->h_scal->kb.bits_and;
+    int top = 0;                                         // number of low bits that can differ
+    while (top < 64 && (varying >> top) != 0ull) ++top;
+    const int end_bit = top < 1 ? 1 : top;
+    const int begin_bit = end_bit > 24 ? end_bit - 24 : 0;   // 3 radix passes of 8 bits
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, begin_bit, end_bit, c->stream));
+    c->stats.kernel_launches += 4;
+    const unsigned long long mask = begin_bit == 0 ? ~0ull : ~((1ull << begin_bit) - 1ull);
+    k_run_rank<<<nblk(n_in, SK_RR_TILE), 256, 0, c->stream>>>(dk.Current(), dv.Current(), n_in, mask, dk.Alternate(),
+                                                              dv.Alternate(), c->head.p, &c->d_kb->overflow);
     LAUNCH_CHECK();
     skeys = dk.Alternate();
     sidx = dv.Alternate();
@@ -344,11 +357,11 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   }
   CK(cub::DeviceScan::InclusiveSum(c->cub_tmp.p, tmp2, c->head.p, c->uid.p, (int)n_in, c->stream));
   c->stats.kernel_launches += 2;
-  // unique table sized for the worst case (n_unique <= n_in): no host round trip before the scatter
+  // unique table sized for the worst case (n_unique <= n_in): no host round trip before the compaction
   CK(c->uxs.ensure(n_in));
-  k_scatter_unique<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, sidx, c->head.p, c->uid.p, n_in, c->uxs.p, c->inv.p);
+  k_compact_unique<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, c->head.p, c->uid.p, n_in, c->uxs.p);
   LAUNCH_CHECK();
-  k_target_summary<<<1, 1, 0, c->stream>>>(c->uxs.p, c->uid.p, n_in, c->badflag.p, c->d_sum);
+  k_target_summary<<<1, 1, 0, c->stream>>>(c->uxs.p, c->uid.p, n_in, c->d_kb, c->d_sum);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
   CK(c->res.ensure(n_in));
@@ -359,6 +372,7 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   if (sm.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
   if (two_level && sm.overflow) return targets_from_device_buffer(c, n_in, info, false);   // heavily clustered input
   const long long nu = sm.n_unique;
+  c->sidx = sidx;                       // sorted position -> original position, for the final scatter
   c->n_in = n_in;
   c->n_unique = nu;
   c->r0 = sm.r0; c->r1 = sm.r1; c->r_last = sm.r_last;
@@ -427,6 +441,7 @@ int sk_ctx_create(int device, sk_ctx **out) {
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc((void **)&c->d_red, sizeof(SkReduceOut)) != cudaSuccess ||
       cudaMalloc((void **)&c->d_sum, sizeof(SkTargetSummary)) != cudaSuccess ||
+      cudaMalloc((void **)&c->d_kb, sizeof(SkKeyBits)) != cudaSuccess ||
       cudaMallocHost((void **)&c->h_scal, sizeof(HostScalars)) != cudaSuccess) {
     delete c;
     return SK_ERR_CUDA;
@@ -454,8 +469,9 @@ int sk_ctx_destroy(sk_ctx *c) {
   c->res.release(); c->pan.release(); c->stage.release();
   c->fftB.release(); c->dsumB.release(); c->bufb1.release(); c->bufb2.release();
   if (c->d_sum) cudaFree(c->d_sum);
+  if (c->d_kb) cudaFree(c->d_kb);
   c->keys.release(); c->keys_alt.release(); c->idx.release(); c->idx_alt.release();
-  c->head.release(); c->uid.release(); c->inv.release(); c->cub_tmp.release(); c->badflag.release();
+  c->head.release(); c->uid.release(); c->cub_tmp.release();
   if (c->d_red) cudaFree(c->d_red);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -973,7 +989,7 @@ int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
   int rc = flush_commit(c);
   if (rc != SK_OK) return rc;
-  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, vals_dev, errs_dev);
+  k_scatter_out<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->sidx, c->uid.p, c->res.p, c->n_in, vals_dev, errs_dev);
   LAUNCH_CHECK();
   CK(cudaStreamSynchronize(c->stream));
   return SK_OK;
@@ -987,7 +1003,8 @@ int sk_results_get(sk_ctx *c, double *vals, double *errs) {
   if (rc != SK_OK) return rc;
   CK(c->out_v.ensure(c->n_in));
   if (errs) CK(c->out_e.ensure(c->n_in));
-  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, c->out_v.p, errs ? c->out_e.p : nullptr);
+  k_scatter_out<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->sidx, c->uid.p, c->res.p, c->n_in, c->out_v.p,
+                                                           errs ? c->out_e.p : nullptr);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(vals, c->out_v.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
   if (errs) CK(cudaMemcpyAsync(errs, c->out_e.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));

@@ -16,7 +16,7 @@
 //                                                                 src/adaptive.jl:163-164, :183-199
 //       k_scan_add          errs += 2 trunc_err for the converged tail   src/adaptive.jl:194
 //   K7  k_direct            direct Fourier summation              src/quadrature.jl:113-128
-//   K8  k_make_keys, k_flag_heads, k_scatter_unique, k_target_summary, k_gather
+//   K8  k_make_keys, k_run_rank, k_compact_unique, k_target_summary, k_scatter_out
 //                           unique/sort/scatter                   src/adaptive.jl:99-120
 #pragma once
 #include <cuda_runtime.h>
@@ -112,11 +112,15 @@ __global__ void k_prep_sources(const __grid_constant__ SkGeom G, long long M, co
   cs[k] = c;
 }
 
-// Spread + mode deconvolution + zero-pad.  Gather: every FFT-input element sums the sources whose
-// kernel support covers it -- no atomics, bitwise reproducible.  Gauss nodes cluster at the sub-panel
-// ends (hundreds of sources within one kernel width there), so SK_SPREAD_LANES lanes share one element:
-// lane t takes sources a+t, a+t+L, ... and the partial sums are combined in a fixed butterfly order.
+// Spread + mode deconvolution.  Gather: every spread-grid cell sums the sources whose kernel support
+// covers it, in source order -- no atomics, bitwise reproducible.  (The zero-padded part of the FFT
+// input is cleared by a memset before this kernel.)  One block = SK_SPREAD_CELLS consecutive cells;
+// one warp finds the block's first relevant source with a 32-ary search; SK_SPREAD_LANES lanes share
+// one cell (Gauss nodes cluster at the sub-panel ends: hundreds of sources within one kernel width
+// there), lane t takes sources s0+t, s0+t+L, ... and the partial sums are combined in a fixed
+// butterfly order.
 #define SK_SPREAD_LANES 8
+#define SK_SPREAD_CELLS (256 / SK_SPREAD_LANES)
 struct SkSpreadSrc {
   const double *pos_hi[2];
   const double *pos_lo[2];
@@ -126,30 +130,47 @@ struct SkSpreadSrc {
 __global__ void __launch_bounds__(256)
 k_spread_modes(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G,
                const __grid_constant__ SkSpreadSrc src, int nrule, sk_cplx *__restrict__ fft_io) {
-  const int sub = threadIdx.x & (SK_SPREAD_LANES - 1);
-  long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / SK_SPREAD_LANES;
   const int r = blockIdx.y;
-  const bool in_range = j < G.nf2;                          // whole lane groups agree; keep all lanes for the shuffles
-  if (!in_range) j = G.nf2 - 1;
-  const long long n = (j < G.nf2 / 2) ? j : j - G.nf2;      // signed mode index
-  double ar = 0.0, ai = 0.0;
-  const bool live = in_range && !(n < -(G.nf / 2) || n >= G.nf / 2);
-  if (live) {
-    const double *__restrict__ ph = src.pos_hi[r];
-    const double *__restrict__ pl = src.pos_lo[r];
-    const sk_cplx *__restrict__ cs = src.cs[r];
-    const long long M = src.M[r];
-    const double ctr = (double)n, half = 0.5 * P.w;
-    const double lo_edge = ctr - half - 1e-6, hi_edge = ctr + half + 1e-6;
-    long long a = 0, b = M;
-    while (a < b) {                                         // first source with pos >= lo_edge
-      const long long mid = (a + b) >> 1;
-      if (ph[mid] < lo_edge) a = mid + 1; else b = mid;
+  const double *__restrict__ ph = src.pos_hi[r];
+  const double *__restrict__ pl = src.pos_lo[r];
+  const sk_cplx *__restrict__ cs = src.cs[r];
+  const long long M = src.M[r];
+  const double half = 0.5 * P.w;
+  const long long l_blk = (long long)blockIdx.x * SK_SPREAD_CELLS;       // first cell of the block
+  __shared__ long long s_start;
+  if (threadIdx.x < 32) {
+    // first source with pos >= (lower edge of the block's first cell), 32-ary search by one warp
+    const double edge = (double)(l_blk - G.nf / 2) - half - 1e-6;
+    long long lo = 0, hi = M;
+    const int lane = threadIdx.x;
+    while (hi > lo) {
+      const long long step = (hi - lo + 31) / 32;
+      const long long probe = lo + (long long)lane * step;
+      const bool below = probe < hi && ph[probe] < edge;
+      const unsigned int m = __ballot_sync(0xffffffffu, below);
+      const int cnt = __popc(m);                                        // sorted: the first cnt probes are below
+      if (cnt == 0) { hi = lo; break; }
+      const long long nlo = lo + (long long)(cnt - 1) * step + 1;
+      const long long nhi = lo + (long long)cnt * step;
+      lo = nlo;
+      hi = nhi < hi ? nhi : hi;
     }
+    if (lane == 0) s_start = lo;
+  }
+  __syncthreads();
+  const int sub = threadIdx.x & (SK_SPREAD_LANES - 1);
+  const long long l = l_blk + (threadIdx.x / SK_SPREAD_LANES);
+  const bool live = l < G.nf;
+  const long long n = l - G.nf / 2;                                      // signed mode index
+  double ar = 0.0, ai = 0.0;
+  if (live) {
+    const double ctr = (double)n;
+    const double lo_edge = ctr - half - 1e-6, hi_edge = ctr + half + 1e-6;
     const double inv_half = 1.0 / half;
-    for (long long k = a + sub; k < M; k += SK_SPREAD_LANES) {
+    for (long long k = s_start + sub; k < M; k += SK_SPREAD_LANES) {
       const double p = ph[k];
       if (p > hi_edge) break;
+      if (p < lo_edge) continue;
       const double z = ((ctr - p) - pl[k]) * inv_half;
       const double wgt = sk_es_direct(z, P.beta);
       const sk_cplx c = cs[k];
@@ -158,20 +179,17 @@ k_spread_modes(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     }
   }
 #pragma unroll
-  for (int o = SK_SPREAD_LANES / 2; o > 0; o >>= 1) {       // fixed-order butterfly inside the lane group
+  for (int o = SK_SPREAD_LANES / 2; o > 0; o >>= 1) {                   // fixed-order butterfly inside the lane group
     ar += __shfl_xor_sync(0xffffffffu, ar, o);
     ai += __shfl_xor_sync(0xffffffffu, ai, o);
   }
-  if (sub == 0 && in_range) {
+  if (sub == 0 && live) {
+    double q = sk_deconv(P, G.t_cell * fabs((double)n));
+    if (n & 1) q = -q;                                                   // shifts the FFT output by nf2/2
     sk_cplx o;
-    o.x = 0.0;
-    o.y = 0.0;
-    if (live) {
-      double q = sk_deconv(P, G.t_cell * fabs((double)n));
-      if (n & 1) q = -q;                                    // shifts the FFT output by nf2/2
-      o.x = ar * q;
-      o.y = ai * q;
-    }
+    o.x = ar * q;
+    o.y = ai * q;
+    const long long j = n >= 0 ? n : n + G.nf2;                          // FFT-input index of mode n
     fft_io[j * nrule + r] = o;
   }
 }
@@ -214,6 +232,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
   double *sO = sE + (W / 2) * (SK_NC / 2);
   double *sWin = sO + (W / 2) * (SK_NC / 2);            // [(cmax + W)][4]
   double *sCoef = sWin + (size_t)(cmax + W) * 4;        // [cmax][SK_NC][4]
+  __shared__ sk_cplx sTab[65];                          // (cos, sin)(2 pi k / 64) for the post-phase
   const long long j0 = (long long)blockIdx.x * SK_TPB;
   const int cnt = (int)((n - j0) < (long long)SK_TPB ? (n - j0) : (long long)SK_TPB);
   const long long l_first = sk_target_coord<W>(G, xs[j0]).l0;
@@ -227,6 +246,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       sE[t] = P.E[t / (SK_NC / 2)][t % (SK_NC / 2)];
       sO[t] = P.O[t / (SK_NC / 2)][t % (SK_NC / 2)];
     }
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + 65) sk_sincos2pi_table_fill(sTab, threadIdx.x - 128);
     // A: window of (ncell + W - 1) grid points x 2 rules, 32 bytes per point
     const double4 *gsrc = reinterpret_cast<const double4 *>(grid + (size_t)l_first * 2);
     double4 *wdst = reinterpret_cast<double4 *>(sWin);
@@ -258,7 +278,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
         double a[4];
         sk_cell_horner<4>(sCoef + (size_t)cell * SK_NC * 4, tc.s, a);
         double sn, cs;
-        sk_post_phase(G, r, &sn, &cs);
+        sk_sincos2pi(sTab, sk_frac_prod(G.wc, r, 0.0), &sn, &cs);      // post-phase exp(2 pi i wc r)
         double f1, f2;
         if (kernel_sin) {
           f1 = a[0] * sn + a[1] * cs;
@@ -471,51 +491,90 @@ __global__ void k_scan_add(const double *__restrict__ xs, sk_cplx *__restrict__ 
 
 // ---- K8 ---------------------------------------------------------------------------------------------
 // keys: bit patterns of the (non-negative) doubles, which order like unsigned integers; -0.0 -> +0.0.
-__global__ void k_make_keys(const double *__restrict__ xs, long long n, unsigned long long *__restrict__ keys,
-                            unsigned int *__restrict__ idx, unsigned int *__restrict__ bad) {
+// Also reduces OR / AND of all keys: the bits that differ between any two keys are (OR ^ AND), which
+// tells the host which 24 bits are worth radix-sorting (SkKeyBits).
+struct SkKeyBits {
+  unsigned long long bits_or, bits_and;
+  unsigned int bad;        // a distance was NaN / negative / infinite
+  unsigned int overflow;   // a run was too long for the two-level sort
+};
+__global__ void __launch_bounds__(256)
+k_make_keys(const double *__restrict__ xs, long long n, unsigned long long *__restrict__ keys,
+            unsigned int *__restrict__ idx, SkKeyBits *__restrict__ kb) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  double x = xs[j];
-  if (!(x >= 0.0) || isinf(x)) { atomicOr(bad, 1u); x = 0.0; }
-  if (x == 0.0) x = 0.0;
-  keys[j] = (unsigned long long)__double_as_longlong(x);
-  idx[j] = (unsigned int)j;
+  unsigned long long k_or = 0ull, k_and = ~0ull;
+  if (j < n) {
+    double x = xs[j];
+    if (!(x >= 0.0) || isinf(x)) { atomicOr(&kb->bad, 1u); x = 0.0; }
+    if (x == 0.0) x = 0.0;
+    const unsigned long long k = (unsigned long long)__double_as_longlong(x);
+    keys[j] = k;
+    idx[j] = (unsigned int)j;
+    k_or = k;
+    k_and = k;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    k_or |= __shfl_xor_sync(0xffffffffu, k_or, o);
+    k_and &= __shfl_xor_sync(0xffffffffu, k_and, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicOr(&kb->bits_or, k_or);
+    atomicAnd(&kb->bits_and, k_and);
+  }
 }
 
-// Second half of the two-level sort.  The radix sort ordered the pairs by the HIGH 32 bits of the key
-// only (4 digit passes instead of 8, stable).  Runs of equal high words are short for real distance
-// sets (a few elements), so every element finds its run by walking left/right and ranks itself inside
-// it on the full 64-bit key (ties: earlier position first => stable).  It writes itself to its final
-// sorted position together with its "first of its value" flag.  Runs longer than lmax raise
-// *overflow and the caller falls back to the full 8-pass sort.
+// Second half of the two-level sort.  The radix sort ordered the pairs by 24 key bits only (3 digit
+// passes instead of 8, stable); `mask` selects those bits and everything above them (the bits above are
+// equal in all keys).  Runs of equal masked keys are short for real distance sets (a handful of elements),
+// so every element finds its run by walking left/right in a shared-memory tile (with a halo of SK_RR_HALO
+// keys on both sides) and ranks itself inside it on the full 64-bit key (ties: earlier position first =>
+// stable).  It writes itself to its final sorted position together with its "first of its value" flag.
+// A run that reaches the end of the halo raises *overflow and the caller falls back to the full sort.
+#define SK_RR_TILE 2048
+#define SK_RR_HALO 128
 __global__ void __launch_bounds__(256)
-k_run_rank(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ idx, long long n, int lmax,
-           unsigned long long *__restrict__ keys_out, unsigned int *__restrict__ idx_out, unsigned int *__restrict__ head_out,
-           unsigned int *__restrict__ overflow) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned long long k = keys[i];
-  const unsigned int hw = (unsigned int)(k >> 32);
-  long long rank = 0;
-  bool first = true;
-  long long s = i;
-  while (s > 0 && (unsigned int)(keys[s - 1] >> 32) == hw) {
-    --s;
-    const unsigned long long o = keys[s];
-    if (o <= k) ++rank;                  // earlier position wins ties
-    if (o == k) first = false;
-    if (i - s > lmax) { atomicOr(overflow, 1u); return; }
+k_run_rank(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ idx, long long n,
+           unsigned long long mask, unsigned long long *__restrict__ keys_out, unsigned int *__restrict__ idx_out,
+           unsigned int *__restrict__ head_out, unsigned int *__restrict__ overflow) {
+  __shared__ unsigned long long sk[SK_RR_TILE + 2 * SK_RR_HALO];
+  const long long t0 = (long long)blockIdx.x * SK_RR_TILE;          // first element of the tile
+  const long long g0 = t0 - SK_RR_HALO;                             // global index of sk[0]
+  for (int t = threadIdx.x; t < SK_RR_TILE + 2 * SK_RR_HALO; t += blockDim.x) {
+    const long long g = g0 + t;
+    sk[t] = (g >= 0 && g < n) ? keys[g] : 0ull;
   }
-  long long e = i + 1;
-  while (e < n && (unsigned int)(keys[e] >> 32) == hw) {
-    if (keys[e] < k) ++rank;
-    ++e;
-    if (e - i > lmax) { atomicOr(overflow, 1u); return; }
+  __syncthreads();
+  const long long lo_g = g0 < 0 ? 0 : g0;                           // valid global range held in smem
+  const long long hi_g = (g0 + SK_RR_TILE + 2 * SK_RR_HALO) < n ? (g0 + SK_RR_TILE + 2 * SK_RR_HALO) : n;
+#pragma unroll 1
+  for (int u = 0; u < SK_RR_TILE / 256; ++u) {
+    const long long i = t0 + threadIdx.x + u * 256;
+    if (i >= n) break;
+    const unsigned long long k = sk[i - g0];
+    const unsigned long long hw = k & mask;
+    long long rank = 0;
+    bool first = true, over = false;
+    long long s = i;
+    while (s > lo_g && (sk[s - 1 - g0] & mask) == hw) {
+      --s;
+      const unsigned long long o = sk[s - g0];
+      if (o <= k) ++rank;                  // earlier position wins ties
+      if (o == k) first = false;
+    }
+    if (s == lo_g && s > 0) over = true;   // the run may continue beyond the halo
+    long long e = i + 1;
+    while (e < hi_g && (sk[e - g0] & mask) == hw) {
+      if (sk[e - g0] < k) ++rank;
+      ++e;
+    }
+    if (e == hi_g && e < n) over = true;
+    if (over) { atomicOr(overflow, 1u); continue; }
+    const long long pos = s + rank;
+    keys_out[pos] = k;
+    idx_out[pos] = idx[i];
+    head_out[pos] = first ? 1u : 0u;
   }
-  const long long pos = s + rank;
-  keys_out[pos] = k;
-  idx_out[pos] = idx[i];
-  head_out[pos] = first ? 1u : 0u;
 }
 
 __global__ void k_flag_heads(const unsigned long long *__restrict__ keys, long long n, unsigned int *__restrict__ head) {
@@ -524,39 +583,40 @@ __global__ void k_flag_heads(const unsigned long long *__restrict__ keys, long l
   head[j] = (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
 }
 
-// uid = inclusive-scan(head) - 1; unique value table and inverse map (original position -> unique id)
-__global__ void k_scatter_unique(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ idx,
-                                 const unsigned int *__restrict__ head, const unsigned int *__restrict__ uid_incl,
-                                 long long n, double *__restrict__ uxs, unsigned int *__restrict__ inv) {
+// uid = inclusive-scan(head); unique value table uxs[uid - 1] (the guards only matter when the two-level
+// sort overflowed and left garbage behind -- the caller then redoes the sort -- never write out of bounds)
+__global__ void k_compact_unique(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ head,
+                                 const unsigned int *__restrict__ uid_incl, long long n, double *__restrict__ uxs) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const unsigned int u = uid_incl[j] - 1u;
-  // the guards only matter when the two-level sort overflowed and left garbage behind (the caller then
-  // redoes the sort): never write out of bounds
   if (head[j] && (long long)u < n) uxs[u] = __longlong_as_double((long long)keys[j]);
-  if ((long long)idx[j] < n) inv[idx[j]] = u;
 }
 
 __global__ void k_target_summary(const double *__restrict__ uxs, const unsigned int *__restrict__ uid_incl, long long n,
-                                 const unsigned int *__restrict__ bad, SkTargetSummary *__restrict__ out) {
-  out->overflow = bad[1];
+                                 const SkKeyBits *__restrict__ kb, SkTargetSummary *__restrict__ out) {
   long long nu = uid_incl[n - 1];
   if (nu < 1 || nu > n) nu = 1;          // only after an overflowed two-level sort
+  out->overflow = kb->overflow;
   out->n_unique = nu;
   out->r0 = uxs[0];
   out->r1 = nu > 1 ? uxs[1] : 0.0;
   out->r_last = uxs[nu - 1];
-  out->bad = *bad;
+  out->bad = kb->bad;
 }
 
-// values and errors in the original input order from res = (ks, errs): one 16-byte random read per target
-__global__ void k_gather(const unsigned int *__restrict__ inv, const sk_cplx *__restrict__ res, long long n,
-                         double *__restrict__ out_v, double *__restrict__ out_e) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const sk_cplx r = res[inv[j]];
-  out_v[j] = r.x;
-  if (out_e) out_e[j] = r.y;
+// values and errors back in the ORIGINAL input order (src/adaptive.jl:105-107): sorted position i holds
+// original position sidx[i] and unique id uid_incl[i]-1.  Reads are coalesced (uid is non-decreasing),
+// writes are the random side.
+__global__ void k_scatter_out(const unsigned int *__restrict__ sidx, const unsigned int *__restrict__ uid_incl,
+                              const sk_cplx *__restrict__ res, long long n, double *__restrict__ out_v,
+                              double *__restrict__ out_e) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const sk_cplx r = res[uid_incl[i] - 1u];
+  const unsigned int o = sidx[i];
+  out_v[o] = r.x;
+  if (out_e) out_e[o] = r.y;
 }
 
 // number of sorted values <= r (== the largest 1-based index with xs[idx] <= r)

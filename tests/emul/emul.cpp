@@ -47,6 +47,8 @@ long long emul_interp_cells(const SkEsPlan *P, const SkGeom *G, long long N, con
   std::vector<double> E(8 * 8), O(8 * 8);
   for (int i = 0; i < 8; ++i) for (int q = 0; q < 8; ++q) { E[i * 8 + q] = P->E[i][q]; O[i * 8 + q] = P->O[i][q]; }
   long long npoly = 0;
+  sk_cplx tab[65];
+  for (int k = 0; k < 65; ++k) sk_sincos2pi_table_fill(tab, k);
   for (long long j0 = 0; j0 < N; j0 += tpb) {
     const int cnt = (int)std::min<long long>(tpb, N - j0);
     const long long lf = sk_target_coord<W>(*G, r[j0]).l0, ll = sk_target_coord<W>(*G, r[j0 + cnt - 1]).l0;
@@ -74,7 +76,7 @@ long long emul_interp_cells(const SkEsPlan *P, const SkGeom *G, long long N, con
         double a[4];
         sk_cell_horner<4>(coef.data() + (size_t)cell * SK_NC * 4, tc.s, a);
         double sn, cs;
-        sk_post_phase(*G, rr, &sn, &cs);
+        sk_sincos2pi(tab, sk_frac_prod(G->wc, rr, 0.0), &sn, &cs);
         double *o = out + (j0 + t) * 4;
         o[0] = a[0] * cs - a[1] * sn; o[1] = a[0] * sn + a[1] * cs;
         o[2] = a[2] * cs - a[3] * sn; o[3] = a[2] * sn + a[3] * cs;
@@ -122,6 +124,22 @@ void emul_gen_sources(int m, int k, double a, double b, double p, int origin_jac
 }
 
 int emul_gauss_rule(int n, double p, double *no, double *wt) { return sk_plan_gauss_rule(n, p, no, wt); }
+
+// max error of the lean sincos against libm over a sweep of |f| <= 1/2
+double emul_sincos_err(int n) {
+  sk_cplx tab[65];
+  for (int k = 0; k < 65; ++k) sk_sincos2pi_table_fill(tab, k);
+  double worst = 0.0;
+  for (int i = 0; i <= n; ++i) {
+    const double f = -0.5 + (double)i / n;
+    double s, c;
+    sk_sincos2pi(tab, f, &s, &c);
+    const long double th = 6.283185307179586476925286766559L * (long double)f;
+    worst = std::fmax(worst, std::fabs((double)(sinl(th) - s)));
+    worst = std::fmax(worst, std::fabs((double)(cosl(th) - c)));
+  }
+  return worst;
+}
 
 double emul_trunc_err(double ta, double tn, double xpow, double x, int panel) { return sk_trunc_err(ta, tn, xpow, x, panel); }
 int emul_converged(double te, double pk, double tau, int crit) { return sk_converged(te, pk, tau, crit) ? 1 : 0; }

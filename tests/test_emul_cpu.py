@@ -157,6 +157,13 @@ def test_device_source_generator_matches_updatequadbufs(emul):
         assert np.max(np.abs(outs[3] / ref[3] - 1)) < 5e-15
 
 
+def test_lean_sincos(emul):
+    L, _ = emul
+    L.emul_sincos_err.restype = ctypes.c_double
+    L.emul_sincos_err.argtypes = [ctypes.c_int]
+    assert L.emul_sincos_err(2_000_003) <= 5e-16
+
+
 def test_convergence_predicate(emul):
     L, _ = emul
     L.emul_trunc_err.restype = ctypes.c_double
