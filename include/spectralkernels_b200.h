@@ -69,13 +69,6 @@ typedef struct sk_target_info {
   double r_max;      /* largest distance                                                   */
 } sk_target_info;
 
-typedef struct sk_subinterval_opts {
-  double cmul;       /* config.c, src/adaptive.jl:43-45, applied at src/quadrature.jl:250-251        */
-  double p;          /* config.p, src/adaptive.jl:42                                                */
-  int32_t kernel;    /* SK_KERNEL_COS / SK_KERNEL_SIN, src/quadrature.jl:177                        */
-  int32_t logw;      /* config.logw: multiply the integrand by log(w), src/quadrature.jl:242        */
-} sk_subinterval_opts;
-
 typedef struct sk_scan_args {
   double trunc_a;    /* -c/(d+dim)*b^(d+dim), first bound of src/adaptive.jl:225-228 (target independent) */
   double trunc_num;  /* c*b^(d+(dim-1)/2), numerator of the second bound                                 */
@@ -84,6 +77,19 @@ typedef struct sk_scan_args {
   int32_t criteria;  /* SK_CRIT_*; the host switches to PANEL after a NaN tail fit (src/adaptive.jl:170-175) */
   int32_t _pad;
 } sk_scan_args;
+
+typedef struct sk_subinterval_opts {
+  double cmul;       /* config.c, src/adaptive.jl:43-45, applied at src/quadrature.jl:250-251        */
+  double p;          /* config.p, src/adaptive.jl:42                                                */
+  int32_t kernel;    /* SK_KERNEL_COS / SK_KERNEL_SIN, src/quadrature.jl:177                        */
+  int32_t logw;      /* config.logw: multiply the integrand by log(w), src/quadrature.jl:242        */
+  /* Optional (may be NULL).  On the FIRST sub-interval of a panel -- the whole panel [a,b] -- the host may
+   * pass the scan arguments it will use for this panel (they depend on (a,b) only: estimate_tail_decay,
+   * src/adaptive.jl:204-220).  The interpolation kernel then also applies ks += I2, errs += |I2-I1| and
+   * evaluates the convergence predicate, so that accept / commit / scan need no further pass over the
+   * targets if the sub-interval is accepted; if it is rejected the update is rolled back bit for bit. */
+  const sk_scan_args *speculate;
+} sk_subinterval_opts;
 
 typedef struct sk_stats {
   int64_t n_subintervals;   /* sub-intervals evaluated since sk_run_begin                     */
@@ -95,6 +101,8 @@ typedef struct sk_stats {
   int64_t kernel_launches;  /* kernels of this library launched since sk_run_begin             */
   int64_t last_nf;          /* spread-grid size of the last NUFFT                              */
   int64_t last_nf2;         /* FFT size of the last NUFFT                                      */
+  int64_t n_speculated;     /* sub-intervals whose commit/scan was fused into the interpolation kernel */
+  int64_t n_spec_rollbacks; /* ... of which were rejected and rolled back                      */
   double interp_ms;         /* device time in the interpolation kernel since sk_run_begin      */
   double source_ms;         /* device time in node/strength/spread/FFT since sk_run_begin      */
   int32_t timing_enabled;

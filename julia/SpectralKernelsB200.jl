@@ -25,11 +25,12 @@ const SK_SDF_MATERN, SK_SDF_EXPONENTIAL = Cint(1), Cint(2)
 struct TargetInfo            # sk_target_info
   n_in::Int64; n_unique::Int64; has_zero::Int32; _pad::Int32; r_min_pos::Float64; r_max::Float64
 end
-struct SubintervalOpts       # sk_subinterval_opts
-  cmul::Float64; p::Float64; kernel::Int32; logw::Int32
-end
 struct ScanArgs              # sk_scan_args
   trunc_a::Float64; trunc_num::Float64; xpow::Float64; tau::Float64; criteria::Int32; _pad::Int32
+end
+struct SubintervalOpts       # sk_subinterval_opts
+  cmul::Float64; p::Float64; kernel::Int32; logw::Int32
+  speculate::Ptr{ScanArgs}   # C_NULL, or the panel's scan arguments on the panel's first sub-interval
 end
 
 mutable struct Ctx
@@ -93,7 +94,9 @@ function kernel_values_b200(config::AdaptiveKernelConfig, xs::AbstractVector{Flo
   conv_crit  = config.convergence_criteria
   (a, b)     = (0.0, 0.0)
   kernel     = config.derivative ? SK_KERNEL_SIN : SK_KERNEL_COS           # quadrature.jl:177
-  opts       = Ref(SubintervalOpts(config.c, config.p, kernel, config.logw ? 1 : 0))
+  opts       = Ref(SubintervalOpts(config.c, config.p, kernel, config.logw ? 1 : 0, C_NULL))
+  # (optional optimisation, see sk_subinterval_opts.speculate: evaluate estimate_tail_decay(config, a, b)
+  #  before the panel and pass pointer_from_objref/Ref of the ScanArgs with the panel's first sub-interval)
   tau        = config.tol*abs(k0)/2
   while r_hi > 0                                                           # adaptive.jl:149
     (a, b) = (b, b + quadsz(config)/(2*r_hi))                              # adaptive.jl:152

@@ -34,19 +34,20 @@ class TargetInfo(ctypes.Structure):
                 ("r_min_pos", c_double), ("r_max", c_double)]
 
 
-class SubintervalOpts(ctypes.Structure):
-    _fields_ = [("cmul", c_double), ("p", c_double), ("kernel", c_int32), ("logw", c_int32)]
-
-
 class ScanArgs(ctypes.Structure):
     _fields_ = [("trunc_a", c_double), ("trunc_num", c_double), ("xpow", c_double), ("tau", c_double),
                 ("criteria", c_int32), ("_pad", c_int32)]
 
 
+class SubintervalOpts(ctypes.Structure):
+    _fields_ = [("cmul", c_double), ("p", c_double), ("kernel", c_int32), ("logw", c_int32),
+                ("speculate", POINTER(ScanArgs))]
+
+
 class Stats(ctypes.Structure):
     _fields_ = [("n_subintervals", c_int64), ("n_accepted", c_int64), ("n_panels", c_int64), ("units", c_int64),
                 ("n_fast", c_int64), ("n_direct", c_int64), ("kernel_launches", c_int64), ("last_nf", c_int64),
-                ("last_nf2", c_int64), ("interp_ms", c_double), ("source_ms", c_double),
+                ("last_nf2", c_int64), ("n_speculated", c_int64), ("n_spec_rollbacks", c_int64), ("interp_ms", c_double), ("source_ms", c_double),
                 ("timing_enabled", c_int32), ("sort_two_level", c_int32)]
 
     def as_dict(self):
@@ -283,14 +284,16 @@ class Session:
     def panel_set_range(self, r_lo: float, r_hi: float):
         self._ck(self._L.sk_panel_set_range(self._h, float(r_lo), float(r_hi)))
 
-    def subinterval(self, a: float, b: float, cmul: float, p: float, kernel: int, logw: bool) -> float:
-        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0)
+    def subinterval(self, a: float, b: float, cmul: float, p: float, kernel: int, logw: bool, speculate=None) -> float:
+        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0,
+                            ctypes.pointer(speculate) if speculate is not None else None)
         out = c_double()
         self._ck(self._L.sk_subinterval(self._h, float(a), float(b), byref(o), byref(out)))
         return out.value
 
-    def subinterval_host(self, a, b, no1, buf1, no2, buf2, cmul, p, kernel, logw) -> float:
-        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0)
+    def subinterval_host(self, a, b, no1, buf1, no2, buf2, cmul, p, kernel, logw, speculate=None) -> float:
+        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0,
+                            ctypes.pointer(speculate) if speculate is not None else None)
         out = c_double()
         no1, buf1, no2, buf2 = _f64(no1), _f64(buf1), _f64(no2), _f64(buf2)
         self._ck(self._L.sk_subinterval_host(self._h, float(a), float(b), _p(no1), _p(buf1), _p(no2), _p(buf2),
@@ -298,7 +301,7 @@ class Session:
         return out.value
 
     def subinterval_logw_host(self, a, b, no1, bufa1, bufb1, no2, bufa2, bufb2, cmul, p, i0_coef, denom) -> float:
-        o = SubintervalOpts(float(cmul), float(p), SK_KERNEL_COS, 1)
+        o = SubintervalOpts(float(cmul), float(p), SK_KERNEL_COS, 1, None)
         out = c_double()
         arrs = [_f64(x) for x in (no1, bufa1, bufb1, no2, bufa2, bufb2)]
         self._ck(self._L.sk_subinterval_logw_host(self._h, float(a), float(b), *[_p(x) for x in arrs], byref(o),

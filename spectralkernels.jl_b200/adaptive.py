@@ -241,7 +241,7 @@ def _host_strengths(cfg: AdaptiveKernelConfig, eng, a: float, b: float, origin: 
 
 
 def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: float, k0: float, comm, active: bool,
-                               verbose: bool = False, trace: Optional[list] = None):
+                               verbose: bool = False, trace: Optional[list] = None, speculate=None):
     """Scalar control flow of src/quadrature.jl:169-275: LIFO bisection, accept test against
     config.tol*k0 (not the split tolerance), 9:1 tolerance split at the origin.  The per-target work of
     every pass happens inside sk_subinterval / sk_subinterval_accept."""
@@ -250,8 +250,13 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
     kernel = SK_KERNEL_SIN if cfg.derivative else SK_KERNEL_COS                  # :177
     stack = [(a, b, cfg.tol)]                                                    # :173
     builtin = is_builtin(cfg.f)
+    first = True
     while stack:
         _a, _b, _tol = stack.pop()                                               # :183
+        # the first interval popped is the whole panel: let the device fuse accept / commit / scan into
+        # the interpolation kernel (rolled back by the library if the interval is rejected)
+        spec = speculate if first else None
+        first = False
         origin = (_a == 0.0 and cfg.p != 0.0)                                    # :185
         if abs(_b - _a) <= 1e-16:                                                # utils.jl:28-36
             raise RuntimeError(f"The sub-interval (a, b) = ({_a}, {_b}) has been split too many times "
@@ -269,10 +274,10 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
                 mx = eng.subinterval_logw_host(_a, _b, no1, ba1, bb1, no2, ba2, bb2, cfg.c, cfg.p, i0,
                                                cfg.dim - cfg.alpha)
             elif builtin:
-                mx = eng.subinterval(_a, _b, cfg.c, cfg.p, kernel, cfg.logw)
+                mx = eng.subinterval(_a, _b, cfg.c, cfg.p, kernel, cfg.logw, speculate=spec)
             else:
                 no1, buf1, no2, buf2 = _host_strengths(cfg, eng, _a, _b, origin)
-                mx = eng.subinterval_host(_a, _b, no1, buf1, no2, buf2, cfg.c, cfg.p, kernel, cfg.logw)
+                mx = eng.subinterval_host(_a, _b, no1, buf1, no2, buf2, cfg.c, cfg.p, kernel, cfg.logw, speculate=spec)
         else:
             mx = 0.0
         # max over all ranks; NaN travels as +inf (both fail the accept test, quadrature.jl:260)
@@ -358,20 +363,27 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
             eng.panel_begin(ix1, hi)
             if comm.world_size > 1:
                 eng.panel_set_range(r_lo_g, r_hi_g)
-        fourier_integrate_interval(cfg, eng, a, b, abs(k0), comm, active, verbose=verbose, trace=trace)   # :157-159
-        if active:
-            eng.panel_commit()                                                   # :163-164
+        # The tail fit depends on (a, b) only, so it is evaluated BEFORE the panel is integrated (the
+        # reference does it after, src/adaptive.jl:168): the scan arguments can then ride along with the
+        # panel's first sub-interval.
         if crit == "panel":                                                      # :168
             c = d = float("nan")
         else:
             c, d = estimate_tail_decay(cfg, a, b, d=cfg.tail)
         if (math.isnan(c) or math.isnan(d)) and crit != "panel":                 # :170-175
-            if verbose:
-                print("\talgebraic tail estimate failed -- using convergence_criteria = :panel")
+            crit_msg = "\talgebraic tail estimate failed -- using convergence_criteria = :panel"
             crit = "panel"
-        elif crit != "panel" and verbose:
-            print(f"\talgebraic tail estimate S(w) ≈ {c:.2e} * w^({d:.2f})")
+        elif crit != "panel":
+            crit_msg = f"\talgebraic tail estimate S(w) ≈ {c:.2e} * w^({d:.2f})"
+        else:
+            crit_msg = None
         sargs = _scan_args(cfg, b, c, d, tau, crit)
+        fourier_integrate_interval(cfg, eng, a, b, abs(k0), comm, active, verbose=verbose, trace=trace,
+                                   speculate=sargs)                              # :157-159
+        if active:
+            eng.panel_commit()                                                   # :163-164
+        if verbose and crit_msg:
+            print(crit_msg)
         hi_before = hi
         if active:
             new_hi, r_stop = eng.converge_scan(sargs)                            # :183-198

@@ -84,7 +84,7 @@ struct sk_ctx {
   DevBuf<double> in, uxs, out_v, out_e;
   DevBuf<sk_cplx> res, pan, stage;   // (ks, errs), (I, err), (I2, |I2-I1|) per unique target
   DevBuf<unsigned long long> keys, keys_alt;
-  DevBuf<unsigned int> idx, idx_alt, head, uid;
+  DevBuf<unsigned int> idx, idx_alt, head, uid, inv;
   DevBuf<unsigned char> cub_tmp;
   SkKeyBits *d_kb = nullptr;
   const unsigned int *sidx = nullptr;        // sorted position -> original position (one of idx / idx_alt)
@@ -99,6 +99,12 @@ struct sk_ctx {
   long long scan_hi = -1;                    // 1-based index / distance returned by the last scan
   double scan_r = 0;
   int interp_mode = 0;                       // 0: cell polynomials (default), 1: per-target taps
+  // speculative commit of the panel's first sub-interval (see sk_subinterval_opts::speculate)
+  bool spec_active = false, spec_accepted = false;
+  long long panel_subs = 0;                  // sub-intervals evaluated in the open panel
+  sk_scan_args spec_args;
+  long long spec_new_hi = 0;
+  double spec_r = 0;
   SkTargetSummary *d_sum = nullptr;
 
   SkReduceOut *d_red = nullptr;
@@ -142,6 +148,7 @@ int fail(sk_ctx *c, int code, const char *fmt, ...) {
   } while (0)
 
 inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
+int flush_commit(sk_ctx *c);
 
 int width_from_eps(double eps) {
   int w = (int)std::ceil(-std::log10(eps / 10.0));
@@ -172,22 +179,22 @@ int get_fft_plan(sk_ctx *c, long long nf2, int batch, cufftHandle *out) {
 }
 
 template <int W>
-int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long long n, double cmul, int ksin) {
+int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long long n, double cmul, int ksin, const SkSpec &spec) {
   if (c->interp_mode == 1) {
-    k_interp_session<W><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage.p + c->lo, c->d_red);
+    k_interp_session<W><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage.p + c->lo, spec, c->d_red);
     return 0;
   }
   // cells the active targets span -> average targets per cell -> how many cells a block may hold
   const double span = (c->r_hi - c->r_lo) * G.kap_hi + 1.0;
   const double per_block = span * (double)SK_TPB / (double)n;
   const int cmax = per_block <= 24.0 ? 32 : 96;
-  const size_t smem = sizeof(double) * (size_t)(2 * (W / 2) * (SK_NC / 2) + (cmax + W) * 4 + cmax * SK_NC * 4);
+  const size_t smem = sizeof(double) * (size_t)(2 * (W / 2) * (SK_NC / 2) + (cmax + W) * 4 + cmax * 4 + cmax * SK_NC * 4);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_interp_cells<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;
   }
-  k_interp_cells<W><<<nblk(n, SK_TPB), 256, smem, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, cmax, c->stage.p + c->lo, c->d_red);
+  k_interp_cells<W><<<nblk(n, SK_TPB), 256, smem, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, cmax, c->stage.p + c->lo, spec, c->d_red);
   return 0;
 }
 template <int W>
@@ -249,9 +256,31 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
   const long long n_act = c->hi - c->lo;
   const long long M1 = (long long)c->m * c->k, M2 = 2 * M1;
   const int ksin = o->kernel == SK_KERNEL_SIN;
-  CK(cudaMemsetAsync(c->d_red, 0, sizeof(SkReduceOut), c->stream));
   // fast = nufft_quad_size_cutoff(length(no2), length(xs)) && length(xs) > 1   (src/quadrature.jl:105, src/utils.jl:39)
   const bool fast = (M2 * n_act > (1LL << 18)) && n_act > 1;
+  // speculation is only meaningful for the first sub-interval of the panel (the whole panel)
+  const bool spec_on = fast && o->speculate != nullptr && c->panel_subs == 0 && o->speculate->criteria >= 0 &&
+                       o->speculate->criteria <= 2;
+  SkSpec spec;
+  std::memset(&spec, 0, sizeof(spec));
+  if (spec_on) {
+    int rc = flush_commit(c);            // res must be current before it is updated in place
+    if (rc != SK_OK) return rc;
+    spec.on = 1;
+    spec.criteria = o->speculate->criteria;
+    spec.lo0 = c->lo;
+    spec.trunc_a = o->speculate->trunc_a;
+    spec.trunc_num = o->speculate->trunc_num;
+    spec.xpow = o->speculate->xpow;
+    spec.tau = o->speculate->tau;
+    spec.res = c->res.p + c->lo;
+    spec.backup = c->stage.p + c->lo;
+  }
+  SkReduceOut init;
+  std::memset(&init, 0, sizeof(init));
+  init.max_unconv = c->lo - 1;
+  c->h_scal->red = init;
+  CK(cudaMemcpyAsync(c->d_red, &c->h_scal->red, sizeof(init), cudaMemcpyHostToDevice, c->stream));
   if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
   if (fast) {
     SkGeom G;
@@ -260,7 +289,7 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
     int rc = run_source_side(c, G, 2, M1, c->buf1.p, nullptr, M2, c->buf2.p, c->fft);
     if (rc != SK_OK) return rc;
     if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
-#define CALL(WW) launch_interp_session<WW>(c, G, c->uxs.p + c->lo, n_act, o->cmul, ksin)
+#define CALL(WW) launch_interp_session<WW>(c, G, c->uxs.p + c->lo, n_act, o->cmul, ksin, spec)
     DISPATCH_W(c->plan.w, CALL)
 #undef CALL
     LAUNCH_CHECK();
@@ -290,10 +319,34 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
   if (fl & SK_FLAG_NAND) mx = std::nan("");
   *max_abs_diff = mx;
   c->staged = true;
+  c->panel_subs++;
   c->stats.n_subintervals++;
   c->stats.units += n_act;
+  if (spec_on) {
+    c->spec_active = true;
+    c->spec_accepted = false;
+    c->spec_args = *o->speculate;
+    const long long top = c->h_scal->red.max_unconv;
+    c->spec_new_hi = top + 1;
+    c->spec_r = 0.0;
+    if (top >= c->lo) std::memcpy(&c->spec_r, &c->h_scal->red.rbits, sizeof(double));
+    c->stats.n_speculated++;
+  }
   // any(isnan, int1) || any(isnan, int2) && throw(...)   (src/quadrature.jl:165)
   if (!(fl & SK_FLAG_NAN1) && (fl & SK_FLAG_NAN2)) return fail(c, SK_ERR_NAN, "NaN detected in panel integral...");
+  return SK_OK;
+}
+
+// a speculative commit that was not accepted is rolled back before anything else touches the panel
+int rollback_speculation(sk_ctx *c) {
+  if (c->spec_active && !c->spec_accepted) {
+    const long long n = c->hi - c->lo;
+    k_restore<<<nblk(n, 256), 256, 0, c->stream>>>(c->res.p + c->lo, c->stage.p + c->lo, n);
+    LAUNCH_CHECK();
+    c->spec_active = false;
+    c->staged = false;
+    c->stats.n_spec_rollbacks++;
+  }
   return SK_OK;
 }
 
@@ -317,7 +370,7 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   kb0.bits_or = 0ull; kb0.bits_and = ~0ull; kb0.bad = 0; kb0.overflow = 0;
   c->h_scal->kb = kb0;
   CK(cudaMemcpyAsync(c->d_kb, &c->h_scal->kb, sizeof(SkKeyBits), cudaMemcpyHostToDevice, c->stream));
-  k_make_keys<<<nblk(n_in, 256), 256, 0, c->stream>>>(c->in.p, n_in, c->keys.p, c->idx.p, c->d_kb);
+  k_make_keys<<<std::min<unsigned int>(nblk(n_in, 256), 148u * 16u), 256, 0, c->stream>>>(c->in.p, n_in, c->keys.p, c->idx.p, c->d_kb);
   LAUNCH_CHECK();
   cub::DoubleBuffer<unsigned long long> dk(c->keys.p, c->keys_alt.p);
   cub::DoubleBuffer<unsigned int> dv(c->idx.p, c->idx_alt.p);
@@ -338,9 +391,9 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
     int top = 0;                                         // number of low bits that can differ
     while (top < 64 && (varying >> top) != 0ull) ++top;
     const int end_bit = top < 1 ? 1 : top;
-    const int begin_bit = end_bit > 24 ? end_bit - 24 : 0;   // 3 radix passes of 8 bits
+    const int begin_bit = end_bit > 32 ? end_bit - 32 : 0;   // 4 radix passes of 8 bits
     CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, begin_bit, end_bit, c->stream));
-    c->stats.kernel_launches += 4;
+    c->stats.kernel_launches += 5;
     const unsigned long long mask = begin_bit == 0 ? ~0ull : ~((1ull << begin_bit) - 1ull);
     k_run_rank<<<nblk(n_in, SK_RR_TILE), 256, 0, c->stream>>>(dk.Current(), dv.Current(), n_in, mask, dk.Alternate(),
                                                               dv.Alternate(), c->head.p, &c->d_kb->overflow);
@@ -359,7 +412,8 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   c->stats.kernel_launches += 2;
   // unique table sized for the worst case (n_unique <= n_in): no host round trip before the compaction
   CK(c->uxs.ensure(n_in));
-  k_compact_unique<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, c->head.p, c->uid.p, n_in, c->uxs.p);
+  CK(c->inv.ensure(n_in));
+  k_scatter_unique<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, sidx, c->head.p, c->uid.p, n_in, c->uxs.p, c->inv.p);
   LAUNCH_CHECK();
   k_target_summary<<<1, 1, 0, c->stream>>>(c->uxs.p, c->uid.p, n_in, c->d_kb, c->d_sum);
   LAUNCH_CHECK();
@@ -471,7 +525,7 @@ int sk_ctx_destroy(sk_ctx *c) {
   if (c->d_sum) cudaFree(c->d_sum);
   if (c->d_kb) cudaFree(c->d_kb);
   c->keys.release(); c->keys_alt.release(); c->idx.release(); c->idx_alt.release();
-  c->head.release(); c->uid.release(); c->cub_tmp.release();
+  c->head.release(); c->uid.release(); c->inv.release(); c->cub_tmp.release();
   if (c->d_red) cudaFree(c->d_red);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -746,6 +800,9 @@ int sk_panel_begin(sk_ctx *c, int64_t ix1, int64_t hi, double *r_lo, double *r_h
   c->in_panel = true;
   c->staged = false;
   c->first_accept = true;
+  c->spec_active = false;
+  c->spec_accepted = false;
+  c->panel_subs = 0;
   return SK_OK;
 }
 
@@ -769,7 +826,7 @@ static int subinterval_prologue(sk_ctx *c, double a, double b, const sk_subinter
                 "The sub-interval (a, b) = (%.17g, %.17g) has been split too many times (b - a < 1e-16). "
                 "Exiting to avoid infinite splitting.", a, b);
   CK(cudaSetDevice(c->device));
-  return SK_OK;
+  return rollback_speculation(c);
 }
 
 int sk_subinterval(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, double *max_abs_diff) {
@@ -897,6 +954,14 @@ int sk_subinterval_accept(sk_ctx *c) {
   if (!c) return SK_ERR_ARG;
   if (!c->staged) return fail(c, SK_ERR_STATE, "no staged sub-interval");
   const long long n = c->hi - c->lo;
+  if (c->spec_active && !c->spec_accepted) {
+    // the interpolation kernel already applied ks += I2, errs += |I2-I1| (sk_subinterval_opts::speculate)
+    c->spec_accepted = true;
+    c->first_accept = false;
+    c->staged = false;
+    c->stats.n_accepted++;
+    return SK_OK;
+  }
   if (c->first_accept) {
     // I = 0 + I2, err = 0 + |I2-I1| exactly (src/quadrature.jl:174-175, :261-262): the staging buffer
     // becomes the panel buffer, no pass over the data
@@ -915,6 +980,10 @@ int sk_panel_commit(sk_ctx *c) {
   if (!c) return SK_ERR_ARG;
   if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
   const long long n = c->hi - c->lo;
+  if (c->spec_active && c->spec_accepted) {   // already in (ks, errs)
+    c->stats.n_panels++;
+    return SK_OK;
+  }
   if (c->first_accept)   // nothing was accepted: I = err = 0
     CK(cudaMemsetAsync(c->pan.p + c->lo, 0, sizeof(sk_cplx) * n, c->stream));
   // ks += I; errs += err (src/adaptive.jl:163-164) is deferred and fused with the convergence scan
@@ -930,6 +999,17 @@ int sk_converge_scan(sk_ctx *c, const sk_scan_args *a, int64_t *new_hi, double *
   if (!c || !a || !new_hi) return SK_ERR_ARG;
   if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
   if (a->criteria < 0 || a->criteria > 2) return fail(c, SK_ERR_ARG, "bad criteria");
+  if (c->spec_active && c->spec_accepted) {
+    const sk_scan_args &s0 = c->spec_args;
+    const bool same = s0.criteria == a->criteria && std::memcmp(&s0.trunc_a, &a->trunc_a, sizeof(double)) == 0 &&
+                      std::memcmp(&s0.trunc_num, &a->trunc_num, sizeof(double)) == 0 && s0.xpow == a->xpow && s0.tau == a->tau;
+    if (!same) return fail(c, SK_ERR_STATE, "scan arguments differ from the ones the panel was speculated with");
+    *new_hi = c->spec_new_hi;
+    if (r_at_new_hi) *r_at_new_hi = c->spec_r;
+    c->scan_hi = c->spec_new_hi;
+    c->scan_r = c->spec_r;
+    return SK_OK;
+  }
   const long long n = c->hi - c->lo;
   SkReduceOut init;
   std::memset(&init, 0, sizeof(init));
@@ -970,6 +1050,7 @@ int sk_converge_apply(sk_ctx *c, const sk_scan_args *a, int64_t new_hi) {
     LAUNCH_CHECK();
   }
   c->in_panel = false;
+  c->spec_active = false;
   return SK_OK;
 }
 
@@ -987,9 +1068,11 @@ int sk_target_upper_index(sk_ctx *c, double r, int64_t *idx) {
 int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
   if (!c || !vals_dev) return SK_ERR_ARG;
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
-  int rc = flush_commit(c);
+  int rc = rollback_speculation(c);
   if (rc != SK_OK) return rc;
-  k_scatter_out<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->sidx, c->uid.p, c->res.p, c->n_in, vals_dev, errs_dev);
+  rc = flush_commit(c);
+  if (rc != SK_OK) return rc;
+  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, vals_dev, errs_dev);
   LAUNCH_CHECK();
   CK(cudaStreamSynchronize(c->stream));
   return SK_OK;
@@ -999,12 +1082,13 @@ int sk_results_get(sk_ctx *c, double *vals, double *errs) {
   if (!c || !vals) return SK_ERR_ARG;
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
   CK(cudaSetDevice(c->device));
-  int rc = flush_commit(c);
+  int rc = rollback_speculation(c);
+  if (rc != SK_OK) return rc;
+  rc = flush_commit(c);
   if (rc != SK_OK) return rc;
   CK(c->out_v.ensure(c->n_in));
   if (errs) CK(c->out_e.ensure(c->n_in));
-  k_scatter_out<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->sidx, c->uid.p, c->res.p, c->n_in, c->out_v.p,
-                                                           errs ? c->out_e.p : nullptr);
+  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, c->out_v.p, errs ? c->out_e.p : nullptr);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(vals, c->out_v.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
   if (errs) CK(cudaMemcpyAsync(errs, c->out_e.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));

@@ -16,7 +16,7 @@
 //                                                                 src/adaptive.jl:163-164, :183-199
 //       k_scan_add          errs += 2 trunc_err for the converged tail   src/adaptive.jl:194
 //   K7  k_direct            direct Fourier summation              src/quadrature.jl:113-128
-//   K8  k_make_keys, k_run_rank, k_compact_unique, k_target_summary, k_scatter_out
+//   K8  k_make_keys, k_run_rank, k_scatter_unique, k_target_summary, k_gather
 //                           unique/sort/scatter                   src/adaptive.jl:99-120
 #pragma once
 #include <cuda_runtime.h>
@@ -40,6 +40,20 @@ struct SkTargetSummary {        // written by k_target_summary
   double r0, r1, r_last;        // smallest, second smallest and largest unique distance
   unsigned int bad;
   unsigned int overflow;        // a run of equal high words was too long for the two-level sort
+};
+
+// Speculative commit (the common case: the first sub-interval of a panel is accepted and is the whole
+// panel).  The interpolation kernel then also does  ks += I2, errs += |I2-I1|  in place (keeping the old
+// (ks, errs) pair in `backup` so that a rejected sub-interval can be rolled back bit for bit) and
+// evaluates the convergence predicate of src/adaptive.jl:185-197 on panel_ks = I2, so that no separate
+// pass over the targets is needed for src/quadrature.jl:261-262, src/adaptive.jl:163-164 and :183-198.
+struct SkSpec {
+  int on;
+  int criteria;
+  long long lo0;          // global 0-based index of element 0
+  double trunc_a, trunc_num, xpow, tau;
+  sk_cplx *res;           // (ks, errs), pre-offset to element 0
+  sk_cplx *backup;        // old (ks, errs), pre-offset
 };
 
 __device__ __forceinline__ double sk_warp_max(double v) {
@@ -81,6 +95,74 @@ __device__ __forceinline__ void sk_stage(double f1, double f2, double cmul, sk_c
   *dst = o;
   if (dd != dd) { fl |= SK_FLAG_NAND; dd = 0.0; }
   d = fmax(d, dd);
+}
+
+// per-thread state of the reductions of the interpolation kernels
+struct SkAcc {
+  double d;                 // max |I2-I1|
+  unsigned int fl;          // NaN flags
+  long long bad;            // highest non-converged global index seen (speculative scan), -1 if none
+  unsigned long long rb;    // bit pattern of its distance
+};
+
+// stage (spec.on == 0) or commit speculatively (spec.on == 1) the target with local index j, distance x
+__device__ __forceinline__ void sk_emit(const SkSpec &spec, double f1, double f2, double cmul, double x, long long j,
+                                        sk_cplx *stage, SkAcc &acc) {
+  if (!spec.on) {
+    sk_stage(f1, f2, cmul, &stage[j], acc.d, acc.fl);
+    return;
+  }
+  const double i1 = f1 * cmul, i2 = f2 * cmul;
+  double dd = fabs(i2 - i1);
+  if (i1 != i1) acc.fl |= SK_FLAG_NAN1;
+  if (i2 != i2) acc.fl |= SK_FLAG_NAN2;
+  const sk_cplx old = spec.res[j];
+  spec.backup[j] = old;
+  sk_cplx nw;
+  nw.x = old.x + i2;        // ks += I with I = 0 + I2   (src/quadrature.jl:261, src/adaptive.jl:163)
+  nw.y = old.y + dd;        // errs += err with err = 0 + |I2-I1|
+  spec.res[j] = nw;
+  if (dd != dd) { acc.fl |= SK_FLAG_NAND; dd = 0.0; }
+  acc.d = fmax(acc.d, dd);
+  const double te = sk_trunc_err(spec.trunc_a, spec.trunc_num, spec.xpow, x, spec.criteria == 0);
+  if (!sk_converged(te, i2, spec.tau, spec.criteria)) {
+    const long long g = spec.lo0 + j;
+    if (g > acc.bad) { acc.bad = g; acc.rb = (unsigned long long)__double_as_longlong(x); }
+  }
+}
+
+// block reduction of SkAcc -> device scalars
+__device__ __forceinline__ void sk_block_reduce_acc(SkAcc a, int spec_on, SkReduceOut *red) {
+  __shared__ double smax[32];
+  __shared__ unsigned int sfl[32];
+  __shared__ long long sbad[32];
+  __shared__ unsigned long long srb[32];
+  a.d = sk_warp_max(a.d);
+  a.fl = __reduce_or_sync(0xffffffffu, a.fl);
+  if (spec_on) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long ob = __shfl_xor_sync(0xffffffffu, a.bad, o);
+      const unsigned long long orb = __shfl_xor_sync(0xffffffffu, a.rb, o);
+      if (ob > a.bad) { a.bad = ob; a.rb = orb; }
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { smax[wid] = a.d; sfl[wid] = a.fl; sbad[wid] = a.bad; srb[wid] = a.rb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < nw; ++w) {
+      a.d = fmax(a.d, smax[w]);
+      a.fl |= sfl[w];
+      if (sbad[w] > a.bad) { a.bad = sbad[w]; a.rb = srb[w]; }
+    }
+    atomicMax(&red->maxbits, (unsigned long long)__double_as_longlong(a.d));
+    if (a.fl) atomicOr(&red->flags, a.fl);
+    if (spec_on && a.bad >= 0) {             // sorted unique distances: max index <=> max distance
+      atomicMax(&red->max_unconv, a.bad);
+      atomicMax(&red->rbits, a.rb);
+    }
+  }
 }
 
 // ---- K1 ---------------------------------------------------------------------------------------------
@@ -127,6 +209,30 @@ struct SkSpreadSrc {
   const sk_cplx *cs[2];
   long long M[2];
 };
+#define SK_SPREAD_CAP 512      // sources cached in shared memory per block
+__device__ __forceinline__ long long sk_warp_lower_bound(const double *__restrict__ ph, long long M, double edge,
+                                                         bool strict_greater) {
+  // first index with ph[i] >= edge (or > edge when strict_greater): 32-ary search by one full warp
+  long long lo = 0, hi = M;
+  const int lane = threadIdx.x & 31;
+  while (hi > lo) {
+    const long long step = (hi - lo + 31) / 32;
+    const long long probe = lo + (long long)lane * step;
+    bool below = false;
+    if (probe < hi) {
+      const double v = ph[probe];
+      below = strict_greater ? (v <= edge) : (v < edge);
+    }
+    const int cnt = __popc(__ballot_sync(0xffffffffu, below));            // sorted: the first cnt probes are below
+    if (cnt == 0) { hi = lo; break; }
+    const long long nlo = lo + (long long)(cnt - 1) * step + 1;
+    const long long nhi = lo + (long long)cnt * step;
+    lo = nlo;
+    hi = nhi < hi ? nhi : hi;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(256)
 k_spread_modes(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G,
                const __grid_constant__ SkSpreadSrc src, int nrule, sk_cplx *__restrict__ fft_io) {
@@ -137,25 +243,26 @@ k_spread_modes(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
   const long long M = src.M[r];
   const double half = 0.5 * P.w;
   const long long l_blk = (long long)blockIdx.x * SK_SPREAD_CELLS;       // first cell of the block
-  __shared__ long long s_start;
+  __shared__ long long s_range[2];
+  __shared__ double s_ph[SK_SPREAD_CAP], s_pl[SK_SPREAD_CAP];
+  __shared__ sk_cplx s_cs[SK_SPREAD_CAP];
   if (threadIdx.x < 32) {
-    // first source with pos >= (lower edge of the block's first cell), 32-ary search by one warp
-    const double edge = (double)(l_blk - G.nf / 2) - half - 1e-6;
-    long long lo = 0, hi = M;
-    const int lane = threadIdx.x;
-    while (hi > lo) {
-      const long long step = (hi - lo + 31) / 32;
-      const long long probe = lo + (long long)lane * step;
-      const bool below = probe < hi && ph[probe] < edge;
-      const unsigned int m = __ballot_sync(0xffffffffu, below);
-      const int cnt = __popc(m);                                        // sorted: the first cnt probes are below
-      if (cnt == 0) { hi = lo; break; }
-      const long long nlo = lo + (long long)(cnt - 1) * step + 1;
-      const long long nhi = lo + (long long)cnt * step;
-      lo = nlo;
-      hi = nhi < hi ? nhi : hi;
+    const long long v = sk_warp_lower_bound(ph, M, (double)(l_blk - G.nf / 2) - half - 1e-6, false);
+    if (threadIdx.x == 0) s_range[0] = v;
+  } else if (threadIdx.x < 64) {
+    const long long v = sk_warp_lower_bound(ph, M, (double)(l_blk + SK_SPREAD_CELLS - 1 - G.nf / 2) + half + 1e-6, true);
+    if (threadIdx.x == 32) s_range[1] = v;
+  }
+  __syncthreads();
+  const long long s0 = s_range[0];
+  const int ns = (int)((s_range[1] - s0) < (long long)(SK_SPREAD_CAP + 1) ? (s_range[1] - s0) : (long long)(SK_SPREAD_CAP + 1));
+  const bool cached = ns <= SK_SPREAD_CAP;
+  if (cached) {
+    for (int t = threadIdx.x; t < ns; t += blockDim.x) {
+      s_ph[t] = ph[s0 + t];
+      s_pl[t] = pl[s0 + t];
+      s_cs[t] = cs[s0 + t];
     }
-    if (lane == 0) s_start = lo;
   }
   __syncthreads();
   const int sub = threadIdx.x & (SK_SPREAD_LANES - 1);
@@ -167,15 +274,32 @@ k_spread_modes(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     const double ctr = (double)n;
     const double lo_edge = ctr - half - 1e-6, hi_edge = ctr + half + 1e-6;
     const double inv_half = 1.0 / half;
-    for (long long k = s_start + sub; k < M; k += SK_SPREAD_LANES) {
-      const double p = ph[k];
-      if (p > hi_edge) break;
-      if (p < lo_edge) continue;
-      const double z = ((ctr - p) - pl[k]) * inv_half;
-      const double wgt = sk_es_direct(z, P.beta);
-      const sk_cplx c = cs[k];
-      ar = sk_fma(wgt, c.x, ar);
-      ai = sk_fma(wgt, c.y, ai);
+    if (cached) {
+      int a = 0, b = ns;                                                 // first cached source with pos >= lo_edge
+      while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (s_ph[mid] < lo_edge) a = mid + 1; else b = mid;
+      }
+      for (int k = a + sub; k < ns; k += SK_SPREAD_LANES) {
+        const double p = s_ph[k];
+        if (p > hi_edge) break;
+        const double z = ((ctr - p) - s_pl[k]) * inv_half;
+        const double wgt = sk_es_direct(z, P.beta);
+        const sk_cplx c = s_cs[k];
+        ar = sk_fma(wgt, c.x, ar);
+        ai = sk_fma(wgt, c.y, ai);
+      }
+    } else {
+      for (long long k = s0 + sub; k < M; k += SK_SPREAD_LANES) {
+        const double p = ph[k];
+        if (p > hi_edge) break;
+        if (p < lo_edge) continue;
+        const double z = ((ctr - p) - pl[k]) * inv_half;
+        const double wgt = sk_es_direct(z, P.beta);
+        const sk_cplx c = cs[k];
+        ar = sk_fma(wgt, c.x, ar);
+        ai = sk_fma(wgt, c.y, ai);
+      }
     }
   }
 #pragma unroll
@@ -200,17 +324,17 @@ template <int W>
 __global__ void __launch_bounds__(256)
 k_interp_session(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G, const double *__restrict__ xs,
                  long long n, const sk_cplx *__restrict__ grid, double cmul, int kernel_sin,
-                 sk_cplx *__restrict__ stage, SkReduceOut *__restrict__ red) {
+                 sk_cplx *__restrict__ stage, const __grid_constant__ SkSpec spec, SkReduceOut *__restrict__ red) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  double d = 0.0;
-  unsigned int fl = 0;
+  SkAcc acc = {0.0, 0u, -1, 0ull};
   if (j < n) {
     double fre[2], fim[2];
-    sk_interp_point<W, 2>(P, G, xs[j], grid, fre, fim);
+    const double x = xs[j];
+    sk_interp_point<W, 2>(P, G, x, grid, fre, fim);
     // kernel == :cos -> real part, :sin -> imaginary part (src/quadrature.jl:130-136); then *c (:250-251)
-    sk_stage(kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, &stage[j], d, fl);
+    sk_emit(spec, kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, x, j, stage, acc);
   }
-  sk_block_reduce_maxflags(d, fl, red);
+  sk_block_reduce_acc(acc, spec.on, red);
 }
 
 // ---- K4 (cell polynomials) -----------------------------------------------------------------------------
@@ -220,26 +344,26 @@ k_interp_session(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkG
 //   B. turns it into SK_NC polynomial coefficients x 4 components (re/im x two rules) per cell,
 //   C. evaluates every target by Horner from shared memory (broadcast reads inside a cell).
 // Otherwise (sparse targets) it falls back to per-target taps straight from L2.
-#define SK_TPT 4
+#define SK_TPT 8
 #define SK_TPB (256 * SK_TPT)
 template <int W>
 __global__ void __launch_bounds__(256, 3)
 k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G, const double *__restrict__ xs,
                long long n, const sk_cplx *__restrict__ grid, double cmul, int kernel_sin, int cmax,
-               sk_cplx *__restrict__ stage, SkReduceOut *__restrict__ red) {
+               sk_cplx *__restrict__ stage, const __grid_constant__ SkSpec spec, SkReduceOut *__restrict__ red) {
   extern __shared__ __align__(16) double smem[];
   double *sE = smem;                                   // [W/2][SK_NC/2]
   double *sO = sE + (W / 2) * (SK_NC / 2);
   double *sWin = sO + (W / 2) * (SK_NC / 2);            // [(cmax + W)][4]
-  double *sCoef = sWin + (size_t)(cmax + W) * 4;        // [cmax][SK_NC][4]
+  double *sQ = sWin + (size_t)(cmax + W) * 4;           // [cmax][4]  deconvolution factor at the 4 Chebyshev nodes
+  double *sCoef = sQ + (size_t)cmax * 4;                // [cmax][SK_NC][4]
   __shared__ sk_cplx sTab[65];                          // (cos, sin)(2 pi k / 64) for the post-phase
   const long long j0 = (long long)blockIdx.x * SK_TPB;
   const int cnt = (int)((n - j0) < (long long)SK_TPB ? (n - j0) : (long long)SK_TPB);
   const long long l_first = sk_target_coord<W>(G, xs[j0]).l0;
   const long long l_last = sk_target_coord<W>(G, xs[j0 + cnt - 1]).l0;
   const long long ncell_ll = l_last - l_first + 1;
-  double d = 0.0;
-  unsigned int fl = 0;
+  SkAcc acc = {0.0, 0u, -1, 0ull};
   if (ncell_ll >= 1 && ncell_ll <= (long long)cmax) {
     const int ncell = (int)ncell_ll;
     for (int t = threadIdx.x; t < (W / 2) * (SK_NC / 2); t += blockDim.x) {
@@ -251,6 +375,14 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     const double4 *gsrc = reinterpret_cast<const double4 *>(grid + (size_t)l_first * 2);
     double4 *wdst = reinterpret_cast<double4 *>(sWin);
     for (int t = threadIdx.x; t < ncell + W - 1; t += blockDim.x) wdst[t] = gsrc[t];
+    // the target-side deconvolution factor at the 4 Chebyshev nodes of every cell (independent of A)
+    for (int t = threadIdx.x; t < ncell * 4; t += blockDim.x) {
+      const int k = t & 3, cell = t >> 2;
+      const double node = (k == 0) ? 0.9238795325112867 : (k == 1) ? 0.3826834323650898
+                        : (k == 2) ? -0.3826834323650898 : -0.9238795325112867;
+      const double ymid = (double)(l_first + cell - G.nf2 / 2) + (0.5 * W - 0.5);
+      sQ[t] = sk_deconv(P, G.t_cell * fabs(ymid - 0.5 * node));
+    }
     __syncthreads();
     // B: coefficient (cell, q, comp) = W/2 FMAs
     for (int t = threadIdx.x; t < ncell * SK_NC * 4; t += blockDim.x) {
@@ -258,36 +390,39 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       sCoef[t] = sk_cell_coef<W>(sE, sO, sWin + cell * 4 + comp, 4, q);
     }
     __syncthreads();
-    // B': fold the target-side deconvolution (a cubic per cell) into the coefficients
+    // B': fold the deconvolution (a cubic per cell) into the coefficients, one column per thread
     for (int t = threadIdx.x; t < ncell * 4; t += blockDim.x) {
       const int comp = t & 3, cell = t >> 2;
       double a[4];
-      sk_cell_deconv_cubic(P, G, (double)(l_first + cell - G.nf2 / 2) + (0.5 * W - 0.5), a);
+      sk_cheb4_to_monomial(sQ + cell * 4, a);
       sk_cell_fold(sCoef + (size_t)cell * SK_NC * 4 + comp, 4, a);
     }
     __syncthreads();
     // C: Horner per target
+#pragma unroll 1
+    for (int uo = 0; uo < SK_TPT / 4; ++uo) {
 #pragma unroll
-    for (int u = 0; u < SK_TPT; ++u) {
-      const int t = threadIdx.x + u * 256;
-      if (t < cnt) {
-        const double r = xs[j0 + t];
-        const SkTargetCoord tc = sk_target_coord<W>(G, r);
-        int cell = (int)(tc.l0 - l_first);
-        cell = cell < 0 ? 0 : (cell >= ncell ? ncell - 1 : cell);
-        double a[4];
-        sk_cell_horner<4>(sCoef + (size_t)cell * SK_NC * 4, tc.s, a);
-        double sn, cs;
-        sk_sincos2pi(sTab, sk_frac_prod(G.wc, r, 0.0), &sn, &cs);      // post-phase exp(2 pi i wc r)
-        double f1, f2;
-        if (kernel_sin) {
-          f1 = a[0] * sn + a[1] * cs;
-          f2 = a[2] * sn + a[3] * cs;
-        } else {
-          f1 = a[0] * cs - a[1] * sn;
-          f2 = a[2] * cs - a[3] * sn;
+      for (int ui = 0; ui < 4; ++ui) {
+        const int t = threadIdx.x + (uo * 4 + ui) * 256;
+        if (t < cnt) {
+          const double r = xs[j0 + t];
+          const SkTargetCoord tc = sk_target_coord<W>(G, r);
+          int cell = (int)(tc.l0 - l_first);
+          cell = cell < 0 ? 0 : (cell >= ncell ? ncell - 1 : cell);
+          double a[4];
+          sk_cell_horner<4>(sCoef + (size_t)cell * SK_NC * 4, tc.s, a);
+          double sn, cs;
+          sk_sincos2pi(sTab, sk_frac_prod(G.wc, r, 0.0), &sn, &cs);      // post-phase exp(2 pi i wc r)
+          double f1, f2;
+          if (kernel_sin) {
+            f1 = a[0] * sn + a[1] * cs;
+            f2 = a[2] * sn + a[3] * cs;
+          } else {
+            f1 = a[0] * cs - a[1] * sn;
+            f2 = a[2] * cs - a[3] * sn;
+          }
+          sk_emit(spec, f1, f2, cmul, r, j0 + t, stage, acc);
         }
-        sk_stage(f1, f2, cmul, &stage[j0 + t], d, fl);
       }
     }
   } else {
@@ -296,12 +431,13 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       const int t = threadIdx.x + u * 256;
       if (t < cnt) {
         double fre[2], fim[2];
-        sk_interp_point<W, 2>(P, G, xs[j0 + t], grid, fre, fim);
-        sk_stage(kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, &stage[j0 + t], d, fl);
+        const double x = xs[j0 + t];
+        sk_interp_point<W, 2>(P, G, x, grid, fre, fim);
+        sk_emit(spec, kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, x, j0 + t, stage, acc);
       }
     }
   }
-  sk_block_reduce_maxflags(d, fl, red);
+  sk_block_reduce_acc(acc, spec.on, red);
 }
 
 // ---- K4 (log-weighted origin sub-interval, src/quadrature.jl:186-228, dim = 1) --------------------------
@@ -424,6 +560,12 @@ __global__ void k_accept_add(sk_cplx *__restrict__ pan, const sk_cplx *__restric
   pan[j] = p;
 }
 
+// roll a rejected speculative commit back: res = backup (bit for bit)
+__global__ void k_restore(sk_cplx *__restrict__ res, const sk_cplx *__restrict__ backup, long long n) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) res[j] = backup[j];
+}
+
 // ---- K6 ---------------------------------------------------------------------------------------------
 // res = (ks, errs) += pan = (I, err)  (src/adaptive.jl:163-164), fused with the convergence predicate of
 // src/adaptive.jl:185-197 on panel_ks = I.  The reference walks ix = hi, hi-1, ... while converged;
@@ -501,30 +643,39 @@ struct SkKeyBits {
 __global__ void __launch_bounds__(256)
 k_make_keys(const double *__restrict__ xs, long long n, unsigned long long *__restrict__ keys,
             unsigned int *__restrict__ idx, SkKeyBits *__restrict__ kb) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // grid-stride: a few thousand blocks, one pair of atomics per block (a single hot address serialises)
   unsigned long long k_or = 0ull, k_and = ~0ull;
-  if (j < n) {
+  unsigned int bad = 0;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
     double x = xs[j];
-    if (!(x >= 0.0) || isinf(x)) { atomicOr(&kb->bad, 1u); x = 0.0; }
+    if (!(x >= 0.0) || isinf(x)) { bad = 1; x = 0.0; }
     if (x == 0.0) x = 0.0;
     const unsigned long long k = (unsigned long long)__double_as_longlong(x);
     keys[j] = k;
     idx[j] = (unsigned int)j;
-    k_or = k;
-    k_and = k;
+    k_or |= k;
+    k_and &= k;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     k_or |= __shfl_xor_sync(0xffffffffu, k_or, o);
     k_and &= __shfl_xor_sync(0xffffffffu, k_and, o);
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
   }
-  if ((threadIdx.x & 31) == 0) {
+  __shared__ unsigned long long s_or[8], s_and[8];
+  __shared__ unsigned int s_bad[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { s_or[wid] = k_or; s_and[wid] = k_and; s_bad[wid] = bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { k_or |= s_or[w]; k_and &= s_and[w]; bad |= s_bad[w]; }
     atomicOr(&kb->bits_or, k_or);
     atomicAnd(&kb->bits_and, k_and);
+    if (bad) atomicOr(&kb->bad, 1u);
   }
 }
 
-// Second half of the two-level sort.  The radix sort ordered the pairs by 24 key bits only (3 digit
+// Second half of the two-level sort.  The radix sort ordered the pairs by 32 key bits only (4 digit
 // passes instead of 8, stable); `mask` selects those bits and everything above them (the bits above are
 // equal in all keys).  Runs of equal masked keys are short for real distance sets (a handful of elements),
 // so every element finds its run by walking left/right in a shared-memory tile (with a halo of SK_RR_HALO
@@ -583,14 +734,17 @@ __global__ void k_flag_heads(const unsigned long long *__restrict__ keys, long l
   head[j] = (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
 }
 
-// uid = inclusive-scan(head); unique value table uxs[uid - 1] (the guards only matter when the two-level
-// sort overflowed and left garbage behind -- the caller then redoes the sort -- never write out of bounds)
-__global__ void k_compact_unique(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ head,
-                                 const unsigned int *__restrict__ uid_incl, long long n, double *__restrict__ uxs) {
+// uid = inclusive-scan(head); unique value table uxs[uid - 1] and inverse map (original position ->
+// unique id).  The guards only matter when the two-level sort overflowed and left garbage behind (the
+// caller then redoes the sort): never write out of bounds.
+__global__ void k_scatter_unique(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ idx,
+                                 const unsigned int *__restrict__ head, const unsigned int *__restrict__ uid_incl,
+                                 long long n, double *__restrict__ uxs, unsigned int *__restrict__ inv) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const unsigned int u = uid_incl[j] - 1u;
   if (head[j] && (long long)u < n) uxs[u] = __longlong_as_double((long long)keys[j]);
+  if ((long long)idx[j] < n) inv[idx[j]] = u;
 }
 
 __global__ void k_target_summary(const double *__restrict__ uxs, const unsigned int *__restrict__ uid_incl, long long n,
@@ -605,18 +759,16 @@ __global__ void k_target_summary(const double *__restrict__ uxs, const unsigned 
   out->bad = kb->bad;
 }
 
-// values and errors back in the ORIGINAL input order (src/adaptive.jl:105-107): sorted position i holds
-// original position sidx[i] and unique id uid_incl[i]-1.  Reads are coalesced (uid is non-decreasing),
-// writes are the random side.
-__global__ void k_scatter_out(const unsigned int *__restrict__ sidx, const unsigned int *__restrict__ uid_incl,
-                              const sk_cplx *__restrict__ res, long long n, double *__restrict__ out_v,
-                              double *__restrict__ out_e) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const sk_cplx r = res[uid_incl[i] - 1u];
-  const unsigned int o = sidx[i];
-  out_v[o] = r.x;
-  if (out_e) out_e[o] = r.y;
+// values and errors back in the ORIGINAL input order (src/adaptive.jl:105-107) from res = (ks, errs): one
+// 16-byte random read per target (random reads are ~2.5x cheaper than the random 8-byte writes of a
+// scatter from sorted order, measured: profiles/r1_c_launches.txt)
+__global__ void k_gather(const unsigned int *__restrict__ inv, const sk_cplx *__restrict__ res, long long n,
+                         double *__restrict__ out_v, double *__restrict__ out_e) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const sk_cplx r = res[inv[j]];
+  out_v[j] = r.x;
+  if (out_e) out_e[j] = r.y;
 }
 
 // number of sorted values <= r (== the largest 1-based index with xs[idx] <= r)

@@ -377,12 +377,11 @@ SK_HD void sk_cell_horner(const double *coef, double s, double *out) {
 // one cell, so inside a cell it is a cubic in s to ~1e-17 (interpolated at the 4 Chebyshev nodes).  Folding
 // that cubic into the cell polynomial (a truncated polynomial product: the dropped degree-16..18 terms are
 // ~1e-4 * 1e-16) makes the deconvolution free per target.  ymid = y at s = 0 (the cell centre), y = ymid - s/2.
-SK_HD void sk_cell_deconv_cubic(const SkEsPlan &P, const SkGeom &G, double ymid, double *a) {
+// q[0..3]: values at the Chebyshev nodes s = cos(pi/8), cos(3pi/8), -cos(3pi/8), -cos(pi/8)  ->  monomial
+// coefficients a[0..3] of the interpolating cubic in s
+SK_HD void sk_cheb4_to_monomial(const double *q, double *a) {
   const double n0 = 0.9238795325112867, n1 = 0.3826834323650898;   // cos(pi/8), cos(3 pi/8)
-  const double q0 = sk_deconv(P, G.t_cell * fabs(ymid - 0.5 * n0));
-  const double q1 = sk_deconv(P, G.t_cell * fabs(ymid - 0.5 * n1));
-  const double q2 = sk_deconv(P, G.t_cell * fabs(ymid + 0.5 * n1));
-  const double q3 = sk_deconv(P, G.t_cell * fabs(ymid + 0.5 * n0));
+  const double q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
   // Chebyshev coefficients of the interpolant: c_j = (2/4) sum_k q_k T_j(s_k), c_0 halved
   const double t2a = 2.0 * n0 * n0 - 1.0, t2b = 2.0 * n1 * n1 - 1.0;               // T2 at +-n0, +-n1
   const double t3a = (4.0 * n0 * n0 - 3.0) * n0, t3b = (4.0 * n1 * n1 - 3.0) * n1; // T3 at n0, n1 (odd)
@@ -394,6 +393,15 @@ SK_HD void sk_cell_deconv_cubic(const SkEsPlan &P, const SkGeom &G, double ymid,
   a[1] = c1 - 3.0 * c3;
   a[2] = 2.0 * c2;
   a[3] = 4.0 * c3;
+}
+SK_HD void sk_cell_deconv_cubic(const SkEsPlan &P, const SkGeom &G, double ymid, double *a) {
+  const double n0 = 0.9238795325112867, n1 = 0.3826834323650898;
+  double q[4];
+  q[0] = sk_deconv(P, G.t_cell * fabs(ymid - 0.5 * n0));
+  q[1] = sk_deconv(P, G.t_cell * fabs(ymid - 0.5 * n1));
+  q[2] = sk_deconv(P, G.t_cell * fabs(ymid + 0.5 * n1));
+  q[3] = sk_deconv(P, G.t_cell * fabs(ymid + 0.5 * n0));
+  sk_cheb4_to_monomial(q, a);
 }
 
 // in-place product of one coefficient column (stride doubles apart) with the cubic a, truncated at SK_NC

@@ -60,7 +60,7 @@ class FakeEngine:
         assert r_lo <= self.range[0] and r_hi >= self.range[1]
         self.calls.append(("range", r_lo, r_hi))
 
-    def subinterval_host(self, a, b, no1, buf1, no2, buf2, cmul, p, kernel, logw):
+    def subinterval_host(self, a, b, no1, buf1, no2, buf2, cmul, p, kernel, logw, speculate=None):
         x = self.uxs[self.lo:self.hi]
         f1, f2 = so.direct_cis(no1, buf1, x), so.direct_cis(no2, buf2, x)
         i1 = (f1.imag if kernel == 1 else f1.real) * cmul

@@ -248,6 +248,31 @@ def test_duplicates_unsorted_zero_and_direct_branch(sk):
     assert np.all(v0 == k0) and np.all(np.isnan(e0))
 
 
+def test_bisection_and_speculation_rollback(sk):
+    """A sharply peaked density (S = exp(-2000|w|)) forces rejected sub-intervals and the LIFO bisection of
+    src/quadrature.jl:263-271.  The panel's first sub-interval is committed speculatively inside the
+    interpolation kernel and must be rolled back bit for bit when it is rejected: values, error estimates
+    and traces equal the oracle's, for both interpolation kernels."""
+    al = 2000.0
+    xs = np.linspace(0.001, 0.05, 400)
+    k0 = 2 / al
+    ocfg = so.OracleConfig(lambda w: np.exp(-al * np.abs(w)))
+    to = []
+    vo, eo = so.kernel_values(ocfg, xs, k0=k0, trace=to)
+    assert sum(1 for t in to if t["kind"] == "subinterval" and not t["accepted"]) >= 3
+    for mode in (0, 1):
+        cfg = sk.AdaptiveKernelConfig(sk.Exponential(1.0, al))
+        cfg.engine.set_interp_mode(mode)
+        tg = []
+        vg, eg = sk.kernel_values(cfg, xs, k0=k0, trace=tg)
+        st = cfg.engine.stats()
+        assert st["n_spec_rollbacks"] >= 1 and st["n_speculated"] >= st["n_spec_rollbacks"]
+        assert _trace_key(tg) == _trace_key(to)
+        assert np.max(np.abs(vg - vo)) <= 1e-11 * k0
+        assert np.allclose(eg, eo, rtol=1e-6, atol=1e-11 * k0)
+        assert np.max(np.abs(vg - 2 * al / (al ** 2 + (2 * np.pi * xs) ** 2))) <= 1e-8 * k0
+
+
 def test_sort_paths(sk):
     """K8: the two-level sort (4 radix passes on the high key word + k_run_rank) and its fallback to the
     full sort for heavily clustered inputs give the same unique/sort/scatter as numpy."""
