@@ -35,9 +35,17 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 # algorithmic work per unit = one (active target, sub-interval) pair
-FLOPS_PER_UNIT_FUSED = 764      # ES taps shared by the m- and 2m-rule grids (our kernel is fused)
-BYTES_PER_UNIT_K4 = 24          # interpolation kernel: read r (8) + write I2 and |I2-I1| (16)
-BYTES_PER_UNIT_STEP = 40        # SURVEY 8(d) figure for the whole sub-interval (r + RMW of value and error)
+FLOPS_PER_UNIT_SURVEY = 764     # F_fused: per-target tap polynomials shared by the m- and 2m-rule grids
+# FP64 flops k_interp_cells actually executes per unit at the benchmark's density (ncu op counters:
+# 87.6 DFMA + 21.4 DADD + 16.1 DMUL per target, profiles/r1_d_interp_cells_ncu.txt): cell polynomials
+# replace the per-target tap evaluation, so far fewer flops are needed for the same result
+FLOPS_PER_UNIT_EXECUTED = 2 * 87.6 + 21.4 + 16.1
+# interpolation kernel with the fused (speculative) commit: read r (8) + read (ks,errs) (16) + write (ks,errs)
+# (16) + write the roll-back copy (16)
+BYTES_PER_UNIT_K4 = 56
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_interp_cells launch over 1e7 targets (ncu --set full,
+# profiles/r1_d_interp_cells_ncu.txt)
+K4_DRAM_TRAFFIC_BYTES_1E7 = 242.2e6 + 263.7e6
 
 
 def parse():
@@ -254,7 +262,8 @@ def main():
         n_launch = max(1, agg["subintervals"])
         units_per_launch = agg["units"] / n_launch
         k4_ms = agg["interp_ms"] / n_launch
-        ach_tf = units_per_launch * FLOPS_PER_UNIT_FUSED / (k4_ms * 1e-3) / 1e12 if k4_ms > 0 else None
+        ach_tf = units_per_launch * FLOPS_PER_UNIT_SURVEY / (k4_ms * 1e-3) / 1e12 if k4_ms > 0 else None
+        exe_tf = units_per_launch * FLOPS_PER_UNIT_EXECUTED / (k4_ms * 1e-3) / 1e12 if k4_ms > 0 else None
         ach_gbs = units_per_launch * BYTES_PER_UNIT_K4 / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else None
         line = {
             "metric": "K(r) evals/sec at tol=1e-8 (Matern S, 1e7 r)",
@@ -272,10 +281,17 @@ def main():
                     "note": "kernel_values with pinned host buffers; values and errors both copied back"},
             "gpu_launches": int(agg["launches"]),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "k_interp_session<16>", "achieved": ach_tf, "peak": fp64_tf,
-                         "unit": "TFLOP/s", "frac": (ach_tf / fp64_tf) if ach_tf else None, "traffic": None,
-                         "flops_per_unit": FLOPS_PER_UNIT_FUSED, "units_per_launch": units_per_launch,
-                         "avg_launch_ms": k4_ms, "kernel_share_of_step": agg["interp_ms"] / res_ms,
+            "roofline": {"bound": "fp64", "kernel": "k_interp_cells<16>", "achieved": ach_tf, "peak": fp64_tf,
+                         "unit": "TFLOP/s", "frac": (ach_tf / fp64_tf) if ach_tf else None,
+                         "traffic": K4_DRAM_TRAFFIC_BYTES_1E7 * units_per_launch / 1e7,
+                         "flops_per_unit": FLOPS_PER_UNIT_SURVEY,
+                         "note": "achieved/frac use SURVEY 8(d)'s ALGORITHMIC figure (764 flops per unit, per-target "
+                                 "tap evaluation); the kernel reaches the same result with cell polynomials, so "
+                                 "fewer flops are executed: see executed_*",
+                         "executed_flops_per_unit": FLOPS_PER_UNIT_EXECUTED, "executed_achieved": exe_tf,
+                         "executed_frac": (exe_tf / fp64_tf) if exe_tf else None,
+                         "units_per_launch": units_per_launch, "avg_launch_ms": k4_ms,
+                         "kernel_share_of_step": agg["interp_ms"] / res_ms,
                          "peak_source": "measured live: sk_fp64_peak DFMA micro-benchmark (MEASURED_PEAKS.json has no FP64 figure)",
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": (ach_gbs / hbm_peak) if ach_gbs else None, "bytes_per_unit": BYTES_PER_UNIT_K4,

@@ -147,6 +147,17 @@ int fail(sk_ctx *c, int code, const char *fmt, ...) {
     c->stats.kernel_launches++;                                                                 \
   } while (0)
 
+#define DISPATCH_W(w, CALL)                \
+  switch (w) {                             \
+    case 4: CALL(4); break;                \
+    case 6: CALL(6); break;                \
+    case 8: CALL(8); break;                \
+    case 10: CALL(10); break;              \
+    case 12: CALL(12); break;              \
+    case 14: CALL(14); break;              \
+    default: CALL(16); break;              \
+  }
+
 inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
 int flush_commit(sk_ctx *c);
 
@@ -202,16 +213,6 @@ void launch_interp_cplx(sk_ctx *c, const SkGeom &G, const double *x, long long n
   k_interp_cplx<W><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, x, n, c->fft.p, out);
 }
 
-#define DISPATCH_W(w, CALL)                \
-  switch (w) {                             \
-    case 4: CALL(4); break;                \
-    case 6: CALL(6); break;                \
-    case 8: CALL(8); break;                \
-    case 10: CALL(10); break;              \
-    case 12: CALL(12); break;              \
-    case 14: CALL(14); break;              \
-    default: CALL(16); break;              \
-  }
 
 // Source side of one transform pair: prep + spread/deconvolve/pad + FFT.  nrule = 1 or 2.
 // re1/im1 (rule 0) and re2 (rule 1) are the strengths over the nodes c->no1 / c->no2; fft_out receives
@@ -238,7 +239,9 @@ int run_source_side(sk_ctx *c, const SkGeom &G, int nrule, long long M1, const d
   }
   CK(cudaMemsetAsync(fft_out.p, 0, sizeof(sk_cplx) * need, c->stream));   // zero-padding of the modes
   dim3 grid(nblk(G.nf, SK_SPREAD_CELLS), nrule);          // SK_SPREAD_LANES lanes per spread-grid cell
-  k_spread_modes<<<grid, 256, 0, c->stream>>>(c->plan, G, src, nrule, fft_out.p);
+#define CALL(WW) k_spread_modes<WW><<<grid, 256, 0, c->stream>>>(c->plan, G, src, nrule, fft_out.p)
+  DISPATCH_W(c->plan.w, CALL)
+#undef CALL
   LAUNCH_CHECK();
   cufftHandle h;
   int rc = get_fft_plan(c, G.nf2, nrule, &h);

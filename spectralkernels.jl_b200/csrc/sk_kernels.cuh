@@ -85,8 +85,8 @@ __device__ __forceinline__ void sk_block_reduce_maxflags(double d, unsigned int 
 
 // staging of one target: I2 and |I2-I1| (src/quadrature.jl:250-257) as one 16-byte store
 __device__ __forceinline__ void sk_stage(double f1, double f2, double cmul, sk_cplx *dst, double &d, unsigned int &fl) {
-  const double i1 = f1 * cmul, i2 = f2 * cmul;
-  double dd = fabs(i2 - i1);
+  const double i1 = sk_mul(f1, cmul), i2 = sk_mul(f2, cmul);     // explicit roundings: identical in every code path
+  double dd = fabs(sk_add(i2, -i1));
   if (i1 != i1) fl |= SK_FLAG_NAN1;
   if (i2 != i2) fl |= SK_FLAG_NAN2;
   sk_cplx o;
@@ -112,15 +112,15 @@ __device__ __forceinline__ void sk_emit(const SkSpec &spec, double f1, double f2
     sk_stage(f1, f2, cmul, &stage[j], acc.d, acc.fl);
     return;
   }
-  const double i1 = f1 * cmul, i2 = f2 * cmul;
-  double dd = fabs(i2 - i1);
+  const double i1 = sk_mul(f1, cmul), i2 = sk_mul(f2, cmul);
+  double dd = fabs(sk_add(i2, -i1));
   if (i1 != i1) acc.fl |= SK_FLAG_NAN1;
   if (i2 != i2) acc.fl |= SK_FLAG_NAN2;
   const sk_cplx old = spec.res[j];
   spec.backup[j] = old;
   sk_cplx nw;
-  nw.x = old.x + i2;        // ks += I with I = 0 + I2   (src/quadrature.jl:261, src/adaptive.jl:163)
-  nw.y = old.y + dd;        // errs += err with err = 0 + |I2-I1|
+  nw.x = sk_add(old.x, i2);   // ks += I with I = 0 + I2   (src/quadrature.jl:261, src/adaptive.jl:163)
+  nw.y = sk_add(old.y, dd);   // errs += err with err = 0 + |I2-I1|
   spec.res[j] = nw;
   if (dd != dd) { acc.fl |= SK_FLAG_NAND; dd = 0.0; }
   acc.d = fmax(acc.d, dd);
@@ -194,22 +194,27 @@ __global__ void k_prep_sources(const __grid_constant__ SkGeom G, long long M, co
   cs[k] = c;
 }
 
-// Spread + mode deconvolution.  Gather: every spread-grid cell sums the sources whose kernel support
-// covers it, in source order -- no atomics, bitwise reproducible.  (The zero-padded part of the FFT
-// input is cleared by a memset before this kernel.)  One block = SK_SPREAD_CELLS consecutive cells;
-// one warp finds the block's first relevant source with a 32-ary search; SK_SPREAD_LANES lanes share
-// one cell (Gauss nodes cluster at the sub-panel ends: hundreds of sources within one kernel width
-// there), lane t takes sources s0+t, s0+t+L, ... and the partial sums are combined in a fixed
-// butterfly order.
-#define SK_SPREAD_LANES 8
+// Spread + mode deconvolution.  Every spread-grid cell sums the sources whose kernel support covers it
+// in source order -- no atomics, bitwise reproducible.  (The zero-padded part of the FFT input is
+// cleared by a memset before this kernel.)  One block = SK_SPREAD_CELLS consecutive cells:
+//   0. two warps find the block's source range [s0, s1) with 32-ary searches (sources are sorted);
+//   1. in chunks of SK_SPREAD_CHUNK sources: one thread per source evaluates its w tap weights with the
+//      shared tap polynomials (Horner, ~8 FMAs per tap -- an exp/sqrt evaluation per (source, cell) pair
+//      would cost ~100 instructions) and parks them in shared memory together with its first cell;
+//   2. SK_SPREAD_LANES lanes per cell pick up the weights that land on their cell (binary search on the
+//      first-cell array, then a short walk) and accumulate weight * strength; the lanes' partial sums are
+//      combined in a fixed butterfly order.
+// Gauss nodes cluster at the sub-panel ends (hundreds of sources within one kernel width there): the
+// chunk loop handles any number of sources per block.
+#define SK_SPREAD_LANES 4
 #define SK_SPREAD_CELLS (256 / SK_SPREAD_LANES)
+#define SK_SPREAD_CHUNK 256
 struct SkSpreadSrc {
   const double *pos_hi[2];
   const double *pos_lo[2];
   const sk_cplx *cs[2];
   long long M[2];
 };
-#define SK_SPREAD_CAP 512      // sources cached in shared memory per block
 __device__ __forceinline__ long long sk_warp_lower_bound(const double *__restrict__ ph, long long M, double edge,
                                                          bool strict_greater) {
   // first index with ph[i] >= edge (or > edge when strict_greater): 32-ary search by one full warp
@@ -233,6 +238,7 @@ __device__ __forceinline__ long long sk_warp_lower_bound(const double *__restric
   return lo;
 }
 
+template <int W>
 __global__ void __launch_bounds__(256)
 k_spread_modes(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G,
                const __grid_constant__ SkSpreadSrc src, int nrule, sk_cplx *__restrict__ fft_io) {
@@ -241,66 +247,61 @@ k_spread_modes(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
   const double *__restrict__ pl = src.pos_lo[r];
   const sk_cplx *__restrict__ cs = src.cs[r];
   const long long M = src.M[r];
-  const double half = 0.5 * P.w;
+  const double half = 0.5 * W;
   const long long l_blk = (long long)blockIdx.x * SK_SPREAD_CELLS;       // first cell of the block
+  const long long n_blk = l_blk - G.nf / 2;                              // its signed mode index
   __shared__ long long s_range[2];
-  __shared__ double s_ph[SK_SPREAD_CAP], s_pl[SK_SPREAD_CAP];
-  __shared__ sk_cplx s_cs[SK_SPREAD_CAP];
+  __shared__ int s_l0[SK_SPREAD_CHUNK];                                  // first cell of the source, relative to n_blk
+  __shared__ sk_cplx s_cs[SK_SPREAD_CHUNK];
+  __shared__ double s_tap[SK_SPREAD_CHUNK][W + 1];                       // +1: spreads the rows over the banks
   if (threadIdx.x < 32) {
-    const long long v = sk_warp_lower_bound(ph, M, (double)(l_blk - G.nf / 2) - half - 1e-6, false);
+    const long long v = sk_warp_lower_bound(ph, M, (double)n_blk - half - 1e-6, false);
     if (threadIdx.x == 0) s_range[0] = v;
   } else if (threadIdx.x < 64) {
-    const long long v = sk_warp_lower_bound(ph, M, (double)(l_blk + SK_SPREAD_CELLS - 1 - G.nf / 2) + half + 1e-6, true);
+    const long long v = sk_warp_lower_bound(ph, M, (double)(n_blk + SK_SPREAD_CELLS - 1) + half + 1e-6, true);
     if (threadIdx.x == 32) s_range[1] = v;
   }
   __syncthreads();
-  const long long s0 = s_range[0];
-  const int ns = (int)((s_range[1] - s0) < (long long)(SK_SPREAD_CAP + 1) ? (s_range[1] - s0) : (long long)(SK_SPREAD_CAP + 1));
-  const bool cached = ns <= SK_SPREAD_CAP;
-  if (cached) {
-    for (int t = threadIdx.x; t < ns; t += blockDim.x) {
-      s_ph[t] = ph[s0 + t];
-      s_pl[t] = pl[s0 + t];
-      s_cs[t] = cs[s0 + t];
-    }
-  }
-  __syncthreads();
+  const long long s0 = s_range[0], s1 = s_range[1];
   const int sub = threadIdx.x & (SK_SPREAD_LANES - 1);
-  const long long l = l_blk + (threadIdx.x / SK_SPREAD_LANES);
+  const int cell = threadIdx.x / SK_SPREAD_LANES;                        // 0 .. SK_SPREAD_CELLS-1
+  const long long l = l_blk + cell;
   const bool live = l < G.nf;
-  const long long n = l - G.nf / 2;                                      // signed mode index
   double ar = 0.0, ai = 0.0;
-  if (live) {
-    const double ctr = (double)n;
-    const double lo_edge = ctr - half - 1e-6, hi_edge = ctr + half + 1e-6;
-    const double inv_half = 1.0 / half;
-    if (cached) {
-      int a = 0, b = ns;                                                 // first cached source with pos >= lo_edge
+  for (long long c0 = s0; c0 < s1; c0 += SK_SPREAD_CHUNK) {
+    const int ns = (int)((s1 - c0) < (long long)SK_SPREAD_CHUNK ? (s1 - c0) : (long long)SK_SPREAD_CHUNK);
+    // 1. tap weights of the chunk's sources
+    if ((int)threadIdx.x < ns) {
+      const long long k = c0 + threadIdx.x;
+      const double p_hi = ph[k], p_lo = pl[k];
+      const double c_first = ceil(p_hi - half);                          // first cell (mode index) under the kernel
+      const double x0 = (c_first - p_hi) - p_lo;                         // in [-W/2, -W/2 + 1)
+      double taps[W];
+      sk_es_taps<W>(P, 2.0 * (x0 + (half - 0.5)), taps);
+#pragma unroll
+      for (int i = 0; i < W; ++i) s_tap[threadIdx.x][i] = taps[i];
+      s_l0[threadIdx.x] = (int)((long long)c_first - n_blk);
+      s_cs[threadIdx.x] = cs[k];
+    }
+    __syncthreads();
+    // 2. cells gather: sources with first cell in [cell - W + 1, cell] (s_l0 is non-decreasing)
+    if (live) {
+      int a = 0, b = ns;
+      const int want = cell - W + 1;
       while (a < b) {
         const int mid = (a + b) >> 1;
-        if (s_ph[mid] < lo_edge) a = mid + 1; else b = mid;
+        if (s_l0[mid] < want) a = mid + 1; else b = mid;
       }
       for (int k = a + sub; k < ns; k += SK_SPREAD_LANES) {
-        const double p = s_ph[k];
-        if (p > hi_edge) break;
-        const double z = ((ctr - p) - s_pl[k]) * inv_half;
-        const double wgt = sk_es_direct(z, P.beta);
+        const int i = cell - s_l0[k];
+        if (i < 0) break;
+        const double wgt = s_tap[k][i];
         const sk_cplx c = s_cs[k];
         ar = sk_fma(wgt, c.x, ar);
         ai = sk_fma(wgt, c.y, ai);
       }
-    } else {
-      for (long long k = s0 + sub; k < M; k += SK_SPREAD_LANES) {
-        const double p = ph[k];
-        if (p > hi_edge) break;
-        if (p < lo_edge) continue;
-        const double z = ((ctr - p) - pl[k]) * inv_half;
-        const double wgt = sk_es_direct(z, P.beta);
-        const sk_cplx c = cs[k];
-        ar = sk_fma(wgt, c.x, ar);
-        ai = sk_fma(wgt, c.y, ai);
-      }
     }
+    __syncthreads();
   }
 #pragma unroll
   for (int o = SK_SPREAD_LANES / 2; o > 0; o >>= 1) {                   // fixed-order butterfly inside the lane group
@@ -308,6 +309,7 @@ k_spread_modes(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     ai += __shfl_xor_sync(0xffffffffu, ai, o);
   }
   if (sub == 0 && live) {
+    const long long n = l - G.nf / 2;                                    // signed mode index
     double q = sk_deconv(P, G.t_cell * fabs((double)n));
     if (n & 1) q = -q;                                                   // shifts the FFT output by nf2/2
     sk_cplx o;
@@ -337,6 +339,23 @@ k_interp_session(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkG
   sk_block_reduce_acc(acc, spec.on, red);
 }
 
+// one target from its cell's folded coefficients: Horner, post-phase, Re/Im select (explicit roundings so
+// that the block path and the warp path of k_interp_cells give bit-identical values)
+__device__ __forceinline__ void sk_cell_eval(const double *coef, const sk_cplx *tab, const SkGeom &G, double r, double s,
+                                             int kernel_sin, double *f1, double *f2) {
+  double a[4];
+  sk_cell_horner<4>(coef, s, a);
+  double sn, cs;
+  sk_sincos2pi(tab, sk_frac_prod(G.wc, r, 0.0), &sn, &cs);            // post-phase exp(2 pi i wc r)
+  if (kernel_sin) {                                                   // Im((a0 + i a1)(cs + i sn))
+    *f1 = sk_fma(a[0], sn, sk_mul(a[1], cs));
+    *f2 = sk_fma(a[2], sn, sk_mul(a[3], cs));
+  } else {                                                            // Re
+    *f1 = sk_fma(a[0], cs, -sk_mul(a[1], sn));
+    *f2 = sk_fma(a[2], cs, -sk_mul(a[3], sn));
+  }
+}
+
 // ---- K4 (cell polynomials) -----------------------------------------------------------------------------
 // One block = SK_TPB consecutive sorted targets.  Sorted targets touch a contiguous run of fine-grid
 // cells; when the run is short enough (ncell <= cmax) the block
@@ -364,13 +383,13 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
   const long long l_last = sk_target_coord<W>(G, xs[j0 + cnt - 1]).l0;
   const long long ncell_ll = l_last - l_first + 1;
   SkAcc acc = {0.0, 0u, -1, 0ull};
+  for (int t = threadIdx.x; t < (W / 2) * (SK_NC / 2); t += blockDim.x) {
+    sE[t] = P.E[t / (SK_NC / 2)][t % (SK_NC / 2)];
+    sO[t] = P.O[t / (SK_NC / 2)][t % (SK_NC / 2)];
+  }
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + 65) sk_sincos2pi_table_fill(sTab, threadIdx.x - 128);
   if (ncell_ll >= 1 && ncell_ll <= (long long)cmax) {
     const int ncell = (int)ncell_ll;
-    for (int t = threadIdx.x; t < (W / 2) * (SK_NC / 2); t += blockDim.x) {
-      sE[t] = P.E[t / (SK_NC / 2)][t % (SK_NC / 2)];
-      sO[t] = P.O[t / (SK_NC / 2)][t % (SK_NC / 2)];
-    }
-    if (threadIdx.x >= 128 && threadIdx.x < 128 + 65) sk_sincos2pi_table_fill(sTab, threadIdx.x - 128);
     // A: window of (ncell + W - 1) grid points x 2 rules, 32 bytes per point
     const double4 *gsrc = reinterpret_cast<const double4 *>(grid + (size_t)l_first * 2);
     double4 *wdst = reinterpret_cast<double4 *>(sWin);
@@ -409,31 +428,65 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
           const SkTargetCoord tc = sk_target_coord<W>(G, r);
           int cell = (int)(tc.l0 - l_first);
           cell = cell < 0 ? 0 : (cell >= ncell ? ncell - 1 : cell);
-          double a[4];
-          sk_cell_horner<4>(sCoef + (size_t)cell * SK_NC * 4, tc.s, a);
-          double sn, cs;
-          sk_sincos2pi(sTab, sk_frac_prod(G.wc, r, 0.0), &sn, &cs);      // post-phase exp(2 pi i wc r)
           double f1, f2;
-          if (kernel_sin) {
-            f1 = a[0] * sn + a[1] * cs;
-            f2 = a[2] * sn + a[3] * cs;
-          } else {
-            f1 = a[0] * cs - a[1] * sn;
-            f2 = a[2] * cs - a[3] * sn;
-          }
+          sk_cell_eval(sCoef + (size_t)cell * SK_NC * 4, sTab, G, r, tc.s, kernel_sin, &f1, &f2);
           sk_emit(spec, f1, f2, cmul, r, j0 + t, stage, acc);
         }
       }
     }
   } else {
+    // Sparse block (more than cmax cells): the same arithmetic, one warp at a time.  The lanes of a warp
+    // that share a cell build that cell's coefficients together in a per-warp scratch area (window from
+    // L2, 2 coefficient items per lane, fold by 4 lanes) and then evaluate their targets from it -- bit
+    // identical to the block path, whatever the tiling (this is what makes results independent of how
+    // the targets are sharded over GPUs).
+    __syncthreads();                                       // sE / sO / sTab ready
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double *wWin = sCoef + (size_t)wid * (W * 4 + 4 + SK_NC * 4);   // [W][4] window
+    double *wQ = wWin + W * 4;                                       // [4] deconvolution nodes
+    double *wCoef = wQ + 4;                                          // [SK_NC][4]
 #pragma unroll 1
     for (int u = 0; u < SK_TPT; ++u) {
       const int t = threadIdx.x + u * 256;
-      if (t < cnt) {
-        double fre[2], fim[2];
-        const double x = xs[j0 + t];
-        sk_interp_point<W, 2>(P, G, x, grid, fre, fim);
-        sk_emit(spec, kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, x, j0 + t, stage, acc);
+      const bool have = t < cnt;
+      const double r = have ? xs[j0 + t] : 0.0;
+      SkTargetCoord tc;
+      tc.l0 = -1;
+      tc.s = 0.0;
+      if (have) tc = sk_target_coord<W>(G, r);
+      unsigned int remaining = __ballot_sync(0xffffffffu, have);
+      while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const long long cellL = __shfl_sync(0xffffffffu, tc.l0, leader);
+        const unsigned int group = __ballot_sync(0xffffffffu, have && tc.l0 == cellL) & remaining;
+        // window of W points x 2 rules = W*4 doubles
+        const double *gsrc = reinterpret_cast<const double *>(grid + (size_t)cellL * 2);
+        for (int i = lane; i < W * 4; i += 32) wWin[i] = gsrc[i];
+        if (lane < 4) {
+          const double node = (lane == 0) ? 0.9238795325112867 : (lane == 1) ? 0.3826834323650898
+                            : (lane == 2) ? -0.3826834323650898 : -0.9238795325112867;
+          const double ymid = (double)(cellL - G.nf2 / 2) + (0.5 * W - 0.5);
+          wQ[lane] = sk_deconv(P, G.t_cell * fabs(ymid - 0.5 * node));
+        }
+        __syncwarp();
+        for (int i = lane; i < SK_NC * 4; i += 32) {
+          const int comp = i & 3, q = i >> 2;
+          wCoef[i] = sk_cell_coef<W>(sE, sO, wWin + comp, 4, q);
+        }
+        __syncwarp();
+        if (lane < 4) {
+          double a[4];
+          sk_cheb4_to_monomial(wQ, a);
+          sk_cell_fold(wCoef + lane, 4, a);
+        }
+        __syncwarp();
+        if (group & (1u << lane)) {
+          double f1, f2;
+          sk_cell_eval(wCoef, sTab, G, r, tc.s, kernel_sin, &f1, &f2);
+          sk_emit(spec, f1, f2, cmul, r, j0 + t, stage, acc);
+        }
+        __syncwarp();
+        remaining &= ~group;
       }
     }
   }

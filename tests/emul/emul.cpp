@@ -82,11 +82,23 @@ long long emul_interp_cells(const SkEsPlan *P, const SkGeom *G, long long N, con
         o[2] = a[2] * cs - a[3] * sn; o[3] = a[2] * sn + a[3] * cs;
       }
     } else {
+      // sparse block: the same cell arithmetic, one cell at a time (the warp path of the kernel)
       for (int t = 0; t < cnt; ++t) {
-        double fre[2], fim[2];
-        sk_interp_point<W, 2>(*P, *G, r[j0 + t], g.data(), fre, fim);
+        const double rr = r[j0 + t];
+        const SkTargetCoord tc = sk_target_coord<W>(*G, rr);
+        const double *win = reinterpret_cast<const double *>(g.data() + (size_t)tc.l0 * 2);
+        double coef[SK_NC * 4];
+        for (int i = 0; i < SK_NC * 4; ++i) coef[i] = sk_cell_coef<W>(E.data(), O.data(), win + (i & 3), 4, i >> 2);
+        double a4[4];
+        sk_cell_deconv_cubic(*P, *G, (double)(tc.l0 - G->nf2 / 2) + (0.5 * W - 0.5), a4);
+        for (int comp = 0; comp < 4; ++comp) sk_cell_fold(coef + comp, 4, a4);
+        double a[4];
+        sk_cell_horner<4>(coef, tc.s, a);
+        double sn, cs;
+        sk_sincos2pi(tab, sk_frac_prod(G->wc, rr, 0.0), &sn, &cs);
         double *o = out + (j0 + t) * 4;
-        o[0] = fre[0]; o[1] = fim[0]; o[2] = fre[1]; o[3] = fim[1];
+        o[0] = a[0] * cs - a[1] * sn; o[1] = a[0] * sn + a[1] * cs;
+        o[2] = a[2] * cs - a[3] * sn; o[3] = a[2] * sn + a[3] * cs;
       }
     }
   }
