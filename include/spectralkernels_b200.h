@@ -173,8 +173,10 @@ int sk_zero_lag_set(sk_ctx *ctx, double value);
 int sk_panel_begin(sk_ctx *ctx, int64_t ix1, int64_t hi, double *r_lo, double *r_hi);
 /* override the distance range the transform geometry is built for (default: the panel's own
  * [r_lo, r_hi]).  A target-sharded multi-GPU run passes the GLOBAL range so that every rank uses the
- * same grids and per-target results do not depend on the sharding. */
-int sk_panel_set_range(sk_ctx *ctx, double r_lo, double r_hi);
+ * same grids and per-target results do not depend on the sharding.  n_active_global (> 0) is the number of
+ * active targets over all ranks: the NUFFT-vs-direct-summation cutoff (src/quadrature.jl:105, src/utils.jl:39)
+ * is then decided on the global count, as a single-GPU run over the union would. */
+int sk_panel_set_range(sk_ctx *ctx, double r_lo, double r_hi, int64_t n_active_global);
 /* one pass of the bisection loop body, src/quadrature.jl:183-258: build both rules on [a,b]
  * (updatequadbufs!, :49-95) from the built-in S, transform (fast or direct, :105-128), select
  * Re/Im, scale by cmul, stage I2 and |I2-I1|, and return max|I2-I1| (NaN if any is NaN). */

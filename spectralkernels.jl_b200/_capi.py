@@ -83,7 +83,7 @@ SIGNATURES = {
     "sk_run_begin": (c_int, [c_void_p]),
     "sk_zero_lag_set": (c_int, [c_void_p, c_double]),
     "sk_panel_begin": (c_int, [c_void_p, c_int64, c_int64, _dp, _dp]),
-    "sk_panel_set_range": (c_int, [c_void_p, c_double, c_double]),
+    "sk_panel_set_range": (c_int, [c_void_p, c_double, c_double, c_int64]),
     "sk_subinterval": (c_int, [c_void_p, c_double, c_double, POINTER(SubintervalOpts), _dp]),
     "sk_subinterval_host": (c_int, [c_void_p, c_double, c_double, _dp, _dp, _dp, _dp, POINTER(SubintervalOpts), _dp]),
     "sk_subinterval_logw_host": (c_int, [c_void_p, c_double, c_double, _dp, _dp, _dp, _dp, _dp, _dp,
@@ -281,8 +281,8 @@ class Session:
         self._ck(self._L.sk_panel_begin(self._h, int(ix1), int(hi), byref(lo), byref(hi_)))
         return lo.value, hi_.value
 
-    def panel_set_range(self, r_lo: float, r_hi: float):
-        self._ck(self._L.sk_panel_set_range(self._h, float(r_lo), float(r_hi)))
+    def panel_set_range(self, r_lo: float, r_hi: float, n_active_global: int = 0):
+        self._ck(self._L.sk_panel_set_range(self._h, float(r_lo), float(r_hi), int(n_active_global)))
 
     def subinterval(self, a: float, b: float, cmul: float, p: float, kernel: int, logw: bool, speculate=None) -> float:
         o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0,

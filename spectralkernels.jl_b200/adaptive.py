@@ -191,6 +191,9 @@ class _NoComm:
     def min(self, vals: Sequence[float]) -> List[float]:
         return list(vals)
 
+    def sum(self, vals: Sequence[float]) -> List[float]:
+        return list(vals)
+
 
 def _host_rules(cfg: AdaptiveKernelConfig, eng):
     if cfg._rules is None:
@@ -359,10 +362,12 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
         if verbose:
             print(f"\nintegrating panel w ∈ [{a:.2e}, {b:.2e}] (length {b - a:.2e}) to resolve {hi} points "
                   f"x ≤ {r_hi_g:.2e} ")
+        if comm.world_size > 1:
+            n_act_g = int(comm.sum([float(hi - ix1 + 1) if active else 0.0])[0])
         if active:
             eng.panel_begin(ix1, hi)
             if comm.world_size > 1:
-                eng.panel_set_range(r_lo_g, r_hi_g)
+                eng.panel_set_range(r_lo_g, r_hi_g, n_act_g)
         # The tail fit depends on (a, b) only, so it is evaluated BEFORE the panel is integrated (the
         # reference does it after, src/adaptive.jl:168): the scan arguments can then ride along with the
         # panel's first sub-interval.

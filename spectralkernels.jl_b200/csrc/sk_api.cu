@@ -102,6 +102,7 @@ struct sk_ctx {
   // speculative commit of the panel's first sub-interval (see sk_subinterval_opts::speculate)
   bool spec_active = false, spec_accepted = false;
   long long panel_subs = 0;                  // sub-intervals evaluated in the open panel
+  long long n_act_global = 0;                // active targets over all ranks (0: this rank only)
   sk_scan_args spec_args;
   long long spec_new_hi = 0;
   double spec_r = 0;
@@ -260,7 +261,8 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
   const long long M1 = (long long)c->m * c->k, M2 = 2 * M1;
   const int ksin = o->kernel == SK_KERNEL_SIN;
   // fast = nufft_quad_size_cutoff(length(no2), length(xs)) && length(xs) > 1   (src/quadrature.jl:105, src/utils.jl:39)
-  const bool fast = (M2 * n_act > (1LL << 18)) && n_act > 1;
+  const long long n_cut = c->n_act_global > 0 ? c->n_act_global : n_act;
+  const bool fast = (M2 * n_cut > (1LL << 18)) && n_cut > 1;
   // speculation is only meaningful for the first sub-interval of the panel (the whole panel)
   const bool spec_on = fast && o->speculate != nullptr && c->panel_subs == 0 && o->speculate->criteria >= 0 &&
                        o->speculate->criteria <= 2;
@@ -806,15 +808,20 @@ int sk_panel_begin(sk_ctx *c, int64_t ix1, int64_t hi, double *r_lo, double *r_h
   c->spec_active = false;
   c->spec_accepted = false;
   c->panel_subs = 0;
+  c->n_act_global = 0;
   return SK_OK;
 }
 
-int sk_panel_set_range(sk_ctx *c, double r_lo, double r_hi) {
+int sk_panel_set_range(sk_ctx *c, double r_lo, double r_hi, int64_t n_active_global) {
   if (!c) return SK_ERR_ARG;
   if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
   if (!(r_lo <= c->r_lo) || !(r_hi >= c->r_hi)) return fail(c, SK_ERR_ARG, "range must contain the panel's targets");
   c->r_lo = r_lo;
   c->r_hi = r_hi;
+  if (n_active_global > 0) {
+    if (n_active_global < c->hi - c->lo) return fail(c, SK_ERR_ARG, "global active count below the local one");
+    c->n_act_global = n_active_global;
+  }
   return SK_OK;
 }
 
@@ -901,7 +908,8 @@ int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, c
   L.i0_coef = i0_coef;
   L.denom = denom;
   L.b = b;
-  const bool fast = (M2 * n_act > (1LL << 18)) && n_act > 1;          // src/quadrature.jl:105
+  const long long n_cut = c->n_act_global > 0 ? c->n_act_global : n_act;
+  const bool fast = (M2 * n_cut > (1LL << 18)) && n_cut > 1;          // src/quadrature.jl:105
   if (fast) {
     SkGeom G;
     if (sk_make_geom(c->plan, a, b, c->r_lo, c->r_hi, &G) != 0) return fail(c, SK_ERR_ARG, "type-3 grid too large");

@@ -107,7 +107,7 @@ struct SkAcc {
 
 // stage (spec.on == 0) or commit speculatively (spec.on == 1) the target with local index j, distance x
 __device__ __forceinline__ void sk_emit(const SkSpec &spec, double f1, double f2, double cmul, double x, long long j,
-                                        sk_cplx *stage, SkAcc &acc) {
+                                        sk_cplx *stage, SkAcc &acc, const sk_cplx old) {
   if (!spec.on) {
     sk_stage(f1, f2, cmul, &stage[j], acc.d, acc.fl);
     return;
@@ -116,8 +116,7 @@ __device__ __forceinline__ void sk_emit(const SkSpec &spec, double f1, double f2
   double dd = fabs(sk_add(i2, -i1));
   if (i1 != i1) acc.fl |= SK_FLAG_NAN1;
   if (i2 != i2) acc.fl |= SK_FLAG_NAN2;
-  const sk_cplx old = spec.res[j];
-  spec.backup[j] = old;
+  spec.backup[j] = old;       // `old` = spec.res[j], loaded early by the caller to hide the latency
   sk_cplx nw;
   nw.x = sk_add(old.x, i2);   // ks += I with I = 0 + I2   (src/quadrature.jl:261, src/adaptive.jl:163)
   nw.y = sk_add(old.y, dd);   // errs += err with err = 0 + |I2-I1|
@@ -332,9 +331,12 @@ k_interp_session(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkG
   if (j < n) {
     double fre[2], fim[2];
     const double x = xs[j];
+    sk_cplx old;
+    old.x = old.y = 0.0;
+    if (spec.on) old = spec.res[j];
     sk_interp_point<W, 2>(P, G, x, grid, fre, fim);
     // kernel == :cos -> real part, :sin -> imaginary part (src/quadrature.jl:130-136); then *c (:250-251)
-    sk_emit(spec, kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, x, j, stage, acc);
+    sk_emit(spec, kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, x, j, stage, acc, old);
   }
   sk_block_reduce_acc(acc, spec.on, red);
 }
@@ -420,17 +422,31 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     // C: Horner per target
 #pragma unroll 1
     for (int uo = 0; uo < SK_TPT / 4; ++uo) {
+      // issue all global loads of the 4 targets first (distances and, when committing speculatively, the
+      // old (ks, errs) pairs): their latency overlaps the arithmetic
+      double rr[4];
+      sk_cplx old[4];
+#pragma unroll
+      for (int ui = 0; ui < 4; ++ui) {
+        const int t = threadIdx.x + (uo * 4 + ui) * 256;
+        rr[ui] = 0.0;
+        old[ui].x = old[ui].y = 0.0;
+        if (t < cnt) {
+          rr[ui] = xs[j0 + t];
+          if (spec.on) old[ui] = spec.res[j0 + t];
+        }
+      }
 #pragma unroll
       for (int ui = 0; ui < 4; ++ui) {
         const int t = threadIdx.x + (uo * 4 + ui) * 256;
         if (t < cnt) {
-          const double r = xs[j0 + t];
+          const double r = rr[ui];
           const SkTargetCoord tc = sk_target_coord<W>(G, r);
           int cell = (int)(tc.l0 - l_first);
           cell = cell < 0 ? 0 : (cell >= ncell ? ncell - 1 : cell);
           double f1, f2;
           sk_cell_eval(sCoef + (size_t)cell * SK_NC * 4, sTab, G, r, tc.s, kernel_sin, &f1, &f2);
-          sk_emit(spec, f1, f2, cmul, r, j0 + t, stage, acc);
+          sk_emit(spec, f1, f2, cmul, r, j0 + t, stage, acc, old[ui]);
         }
       }
     }
@@ -450,6 +466,9 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       const int t = threadIdx.x + u * 256;
       const bool have = t < cnt;
       const double r = have ? xs[j0 + t] : 0.0;
+      sk_cplx old;
+      old.x = old.y = 0.0;
+      if (have && spec.on) old = spec.res[j0 + t];
       SkTargetCoord tc;
       tc.l0 = -1;
       tc.s = 0.0;
@@ -483,7 +502,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
         if (group & (1u << lane)) {
           double f1, f2;
           sk_cell_eval(wCoef, sTab, G, r, tc.s, kernel_sin, &f1, &f2);
-          sk_emit(spec, f1, f2, cmul, r, j0 + t, stage, acc);
+          sk_emit(spec, f1, f2, cmul, r, j0 + t, stage, acc, old);
         }
         __syncwarp();
         remaining &= ~group;

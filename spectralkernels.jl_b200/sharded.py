@@ -2,9 +2,10 @@
 Scalar reductions for a target-sharded multi-GPU run of kernel_values.
 
 Every rank passes its own chunk of the distances (no exchange of targets).  The adaptive loop stays in
-lock step through three kinds of scalar all-reduces: max of the largest unconverged distance (panel
-choice, src/adaptive.jl:152), max of max|I2-I1| (accept test, src/quadrature.jl:258-260) and max of the
-stopping distance of the convergence scan (src/adaptive.jl:183-198).  Because every rank builds the
+lock step through scalar all-reduces: max of the largest unconverged distance (panel choice,
+src/adaptive.jl:152), sum of the active counts (NUFFT-vs-direct cutoff, src/quadrature.jl:105), max of
+max|I2-I1| (accept test, src/quadrature.jl:258-260) and max of the stopping distance of the convergence
+scan (src/adaptive.jl:183-198).  Because every rank builds the
 same transform geometry (sk_panel_set_range) the per-target arithmetic does not depend on the sharding:
 the values are bit-identical to a single-GPU run over the union of the chunks.
 
@@ -40,3 +41,6 @@ class TorchComm:
 
     def min(self, vals):
         return self._reduce(vals, self._dist.ReduceOp.MIN)
+
+    def sum(self, vals):
+        return self._reduce(vals, self._dist.ReduceOp.SUM)

@@ -56,7 +56,7 @@ class FakeEngine:
         self.range = (self.uxs[self.lo], self.uxs[hi - 1])
         return self.range
 
-    def panel_set_range(self, r_lo, r_hi):
+    def panel_set_range(self, r_lo, r_hi, n_active_global=0):
         assert r_lo <= self.range[0] and r_hi >= self.range[1]
         self.calls.append(("range", r_lo, r_hi))
 
