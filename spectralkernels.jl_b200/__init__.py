@@ -5,6 +5,7 @@ spectralkernels.jl_b200 -- B200 (sm_100a) evaluator for the K(r) hot path of pbe
     _capi.py              ctypes binding of that ABI (what Julia binds with ccall)
     adaptive.py           host mirror of AdaptiveKernelConfig / kernel_values (scalar control flow only)
     sdf.py                built-in spectral-density families with device generators
+    derivatives.py        K', dK/dtheta_j, dK/dalpha as further kernel_values runs over the same lags
     sharded.py            scalar reductions for a target-sharded multi-GPU run (torch.distributed)
 
 The directory name contains a dot, so import it through the loader module at the repository root:
@@ -15,8 +16,9 @@ from . import _capi, sdf
 from ._capi import PinnedArray, Session, SkError, host_gauss_rule, load
 from .adaptive import (AdaptiveKernelConfig, compute_k0, estimate_tail_decay, gen_derivative_config,
                        gen_new_sdf_config, kernel_values)
+from .derivatives import kernel_derivative, kernel_sdf_derivatives, kernel_singularity_derivative
 from .sdf import Exponential, Matern
 
 __all__ = ["AdaptiveKernelConfig", "kernel_values", "compute_k0", "estimate_tail_decay", "gen_derivative_config",
-           "gen_new_sdf_config", "Matern", "Exponential", "Session", "SkError", "PinnedArray", "host_gauss_rule",
+           "gen_new_sdf_config", "kernel_derivative", "kernel_sdf_derivatives", "kernel_singularity_derivative", "Matern", "Exponential", "Session", "SkError", "PinnedArray", "host_gauss_rule",
            "load", "sdf"]

@@ -310,13 +310,16 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
 def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, param_derivative: bool = False,
                   verbose: bool = False, trace: Optional[list] = None, comm=None, want_errors: bool = True,
                   out_vals=None, out_errs=None, xs_device: Optional[Tuple[int, int]] = None,
-                  out_device: Optional[Tuple[int, int]] = None):
+                  out_device: Optional[Tuple[int, int]] = None, reuse_targets: bool = False):
     """`kernel_values(config, xs; k0, param_derivative, verbose)` (src/adaptive.jl:95-108): returns
     (values, errors) in the order of `xs`, duplicates included.
 
     Optional extras: `trace` (list, receives the panel trace), `comm` (scalar reductions of a
     target-sharded multi-GPU run: every rank passes its own chunk of the distances), `xs_device` /
-    `out_device` ((pointer, n) / (vals_ptr, errs_ptr): device-resident input and output, no PCIe)."""
+    `out_device` ((pointer, n) / (vals_ptr, errs_ptr): device-resident input and output, no PCIe),
+    `reuse_targets` (the engine already holds exactly these distances from the previous call -- the
+    P_sdf + 2 derivative runs of src/derivatives.jl:86-112 all use the same lags -- so the upload and the
+    sort/unique are skipped)."""
     eng = cfg.engine
     comm = comm or _NoComm()
     if k0 is None:
@@ -326,13 +329,19 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
     if is_builtin(cfg.f):
         eng.sdf_builtin(cfg.f.family, cfg.f.params, cfg.f.deriv)
     # unique + sort + inverse map on the device (adaptive.jl:99, :113-120)
-    if xs_device is not None:
+    if reuse_targets and getattr(eng, "_last_targets", None) is not None:
+        info, n_in = eng._last_targets
+    elif xs_device is not None:
         info = eng.targets_set_device(*xs_device)
         n_in = int(xs_device[1])
     else:
         xs = np.ascontiguousarray(xs, dtype=np.float64)
         n_in = xs.size
         info = eng.targets_set(xs)
+    try:
+        eng._last_targets = (info, n_in)
+    except AttributeError:
+        pass
     if verbose:
         print(f"Reducing {info.n_in} to {info.n_unique} unique lags for evaluation...")
     eng.run_begin()

@@ -67,6 +67,9 @@ struct sk_ctx {
   bool have_rule = false, have_jac = false;
   DevBuf<double> leg_no1, leg_wt1, leg_no2, leg_wt2, jac_no1, jac_wt1, jac_no2, jac_wt2;
   std::vector<double> h_rule[8];
+  // generated rules, kept for the life of the context: (n, p) -> (nodes, weights).  Derivative configs flip
+  // between p = 0 and p = 1 (src/adaptive.jl:42), and a generation costs ~0.3 s of host time at n = 8192
+  std::map<std::pair<int, double>, std::pair<std::vector<double>, std::vector<double>>> rule_cache;
 
   // integrand
   int family = SK_SDF_HOST, deriv = 0, nparam = 0;
@@ -353,6 +356,19 @@ int rollback_speculation(sk_ctx *c) {
     c->stats.n_spec_rollbacks++;
   }
   return SK_OK;
+}
+
+int cached_gauss_rule(sk_ctx *c, int n, double p, std::vector<double> &no, std::vector<double> &wt) {
+  auto key = std::make_pair(n, p);
+  auto it = c->rule_cache.find(key);
+  if (it == c->rule_cache.end()) {
+    std::vector<double> x(n), w(n);
+    if (sk_plan_gauss_rule(n, p, x.data(), w.data()) != 0) return -1;
+    it = c->rule_cache.emplace(key, std::make_pair(std::move(x), std::move(w))).first;
+  }
+  no = it->second.first;
+  wt = it->second.second;
+  return 0;
 }
 
 int upload_rule(sk_ctx *c, DevBuf<double> &dst, const double *src, int n) {
@@ -671,8 +687,8 @@ int sk_rule_set(sk_ctx *c, int32_t m, int32_t k, double p, const double *leg_no1
     const double *src[4] = {leg_no1, leg_wt1, leg_no2, leg_wt2};
     for (int i = 0; i < 4; ++i) std::copy(src[i], src[i] + sizes[i], c->h_rule[i].begin());
   } else {
-    if (sk_plan_gauss_rule(m, 0.0, c->h_rule[0].data(), c->h_rule[1].data()) != 0 ||
-        sk_plan_gauss_rule(2 * m, 0.0, c->h_rule[2].data(), c->h_rule[3].data()) != 0)
+    if (cached_gauss_rule(c, m, 0.0, c->h_rule[0], c->h_rule[1]) != 0 ||
+        cached_gauss_rule(c, 2 * m, 0.0, c->h_rule[2], c->h_rule[3]) != 0)
       return fail(c, SK_ERR_ARG, "Gauss-Legendre generation failed for m=%d", m);
   }
   c->have_jac = (p != 0.0);
@@ -681,8 +697,8 @@ int sk_rule_set(sk_ctx *c, int32_t m, int32_t k, double p, const double *leg_no1
       const double *src[4] = {jac_no1, jac_wt1, jac_no2, jac_wt2};
       for (int i = 0; i < 4; ++i) std::copy(src[i], src[i] + sizes[4 + i], c->h_rule[4 + i].begin());
     } else {
-      if (sk_plan_gauss_rule(m, p, c->h_rule[4].data(), c->h_rule[5].data()) != 0 ||
-          sk_plan_gauss_rule(2 * m, p, c->h_rule[6].data(), c->h_rule[7].data()) != 0)
+      if (cached_gauss_rule(c, m, p, c->h_rule[4], c->h_rule[5]) != 0 ||
+          cached_gauss_rule(c, 2 * m, p, c->h_rule[6], c->h_rule[7]) != 0)
         return fail(c, SK_ERR_ARG, "Gauss-Jacobi generation failed for m=%d p=%g", m, p);
     }
   } else {

@@ -215,6 +215,46 @@ def test_singularity_derivative_logw(sk, golden):
     assert np.max(np.abs(v2 - o2)) <= 1e-11 * k0
 
 
+def test_sdf_param_derivatives_and_target_reuse(sk, golden):
+    """test/derivatives/sdf_params.jl (enabled upstream): dK/d(phi, rho, nu) with the device generators of the
+    Matern parameter derivatives; the three runs reuse the uploaded / sorted lags (BASELINE config 4 shape)."""
+    parms = tuple(golden["sdfp_parms"])
+    xs = golden["sdfp_r"]
+    cfg = sk.AdaptiveKernelConfig(sk.Matern(*parms), tol=1e-12)
+    k0 = sk.compute_k0(cfg)
+    vals, _ = sk.kernel_values(cfg, xs, k0=k0)
+    assert np.max(np.abs(vals - golden["sdfp_K"])) <= 1e-10 * k0
+    derivs = sk.kernel_sdf_derivatives(cfg, xs, k0, reuse_targets=True)
+    for d, key in zip(derivs, ("sdfp_dphi", "sdfp_drho", "sdfp_dnu")):
+        assert np.max(np.abs(d - golden[key])) < 1e-5                       # upstream threshold
+    # same values when every run uploads its lags again, and against the oracle
+    derivs2 = sk.kernel_sdf_derivatives(sk.AdaptiveKernelConfig(sk.Matern(*parms), tol=1e-12), xs, k0)
+    for a, b in zip(derivs, derivs2):
+        assert np.array_equal(a, b)
+    ocfg = so.OracleConfig(lambda w: cf.matern_sdf(w, parms), tol=1e-12)
+    ex = -parms[2] - 0.5
+    dnu = lambda w: -parms[0] * (parms[1] ** 2 + w ** 2) ** ex * np.log(parms[1] ** 2 + w ** 2)
+    vo, _ = so.kernel_values(so.gen_new_sdf_config(ocfg, dnu), xs, k0=k0, param_derivative=True)
+    assert np.max(np.abs(derivs[2] - vo)) <= 1e-10 * max(1.0, np.max(np.abs(vo)))
+
+
+def test_kernel_derivative_warping(sk, golden):
+    """test/derivatives/warping.jl:36-44: K'(lag) from the derivative config times the warp gradient."""
+    p1, p2 = 1 / 50.0, 1.1
+    xs = np.linspace(1.1, 2.0, 100)
+    wx, wy = (xs / p1) ** p2, (1.0 / p1) ** p2
+    lags = np.abs(wy - wx)
+    assert np.allclose(lags, golden["warp_lags"])
+    sgn = np.sign(wx - wy)
+    dlag = np.stack([sgn * (-p2 / p1) * (wx - wy), sgn * (wx * np.log(xs / p1) - wy * np.log(1.0 / p1))], axis=1)
+    cfg = sk.AdaptiveKernelConfig(sk.Exponential(1.0, 1.0), tol=1e-12)
+    k0 = sk.compute_k0(cfg)
+    kv, _ = sk.kernel_values(cfg, lags, k0=k0)
+    assert np.linalg.norm(kv - golden["warp_K"]) <= 1.5e-8 * np.linalg.norm(golden["warp_K"])   # warping.jl:21-23
+    dK = sk.kernel_derivative(cfg, lags, k0, reuse_targets=True)
+    assert np.max(np.linalg.norm(dK[:, None] * dlag - cf.exponential_dcov(lags)[:, None] * dlag, axis=1)) < 1e-8
+
+
 def test_host_callable_equals_builtin(sk, golden):
     """Arbitrary closures are evaluated on the host and uploaded (sk_subinterval_host)."""
     xs = golden["readme_r"][::7]

@@ -108,6 +108,47 @@ def test_warping_lags(golden):
     assert np.linalg.norm(vals - true) <= 1.5e-8 * np.linalg.norm(true)
 
 
+def _matern_param_derivs(parms):
+    phi, rho, nu = parms
+    ex = -nu - 0.5
+    base = lambda w: rho ** 2 + w ** 2
+    return [lambda w: base(w) ** ex,
+            lambda w: phi * ex * base(w) ** (ex - 1) * 2 * rho,
+            lambda w: -phi * base(w) ** ex * np.log(base(w))]
+
+
+def test_sdf_param_derivatives(golden):
+    """test/derivatives/sdf_params.jl (an ENABLED reference test): dK/d(phi, rho, nu) by one adaptive run per
+    parameter with f = dS/dtheta_j (src/derivatives.jl:63-72), tol = 1e-12, threshold 1e-5 as upstream."""
+    parms = tuple(golden["sdfp_parms"])
+    xs = golden["sdfp_r"]
+    cfg = so.OracleConfig(lambda w: cf.matern_sdf(w, parms), tol=1e-12)
+    k0 = so.compute_k0(cfg)
+    assert abs(k0 - golden["sdfp_K"][0]) <= 1e-8 * k0
+    for dS, key in zip(_matern_param_derivs(parms), ("sdfp_dphi", "sdfp_drho", "sdfp_dnu")):
+        cfgj = so.gen_new_sdf_config(cfg, dS)                   # tol carried over, default quadspec (adaptive.jl:69-72)
+        vals, _ = so.kernel_values(cfgj, xs, k0=k0, param_derivative=True)
+        assert np.max(np.abs(vals - golden[key])) < 1e-5
+
+
+def test_kernel_warping_gradients(golden):
+    """test/derivatives/warping.jl:36-44: d kernel / d warp-params = K'(lag) * d lag / d params, with K' from
+    the derivative config (sin kernel; src/derivatives.jl:51-59), threshold 1e-8 as upstream.  The warp
+    (x/p1)^p2 is differentiated by hand here (ForwardDiff upstream)."""
+    p1, p2 = 1 / 50.0, 1.1
+    xs = np.linspace(1.1, 2.0, 100)[::5]
+    wx, wy = (xs / p1) ** p2, (1.0 / p1) ** p2
+    lags = np.abs(wy - wx)
+    sgn = np.sign(wx - wy)
+    dlag = np.stack([sgn * (-p2 / p1) * (wx - wy), sgn * (wx * np.log(xs / p1) - wy * np.log(1.0 / p1))], axis=1)
+    cfg = so.OracleConfig(cf.exponential_sdf, tol=1e-12)
+    k0 = so.compute_k0(cfg)
+    dK, _ = so.kernel_values(so.gen_derivative_config(cfg), lags, k0=k0)
+    grads = dK[:, None] * dlag
+    true = cf.exponential_dcov(lags)[:, None] * dlag
+    assert np.max(np.linalg.norm(grads - true, axis=1)) < 1e-8
+
+
 def test_duplicates_unsorted_and_zero():
     """adaptive.jl:99-107 (unique + scatter), :113-120 (sort), :133-146 (r = 0 row)."""
     cfg = so.OracleConfig(cf.exponential_sdf)
