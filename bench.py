@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--n", type=int, default=10_000_000, help="distances per GPU")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000, help="distances in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--interp-mode", type=int, default=0, help="0 cells (default), 1 per-target taps, 2 cells @4 blocks/SM")
     return ap.parse_args()
 
 
@@ -187,6 +188,8 @@ def main():
     phi, rho, nu = workload_sdf_params()
     cfg = sk.AdaptiveKernelConfig(sk.Matern(phi, rho, nu), device=local_rank)
     eng = cfg.engine
+    if args.interp_mode:
+        eng.set_interp_mode(args.interp_mode)
     k0 = 1.0
 
     # synthetic distances: pinned host copy (e2e) and device copy (resident)

@@ -196,7 +196,10 @@ int get_fft_plan(sk_ctx *c, long long nf2, int batch, cufftHandle *out) {
 template <int W>
 int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long long n, double cmul, int ksin, const SkSpec &spec) {
   if (c->interp_mode == 1) {
-    k_interp_session<W><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage.p + c->lo, spec, c->d_red);
+    if (spec.on)
+      k_interp_session<W, true><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage.p + c->lo, spec, c->d_red);
+    else
+      k_interp_session<W, false><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage.p + c->lo, spec, c->d_red);
     return 0;
   }
   // cells the active targets span -> average targets per cell -> how many cells a block may hold
@@ -206,10 +209,21 @@ int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long lon
   const size_t smem = sizeof(double) * (size_t)(2 * (W / 2) * (SK_NC / 2) + (cmax + W) * 4 + cmax * 4 + cmax * SK_NC * 4);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_interp_cells<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_interp_cells<W, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_interp_cells<W, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_interp_cells<W, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_interp_cells<W, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;
   }
-  k_interp_cells<W><<<nblk(n, SK_TPB), 256, smem, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, cmax, c->stage.p + c->lo, spec, c->d_red);
+#define SK_LAUNCH_CELLS(SPECV, MINBV)                                                                                  \
+  k_interp_cells<W, SPECV, MINBV><<<nblk(n, SK_TPB), 256, smem, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, cmax, \
+                                                                              c->stage.p + c->lo, spec, c->d_red)
+  if (c->interp_mode == 2) {           // A/B variant: 4 resident blocks per SM (<= 64 registers)
+    if (spec.on) SK_LAUNCH_CELLS(true, 4); else SK_LAUNCH_CELLS(false, 4);
+  } else {
+    if (spec.on) SK_LAUNCH_CELLS(true, 3); else SK_LAUNCH_CELLS(false, 3);
+  }
+#undef SK_LAUNCH_CELLS
   return 0;
 }
 template <int W>
@@ -1124,7 +1138,7 @@ int sk_results_get(sk_ctx *c, double *vals, double *errs) {
 }
 
 int sk_ctx_set_interp_mode(sk_ctx *c, int mode) {
-  if (!c || mode < 0 || mode > 1) return SK_ERR_ARG;
+  if (!c || mode < 0 || mode > 2) return SK_ERR_ARG;
   c->interp_mode = mode;
   return SK_OK;
 }

@@ -87,13 +87,16 @@ __device__ __forceinline__ void sk_block_reduce_maxflags(double d, unsigned int 
 __device__ __forceinline__ void sk_stage(double f1, double f2, double cmul, sk_cplx *dst, double &d, unsigned int &fl) {
   const double i1 = sk_mul(f1, cmul), i2 = sk_mul(f2, cmul);     // explicit roundings: identical in every code path
   double dd = fabs(sk_add(i2, -i1));
-  if (i1 != i1) fl |= SK_FLAG_NAN1;
-  if (i2 != i2) fl |= SK_FLAG_NAN2;
   sk_cplx o;
   o.x = i2;
   o.y = dd;
   *dst = o;
-  if (dd != dd) { fl |= SK_FLAG_NAND; dd = 0.0; }
+  if (dd != dd) {                                                 // NaN in I1 or I2 (or inf - inf): rare path
+    fl |= SK_FLAG_NAND;
+    if (i1 != i1) fl |= SK_FLAG_NAN1;
+    if (i2 != i2) fl |= SK_FLAG_NAN2;
+    dd = 0.0;
+  }
   d = fmax(d, dd);
 }
 
@@ -105,23 +108,27 @@ struct SkAcc {
   unsigned long long rb;    // bit pattern of its distance
 };
 
-// stage (spec.on == 0) or commit speculatively (spec.on == 1) the target with local index j, distance x
+// stage (SPEC == false) or commit speculatively (SPEC == true) the target with local index j, distance x
+template <bool SPEC>
 __device__ __forceinline__ void sk_emit(const SkSpec &spec, double f1, double f2, double cmul, double x, long long j,
                                         sk_cplx *stage, SkAcc &acc, const sk_cplx old) {
-  if (!spec.on) {
+  if (!SPEC) {
     sk_stage(f1, f2, cmul, &stage[j], acc.d, acc.fl);
     return;
   }
   const double i1 = sk_mul(f1, cmul), i2 = sk_mul(f2, cmul);
   double dd = fabs(sk_add(i2, -i1));
-  if (i1 != i1) acc.fl |= SK_FLAG_NAN1;
-  if (i2 != i2) acc.fl |= SK_FLAG_NAN2;
   spec.backup[j] = old;       // `old` = spec.res[j], loaded early by the caller to hide the latency
   sk_cplx nw;
   nw.x = sk_add(old.x, i2);   // ks += I with I = 0 + I2   (src/quadrature.jl:261, src/adaptive.jl:163)
   nw.y = sk_add(old.y, dd);   // errs += err with err = 0 + |I2-I1|
   spec.res[j] = nw;
-  if (dd != dd) { acc.fl |= SK_FLAG_NAND; dd = 0.0; }
+  if (dd != dd) {
+    acc.fl |= SK_FLAG_NAND;
+    if (i1 != i1) acc.fl |= SK_FLAG_NAN1;
+    if (i2 != i2) acc.fl |= SK_FLAG_NAN2;
+    dd = 0.0;
+  }
   acc.d = fmax(acc.d, dd);
   const double te = sk_trunc_err(spec.trunc_a, spec.trunc_num, spec.xpow, x, spec.criteria == 0);
   if (!sk_converged(te, i2, spec.tau, spec.criteria)) {
@@ -321,7 +328,7 @@ k_spread_modes(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
 
 // ---- K4 (reference-style per-target taps) -------------------------------------------------------------
 // grid layout [nf2][2] (m-rule, 2m-rule); stage[j] = (I2, |I2-I1|)
-template <int W>
+template <int W, bool SPEC>
 __global__ void __launch_bounds__(256)
 k_interp_session(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G, const double *__restrict__ xs,
                  long long n, const sk_cplx *__restrict__ grid, double cmul, int kernel_sin,
@@ -333,12 +340,12 @@ k_interp_session(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkG
     const double x = xs[j];
     sk_cplx old;
     old.x = old.y = 0.0;
-    if (spec.on) old = spec.res[j];
+    if (SPEC) old = spec.res[j];
     sk_interp_point<W, 2>(P, G, x, grid, fre, fim);
     // kernel == :cos -> real part, :sin -> imaginary part (src/quadrature.jl:130-136); then *c (:250-251)
-    sk_emit(spec, kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, x, j, stage, acc, old);
+    sk_emit<SPEC>(spec, kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, x, j, stage, acc, old);
   }
-  sk_block_reduce_acc(acc, spec.on, red);
+  sk_block_reduce_acc(acc, SPEC ? 1 : 0, red);
 }
 
 // one target from its cell's folded coefficients: Horner, post-phase, Re/Im select (explicit roundings so
@@ -367,8 +374,8 @@ __device__ __forceinline__ void sk_cell_eval(const double *coef, const sk_cplx *
 // Otherwise (sparse targets) it falls back to per-target taps straight from L2.
 #define SK_TPT 8
 #define SK_TPB (256 * SK_TPT)
-template <int W>
-__global__ void __launch_bounds__(256, 3)
+template <int W, bool SPEC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G, const double *__restrict__ xs,
                long long n, const sk_cplx *__restrict__ grid, double cmul, int kernel_sin, int cmax,
                sk_cplx *__restrict__ stage, const __grid_constant__ SkSpec spec, SkReduceOut *__restrict__ red) {
@@ -433,7 +440,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
         old[ui].x = old[ui].y = 0.0;
         if (t < cnt) {
           rr[ui] = xs[j0 + t];
-          if (spec.on) old[ui] = spec.res[j0 + t];
+          if (SPEC) old[ui] = spec.res[j0 + t];
         }
       }
 #pragma unroll
@@ -446,7 +453,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
           cell = cell < 0 ? 0 : (cell >= ncell ? ncell - 1 : cell);
           double f1, f2;
           sk_cell_eval(sCoef + (size_t)cell * SK_NC * 4, sTab, G, r, tc.s, kernel_sin, &f1, &f2);
-          sk_emit(spec, f1, f2, cmul, r, j0 + t, stage, acc, old[ui]);
+          sk_emit<SPEC>(spec, f1, f2, cmul, r, j0 + t, stage, acc, old[ui]);
         }
       }
     }
@@ -468,7 +475,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       const double r = have ? xs[j0 + t] : 0.0;
       sk_cplx old;
       old.x = old.y = 0.0;
-      if (have && spec.on) old = spec.res[j0 + t];
+      if (have && SPEC) old = spec.res[j0 + t];
       SkTargetCoord tc;
       tc.l0 = -1;
       tc.s = 0.0;
@@ -502,14 +509,14 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
         if (group & (1u << lane)) {
           double f1, f2;
           sk_cell_eval(wCoef, sTab, G, r, tc.s, kernel_sin, &f1, &f2);
-          sk_emit(spec, f1, f2, cmul, r, j0 + t, stage, acc, old);
+          sk_emit<SPEC>(spec, f1, f2, cmul, r, j0 + t, stage, acc, old);
         }
         __syncwarp();
         remaining &= ~group;
       }
     }
   }
-  sk_block_reduce_acc(acc, spec.on, red);
+  sk_block_reduce_acc(acc, SPEC ? 1 : 0, red);
 }
 
 // ---- K4 (log-weighted origin sub-interval, src/quadrature.jl:186-228, dim = 1) --------------------------
