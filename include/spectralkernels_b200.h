@@ -47,6 +47,7 @@ extern "C" {
 /* integral kernels, src/quadrature.jl:176-180 and :130-136 */
 #define SK_KERNEL_COS 0
 #define SK_KERNEL_SIN 1
+#define SK_KERNEL_BESSEL 2   /* (:J, nu), dim >= 2 (even): sum_k c_k J_nu(2 pi w_k r), src/quadrature.jl:137-161, :179 */
 
 /* convergence criteria, src/adaptive.jl:12, :231-233 */
 #define SK_CRIT_PANEL 0
@@ -83,6 +84,9 @@ typedef struct sk_subinterval_opts {
   double p;          /* config.p, src/adaptive.jl:42                                                */
   int32_t kernel;    /* SK_KERNEL_COS / SK_KERNEL_SIN, src/quadrature.jl:177                        */
   int32_t logw;      /* config.logw: multiply the integrand by log(w), src/quadrature.jl:242        */
+  int32_t nu;        /* Bessel order for SK_KERNEL_BESSEL: dim/2-1, or dim/2 for the derivative (:179)   */
+  int32_t _pad;
+  double xdiv_pow;   /* dim/2 - 1: the integrals are divided by x^xdiv_pow (src/quadrature.jl:252-254); 0 for dim = 1 */
   /* Optional (may be NULL).  On the FIRST sub-interval of a panel -- the whole panel [a,b] -- the host may
    * pass the scan arguments it will use for this panel (they depend on (a,b) only: estimate_tail_decay,
    * src/adaptive.jl:204-220).  The interpolation kernel then also applies ks += I2, errs += |I2-I1| and
@@ -160,6 +164,12 @@ int sk_sdf_builtin(sk_ctx *ctx, int32_t family, const double *params, int32_t np
 /* ---- Level 1: targets, replaces unique/sort/Dict of src/adaptive.jl:99-107, :113-120 ----------- */
 int sk_targets_set(sk_ctx *ctx, const double *xs_host, int64_t n_in, sk_target_info *info);
 int sk_targets_set_device(sk_ctx *ctx, const double *xs_dev, int64_t n_in, sk_target_info *info);
+/* lags of point pairs computed on the device (src/model.jl:53-68 with NoWarping: lag = norm(pts[i] - pts[j])):
+ * pts_host is npts x dim row-major; pairs_host holds npairs 0-based (i, j) index pairs, or NULL for all
+ * npts (npts-1) / 2 pairs i < j in row-major order of the strict upper triangle.  The results of
+ * sk_results_get are then in pair order.  Replaces the host-side lag list and its upload. */
+int sk_targets_set_pairs(sk_ctx *ctx, const double *pts_host, int64_t npts, int32_t dim, const int64_t *pairs_host,
+                         int64_t npairs, sk_target_info *info);
 /* sorted unique value at 1-based index idx */
 int sk_target_value(sk_ctx *ctx, int64_t idx, double *out);
 

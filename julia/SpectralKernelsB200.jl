@@ -30,6 +30,8 @@ struct ScanArgs              # sk_scan_args
 end
 struct SubintervalOpts       # sk_subinterval_opts
   cmul::Float64; p::Float64; kernel::Int32; logw::Int32
+  nu::Int32; _pad::Int32     # Bessel order for SK_KERNEL_BESSEL (dim >= 2)
+  xdiv_pow::Float64          # dim/2 - 1
   speculate::Ptr{ScanArgs}   # C_NULL, or the panel's scan arguments on the panel's first sub-interval
 end
 
@@ -94,7 +96,7 @@ function kernel_values_b200(config::AdaptiveKernelConfig, xs::AbstractVector{Flo
   conv_crit  = config.convergence_criteria
   (a, b)     = (0.0, 0.0)
   kernel     = config.derivative ? SK_KERNEL_SIN : SK_KERNEL_COS           # quadrature.jl:177
-  opts       = Ref(SubintervalOpts(config.c, config.p, kernel, config.logw ? 1 : 0, C_NULL))
+  opts       = Ref(SubintervalOpts(config.c, config.p, kernel, config.logw ? 1 : 0, 0, 0, 0.0, C_NULL))
   # (optional optimisation, see sk_subinterval_opts.speculate: evaluate estimate_tail_decay(config, a, b)
   #  before the panel and pass pointer_from_objref/Ref of the ScanArgs with the panel's first sub-interval)
   tau        = config.tol*abs(k0)/2

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsk_b200.so")
 
 SK_OK = 0
-SK_KERNEL_COS, SK_KERNEL_SIN = 0, 1
+SK_KERNEL_COS, SK_KERNEL_SIN, SK_KERNEL_BESSEL = 0, 1, 2
 SK_CRIT = {"panel": 0, "tails": 1, "both": 2}
 SK_SDF_HOST, SK_SDF_MATERN, SK_SDF_EXPONENTIAL = 0, 1, 2
 SK_ERR_NAN, SK_ERR_SPLIT, SK_ERR_UNSUPPORTED = -4, -5, -8
@@ -41,7 +41,7 @@ class ScanArgs(ctypes.Structure):
 
 class SubintervalOpts(ctypes.Structure):
     _fields_ = [("cmul", c_double), ("p", c_double), ("kernel", c_int32), ("logw", c_int32),
-                ("speculate", POINTER(ScanArgs))]
+                ("nu", c_int32), ("_pad", c_int32), ("xdiv_pow", c_double), ("speculate", POINTER(ScanArgs))]
 
 
 class Stats(ctypes.Structure):
@@ -79,6 +79,7 @@ SIGNATURES = {
     "sk_sdf_builtin": (c_int, [c_void_p, c_int32, _dp, c_int32, c_int32]),
     "sk_targets_set": (c_int, [c_void_p, c_void_p, c_int64, POINTER(TargetInfo)]),
     "sk_targets_set_device": (c_int, [c_void_p, c_void_p, c_int64, POINTER(TargetInfo)]),
+    "sk_targets_set_pairs": (c_int, [c_void_p, _dp, c_int64, c_int32, POINTER(c_int64), c_int64, POINTER(TargetInfo)]),
     "sk_target_value": (c_int, [c_void_p, c_int64, _dp]),
     "sk_run_begin": (c_int, [c_void_p]),
     "sk_zero_lag_set": (c_int, [c_void_p, c_double]),
@@ -265,6 +266,21 @@ class Session:
         self._ck(self._L.sk_targets_set_device(self._h, c_void_p(dev_ptr), int(n), byref(info)))
         return info
 
+    def targets_set_pairs(self, pts, pairs=None) -> TargetInfo:
+        """pts: (npts, dim) array; pairs: (npairs, 2) int64 0-based index pairs, or None for all i < j."""
+        pts = np.ascontiguousarray(np.atleast_2d(np.asarray(pts, dtype=np.float64).T).T if np.ndim(pts) == 1
+                                   else np.asarray(pts, dtype=np.float64))
+        if pts.ndim == 1:
+            pts = pts.reshape(-1, 1)
+        info = TargetInfo()
+        if pairs is None:
+            self._ck(self._L.sk_targets_set_pairs(self._h, _p(pts), pts.shape[0], pts.shape[1], None, 0, byref(info)))
+        else:
+            pr = np.ascontiguousarray(pairs, dtype=np.int64)
+            self._ck(self._L.sk_targets_set_pairs(self._h, _p(pts), pts.shape[0], pts.shape[1],
+                                                  pr.ctypes.data_as(POINTER(c_int64)), pr.shape[0], byref(info)))
+        return info
+
     def target_value(self, idx: int) -> float:
         out = c_double()
         self._ck(self._L.sk_target_value(self._h, int(idx), byref(out)))
@@ -284,15 +300,17 @@ class Session:
     def panel_set_range(self, r_lo: float, r_hi: float, n_active_global: int = 0):
         self._ck(self._L.sk_panel_set_range(self._h, float(r_lo), float(r_hi), int(n_active_global)))
 
-    def subinterval(self, a: float, b: float, cmul: float, p: float, kernel: int, logw: bool, speculate=None) -> float:
-        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0,
+    def subinterval(self, a: float, b: float, cmul: float, p: float, kernel: int, logw: bool, speculate=None,
+                    nu: int = 0, xdiv_pow: float = 0.0) -> float:
+        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0, int(nu), 0, float(xdiv_pow),
                             ctypes.pointer(speculate) if speculate is not None else None)
         out = c_double()
         self._ck(self._L.sk_subinterval(self._h, float(a), float(b), byref(o), byref(out)))
         return out.value
 
-    def subinterval_host(self, a, b, no1, buf1, no2, buf2, cmul, p, kernel, logw, speculate=None) -> float:
-        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0,
+    def subinterval_host(self, a, b, no1, buf1, no2, buf2, cmul, p, kernel, logw, speculate=None,
+                         nu: int = 0, xdiv_pow: float = 0.0) -> float:
+        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0, int(nu), 0, float(xdiv_pow),
                             ctypes.pointer(speculate) if speculate is not None else None)
         out = c_double()
         no1, buf1, no2, buf2 = _f64(no1), _f64(buf1), _f64(no2), _f64(buf2)
@@ -301,7 +319,7 @@ class Session:
         return out.value
 
     def subinterval_logw_host(self, a, b, no1, bufa1, bufb1, no2, bufa2, bufb2, cmul, p, i0_coef, denom) -> float:
-        o = SubintervalOpts(float(cmul), float(p), SK_KERNEL_COS, 1, None)
+        o = SubintervalOpts(float(cmul), float(p), SK_KERNEL_COS, 1, 0, 0, 0.0, None)
         out = c_double()
         arrs = [_f64(x) for x in (no1, bufa1, bufb1, no2, bufa2, bufb2)]
         self._ck(self._L.sk_subinterval_logw_host(self._h, float(a), float(b), *[_p(x) for x in arrs], byref(o),

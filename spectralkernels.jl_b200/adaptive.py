@@ -20,7 +20,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _capi
-from ._capi import SK_CRIT, SK_KERNEL_COS, SK_KERNEL_SIN, ScanArgs, Session, SkError
+from ._capi import SK_CRIT, SK_KERNEL_BESSEL, SK_KERNEL_COS, SK_KERNEL_SIN, ScanArgs, Session, SkError
 from .sdf import is_builtin
 
 _CRITERIA = ("panel", "tails", "both")
@@ -248,9 +248,17 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
     """Scalar control flow of src/quadrature.jl:169-275: LIFO bisection, accept test against
     config.tol*k0 (not the split tolerance), 9:1 tolerance split at the origin.  The per-target work of
     every pass happens inside sk_subinterval / sk_subinterval_accept."""
-    if cfg.dim != 1:
-        raise NotImplementedError("dim > 1 (Hankel kernel, src/quadrature.jl:137-161) is not built yet")
-    kernel = SK_KERNEL_SIN if cfg.derivative else SK_KERNEL_COS                  # :177
+    nu, xdiv = 0, 0.0
+    if cfg.dim == 1:
+        kernel = SK_KERNEL_SIN if cfg.derivative else SK_KERNEL_COS              # :177
+    else:
+        # (:J, dim/2) or (:J, dim/2-1), :179; only even dims are usable (Int64(kernel[2]), :138).  The device
+        # evaluates the reference's direct Bessel summation (:145-160) at every size: the O(N) NUFHT of
+        # FastHankelTransform.jl is not built.
+        order = cfg.dim / 2 if cfg.derivative else cfg.dim / 2 - 1
+        if order != int(order):
+            raise ValueError(f"InexactError: Int64({order})")                    # :138
+        kernel, nu, xdiv = SK_KERNEL_BESSEL, int(order), cfg.dim / 2 - 1         # :252-254
     stack = [(a, b, cfg.tol)]                                                    # :173
     builtin = is_builtin(cfg.f)
     first = True
@@ -266,6 +274,8 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
                                f"(b - a < 1e-16). Exiting to avoid infinite splitting.")
         if active:
             if origin and cfg.logw:                                              # :186-228, integration by parts
+                if cfg.dim != 1:
+                    raise NotImplementedError("log-weighted origin sub-interval for dim > 1 (src/quadrature.jl:204-221)")
                 f, df = cfg.f, cfg.df
                 if df is None:
                     raise TypeError("logw=true needs df (the derivative of the spectral density)")
@@ -277,10 +287,11 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
                 mx = eng.subinterval_logw_host(_a, _b, no1, ba1, bb1, no2, ba2, bb2, cfg.c, cfg.p, i0,
                                                cfg.dim - cfg.alpha)
             elif builtin:
-                mx = eng.subinterval(_a, _b, cfg.c, cfg.p, kernel, cfg.logw, speculate=spec)
+                mx = eng.subinterval(_a, _b, cfg.c, cfg.p, kernel, cfg.logw, speculate=spec, nu=nu, xdiv_pow=xdiv)
             else:
                 no1, buf1, no2, buf2 = _host_strengths(cfg, eng, _a, _b, origin)
-                mx = eng.subinterval_host(_a, _b, no1, buf1, no2, buf2, cfg.c, cfg.p, kernel, cfg.logw, speculate=spec)
+                mx = eng.subinterval_host(_a, _b, no1, buf1, no2, buf2, cfg.c, cfg.p, kernel, cfg.logw, speculate=spec,
+                                          nu=nu, xdiv_pow=xdiv)
         else:
             mx = 0.0
         # max over all ranks; NaN travels as +inf (both fail the accept test, quadrature.jl:260)
@@ -310,7 +321,8 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
 def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, param_derivative: bool = False,
                   verbose: bool = False, trace: Optional[list] = None, comm=None, want_errors: bool = True,
                   out_vals=None, out_errs=None, xs_device: Optional[Tuple[int, int]] = None,
-                  out_device: Optional[Tuple[int, int]] = None, reuse_targets: bool = False):
+                  out_device: Optional[Tuple[int, int]] = None, reuse_targets: bool = False,
+                  points=None, pairs=None):
     """`kernel_values(config, xs; k0, param_derivative, verbose)` (src/adaptive.jl:95-108): returns
     (values, errors) in the order of `xs`, duplicates included.
 
@@ -319,7 +331,9 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
     `out_device` ((pointer, n) / (vals_ptr, errs_ptr): device-resident input and output, no PCIe),
     `reuse_targets` (the engine already holds exactly these distances from the previous call -- the
     P_sdf + 2 derivative runs of src/derivatives.jl:86-112 all use the same lags -- so the upload and the
-    sort/unique are skipped)."""
+    sort/unique are skipped), `points` (+ optional `pairs`): evaluate at lag = ||points[i] - points[j]|| for the
+    given index pairs (default: all i < j), computed on the device (src/model.jl:53-68 with NoWarping); `xs` is
+    ignored and the results come back in pair order."""
     eng = cfg.engine
     comm = comm or _NoComm()
     if k0 is None:
@@ -331,6 +345,9 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
     # unique + sort + inverse map on the device (adaptive.jl:99, :113-120)
     if reuse_targets and getattr(eng, "_last_targets", None) is not None:
         info, n_in = eng._last_targets
+    elif points is not None:
+        info = eng.targets_set_pairs(points, pairs)
+        n_in = int(info.n_in)
     elif xs_device is not None:
         info = eng.targets_set_device(*xs_device)
         n_in = int(xs_device[1])

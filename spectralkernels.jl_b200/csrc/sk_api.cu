@@ -279,7 +279,8 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
   const int ksin = o->kernel == SK_KERNEL_SIN;
   // fast = nufft_quad_size_cutoff(length(no2), length(xs)) && length(xs) > 1   (src/quadrature.jl:105, src/utils.jl:39)
   const long long n_cut = c->n_act_global > 0 ? c->n_act_global : n_act;
-  const bool fast = (M2 * n_cut > (1LL << 18)) && n_cut > 1;
+  const bool bessel = o->kernel == SK_KERNEL_BESSEL;
+  const bool fast = !bessel && (M2 * n_cut > (1LL << 18)) && n_cut > 1;
   // speculation is only meaningful for the first sub-interval of the panel (the whole panel)
   const bool spec_on = fast && o->speculate != nullptr && c->panel_subs == 0 && o->speculate->criteria >= 0 &&
                        o->speculate->criteria <= 2;
@@ -318,11 +319,16 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
     if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
     c->stats.n_fast++;
   } else {
+    if (n_act > 2000000000LL) return fail(c, SK_ERR_ARG, "too many targets for the direct branch");
     CK(c->dsum.ensure((size_t)n_act * 2));
     dim3 grid((unsigned int)n_act, 2);
-    k_direct<<<grid, 256, 0, c->stream>>>(c->no1.p, c->buf1.p, M1, c->no2.p, c->buf2.p, M2, c->uxs.p + c->lo, c->dsum.p);
+    if (bessel)
+      k_direct_bessel<<<grid, 256, 0, c->stream>>>(o->nu, c->no1.p, c->buf1.p, M1, c->no2.p, c->buf2.p, M2, c->uxs.p + c->lo, c->dsum.p);
+    else
+      k_direct<<<grid, 256, 0, c->stream>>>(c->no1.p, c->buf1.p, M1, c->no2.p, c->buf2.p, M2, c->uxs.p + c->lo, c->dsum.p);
     LAUNCH_CHECK();
-    k_direct_finish<<<1, 256, 0, c->stream>>>(c->dsum.p, n_act, o->cmul, ksin, c->stage.p + c->lo, c->d_red);
+    k_direct_finish<<<nblk(n_act, 256), 256, 0, c->stream>>>(c->dsum.p, c->uxs.p + c->lo, n_act, o->cmul, ksin,
+                                                            bessel ? o->xdiv_pow : 0.0, c->stage.p + c->lo, c->d_red);
     LAUNCH_CHECK();
     c->stats.n_direct++;
   }
@@ -770,6 +776,33 @@ int sk_targets_set_device(sk_ctx *c, const double *xs_dev, int64_t n_in, sk_targ
   return targets_from_device_buffer(c, n_in, info);
 }
 
+int sk_targets_set_pairs(sk_ctx *c, const double *pts_host, int64_t npts, int32_t dim, const int64_t *pairs_host,
+                         int64_t npairs, sk_target_info *info) {
+  if (!c || !pts_host || npts < 1 || dim < 1) return fail(c, SK_ERR_ARG, "bad points");
+  CK(cudaSetDevice(c->device));
+  const long long all_pairs = (long long)npts * (npts - 1) / 2;
+  const long long np = pairs_host ? (long long)npairs : all_pairs;
+  if (np < 1) return fail(c, SK_ERR_ARG, "no pairs");
+  if (pairs_host)
+    for (long long t = 0; t < 2 * np; ++t)
+      if (pairs_host[t] < 0 || pairs_host[t] >= npts) return fail(c, SK_ERR_ARG, "pair index out of range");
+  DevBuf<double> d_pts;
+  DevBuf<long long> d_pairs;
+  CK(d_pts.ensure((size_t)npts * dim));
+  CK(cudaMemcpyAsync(d_pts.p, pts_host, sizeof(double) * npts * dim, cudaMemcpyHostToDevice, c->stream));
+  if (pairs_host) {
+    CK(d_pairs.ensure((size_t)2 * np));
+    CK(cudaMemcpyAsync(d_pairs.p, pairs_host, sizeof(long long) * 2 * np, cudaMemcpyHostToDevice, c->stream));
+  }
+  CK(c->in.ensure(np));
+  k_pair_lags<<<nblk(np, 256), 256, 0, c->stream>>>(d_pts.p, npts, dim, pairs_host ? d_pairs.p : nullptr, np, c->in.p);
+  LAUNCH_CHECK();
+  int rc = targets_from_device_buffer(c, np, info);
+  d_pts.release();
+  d_pairs.release();
+  return rc;
+}
+
 int sk_target_value(sk_ctx *c, int64_t idx, double *out) {
   if (!c || !out) return SK_ERR_ARG;
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
@@ -859,7 +892,9 @@ static int subinterval_prologue(sk_ctx *c, double a, double b, const sk_subinter
   if (!c || !o) return SK_ERR_ARG;
   if (!c->have_rule) return fail(c, SK_ERR_STATE, "sk_rule_set first");
   if (!c->in_panel) return fail(c, SK_ERR_STATE, "sk_panel_begin first");
-  if (o->kernel != SK_KERNEL_COS && o->kernel != SK_KERNEL_SIN) return fail(c, SK_ERR_UNSUPPORTED, "kernel %d", o->kernel);
+  if (o->kernel != SK_KERNEL_COS && o->kernel != SK_KERNEL_SIN && o->kernel != SK_KERNEL_BESSEL)
+    return fail(c, SK_ERR_UNSUPPORTED, "kernel %d", o->kernel);
+  if (o->kernel == SK_KERNEL_BESSEL && (o->nu < 0 || o->nu > 64)) return fail(c, SK_ERR_ARG, "Bessel order %d", o->nu);
   // check_subdivide_failure, src/utils.jl:28-36
   if (!(std::fabs(b - a) > 1e-16))
     return fail(c, SK_ERR_SPLIT,

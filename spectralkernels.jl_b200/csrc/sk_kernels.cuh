@@ -613,16 +613,53 @@ k_direct(const double *__restrict__ no1, const double *__restrict__ buf1, long l
   if (threadIdx.x == 0) { sk_cplx o; o.x = sr[0]; o.y = si[0]; sums[(long long)blockIdx.x * 2 + r] = o; }
 }
 
-// epilogue of the direct branch: same staging as the interpolation kernels (single block, n is tiny)
-__global__ void k_direct_finish(const sk_cplx *__restrict__ sums, long long n, double cmul, int kernel_sin,
-                                sk_cplx *__restrict__ stage, SkReduceOut *__restrict__ red) {
+// epilogue of the direct branches: same staging as the interpolation kernels.  xdiv != 0 divides by
+// x^xdiv (dim > 1, src/quadrature.jl:252-254; the reference scales by c first, then divides).
+__global__ void __launch_bounds__(256)
+k_direct_finish(const sk_cplx *__restrict__ sums, const double *__restrict__ xs, long long n, double cmul, int kernel_sin,
+                double xdiv, sk_cplx *__restrict__ stage, SkReduceOut *__restrict__ red) {
   double d = 0.0;
   unsigned int fl = 0;
-  for (long long j = threadIdx.x; j < n; j += blockDim.x) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) {
     const sk_cplx f1 = sums[2 * j], f2 = sums[2 * j + 1];
-    sk_stage(kernel_sin ? f1.y : f1.x, kernel_sin ? f2.y : f2.x, cmul, &stage[j], d, fl);
+    double i1 = sk_mul(kernel_sin ? f1.y : f1.x, cmul), i2 = sk_mul(kernel_sin ? f2.y : f2.x, cmul);
+    if (xdiv != 0.0) {
+      const double den = pow(xs[j], xdiv);
+      i1 = i1 / den;
+      i2 = i2 / den;
+    }
+    sk_stage(i1, i2, 1.0, &stage[j], d, fl);
   }
   sk_block_reduce_maxflags(d, fl, red);
+}
+
+// direct Bessel summation, int[j] = sum_k buf[k] besselj(nu, 2 pi no[k] x[j])  (src/quadrature.jl:145-160).
+// This is the reference's own definition of the dim >= 2 transform; the O(N) NUFHT it uses for large
+// problems (FastHankelTransform.jl) is not built, so this branch costs O(M N) at any size.
+__global__ void __launch_bounds__(256)
+k_direct_bessel(int nu, const double *__restrict__ no1, const double *__restrict__ buf1, long long M1,
+                const double *__restrict__ no2, const double *__restrict__ buf2, long long M2,
+                const double *__restrict__ xs, sk_cplx *__restrict__ sums) {
+  const int r = blockIdx.y;
+  const double *no = r ? no2 : no1;
+  const double *buf = r ? buf2 : buf1;
+  const long long M = r ? M2 : M1;
+  const double xj = xs[blockIdx.x];
+  double acc = 0.0;
+  for (long long k = threadIdx.x; k < M; k += blockDim.x) {
+    const double z = sk_mul(sk_mul(6.283185307179586, no[k]), xj);       // 2pi*no[k]*xj
+    const double jv = nu == 0 ? j0(z) : (nu == 1 ? j1(z) : jn(nu, z));
+    acc = sk_fma(buf[k], jv, acc);
+  }
+  __shared__ double sr[256];
+  sr[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sr[threadIdx.x] += sr[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { sk_cplx o; o.x = sr[0]; o.y = 0.0; sums[(long long)blockIdx.x * 2 + r] = o; }
 }
 
 // ---- K5 ---------------------------------------------------------------------------------------------
@@ -848,6 +885,35 @@ __global__ void k_gather(const unsigned int *__restrict__ inv, const sk_cplx *__
   const sk_cplx r = res[inv[j]];
   out_v[j] = r.x;
   if (out_e) out_e[j] = r.y;
+}
+
+// lags of point pairs, computed where they are consumed (src/model.jl:53-68: warp_lags = norm(x_j - x_k) for
+// every index pair; config 3's 49 995 000 pairwise distances of 1e4 points never cross PCIe).
+// pairs == nullptr: all pairs i < j in row-major order of the strict upper triangle (plus nothing for i == j).
+__global__ void k_pair_lags(const double *__restrict__ pts, long long npts, int dim, const long long *__restrict__ pairs,
+                            long long npairs, double *__restrict__ lags) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npairs) return;
+  long long i, j;
+  if (pairs) {
+    i = pairs[2 * t];
+    j = pairs[2 * t + 1];
+  } else {
+    // t-th pair of the strict upper triangle: row i has npts-1-i entries
+    const double nn = (double)npts;
+    long long ii = (long long)floor(((2.0 * nn - 1.0) - sqrt((2.0 * nn - 1.0) * (2.0 * nn - 1.0) - 8.0 * (double)t)) * 0.5);
+    if (ii < 0) ii = 0;
+    while (ii * (2 * npts - ii - 1) / 2 > t) --ii;                       // fix floating-point off-by-one
+    while ((ii + 1) * (2 * npts - ii - 2) / 2 <= t) ++ii;
+    i = ii;
+    j = t - ii * (2 * npts - ii - 1) / 2 + ii + 1;
+  }
+  double acc = 0.0;
+  for (int d = 0; d < dim; ++d) {
+    const double df = sk_add(pts[i * dim + d], -pts[j * dim + d]);
+    acc = sk_add(acc, sk_mul(df, df));
+  }
+  lags[t] = dim == 1 ? fabs(sk_add(pts[i], -pts[j])) : sqrt(acc);
 }
 
 // number of sorted values <= r (== the largest 1-based index with xs[idx] <= r)

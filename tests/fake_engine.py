@@ -60,8 +60,15 @@ class FakeEngine:
         assert r_lo <= self.range[0] and r_hi >= self.range[1]
         self.calls.append(("range", r_lo, r_hi))
 
-    def subinterval_host(self, a, b, no1, buf1, no2, buf2, cmul, p, kernel, logw, speculate=None):
+    def subinterval_host(self, a, b, no1, buf1, no2, buf2, cmul, p, kernel, logw, speculate=None, nu=0, xdiv_pow=0.0):
         x = self.uxs[self.lo:self.hi]
+        if kernel == 2:
+            i1 = so.direct_bessel(nu, no1, buf1, x) * cmul
+            i2 = so.direct_bessel(nu, no2, buf2, x) * cmul
+            if xdiv_pow != 0.0:
+                i1, i2 = i1 / x ** xdiv_pow, i2 / x ** xdiv_pow
+            self._stage = (i2, np.abs(i2 - i1))
+            return float(np.max(self._stage[1]))
         f1, f2 = so.direct_cis(no1, buf1, x), so.direct_cis(no2, buf2, x)
         i1 = (f1.imag if kernel == 1 else f1.real) * cmul
         i2 = (f2.imag if kernel == 1 else f2.real) * cmul

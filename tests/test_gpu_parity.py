@@ -255,6 +255,32 @@ def test_kernel_derivative_warping(sk, golden):
     assert np.max(np.linalg.norm(dK[:, None] * dlag - cf.exponential_dcov(lags)[:, None] * dlag, axis=1)) < 1e-8
 
 
+def test_pair_lags_on_device(sk):
+    """src/model.jl:53-68 (NoWarping): lags of index pairs computed on the device equal the host-computed
+    ones bit for bit, so kernel_values(points=...) equals kernel_values(lags)."""
+    rng = np.random.default_rng(9)
+    pts = rng.uniform(0, 1, (300, 2))
+    iu = np.triu_indices(300, k=1)
+    lags = np.sqrt((pts[iu[0], 0] - pts[iu[1], 0]) ** 2 + (pts[iu[0], 1] - pts[iu[1], 1]) ** 2)
+    cfg = sk.AdaptiveKernelConfig(sk.Matern(2.14, 0.97, 0.89), alpha=0.5)
+    k0 = sk.compute_k0(cfg)
+    v_all, e_all = sk.kernel_values(cfg, None, k0=k0, points=pts)
+    v_ref, e_ref = sk.kernel_values(cfg, lags, k0=k0)
+    assert v_all.size == 300 * 299 // 2
+    assert np.max(np.abs(v_all - v_ref)) <= 1e-13 * k0          # sqrt on device vs numpy: last-bit lags
+    pairs = np.stack([rng.integers(0, 300, 5000), rng.integers(0, 300, 5000)], axis=1)
+    v_p, _ = sk.kernel_values(cfg, None, k0=k0, points=pts, pairs=pairs)
+    d = pts[pairs[:, 0]] - pts[pairs[:, 1]]
+    v_q, _ = sk.kernel_values(cfg, np.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2), k0=k0)
+    assert np.max(np.abs(v_p - v_q)) <= 1e-13 * k0
+    same = pairs[:, 0] == pairs[:, 1]
+    assert np.all(v_p[same] == k0)                              # zero lag -> K(0)
+    x1 = rng.uniform(0, 2, 200)
+    v1, _ = sk.kernel_values(sk.AdaptiveKernelConfig(sk.Exponential(1.0, 1.0)), None, k0=2.0, points=x1)
+    i1 = np.triu_indices(200, k=1)
+    assert np.max(np.abs(v1 - cf.exponential_cov(np.abs(x1[i1[0]] - x1[i1[1]])))) <= 2e-8
+
+
 def test_host_callable_equals_builtin(sk, golden):
     """Arbitrary closures are evaluated on the host and uploaded (sk_subinterval_host)."""
     xs = golden["readme_r"][::7]
@@ -350,14 +376,35 @@ def test_shrinking_active_set_trace(sk):
     assert np.allclose(eg, eo, rtol=1e-6, atol=1e-11 * k0)
 
 
+@pytest.mark.parametrize("derivative", [False, True])
+def test_matern_2d_bessel_branch(sk, golden, derivative):
+    """dim = 2 (test/matern_sdf.jl with dim = 2; the enabled nll_2d tests run on this branch): Bessel kernel by the
+    reference's direct Bessel summation (src/quadrature.jl:145-160) on the device, against the oracle and the
+    closed form."""
+    i = np.unique(np.append(np.arange(0, 1000, 10), 999))
+    parms = tuple(golden["matern_parms"])
+    xs = golden["matern_r"][i]
+    true = (golden["matern2d_dK"] if derivative else golden["matern2d_K"])[i]
+    k0 = float(golden["matern2d_K"][0])
+    cfg = sk.AdaptiveKernelConfig(sk.Matern(*parms, d=2), dim=2, derivative=derivative)
+    ocfg = so.OracleConfig(lambda w: cf.matern_sdf(w, parms, d=2), dim=2, derivative=derivative)
+    tg, to = [], []
+    vg, eg = sk.kernel_values(cfg, xs, k0=k0, trace=tg)
+    vo, eo = so.kernel_values(ocfg, xs, k0=k0, trace=to)
+    assert np.all(np.abs(vg - true) / k0 <= 10 * 1e-8)
+    assert np.max(np.abs(vg - vo)) <= 1e-11 * k0
+    assert _trace_key(tg) == _trace_key(to)
+    assert cfg.engine.stats()["n_fast"] == 0
+
+
 def test_errors(sk):
     cfg = sk.AdaptiveKernelConfig(sk.Matern())
     with pytest.raises(sk.SkError):
         sk.kernel_values(cfg, np.array([0.1, -0.2]), k0=1.0)              # negative distance
     with pytest.raises(sk.SkError):
         sk.kernel_values(cfg, np.array([0.1, np.nan]), k0=1.0)
-    with pytest.raises(NotImplementedError):
-        sk.kernel_values(sk.AdaptiveKernelConfig(sk.Matern(d=2), dim=2), np.array([0.1, 0.2, 0.3]), k0=1.0)
+    with pytest.raises(ValueError):                                           # odd dim >= 3: InexactError upstream
+        sk.kernel_values(sk.AdaptiveKernelConfig(sk.Matern(d=3), dim=3), np.array([0.1, 0.2, 0.3]), k0=1.0)
 
 
 # ---- full BASELINE size: size-independent properties --------------------------------------------------------

@@ -47,6 +47,21 @@ def test_matern_sdf_1d(golden, tol, derivative):
     assert np.all(np.abs(vals - true) / k0 <= 10 * tol)
 
 
+@pytest.mark.parametrize("derivative", [False, True])
+def test_matern_sdf_2d(golden, derivative):
+    """test/matern_sdf.jl:2-34 with dim = 2: the (:J, nu) Bessel kernel (src/quadrature.jl:137-161, :176-180),
+    prefactor 2 pi (src/adaptive.jl:43) and p = dim/2 (+1).  40 of the reference's 1000 grid points (direct
+    Bessel summation is O(M N))."""
+    i = np.unique(np.append(np.arange(0, 1000, 25), 999))
+    parms = tuple(golden["matern_parms"])
+    r = golden["matern_r"][i]
+    true = (golden["matern2d_dK"] if derivative else golden["matern2d_K"])[i]
+    k0 = float(golden["matern2d_K"][0])
+    cfg = so.OracleConfig(lambda w: cf.matern_sdf(w, parms, d=2), dim=2, tol=1e-8, derivative=derivative)
+    vals, _ = so.kernel_values(cfg, r, **({"k0": k0} if derivative else {}))
+    assert np.all(np.abs(vals - true) / k0 <= 10 * 1e-8)
+
+
 @pytest.mark.parametrize("tol", [1e-4, 1e-8])
 def test_singular_matern_1d(golden, tol):
     """test/matern_sdf.jl:36-64 with dim=1, alpha=0.5 (Jacobi origin panel).  K(0) is infinite for the

@@ -106,6 +106,17 @@ def test_driver_with_fake_engine_matches_oracle_driver():
         vg, eg = sk.kernel_values(cfg, xs, k0=5.9, trace=tg)
         vo, eo = so.kernel_values(ocfg, xs, k0=5.9, trace=to)
         assert np.array_equal(vg, vo), kw
+        assert _key(tg, True) == _key(to, True), kw
+    # dim = 2: Bessel kernels (src/quadrature.jl:137-161, :176-180, :252-254), direct Bessel sums on both sides
+    S2 = lambda w: (0.25 + w ** 2) ** -2.0
+    xs2 = np.concatenate([[0.0], 10 ** np.linspace(-2, 0, 25)])
+    for kw in ({"dim": 2}, {"dim": 2, "derivative": True}, {"dim": 2, "alpha": 0.5}, {"dim": 4}):
+        cfg = sk.AdaptiveKernelConfig(S2, engine=FakeEngine(), quadspec=(256, 4), **kw)
+        ocfg = so.OracleConfig(S2, quadspec=(256, 4), **kw)
+        tg, to = [], []
+        vg, eg = sk.kernel_values(cfg, xs2, k0=3.0, trace=tg)
+        vo, eo = so.kernel_values(ocfg, xs2, k0=3.0, trace=to)
+        assert np.array_equal(vg, vo), kw
         # error estimates contain 2*trunc_err, whose (c, d) come from two different evaluations of the same
         # rank-one least-squares fit (closed form vs. lstsq): equal to ~1e-13 relative, not bit for bit
         assert np.array_equal(np.isnan(eg), np.isnan(eo)), kw
