@@ -134,7 +134,7 @@ def oracle_cpu_run(n_sample: int, steps: int, warmup: int):
 
 def run_reference(args, rank: int, world: int):
     if rank != 0:
-        return
+        return None
     steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
     r = oracle_cpu_run(args.cpu_sample, steps, warmup)
     line = {
@@ -151,17 +151,32 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": r["evals_per_s"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "max_abs_err_vs_closed_form": r["max_err"],
     }
-    print(json.dumps(line))
+    return line
 
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line (the JSON); libraries that print banners to stdout (NCCL's version
+    # line) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def run(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
+        return run_reference(args, rank, world)
 
     import torch
     import torch.distributed as dist
@@ -308,9 +323,9 @@ def main():
             line["cpu_baseline"] = {"value": r["evals_per_s"], "unit": "evals/s", "cores": r["threads"], "kind": "port",
                                     "sample": f"first {args.cpu_sample} of the 1e7 distances, 1 pass "
                                               f"({r['seconds']:.1f} s); oracle port (CPU restatement, not FINUFFT)"}
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 if __name__ == "__main__":

@@ -194,6 +194,9 @@ class _NoComm:
     def sum(self, vals: Sequence[float]) -> List[float]:
         return list(vals)
 
+    def gather(self, vals: Sequence[float]) -> List[List[float]]:
+        return [list(vals)]
+
 
 def _host_rules(cfg: AdaptiveKernelConfig, eng):
     if cfg._rules is None:
@@ -378,8 +381,12 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
     a = b = 0.0
     # global distance range over all ranks (scalars only)
     r_hi_local = info.r_max if (n >= ix1) else 0.0
-    r_lo_g = comm.min([info.r_min_pos if info.r_min_pos > 0 else math.inf])[0]
-    r_hi_g = comm.max([r_hi_local])[0]
+    # one gather of (smallest positive distance, largest distance, active count) per rank
+    g0 = comm.gather([info.r_min_pos if info.r_min_pos > 0 else math.inf, r_hi_local, float(max(n - ix1 + 1, 0))])
+    r_lo_g = min(v[0] for v in g0)
+    r_hi_g = max(v[1] for v in g0)
+    n_act_g = int(sum(v[2] for v in g0))
+    m2 = 2 * cfg.quadsz
     ipanel = 0
     tau = cfg.tol * abs(k0) / 2                                                  # :191
     while r_hi_g > 0:                                                            # :149 (hi > 0 && xs[hi] > 0)
@@ -388,8 +395,6 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
         if verbose:
             print(f"\nintegrating panel w ∈ [{a:.2e}, {b:.2e}] (length {b - a:.2e}) to resolve {hi} points "
                   f"x ≤ {r_hi_g:.2e} ")
-        if comm.world_size > 1:
-            n_act_g = int(comm.sum([float(hi - ix1 + 1) if active else 0.0])[0])
         if active:
             eng.panel_begin(ix1, hi)
             if comm.world_size > 1:
@@ -420,13 +425,24 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
             new_hi, r_stop = eng.converge_scan(sargs)                            # :183-198
         else:
             new_hi, r_stop = hi, 0.0
-        r_stop_g = comm.max([r_stop])[0]
+        # one gather per panel: every rank's stopping distance and the number of targets it keeps active if
+        # the walk stopped at ITS OWN stopping distance (a lower bound of what it keeps for the global one)
+        g1 = comm.gather([r_stop, float(max(new_hi - ix1 + 1, 0))])
+        r_stop_g = max(v[0] for v in g1)
         if comm.world_size > 1 and active and r_stop_g > r_stop:
             new_hi = eng.target_upper_index(r_stop_g)
         if active:
             eng.converge_apply(sargs, new_hi)                                    # :194
         hi = new_hi
         r_hi_g = r_stop_g
+        if comm.world_size > 1 and r_hi_g > 0:
+            # global active count of the next panel, needed only for the NUFFT-vs-direct cutoff
+            # (src/quadrature.jl:105): the lower bounds usually decide it; otherwise one exact sum
+            n_lb = int(sum(v[1] for v in g1))
+            if m2 * n_lb > 2 ** 18 and n_lb > 1:
+                n_act_g = max(n_lb, hi - ix1 + 1)
+            else:
+                n_act_g = int(comm.sum([float(max(hi - ix1 + 1, 0))])[0])
         if trace is not None:
             trace.append({"kind": "panel", "index": ipanel, "a": float(a), "b": float(b), "hi_before": int(hi_before),
                           "hi_after": int(hi), "ix1": int(ix1), "c": float(c), "d": float(d), "criteria": crit})

@@ -17,6 +17,9 @@ from typing import List, Sequence
 
 
 class TorchComm:
+    """max / min / sum all-reduces and an all-gather of a few doubles per rank.  The device buffers are
+    allocated once; every call is one H2D copy, one collective, one D2H copy."""
+
     def __init__(self, device=None, group=None):
         import torch
         import torch.distributed as dist
@@ -44,3 +47,10 @@ class TorchComm:
 
     def sum(self, vals):
         return self._reduce(vals, self._dist.ReduceOp.SUM)
+
+    def gather(self, vals):
+        t = self._torch.tensor(list(vals), dtype=self._torch.float64, device=self.device)
+        out = self._torch.empty(self.world_size * t.numel(), dtype=self._torch.float64, device=self.device)
+        self._dist.all_gather_into_tensor(out, t, group=self._group)
+        self.n_reductions += 1
+        return out.view(self.world_size, t.numel()).cpu().tolist()
