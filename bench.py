@@ -189,8 +189,8 @@ def run(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        from spectralkernels_jl_b200.sharded import TorchComm
-        comm = TorchComm(device=torch.device("cuda", local_rank))
+        from spectralkernels_jl_b200.sharded import LibComm, TorchComm
+        comm = "torch" if os.environ.get("SK_COMM", "lib") == "torch" else "lib"
 
     def barrier():
         if world > 1:
@@ -203,6 +203,10 @@ def run(args):
     phi, rho, nu = workload_sdf_params()
     cfg = sk.AdaptiveKernelConfig(sk.Matern(phi, rho, nu), device=local_rank)
     eng = cfg.engine
+    if comm == "lib":       # scalar all-reduces inside the library, on its stream (NCCL)
+        comm = LibComm.from_torch(eng)
+    elif comm == "torch":   # the same reductions through torch.distributed (A/B)
+        comm = TorchComm(device=torch.device("cuda", local_rank))
     if args.interp_mode:
         eng.set_interp_mode(args.interp_mode)
     k0 = 1.0
@@ -292,7 +296,9 @@ def run(args):
                                    "quadspec (4096,16), :both (BASELINE config 2)",
                        "n_per_gpu": n, "k0": "passed (=1.0) in both arms", "nufft_eps": 1e-15,
                        "l2": "inputs + work arrays (>1 GB per step) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": "target-sharded, scalar NCCL all-reduces only" if world > 1 else "single GPU",
+                       "parallelism": ("target-sharded, scalar NCCL all-reduces only ("
+                                       + ("in-library, on the compute stream" if getattr(comm, "fused", False) else "torch.distributed")
+                                       + ")") if world > 1 else "single GPU",
                        "panels": [(t["a"], t["b"], t["hi_before"], t["hi_after"]) for t in trace if t["kind"] == "panel"]},
             "e2e": {"value": world * n * K / (e2e_ms * 1e-3), "unit": "evals/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 16 * n,

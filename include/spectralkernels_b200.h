@@ -110,7 +110,7 @@ typedef struct sk_stats {
   double interp_ms;         /* device time in the interpolation kernel since sk_run_begin      */
   double source_ms;         /* device time in node/strength/spread/FFT since sk_run_begin      */
   int32_t timing_enabled;
-  int32_t sort_two_level;   /* 1 if the last sk_targets_set used the 4-pass + run-rank sort, 0 = full 8-pass sort */
+  int32_t sort_two_level;   /* last sk_targets_set: 2 = input was already sorted and unique (no sort), 1 = 4-pass + run-rank sort, 0 = full 8-pass sort */
 } sk_stats;
 
 /* ---- library --------------------------------------------------------------------------------- */
@@ -136,6 +136,22 @@ int sk_timer_end(sk_ctx *ctx, double *ms);
 /* measured FP64 FMA throughput of this GPU (dependent-chain DFMA micro-benchmark, TFLOP/s); the
  * denominator of the FP64 roofline, which MEASURED_PEAKS.json does not contain */
 int sk_fp64_peak(sk_ctx *ctx, double *tflops, double *ms);
+
+/* ---- target-sharded multi-GPU (one process per GPU) ---------------------------------------------------
+ * Every rank holds its own chunk of the distances; the ranks run ONE adaptive loop in lock step.  With a
+ * communicator the scalar reductions of that loop run as NCCL all-reduces on the context's stream, right
+ * behind the kernel that produced the local value: sk_subinterval* then return the maximum of max|I2-I1|
+ * over all ranks, and sk_converge_scan is a collective point too (sk_comm_last gives the global stopping
+ * distance and the summed lower bound of the active counts).  NCCL is dlopen'ed (libnccl.so.2) on first use.
+ * sk_comm_unique_id: rank 0 creates the 128-byte id, the host broadcasts it (MPI / torch.distributed / file). */
+int sk_comm_unique_id(void *out128);
+int sk_comm_init(sk_ctx *ctx, const void *id128, int32_t rank, int32_t nranks);
+int sk_comm_destroy(sk_ctx *ctx);
+/* all-reduce of up to 8 host doubles (op: 0 max, 1 min, 2 sum); synchronous; no-op without a communicator */
+int sk_comm_allreduce(sk_ctx *ctx, double *vals, int32_t n, int32_t op);
+/* a rank whose active set is empty joins the others' collective points: which = 0 sub-interval, 1 scan */
+int sk_comm_idle(sk_ctx *ctx, int32_t which);
+int sk_comm_last(sk_ctx *ctx, double *max_abs_diff, double *r_stop, int64_t *n_active_lb);
 
 /* pinned host memory for callers that want full PCIe rate (Julia: unsafe_wrap the pointer) */
 int sk_host_alloc(size_t bytes, void **out);

@@ -71,6 +71,12 @@ SIGNATURES = {
     "sk_timer_begin": (c_int, [c_void_p]),
     "sk_timer_end": (c_int, [c_void_p, _dp]),
     "sk_fp64_peak": (c_int, [c_void_p, _dp, _dp]),
+    "sk_comm_unique_id": (c_int, [c_void_p]),
+    "sk_comm_init": (c_int, [c_void_p, c_void_p, c_int32, c_int32]),
+    "sk_comm_destroy": (c_int, [c_void_p]),
+    "sk_comm_allreduce": (c_int, [c_void_p, _dp, c_int32, c_int32]),
+    "sk_comm_idle": (c_int, [c_void_p, c_int32]),
+    "sk_comm_last": (c_int, [c_void_p, _dp, _dp, POINTER(c_int64)]),
     "sk_host_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "sk_host_free": (c_int, [c_void_p]),
     "sk_nufft1d3": (c_int, [c_void_p, c_int64, _dp, _dp, c_int64, _dp, _dp, c_double]),
@@ -208,6 +214,37 @@ class Session:
 
     def set_timing(self, on: bool):
         self._ck(self._L.sk_ctx_set_timing(self._h, 1 if on else 0))
+
+    # -- in-library communicator (NCCL on the context's stream) -------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        rc = load().sk_comm_unique_id(buf)
+        if rc != SK_OK:
+            raise SkError(rc, "sk_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, nranks: int):
+        buf = ctypes.create_string_buffer(bytes(uid), 128)
+        self._ck(self._L.sk_comm_init(self._h, buf, int(rank), int(nranks)))
+        self.comm_size = int(nranks)
+
+    def comm_destroy(self):
+        self._ck(self._L.sk_comm_destroy(self._h))
+        self.comm_size = 1
+
+    def comm_allreduce(self, vals, op: int):
+        a = _f64(list(vals)).copy()
+        self._ck(self._L.sk_comm_allreduce(self._h, _p(a), a.size, int(op)))
+        return a.tolist()
+
+    def comm_idle(self, which: int):
+        self._ck(self._L.sk_comm_idle(self._h, int(which)))
+
+    def comm_last(self):
+        mx, r, n = c_double(), c_double(), c_int64()
+        self._ck(self._L.sk_comm_last(self._h, byref(mx), byref(r), byref(n)))
+        return mx.value, r.value, n.value
 
     def set_interp_mode(self, mode: int):
         self._ck(self._L.sk_ctx_set_interp_mode(self._h, int(mode)))

@@ -297,8 +297,15 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
                                           nu=nu, xdiv_pow=xdiv)
         else:
             mx = 0.0
-        # max over all ranks; NaN travels as +inf (both fail the accept test, quadrature.jl:260)
-        mx_g = comm.max([math.inf if math.isnan(mx) else mx])[0]
+        if getattr(comm, "fused", False):
+            # the library reduced over the ranks on its stream (sk_comm_init); idle ranks join the collective
+            if not active:
+                eng.comm_idle(0)
+                mx = eng.comm_last()[0]
+            mx_g = math.inf if math.isnan(mx) else mx
+        else:
+            # max over all ranks; NaN travels as +inf (both fail the accept test, quadrature.jl:260)
+            mx_g = comm.max([math.inf if math.isnan(mx) else mx])[0]
         accepted = mx_g < cfg.tol * k0                                           # :260
         if verbose:
             word = "converged" if mx_g / k0 <= _tol else "did not converge"
@@ -382,10 +389,17 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
     # global distance range over all ranks (scalars only)
     r_hi_local = info.r_max if (n >= ix1) else 0.0
     # one gather of (smallest positive distance, largest distance, active count) per rank
-    g0 = comm.gather([info.r_min_pos if info.r_min_pos > 0 else math.inf, r_hi_local, float(max(n - ix1 + 1, 0))])
-    r_lo_g = min(v[0] for v in g0)
-    r_hi_g = max(v[1] for v in g0)
-    n_act_g = int(sum(v[2] for v in g0))
+    fused = getattr(comm, "fused", False)
+    rmin_local = info.r_min_pos if info.r_min_pos > 0 else math.inf
+    if fused:
+        mxs = comm.max([-rmin_local, r_hi_local])
+        r_lo_g, r_hi_g = -mxs[0], mxs[1]
+        n_act_g = int(comm.sum([float(max(n - ix1 + 1, 0))])[0])
+    else:
+        g0 = comm.gather([rmin_local, r_hi_local, float(max(n - ix1 + 1, 0))])
+        r_lo_g = min(v[0] for v in g0)
+        r_hi_g = max(v[1] for v in g0)
+        n_act_g = int(sum(v[2] for v in g0))
     m2 = 2 * cfg.quadsz
     ipanel = 0
     tau = cfg.tol * abs(k0) / 2                                                  # :191
@@ -427,7 +441,13 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
             new_hi, r_stop = hi, 0.0
         # one gather per panel: every rank's stopping distance and the number of targets it keeps active if
         # the walk stopped at ITS OWN stopping distance (a lower bound of what it keeps for the global one)
-        g1 = comm.gather([r_stop, float(max(new_hi - ix1 + 1, 0))])
+        if fused:
+            if not active:
+                eng.comm_idle(1)
+            _, r_g, n_lb_g = eng.comm_last()
+            g1 = [[r_g, float(n_lb_g)]]
+        else:
+            g1 = comm.gather([r_stop, float(max(new_hi - ix1 + 1, 0))])
         r_stop_g = max(v[0] for v in g1)
         if comm.world_size > 1 and active and r_stop_g > r_stop:
             new_hi = eng.target_upper_index(r_stop_g)

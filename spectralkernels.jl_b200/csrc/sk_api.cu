@@ -6,6 +6,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cufft.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -44,10 +46,47 @@ struct DevBuf {
   }
 };
 
+// NCCL is loaded with dlopen when (and only when) a communicator is requested: a single-GPU user needs no
+// NCCL at all, and inside a torch process the already loaded libnccl.so.2 is reused.
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+      api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+      api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GroupStart && api.GroupEnd)
+        api.handle = h;
+    }
+  }
+  return api.handle ? &api : nullptr;
+}
+
 struct HostScalars {          // pinned mirror of the device scalars
   SkReduceOut red;
   SkTargetSummary sum;
   SkKeyBits kb;
+  SkGlobalA ga;
+  SkGlobalB gb;
+  double hv[8];               // generic host-value collectives
   double r[2];
 };
 
@@ -102,6 +141,16 @@ struct sk_ctx {
   long long scan_hi = -1;                    // 1-based index / distance returned by the last scan
   double scan_r = 0;
   int interp_mode = 0;                       // 0: cell polynomials (default), 1: per-target taps
+  bool smem_attr_set[SK_WMAX + 1] = {false};
+  // target-sharded multi-GPU: scalar NCCL all-reduces on the context's stream
+  ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  SkGlobalA *d_ga = nullptr;
+  SkGlobalB *d_gb = nullptr;
+  double *d_hv = nullptr;
+  double g_max_abs = 0;                      // global results of the last collectives
+  double g_r_stop = 0;
+  long long g_n_lb = 0;
   // speculative commit of the panel's first sub-interval (see sk_subinterval_opts::speculate)
   bool spec_active = false, spec_accepted = false;
   long long panel_subs = 0;                  // sub-intervals evaluated in the open panel
@@ -165,6 +214,52 @@ int fail(sk_ctx *c, int code, const char *fmt, ...) {
 inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
 int flush_commit(sk_ctx *c);
 
+#define NCK(call)                                                                                     \
+  do {                                                                                                \
+    ncclResult_t r_ = (call);                                                                         \
+    if (r_ != ncclSuccess)                                                                            \
+      return fail(c, SK_ERR_CUDA, "NCCL: %s (%s:%d)", nccl_api()->GetErrorString ? nccl_api()->GetErrorString(r_) : "error", \
+                  __FILE__, __LINE__);                                                                \
+  } while (0)
+
+// collective A (after a sub-interval): MAX of max|I2-I1| and of the NaN flags.  Enqueued on the stream
+// right behind the kernel that filled d_red; the caller's read-back then also fetches h_scal->ga.
+int comm_reduce_a(sk_ctx *c, int idle) {
+  if (!c->comm) return SK_OK;
+  NcclApi *N = nccl_api();
+  k_pack_global_a<<<1, 1, 0, c->stream>>>(c->d_red, c->d_ga, idle);
+  LAUNCH_CHECK();
+  NCK(N->AllReduce(c->d_ga, c->d_ga, 4, ncclUint64, ncclMax, c->comm, c->stream));
+  CK(cudaMemcpyAsync(&c->h_scal->ga, c->d_ga, sizeof(SkGlobalA), cudaMemcpyDeviceToHost, c->stream));
+  return SK_OK;
+}
+// collective B (after a scan): MAX of the stopping distance, SUM of the per-rank lower bounds of the
+// number of targets that stay active.  from_red: take the values from d_red (lo = first index of the panel).
+int comm_reduce_b(sk_ctx *c, bool from_red, unsigned long long rbits, long long n_lb) {
+  if (!c->comm) return SK_OK;
+  NcclApi *N = nccl_api();
+  if (from_red) k_pack_global_b_from_red<<<1, 1, 0, c->stream>>>(c->d_red, c->lo, c->d_gb);
+  else k_pack_global_b<<<1, 1, 0, c->stream>>>(c->d_gb, rbits, n_lb);
+  LAUNCH_CHECK();
+  NCK(N->GroupStart());
+  NCK(N->AllReduce(&c->d_gb->rbits, &c->d_gb->rbits, 1, ncclUint64, ncclMax, c->comm, c->stream));
+  NCK(N->AllReduce(&c->d_gb->n_lb, &c->d_gb->n_lb, 1, ncclInt64, ncclSum, c->comm, c->stream));
+  NCK(N->GroupEnd());
+  CK(cudaMemcpyAsync(&c->h_scal->gb, c->d_gb, sizeof(SkGlobalB), cudaMemcpyDeviceToHost, c->stream));
+  return SK_OK;
+}
+void comm_take_a(sk_ctx *c, unsigned int *fl, double *mx) {   // after the stream sync
+  if (!c->comm) return;
+  const SkGlobalA &g = c->h_scal->ga;
+  std::memcpy(mx, &g.maxbits, sizeof(double));
+  *fl = (g.nan1 ? SK_FLAG_NAN1 : 0u) | (g.nan2 ? SK_FLAG_NAN2 : 0u) | (g.nand ? SK_FLAG_NAND : 0u);
+}
+void comm_take_b(sk_ctx *c) {
+  if (!c->comm) return;
+  std::memcpy(&c->g_r_stop, &c->h_scal->gb.rbits, sizeof(double));
+  c->g_n_lb = c->h_scal->gb.n_lb;
+}
+
 int width_from_eps(double eps) {
   int w = (int)std::ceil(-std::log10(eps / 10.0));
   if (w & 1) ++w;
@@ -207,7 +302,8 @@ int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long lon
   const double per_block = span * (double)SK_TPB / (double)n;
   const int cmax = per_block <= 24.0 ? 32 : 96;
   const size_t smem = sizeof(double) * (size_t)(2 * (W / 2) * (SK_NC / 2) + (cmax + W) * 4 + cmax * 4 + cmax * SK_NC * 4);
-  static bool attr_set = false;
+  // function attributes are per device: remember per context (one context = one device)
+  bool &attr_set = c->smem_attr_set[W];
   if (!attr_set) {
     cudaFuncSetAttribute(k_interp_cells<W, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_interp_cells<W, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -333,6 +429,10 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
     c->stats.n_direct++;
   }
   CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  {
+    int rcc = comm_reduce_a(c, 0);
+    if (rcc != SK_OK) return rcc;
+  }
   CK(cudaStreamSynchronize(c->stream));
   if (c->timing && fast) {
     float ms = 0;
@@ -341,11 +441,13 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
     c->stats.interp_ms += ms;
   }
-  const unsigned int fl = c->h_scal->red.flags;
+  unsigned int fl = c->h_scal->red.flags;
   double mx;
   std::memcpy(&mx, &c->h_scal->red.maxbits, sizeof(double));
+  comm_take_a(c, &fl, &mx);                 // sharded run: the maximum and the NaN flags over all ranks
   if (fl & SK_FLAG_NAND) mx = std::nan("");
   *max_abs_diff = mx;
+  c->g_max_abs = mx;
   c->staged = true;
   c->panel_subs++;
   c->stats.n_subintervals++;
@@ -408,7 +510,7 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   CK(c->head.ensure(n_in));
   CK(c->uid.ensure(n_in));
   SkKeyBits kb0;
-  kb0.bits_or = 0ull; kb0.bits_and = ~0ull; kb0.bad = 0; kb0.overflow = 0;
+  kb0.bits_or = 0ull; kb0.bits_and = ~0ull; kb0.bad = 0; kb0.overflow = 0; kb0.unsorted = 0; kb0._pad = 0;
   c->h_scal->kb = kb0;
   CK(cudaMemcpyAsync(c->d_kb, &c->h_scal->kb, sizeof(SkKeyBits), cudaMemcpyHostToDevice, c->stream));
   k_make_keys<<<std::min<unsigned int>(nblk(n_in, 256), 148u * 16u), 256, 0, c->stream>>>(c->in.p, n_in, c->keys.p, c->idx.p, c->d_kb);
@@ -422,12 +524,23 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   tmp_bytes = tmp2 = c->cub_tmp.cap;
   const unsigned long long *skeys;
   const unsigned int *sidx;
+  bool presorted = false;
   if (two_level) {
     // Which key bits differ at all?  (one 24-byte read-back; the keys are non-negative doubles, so the
     // sign bit never varies and for a distance set spanning a few binades neither do the top exponent bits)
     CK(cudaMemcpyAsync(&c->h_scal->kb, c->d_kb, sizeof(SkKeyBits), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (c->h_scal->kb.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
+    presorted = c->h_scal->kb.unsorted == 0;       // strictly increasing input: nothing to sort or de-duplicate
+  }
+  if (presorted) {
+    CK(c->uxs.ensure(n_in));
+    CK(c->inv.ensure(n_in));
+    k_identity_targets<<<nblk(n_in, 256), 256, 0, c->stream>>>(c->keys.p, n_in, c->uxs.p, c->inv.p, c->uid.p);
+    LAUNCH_CHECK();
+    skeys = c->keys.p;
+    sidx = c->idx.p;
+  } else if (two_level) {
     const unsigned long long varying = c->h_scal->kb.bits_or ^ c->h_scal->kb.bits_and;
     int top = 0;                                         // number of low bits that can differ
     while (top < 64 && (varying >> top) != 0ull) ++top;
@@ -449,13 +562,15 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
     k_flag_heads<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, n_in, c->head.p);
     LAUNCH_CHECK();
   }
-  CK(cub::DeviceScan::InclusiveSum(c->cub_tmp.p, tmp2, c->head.p, c->uid.p, (int)n_in, c->stream));
-  c->stats.kernel_launches += 2;
-  // unique table sized for the worst case (n_unique <= n_in): no host round trip before the compaction
-  CK(c->uxs.ensure(n_in));
-  CK(c->inv.ensure(n_in));
-  k_scatter_unique<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, sidx, c->head.p, c->uid.p, n_in, c->uxs.p, c->inv.p);
-  LAUNCH_CHECK();
+  if (!presorted) {
+    CK(cub::DeviceScan::InclusiveSum(c->cub_tmp.p, tmp2, c->head.p, c->uid.p, (int)n_in, c->stream));
+    c->stats.kernel_launches += 2;
+    // unique table sized for the worst case (n_unique <= n_in): no host round trip before the compaction
+    CK(c->uxs.ensure(n_in));
+    CK(c->inv.ensure(n_in));
+    k_scatter_unique<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, sidx, c->head.p, c->uid.p, n_in, c->uxs.p, c->inv.p);
+    LAUNCH_CHECK();
+  }
   k_target_summary<<<1, 1, 0, c->stream>>>(c->uxs.p, c->uid.p, n_in, c->d_kb, c->d_sum);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
@@ -477,7 +592,7 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   c->staged = false;
   c->commit_pending = false;
   c->scan_hi = -1;
-  c->stats.sort_two_level = two_level ? 1 : 0;
+  c->stats.sort_two_level = presorted ? 2 : (two_level ? 1 : 0);
   if (info) {
     info->n_in = n_in;
     info->n_unique = nu;
@@ -563,6 +678,10 @@ int sk_ctx_destroy(sk_ctx *c) {
   c->cs1.release(); c->cs2.release(); c->fft.release(); c->dsum.release();
   c->res.release(); c->pan.release(); c->stage.release();
   c->fftB.release(); c->dsumB.release(); c->bufb1.release(); c->bufb2.release();
+  if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
+  if (c->d_ga) cudaFree(c->d_ga);
+  if (c->d_gb) cudaFree(c->d_gb);
+  if (c->d_hv) cudaFree(c->d_hv);
   if (c->d_sum) cudaFree(c->d_sum);
   if (c->d_kb) cudaFree(c->d_kb);
   c->keys.release(); c->keys_alt.release(); c->idx.release(); c->idx_alt.release();
@@ -638,6 +757,95 @@ int sk_fp64_peak(sk_ctx *c, double *tflops, double *ms_out) {
   const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
   *tflops = flops / (best * 1e-3) / 1e12;
   if (ms_out) *ms_out = best;
+  return SK_OK;
+}
+
+// ---- target-sharded multi-GPU: communicator and collectives ---------------------------------------------
+int sk_comm_unique_id(void *out128) {
+  if (!out128) return SK_ERR_ARG;
+  NcclApi *N = nccl_api();
+  if (!N) return SK_ERR_UNSUPPORTED;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (N->GetUniqueId(&id) != ncclSuccess) return SK_ERR_CUDA;
+  std::memcpy(out128, &id, sizeof(id));
+  return SK_OK;
+}
+
+int sk_comm_init(sk_ctx *c, const void *id128, int32_t rank, int32_t nranks) {
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(c, SK_ERR_ARG, "bad communicator arguments");
+  NcclApi *N = nccl_api();
+  if (!N) return fail(c, SK_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  CK(cudaSetDevice(c->device));
+  if (c->comm) { N->CommDestroy(c->comm); c->comm = nullptr; }
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  NCK(N->CommInitRank(&c->comm, nranks, id, rank));
+  c->comm_rank = rank;
+  c->comm_size = nranks;
+  if (!c->d_ga) CK(cudaMalloc((void **)&c->d_ga, sizeof(SkGlobalA)));
+  if (!c->d_gb) CK(cudaMalloc((void **)&c->d_gb, sizeof(SkGlobalB)));
+  if (!c->d_hv) CK(cudaMalloc((void **)&c->d_hv, 8 * sizeof(double)));
+  return SK_OK;
+}
+
+int sk_comm_destroy(sk_ctx *c) {
+  if (!c) return SK_ERR_ARG;
+  if (c->comm) {
+    cudaStreamSynchronize(c->stream);
+    nccl_api()->CommDestroy(c->comm);
+    c->comm = nullptr;
+  }
+  c->comm_size = 1;
+  return SK_OK;
+}
+
+// generic collective on up to 8 host doubles (op: 0 max, 1 min, 2 sum); synchronous.  Used once per
+// kernel_values call (global distance range / counts) and for the rare exact count.
+int sk_comm_allreduce(sk_ctx *c, double *vals, int32_t n, int32_t op) {
+  if (!c || !vals || n < 1 || n > 8 || op < 0 || op > 2) return fail(c, SK_ERR_ARG, "bad allreduce arguments");
+  if (!c->comm) return SK_OK;
+  NcclApi *N = nccl_api();
+  for (int i = 0; i < n; ++i) c->h_scal->hv[i] = vals[i];
+  CK(cudaMemcpyAsync(c->d_hv, c->h_scal->hv, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  NCK(N->AllReduce(c->d_hv, c->d_hv, n, ncclDouble, op == 0 ? ncclMax : (op == 1 ? ncclMin : ncclSum), c->comm, c->stream));
+  CK(cudaMemcpyAsync(c->h_scal->hv, c->d_hv, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; ++i) vals[i] = c->h_scal->hv[i];
+  return SK_OK;
+}
+
+// a rank without active targets takes part in the collective points of the other ranks' sub-intervals
+// (which = 0) and scans (which = 1) with neutral contributions
+int sk_comm_idle(sk_ctx *c, int32_t which) {
+  if (!c) return SK_ERR_ARG;
+  if (!c->comm) return SK_OK;
+  CK(cudaSetDevice(c->device));
+  if (which == 0) {
+    int rc = comm_reduce_a(c, 1);
+    if (rc != SK_OK) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned int fl = 0;
+    double mx = 0.0;
+    comm_take_a(c, &fl, &mx);
+    if (fl & SK_FLAG_NAND) mx = std::nan("");
+    c->g_max_abs = mx;
+  } else {
+    int rc = comm_reduce_b(c, false, 0ull, 0);
+    if (rc != SK_OK) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    comm_take_b(c);
+  }
+  return SK_OK;
+}
+
+// global results of the last collective points: max |I2-I1| over all ranks (last sub-interval), stopping
+// distance over all ranks and the summed lower bound of the active counts (last scan)
+int sk_comm_last(sk_ctx *c, double *max_abs_diff, double *r_stop, int64_t *n_active_lb) {
+  if (!c) return SK_ERR_ARG;
+  if (max_abs_diff) *max_abs_diff = c->g_max_abs;
+  if (r_stop) *r_stop = c->g_r_stop;
+  if (n_active_lb) *n_active_lb = c->g_n_lb;
   return SK_OK;
 }
 
@@ -1003,13 +1211,20 @@ int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, c
     c->stats.n_direct++;
   }
   CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  {
+    int rcc = comm_reduce_a(c, 0);
+    if (rcc != SK_OK) return rcc;
+  }
   CK(cudaStreamSynchronize(c->stream));
-  const unsigned int fl = c->h_scal->red.flags;
+  unsigned int fl = c->h_scal->red.flags;
   double mx;
   std::memcpy(&mx, &c->h_scal->red.maxbits, sizeof(double));
+  comm_take_a(c, &fl, &mx);
   if (fl & SK_FLAG_NAND) mx = std::nan("");
   *max_abs_diff = mx;
+  c->g_max_abs = mx;
   c->staged = true;
+  c->panel_subs++;
   c->stats.n_subintervals++;
   c->stats.units += n_act;
   if (!(fl & SK_FLAG_NAN1) && (fl & SK_FLAG_NAN2)) return fail(c, SK_ERR_NAN, "NaN detected in panel integral...");
@@ -1084,6 +1299,15 @@ int sk_converge_scan(sk_ctx *c, const sk_scan_args *a, int64_t *new_hi, double *
     if (r_at_new_hi) *r_at_new_hi = c->spec_r;
     c->scan_hi = c->spec_new_hi;
     c->scan_r = c->spec_r;
+    if (c->comm) {   // sharded run: the scan is a collective point for every rank
+      unsigned long long rb = 0ull;
+      std::memcpy(&rb, &c->spec_r, sizeof(double));
+      const long long nlb = c->spec_new_hi - c->lo > 0 ? c->spec_new_hi - c->lo : 0;
+      int rcc = comm_reduce_b(c, false, rb, nlb);
+      if (rcc != SK_OK) return rcc;
+      CK(cudaStreamSynchronize(c->stream));
+      comm_take_b(c);
+    }
     return SK_OK;
   }
   const long long n = c->hi - c->lo;
@@ -1102,7 +1326,12 @@ int sk_converge_scan(sk_ctx *c, const sk_scan_args *a, int64_t *new_hi, double *
   LAUNCH_CHECK();
   c->commit_pending = false;
   CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  {
+    int rcc = comm_reduce_b(c, true, 0ull, 0);
+    if (rcc != SK_OK) return rcc;
+  }
   CK(cudaStreamSynchronize(c->stream));
+  comm_take_b(c);
   const long long top = c->h_scal->red.max_unconv;      // 0-based index of the highest unconverged target, or lo-1
   double r = 0.0;
   if (top >= c->lo) std::memcpy(&r, &c->h_scal->red.rbits, sizeof(double));

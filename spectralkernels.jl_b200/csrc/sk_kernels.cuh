@@ -676,6 +676,33 @@ __global__ void k_accept_add(sk_cplx *__restrict__ pan, const sk_cplx *__restric
   pan[j] = p;
 }
 
+// ---- scalars exchanged between the ranks of a target-sharded run (NCCL all-reduces on the stream) -------
+struct SkGlobalA {                 // after a sub-interval: MAX over ranks
+  unsigned long long maxbits;      // bit pattern of max |I2-I1|
+  unsigned long long nan1, nan2, nand;
+};
+struct SkGlobalB {                 // after a convergence scan
+  unsigned long long rbits;        // MAX: bit pattern of the stopping distance
+  long long n_lb;                  // SUM: targets each rank keeps active if the walk stopped at its own distance
+};
+__global__ void k_pack_global_a(const SkReduceOut *__restrict__ red, SkGlobalA *__restrict__ g, int idle) {
+  g->maxbits = idle ? 0ull : red->maxbits;
+  const unsigned int fl = idle ? 0u : red->flags;
+  g->nan1 = (fl & SK_FLAG_NAN1) ? 1ull : 0ull;
+  g->nan2 = (fl & SK_FLAG_NAN2) ? 1ull : 0ull;
+  g->nand = (fl & SK_FLAG_NAND) ? 1ull : 0ull;
+}
+__global__ void k_pack_global_b(SkGlobalB *__restrict__ g, unsigned long long rbits, long long n_lb) {
+  g->rbits = rbits;
+  g->n_lb = n_lb;
+}
+
+__global__ void k_pack_global_b_from_red(const SkReduceOut *__restrict__ red, long long lo, SkGlobalB *__restrict__ g) {
+  g->rbits = red->max_unconv >= lo ? red->rbits : 0ull;
+  const long long n = red->max_unconv - lo + 1;
+  g->n_lb = n > 0 ? n : 0;
+}
+
 // roll a rejected speculative commit back: res = backup (bit for bit)
 __global__ void k_restore(sk_cplx *__restrict__ res, const sk_cplx *__restrict__ backup, long long n) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -755,16 +782,19 @@ struct SkKeyBits {
   unsigned long long bits_or, bits_and;
   unsigned int bad;        // a distance was NaN / negative / infinite
   unsigned int overflow;   // a run was too long for the two-level sort
+  unsigned int unsorted;   // some x[j] <= x[j-1]: the input is not already strictly increasing
+  unsigned int _pad;
 };
 __global__ void __launch_bounds__(256)
 k_make_keys(const double *__restrict__ xs, long long n, unsigned long long *__restrict__ keys,
             unsigned int *__restrict__ idx, SkKeyBits *__restrict__ kb) {
   // grid-stride: a few thousand blocks, one pair of atomics per block (a single hot address serialises)
   unsigned long long k_or = 0ull, k_and = ~0ull;
-  unsigned int bad = 0;
+  unsigned int bad = 0, unsorted = 0;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
     double x = xs[j];
     if (!(x >= 0.0) || isinf(x)) { bad = 1; x = 0.0; }
+    if (j > 0 && !(x > xs[j - 1])) unsorted = 1;          // already sorted and unique? (src/adaptive.jl:113)
     if (x == 0.0) x = 0.0;
     const unsigned long long k = (unsigned long long)__double_as_longlong(x);
     keys[j] = k;
@@ -777,17 +807,19 @@ k_make_keys(const double *__restrict__ xs, long long n, unsigned long long *__re
     k_or |= __shfl_xor_sync(0xffffffffu, k_or, o);
     k_and &= __shfl_xor_sync(0xffffffffu, k_and, o);
     bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    unsorted |= __shfl_xor_sync(0xffffffffu, unsorted, o);
   }
   __shared__ unsigned long long s_or[8], s_and[8];
-  __shared__ unsigned int s_bad[8];
+  __shared__ unsigned int s_bad[8], s_uns[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) { s_or[wid] = k_or; s_and[wid] = k_and; s_bad[wid] = bad; }
+  if (lane == 0) { s_or[wid] = k_or; s_and[wid] = k_and; s_bad[wid] = bad; s_uns[wid] = unsorted; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) { k_or |= s_or[w]; k_and &= s_and[w]; bad |= s_bad[w]; }
+    for (int w = 1; w < 8; ++w) { k_or |= s_or[w]; k_and &= s_and[w]; bad |= s_bad[w]; unsorted |= s_uns[w]; }
     atomicOr(&kb->bits_or, k_or);
     atomicAnd(&kb->bits_and, k_and);
     if (bad) atomicOr(&kb->bad, 1u);
+    if (unsorted) atomicOr(&kb->unsorted, 1u);
   }
 }
 
@@ -861,6 +893,16 @@ __global__ void k_scatter_unique(const unsigned long long *__restrict__ keys, co
   const unsigned int u = uid_incl[j] - 1u;
   if (head[j] && (long long)u < n) uxs[u] = __longlong_as_double((long long)keys[j]);
   if ((long long)idx[j] < n) inv[idx[j]] = u;
+}
+
+// already sorted and unique input: the unique table is the input itself and the inverse map is the identity
+__global__ void k_identity_targets(const unsigned long long *__restrict__ keys, long long n, double *__restrict__ uxs,
+                                   unsigned int *__restrict__ inv, unsigned int *__restrict__ uid_incl) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uxs[j] = __longlong_as_double((long long)keys[j]);
+  inv[j] = (unsigned int)j;
+  if (j == n - 1) uid_incl[j] = (unsigned int)n;       // what k_target_summary reads
 }
 
 __global__ void k_target_summary(const double *__restrict__ uxs, const unsigned int *__restrict__ uid_incl, long long n,

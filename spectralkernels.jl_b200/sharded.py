@@ -54,3 +54,43 @@ class TorchComm:
         self._dist.all_gather_into_tensor(out, t, group=self._group)
         self.n_reductions += 1
         return out.view(self.world_size, t.numel()).cpu().tolist()
+
+
+class LibComm:
+    """The scalar reductions of a target-sharded run done INSIDE libsk_b200: NCCL all-reduces enqueued on the
+    context's stream right behind the kernel that produced the local value (sk_comm_init).  The per-sub-interval
+    and per-scan reductions then cost no extra host synchronisation; this object only serves the once-per-call
+    reductions (global distance range, counts) through sk_comm_allreduce.
+
+    `LibComm.from_torch(engine)` bootstraps the NCCL communicator through an initialised torch.distributed
+    group (rank 0 creates the unique id and broadcasts it)."""
+    fused = True
+
+    def __init__(self, engine, rank: int, world_size: int, uid: bytes):
+        self.engine, self.rank, self.world_size = engine, int(rank), int(world_size)
+        engine.comm_init(uid, rank, world_size)
+        self.n_reductions = 0
+
+    @classmethod
+    def from_torch(cls, engine, group=None):
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls(engine, rank, world, box[0])
+
+    def _r(self, vals, op):
+        self.n_reductions += 1
+        return self.engine.comm_allreduce(vals, op)
+
+    def max(self, vals):
+        return self._r(vals, 0)
+
+    def min(self, vals):
+        return self._r(vals, 1)
+
+    def sum(self, vals):
+        return self._r(vals, 2)
+
+    def close(self):
+        self.engine.comm_destroy()

@@ -18,15 +18,15 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import spectralkernels_jl_b200 as sk  # noqa: E402
-from spectralkernels_jl_b200.sharded import TorchComm  # noqa: E402
+from spectralkernels_jl_b200.sharded import LibComm, TorchComm  # noqa: E402
 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    comm = TorchComm(device=torch.device("cuda", local))
     ok = True
+    flavour = os.environ.get("SK_COMM", "lib")
     for name, S, gen, k0 in (
         ("matern_uniform", sk.Matern(1 / (np.pi / 2), 1.0, 1.5), lambda rng, n: rng.uniform(0, 1, n), 1.0),
         ("slow_decay_logspaced", sk.Matern(1.0, 0.5, 0.55), lambda rng, n: 10 ** rng.uniform(-4, 0, n), 5.9),
@@ -36,8 +36,11 @@ def main():
         if name == "slow_decay_logspaced":
             chunks[world - 1] = chunks[world - 1] * 1e-2          # the last rank runs out of active targets early
         cfg = sk.AdaptiveKernelConfig(S, device=local)
+        comm = LibComm.from_torch(cfg.engine) if flavour == "lib" else TorchComm(device=torch.device("cuda", local))
         tr = []
         v, e = sk.kernel_values(cfg, chunks[rank], k0=k0, comm=comm, trace=tr)
+        if flavour == "lib":
+            comm.close()
         # gather everything on rank 0 (padded to the longest chunk)
         m = max(c.size for c in chunks)
         buf = torch.zeros(2, m, dtype=torch.float64, device=f"cuda:{local}")
@@ -60,7 +63,7 @@ def main():
             same_t = all(k == key1 for k in keys)
             npan = sum(1 for t in tr1 if t["kind"] == "panel")
             print(f"[multi_gpu_check] {name}: world={world} values_bitwise={same_v} errs_bitwise={same_e} "
-                  f"traces_equal={same_t} panels={npan} reductions={comm.n_reductions} "
+                  f"traces_equal={same_t} panels={npan} comm={flavour} host_reductions={comm.n_reductions} "
                   f"max|dv|={np.max(np.abs(vs - v1)):.2e}", flush=True)
             ok = ok and same_v and same_e and same_t
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")

@@ -349,7 +349,8 @@ def test_sort_paths(sk):
     spread[100:200] = spread[0:100]                                    # exact duplicates
     clustered = 0.5 + rng.uniform(0, 1e-9, 3000)                       # one high word: > 128 per run -> fallback
     clustered[::7] = clustered[0]
-    for xs, two_level in ((spread, 1), (np.concatenate([spread, clustered]), 0)):
+    presorted = np.unique(spread)
+    for xs, two_level in ((spread, 1), (np.concatenate([spread, clustered]), 0), (presorted, 2)):
         info = cfg.engine.targets_set(xs)
         assert info.n_unique == np.unique(xs).size
         assert cfg.engine.stats()["sort_two_level"] == two_level
