@@ -268,10 +268,12 @@ SK_HD SkTargetCoord sk_target_coord(const SkGeom &G, double r) {
   const double x0 = (c0 - y_hi) - y_lo;          // in [-W/2, -W/2 + 1)
   SkTargetCoord t;
   t.s = 2.0 * (x0 + (0.5 * W - 0.5));
-  long long l0 = (long long)c0 + G.nf2 / 2;
-  if (l0 < 0) l0 = 0;
-  if (l0 > G.nf2 - W) l0 = G.nf2 - W;
-  t.l0 = l0;
+  // window start in 32-bit arithmetic (nf2 < 2^31); one unsigned min clamps both ends (a negative start
+  // wraps to a huge unsigned).  Targets inside the range the geometry was built for never hit the clamp.
+  const unsigned int hi_ok = (unsigned int)(G.nf2 - W);
+  unsigned int l0u = (unsigned int)((int)c0 + (int)(G.nf2 / 2));
+  l0u = l0u < hi_ok ? l0u : hi_ok;
+  t.l0 = (long long)l0u;
   t.yabs = fabs(y_hi);
   return t;
 }
