@@ -79,9 +79,11 @@ class ClockSampler:
         self.idx, self.rows, self.proc = gpu_index, [], None
 
     def start(self):
+        if self.idx < 0:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -233,7 +235,10 @@ def run(args):
     for _ in range(W - 1):
         step_resident()
     eng.set_timing(True)
-    sampler = ClockSampler(local_rank)
+    import gc
+    gc.collect()
+    gc.disable()                      # no collector pauses inside the timed regions (ranks wait for each other)
+    sampler = ClockSampler(local_rank if rank == 0 else -1)   # one sampler per job: nvidia-smi queries take a driver lock
     agg = {"units": 0, "interp_ms": 0.0, "source_ms": 0.0, "launches": 0, "subintervals": 0}
     barrier()
     sampler.start()

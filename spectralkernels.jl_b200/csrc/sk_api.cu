@@ -298,8 +298,10 @@ int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long lon
     return 0;
   }
   // cells the active targets span -> average targets per cell -> how many cells a block may hold
+  const int tpt = n >= 4000000 ? 8 : 4;
+  const int tpb = 256 * tpt;
   const double span = (c->r_hi - c->r_lo) * G.kap_hi + 1.0;
-  const double per_block = span * (double)SK_TPB / (double)n;
+  const double per_block = span * (double)tpb / (double)n;
   const int cmax = per_block <= 24.0 ? 32 : 96;
   const size_t smem = sizeof(double) * (size_t)(2 * (W / 2) * (SK_NC / 2) + (cmax + W) * 4 + cmax * 4 + cmax * SK_NC * 4);
   // function attributes are per device: remember per context (one context = one device)
@@ -312,7 +314,7 @@ int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long lon
     attr_set = true;
   }
 #define SK_LAUNCH_CELLS(SPECV, MINBV)                                                                                  \
-  k_interp_cells<W, SPECV, MINBV><<<nblk(n, SK_TPB), 256, smem, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, cmax, \
+  k_interp_cells<W, SPECV, MINBV><<<nblk(n, tpb), 256, smem, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, cmax, tpt, \
                                                                               c->stage.p + c->lo, spec, c->d_red)
   if (c->interp_mode == 2) {           // A/B variant: 4 resident blocks per SM (<= 64 registers)
     if (spec.on) SK_LAUNCH_CELLS(true, 4); else SK_LAUNCH_CELLS(false, 4);

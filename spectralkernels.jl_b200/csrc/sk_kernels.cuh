@@ -377,8 +377,10 @@ __device__ __forceinline__ void sk_cell_eval(const double *coef, const sk_cplx *
 template <int W, bool SPEC, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G, const double *__restrict__ xs,
-               long long n, const sk_cplx *__restrict__ grid, double cmul, int kernel_sin, int cmax,
+               long long n, const sk_cplx *__restrict__ grid, double cmul, int kernel_sin, int cmax, int tpt,
                sk_cplx *__restrict__ stage, const __grid_constant__ SkSpec spec, SkReduceOut *__restrict__ red) {
+  // tpt (4 or 8) targets per thread: 2048-target blocks amortise the per-cell work best; smaller launches use
+  // 1024-target blocks so that the grid still fills the 148 SMs several times over
   extern __shared__ __align__(16) double smem[];
   double *sE = smem;                                   // [W/2][SK_NC/2]
   double *sO = sE + (W / 2) * (SK_NC / 2);
@@ -386,8 +388,9 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
   double *sQ = sWin + (size_t)(cmax + W) * 4;           // [cmax][4]  deconvolution factor at the 4 Chebyshev nodes
   double *sCoef = sQ + (size_t)cmax * 4;                // [cmax][SK_NC][4]
   __shared__ sk_cplx sTab[65];                          // (cos, sin)(2 pi k / 64) for the post-phase
-  const long long j0 = (long long)blockIdx.x * SK_TPB;
-  const int cnt = (int)((n - j0) < (long long)SK_TPB ? (n - j0) : (long long)SK_TPB);
+  const int tpb = 256 * tpt;
+  const long long j0 = (long long)blockIdx.x * tpb;
+  const int cnt = (int)((n - j0) < (long long)tpb ? (n - j0) : (long long)tpb);
   const long long l_first = sk_target_coord<W>(G, xs[j0]).l0;
   const long long l_last = sk_target_coord<W>(G, xs[j0 + cnt - 1]).l0;
   const long long ncell_ll = l_last - l_first + 1;
@@ -428,7 +431,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     __syncthreads();
     // C: Horner per target
 #pragma unroll 1
-    for (int uo = 0; uo < SK_TPT / 4; ++uo) {
+    for (int uo = 0; uo < tpt / 4; ++uo) {
       // issue all global loads of the 4 targets first (distances and, when committing speculatively, the
       // old (ks, errs) pairs): their latency overlaps the arithmetic
       double rr[4];
@@ -469,7 +472,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     double *wQ = wWin + W * 4;                                       // [4] deconvolution nodes
     double *wCoef = wQ + 4;                                          // [SK_NC][4]
 #pragma unroll 1
-    for (int u = 0; u < SK_TPT; ++u) {
+    for (int u = 0; u < tpt; ++u) {
       const int t = threadIdx.x + u * 256;
       const bool have = t < cnt;
       const double r = have ? xs[j0 + t] : 0.0;
