@@ -96,7 +96,7 @@ int sk_plan_make_es(int w, SkEsPlan *out) {
     if (sk_plan_gauss_rule(ng, 0.0, xd.data(), wd.data()) != 0) return -2;
     for (int i = 0; i < ng; ++i) { gxl[i] = xd[i]; gwl[i] = wd[i]; }
   }
-  out->ximax = (double)(Q_PI * w / 4) * 1.0005;
+  out->ximax = (double)(Q_PI * w / 4) * 1.002;      // sigma >= 1.996 on both the mode and the target side
   const q128 ximax = out->ximax;
   auto phihat = [&](q128 xi) {
     q128 acc = 0;

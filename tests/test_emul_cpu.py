@@ -70,7 +70,7 @@ def test_type3_math_default_panels(emul):
         no1, buf1, no2, buf2 = so.updatequadbufs(cfg, cfg.f, a, b)
         for no, buf in ((no1, buf1), (no2, buf2)):
             f, G = _nufft(emul, no, buf, x)
-            assert G.D == 0.0 and G.nf2 == 262440
+            assert G.D == 0.0 and G.nf2 == 262144             # 2^18 (power of two preferred)
             assert np.max(np.abs(f - so.direct_cis(no, buf, x))) <= 5e-13 * np.sum(np.abs(buf))
 
 
