@@ -119,6 +119,7 @@ def oracle_cpu_run(n_sample: int, steps: int, warmup: int):
     with all host threads, on a bounded sample of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import sk_oracle as so
+    so.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     phi, rho, nu = workload_sdf_params()
     S = lambda w: phi * (rho ** 2 + w ** 2) ** (-nu - 0.5)
     cfg = so.OracleConfig(S)

@@ -44,6 +44,14 @@
 #define M_PI 3.14159265358979323846
 #endif
 
+void sko_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int sko_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -60,6 +60,8 @@ def lib():
         L.sko_nufft1d3.argtypes = [ctypes.c_int64, dp, dp, ctypes.c_int64, dp, dp, ctypes.c_double]
         L.sko_nufft1d3.restype = ctypes.c_int
         L.sko_num_threads.restype = ctypes.c_int
+        L.sko_set_num_threads.argtypes = [ctypes.c_int]
+        L.sko_set_num_threads.restype = None
         _lib = L
     return _lib
 
@@ -70,6 +72,11 @@ def _ptr(a: np.ndarray):
 
 def num_threads() -> int:
     return int(lib().sko_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants all host cores."""
+    lib().sko_set_num_threads(int(n))
 
 
 # --------------------------------------------------------------------------- #

@@ -300,7 +300,7 @@ int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long lon
   }
   // cells the active targets span -> average targets per cell -> how many cells a block may hold
   static const int tpt_env = getenv("SK_TPT") ? atoi(getenv("SK_TPT")) : 0;     // tuning knob (4, 8, 16)
-  const int tpt = (tpt_env == 4 || tpt_env == 8 || tpt_env == 16) ? tpt_env : (n >= 4000000 ? 8 : 4);
+  const int tpt = (tpt_env == 4 || tpt_env == 8 || tpt_env == 16) ? tpt_env : (n >= 8000000 ? 16 : (n >= 2000000 ? 8 : 4));
   const int tpb = 256 * tpt;
   const double span = (c->r_hi - c->r_lo) * G.kap_hi + 1.0;
   const double per_block = span * (double)tpb / (double)n;
