@@ -23,6 +23,7 @@
 #include "../../include/spectralkernels_b200.h"
 #include "sk_host_util.h"
 #include "sk_kernels.cuh"
+#include "sk_rules.cuh"
 
 namespace {
 
@@ -484,12 +485,48 @@ int rollback_speculation(sk_ctx *c) {
   return SK_OK;
 }
 
+// Rules are generated on the device (k_gauss_rules, double-double Newton) and kept for the life of the
+// context; the host long-double generator (sk_plan_gauss_rule) remains as the cross-check in the tests.
 int cached_gauss_rule(sk_ctx *c, int n, double p, std::vector<double> &no, std::vector<double> &wt) {
   auto key = std::make_pair(n, p);
   auto it = c->rule_cache.find(key);
   if (it == c->rule_cache.end()) {
-    std::vector<double> x(n), w(n);
-    if (sk_plan_gauss_rule(n, p, x.data(), w.data()) != 0) return -1;
+    std::vector<double> hA(2 * (size_t)n), hB(2 * (size_t)n), hC(2 * (size_t)n), x(n), w(n);
+    if (sk_plan_jacobi_coeffs(n, p, hA.data(), hB.data(), hC.data()) != 0) return -1;
+    double *dA = nullptr, *dNo = nullptr;
+    SkRuleJob *dJob = nullptr;
+    const size_t cb = sizeof(double) * 2 * (size_t)n;
+    bool ok = cudaMalloc((void **)&dA, 3 * cb) == cudaSuccess && cudaMalloc((void **)&dNo, sizeof(double) * 2 * (size_t)n) == cudaSuccess &&
+              cudaMalloc((void **)&dJob, sizeof(SkRuleJob)) == cudaSuccess;
+    if (ok) {
+      SkRuleJob J;
+      J.n = n;
+      J.p = p;
+      J.A = (const sk_dd *)dA;
+      J.B = (const sk_dd *)((char *)dA + cb);
+      J.C = (const sk_dd *)((char *)dA + 2 * cb);
+      J.no = dNo;
+      J.wt = dNo + n;
+      ok = cudaMemcpyAsync((void *)J.A, hA.data(), cb, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+           cudaMemcpyAsync((void *)J.B, hB.data(), cb, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+           cudaMemcpyAsync((void *)J.C, hC.data(), cb, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+           cudaMemcpyAsync(dJob, &J, sizeof(J), cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+      if (ok) {
+        dim3 grid((n + 63) / 64, 1);
+        k_gauss_rules<<<grid, 64, 0, c->stream>>>(dJob, 1);
+        c->stats.kernel_launches++;
+        ok = cudaGetLastError() == cudaSuccess &&
+             cudaMemcpyAsync(x.data(), J.no, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+             cudaMemcpyAsync(w.data(), J.wt, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+             cudaStreamSynchronize(c->stream) == cudaSuccess;
+      }
+    }
+    if (dA) cudaFree(dA);
+    if (dNo) cudaFree(dNo);
+    if (dJob) cudaFree(dJob);
+    if (!ok) return -2;
+    for (int i = 1; i < n; ++i)
+      if (!(x[i] > x[i - 1])) return -3;                 // Newton landed on a neighbouring zero
     it = c->rule_cache.emplace(key, std::make_pair(std::move(x), std::move(w))).first;
   }
   no = it->second.first;

@@ -22,3 +22,4 @@ struct SkEsPlan {
 // Host planner (sk_plan_host.cpp, compiled by g++ with libquadmath)
 int sk_plan_make_es(int w, SkEsPlan *out);
 int sk_plan_gauss_rule(int n, double p, double *no, double *wt);
+int sk_plan_jacobi_coeffs(int n, double p, double *A, double *B, double *C);   // (hi, lo) pairs, 2n doubles each

@@ -152,6 +152,27 @@ struct JacobiEval {
 };
 }  // namespace
 
+// recurrence coefficients of P_k^{(0,p)} as (hi, lo) double pairs for the device generator (sk_rules.cuh);
+// out arrays hold 2*n doubles each, entry k at [2k], [2k+1]; k = 0 is unused
+int sk_plan_jacobi_coeffs(int n, double p_, double *A, double *B, double *C) {
+  if (n < 1 || !(p_ > -1.0)) return -1;
+  const ld p = p_;
+  auto split = [](ld v, double *dst) {
+    const double hi = (double)v;
+    dst[0] = hi;
+    dst[1] = (double)(v - (ld)hi);
+  };
+  A[0] = A[1] = B[0] = B[1] = C[0] = C[1] = 0.0;
+  for (int k = 1; k < n; ++k) {
+    const ld kk = k, s = 2 * kk + p;
+    const ld den = 2 * (kk + 1) * (kk + p + 1) * s;
+    split((s + 1) * (s + 2) * s / den, A + 2 * k);
+    split(-(s + 1) * p * p / den, B + 2 * k);
+    split(2 * kk * (kk + p) * (s + 2) / den, C + 2 * k);
+  }
+  return 0;
+}
+
 int sk_plan_gauss_rule(int n, double p_, double *no, double *wt) {
   if (n < 1 || !(p_ > -1.0)) return -1;
   const ld p = p_;

@@ -3,6 +3,7 @@
 // plain loops, so that the index arithmetic of the CUDA kernels can be checked against the oracle on
 // a machine without a GPU.  It is not a product path: nothing in spectralkernels.jl_b200/ loads it.
 #include "sk_host_util.h"
+#include "sk_rules.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -136,6 +137,19 @@ void emul_gen_sources(int m, int k, double a, double b, double p, int origin_jac
 }
 
 int emul_gauss_rule(int n, double p, double *no, double *wt) { return sk_plan_gauss_rule(n, p, no, wt); }
+
+// the device rule generator (sk_rules.cuh: double-double Newton) in a plain loop
+int emul_gauss_rule_dd(int n, double p, double *no, double *wt) {
+  std::vector<double> A(2 * (size_t)n), B(2 * (size_t)n), C(2 * (size_t)n);
+  if (sk_plan_jacobi_coeffs(n, p, A.data(), B.data(), C.data()) != 0) return -1;
+  SkRuleJob J;
+  J.n = n; J.p = p;
+  J.A = (const sk_dd *)A.data(); J.B = (const sk_dd *)B.data(); J.C = (const sk_dd *)C.data();
+  J.no = no; J.wt = wt;
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int i = 0; i < n; ++i) sk_gauss_node(J, i);
+  return 0;
+}
 
 // max error of the lean sincos against libm over a sweep of |f| <= 1/2
 double emul_sincos_err(int n) {

@@ -157,6 +157,25 @@ def test_device_source_generator_matches_updatequadbufs(emul):
         assert np.max(np.abs(outs[3] / ref[3] - 1)) < 5e-15
 
 
+def test_device_rule_generator(emul):
+    """sk_rules.cuh (double-double Newton, the generator the device runs) against the oracle's long-double
+    rules and exact moments."""
+    L, _ = emul
+    L.emul_gauss_rule_dd.argtypes = [ctypes.c_int, ctypes.c_double, dp, dp]
+    for n, p in ((64, 0.0), (4096, 0.0), (8192, -0.5), (4096, 1.5), (8192, 0.5), (1, 0.0), (2, -0.9)):
+        no, wt = np.empty(n), np.empty(n)
+        assert L.emul_gauss_rule_dd(n, p, _ptr(no), _ptr(wt)) == 0
+        xo, wo = so.gauss_rule(n, p)
+        assert np.all(np.diff(no) > 0) if n > 1 else True
+        assert np.max(np.abs(no - xo)) <= 2.3e-16
+        assert np.max(np.abs(wt / wo - 1)) <= 2e-12      # the long-double oracle loses ~1e-12 in the weights next to x = +-1 (1 - x^2 cancels); double-double does not
+        for j in (0, 1, 5):
+            if j > 2 * n - 1:
+                continue                                   # an n-point rule is exact up to degree 2n - 1
+            exact = 2 ** (p + j + 1) / (p + j + 1)
+            assert abs((wt * (1 + no) ** j).sum() / exact - 1) < 2e-14
+
+
 def test_lean_sincos(emul):
     L, _ = emul
     L.emul_sincos_err.restype = ctypes.c_double

@@ -81,6 +81,22 @@ def test_nufft1d3_matches_cpu_nufft_midsize(sess):
     assert np.max(np.abs(f - g)) <= 5e-11 * np.sum(np.abs(buf2))
 
 
+def test_device_generated_rules(sk, sess):
+    """QuadRule (src/quadrature.jl:27-47) generated on the device (double-double Newton, sk_rules.cuh) against
+    the host long-double generator and exact moments."""
+    for m, p in ((4096, 0.0), (4096, -0.5), (256, 1.5)):
+        sess.rule_set(m, 4, p)
+        for which, n, pp in ((0, m, 0.0), (1, 2 * m, 0.0), (2, m, p), (3, 2 * m, p)):
+            no, wt = sess.rule_get(which)
+            xo, wo = sk.host_gauss_rule(n, pp)
+            assert np.all(np.diff(no) > 0)
+            assert np.max(np.abs(no - xo)) <= 2.3e-16
+            assert np.max(np.abs(wt / wo - 1)) <= 2e-12
+            for j in (0, 1, 9):
+                exact = 2 ** (pp + j + 1) / (pp + j + 1)
+                assert abs((wt * (1 + no) ** j).sum() / exact - 1) < 2e-14
+
+
 # ---- K1: updatequadbufs! on the device -------------------------------------------------------------------
 @pytest.mark.parametrize("alpha,a,b", [(0.0, 0.0, 32768.0), (0.5, 0.0, 32768.0), (0.5, 32768.0, 65536.0)])
 def test_device_sources_match_updatequadbufs(sk, sess, alpha, a, b):
