@@ -414,6 +414,42 @@ def test_matern_2d_bessel_branch(sk, golden, derivative):
     assert cfg.engine.stats()["n_fast"] == 0
 
 
+@pytest.mark.parametrize("kw", [
+    {"quadspec": (2048, 3)},                   # k not a power of two: range(a, b, length=k+1) edges
+    {"quadspec": (32, 128)},                   # largest supported k
+    {"quadspec": (1024, 1), "alpha": 0.3},     # a single sub-panel, Jacobi everywhere at the origin
+    {"tol": 1e-13},                            # tol < 1e-12 => quadspec (4096, 1), src/adaptive.jl:37-40
+    {"convergence_criteria": "tails"}, {"convergence_criteria": "panel"}, {"tail": -3.2},
+])
+def test_config_variants_vs_oracle(sk, kw):
+    """Less common AdaptiveKernelConfig settings (README.md:52-61): values and traces against the oracle."""
+    import warnings
+    parms = (1.3, 0.7, 1.1)
+    xs = np.concatenate([[0.0], 10 ** np.linspace(-3, 0.3, 300)])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cfg = sk.AdaptiveKernelConfig(sk.Matern(*parms), **kw)
+    ocfg = so.OracleConfig(lambda w: cf.matern_sdf(w, parms), **kw)
+    assert cfg.quadspec == ocfg.quadspec
+    k0 = so.compute_k0(so.OracleConfig(lambda w: cf.matern_sdf(w, parms), alpha=kw.get("alpha", 0.0)))
+    tg, to = [], []
+    vg, eg = sk.kernel_values(cfg, xs, k0=k0, trace=tg)
+    vo, eo = so.kernel_values(ocfg, xs, k0=k0, trace=to)
+    assert _trace_key(tg) == _trace_key(to)
+    assert np.max(np.abs(vg - vo)) <= 1e-11 * abs(k0)
+    assert np.allclose(eg[1:], eo[1:], rtol=1e-6, atol=1e-11 * abs(k0)) and np.isnan(eg[0])
+
+
+def test_nufft_eps_override(sk):
+    """`nufft_eps` (optional keyword; the reference hard-wires 1e-15, src/utils.jl:10): a looser transform still
+    meets tol = 1e-6 and uses a narrower kernel."""
+    xs = 10 ** np.linspace(-4, 0, 2000)
+    cfg = sk.AdaptiveKernelConfig(sk.Matern(1.0, 1.0, 1.5), tol=1e-6, nufft_eps=1e-9)
+    v, _ = sk.kernel_values(cfg, xs, k0=np.pi / 2)
+    err = np.max(np.abs(v - cf.readme_cov(xs))) / (np.pi / 2)
+    assert 1e-13 < err < 1e-6
+
+
 def test_errors(sk):
     cfg = sk.AdaptiveKernelConfig(sk.Matern())
     with pytest.raises(sk.SkError):
