@@ -79,7 +79,50 @@ def config4():
             "max_err_dphi": float(np.max(np.abs(d[0] - true * (np.pi / 2))))}
 
 
+def config3_dim2():
+    """config 3 (ii): the same 49 995 000 pairwise distances with dim = 2 (J_0 kernel, p = +0.5, c = 2 pi,
+    src/adaptive.jl:42-43): the O(N) nonuniform Hankel transform."""
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0, 1, (10_000, 2))
+    parms = (1.0, 1.0, 1.5)
+    cfg = sk.AdaptiveKernelConfig(sk.Matern(*parms, d=2), alpha=0.5, dim=2)
+    k0 = sk.compute_k0(cfg)
+    n = pts.shape[0] * (pts.shape[0] - 1) // 2
+    host_v, host_e = sk.PinnedArray(n), sk.PinnedArray(n)
+    tr = []
+    cfg.engine.set_timing(True)
+    dt, _ = timed(lambda: sk.kernel_values(cfg, None, k0=k0, points=pts, out_vals=host_v.array, out_errs=host_e.array,
+                                           trace=tr), warm=1, reps=2)
+    st = cfg.engine.stats()
+    return {"config": "3-dim2", "workload": "singular Matern alpha=0.5, dim=2 (J_0 kernel), 49 995 000 pairwise distances of "
+                                            "1e4 2-D points, lags computed on device, values+errors copied back",
+            "ms": 1e3 * dt, "evals_per_s": n / dt, "n": n, "units": st["units"], "subintervals": st["n_subintervals"],
+            "n_hankel": st["n_hankel"], "interp_ms": st["interp_ms"], "source_ms": st["source_ms"],
+            "panels": [(t["a"], t["b"], t["hi_before"], t["hi_after"]) for t in tr if t["kind"] == "panel"][-8:],
+            "finite": bool(np.all(np.isfinite(host_v.array)))}
+
+
+def config2_dim2():
+    """1e7 uniform lags, Matern nu = 1.5 in 2-D (J_0 kernel): closed form available."""
+    from scipy import special
+    rng = np.random.default_rng(0)
+    xs = rng.uniform(0, 1, 10_000_000)
+    parms = (1.0, 1.0, 1.5)
+    cfg = sk.AdaptiveKernelConfig(sk.Matern(*parms, d=2), dim=2)
+    k0 = float(np.pi * parms[0] / (2 ** 0.5 * special.gamma(2.5)) * 2 ** 0.5 * special.gamma(1.5))
+    host_v, host_e = sk.PinnedArray(xs.size), sk.PinnedArray(xs.size)
+    cfg.engine.set_timing(True)
+    dt, _ = timed(lambda: sk.kernel_values(cfg, xs, k0=k0, out_vals=host_v.array, out_errs=host_e.array), warm=1, reps=3)
+    st = cfg.engine.stats()
+    arg = 2 * np.pi * xs
+    true = np.pi * parms[0] / (2 ** 0.5 * special.gamma(2.5)) * special.kv(1.5, arg) * arg ** 1.5
+    return {"config": "2-dim2", "workload": "Matern nu=1.5 in 2-D (J_0 kernel), 1e7 uniform lags, end to end",
+            "ms": 1e3 * dt, "evals_per_s": xs.size / dt, "units": st["units"], "subintervals": st["n_subintervals"],
+            "n_hankel": st["n_hankel"], "interp_ms": st["interp_ms"], "source_ms": st["source_ms"],
+            "max_err_over_k0": float(np.max(np.abs(host_v.array - true)) / k0)}
+
+
 if __name__ == "__main__":
     which = [int(a) for a in sys.argv[1:]] or [1, 4, 3]
     for c in which:
-        print(json.dumps({1: config1, 3: config3, 4: config4}[c]()), flush=True)
+        print(json.dumps({1: config1, 3: config3, 4: config4, 32: config3_dim2, 22: config2_dim2}[c]()), flush=True)

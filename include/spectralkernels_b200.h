@@ -111,6 +111,7 @@ typedef struct sk_stats {
   double source_ms;         /* device time in node/strength/spread/FFT since sk_run_begin      */
   int32_t timing_enabled;
   int32_t sort_two_level;   /* last sk_targets_set: 2 = input was already sorted and unique (no sort), 1 = 4-pass + run-rank sort, 0 = full 8-pass sort */
+  int64_t n_hankel;         /* sub-intervals that took the O(N) nonuniform Hankel transform (dim >= 2) */
 } sk_stats;
 
 /* ---- library --------------------------------------------------------------------------------- */
@@ -125,6 +126,11 @@ int sk_ctx_set_nufft_eps(sk_ctx *ctx, double eps);        /* default 1e-15, as h
 /* interpolation kernel: 0 (default) = cell polynomials in shared memory (k_interp_cells); 1 = per-target
  * exp-of-semicircle taps, the textbook evaluation (k_interp_session), kept for A/B measurements */
 int sk_ctx_set_interp_mode(sk_ctx *ctx, int mode);
+/* dim >= 2 (SK_KERNEL_BESSEL), replaces FastHankelTransform.jl's nufht (src/quadrature.jl:139-143):
+ * 0 (default) = O(N) nonuniform Hankel transform when more than ~4096 targets are active, the reference's
+ * direct Bessel summation (src/quadrature.jl:145-160) below that; 1 = always the direct summation;
+ * 2 = always the O(N) transform (orders 0..3) */
+int sk_ctx_set_hankel_mode(sk_ctx *ctx, int mode);
 int sk_ctx_synchronize(sk_ctx *ctx);
 /* the CUDA stream of the context as an opaque handle (cudaStream_t), for event timing by the caller */
 int sk_ctx_stream(sk_ctx *ctx, void **stream_out);

@@ -48,7 +48,7 @@ class Stats(ctypes.Structure):
     _fields_ = [("n_subintervals", c_int64), ("n_accepted", c_int64), ("n_panels", c_int64), ("units", c_int64),
                 ("n_fast", c_int64), ("n_direct", c_int64), ("kernel_launches", c_int64), ("last_nf", c_int64),
                 ("last_nf2", c_int64), ("n_speculated", c_int64), ("n_spec_rollbacks", c_int64), ("interp_ms", c_double), ("source_ms", c_double),
-                ("timing_enabled", c_int32), ("sort_two_level", c_int32)]
+                ("timing_enabled", c_int32), ("sort_two_level", c_int32), ("n_hankel", c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
@@ -66,6 +66,7 @@ SIGNATURES = {
     "sk_ctx_set_timing": (c_int, [c_void_p, c_int]),
     "sk_ctx_set_nufft_eps": (c_int, [c_void_p, c_double]),
     "sk_ctx_set_interp_mode": (c_int, [c_void_p, c_int]),
+    "sk_ctx_set_hankel_mode": (c_int, [c_void_p, c_int]),
     "sk_ctx_synchronize": (c_int, [c_void_p]),
     "sk_ctx_stream": (c_int, [c_void_p, POINTER(c_void_p)]),
     "sk_timer_begin": (c_int, [c_void_p]),
@@ -245,6 +246,10 @@ class Session:
         mx, r, n = c_double(), c_double(), c_int64()
         self._ck(self._L.sk_comm_last(self._h, byref(mx), byref(r), byref(n)))
         return mx.value, r.value, n.value
+
+    def set_hankel_mode(self, mode: int):
+        """dim >= 2: 0 auto, 1 always the direct Bessel summation, 2 always the O(N) nonuniform Hankel transform."""
+        self._ck(self._L.sk_ctx_set_hankel_mode(self._h, int(mode)))
 
     def set_interp_mode(self, mode: int):
         self._ck(self._L.sk_ctx_set_interp_mode(self._h, int(mode)))

@@ -23,6 +23,7 @@
 #include "../../include/spectralkernels_b200.h"
 #include "sk_host_util.h"
 #include "sk_kernels.cuh"
+#include "sk_hankel.cuh"
 #include "sk_rules.cuh"
 
 namespace {
@@ -90,6 +91,7 @@ struct HostScalars {          // pinned mirror of the device scalars
   SkGlobalB gb;
   double hv[8];               // generic host-value collectives
   double r[2];
+  SkHankelGroup grp[SK_HK_NGRP];   // transform groups of the current Hankel sub-interval
 };
 
 }  // namespace
@@ -143,6 +145,13 @@ struct sk_ctx {
   long long scan_hi = -1;                    // 1-based index / distance returned by the last scan
   double scan_r = 0;
   int interp_mode = 0;                       // 0: cell polynomials (default), 1: per-target taps
+  // nonuniform Hankel transform (dim >= 2): 0 auto, 1 always the direct Bessel summation, 2 always the O(N) scheme
+  int hankel_mode = 0;
+  bool hk_tab_ready = false;
+  DevBuf<double> hk_tab, hk_vals, hk_cheb, hk_lam1, hk_lam2;
+  DevBuf<long long> hk_lev;
+  DevBuf<SkHankelGroup> hk_groups;
+  DevBuf<sk_cplx> hk_grid;
   bool smem_attr_set[SK_WMAX + 1] = {false};
   // target-sharded multi-GPU: scalar NCCL all-reduces on the context's stream
   ncclComm_t comm = nullptr;
@@ -373,6 +382,75 @@ int run_source_side(sk_ctx *c, const SkGeom &G, int nrule, long long M1, const d
   return SK_OK;
 }
 
+// O(N) nonuniform Hankel transform of the sub-interval's sources at the active targets (sk_hankel.h), staged
+// like the other branches.  Returns SK_ERR_UNSUPPORTED (without touching the staging buffers) when the dyadic
+// scheme does not apply; the caller then takes the direct Bessel summation.
+int hankel_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, long long n_act, long long M1, long long M2) {
+  SkHankelPlan H;
+  SkHankelGroup *hg = c->h_scal->grp;
+  const long long total = sk_hk_make_plan(c->plan, o->nu, a, b, c->r_lo, c->r_hi, &H, hg);
+  if (total < 0 || c->plan.w != 16) return SK_ERR_UNSUPPORTED;
+  if (!c->hk_tab_ready) {
+    std::vector<double> tab(SK_HK_TAB_SIZE);
+    if (sk_plan_bessel_table(SK_HK_NUMAX, SK_HK_TAB_INT, SK_HK_TAB_NC, tab.data()) != 0) return fail(c, SK_ERR_ARG, "Bessel table");
+    CK(c->hk_tab.ensure(SK_HK_TAB_SIZE));
+    CK(cudaMemcpyAsync(c->hk_tab.p, tab.data(), sizeof(double) * SK_HK_TAB_SIZE, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(c->hk_vals.ensure(2 * SK_HK_NLEV * SK_HK_NCH));
+    CK(c->hk_cheb.ensure(2 * SK_HK_NLEV * SK_HK_NCH));
+    CK(c->hk_lev.ensure(2 * (SK_HK_NLEV + 1)));
+    CK(c->hk_groups.ensure(SK_HK_NGRP));
+    c->hk_tab_ready = true;
+  }
+  CK(c->hk_grid.ensure((size_t)std::max<long long>(total, 1)));
+  CK(c->pos_hi1.ensure(M1)); CK(c->pos_lo1.ensure(M1)); CK(c->cs1.ensure(M1)); CK(c->hk_lam1.ensure(M1));
+  CK(c->pos_hi2.ensure(M2)); CK(c->pos_lo2.ensure(M2)); CK(c->cs2.ensure(M2)); CK(c->hk_lam2.ensure(M2));
+  if (H.ngroups > 0)
+    CK(cudaMemcpyAsync(c->hk_groups.p, hg, sizeof(SkHankelGroup) * H.ngroups, cudaMemcpyHostToDevice, c->stream));
+  // local part: level boundaries, node sums, Chebyshev coefficients
+  k_hankel_levels<<<nblk(M1 + M2, 256), 256, 0, c->stream>>>(H.wT, c->no1.p, M1, c->no2.p, M2, c->hk_lev.p);
+  LAUNCH_CHECK();
+  {
+    dim3 grid(SK_HK_NCH, H.q_hi - H.q_lo + 1, 2);
+    k_hankel_fit<<<grid, 256, 0, c->stream>>>(H, c->hk_tab.p, c->no1.p, c->buf1.p, c->no2.p, c->buf2.p, c->hk_lev.p, c->hk_vals.p);
+    LAUNCH_CHECK();
+    k_hankel_cheb<<<nblk(2 * (H.q_hi - H.q_lo + 1) * SK_HK_NCH, 128), 128, 0, c->stream>>>(H, c->hk_vals.p, c->hk_cheb.p);
+    LAUNCH_CHECK();
+  }
+  // asymptotic part: one batched transform (K terms x 2 rules) per group
+  SkHkSrc S;
+  S.no[0] = c->no1.p; S.no[1] = c->no2.p; S.buf[0] = c->buf1.p; S.buf[1] = c->buf2.p;
+  S.pos_hi[0] = c->pos_hi1.p; S.pos_hi[1] = c->pos_hi2.p; S.pos_lo[0] = c->pos_lo1.p; S.pos_lo[1] = c->pos_lo2.p;
+  S.cs[0] = c->cs1.p; S.cs[1] = c->cs2.p; S.lam[0] = c->hk_lam1.p; S.lam[1] = c->hk_lam2.p;
+  S.M[0] = M1; S.M[1] = M2;
+  if (total > 0) CK(cudaMemsetAsync(c->hk_grid.p, 0, sizeof(sk_cplx) * (size_t)total, c->stream));   // zero padding
+  for (int gi = 0; gi < H.ngroups; ++gi) {
+    const SkGeom &G = hg[gi].G;
+    k_hankel_prep<<<nblk(M1 + M2, 256), 256, 0, c->stream>>>(c->hk_groups.p, gi, H.wT, S);
+    LAUNCH_CHECK();
+    dim3 grid(nblk(G.nf, SK_SPREAD_CELLS), 2);
+    k_spread_hankel<16><<<grid, 256, 0, c->stream>>>(c->plan, c->hk_groups.p, gi, H, S, c->hk_grid.p);
+    LAUNCH_CHECK();
+    cufftHandle h;
+    int rc = get_fft_plan(c, G.nf2, 2 * SK_HK_K, &h);
+    if (rc != SK_OK) return rc;
+    cufftDoubleComplex *gp = (cufftDoubleComplex *)(c->hk_grid.p + hg[gi].grid_off);
+    cufftResult fr = cufftExecZ2Z(h, gp, gp, CUFFT_INVERSE);
+    if (fr != CUFFT_SUCCESS) return fail(c, SK_ERR_CUFFT, "cufftExecZ2Z failed: %d", (int)fr);
+    c->stats.kernel_launches++;
+    c->stats.last_nf = G.nf;
+    c->stats.last_nf2 = G.nf2;
+  }
+  if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
+  k_hankel_interp<16><<<nblk(n_act, 256), 256, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p, c->hk_cheb.p,
+                                                               c->uxs.p + c->lo, n_act, o->cmul, o->xdiv_pow,
+                                                               c->stage.p + c->lo, c->d_red);
+  LAUNCH_CHECK();
+  if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
+  c->stats.n_hankel++;
+  return SK_OK;
+}
+
 // transform + stage for the sub-interval whose sources are in no1/buf1/no2/buf2
 int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, double *max_abs_diff) {
   const long long n_act = c->hi - c->lo;
@@ -406,6 +484,16 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
   c->h_scal->red = init;
   CK(cudaMemcpyAsync(c->d_red, &c->h_scal->red, sizeof(init), cudaMemcpyHostToDevice, c->stream));
   if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+  // dim >= 2: the reference calls nufht whenever its NUFFT cutoff holds (src/quadrature.jl:139-143); here the
+  // O(N) scheme is taken when it is cheaper than the direct Bessel summation (more than ~4096 active targets)
+  int hk_rc = SK_ERR_UNSUPPORTED;
+  bool hk_timed = false;
+  if (bessel && c->hankel_mode != 1 && n_cut > 1 && c->r_lo > 0.0 &&
+      (c->hankel_mode == 2 || (M2 * n_cut > (1LL << 29)))) {
+    hk_rc = hankel_stage(c, a, b, o, n_act, M1, M2);
+    if (hk_rc != SK_OK && hk_rc != SK_ERR_UNSUPPORTED) return hk_rc;
+    hk_timed = hk_rc == SK_OK;
+  }
   if (fast) {
     SkGeom G;
     if (sk_make_geom(c->plan, a, b, c->r_lo, c->r_hi, &G) != 0)
@@ -419,6 +507,8 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
     LAUNCH_CHECK();
     if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
     c->stats.n_fast++;
+  } else if (bessel && hk_rc == SK_OK) {
+    // staged by hankel_stage above
   } else {
     if (n_act > 2000000000LL) return fail(c, SK_ERR_ARG, "too many targets for the direct branch");
     CK(c->dsum.ensure((size_t)n_act * 2));
@@ -439,7 +529,7 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
     if (rcc != SK_OK) return rcc;
   }
   CK(cudaStreamSynchronize(c->stream));
-  if (c->timing && fast) {
+  if (c->timing && (fast || hk_timed)) {
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
     c->stats.source_ms += ms;
@@ -719,6 +809,8 @@ int sk_ctx_destroy(sk_ctx *c) {
   c->cs1.release(); c->cs2.release(); c->fft.release(); c->dsum.release();
   c->res.release(); c->pan.release(); c->stage.release();
   c->fftB.release(); c->dsumB.release(); c->bufb1.release(); c->bufb2.release();
+  c->hk_tab.release(); c->hk_vals.release(); c->hk_cheb.release(); c->hk_lam1.release(); c->hk_lam2.release();
+  c->hk_lev.release(); c->hk_groups.release(); c->hk_grid.release();
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   if (c->d_ga) cudaFree(c->d_ga);
   if (c->d_gb) cudaFree(c->d_gb);
@@ -1445,6 +1537,12 @@ int sk_results_get(sk_ctx *c, double *vals, double *errs) {
 int sk_ctx_set_interp_mode(sk_ctx *c, int mode) {
   if (!c || mode < 0 || mode > 2) return SK_ERR_ARG;
   c->interp_mode = mode;
+  return SK_OK;
+}
+
+int sk_ctx_set_hankel_mode(sk_ctx *c, int mode) {
+  if (!c || mode < 0 || mode > 2) return SK_ERR_ARG;
+  c->hankel_mode = mode;
   return SK_OK;
 }
 

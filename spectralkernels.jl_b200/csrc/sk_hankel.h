@@ -1,0 +1,224 @@
+// sk_hankel.h -- per-element arithmetic of the O(N) nonuniform Hankel transform
+//
+//     g_j = sum_k c_k J_nu(2 pi w_k r_j)                      (src/quadrature.jl:137-161, `nufht`)
+//
+// which the reference takes from FastHankelTransform.jl for dim >= 2.  Written from scratch on top of
+// the type-3 NUFFT of sk_math.h; host/device inline functions, so the CUDA kernels of sk_hankel.cuh are
+// thin wrappers and tests/emul/ can run the same arithmetic with g++.
+//
+// Scheme.  With ZL = 32 the Hankel expansion
+//     J_nu(z) = sqrt(2/(pi z)) Re[ e^{i(z - nu pi/2 - pi/4)} sum_{n<K} a_n(nu) (i/z)^n ]   (DLMF 10.17.3)
+// with K = 12 terms is exact to ~1e-15 for z >= ZL.  The (frequency, distance) plane is cut dyadically:
+//     frequency levels   L_0 = [0, wT),  L_q = [wT 2^(q-1), wT 2^q)          wT = ZL / (2 pi r_hi)
+//     distance octaves   O_t = (r_hi 2^-(t+1), r_hi 2^-t]                     t = 0, 1, ...
+// For a target in octave t every source of level >= t+2 has z >= ZL: that suffix of the (ascending) source
+// list is summed with K type-3 NUFFTs (one per term: strengths c_k a_n (w_ref/w_k)^(n+1/2), the target
+// applies (2 pi w_ref r)^(-n) by Horner in i/z_ref), all K terms and both quadrature rules in one batched
+// grid.  Levels q <= t+1 have z < 2 ZL on the whole of [0, R_q], R_q = r_hi 2^(1-q): there the level's
+// partial sum is a band-limited function of r and is replaced by its Chebyshev interpolant of SK_HK_NCH
+// terms on [0, R_q], built from direct sums at the Chebyshev nodes (J_nu from a piecewise-polynomial table on
+// [0, 64] fitted in quad precision).  Nothing is evaluated per (source, target) pair: the work per target is
+// K * 4 * w FMAs (interpolation) plus ~2-3 Clenshaw recurrences.
+// Octaves t with t+2 <= level(a) see the whole sub-interval [a, b] asymptotically and share one transform.
+#pragma once
+#include "sk_math.h"
+
+#define SK_HK_ZL 32.0
+#define SK_HK_K 12           // terms of the Hankel expansion
+#define SK_HK_NCH 72         // Chebyshev terms per level (z < 2 ZL = 64 needs ~64/2 + 26)
+#define SK_HK_NLEV 48        // dyadic frequency levels
+#define SK_HK_NGRP 48        // transforms per sub-interval
+#define SK_HK_NUMAX 3        // tabulated Bessel orders 0..3 (dim <= 6, or dim <= 4 with derivatives)
+#define SK_HK_TAB_INT 32     // table intervals [2i, 2i+2]
+#define SK_HK_TAB_NC 16      // monomial coefficients per interval, in t = z - (2i+1)
+#define SK_HK_TAB_SIZE ((SK_HK_NUMAX + 1) * SK_HK_TAB_INT * SK_HK_TAB_NC)
+
+struct SkHankelGroup {       // one batched transform: a suffix of the sources against a band of targets
+  SkGeom G;
+  double w_ref;              // strengths carry (w_ref / w)^(n + 1/2), targets (2 pi w_ref r)^(-n - 1/2)
+  int q_cut;                 // sources of level >= q_cut belong to the group
+  int _pad;
+  long long grid_off;        // offset (in sk_cplx) of the group's grids; layout [nf2][K][2 rules]
+};
+
+struct SkHankelPlan {
+  int nu;
+  int q_lo, q_hi;            // levels that can hold sources of [a, b]
+  int t_full;                // octaves t <= t_full share group 0 (all of [a, b] is asymptotic); -1: none
+  int t_last;                // octaves t > t_last have no asymptotic part
+  int ngroups;
+  double wT;                 // ZL / (2 pi r_hi)
+  double r_hi;               // largest active distance (global over the ranks of a sharded run)
+  double cphi, sphi;         // cos, sin of nu pi/2 + pi/4
+  double ratio[SK_HK_K];     // a_{n+1}(nu) / a_n(nu) = (4 nu^2 - (2n+1)^2) / (8 (n+1))
+};
+
+// ---- J_nu(z), 0 <= z <= 64, from the table ----------------------------------------------------------
+SK_HD double sk_bessel_tab(const double *tab, int nu, double z) {
+  int i = (int)(0.5 * z);
+  i = i < 0 ? 0 : (i > SK_HK_TAB_INT - 1 ? SK_HK_TAB_INT - 1 : i);
+  const double t = z - (double)(2 * i + 1);
+  const double *c = tab + ((size_t)nu * SK_HK_TAB_INT + i) * SK_HK_TAB_NC;
+  double v = c[SK_HK_TAB_NC - 1];
+#pragma unroll
+  for (int q = SK_HK_TAB_NC - 2; q >= 0; --q) v = sk_fma(v, t, c[q]);
+  return v;
+}
+
+// ---- dyadic cuts (exact comparisons against power-of-two multiples: the same answer on host and device) --
+// level of a frequency: the number of boundaries wT 2^(q-1), q >= 1, that are <= w
+SK_HD int sk_hk_level(double wT, double w) {
+  if (!(w >= wT)) return 0;
+  const int e = ilogb(w) - ilogb(wT);                 // w / wT in (2^(e-1), 2^(e+1))
+  const int fl = (w >= ldexp(wT, e)) ? e : e - 1;     // floor(log2(w / wT))
+  const int q = fl + 1;
+  return q > SK_HK_NLEV - 1 ? SK_HK_NLEV - 1 : q;
+}
+// octave of a distance: t >= 0 with r in (r_hi 2^-(t+1), r_hi 2^-t]; r >= r_hi gives 0
+SK_HD int sk_hk_octave(double r_hi, double r) {
+  if (!(r < r_hi)) return 0;
+  if (!(r > 0.0)) return 4096;
+  const int e = ilogb(r_hi) - ilogb(r);               // r_hi / r in (2^(e-1), 2^(e+1))
+  return (r <= ldexp(r_hi, -e)) ? e : e - 1;          // floor(log2(r_hi / r))
+}
+SK_HD int sk_hk_group_of_octave(const SkHankelPlan &H, int t) {
+  if (t > H.t_last) return -1;
+  if (t <= H.t_full) return 0;
+  return (t - H.t_full - 1) + (H.t_full >= 0 ? 1 : 0);
+}
+// right end of the interval on which level q is expanded locally
+SK_HD double sk_hk_level_radius(double r_hi, int q) { return q >= 1 ? ldexp(r_hi, 1 - q) : r_hi; }
+
+// ---- local part: Chebyshev interpolants of the levels' partial sums ------------------------------------
+SK_HD double sk_hk_cheb_node(int i) {   // first-kind nodes, descending
+  double s, c;
+  sk_sincospi(((double)i + 0.5) / (double)SK_HK_NCH, &s, &c);
+  return c;
+}
+// one term of the direct sum at a node: c_k J_nu(2 pi w_k rho)
+SK_HD double sk_hk_fit_term(const double *tab, int nu, double no, double buf, double rho) {
+  return sk_mul(buf, sk_bessel_tab(tab, nu, sk_mul(sk_mul(6.283185307179586, no), rho)));
+}
+// coefficient m of the interpolant from the NCH node values
+SK_HD double sk_hk_cheb_coef(const double *vals, int m) {
+  double acc = 0.0;
+  for (int i = 0; i < SK_HK_NCH; ++i) {
+    const int k = (m * (2 * i + 1)) % (4 * SK_HK_NCH);          // cos(pi k / (2 NCH)), exact reduction
+    double s, c;
+    sk_sincospi((double)k / (double)(2 * SK_HK_NCH), &s, &c);
+    acc = sk_fma(vals[i], c, acc);
+  }
+  return acc * (m == 0 ? 1.0 : 2.0) / (double)SK_HK_NCH;
+}
+// sum over the local levels of a target in octave t; cheb layout [2 rules][SK_HK_NLEV][SK_HK_NCH]
+SK_HD void sk_hk_local(const SkHankelPlan &H, const double *cheb, double r, int t, double *out) {
+  out[0] = out[1] = 0.0;
+  const int qe = (t + 1 < H.q_hi) ? t + 1 : H.q_hi;
+  for (int q = H.q_lo; q <= qe; ++q) {
+    const double R = sk_hk_level_radius(H.r_hi, q);
+    const double x2 = 2.0 * sk_fma(r, 2.0 / R, -1.0);             // 2x, x in [-1, 1]
+    const double *c0 = cheb + (size_t)q * SK_HK_NCH;
+    const double *c1 = c0 + (size_t)SK_HK_NLEV * SK_HK_NCH;
+    double b1 = 0.0, b2 = 0.0, d1 = 0.0, d2 = 0.0;
+    for (int j = SK_HK_NCH - 1; j >= 1; --j) {
+      const double b0 = sk_fma(x2, b1, c0[j] - b2);
+      const double d0 = sk_fma(x2, d1, c1[j] - d2);
+      b2 = b1; b1 = b0;
+      d2 = d1; d1 = d0;
+    }
+    out[0] += sk_fma(0.5 * x2, b1, c0[0] - b2);
+    out[1] += sk_fma(0.5 * x2, d1, c1[0] - d2);
+  }
+}
+
+// ---- asymptotic part ---------------------------------------------------------------------------------------
+// position on the group's spread grid, term-0 strength c_k (w_ref/w_k)^(1/2) (pre-phased), and the ratio
+// lam = w_ref / w_k that advances the strength from one term to the next
+SK_HD void sk_hk_source_prep(const SkHankelGroup &g, double wT, double no, double buf, double *pos_hi, double *pos_lo,
+                             sk_cplx *cs, double *lam) {
+  const bool in = sk_hk_level(wT, no) >= g.q_cut && no > 0.0;
+  const double l = in ? g.w_ref / no : 0.0;
+  sk_source_prep(g.G, no, in ? sk_mul(buf, sqrt(l)) : 0.0, 0.0, pos_hi, pos_lo, &cs->x, &cs->y);
+  *lam = l;
+}
+
+// spread + mode deconvolution + zero-pad for all K terms of one rule: FFT-input element j (emulation
+// twin of k_spread_hankel; exp-of-semicircle evaluated directly instead of through the tap polynomials)
+SK_HD void sk_hk_spread_mode(const SkEsPlan &P, const SkHankelPlan &H, const SkGeom &G, long long j, const double *pos_hi,
+                             const double *pos_lo, const sk_cplx *cs, const double *lam, long long M, sk_cplx *out /*[K]*/) {
+  for (int n = 0; n < SK_HK_K; ++n) out[n].x = out[n].y = 0.0;
+  const long long nm = (j < G.nf2 / 2) ? j : j - G.nf2;
+  if (nm < -(G.nf / 2) || nm >= G.nf / 2) return;
+  const double ctr = (double)nm, half = 0.5 * P.w;
+  long long a = 0, b = M;
+  while (a < b) {
+    const long long mid = (a + b) >> 1;
+    if (pos_hi[mid] < ctr - half - 1e-6) a = mid + 1; else b = mid;
+  }
+  for (long long k = a; k < M && pos_hi[k] <= ctr + half + 1e-6; ++k) {
+    const double z = ((ctr - pos_hi[k]) - pos_lo[k]) / half;
+    const double wgt = sk_es_direct(z, P.beta);
+    double cx = wgt * cs[k].x, cy = wgt * cs[k].y;
+    for (int n = 0; n < SK_HK_K; ++n) {
+      out[n].x += cx;
+      out[n].y += cy;
+      const double f = lam[k] * H.ratio[n];
+      cx *= f;
+      cy *= f;
+    }
+  }
+  double q = sk_deconv(P, G.t_cell * fabs(ctr));
+  if (nm & 1) q = -q;
+  for (int n = 0; n < SK_HK_K; ++n) { out[n].x *= q; out[n].y *= q; }
+}
+
+// interpolate the K x 2 grids of a group at distance r and sum the expansion: out[rule]
+template <int W>
+SK_HD void sk_hk_interp_point(const SkEsPlan &P, const SkHankelPlan &H, const SkHankelGroup &g, const sk_cplx *grid,
+                              double r, double *out) {
+  const SkTargetCoord t = sk_target_coord<W>(g.G, r);
+  double taps[W];
+  sk_es_taps<W>(P, t.s, taps);
+  const double zref = sk_mul(sk_mul(6.283185307179586, g.w_ref), r);
+  const double iz = 1.0 / zref;
+  double c0r = 0.0, c0i = 0.0, c1r = 0.0, c1i = 0.0;
+  const sk_cplx *gp = grid + (size_t)t.l0 * (SK_HK_K * 2);
+#pragma unroll 1
+  for (int n = SK_HK_K - 1; n >= 0; --n) {
+    double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const sk_cplx v0 = gp[(i * SK_HK_K + n) * 2], v1 = gp[(i * SK_HK_K + n) * 2 + 1];
+      a0r = sk_fma(taps[i], v0.x, a0r);
+      a0i = sk_fma(taps[i], v0.y, a0i);
+      a1r = sk_fma(taps[i], v1.x, a1r);
+      a1i = sk_fma(taps[i], v1.y, a1i);
+    }
+    // C <- raw_n + (i / z_ref) C
+    const double n0r = sk_fma(-c0i, iz, a0r), n0i = sk_fma(c0r, iz, a0i);
+    const double n1r = sk_fma(-c1i, iz, a1r), n1i = sk_fma(c1r, iz, a1i);
+    c0r = n0r; c0i = n0i; c1r = n1r; c1i = n1i;
+  }
+  const double qf = sk_deconv(P, g.G.t_cell * t.yabs);
+  double sn, cs;
+  sk_post_phase(g.G, r, &sn, &cs);
+  // e^{i (2 pi wc r - phi)}
+  const double er = sk_fma(cs, H.cphi, sn * H.sphi), ei = sk_fma(sn, H.cphi, -cs * H.sphi);
+  const double amp = qf * sqrt(0.6366197723675814 * iz);             // sqrt(2 / (pi z_ref))
+  out[0] = amp * sk_fma(c0r, er, -c0i * ei);
+  out[1] = amp * sk_fma(c1r, er, -c1i * ei);
+}
+
+// the whole transform at one target (both rules)
+template <int W>
+SK_HD void sk_hk_point(const SkEsPlan &P, const SkHankelPlan &H, const SkHankelGroup *groups, const sk_cplx *grid,
+                       const double *cheb, double r, double *out) {
+  const int t = sk_hk_octave(H.r_hi, r);
+  double loc[2];
+  sk_hk_local(H, cheb, r, t, loc);
+  const int gi = sk_hk_group_of_octave(H, t);
+  double asy[2] = {0.0, 0.0};
+  if (gi >= 0 && gi < H.ngroups) sk_hk_interp_point<W>(P, H, groups[gi], grid + groups[gi].grid_off, r, asy);
+  out[0] = asy[0] + loc[0];
+  out[1] = asy[1] + loc[1];
+}

@@ -1,9 +1,11 @@
 // sk_host_util.h -- host-side geometry / panel bookkeeping shared by the C-ABI translation unit and
 // the host-emulation test harness.
 #pragma once
+#include "sk_hankel.h"
 #include "sk_math.h"
 
 #include <cmath>
+#include <cstring>
 
 static inline long long sk_next235even(long long n) {
   if (n <= 2) return 2;
@@ -20,7 +22,8 @@ static inline long long sk_next235even(long long n) {
 // Geometry of one type-3 transform: sources in [w_lo, w_hi], targets in [r_lo, r_hi].
 // sigma = 2 for both the spread and the inner type-2 step.
 // Returns 0, or -1 if the grid would be unreasonably large.
-static inline int sk_make_geom(const SkEsPlan &P, double w_lo, double w_hi, double r_lo, double r_hi, SkGeom *G) {
+static inline int sk_make_geom(const SkEsPlan &P, double w_lo, double w_hi, double r_lo, double r_hi, SkGeom *G,
+                               bool force_center = false) {
   const double sigma = 2.0;
   const double PI = 3.14159265358979323846;
   double X = 0.5 * (w_hi - w_lo);
@@ -28,7 +31,7 @@ static inline int sk_make_geom(const SkEsPlan &P, double w_lo, double w_hi, doub
   double S;
   // centre the targets only when they form a narrow band away from the origin; otherwise keep
   // D = 0 (no pre-phase, r - D exact) -- the adaptive driver's targets always start near 0.
-  if (r_lo > 0.5 * r_hi && r_lo > 0.0) {
+  if ((r_lo > 0.5 * r_hi || force_center) && r_lo > 0.0) {
     G->D = 0.5 * (r_lo + r_hi);
     S = 0.5 * (r_hi - r_lo);
   } else if (r_hi < 0.0 && r_hi < 0.5 * r_lo) {
@@ -75,4 +78,54 @@ static inline void sk_fill_subpanels(double a, double b, int k, double *bmad2, d
     bpad2[i - 1] = (e + prev) / 2;
     prev = e;
   }
+}
+
+// Plan of one nonuniform Hankel transform (sk_hankel.h): sources in [a, b], active targets in [r_lo, r_hi].
+// Fills H and groups[0 .. H->ngroups) and returns the total number of sk_cplx grid entries, or -1 when the
+// dyadic scheme does not apply (order not tabulated, too many levels, a grid too large): the caller then uses
+// the direct Bessel summation.
+static inline long long sk_hk_make_plan(const SkEsPlan &P, int nu, double a, double b, double r_lo, double r_hi,
+                                        SkHankelPlan *H, SkHankelGroup *groups) {
+  const double PI = 3.14159265358979323846;
+  if (nu < 0 || nu > SK_HK_NUMAX || !(r_hi > 0.0) || !(b > a) || !(a >= 0.0) || !(r_lo > 0.0) || !(r_lo <= r_hi)) return -1;
+  std::memset(H, 0, sizeof(*H));
+  H->nu = nu;
+  H->r_hi = r_hi;
+  H->wT = SK_HK_ZL / (2.0 * PI * r_hi);
+  const double phi = nu * PI / 2 + PI / 4;
+  H->cphi = std::cos(phi);
+  H->sphi = std::sin(phi);
+  for (int n = 0; n < SK_HK_K; ++n) H->ratio[n] = (4.0 * nu * nu - (2.0 * n + 1.0) * (2.0 * n + 1.0)) / (8.0 * (n + 1.0));
+  H->q_lo = sk_hk_level(H->wT, a);
+  H->q_hi = sk_hk_level(H->wT, b);
+  if (H->q_hi >= SK_HK_NLEV - 1) return -1;
+  H->t_full = H->q_lo >= 2 ? H->q_lo - 2 : -1;
+  H->t_last = H->q_hi - 2;                                     // may be negative: no asymptotic part at all
+  const int t_need = sk_hk_octave(r_hi, r_lo);
+  long long total = 0;
+  int ng = 0;
+  auto add = [&](double w_lo, double rl, double rh, double w_ref, int q_cut, bool center) -> bool {
+    if (ng >= SK_HK_NGRP) return false;
+    SkHankelGroup &g = groups[ng];
+    std::memset(&g, 0, sizeof(g));
+    if (sk_make_geom(P, w_lo, b, rl, rh, &g.G, center) != 0) return false;
+    g.w_ref = w_ref;
+    g.q_cut = q_cut;
+    g.grid_off = total;
+    total += g.G.nf2 * (long long)(2 * SK_HK_K);
+    ++ng;
+    return true;
+  };
+  if (H->t_full >= 0) {
+    const int tm = H->t_full < t_need ? H->t_full : t_need;
+    const double rl = std::fmax(r_lo, std::ldexp(r_hi, -(tm + 1)));
+    if (!add(a, rl, r_hi, std::ldexp(H->wT, H->q_lo - 1), 0, false)) return -1;
+  }
+  for (int t = H->t_full + 1; t <= H->t_last && t <= t_need; ++t) {
+    const double w_ref = std::ldexp(H->wT, t + 1);               // lower boundary of level t+2
+    if (!add(w_ref, std::ldexp(r_hi, -(t + 1)), std::ldexp(r_hi, -t), w_ref, t + 2, true)) return -1;
+  }
+  H->ngroups = ng;
+  if (total > (1LL << 31)) return -1;
+  return total;
 }

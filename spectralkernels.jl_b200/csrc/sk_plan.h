@@ -23,3 +23,5 @@ struct SkEsPlan {
 int sk_plan_make_es(int w, SkEsPlan *out);
 int sk_plan_gauss_rule(int n, double p, double *no, double *wt);
 int sk_plan_jacobi_coeffs(int n, double p, double *A, double *B, double *C);   // (hi, lo) pairs, 2n doubles each
+// piecewise-polynomial table of J_0 .. J_numax on [0, 2 nint] (sk_hankel.h): tab[numax+1][nint][nc]
+int sk_plan_bessel_table(int numax, int nint, int nc, double *tab);

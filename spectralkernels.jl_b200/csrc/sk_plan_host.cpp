@@ -203,3 +203,44 @@ int sk_plan_gauss_rule(int n, double p_, double *no, double *wt) {
     if (!(no[i] > no[i - 1])) return -3;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// J_nu(z), nu = 0 .. numax, 0 <= z <= 2 nint, as piecewise polynomials: interval i = [2i, 2i+2],
+// nc monomial coefficients in t = z - (2i+1).  Values by Miller's backward recurrence in __float128
+// (normalised with J_0 + 2 sum_k J_2k = 1), fitted at Chebyshev nodes: the double coefficients are
+// correctly rounded and the table is good to ~1e-16 absolute (sk_hankel.h uses it for the local
+// Chebyshev expansions of the nonuniform Hankel transform).
+// ---------------------------------------------------------------------------------------------
+static void bessel_miller_q(int numax, q128 z, q128 *J) {
+  if (z == 0) {
+    for (int n = 0; n <= numax; ++n) J[n] = (n == 0) ? 1 : 0;
+    return;
+  }
+  const int N = 2 * ((int)(double)z / 2) + 120;      // even, well above z
+  q128 jp1 = 0, j = 1e-300Q, sum = 0;
+  std::vector<q128> keep(numax + 1, 0);
+  for (int n = N; n >= 1; --n) {
+    const q128 jm1 = (2 * (q128)n / z) * j - jp1;     // J_{n-1} = (2n/z) J_n - J_{n+1}
+    jp1 = j;
+    j = jm1;
+    // j is now J_{n-1} (unnormalised)
+    if (n - 1 <= numax) keep[n - 1] = j;
+    if ((n - 1) % 2 == 0) sum += (n - 1 == 0) ? j : 2 * j;
+  }
+  for (int n = 0; n <= numax; ++n) J[n] = keep[n] / sum;
+}
+
+int sk_plan_bessel_table(int numax, int nint, int nc, double *tab) {
+  if (numax < 0 || nint < 1 || nc < 2 || !tab) return -1;
+  for (int nu = 0; nu <= numax; ++nu)
+    for (int i = 0; i < nint; ++i) {
+      std::vector<q128> mono;
+      cheb_fit_monomial(nc, [&](q128 t) {
+        std::vector<q128> J(numax + 1);
+        bessel_miller_q(numax, (q128)(2 * i + 1) + t, J.data());
+        return J[nu];
+      }, mono);
+      for (int q = 0; q < nc; ++q) tab[((size_t)nu * nint + i) * nc + q] = (double)mono[q];
+    }
+  return 0;
+}

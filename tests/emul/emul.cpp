@@ -169,4 +169,70 @@ double emul_sincos_err(int n) {
 
 double emul_trunc_err(double ta, double tn, double xpow, double x, int panel) { return sk_trunc_err(ta, tn, xpow, x, panel); }
 int emul_converged(double te, double pk, double tau, int crit) { return sk_converged(te, pk, tau, crit) ? 1 : 0; }
+
+// ---- nonuniform Hankel transform (sk_hankel.h), the arithmetic of sk_hankel.cuh in plain loops ----------
+int emul_bessel_table(double *tab) { return sk_plan_bessel_table(SK_HK_NUMAX, SK_HK_TAB_INT, SK_HK_TAB_NC, tab); }
+double emul_bessel_eval(const double *tab, int nu, double z) { return sk_bessel_tab(tab, nu, z); }
+int emul_hk_sizes(int *plan_bytes, int *group_bytes, int *K, int *nlev, int *nch, int *ngrp) {
+  *plan_bytes = (int)sizeof(SkHankelPlan); *group_bytes = (int)sizeof(SkHankelGroup);
+  *K = SK_HK_K; *nlev = SK_HK_NLEV; *nch = SK_HK_NCH; *ngrp = SK_HK_NGRP;
+  return 0;
+}
+long long emul_hk_plan(const SkEsPlan *P, int nu, double a, double b, double r_lo, double r_hi, SkHankelPlan *H,
+                       SkHankelGroup *groups) {
+  return sk_hk_make_plan(*P, nu, a, b, r_lo, r_hi, H, groups);
+}
+void emul_hk_plan_info(const SkHankelPlan *H, int *out /*q_lo q_hi t_full t_last ngroups*/) {
+  out[0] = H->q_lo; out[1] = H->q_hi; out[2] = H->t_full; out[3] = H->t_last; out[4] = H->ngroups;
+}
+void emul_hk_group_info(const SkHankelGroup *g, int gi, long long *nf2, long long *off, double *D) {
+  *nf2 = g[gi].G.nf2; *off = g[gi].grid_off; *D = g[gi].G.D;
+}
+int emul_hk_level(double wT, double w) { return sk_hk_level(wT, w); }
+int emul_hk_octave(double r_hi, double r) { return sk_hk_octave(r_hi, r); }
+// Chebyshev coefficients of every level's partial sum for one rule: cheb[NLEV][NCH]
+void emul_hk_fit(const SkHankelPlan *H, const double *tab, long long M, const double *no, const double *buf, double *cheb) {
+  std::vector<long long> start(SK_HK_NLEV + 1, M);
+  for (long long k = M - 1; k >= 0; --k) {                 // lev_start[q] = first source of level >= q
+    const int l = sk_hk_level(H->wT, no[k]);
+    for (int q = 0; q <= l; ++q) start[q] = k;
+  }
+  std::memset(cheb, 0, sizeof(double) * SK_HK_NLEV * SK_HK_NCH);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int q = H->q_lo; q <= H->q_hi; ++q) {
+    const double R = sk_hk_level_radius(H->r_hi, q);
+    double vals[SK_HK_NCH];
+    for (int i = 0; i < SK_HK_NCH; ++i) {
+      const double rho = 0.5 * R * (sk_hk_cheb_node(i) + 1.0);
+      double acc = 0.0;
+      for (long long k = start[q]; k < start[q + 1]; ++k) acc += sk_hk_fit_term(tab, H->nu, no[k], buf[k], rho);
+      vals[i] = acc;
+    }
+    for (int m = 0; m < SK_HK_NCH; ++m) cheb[q * SK_HK_NCH + m] = sk_hk_cheb_coef(vals, m);
+  }
+}
+// FFT input of group gi for one rule: fft_in[nf2][K][2] (interleaved complex), entries of the other rule untouched
+void emul_hk_spread(const SkEsPlan *P, const SkHankelPlan *H, const SkHankelGroup *groups, int gi, int rule, long long M,
+                    const double *no, const double *buf, double *fft_in) {
+  const SkHankelGroup &g = groups[gi];
+  std::vector<double> ph(M), pl(M), lam(M);
+  std::vector<sk_cplx> cs(M);
+  for (long long k = 0; k < M; ++k) sk_hk_source_prep(g, H->wT, no[k], buf[k], &ph[k], &pl[k], &cs[k], &lam[k]);
+#pragma omp parallel for schedule(static)
+  for (long long j = 0; j < g.G.nf2; ++j) {
+    sk_cplx o[SK_HK_K];
+    sk_hk_spread_mode(*P, *H, g.G, j, ph.data(), pl.data(), cs.data(), lam.data(), M, o);
+    for (int n = 0; n < SK_HK_K; ++n) {
+      fft_in[((j * SK_HK_K + n) * 2 + rule) * 2] = o[n].x;
+      fft_in[((j * SK_HK_K + n) * 2 + rule) * 2 + 1] = o[n].y;
+    }
+  }
+}
+// all targets: out[N][2]
+void emul_hk_eval(const SkEsPlan *P, const SkHankelPlan *H, const SkHankelGroup *groups, const double *grid,
+                  const double *cheb, long long N, const double *r, double *out) {
+#pragma omp parallel for schedule(static)
+  for (long long j = 0; j < N; ++j)
+    sk_hk_point<16>(*P, *H, groups, reinterpret_cast<const sk_cplx *>(grid), cheb, r[j], &out[2 * j]);
+}
 }
