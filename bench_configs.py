@@ -106,7 +106,9 @@ def config2_dim2():
     """1e7 uniform lags, Matern nu = 1.5 in 2-D (J_0 kernel): closed form available."""
     from scipy import special
     rng = np.random.default_rng(0)
-    xs = rng.uniform(0, 1, 10_000_000)
+    pin = sk.PinnedArray(10_000_000)
+    xs = pin.array
+    xs[:] = rng.uniform(0, 1, xs.size)
     parms = (1.0, 1.0, 1.5)
     cfg = sk.AdaptiveKernelConfig(sk.Matern(*parms, d=2), dim=2)
     k0 = float(np.pi * parms[0] / (2 ** 0.5 * special.gamma(2.5)) * 2 ** 0.5 * special.gamma(1.5))

@@ -151,7 +151,7 @@ struct sk_ctx {
   DevBuf<double> hk_tab, hk_vals, hk_cheb, hk_lam1, hk_lam2;
   DevBuf<long long> hk_lev;
   DevBuf<SkHankelGroup> hk_groups;
-  DevBuf<sk_cplx> hk_grid;
+  DevBuf<sk_cplx> hk_grid, hk_part;
   bool smem_attr_set[SK_WMAX + 1] = {false};
   // target-sharded multi-GPU: scalar NCCL all-reduces on the context's stream
   ncclComm_t comm = nullptr;
@@ -396,7 +396,7 @@ int hankel_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, lo
     CK(c->hk_tab.ensure(SK_HK_TAB_SIZE));
     CK(cudaMemcpyAsync(c->hk_tab.p, tab.data(), sizeof(double) * SK_HK_TAB_SIZE, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    CK(c->hk_vals.ensure(2 * SK_HK_NLEV * SK_HK_NCH));
+    CK(c->hk_vals.ensure(SK_HK_FITSPLIT * 2 * SK_HK_NLEV * SK_HK_NCH));
     CK(c->hk_cheb.ensure(2 * SK_HK_NLEV * SK_HK_NCH));
     CK(c->hk_lev.ensure(2 * (SK_HK_NLEV + 1)));
     CK(c->hk_groups.ensure(SK_HK_NGRP));
@@ -411,7 +411,7 @@ int hankel_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, lo
   k_hankel_levels<<<nblk(M1 + M2, 256), 256, 0, c->stream>>>(H.wT, c->no1.p, M1, c->no2.p, M2, c->hk_lev.p);
   LAUNCH_CHECK();
   {
-    dim3 grid(SK_HK_NCH, H.q_hi - H.q_lo + 1, 2);
+    dim3 grid(SK_HK_NCH, H.q_hi - H.q_lo + 1, 2 * SK_HK_FITSPLIT);
     k_hankel_fit<<<grid, 256, 0, c->stream>>>(H, c->hk_tab.p, c->no1.p, c->buf1.p, c->no2.p, c->buf2.p, c->hk_lev.p, c->hk_vals.p);
     LAUNCH_CHECK();
     k_hankel_cheb<<<nblk(2 * (H.q_hi - H.q_lo + 1) * SK_HK_NCH, 128), 128, 0, c->stream>>>(H, c->hk_vals.p, c->hk_cheb.p);
@@ -428,9 +428,19 @@ int hankel_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, lo
     const SkGeom &G = hg[gi].G;
     k_hankel_prep<<<nblk(M1 + M2, 256), 256, 0, c->stream>>>(c->hk_groups.p, gi, H.wT, S);
     LAUNCH_CHECK();
-    dim3 grid(nblk(G.nf, SK_SPREAD_CELLS), 2);
-    k_spread_hankel<16><<<grid, 256, 0, c->stream>>>(c->plan, c->hk_groups.p, gi, H, S, c->hk_grid.p);
+    // enough blocks to fill the GPU: small grids split each cell block's source range (split-K)
+    const unsigned int bx = nblk(G.nf, SK_SPREAD_CELLS);
+    int nsplit = (int)((148u * 4u + 2u * bx - 1u) / (2u * bx));
+    nsplit = nsplit < 1 ? 1 : (nsplit > 64 ? 64 : nsplit);
+    if (nsplit > 1) CK(c->hk_part.ensure((size_t)nsplit * G.nf * 2 * SK_HK_K));
+    dim3 grid(bx, 2, nsplit);
+    k_spread_hankel<16><<<grid, 256, 0, c->stream>>>(c->plan, c->hk_groups.p, gi, H, S, c->hk_grid.p, c->hk_part.p);
     LAUNCH_CHECK();
+    if (nsplit > 1) {
+      k_spread_hankel_reduce<<<nblk(G.nf * 2 * SK_HK_K, 256), 256, 0, c->stream>>>(c->plan, c->hk_groups.p, gi, nsplit,
+                                                                                  c->hk_part.p, c->hk_grid.p);
+      LAUNCH_CHECK();
+    }
     cufftHandle h;
     int rc = get_fft_plan(c, G.nf2, 2 * SK_HK_K, &h);
     if (rc != SK_OK) return rc;
@@ -442,9 +452,14 @@ int hankel_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, lo
     c->stats.last_nf2 = G.nf2;
   }
   if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
-  k_hankel_interp<16><<<nblk(n_act, 256), 256, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p, c->hk_cheb.p,
-                                                               c->uxs.p + c->lo, n_act, o->cmul, o->xdiv_pow,
-                                                               c->stage.p + c->lo, c->d_red);
+  if (c->interp_mode == 1)     // A/B: one target per thread, 16-byte loads (the plain restatement of sk_hk_point)
+    k_hankel_interp<16><<<nblk(n_act, 256), 256, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p, c->hk_cheb.p,
+                                                                 c->uxs.p + c->lo, n_act, o->cmul, o->xdiv_pow,
+                                                                 c->stage.p + c->lo, c->d_red);
+  else
+    k_hankel_interp2<16><<<nblk((n_act + 1) / 2, SK_HK_TPB2), SK_HK_TPB2, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p,
+                                                                            c->hk_cheb.p, c->uxs.p + c->lo, n_act, o->cmul,
+                                                                            o->xdiv_pow, c->stage.p + c->lo, c->d_red);
   LAUNCH_CHECK();
   if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
   c->stats.n_hankel++;
@@ -810,7 +825,7 @@ int sk_ctx_destroy(sk_ctx *c) {
   c->res.release(); c->pan.release(); c->stage.release();
   c->fftB.release(); c->dsumB.release(); c->bufb1.release(); c->bufb2.release();
   c->hk_tab.release(); c->hk_vals.release(); c->hk_cheb.release(); c->hk_lam1.release(); c->hk_lam2.release();
-  c->hk_lev.release(); c->hk_groups.release(); c->hk_grid.release();
+  c->hk_lev.release(); c->hk_groups.release(); c->hk_grid.release(); c->hk_part.release();
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   if (c->d_ga) cudaFree(c->d_ga);
   if (c->d_gb) cudaFree(c->d_gb);

@@ -30,15 +30,19 @@ __global__ void k_hankel_levels(double wT, const double *__restrict__ no1, long 
     for (int q = l + 1; q <= SK_HK_NLEV; ++q) ls[q] = M;
 }
 
-// grid (SK_HK_NCH nodes, levels q_lo..q_hi, 2 rules); fixed-order tree reduction (bitwise reproducible)
+// grid (SK_HK_NCH nodes, levels q_lo..q_hi, 2 rules x SK_HK_FITSPLIT slices of the level's sources); fixed-order
+// tree reduction per slice, the slices are added in order by k_hankel_cheb (bitwise reproducible)
+#define SK_HK_FITSPLIT 8
 __global__ void __launch_bounds__(256)
 k_hankel_fit(const __grid_constant__ SkHankelPlan H, const double *__restrict__ tab, const double *__restrict__ no1,
              const double *__restrict__ buf1, const double *__restrict__ no2, const double *__restrict__ buf2,
-             const long long *__restrict__ lev_start, double *__restrict__ vals /*[2][SK_HK_NLEV][SK_HK_NCH]*/) {
-  const int i = blockIdx.x, q = H.q_lo + blockIdx.y, rule = blockIdx.z;
+             const long long *__restrict__ lev_start, double *__restrict__ vals /*[FITSPLIT][2][SK_HK_NLEV][SK_HK_NCH]*/) {
+  const int i = blockIdx.x, q = H.q_lo + blockIdx.y, rule = blockIdx.z & 1, z = blockIdx.z >> 1;
   const double *no = rule ? no2 : no1;
   const double *buf = rule ? buf2 : buf1;
-  const long long s0 = lev_start[rule * (SK_HK_NLEV + 1) + q], s1 = lev_start[rule * (SK_HK_NLEV + 1) + q + 1];
+  const long long l0 = lev_start[rule * (SK_HK_NLEV + 1) + q], l1 = lev_start[rule * (SK_HK_NLEV + 1) + q + 1];
+  const long long len = (l1 - l0 + SK_HK_FITSPLIT - 1) / SK_HK_FITSPLIT;
+  const long long s0 = l0 + z * len, s1 = (s0 + len) < l1 ? (s0 + len) : l1;
   const double rho = 0.5 * sk_hk_level_radius(H.r_hi, q) * (sk_hk_cheb_node(i) + 1.0);
   double acc = 0.0;
   for (long long k = s0 + threadIdx.x; k < s1; k += blockDim.x) acc += sk_hk_fit_term(tab, H.nu, no[k], buf[k], rho);
@@ -49,7 +53,7 @@ k_hankel_fit(const __grid_constant__ SkHankelPlan H, const double *__restrict__ 
     if ((int)threadIdx.x < o) sr[threadIdx.x] += sr[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) vals[((size_t)rule * SK_HK_NLEV + q) * SK_HK_NCH + i] = sr[0];
+  if (threadIdx.x == 0) vals[(((size_t)z * 2 + rule) * SK_HK_NLEV + q) * SK_HK_NCH + i] = sr[0];
 }
 
 __global__ void k_hankel_cheb(const __grid_constant__ SkHankelPlan H, const double *__restrict__ vals,
@@ -59,7 +63,13 @@ __global__ void k_hankel_cheb(const __grid_constant__ SkHankelPlan H, const doub
   if (t >= 2 * nq * SK_HK_NCH) return;
   const int m = t % SK_HK_NCH, q = H.q_lo + (t / SK_HK_NCH) % nq, rule = t / (SK_HK_NCH * nq);
   const size_t base = ((size_t)rule * SK_HK_NLEV + q) * SK_HK_NCH;
-  cheb[base + m] = sk_hk_cheb_coef(vals + base, m);
+  double v[SK_HK_NCH];
+  for (int i = 0; i < SK_HK_NCH; ++i) {
+    double a = 0.0;
+    for (int z = 0; z < SK_HK_FITSPLIT; ++z) a += vals[(size_t)z * 2 * SK_HK_NLEV * SK_HK_NCH + base + i];
+    v[i] = a;
+  }
+  cheb[((size_t)q * SK_HK_NCH + m) * 2 + rule] = sk_hk_cheb_coef(v, m);      // layout [NLEV][NCH][2 rules]
 }
 
 struct SkHkSrc {
@@ -86,7 +96,8 @@ __global__ void k_hankel_prep(const SkHankelGroup *__restrict__ groups, int gi, 
 template <int W>
 __global__ void __launch_bounds__(256)
 k_spread_hankel(const __grid_constant__ SkEsPlan P, const SkHankelGroup *__restrict__ groups, int gi,
-                const __grid_constant__ SkHankelPlan H, const __grid_constant__ SkHkSrc src, sk_cplx *__restrict__ grid_all) {
+                const __grid_constant__ SkHankelPlan H, const __grid_constant__ SkHkSrc src, sk_cplx *__restrict__ grid_all,
+                sk_cplx *__restrict__ part /*[gridDim.z][nf][K][2] when gridDim.z > 1*/) {
   const SkGeom G = groups[gi].G;
   sk_cplx *__restrict__ fft_io = grid_all + groups[gi].grid_off;
   const int r = blockIdx.y;
@@ -111,7 +122,14 @@ k_spread_hankel(const __grid_constant__ SkEsPlan P, const SkHankelGroup *__restr
     if (threadIdx.x == 32) s_range[1] = v;
   }
   __syncthreads();
-  const long long s0 = s_range[0], s1 = s_range[1];
+  // small grids hold many sources per cell: gridDim.z blocks share a cell block's source range (split-K); their
+  // partial sums are added in slice order by k_spread_hankel_reduce, so the result stays reproducible
+  long long s0 = s_range[0], s1 = s_range[1];
+  if (gridDim.z > 1) {
+    const long long len = (s1 - s0 + gridDim.z - 1) / gridDim.z;
+    s0 += (long long)blockIdx.z * len;
+    s1 = (s0 + len) < s1 ? (s0 + len) : s1;
+  }
   const int sub = threadIdx.x & (SK_SPREAD_LANES - 1);
   const int cell = threadIdx.x / SK_SPREAD_LANES;
   const long long l = l_blk + cell;
@@ -179,11 +197,42 @@ k_spread_hankel(const __grid_constant__ SkEsPlan P, const SkHankelGroup *__restr
     }
     if (sub == 0 && live) {
       sk_cplx o;
-      o.x = vr * q;
-      o.y = vi * q;
-      fft_io[(jout * SK_HK_K + n) * 2 + r] = o;
+      if (gridDim.z > 1) {
+        o.x = vr;
+        o.y = vi;
+        part[(((size_t)blockIdx.z * G.nf + l) * SK_HK_K + n) * 2 + r] = o;
+      } else {
+        o.x = vr * q;
+        o.y = vi * q;
+        fft_io[(jout * SK_HK_K + n) * 2 + r] = o;
+      }
     }
   }
+}
+
+// second half of the split-K spread: add the slices in order, deconvolve the mode, write the FFT input
+__global__ void k_spread_hankel_reduce(const __grid_constant__ SkEsPlan P, const SkHankelGroup *__restrict__ groups, int gi,
+                                       int nsplit, const sk_cplx *__restrict__ part, sk_cplx *__restrict__ grid_all) {
+  const SkGeom G = groups[gi].G;
+  sk_cplx *__restrict__ fft_io = grid_all + groups[gi].grid_off;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= G.nf * (SK_HK_K * 2)) return;
+  const long long l = t / (SK_HK_K * 2);
+  const int nr = (int)(t % (SK_HK_K * 2));
+  double vr = 0.0, vi = 0.0;
+  for (int z = 0; z < nsplit; ++z) {
+    const sk_cplx v = part[((size_t)z * G.nf + l) * (SK_HK_K * 2) + nr];
+    vr += v.x;
+    vi += v.y;
+  }
+  const long long n = l - G.nf / 2;
+  double q = sk_deconv(P, G.t_cell * fabs((double)n));
+  if (n & 1) q = -q;
+  const long long jout = n >= 0 ? n : n + G.nf2;
+  sk_cplx o;
+  o.x = vr * q;
+  o.y = vi * q;
+  fft_io[jout * (SK_HK_K * 2) + nr] = o;
 }
 
 template <int W>
@@ -207,6 +256,152 @@ k_hankel_interp(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHa
       i2 = i2 / den;
     }
     sk_stage(i1, i2, 1.0, &stage[j], d, fl);
+  }
+  sk_block_reduce_maxflags(d, fl, red);
+}
+
+// ---- K9d, production variant ---------------------------------------------------------------------------------
+// k_hankel_interp above is bound by the L1/LSU path (ncu: l1tex throughput 95 %, FP64 pipe 25 %): one 16-byte
+// load per two FMAs.  Here every thread owns TWO consecutive sorted targets; when they share the group and the
+// grid window (the usual case: ~100 targets per cell) each grid value is fetched once with one 256-bit load
+// and feeds 8 FMAs, and the Chebyshev coefficients of the local levels are fetched four at a time for 8 FMAs.
+// The arithmetic per target is the sequence of sk_hk_point, operation for operation: results are bit-identical
+// to k_hankel_interp whatever the pairing (tests: test_hankel_interp_variants_agree).
+__device__ __forceinline__ void sk_ld256(const void *p, double &a, double &b, double &c, double &d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+template <int W>
+__device__ __forceinline__ void sk_hk_interp_pair(const SkEsPlan &P, const SkHankelPlan &H, const SkHankelGroup &g,
+                                                  const sk_cplx *grid, const SkTargetCoord &tA, const SkTargetCoord &tB,
+                                                  double rA, double rB, double *outA, double *outB) {
+  double tapA[W], tapB[W];
+  sk_es_taps<W>(P, tA.s, tapA);
+  sk_es_taps<W>(P, tB.s, tapB);
+  const double izA = 1.0 / sk_mul(sk_mul(6.283185307179586, g.w_ref), rA);
+  const double izB = 1.0 / sk_mul(sk_mul(6.283185307179586, g.w_ref), rB);
+  double cA[4] = {0.0, 0.0, 0.0, 0.0}, cB[4] = {0.0, 0.0, 0.0, 0.0};      // (rule0 re, im, rule1 re, im)
+  const sk_cplx *gp = grid + (size_t)tA.l0 * (SK_HK_K * 2);
+#pragma unroll 1
+  for (int n = SK_HK_K - 1; n >= 0; --n) {
+    double aA[4] = {0.0, 0.0, 0.0, 0.0}, aB[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      double v0, v1, v2, v3;
+      sk_ld256(gp + (i * SK_HK_K + n) * 2, v0, v1, v2, v3);
+      aA[0] = sk_fma(tapA[i], v0, aA[0]); aA[1] = sk_fma(tapA[i], v1, aA[1]);
+      aA[2] = sk_fma(tapA[i], v2, aA[2]); aA[3] = sk_fma(tapA[i], v3, aA[3]);
+      aB[0] = sk_fma(tapB[i], v0, aB[0]); aB[1] = sk_fma(tapB[i], v1, aB[1]);
+      aB[2] = sk_fma(tapB[i], v2, aB[2]); aB[3] = sk_fma(tapB[i], v3, aB[3]);
+    }
+    const double a0 = sk_fma(-cA[1], izA, aA[0]), a1 = sk_fma(cA[0], izA, aA[1]);
+    const double a2 = sk_fma(-cA[3], izA, aA[2]), a3 = sk_fma(cA[2], izA, aA[3]);
+    cA[0] = a0; cA[1] = a1; cA[2] = a2; cA[3] = a3;
+    const double b0 = sk_fma(-cB[1], izB, aB[0]), b1 = sk_fma(cB[0], izB, aB[1]);
+    const double b2 = sk_fma(-cB[3], izB, aB[2]), b3 = sk_fma(cB[2], izB, aB[3]);
+    cB[0] = b0; cB[1] = b1; cB[2] = b2; cB[3] = b3;
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const SkTargetCoord &t = u ? tB : tA;
+    const double r = u ? rB : rA, iz = u ? izB : izA;
+    const double *c = u ? cB : cA;
+    const double qf = sk_deconv(P, g.G.t_cell * t.yabs);
+    double sn, cs;
+    sk_post_phase(g.G, r, &sn, &cs);
+    const double er = sk_fma(cs, H.cphi, sn * H.sphi), ei = sk_fma(sn, H.cphi, -cs * H.sphi);
+    const double amp = qf * sqrt(0.6366197723675814 * iz);
+    double *o = u ? outB : outA;
+    o[0] = amp * sk_fma(c[0], er, -c[1] * ei);
+    o[1] = amp * sk_fma(c[2], er, -c[3] * ei);
+  }
+}
+
+// local levels of two targets of the same octave: 4 Clenshaw recurrences fed by 256-bit coefficient loads
+__device__ __forceinline__ void sk_hk_local_pair(const SkHankelPlan &H, const double *cheb, double rA, double rB, int t,
+                                                 double *outA, double *outB) {
+  outA[0] = outA[1] = outB[0] = outB[1] = 0.0;
+  const int qe = (t + 1 < H.q_hi) ? t + 1 : H.q_hi;
+  for (int q = H.q_lo; q <= qe; ++q) {
+    const double R = sk_hk_level_radius(H.r_hi, q);
+    const double xA = 2.0 * sk_fma(rA, 2.0 / R, -1.0), xB = 2.0 * sk_fma(rB, 2.0 / R, -1.0);
+    const double *c = cheb + (size_t)q * (SK_HK_NCH * 2);
+    double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0, e1 = 0.0, e2 = 0.0, f1 = 0.0, f2 = 0.0;   // A rule0, A rule1, B rule0, B rule1
+#pragma unroll 1
+    for (int j = SK_HK_NCH - 1; j >= 3; j -= 2) {
+      double lo0, lo1, hi0, hi1;                               // c[j-1][0..1], c[j][0..1]
+      sk_ld256(c + 2 * (j - 1), lo0, lo1, hi0, hi1);
+      double a0 = sk_fma(xA, a1, hi0 - a2), b0 = sk_fma(xA, b1, hi1 - b2);
+      double e0 = sk_fma(xB, e1, hi0 - e2), f0 = sk_fma(xB, f1, hi1 - f2);
+      a2 = a1; a1 = a0; b2 = b1; b1 = b0; e2 = e1; e1 = e0; f2 = f1; f1 = f0;
+      a0 = sk_fma(xA, a1, lo0 - a2); b0 = sk_fma(xA, b1, lo1 - b2);
+      e0 = sk_fma(xB, e1, lo0 - e2); f0 = sk_fma(xB, f1, lo1 - f2);
+      a2 = a1; a1 = a0; b2 = b1; b1 = b0; e2 = e1; e1 = e0; f2 = f1; f1 = f0;
+    }
+    double z0, z1, o0, o1;                                     // c[0][0..1], c[1][0..1]
+    sk_ld256(c, z0, z1, o0, o1);
+    {
+      const double a0 = sk_fma(xA, a1, o0 - a2), b0 = sk_fma(xA, b1, o1 - b2);
+      const double e0 = sk_fma(xB, e1, o0 - e2), f0 = sk_fma(xB, f1, o1 - f2);
+      a2 = a1; a1 = a0; b2 = b1; b1 = b0; e2 = e1; e1 = e0; f2 = f1; f1 = f0;
+    }
+    outA[0] += sk_fma(0.5 * xA, a1, z0 - a2);
+    outA[1] += sk_fma(0.5 * xA, b1, z1 - b2);
+    outB[0] += sk_fma(0.5 * xB, e1, z0 - e2);
+    outB[1] += sk_fma(0.5 * xB, f1, z1 - f2);
+  }
+}
+
+#define SK_HK_TPB2 128       // ~160 registers per thread: 3 blocks of 128 threads per SM
+template <int W>
+__global__ void __launch_bounds__(SK_HK_TPB2, 3)
+k_hankel_interp2(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHankelPlan H,
+                 const SkHankelGroup *__restrict__ groups, const sk_cplx *__restrict__ grid, const double *__restrict__ cheb,
+                 const double *__restrict__ xs, long long n, double cmul, double xdiv, sk_cplx *__restrict__ stage,
+                 SkReduceOut *__restrict__ red) {
+  static_assert(SK_HK_NCH % 2 == 0, "the paired Clenshaw loop consumes two coefficients per step");
+  const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  double d = 0.0;
+  unsigned int fl = 0;
+  if (j < n) {
+    const bool two = j + 1 < n;
+    const double xA = xs[j], xB = two ? xs[j + 1] : xA;
+    const int tA = sk_hk_octave(H.r_hi, xA), tB = sk_hk_octave(H.r_hi, xB);
+    int gA = sk_hk_group_of_octave(H, tA), gB = sk_hk_group_of_octave(H, tB);
+    if (gA >= H.ngroups) gA = -1;
+    if (gB >= H.ngroups) gB = -1;
+    double fA[2] = {0.0, 0.0}, fB[2] = {0.0, 0.0}, lA[2], lB[2];
+    if (tA == tB) {
+      sk_hk_local_pair(H, cheb, xA, xB, tA, lA, lB);
+    } else {
+      sk_hk_local(H, cheb, xA, tA, lA);
+      sk_hk_local(H, cheb, xB, tB, lB);
+    }
+    bool paired = false;
+    if (gA >= 0 && gA == gB) {
+      const SkTargetCoord cA = sk_target_coord<W>(groups[gA].G, xA), cB = sk_target_coord<W>(groups[gA].G, xB);
+      if (cA.l0 == cB.l0) {
+        sk_hk_interp_pair<W>(P, H, groups[gA], grid + groups[gA].grid_off, cA, cB, xA, xB, fA, fB);
+        paired = true;
+      }
+    }
+    if (!paired) {
+      if (gA >= 0) sk_hk_interp_point<W>(P, H, groups[gA], grid + groups[gA].grid_off, xA, fA);
+      if (gB >= 0) sk_hk_interp_point<W>(P, H, groups[gB], grid + groups[gB].grid_off, xB, fB);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const double x = u ? xB : xA;
+      const double f0 = (u ? fB[0] : fA[0]) + (u ? lB[0] : lA[0]), f1 = (u ? fB[1] : fA[1]) + (u ? lB[1] : lA[1]);
+      double i1 = sk_mul(f0, cmul), i2 = sk_mul(f1, cmul);
+      if (xdiv != 0.0) {
+        const double den = pow(x, xdiv);
+        i1 = i1 / den;
+        i2 = i2 / den;
+      }
+      sk_stage(i1, i2, 1.0, &stage[j + u], d, fl);
+    }
   }
   sk_block_reduce_maxflags(d, fl, red);
 }

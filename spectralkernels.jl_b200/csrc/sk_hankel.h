@@ -110,24 +110,23 @@ SK_HD double sk_hk_cheb_coef(const double *vals, int m) {
   }
   return acc * (m == 0 ? 1.0 : 2.0) / (double)SK_HK_NCH;
 }
-// sum over the local levels of a target in octave t; cheb layout [2 rules][SK_HK_NLEV][SK_HK_NCH]
+// sum over the local levels of a target in octave t; cheb layout [SK_HK_NLEV][SK_HK_NCH][2 rules]
 SK_HD void sk_hk_local(const SkHankelPlan &H, const double *cheb, double r, int t, double *out) {
   out[0] = out[1] = 0.0;
   const int qe = (t + 1 < H.q_hi) ? t + 1 : H.q_hi;
   for (int q = H.q_lo; q <= qe; ++q) {
     const double R = sk_hk_level_radius(H.r_hi, q);
     const double x2 = 2.0 * sk_fma(r, 2.0 / R, -1.0);             // 2x, x in [-1, 1]
-    const double *c0 = cheb + (size_t)q * SK_HK_NCH;
-    const double *c1 = c0 + (size_t)SK_HK_NLEV * SK_HK_NCH;
+    const double *c = cheb + (size_t)q * (SK_HK_NCH * 2);
     double b1 = 0.0, b2 = 0.0, d1 = 0.0, d2 = 0.0;
     for (int j = SK_HK_NCH - 1; j >= 1; --j) {
-      const double b0 = sk_fma(x2, b1, c0[j] - b2);
-      const double d0 = sk_fma(x2, d1, c1[j] - d2);
+      const double b0 = sk_fma(x2, b1, c[2 * j] - b2);
+      const double d0 = sk_fma(x2, d1, c[2 * j + 1] - d2);
       b2 = b1; b1 = b0;
       d2 = d1; d1 = d0;
     }
-    out[0] += sk_fma(0.5 * x2, b1, c0[0] - b2);
-    out[1] += sk_fma(0.5 * x2, d1, c1[0] - d2);
+    out[0] += sk_fma(0.5 * x2, b1, c[0] - b2);
+    out[1] += sk_fma(0.5 * x2, d1, c[1] - d2);
   }
 }
 

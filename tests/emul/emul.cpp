@@ -190,14 +190,14 @@ void emul_hk_group_info(const SkHankelGroup *g, int gi, long long *nf2, long lon
 }
 int emul_hk_level(double wT, double w) { return sk_hk_level(wT, w); }
 int emul_hk_octave(double r_hi, double r) { return sk_hk_octave(r_hi, r); }
-// Chebyshev coefficients of every level's partial sum for one rule: cheb[NLEV][NCH]
-void emul_hk_fit(const SkHankelPlan *H, const double *tab, long long M, const double *no, const double *buf, double *cheb) {
+// Chebyshev coefficients of every level's partial sum for one rule: cheb[NLEV][NCH][2 rules], column `rule`
+void emul_hk_fit(const SkHankelPlan *H, const double *tab, int rule, long long M, const double *no, const double *buf, double *cheb) {
   std::vector<long long> start(SK_HK_NLEV + 1, M);
   for (long long k = M - 1; k >= 0; --k) {                 // lev_start[q] = first source of level >= q
     const int l = sk_hk_level(H->wT, no[k]);
     for (int q = 0; q <= l; ++q) start[q] = k;
   }
-  std::memset(cheb, 0, sizeof(double) * SK_HK_NLEV * SK_HK_NCH);
+  for (int i = 0; i < SK_HK_NLEV * SK_HK_NCH; ++i) cheb[2 * i + rule] = 0.0;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int q = H->q_lo; q <= H->q_hi; ++q) {
     const double R = sk_hk_level_radius(H->r_hi, q);
@@ -208,7 +208,7 @@ void emul_hk_fit(const SkHankelPlan *H, const double *tab, long long M, const do
       for (long long k = start[q]; k < start[q + 1]; ++k) acc += sk_hk_fit_term(tab, H->nu, no[k], buf[k], rho);
       vals[i] = acc;
     }
-    for (int m = 0; m < SK_HK_NCH; ++m) cheb[q * SK_HK_NCH + m] = sk_hk_cheb_coef(vals, m);
+    for (int m = 0; m < SK_HK_NCH; ++m) cheb[(q * SK_HK_NCH + m) * 2 + rule] = sk_hk_cheb_coef(vals, m);
   }
 }
 // FFT input of group gi for one rule: fft_in[nf2][K][2] (interleaved complex), entries of the other rule untouched

@@ -27,15 +27,18 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
     flavour = os.environ.get("SK_COMM", "lib")
-    for name, S, gen, k0 in (
-        ("matern_uniform", sk.Matern(1 / (np.pi / 2), 1.0, 1.5), lambda rng, n: rng.uniform(0, 1, n), 1.0),
-        ("slow_decay_logspaced", sk.Matern(1.0, 0.5, 0.55), lambda rng, n: 10 ** rng.uniform(-4, 0, n), 5.9),
+    for name, S, gen, k0, kw in (
+        ("matern_uniform", sk.Matern(1 / (np.pi / 2), 1.0, 1.5), lambda rng, n: rng.uniform(0, 1, n), 1.0, {}),
+        ("slow_decay_logspaced", sk.Matern(1.0, 0.5, 0.55), lambda rng, n: 10 ** rng.uniform(-4, 0, n), 5.9, {}),
+        # dim = 2: the O(N) nonuniform Hankel transform (octave groups are built from the global distance range)
+        ("matern_2d_hankel", sk.Matern(1.0, 1.0, 1.5, d=2), lambda rng, n: rng.uniform(0, 1, n), 2.0943951023931953,
+         {"dim": 2}),
     ):
         n = 400_000
         chunks = [gen(np.random.default_rng(100 + r), n + 1000 * r) for r in range(world)]
         if name == "slow_decay_logspaced":
             chunks[world - 1] = chunks[world - 1] * 1e-2          # the last rank runs out of active targets early
-        cfg = sk.AdaptiveKernelConfig(S, device=local)
+        cfg = sk.AdaptiveKernelConfig(S, device=local, **kw)
         comm = LibComm.from_torch(cfg.engine) if flavour == "lib" else TorchComm(device=torch.device("cuda", local))
         tr = []
         v, e = sk.kernel_values(cfg, chunks[rank], k0=k0, comm=comm, trace=tr)
@@ -52,7 +55,7 @@ def main():
         dist.all_gather_object(keys, [(t["a"], t["b"], t.get("accepted"), t.get("criteria")) for t in tr])
         if rank == 0:
             union = np.concatenate(chunks)
-            cfg1 = sk.AdaptiveKernelConfig(S, device=local)
+            cfg1 = sk.AdaptiveKernelConfig(S, device=local, **kw)
             tr1 = []
             v1, e1 = sk.kernel_values(cfg1, union, k0=k0, trace=tr1)
             vs = np.concatenate([out[r][0, : chunks[r].size].cpu().numpy() for r in range(world)])

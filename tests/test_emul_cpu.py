@@ -205,7 +205,7 @@ def _hk_api(L):
     L.emul_hk_sizes(*[ctypes.byref(v) for v in sz])
     L.emul_hk_plan.restype = ctypes.c_longlong
     L.emul_hk_plan.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_double] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
-    L.emul_hk_fit.argtypes = [ctypes.c_void_p, dp, ctypes.c_longlong, dp, dp, dp]
+    L.emul_hk_fit.argtypes = [ctypes.c_void_p, dp, ctypes.c_int, ctypes.c_longlong, dp, dp, dp]
     L.emul_hk_spread.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_longlong, dp, dp, dp]
     L.emul_hk_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, dp, dp, ctypes.c_longlong, dp, dp]
@@ -225,9 +225,9 @@ def _hk_transform(L, P, tab, nu, no1, buf1, no2, buf2, a, b, xs):
     assert total >= 0
     info = (ctypes.c_int * 5)()
     L.emul_hk_plan_info(H, info)
-    cheb = np.zeros((2, NLEV, NCH))
-    L.emul_hk_fit(H, _ptr(tab), no1.size, _ptr(no1), _ptr(buf1), _ptr(cheb[0]))
-    L.emul_hk_fit(H, _ptr(tab), no2.size, _ptr(no2), _ptr(buf2), _ptr(cheb[1]))
+    cheb = np.zeros((NLEV, NCH, 2))
+    L.emul_hk_fit(H, _ptr(tab), 0, no1.size, _ptr(no1), _ptr(buf1), _ptr(cheb))
+    L.emul_hk_fit(H, _ptr(tab), 1, no2.size, _ptr(no2), _ptr(buf2), _ptr(cheb))
     grid = np.zeros(max(total, 1), dtype=complex)
     for g in range(info[4]):
         nf2, off, D = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_double()

@@ -484,6 +484,24 @@ def test_hankel_fast_path_vs_oracle(sk, derivative, alpha):
     cfg.engine.set_hankel_mode(0)
 
 
+def test_hankel_interp_variants_agree(sk):
+    """k_hankel_interp2 (two targets per thread, 256-bit loads) against k_hankel_interp (the plain restatement of
+    sk_hk_point, interp_mode = 1): the same operations in the same order, so values and error estimates are
+    bit-identical -- dense lags (pairs share a grid window), sparse lags (they do not) and an odd count."""
+    rng = np.random.default_rng(3)
+    S = sk.Matern(1.3, 0.7, 1.1, d=2)
+    for xs in (rng.uniform(0, 1, 300_001), np.concatenate([rng.uniform(0, 2, 700), 10 ** rng.uniform(-6, 0, 300)])):
+        cfg = sk.AdaptiveKernelConfig(S, dim=2, alpha=0.3)
+        cfg.engine.set_hankel_mode(2)
+        k0 = 1.0
+        v0, e0 = sk.kernel_values(cfg, xs, k0=k0)
+        cfg.engine.set_interp_mode(1)
+        v1, e1 = sk.kernel_values(cfg, xs, k0=k0, reuse_targets=True)
+        cfg.engine.set_interp_mode(0)
+        assert cfg.engine.stats()["n_hankel"] > 0
+        assert np.array_equal(v0, v1) and np.array_equal(e0, e1)
+
+
 def test_hankel_full_size_properties(sk):
     """2e6 lags in 2-D (auto mode takes the O(N) transform): closed form at 10 tol, duplicates and input order
     preserved, and a strided subset re-evaluated with the direct Bessel summation agrees."""
