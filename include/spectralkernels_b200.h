@@ -222,7 +222,10 @@ int sk_subinterval_host(sk_ctx *ctx, double a, double b, const double *no1, cons
  * integration by parts with two :cis transforms per rule.  bufa* = wt * (f + w log w f')(no*), bufb* =
  * wt * (w log w f)(no*) built by updatequadbufs! with p = config.p (Jacobi first sub-panel);
  * i0_coef = b^(dim/2+1-alpha) * log(b) * f(b), denom = dim - alpha.  Stages
- * I_k = (I0 - Re A_k + 2 pi x Im B_k) / denom * cmul like sk_subinterval. */
+ * I_k = (I0 - Re A_k + 2 pi x Im B_k) / denom * cmul like sk_subinterval.
+ * With opts->kernel == SK_KERNEL_BESSEL (dim >= 2, :204-221) the two transforms are Bessel sums of orders
+ * opts->nu = dim/2-1 (A) and opts->nu + 1 (B), I0 carries J_nu(2 pi b x) and the result is divided by
+ * x^xdiv_pow: I_k = (I0 - A_k + 2 pi x B_k) / denom * cmul / x^(dim/2-1). */
 int sk_subinterval_logw_host(sk_ctx *ctx, double a, double b, const double *no1, const double *bufa1,
                              const double *bufb1, const double *no2, const double *bufa2, const double *bufb2,
                              const sk_subinterval_opts *opts, double i0_coef, double denom, double *max_abs_diff);

@@ -360,8 +360,9 @@ class Session:
                                              byref(o), byref(out)))
         return out.value
 
-    def subinterval_logw_host(self, a, b, no1, bufa1, bufb1, no2, bufa2, bufb2, cmul, p, i0_coef, denom) -> float:
-        o = SubintervalOpts(float(cmul), float(p), SK_KERNEL_COS, 1, 0, 0, 0.0, None)
+    def subinterval_logw_host(self, a, b, no1, bufa1, bufb1, no2, bufa2, bufb2, cmul, p, i0_coef, denom,
+                              kernel: int = SK_KERNEL_COS, nu: int = 0, xdiv_pow: float = 0.0) -> float:
+        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1, int(nu), 0, float(xdiv_pow), None)
         out = c_double()
         arrs = [_f64(x) for x in (no1, bufa1, bufb1, no2, bufa2, bufb2)]
         self._ck(self._L.sk_subinterval_logw_host(self._h, float(a), float(b), *[_p(x) for x in arrs], byref(o),

@@ -277,8 +277,8 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
                                f"(b - a < 1e-16). Exiting to avoid infinite splitting.")
         if active:
             if origin and cfg.logw:                                              # :186-228, integration by parts
-                if cfg.dim != 1:
-                    raise NotImplementedError("log-weighted origin sub-interval for dim > 1 (src/quadrature.jl:204-221)")
+                if cfg.dim not in (1, 2):
+                    raise NotImplementedError("singularity derivative not implemented in d > 2")   # :222-223
                 f, df = cfg.f, cfg.df
                 if df is None:
                     raise TypeError("logw=true needs df (the derivative of the spectral density)")
@@ -287,8 +287,13 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
                 no1, ba1, no2, ba2 = _host_strengths(cfg, eng, _a, _b, True, integrand=ga)
                 _, bb1, _, bb2 = _host_strengths(cfg, eng, _a, _b, True, integrand=gb)
                 i0 = _b ** (cfg.dim / 2 + 1 - cfg.alpha) * math.log(_b) * _f_scalar(f, _b)      # :189
-                mx = eng.subinterval_logw_host(_a, _b, no1, ba1, bb1, no2, ba2, bb2, cfg.c, cfg.p, i0,
-                                               cfg.dim - cfg.alpha)
+                if cfg.dim == 1:
+                    mx = eng.subinterval_logw_host(_a, _b, no1, ba1, bb1, no2, ba2, bb2, cfg.c, cfg.p, i0,
+                                                   cfg.dim - cfg.alpha)
+                else:                                                            # :204-221: (:J, dim/2-1) and (:J, dim/2)
+                    mx = eng.subinterval_logw_host(_a, _b, no1, ba1, bb1, no2, ba2, bb2, cfg.c, cfg.p, i0,
+                                                   cfg.dim - cfg.alpha, kernel=SK_KERNEL_BESSEL,
+                                                   nu=int(cfg.dim / 2 - 1), xdiv_pow=cfg.dim / 2 - 1)
             elif builtin:
                 mx = eng.subinterval(_a, _b, cfg.c, cfg.p, kernel, cfg.logw, speculate=spec, nu=nu, xdiv_pow=xdiv)
             else:

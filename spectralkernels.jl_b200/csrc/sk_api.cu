@@ -385,10 +385,13 @@ int run_source_side(sk_ctx *c, const SkGeom &G, int nrule, long long M1, const d
 // O(N) nonuniform Hankel transform of the sub-interval's sources at the active targets (sk_hankel.h), staged
 // like the other branches.  Returns SK_ERR_UNSUPPORTED (without touching the staging buffers) when the dyadic
 // scheme does not apply; the caller then takes the direct Bessel summation.
-int hankel_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, long long n_act, long long M1, long long M2) {
+// nu: Bessel order; sbuf1 / sbuf2: strengths over the nodes c->no1 / c->no2; raw != nullptr: write the two rule sums
+// per target (raw[2j + rule].x) instead of staging.
+int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, const double *sbuf2, double cmul, double xdiv,
+                 long long n_act, long long M1, long long M2, sk_cplx *raw) {
   SkHankelPlan H;
   SkHankelGroup *hg = c->h_scal->grp;
-  const long long total = sk_hk_make_plan(c->plan, o->nu, a, b, c->r_lo, c->r_hi, &H, hg);
+  const long long total = sk_hk_make_plan(c->plan, nu, a, b, c->r_lo, c->r_hi, &H, hg);
   if (total < 0 || c->plan.w != 16) return SK_ERR_UNSUPPORTED;
   if (!c->hk_tab_ready) {
     std::vector<double> tab(SK_HK_TAB_SIZE);
@@ -412,14 +415,14 @@ int hankel_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, lo
   LAUNCH_CHECK();
   {
     dim3 grid(SK_HK_NCH, H.q_hi - H.q_lo + 1, 2 * SK_HK_FITSPLIT);
-    k_hankel_fit<<<grid, 256, 0, c->stream>>>(H, c->hk_tab.p, c->no1.p, c->buf1.p, c->no2.p, c->buf2.p, c->hk_lev.p, c->hk_vals.p);
+    k_hankel_fit<<<grid, 256, 0, c->stream>>>(H, c->hk_tab.p, c->no1.p, sbuf1, c->no2.p, sbuf2, c->hk_lev.p, c->hk_vals.p);
     LAUNCH_CHECK();
     k_hankel_cheb<<<nblk(2 * (H.q_hi - H.q_lo + 1) * SK_HK_NCH, 128), 128, 0, c->stream>>>(H, c->hk_vals.p, c->hk_cheb.p);
     LAUNCH_CHECK();
   }
   // asymptotic part: one batched transform (K terms x 2 rules) per group
   SkHkSrc S;
-  S.no[0] = c->no1.p; S.no[1] = c->no2.p; S.buf[0] = c->buf1.p; S.buf[1] = c->buf2.p;
+  S.no[0] = c->no1.p; S.no[1] = c->no2.p; S.buf[0] = sbuf1; S.buf[1] = sbuf2;
   S.pos_hi[0] = c->pos_hi1.p; S.pos_hi[1] = c->pos_hi2.p; S.pos_lo[0] = c->pos_lo1.p; S.pos_lo[1] = c->pos_lo2.p;
   S.cs[0] = c->cs1.p; S.cs[1] = c->cs2.p; S.lam[0] = c->hk_lam1.p; S.lam[1] = c->hk_lam2.p;
   S.M[0] = M1; S.M[1] = M2;
@@ -454,12 +457,12 @@ int hankel_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, lo
   if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
   if (c->interp_mode == 1)     // A/B: one target per thread, 16-byte loads (the plain restatement of sk_hk_point)
     k_hankel_interp<16><<<nblk(n_act, 256), 256, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p, c->hk_cheb.p,
-                                                                 c->uxs.p + c->lo, n_act, o->cmul, o->xdiv_pow,
-                                                                 c->stage.p + c->lo, c->d_red);
+                                                                 c->uxs.p + c->lo, n_act, cmul, xdiv,
+                                                                 c->stage.p + c->lo, c->d_red, raw);
   else
     k_hankel_interp2<16><<<nblk((n_act + 1) / 2, SK_HK_TPB2), SK_HK_TPB2, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p,
-                                                                            c->hk_cheb.p, c->uxs.p + c->lo, n_act, o->cmul,
-                                                                            o->xdiv_pow, c->stage.p + c->lo, c->d_red);
+                                                                            c->hk_cheb.p, c->uxs.p + c->lo, n_act, cmul,
+                                                                            xdiv, c->stage.p + c->lo, c->d_red, raw);
   LAUNCH_CHECK();
   if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
   c->stats.n_hankel++;
@@ -505,7 +508,7 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
   bool hk_timed = false;
   if (bessel && c->hankel_mode != 1 && n_cut > 1 && c->r_lo > 0.0 &&
       (c->hankel_mode == 2 || (M2 * n_cut > (1LL << 29)))) {
-    hk_rc = hankel_stage(c, a, b, o, n_act, M1, M2);
+    hk_rc = hankel_stage(c, a, b, o->nu, c->buf1.p, c->buf2.p, o->cmul, o->xdiv_pow, n_act, M1, M2, nullptr);
     if (hk_rc != SK_OK && hk_rc != SK_ERR_UNSUPPORTED) return hk_rc;
     hk_timed = hk_rc == SK_OK;
   }
@@ -1330,8 +1333,34 @@ int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, c
   L.denom = denom;
   L.b = b;
   const long long n_cut = c->n_act_global > 0 ? c->n_act_global : n_act;
-  const bool fast = (M2 * n_cut > (1LL << 18)) && n_cut > 1;          // src/quadrature.jl:105
-  if (fast) {
+  const bool bessel = o->kernel == SK_KERNEL_BESSEL;                  // dim >= 2: orders nu and nu + 1, :204-221
+  const bool fast = !bessel && (M2 * n_cut > (1LL << 18)) && n_cut > 1;          // src/quadrature.jl:105
+  if (bessel) {
+    if (n_act > 2000000000LL) return fail(c, SK_ERR_ARG, "too many targets");
+    CK(c->dsum.ensure((size_t)n_act * 2));
+    CK(c->dsumB.ensure((size_t)n_act * 2));
+    int hk = SK_ERR_UNSUPPORTED;
+    if (c->hankel_mode != 1 && n_cut > 1 && c->r_lo > 0.0 && o->nu + 1 <= SK_HK_NUMAX &&
+        (c->hankel_mode == 2 || (M2 * n_cut > (1LL << 29)))) {
+      hk = hankel_stage(c, a, b, o->nu, c->buf1.p, c->buf2.p, 1.0, 0.0, n_act, M1, M2, c->dsum.p);
+      if (hk == SK_OK) {
+        CK(cudaStreamSynchronize(c->stream));     // the pinned group table is rewritten by the second plan
+        hk = hankel_stage(c, a, b, o->nu + 1, c->bufb1.p, c->bufb2.p, 1.0, 0.0, n_act, M1, M2, c->dsumB.p);
+      }
+      if (hk != SK_OK && hk != SK_ERR_UNSUPPORTED) return hk;
+    }
+    if (hk != SK_OK) {
+      dim3 grid((unsigned int)n_act, 2);
+      k_direct_bessel<<<grid, 256, 0, c->stream>>>(o->nu, c->no1.p, c->buf1.p, M1, c->no2.p, c->buf2.p, M2, c->uxs.p + c->lo, c->dsum.p);
+      LAUNCH_CHECK();
+      k_direct_bessel<<<grid, 256, 0, c->stream>>>(o->nu + 1, c->no1.p, c->bufb1.p, M1, c->no2.p, c->bufb2.p, M2, c->uxs.p + c->lo, c->dsumB.p);
+      LAUNCH_CHECK();
+      c->stats.n_direct++;
+    }
+    k_bessel_logw_finish<<<nblk(n_act, 256), 256, 0, c->stream>>>(c->dsum.p, c->dsumB.p, c->uxs.p + c->lo, n_act, o->cmul, L,
+                                                                  o->nu, o->xdiv_pow, c->stage.p + c->lo, c->d_red);
+    LAUNCH_CHECK();
+  } else if (fast) {
     SkGeom G;
     if (sk_make_geom(c->plan, a, b, c->r_lo, c->r_hi, &G) != 0) return fail(c, SK_ERR_ARG, "type-3 grid too large");
     rc = run_source_side(c, G, 2, M1, c->buf1.p, nullptr, M2, c->buf2.p, c->fft);

@@ -240,11 +240,18 @@ __global__ void __launch_bounds__(256)
 k_hankel_interp(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHankelPlan H,
                 const SkHankelGroup *__restrict__ groups, const sk_cplx *__restrict__ grid, const double *__restrict__ cheb,
                 const double *__restrict__ xs, long long n, double cmul, double xdiv, sk_cplx *__restrict__ stage,
-                SkReduceOut *__restrict__ red) {
+                SkReduceOut *__restrict__ red, sk_cplx *__restrict__ raw) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double d = 0.0;
   unsigned int fl = 0;
-  if (j < n) {
+  if (j < n && raw) {           // raw sums of both rules, layout of k_direct_bessel: raw[2j + rule].x
+    double f[2];
+    sk_hk_point<W>(P, H, groups, grid, cheb, xs[j], f);
+    sk_cplx o;
+    o.y = 0.0;
+    o.x = f[0]; raw[2 * j] = o;
+    o.x = f[1]; raw[2 * j + 1] = o;
+  } else if (j < n) {
     const double x = xs[j];
     double f[2];
     sk_hk_point<W>(P, H, groups, grid, cheb, x, f);
@@ -282,8 +289,11 @@ __device__ __forceinline__ void sk_hk_interp_pair(const SkEsPlan &P, const SkHan
   const double izB = 1.0 / sk_mul(sk_mul(6.283185307179586, g.w_ref), rB);
   double cA[4] = {0.0, 0.0, 0.0, 0.0}, cB[4] = {0.0, 0.0, 0.0, 0.0};      // (rule0 re, im, rule1 re, im)
   const sk_cplx *gp = grid + (size_t)tA.l0 * (SK_HK_K * 2);
+  // each target keeps its own leading block of terms (sk_hk_nterms), exactly as when evaluated alone
+  const int nA = sk_hk_nterms(H, sk_mul(sk_mul(6.283185307179586, g.w_ref), rA));
+  const int nB = sk_hk_nterms(H, sk_mul(sk_mul(6.283185307179586, g.w_ref), rB));
 #pragma unroll 1
-  for (int n = SK_HK_K - 1; n >= 0; --n) {
+  for (int n = (nA > nB ? nA : nB) - 1; n >= 0; --n) {
     double aA[4] = {0.0, 0.0, 0.0, 0.0}, aB[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < W; ++i) {
@@ -294,12 +304,16 @@ __device__ __forceinline__ void sk_hk_interp_pair(const SkEsPlan &P, const SkHan
       aB[0] = sk_fma(tapB[i], v0, aB[0]); aB[1] = sk_fma(tapB[i], v1, aB[1]);
       aB[2] = sk_fma(tapB[i], v2, aB[2]); aB[3] = sk_fma(tapB[i], v3, aB[3]);
     }
-    const double a0 = sk_fma(-cA[1], izA, aA[0]), a1 = sk_fma(cA[0], izA, aA[1]);
-    const double a2 = sk_fma(-cA[3], izA, aA[2]), a3 = sk_fma(cA[2], izA, aA[3]);
-    cA[0] = a0; cA[1] = a1; cA[2] = a2; cA[3] = a3;
-    const double b0 = sk_fma(-cB[1], izB, aB[0]), b1 = sk_fma(cB[0], izB, aB[1]);
-    const double b2 = sk_fma(-cB[3], izB, aB[2]), b3 = sk_fma(cB[2], izB, aB[3]);
-    cB[0] = b0; cB[1] = b1; cB[2] = b2; cB[3] = b3;
+    if (n < nA) {
+      const double a0 = sk_fma(-cA[1], izA, aA[0]), a1 = sk_fma(cA[0], izA, aA[1]);
+      const double a2 = sk_fma(-cA[3], izA, aA[2]), a3 = sk_fma(cA[2], izA, aA[3]);
+      cA[0] = a0; cA[1] = a1; cA[2] = a2; cA[3] = a3;
+    }
+    if (n < nB) {
+      const double b0 = sk_fma(-cB[1], izB, aB[0]), b1 = sk_fma(cB[0], izB, aB[1]);
+      const double b2 = sk_fma(-cB[3], izB, aB[2]), b3 = sk_fma(cB[2], izB, aB[3]);
+      cB[0] = b0; cB[1] = b1; cB[2] = b2; cB[3] = b3;
+    }
   }
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
@@ -358,8 +372,12 @@ __global__ void __launch_bounds__(SK_HK_TPB2, 3)
 k_hankel_interp2(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHankelPlan H,
                  const SkHankelGroup *__restrict__ groups, const sk_cplx *__restrict__ grid, const double *__restrict__ cheb,
                  const double *__restrict__ xs, long long n, double cmul, double xdiv, sk_cplx *__restrict__ stage,
-                 SkReduceOut *__restrict__ red) {
+                 SkReduceOut *__restrict__ red, sk_cplx *__restrict__ raw) {
   static_assert(SK_HK_NCH % 2 == 0, "the paired Clenshaw loop consumes two coefficients per step");
+  __shared__ unsigned long long s_max;
+  __shared__ unsigned int s_fl, s_cnt;
+  if (threadIdx.x == 0) { s_max = 0ull; s_fl = 0u; s_cnt = 0u; }
+  __syncthreads();
   const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
   double d = 0.0;
   unsigned int fl = 0;
@@ -394,6 +412,13 @@ k_hankel_interp2(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkH
       if (u == 1 && !two) break;
       const double x = u ? xB : xA;
       const double f0 = (u ? fB[0] : fA[0]) + (u ? lB[0] : lA[0]), f1 = (u ? fB[1] : fA[1]) + (u ? lB[1] : lA[1]);
+      if (raw) {
+        sk_cplx o;
+        o.y = 0.0;
+        o.x = f0; raw[2 * (j + u)] = o;
+        o.x = f1; raw[2 * (j + u) + 1] = o;
+        continue;
+      }
       double i1 = sk_mul(f0, cmul), i2 = sk_mul(f1, cmul);
       if (xdiv != 0.0) {
         const double den = pow(x, xdiv);
@@ -403,5 +428,18 @@ k_hankel_interp2(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkH
       sk_stage(i1, i2, 1.0, &stage[j + u], d, fl);
     }
   }
-  sk_block_reduce_maxflags(d, fl, red);
+  // warps finish at very different times (octaves, slow pairs): no block barrier -- every warp folds its maximum
+  // into shared memory and the last one to arrive publishes the block's result
+  d = sk_warp_max(d);
+  fl = __reduce_or_sync(0xffffffffu, fl);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&s_max, (unsigned long long)__double_as_longlong(d));
+    if (fl) atomicOr(&s_fl, fl);
+    __threadfence_block();
+    if (atomicAdd(&s_cnt, 1u) == (blockDim.x >> 5) - 1) {
+      atomicMax(&red->maxbits, atomicMax(&s_max, 0ull));
+      const unsigned int f = atomicOr(&s_fl, 0u);
+      if (f) atomicOr(&red->flags, f);
+    }
+  }
 }

@@ -51,6 +51,7 @@ struct SkHankelPlan {
   double r_hi;               // largest active distance (global over the ranks of a sharded run)
   double cphi, sphi;         // cos, sin of nu pi/2 + pi/4
   double ratio[SK_HK_K];     // a_{n+1}(nu) / a_n(nu) = (4 nu^2 - (2n+1)^2) / (8 (n+1))
+  double zthr[SK_HK_K];      // term n contributes less than 1e-17 once z >= zthr[n] (non-increasing in n >= 1)
 };
 
 // ---- J_nu(z), 0 <= z <= 64, from the table ----------------------------------------------------------
@@ -80,6 +81,13 @@ SK_HD int sk_hk_octave(double r_hi, double r) {
   if (!(r > 0.0)) return 4096;
   const int e = ilogb(r_hi) - ilogb(r);               // r_hi / r in (2^(e-1), 2^(e+1))
   return (r <= ldexp(r_hi, -e)) ? e : e - 1;          // floor(log2(r_hi / r))
+}
+// number of leading terms of the expansion a target needs: every source of its group has z >= z_ref
+SK_HD int sk_hk_nterms(const SkHankelPlan &H, double zref) {
+  int k = 1;
+#pragma unroll
+  for (int n = 1; n < SK_HK_K; ++n) k = (zref < H.zthr[n]) ? n + 1 : k;
+  return k;
 }
 SK_HD int sk_hk_group_of_octave(const SkHankelPlan &H, int t) {
   if (t > H.t_last) return -1;
@@ -183,7 +191,7 @@ SK_HD void sk_hk_interp_point(const SkEsPlan &P, const SkHankelPlan &H, const Sk
   double c0r = 0.0, c0i = 0.0, c1r = 0.0, c1i = 0.0;
   const sk_cplx *gp = grid + (size_t)t.l0 * (SK_HK_K * 2);
 #pragma unroll 1
-  for (int n = SK_HK_K - 1; n >= 0; --n) {
+  for (int n = sk_hk_nterms(H, zref) - 1; n >= 0; --n) {
     double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
 #pragma unroll
     for (int i = 0; i < W; ++i) {

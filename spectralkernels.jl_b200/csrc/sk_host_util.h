@@ -96,6 +96,17 @@ static inline long long sk_hk_make_plan(const SkEsPlan &P, int nu, double a, dou
   H->cphi = std::cos(phi);
   H->sphi = std::sin(phi);
   for (int n = 0; n < SK_HK_K; ++n) H->ratio[n] = (4.0 * nu * nu - (2.0 * n + 1.0) * (2.0 * n + 1.0)) / (8.0 * (n + 1.0));
+  {
+    // |a_n| / z^n <= 1e-17  <=>  z >= (|a_n| 1e17)^(1/n); made non-increasing from the top so that the terms a
+    // target keeps are always a leading block 0 .. k-1
+    double an = 1.0;
+    H->zthr[0] = 1e300;
+    for (int n = 1; n < SK_HK_K; ++n) {
+      an *= H->ratio[n - 1];
+      H->zthr[n] = std::pow(std::fabs(an) * 1e17, 1.0 / n);
+    }
+    for (int n = SK_HK_K - 2; n >= 1; --n) H->zthr[n] = std::fmax(H->zthr[n], H->zthr[n + 1]);
+  }
   H->q_lo = sk_hk_level(H->wT, a);
   H->q_hi = sk_hk_level(H->wT, b);
   if (H->q_hi >= SK_HK_NLEV - 1) return -1;

@@ -665,6 +665,36 @@ k_direct_bessel(int nu, const double *__restrict__ no1, const double *__restrict
   if (threadIdx.x == 0) { sk_cplx o; o.x = sr[0]; o.y = 0.0; sums[(long long)blockIdx.x * 2 + r] = o; }
 }
 
+// log-weighted origin sub-interval for dim >= 2 (src/quadrature.jl:189, :204-227): sumsA / sumsB hold the Bessel
+// sums of orders nu0 = dim/2-1 (integrand f + w log w f') and nu0+1 (integrand w log w f) of both rules;
+// I_k = (I0 - A_k + 2 pi x B_k) / (dim - alpha) with I0 = b^(dim/2+1-alpha) log(b) f(b) J_nu0(2 pi b x), then *c and
+// / x^(dim/2-1) (:250-254)
+__global__ void __launch_bounds__(256)
+k_bessel_logw_finish(const sk_cplx *__restrict__ sumsA, const sk_cplx *__restrict__ sumsB, const double *__restrict__ xs,
+                     long long n, double cmul, const __grid_constant__ SkLogwArgs L, int nu0, double xdiv,
+                     sk_cplx *__restrict__ stage, SkReduceOut *__restrict__ red) {
+  double d = 0.0;
+  unsigned int fl = 0;
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) {
+    const double x = xs[j];
+    const double z = sk_mul(sk_mul(6.283185307179586, L.b), x);
+    const double jv = nu0 == 0 ? j0(z) : (nu0 == 1 ? j1(z) : jn(nu0, z));
+    const double i0 = L.i0_coef * jv;
+    const double tx = 6.283185307179586 * x;
+    const double f1 = ((i0 - sumsA[2 * j].x) + tx * sumsB[2 * j].x) / L.denom;
+    const double f2 = ((i0 - sumsA[2 * j + 1].x) + tx * sumsB[2 * j + 1].x) / L.denom;
+    double i1 = sk_mul(f1, cmul), i2 = sk_mul(f2, cmul);
+    if (xdiv != 0.0) {
+      const double den = pow(x, xdiv);
+      i1 = i1 / den;
+      i2 = i2 / den;
+    }
+    sk_stage(i1, i2, 1.0, &stage[j], d, fl);
+  }
+  sk_block_reduce_maxflags(d, fl, red);
+}
+
 // ---- K5 ---------------------------------------------------------------------------------------------
 // pan = (I, err), stage = (I2, |I2-I1|):  I += I2; err += |I2-I1|   (src/quadrature.jl:261-262).
 // The first accepted sub-interval of a panel is not added at all: the staging buffer BECOMES the panel

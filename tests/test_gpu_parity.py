@@ -484,6 +484,35 @@ def test_hankel_fast_path_vs_oracle(sk, derivative, alpha):
     cfg.engine.set_hankel_mode(0)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_singularity_derivative_logw_dim2(sk, mode):
+    """dK/d alpha in 2-D (logw = true, dim = 2): the integration-by-parts origin sub-interval with Bessel orders 0
+    and 1 (src/quadrature.jl:204-221), through the direct Bessel summation (mode 1) and the O(N) transform (mode 2),
+    against the oracle; and against a central difference in alpha of K itself."""
+    parms = (1.2, 0.8, 1.3)
+    rng = np.random.default_rng(21)
+    xs = np.concatenate([rng.uniform(0, 1.2, 60), 10 ** rng.uniform(-4, 0, 30)])
+    S = sk.Matern(*parms, d=2)
+    Sh = lambda w: cf.matern_sdf(w, parms, d=2)
+    alpha = 0.5
+    k0 = so.compute_k0(so.OracleConfig(Sh, dim=2, alpha=alpha))
+    cfg = sk.AdaptiveKernelConfig(S, df=S.dw, dim=2, alpha=alpha, logw=True)
+    ocfg = so.OracleConfig(Sh, df=S.dw, dim=2, alpha=alpha, logw=True)
+    cfg.engine.set_hankel_mode(mode)
+    tg, to = [], []
+    vg, eg = sk.kernel_values(cfg, xs, k0=k0, param_derivative=True, trace=tg)
+    st = cfg.engine.stats()
+    vo, eo = so.kernel_values(ocfg, xs, k0=k0, param_derivative=True, trace=to)
+    assert (st["n_hankel"] > 0) == (mode == 2)
+    assert np.max(np.abs(vg - vo)) <= 5e-11 * k0
+    assert _trace_key(tg) == _trace_key(to)
+    h = 1e-4
+    kp, _ = sk.kernel_values(sk.AdaptiveKernelConfig(S, dim=2, alpha=alpha + h, tol=1e-11), xs, k0=k0)
+    km, _ = sk.kernel_values(sk.AdaptiveKernelConfig(S, dim=2, alpha=alpha - h, tol=1e-11), xs, k0=k0)
+    assert np.max(np.abs((kp - km) / (2 * h) - vg)) <= 1e-5 * k0
+    cfg.engine.set_hankel_mode(0)
+
+
 def test_hankel_interp_variants_agree(sk):
     """k_hankel_interp2 (two targets per thread, 256-bit loads) against k_hankel_interp (the plain restatement of
     sk_hk_point, interp_mode = 1): the same operations in the same order, so values and error estimates are
