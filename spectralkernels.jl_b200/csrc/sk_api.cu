@@ -148,7 +148,7 @@ struct sk_ctx {
   // nonuniform Hankel transform (dim >= 2): 0 auto, 1 always the direct Bessel summation, 2 always the O(N) scheme
   int hankel_mode = 0;
   bool hk_tab_ready = false;
-  DevBuf<double> hk_tab, hk_vals, hk_cheb, hk_lam1, hk_lam2;
+  DevBuf<double> hk_tab, hk_vals, hk_cheb, hk_loc, hk_lam1, hk_lam2;
   DevBuf<long long> hk_lev;
   DevBuf<SkHankelGroup> hk_groups;
   DevBuf<sk_cplx> hk_grid, hk_part;
@@ -401,6 +401,7 @@ int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, con
     CK(cudaStreamSynchronize(c->stream));
     CK(c->hk_vals.ensure(SK_HK_FITSPLIT * 2 * SK_HK_NLEV * SK_HK_NCH));
     CK(c->hk_cheb.ensure(2 * SK_HK_NLEV * SK_HK_NCH));
+    CK(c->hk_loc.ensure((size_t)SK_HK_NLEV * SK_HK_NSUB * SK_HK_NLOC * 2));
     CK(c->hk_lev.ensure(2 * (SK_HK_NLEV + 1)));
     CK(c->hk_groups.ensure(SK_HK_NGRP));
     c->hk_tab_ready = true;
@@ -418,6 +419,11 @@ int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, con
     k_hankel_fit<<<grid, 256, 0, c->stream>>>(H, c->hk_tab.p, c->no1.p, sbuf1, c->no2.p, sbuf2, c->hk_lev.p, c->hk_vals.p);
     LAUNCH_CHECK();
     k_hankel_cheb<<<nblk(2 * (H.q_hi - H.q_lo + 1) * SK_HK_NCH, 128), 128, 0, c->stream>>>(H, c->hk_vals.p, c->hk_cheb.p);
+    LAUNCH_CHECK();
+    // the levels an octave needs, summed once into a piecewise expansion of the octave
+    const int t_need = sk_hk_octave(c->r_hi, c->r_lo);
+    dim3 gl(SK_HK_NSUB, (t_need < H.q_hi ? t_need : H.q_hi) + 1);
+    k_hankel_local_poly<<<gl, 32, 0, c->stream>>>(H, c->hk_cheb.p, c->hk_loc.p);
     LAUNCH_CHECK();
   }
   // asymptotic part: one batched transform (K terms x 2 rules) per group
@@ -456,12 +462,12 @@ int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, con
   }
   if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
   if (c->interp_mode == 1)     // A/B: one target per thread, 16-byte loads (the plain restatement of sk_hk_point)
-    k_hankel_interp<16><<<nblk(n_act, 256), 256, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p, c->hk_cheb.p,
+    k_hankel_interp<16><<<nblk(n_act, 256), 256, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p, c->hk_loc.p,
                                                                  c->uxs.p + c->lo, n_act, cmul, xdiv,
                                                                  c->stage.p + c->lo, c->d_red, raw);
   else
     k_hankel_interp2<16><<<nblk((n_act + 1) / 2, SK_HK_TPB2), SK_HK_TPB2, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p,
-                                                                            c->hk_cheb.p, c->uxs.p + c->lo, n_act, cmul,
+                                                                            c->hk_loc.p, c->uxs.p + c->lo, n_act, cmul,
                                                                             xdiv, c->stage.p + c->lo, c->d_red, raw);
   LAUNCH_CHECK();
   if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
@@ -827,7 +833,7 @@ int sk_ctx_destroy(sk_ctx *c) {
   c->cs1.release(); c->cs2.release(); c->fft.release(); c->dsum.release();
   c->res.release(); c->pan.release(); c->stage.release();
   c->fftB.release(); c->dsumB.release(); c->bufb1.release(); c->bufb2.release();
-  c->hk_tab.release(); c->hk_vals.release(); c->hk_cheb.release(); c->hk_lam1.release(); c->hk_lam2.release();
+  c->hk_tab.release(); c->hk_vals.release(); c->hk_cheb.release(); c->hk_loc.release(); c->hk_lam1.release(); c->hk_lam2.release();
   c->hk_lev.release(); c->hk_groups.release(); c->hk_grid.release(); c->hk_part.release();
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   if (c->d_ga) cudaFree(c->d_ga);

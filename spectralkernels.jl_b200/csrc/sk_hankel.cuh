@@ -72,6 +72,19 @@ __global__ void k_hankel_cheb(const __grid_constant__ SkHankelPlan H, const doub
   cheb[((size_t)q * SK_HK_NCH + m) * 2 + rule] = sk_hk_cheb_coef(v, m);      // layout [NLEV][NCH][2 rules]
 }
 
+// per-octave piecewise expansions (sk_hk_local2) from the per-level coefficients: grid (SK_HK_NSUB, q_hi + 1),
+// 32 threads = (node or coefficient index, rule)
+__global__ void __launch_bounds__(32)
+k_hankel_local_poly(const __grid_constant__ SkHankelPlan H, const double *__restrict__ cheb, double *__restrict__ loc) {
+  const int s = blockIdx.x, tt = blockIdx.y;
+  __shared__ double vals[SK_HK_NLOC * 2];
+  if (threadIdx.x < SK_HK_NLOC)
+    sk_hk_local(H, cheb, sk_hk_local_node(H, tt, s, threadIdx.x), tt < H.q_hi ? tt : 4096, &vals[2 * threadIdx.x]);
+  __syncthreads();
+  const int m = threadIdx.x >> 1, rule = threadIdx.x & 1;
+  loc[(((size_t)tt * SK_HK_NSUB + s) * SK_HK_NLOC + m) * 2 + rule] = sk_hk_local_coef(vals + rule, m);
+}
+
 struct SkHkSrc {
   const double *no[2];
   const double *buf[2];
@@ -271,7 +284,7 @@ k_hankel_interp(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHa
 // k_hankel_interp above is bound by the L1/LSU path (ncu: l1tex throughput 95 %, FP64 pipe 25 %): one 16-byte
 // load per two FMAs.  Here every thread owns TWO consecutive sorted targets; when they share the group and the
 // grid window (the usual case: ~100 targets per cell) each grid value is fetched once with one 256-bit load
-// and feeds 8 FMAs, and the Chebyshev coefficients of the local levels are fetched four at a time for 8 FMAs.
+// and feeds 8 FMAs.
 // The arithmetic per target is the sequence of sk_hk_point, operation for operation: results are bit-identical
 // to k_hankel_interp whatever the pairing (tests: test_hankel_interp_variants_agree).
 __device__ __forceinline__ void sk_ld256(const void *p, double &a, double &b, double &c, double &d) {
@@ -331,41 +344,6 @@ __device__ __forceinline__ void sk_hk_interp_pair(const SkEsPlan &P, const SkHan
   }
 }
 
-// local levels of two targets of the same octave: 4 Clenshaw recurrences fed by 256-bit coefficient loads
-__device__ __forceinline__ void sk_hk_local_pair(const SkHankelPlan &H, const double *cheb, double rA, double rB, int t,
-                                                 double *outA, double *outB) {
-  outA[0] = outA[1] = outB[0] = outB[1] = 0.0;
-  const int qe = (t + 1 < H.q_hi) ? t + 1 : H.q_hi;
-  for (int q = H.q_lo; q <= qe; ++q) {
-    const double R = sk_hk_level_radius(H.r_hi, q);
-    const double xA = 2.0 * sk_fma(rA, 2.0 / R, -1.0), xB = 2.0 * sk_fma(rB, 2.0 / R, -1.0);
-    const double *c = cheb + (size_t)q * (SK_HK_NCH * 2);
-    double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0, e1 = 0.0, e2 = 0.0, f1 = 0.0, f2 = 0.0;   // A rule0, A rule1, B rule0, B rule1
-#pragma unroll 1
-    for (int j = SK_HK_NCH - 1; j >= 3; j -= 2) {
-      double lo0, lo1, hi0, hi1;                               // c[j-1][0..1], c[j][0..1]
-      sk_ld256(c + 2 * (j - 1), lo0, lo1, hi0, hi1);
-      double a0 = sk_fma(xA, a1, hi0 - a2), b0 = sk_fma(xA, b1, hi1 - b2);
-      double e0 = sk_fma(xB, e1, hi0 - e2), f0 = sk_fma(xB, f1, hi1 - f2);
-      a2 = a1; a1 = a0; b2 = b1; b1 = b0; e2 = e1; e1 = e0; f2 = f1; f1 = f0;
-      a0 = sk_fma(xA, a1, lo0 - a2); b0 = sk_fma(xA, b1, lo1 - b2);
-      e0 = sk_fma(xB, e1, lo0 - e2); f0 = sk_fma(xB, f1, lo1 - f2);
-      a2 = a1; a1 = a0; b2 = b1; b1 = b0; e2 = e1; e1 = e0; f2 = f1; f1 = f0;
-    }
-    double z0, z1, o0, o1;                                     // c[0][0..1], c[1][0..1]
-    sk_ld256(c, z0, z1, o0, o1);
-    {
-      const double a0 = sk_fma(xA, a1, o0 - a2), b0 = sk_fma(xA, b1, o1 - b2);
-      const double e0 = sk_fma(xB, e1, o0 - e2), f0 = sk_fma(xB, f1, o1 - f2);
-      a2 = a1; a1 = a0; b2 = b1; b1 = b0; e2 = e1; e1 = e0; f2 = f1; f1 = f0;
-    }
-    outA[0] += sk_fma(0.5 * xA, a1, z0 - a2);
-    outA[1] += sk_fma(0.5 * xA, b1, z1 - b2);
-    outB[0] += sk_fma(0.5 * xB, e1, z0 - e2);
-    outB[1] += sk_fma(0.5 * xB, f1, z1 - f2);
-  }
-}
-
 #define SK_HK_TPB2 128       // ~160 registers per thread: 3 blocks of 128 threads per SM
 template <int W>
 __global__ void __launch_bounds__(SK_HK_TPB2, 3)
@@ -373,7 +351,6 @@ k_hankel_interp2(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkH
                  const SkHankelGroup *__restrict__ groups, const sk_cplx *__restrict__ grid, const double *__restrict__ cheb,
                  const double *__restrict__ xs, long long n, double cmul, double xdiv, sk_cplx *__restrict__ stage,
                  SkReduceOut *__restrict__ red, sk_cplx *__restrict__ raw) {
-  static_assert(SK_HK_NCH % 2 == 0, "the paired Clenshaw loop consumes two coefficients per step");
   __shared__ unsigned long long s_max;
   __shared__ unsigned int s_fl, s_cnt;
   if (threadIdx.x == 0) { s_max = 0ull; s_fl = 0u; s_cnt = 0u; }
@@ -389,12 +366,8 @@ k_hankel_interp2(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkH
     if (gA >= H.ngroups) gA = -1;
     if (gB >= H.ngroups) gB = -1;
     double fA[2] = {0.0, 0.0}, fB[2] = {0.0, 0.0}, lA[2], lB[2];
-    if (tA == tB) {
-      sk_hk_local_pair(H, cheb, xA, xB, tA, lA, lB);
-    } else {
-      sk_hk_local(H, cheb, xA, tA, lA);
-      sk_hk_local(H, cheb, xB, tB, lB);
-    }
+    sk_hk_local2(H, cheb, xA, tA, lA);
+    sk_hk_local2(H, cheb, xB, tB, lB);
     bool paired = false;
     if (gA >= 0 && gA == gB) {
       const SkTargetCoord cA = sk_target_coord<W>(groups[gA].G, xA), cB = sk_target_coord<W>(groups[gA].G, xB);

@@ -18,7 +18,8 @@
 // partial sum is a band-limited function of r and is replaced by its Chebyshev interpolant of SK_HK_NCH
 // terms on [0, R_q], built from direct sums at the Chebyshev nodes (J_nu from a piecewise-polynomial table on
 // [0, 64] fitted in quad precision).  Nothing is evaluated per (source, target) pair: the work per target is
-// K * 4 * w FMAs (interpolation) plus ~2-3 Clenshaw recurrences.
+// K * 4 * w FMAs (interpolation) plus one short Clenshaw recurrence: the local levels of an octave are summed
+// once per sub-interval into a piecewise expansion of the octave (SK_HK_NSUB pieces x SK_HK_NLOC terms).
 // Octaves t with t+2 <= level(a) see the whole sub-interval [a, b] asymptotically and share one transform.
 #pragma once
 #include "sk_math.h"
@@ -27,6 +28,8 @@
 #define SK_HK_K 12           // terms of the Hankel expansion
 #define SK_HK_NCH 72         // Chebyshev terms per level (z < 2 ZL = 64 needs ~64/2 + 26)
 #define SK_HK_NLEV 48        // dyadic frequency levels
+#define SK_HK_NSUB 16        // pieces per octave of the per-octave local expansion
+#define SK_HK_NLOC 16        // Chebyshev terms per piece (z changes by 2 across a piece: truncation < 1e-18)
 #define SK_HK_NGRP 48        // transforms per sub-interval
 #define SK_HK_NUMAX 3        // tabulated Bessel orders 0..3 (dim <= 6, or dim <= 4 with derivatives)
 #define SK_HK_TAB_INT 32     // table intervals [2i, 2i+2]
@@ -138,6 +141,58 @@ SK_HD void sk_hk_local(const SkHankelPlan &H, const double *cheb, double r, int 
   }
 }
 
+// Per-octave local expansion.  All targets of octave t need the same sum over the levels q <= t+1, a function of r
+// with z < 2 ZL on the octave: it is tabulated once per sub-interval as SK_HK_NSUB pieces of SK_HK_NLOC Chebyshev
+// terms (table index tt = min(t, q_hi); tt = q_hi is the catch-all piece set on [0, r_hi 2^-q_hi], where every
+// level is local and z < ZL).  Per target this replaces ~2-3 recurrences of 72 terms by one of 16.
+SK_HD void sk_hk_local_piece(const SkHankelPlan &H, double r, int t, int *tt, int *sp, double *u) {
+  const int ti = t < H.q_hi ? t : H.q_hi;
+  double v;
+  if (ti < H.q_hi) v = sk_fma(r, 32.0 / ldexp(H.r_hi, -ti), -16.0);     // r in (R/2, R]  ->  (0, 16]
+  else v = r * (16.0 / ldexp(H.r_hi, -H.q_hi));                          // r in (0, Rc]   ->  (0, 16]
+  int s = (int)v;
+  s = s < 0 ? 0 : (s > SK_HK_NSUB - 1 ? SK_HK_NSUB - 1 : s);
+  *tt = ti;
+  *sp = s;
+  *u = 2.0 * (v - (double)s) - 1.0;
+}
+// distance of Chebyshev node i of piece s of table octave tt (the inverse of the map above)
+SK_HD double sk_hk_local_node(const SkHankelPlan &H, int tt, int s, int i) {
+  double sn, cs;
+  sk_sincospi(((double)i + 0.5) / (double)SK_HK_NLOC, &sn, &cs);
+  const double v = (double)s + 0.5 * (cs + 1.0);
+  if (tt < H.q_hi) return (v + 16.0) * (ldexp(H.r_hi, -tt) / 32.0);
+  return v * (ldexp(H.r_hi, -H.q_hi) / 16.0);
+}
+SK_HD double sk_hk_local_coef(const double *vals /*[NLOC], stride 2*/, int m) {
+  double acc = 0.0;
+  for (int i = 0; i < SK_HK_NLOC; ++i) {
+    const int k = (m * (2 * i + 1)) % (4 * SK_HK_NLOC);
+    double s, c;
+    sk_sincospi((double)k / (double)(2 * SK_HK_NLOC), &s, &c);
+    acc = sk_fma(vals[2 * i], c, acc);
+  }
+  return acc * (m == 0 ? 1.0 : 2.0) / (double)SK_HK_NLOC;
+}
+// loc layout [table octave][SK_HK_NSUB][SK_HK_NLOC][2 rules]
+SK_HD void sk_hk_local2(const SkHankelPlan &H, const double *loc, double r, int t, double *out) {
+  int tt, s;
+  double u;
+  sk_hk_local_piece(H, r, t, &tt, &s, &u);
+  const double *c = loc + ((size_t)tt * SK_HK_NSUB + s) * (SK_HK_NLOC * 2);
+  const double x2 = 2.0 * u;
+  double b1 = 0.0, b2 = 0.0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+  for (int j = SK_HK_NLOC - 1; j >= 1; --j) {
+    const double b0 = sk_fma(x2, b1, c[2 * j] - b2);
+    const double d0 = sk_fma(x2, d1, c[2 * j + 1] - d2);
+    b2 = b1; b1 = b0;
+    d2 = d1; d1 = d0;
+  }
+  out[0] = sk_fma(u, b1, c[0] - b2);
+  out[1] = sk_fma(u, d1, c[1] - d2);
+}
+
 // ---- asymptotic part ---------------------------------------------------------------------------------------
 // position on the group's spread grid, term-0 strength c_k (w_ref/w_k)^(1/2) (pre-phased), and the ratio
 // lam = w_ref / w_k that advances the strength from one term to the next
@@ -219,10 +274,10 @@ SK_HD void sk_hk_interp_point(const SkEsPlan &P, const SkHankelPlan &H, const Sk
 // the whole transform at one target (both rules)
 template <int W>
 SK_HD void sk_hk_point(const SkEsPlan &P, const SkHankelPlan &H, const SkHankelGroup *groups, const sk_cplx *grid,
-                       const double *cheb, double r, double *out) {
+                       const double *loctab, double r, double *out) {
   const int t = sk_hk_octave(H.r_hi, r);
   double loc[2];
-  sk_hk_local(H, cheb, r, t, loc);
+  sk_hk_local2(H, loctab, r, t, loc);
   const int gi = sk_hk_group_of_octave(H, t);
   double asy[2] = {0.0, 0.0};
   if (gi >= 0 && gi < H.ngroups) sk_hk_interp_point<W>(P, H, groups[gi], grid + groups[gi].grid_off, r, asy);

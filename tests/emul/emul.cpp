@@ -211,6 +211,19 @@ void emul_hk_fit(const SkHankelPlan *H, const double *tab, int rule, long long M
     for (int m = 0; m < SK_HK_NCH; ++m) cheb[(q * SK_HK_NCH + m) * 2 + rule] = sk_hk_cheb_coef(vals, m);
   }
 }
+// per-octave piecewise expansions from the per-level Chebyshev coefficients: loc[NLEV][NSUB][NLOC][2]
+void emul_hk_local_poly(const SkHankelPlan *H, const double *cheb, double *loc) {
+  std::memset(loc, 0, sizeof(double) * SK_HK_NLEV * SK_HK_NSUB * SK_HK_NLOC * 2);
+  for (int tt = 0; tt <= H->q_hi; ++tt)
+    for (int s = 0; s < SK_HK_NSUB; ++s) {
+      double vals[SK_HK_NLOC * 2];
+      for (int i = 0; i < SK_HK_NLOC; ++i)
+        sk_hk_local(*H, cheb, sk_hk_local_node(*H, tt, s, i), tt < H->q_hi ? tt : 4096, &vals[2 * i]);
+      for (int m = 0; m < SK_HK_NLOC; ++m)
+        for (int rule = 0; rule < 2; ++rule)
+          loc[(((size_t)tt * SK_HK_NSUB + s) * SK_HK_NLOC + m) * 2 + rule] = sk_hk_local_coef(vals + rule, m);
+    }
+}
 // FFT input of group gi for one rule: fft_in[nf2][K][2] (interleaved complex), entries of the other rule untouched
 void emul_hk_spread(const SkEsPlan *P, const SkHankelPlan *H, const SkHankelGroup *groups, int gi, int rule, long long M,
                     const double *no, const double *buf, double *fft_in) {
@@ -230,9 +243,9 @@ void emul_hk_spread(const SkEsPlan *P, const SkHankelPlan *H, const SkHankelGrou
 }
 // all targets: out[N][2]
 void emul_hk_eval(const SkEsPlan *P, const SkHankelPlan *H, const SkHankelGroup *groups, const double *grid,
-                  const double *cheb, long long N, const double *r, double *out) {
+                  const double *loc, long long N, const double *r, double *out) {
 #pragma omp parallel for schedule(static)
   for (long long j = 0; j < N; ++j)
-    sk_hk_point<16>(*P, *H, groups, reinterpret_cast<const sk_cplx *>(grid), cheb, r[j], &out[2 * j]);
+    sk_hk_point<16>(*P, *H, groups, reinterpret_cast<const sk_cplx *>(grid), loc, r[j], &out[2 * j]);
 }
 }

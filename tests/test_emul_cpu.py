@@ -236,8 +236,11 @@ def _hk_transform(L, P, tab, nu, no1, buf1, no2, buf2, a, b, xs):
         L.emul_hk_spread(ctypes.byref(P), H, G, g, 0, no1.size, _ptr(no1), _ptr(buf1), _ptr(fin.view(float)))
         L.emul_hk_spread(ctypes.byref(P), H, G, g, 1, no2.size, _ptr(no2), _ptr(buf2), _ptr(fin.view(float)))
         grid[off.value:off.value + nf2.value * K * 2] = (np.fft.ifft(fin, axis=0) * nf2.value).reshape(-1)
+    loc = np.zeros((NLEV, 16, 16, 2))
+    L.emul_hk_local_poly.argtypes = [ctypes.c_void_p, dp, dp]
+    L.emul_hk_local_poly(H, _ptr(cheb), _ptr(loc))
     out = np.zeros((xs.size, 2))
-    L.emul_hk_eval(ctypes.byref(P), H, G, _ptr(grid.view(float)), _ptr(cheb), xs.size, _ptr(xs), _ptr(out))
+    L.emul_hk_eval(ctypes.byref(P), H, G, _ptr(grid.view(float)), _ptr(loc), xs.size, _ptr(xs), _ptr(out))
     return out, list(info)
 
 
