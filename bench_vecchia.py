@@ -1,0 +1,139 @@
+#!/usr/bin/env python
+"""
+BASELINE config 5: the kernel-evaluation stage of a Vecchia GP fit (ext/SpectralKernelsVecchiaExt.jl calls
+gen_kernel, src/model.jl:72-78, once per hyperparameter vector): 1e5 synthetic 2-D locations, KNN-15 conditioning
+sets (scripts/fit_vecchia_demo.jl:40-41) => ~1.36e7 index pairs; B hyperparameter vectors evaluated as independent
+`kernel_values` runs over the SAME pair list, sharded over the GPUs of one box (replica-style sharding, SURVEY 8e:
+one context per GPU, no collective on the data path).  Vecchia.jl itself (the sparse Cholesky) is not part of the
+path and is not built: this measures gen_kernel only.
+
+    python bench_vecchia.py [--gpus N] [--npts 100000] [--batch 24] [--dim 2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench_vecchia.py --gpus N
+
+Per hyperparameter vector: lags of the index pairs are computed, sorted and de-duplicated on the device ONCE
+(sk_targets_set_pairs; later vectors reuse them), the adaptive panel loop runs (dim = 2: J_0 kernel through the O(N)
+nonuniform Hankel transform), and the values come back to pinned host memory in pair order (the flat equivalent of
+the Dict of src/model.jl:77).  One JSON line from rank 0; `value` = pair evaluations per second over all GPUs.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import spectralkernels_jl_b200 as sk  # noqa: E402
+
+
+def knn_pairs(pts: np.ndarray, k: int = 15) -> np.ndarray:
+    """Index pairs of a Vecchia approximation with KNN conditioning: point i is conditioned on (up to) its k nearest
+    predecessors in the given ordering; every pair (j, l), j <= l, inside {i} + cond(i) is needed (the block's
+    covariance matrix).  Pairs with j == l are lag 0."""
+    from scipy.spatial import cKDTree
+    n = pts.shape[0]
+    chunk = 1024
+    jj, ll = np.triu_indices(k + 1)
+    rows = []
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        m = e - s
+        # candidates: the k nearest among the points before the chunk (k-d tree) and the chunk's own points
+        if s > 0:
+            kk = min(k, s)
+            d0, i0 = cKDTree(pts[:s]).query(pts[s:e], k=kk)
+            d0, i0 = d0.reshape(m, kk) ** 2, i0.reshape(m, kk)
+        else:
+            d0, i0 = np.empty((m, 0)), np.empty((m, 0), dtype=np.int64)
+        diff = pts[s:e, None, :] - pts[None, s:e, :]
+        d1 = np.sum(diff * diff, axis=2)
+        d1[np.triu_indices(m)] = np.inf                            # predecessors only (strictly earlier in the chunk)
+        d = np.concatenate([d0, d1], axis=1)
+        idx = np.concatenate([i0, np.broadcast_to(np.arange(s, e), (m, m))], axis=1)
+        kk = min(k, d.shape[1])
+        order = np.argpartition(d, kk - 1, axis=1)[:, :kk] if d.shape[1] > kk else np.broadcast_to(np.arange(kk), (m, kk))
+        dk = np.take_along_axis(d, order, axis=1)
+        ik = np.take_along_axis(idx, order, axis=1)
+        for r in range(m):
+            i = s + r
+            cand = ik[r][np.isfinite(dk[r])]
+            if cand.size == k:
+                continue
+            blk = np.sort(np.append(cand, i))                       # the first k points have fewer predecessors
+            j2, l2 = np.triu_indices(blk.size)
+            rows.append(np.stack([blk[j2], blk[l2]], axis=1))
+        full = np.all(np.isfinite(dk), axis=1) & (dk.shape[1] == k)
+        if np.any(full):
+            blk = np.sort(np.concatenate([ik[full], np.arange(s, e)[full, None]], axis=1), axis=1)     # [nfull, k+1]
+            rows.append(np.stack([blk[:, jj].ravel(), blk[:, ll].ravel()], axis=1))
+    return np.concatenate(rows).astype(np.int64)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--npts", type=int, default=100_000)
+    ap.add_argument("--batch", type=int, default=24, help="hyperparameter vectors in the job (8 x P, P = 3)")
+    ap.add_argument("--dim", type=int, default=2)
+    ap.add_argument("--alpha", type=float, default=0.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0, 1, (args.npts, 2))
+    pairs = knn_pairs(pts)
+    npairs = pairs.shape[0]
+    # B hyperparameter vectors (phi, rho, nu) around (1, 4, 1.5): what an optimiser's line searches / finite
+    # differences over P = 3 parameters ask for
+    hp = np.stack([1.0 + 0.05 * rng.standard_normal(args.batch), 4.0 * np.exp(0.1 * rng.standard_normal(args.batch)),
+                   1.5 + 0.05 * rng.standard_normal(args.batch)], axis=1)
+    mine = list(range(rank, args.batch, world))
+    out = sk.PinnedArray(npairs)
+    eng = sk.Session(local)
+
+    def run(h, reuse):
+        cfg = sk.AdaptiveKernelConfig(sk.Matern(h[0], h[1], h[2], d=args.dim), dim=args.dim, alpha=args.alpha, device=local,
+                                      engine=eng)
+        k0 = sk.compute_k0(cfg)
+        sk.kernel_values(cfg, None, k0=k0, points=pts, pairs=pairs, reuse_targets=reuse, want_errors=False,
+                         out_vals=out.array)
+        return k0
+
+    run(hp[mine[0]], False)                               # warm-up: pair upload + sort + plans
+    run(hp[mine[0]], True)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    first = True
+    for b in mine:
+        k0 = run(hp[b], not first)                        # the first vector of the timed region pays the pair sort
+        first = False
+    dt = time.perf_counter() - t0
+    st = eng.stats()
+    ok = bool(np.all(np.isfinite(out.array)) and abs(out.array[np.flatnonzero(pairs[:, 0] == pairs[:, 1])[0]] - k0) < 1e-12 * abs(k0))
+    if dist is not None:
+        import torch
+        t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps({"config": 5, "workload": f"Vecchia kernel stage: {args.npts} 2-D points, KNN-15 => {npairs} index pairs, "
+                                                   f"{args.batch} hyperparameter vectors (Matern, dim={args.dim}, alpha={args.alpha})",
+                          "metric": "pair evaluations/s (all GPUs)", "value": args.batch * npairs / dt, "n_gpus": world,
+                          "ms_per_vector_per_gpu": 1e3 * dt / len(mine), "seconds": dt, "vectors_per_gpu": len(mine),
+                          "n_pairs": npairs, "n_hankel_last": st["n_hankel"], "subintervals_last": st["n_subintervals"],
+                          "scaling": "strong (fixed batch)", "check_finite_and_k0": ok}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
