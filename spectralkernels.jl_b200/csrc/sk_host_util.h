@@ -7,18 +7,6 @@
 #include <cmath>
 #include <cstring>
 
-static inline long long sk_next235even(long long n) {
-  if (n <= 2) return 2;
-  if (n & 1) ++n;
-  for (;; n += 2) {
-    long long m = n;
-    while (m % 2 == 0) m /= 2;
-    while (m % 3 == 0) m /= 3;
-    while (m % 5 == 0) m /= 5;
-    if (m == 1) return n;
-  }
-}
-
 // Geometry of one type-3 transform: sources in [w_lo, w_hi], targets in [r_lo, r_hi].
 // sigma = 2 for both the spread and the inner type-2 step.
 // Returns 0, or -1 if the grid would be unreasonably large.
@@ -52,14 +40,15 @@ static inline int sk_make_geom(const SkEsPlan &P, double w_lo, double w_hi, doub
   if (nf & 1) ++nf;
   if (nf < 2 * P.w) nf = 2 * P.w;
   G->nf = nf;
-  // FFT size: oversampling >= 1.999 (the deconvolution fit covers up to 2/1.996; the kernel's aliasing error
-  // is flat around sigma = 2).  cuFFT is ~3x faster on powers of two than on sizes with large 3^k factors, so a
-  // power of two is taken whenever it costs less than 25 % extra length -- the adaptive driver's default
-  // geometry (nf = 131 090) lands on 2^18 instead of 262 440 = 2^3 3^8 5.
+  // FFT size: oversampling >= 1.999 (the deconvolution fit covers up to 2/1.996; the kernel's aliasing error is flat
+  // around sigma = 2), rounded up to the next 2^k or 3*2^(k-1).  cuFFT is ~3x faster on such sizes than on sizes
+  // with large 3^k 5^l factors, and -- as important for a fitting loop, where every hyperparameter vector moves the
+  // panel ends a little -- the set of sizes is small, so cuFFT plans (tens of ms to create) are reused instead of
+  // being rebuilt for every new geometry.  The adaptive driver's default geometry (nf = 131 090) lands on 2^18.
   const long long need = (long long)std::ceil(1.999 * (double)nf);
   long long pow2 = 2;
   while (pow2 < need) pow2 <<= 1;
-  G->nf2 = ((double)pow2 <= 1.25 * (double)need) ? pow2 : sk_next235even(need);
+  G->nf2 = (pow2 >= 8 && 3 * (pow2 / 4) >= need) ? 3 * (pow2 / 4) : pow2;
   const double n2 = (double)G->nf2;
   G->kap_hi = n2 / G->inv_hu;
   G->kap_lo = -std::fma(G->kap_hi, G->inv_hu, -n2) / G->inv_hu;

@@ -38,7 +38,7 @@ struct SkGeom {
   double kap_lo;
   double t_cell;      // (pi w / nf2) / ximax : normalised deconvolution argument per fine-grid cell / mode index
   long long nf;       // spread-grid size (even)
-  long long nf2;      // FFT size (even, 2^a 3^b 5^c)
+  long long nf2;      // FFT size (2^k or 3*2^(k-1))
 };
 
 struct SkPanelSpec {     // updatequadbufs! (src/quadrature.jl:49-95) for one sub-interval
