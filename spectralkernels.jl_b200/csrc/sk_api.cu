@@ -465,10 +465,14 @@ int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, con
     k_hankel_interp<16><<<nblk(n_act, 256), 256, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p, c->hk_loc.p,
                                                                  c->uxs.p + c->lo, n_act, cmul, xdiv,
                                                                  c->stage.p + c->lo, c->d_red, raw);
-  else
+  else if (c->interp_mode == 2)   // A/B: two targets per thread, 256-bit loads; bit-identical to mode 1
     k_hankel_interp2<16><<<nblk((n_act + 1) / 2, SK_HK_TPB2), SK_HK_TPB2, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p,
                                                                             c->hk_loc.p, c->uxs.p + c->lo, n_act, cmul,
                                                                             xdiv, c->stage.p + c->lo, c->d_red, raw);
+  else                            // default: cell polynomials across the K terms
+    k_hankel_cells<16><<<nblk(n_act, 256 * SK_HK_CT), 256, 0, c->stream>>>(c->plan, H, c->hk_groups.p, c->hk_grid.p, c->hk_loc.p,
+                                                                          c->uxs.p + c->lo, n_act, cmul, xdiv,
+                                                                          c->stage.p + c->lo, c->d_red, raw);
   LAUNCH_CHECK();
   if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
   c->stats.n_hankel++;

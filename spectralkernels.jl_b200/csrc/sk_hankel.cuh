@@ -416,3 +416,145 @@ k_hankel_interp2(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkH
     }
   }
 }
+
+// ---- K9d, cell polynomials across the K terms (default) ------------------------------------------------------
+// See sk_hankel.h ("cell polynomials across the K terms").  One warp owns SK_HK_CT x 32 consecutive sorted targets
+// and walks them 32 at a time; the lanes whose targets share a cell build that cell's polynomial together in the
+// warp's shared-memory scratch (skipped when the cell is the one already there -- consecutive targets mostly are
+// in the same cell) and then evaluate their targets with four Horner chains.  No block-level cooperation: which
+// targets share a warp never changes the arithmetic of a target, so results are independent of the tiling and
+// of how the targets are sharded over GPUs.  Targets too close to r = 0 for the truncated binomial series
+// (SkHkCell::ok == 0: a few cells of the merged group, and the groups of tiny octaves) take sk_hk_interp_point.
+#define SK_HK_CT 8
+struct SkHkWarpScratch {
+  sk_cplx w[SK_HK_K * SK_HK_NJ];          // weights of term n in power j
+  double gc[SK_HK_NJ][16][4];             // grid values combined over n, per power j
+  double cj[SK_HK_NJ * SK_NC * 4];        // polynomial coefficients per power j
+  double coef[SK_NC * 4];                 // the cell polynomial
+  double dq[4];                           // deconvolution factor at the 4 Chebyshev nodes of the cell
+};
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_hankel_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHankelPlan H,
+               const SkHankelGroup *__restrict__ groups, const sk_cplx *__restrict__ grid, const double *__restrict__ loc,
+               const double *__restrict__ xs, long long n, double cmul, double xdiv, sk_cplx *__restrict__ stage,
+               SkReduceOut *__restrict__ red, sk_cplx *__restrict__ raw) {
+  static_assert(W == 16, "the lane <-> (window point, rule) map of the build assumes 16 taps");
+  __shared__ double sE[(W / 2) * (SK_NC / 2)], sO[(W / 2) * (SK_NC / 2)];
+  __shared__ SkHkWarpScratch sW[8];
+  __shared__ unsigned long long s_max;
+  __shared__ unsigned int s_fl, s_cnt;
+  for (int t = threadIdx.x; t < (W / 2) * (SK_NC / 2); t += blockDim.x) {
+    sE[t] = P.E[t / (SK_NC / 2)][t % (SK_NC / 2)];
+    sO[t] = P.O[t / (SK_NC / 2)][t % (SK_NC / 2)];
+  }
+  if (threadIdx.x == 0) { s_max = 0ull; s_fl = 0u; s_cnt = 0u; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  SkHkWarpScratch &S = sW[wid];
+  const long long base = ((long long)blockIdx.x * 8 + wid) * (32 * SK_HK_CT);
+  int cur_g = -1;
+  long long cur_l0 = -1;
+  double d = 0.0;
+  unsigned int fl = 0;
+#pragma unroll 1
+  for (int u = 0; u < SK_HK_CT; ++u) {
+    const long long j = base + (long long)u * 32 + lane;
+    const bool have = j < n;
+    const double x = have ? xs[j] : 0.0;
+    double f[2] = {0.0, 0.0}, lo[2] = {0.0, 0.0};
+    int gi = -1;
+    SkTargetCoord tc;
+    tc.l0 = -1;
+    tc.s = 0.0;
+    bool cellpath = false;
+    if (have) {
+      const int t = sk_hk_octave(H.r_hi, x);
+      sk_hk_local2(H, loc, x, t, lo);
+      gi = sk_hk_group_of_octave(H, t);
+      if (gi >= H.ngroups) gi = -1;
+      if (gi >= 0) {
+        tc = sk_target_coord<W>(groups[gi].G, x);
+        cellpath = sk_hk_cell_setup<W>(H, groups[gi], tc.l0).ok != 0;
+        if (!cellpath) sk_hk_interp_point<W>(P, H, groups[gi], grid + groups[gi].grid_off, x, f);
+      }
+    }
+    unsigned int remaining = __ballot_sync(0xffffffffu, cellpath);
+    while (remaining) {
+      const int leader = __ffs(remaining) - 1;
+      const int gL = __shfl_sync(0xffffffffu, gi, leader);
+      const long long cellL = __shfl_sync(0xffffffffu, tc.l0, leader);
+      const unsigned int grp = __ballot_sync(0xffffffffu, cellpath && gi == gL && tc.l0 == cellL) & remaining;
+      if (gL != cur_g || cellL != cur_l0) {
+        // ---- build the polynomial of cell (gL, cellL): all 32 lanes ----
+        const SkHankelGroup &g = groups[gL];
+        const sk_cplx *gg = grid + g.grid_off;
+        const SkHkCell c = sk_hk_cell_setup<W>(H, g, cellL);
+        __syncwarp();                                             // the previous cell's evaluations are done
+        for (int it = lane; it < c.nt * SK_HK_NJ; it += 32)
+          sk_hk_cell_weight(H, c, it / SK_HK_NJ, it % SK_HK_NJ, &S.w[it].x, &S.w[it].y);
+        if (lane < 4) {
+          const double node = (lane == 0) ? 0.9238795325112867 : (lane == 1) ? 0.3826834323650898
+                            : (lane == 2) ? -0.3826834323650898 : -0.9238795325112867;
+          S.dq[lane] = sk_deconv(P, g.G.t_cell * fabs(c.ymid - 0.5 * node));
+        }
+        __syncwarp();
+        {
+          const int i = lane >> 1, rule = lane & 1;              // one (window point, rule) per lane
+          sk_cplx o[SK_HK_NJ];
+          sk_hk_cell_combine(S.w, c.nt, gg + ((size_t)(cellL + i) * SK_HK_K) * 2 + rule, o);
+#pragma unroll
+          for (int jj = 0; jj < SK_HK_NJ; ++jj) { S.gc[jj][i][rule * 2] = o[jj].x; S.gc[jj][i][rule * 2 + 1] = o[jj].y; }
+        }
+        __syncwarp();
+        for (int it = lane; it < SK_HK_NJ * SK_NC * 4; it += 32) {
+          const int comp = it & 3, q = (it >> 2) & (SK_NC - 1), jj = it / (SK_NC * 4);
+          S.cj[it] = sk_cell_coef<W>(sE, sO, &S.gc[jj][0][comp], 4, q);
+        }
+        __syncwarp();
+        for (int it = lane; it < SK_NC * 4; it += 32) S.coef[it] = sk_hk_cell_shift_add(S.cj, it >> 2, it & 3);
+        __syncwarp();
+        if (lane < 4) {
+          double a[4];
+          sk_cheb4_to_monomial(S.dq, a);
+          sk_cell_fold(S.coef + lane, 4, a);
+        }
+        __syncwarp();
+        cur_g = gL;
+        cur_l0 = cellL;
+      }
+      if (grp & (1u << lane)) sk_hk_cell_eval(S.coef, groups[gL].G, x, tc.s, f);
+      remaining &= ~grp;
+    }
+    if (have) {
+      const double f0 = f[0] + lo[0], f1 = f[1] + lo[1];
+      if (raw) {
+        sk_cplx o;
+        o.y = 0.0;
+        o.x = f0; raw[2 * j] = o;
+        o.x = f1; raw[2 * j + 1] = o;
+      } else {
+        double i1 = sk_mul(f0, cmul), i2 = sk_mul(f1, cmul);
+        if (xdiv != 0.0) {
+          const double den = pow(x, xdiv);
+          i1 = i1 / den;
+          i2 = i2 / den;
+        }
+        sk_stage(i1, i2, 1.0, &stage[j], d, fl);
+      }
+    }
+  }
+  d = sk_warp_max(d);
+  fl = __reduce_or_sync(0xffffffffu, fl);
+  if (lane == 0) {
+    atomicMax(&s_max, (unsigned long long)__double_as_longlong(d));
+    if (fl) atomicOr(&s_fl, fl);
+    __threadfence_block();
+    if (atomicAdd(&s_cnt, 1u) == (blockDim.x >> 5) - 1) {
+      atomicMax(&red->maxbits, atomicMax(&s_max, 0ull));
+      const unsigned int ff = atomicOr(&s_fl, 0u);
+      if (ff) atomicOr(&red->flags, ff);
+    }
+  }
+}

@@ -284,3 +284,115 @@ SK_HD void sk_hk_point(const SkEsPlan &P, const SkHankelPlan &H, const SkHankelG
   out[0] = asy[0] + loc[0];
   out[1] = asy[1] + loc[1];
 }
+
+// ---- cell polynomials across the K terms --------------------------------------------------------------------
+// All targets whose w-wide window starts at the same fine-grid index ("cell") see the same 16 x K x 2 grid values,
+// and inside a cell r = r_mid - s h (h = half a cell) moves 1/z by a relative eps = h / r_mid only.  With
+//   (1/z)^(n + 1/2) = z_mid^-(n + 1/2) (1 - eps s)^-(n + 1/2) = z_mid^-(n + 1/2) sum_j beta_{n,j} (eps s)^j
+// truncated at j <= 3 (eps <= 2^-12: the dropped term is < 1e-17 of the sum), the whole expansion
+//   sqrt(2/(pi z)) e^{-i phi} sum_n a_n (i/z)^n sum_i tap_i(s) g_{i,n}
+// becomes ONE complex polynomial of degree 15 in s per rule and cell (layout [SK_NC][4], exactly the cell
+// polynomial of K4, sk_math.h), and a target costs four Horner chains instead of K x 4 x w FMAs.  The 16 x K x 2
+// grid values of the cell are first combined over n for each j (weights w_{n,j}), then turned into polynomial
+// coefficients (sk_cell_coef), shifted-added over j and folded with the deconvolution cubic (sk_cell_fold).
+// Every output item is computed by a fixed formula from the cell's data only, so results do not depend on which
+// thread, warp or GPU evaluates a target.
+#define SK_HK_NJ 4
+#define SK_HK_CELL_MIN 2048.0     // cells between r = 0 and the cell centre: eps = 1 / (2 * that) <= 2^-12
+
+struct SkHkCell {
+  double ymid;      // y at s = 0 (cell centre), y = ymid - s/2
+  double eps;       // relative change of r per unit s
+  double iz_mid;    // 1 / (2 pi w_ref r_mid)
+  int nt;           // leading terms kept (for the smallest z of the cell)
+  int ok;           // eps small enough for the truncated binomial series
+};
+
+template <int W>
+SK_HD SkHkCell sk_hk_cell_setup(const SkHankelPlan &H, const SkHankelGroup &g, long long l0) {
+  SkHkCell c;
+  c.ymid = (double)(l0 - g.G.nf2 / 2) + (0.5 * W - 0.5);
+  const double cfo = sk_fma(g.G.D, g.G.kap_hi, c.ymid);           // cells from the origin r = 0 to the cell centre
+  c.ok = cfo >= SK_HK_CELL_MIN;
+  c.eps = 0.5 / cfo;
+  const double r_mid = cfo / g.G.kap_hi;
+  const double z_mid = sk_mul(sk_mul(6.283185307179586, g.w_ref), r_mid);
+  c.iz_mid = 1.0 / z_mid;
+  c.nt = sk_hk_nterms(H, z_mid * (1.0 - c.eps));                  // s = +1 is the smallest r of the cell
+  return c;
+}
+
+// weight of grid term n in the j-th power of (eps s): amp_mid e^{-i phi} i^n z_mid^-n beta_{n,j} eps^j
+SK_HD void sk_hk_cell_weight(const SkHankelPlan &H, const SkHkCell &c, int n, int j, double *wr, double *wi) {
+  double m = sqrt(0.6366197723675814 * c.iz_mid);                 // sqrt(2 / (pi z_mid))
+  for (int k = 0; k < n; ++k) m *= c.iz_mid;
+  const double e = (double)n + 0.5;
+  double beta = 1.0;
+  for (int k = 0; k < j; ++k) beta = beta * (e + (double)k) / (double)(k + 1) * c.eps;
+  m *= beta;
+  // (cphi - i sphi) i^n
+  double rr = H.cphi, ri = -H.sphi;
+  for (int k = 0; k < (n & 3); ++k) { const double t = rr; rr = -ri; ri = t; }
+  *wr = m * rr;
+  *wi = m * ri;
+}
+
+// combination over n of the grid values at window point i of one rule, for the SK_HK_NJ powers:
+// out[j] (complex) = sum_{n < nt} w[n][j] * g[i][n][rule];   w: [SK_HK_K][SK_HK_NJ] complex
+SK_HD void sk_hk_cell_combine(const sk_cplx *w, int nt, const sk_cplx *gpoint /* &grid[((l0+i) K + 0) 2 + rule] */, sk_cplx *out) {
+  for (int j = 0; j < SK_HK_NJ; ++j) out[j].x = out[j].y = 0.0;
+  for (int n = 0; n < nt; ++n) {
+    const sk_cplx gv = gpoint[n * 2];
+#pragma unroll
+    for (int j = 0; j < SK_HK_NJ; ++j) {
+      const sk_cplx ww = w[n * SK_HK_NJ + j];
+      out[j].x = sk_fma(ww.x, gv.x, sk_fma(-ww.y, gv.y, out[j].x));
+      out[j].y = sk_fma(ww.x, gv.y, sk_fma(ww.y, gv.x, out[j].y));
+    }
+  }
+}
+
+// coefficient q, component comp of the cell polynomial before the deconvolution fold; cj: [SK_HK_NJ][SK_NC][4]
+SK_HD double sk_hk_cell_shift_add(const double *cj, int q, int comp) {
+  double v = cj[q * 4 + comp];
+  if (q >= 1) v += cj[(1 * SK_NC + (q - 1)) * 4 + comp];
+  if (q >= 2) v += cj[(2 * SK_NC + (q - 2)) * 4 + comp];
+  if (q >= 3) v += cj[(3 * SK_NC + (q - 3)) * 4 + comp];
+  return v;
+}
+
+// the whole cell polynomial in one place (plain loops; the warp kernel distributes exactly these items)
+template <int W>
+SK_HD void sk_hk_cell_build(const SkEsPlan &P, const SkHankelPlan &H, const SkHankelGroup &g, const sk_cplx *grid, long long l0,
+                            const double *E, const double *O, double *coef /*[SK_NC][4]*/) {
+  const SkHkCell c = sk_hk_cell_setup<W>(H, g, l0);
+  sk_cplx w[SK_HK_K * SK_HK_NJ];
+  for (int n = 0; n < c.nt; ++n)
+    for (int j = 0; j < SK_HK_NJ; ++j) sk_hk_cell_weight(H, c, n, j, &w[n * SK_HK_NJ + j].x, &w[n * SK_HK_NJ + j].y);
+  double gc[SK_HK_NJ][W][4];
+  for (int i = 0; i < W; ++i)
+    for (int rule = 0; rule < 2; ++rule) {
+      sk_cplx o[SK_HK_NJ];
+      sk_hk_cell_combine(w, c.nt, grid + ((size_t)(l0 + i) * SK_HK_K) * 2 + rule, o);
+      for (int j = 0; j < SK_HK_NJ; ++j) { gc[j][i][rule * 2] = o[j].x; gc[j][i][rule * 2 + 1] = o[j].y; }
+    }
+  double cj[SK_HK_NJ * SK_NC * 4];
+  for (int j = 0; j < SK_HK_NJ; ++j)
+    for (int q = 0; q < SK_NC; ++q)
+      for (int comp = 0; comp < 4; ++comp) cj[(j * SK_NC + q) * 4 + comp] = sk_cell_coef<W>(E, O, &gc[j][0][comp], 4, q);
+  for (int q = 0; q < SK_NC; ++q)
+    for (int comp = 0; comp < 4; ++comp) coef[q * 4 + comp] = sk_hk_cell_shift_add(cj, q, comp);
+  double a[4];
+  sk_cell_deconv_cubic(P, g.G, c.ymid, a);
+  for (int comp = 0; comp < 4; ++comp) sk_cell_fold(coef + comp, 4, a);
+}
+
+// one target through its cell polynomial (asymptotic part only): Horner, post-phase, real part
+SK_HD void sk_hk_cell_eval(const double *coef, const SkGeom &G, double r, double s, double *out) {
+  double a[4];
+  sk_cell_horner<4>(coef, s, a);
+  double sn, cs;
+  sk_post_phase(G, r, &sn, &cs);
+  out[0] = sk_fma(a[0], cs, -sk_mul(a[1], sn));
+  out[1] = sk_fma(a[2], cs, -sk_mul(a[3], sn));
+}

@@ -248,4 +248,36 @@ void emul_hk_eval(const SkEsPlan *P, const SkHankelPlan *H, const SkHankelGroup 
   for (long long j = 0; j < N; ++j)
     sk_hk_point<16>(*P, *H, groups, reinterpret_cast<const sk_cplx *>(grid), loc, r[j], &out[2 * j]);
 }
+
+// the cell-polynomial variant (k_hankel_cells): every target builds the polynomial of its cell with the same
+// per-item formulas the warp kernel distributes over its lanes
+void emul_hk_eval_cells(const SkEsPlan *P, const SkHankelPlan *H, const SkHankelGroup *groups, const double *grid,
+                        const double *loc, long long N, const double *r, double *out, long long *ncell_path) {
+  std::vector<double> E(8 * 8), O(8 * 8);
+  for (int i = 0; i < 8; ++i) for (int q = 0; q < 8; ++q) { E[i * 8 + q] = P->E[i][q]; O[i * 8 + q] = P->O[i][q]; }
+  long long cnt = 0;
+#pragma omp parallel for schedule(static) reduction(+ : cnt)
+  for (long long j = 0; j < N; ++j) {
+    const int t = sk_hk_octave(H->r_hi, r[j]);
+    double lo[2], asy[2] = {0.0, 0.0};
+    sk_hk_local2(*H, loc, r[j], t, lo);
+    const int gi = sk_hk_group_of_octave(*H, t);
+    if (gi >= 0 && gi < H->ngroups) {
+      const SkHankelGroup &g = groups[gi];
+      const sk_cplx *gg = reinterpret_cast<const sk_cplx *>(grid) + g.grid_off;
+      const SkTargetCoord tc = sk_target_coord<16>(g.G, r[j]);
+      if (sk_hk_cell_setup<16>(*H, g, tc.l0).ok) {
+        double coef[SK_NC * 4];
+        sk_hk_cell_build<16>(*P, *H, g, gg, tc.l0, E.data(), O.data(), coef);
+        sk_hk_cell_eval(coef, g.G, r[j], tc.s, asy);
+        ++cnt;
+      } else {
+        sk_hk_interp_point<16>(*P, *H, g, gg, r[j], asy);
+      }
+    }
+    out[2 * j] = asy[0] + lo[0];
+    out[2 * j + 1] = asy[1] + lo[1];
+  }
+  *ncell_path = cnt;
+}
 }

@@ -241,7 +241,15 @@ def _hk_transform(L, P, tab, nu, no1, buf1, no2, buf2, a, b, xs):
     L.emul_hk_local_poly(H, _ptr(cheb), _ptr(loc))
     out = np.zeros((xs.size, 2))
     L.emul_hk_eval(ctypes.byref(P), H, G, _ptr(grid.view(float)), _ptr(loc), xs.size, _ptr(xs), _ptr(out))
-    return out, list(info)
+    # the cell-polynomial variant of the same transform
+    out_c = np.zeros((xs.size, 2))
+    ncell = ctypes.c_longlong()
+    L.emul_hk_eval_cells.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, dp, dp, ctypes.c_longlong, dp, dp,
+                                     ctypes.c_void_p]
+    L.emul_hk_eval_cells(ctypes.byref(P), H, G, _ptr(grid.view(float)), _ptr(loc), xs.size, _ptr(xs), _ptr(out_c),
+                         ctypes.byref(ncell))
+    info = list(info) + [ncell.value, out_c]
+    return out, info
 
 
 def test_bessel_table_and_dyadic_cuts(emul):
@@ -292,7 +300,18 @@ def test_hankel_transform_math(emul, nu, alpha):
             assert info[2] == -1 and info[4] >= 10          # no shared transform; one group per octave
         else:
             assert info[2] >= 10 and info[4] <= 2           # the whole panel is asymptotic for most octaves
+        ncell, got_c = info[5], info[6]
+        assert ncell >= xs.size // 3                         # most targets sit far enough from the origin for the cell path
         for col, (no, buf) in enumerate(((no1, buf1), (no2, buf2))):
             ref = so.direct_bessel(nu, no, buf, xs)
             # the direct sum itself carries ~1e-12 sum|c| (131 072 sequential additions, 2 pi w r rounded)
             assert np.max(np.abs(got[:, col] - ref)) <= 3e-12 * np.sum(np.abs(buf)), (a, col)
+            # cell polynomials across the K terms (k_hankel_cells) against the per-target evaluation
+            assert np.max(np.abs(got_c[:, col] - got[:, col])) <= 2e-14 * np.sum(np.abs(buf)), (a, col)
+        # random strengths: the asymptotic part dominates (a smooth S leaves it at ~1e-5 of the sum)
+        b1, b2 = rng.normal(size=no1.size) / no1.size, rng.normal(size=no2.size) / no2.size
+        xs3 = np.ascontiguousarray(xs[::3])
+        got, info = _hk_transform(L, P, tab, nu, no1, b1, no2, b2, a, b, xs3)
+        ref = so.direct_bessel(nu, no2, b2, xs3)
+        assert np.max(np.abs(got[:, 1] - ref)) <= 5e-15 * np.sum(np.abs(b2))
+        assert np.max(np.abs(info[6][:, 1] - got[:, 1])) <= 1e-15 * np.sum(np.abs(b2))

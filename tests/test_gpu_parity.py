@@ -514,21 +514,25 @@ def test_singularity_derivative_logw_dim2(sk, mode):
 
 
 def test_hankel_interp_variants_agree(sk):
-    """k_hankel_interp2 (two targets per thread, 256-bit loads) against k_hankel_interp (the plain restatement of
-    sk_hk_point, interp_mode = 1): the same operations in the same order, so values and error estimates are
-    bit-identical -- dense lags (pairs share a grid window), sparse lags (they do not) and an odd count."""
+    """The three interpolation kernels of the O(N) Hankel transform.  k_hankel_interp2 (interp_mode 2: two targets per
+    thread, 256-bit loads) executes the operations of k_hankel_interp (mode 1, the plain restatement of sk_hk_point)
+    in the same order: bit-identical.  k_hankel_cells (mode 0, default: one polynomial per cell across the 12 terms)
+    reassociates the sums: agreement at rounding level, <= 1e-14 K(0).  Dense lags, sparse lags, an odd count."""
     rng = np.random.default_rng(3)
     S = sk.Matern(1.3, 0.7, 1.1, d=2)
     for xs in (rng.uniform(0, 1, 300_001), np.concatenate([rng.uniform(0, 2, 700), 10 ** rng.uniform(-6, 0, 300)])):
         cfg = sk.AdaptiveKernelConfig(S, dim=2, alpha=0.3)
         cfg.engine.set_hankel_mode(2)
-        k0 = 1.0
-        v0, e0 = sk.kernel_values(cfg, xs, k0=k0)
-        cfg.engine.set_interp_mode(1)
-        v1, e1 = sk.kernel_values(cfg, xs, k0=k0, reuse_targets=True)
+        k0 = sk.compute_k0(cfg)
+        out = {}
+        for mode in (0, 1, 2):
+            cfg.engine.set_interp_mode(mode)
+            out[mode] = sk.kernel_values(cfg, xs, k0=k0, reuse_targets=mode > 0)
+            assert cfg.engine.stats()["n_hankel"] > 0
         cfg.engine.set_interp_mode(0)
-        assert cfg.engine.stats()["n_hankel"] > 0
-        assert np.array_equal(v0, v1) and np.array_equal(e0, e1)
+        assert np.array_equal(out[1][0], out[2][0]) and np.array_equal(out[1][1], out[2][1])
+        assert np.max(np.abs(out[0][0] - out[1][0])) <= 1e-14 * abs(k0)
+        assert np.max(np.abs(out[0][1] - out[1][1])) <= 1e-14 * abs(k0)
 
 
 def test_hankel_full_size_properties(sk):
