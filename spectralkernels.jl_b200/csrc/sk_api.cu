@@ -399,7 +399,7 @@ int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, con
     CK(c->hk_tab.ensure(SK_HK_TAB_SIZE));
     CK(cudaMemcpyAsync(c->hk_tab.p, tab.data(), sizeof(double) * SK_HK_TAB_SIZE, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    CK(c->hk_vals.ensure(SK_HK_FITSPLIT * 2 * SK_HK_NLEV * SK_HK_NCH));
+    // (allocated per call below: the number of source slices depends on the rule size)
     CK(c->hk_cheb.ensure(2 * SK_HK_NLEV * SK_HK_NCH));
     CK(c->hk_loc.ensure((size_t)SK_HK_NLEV * SK_HK_NSUB * SK_HK_NLOC * 2));
     CK(c->hk_lev.ensure(2 * (SK_HK_NLEV + 1)));
@@ -415,15 +415,17 @@ int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, con
   k_hankel_levels<<<nblk(M1 + M2, 256), 256, 0, c->stream>>>(H.wT, c->no1.p, M1, c->no2.p, M2, c->hk_lev.p);
   LAUNCH_CHECK();
   {
+    CK(c->hk_vals.ensure((size_t)SK_HK_FITSPLIT * 2 * SK_HK_NLEV * SK_HK_NCH));
     dim3 grid(SK_HK_NCH, H.q_hi - H.q_lo + 1, 2 * SK_HK_FITSPLIT);
     k_hankel_fit<<<grid, 256, 0, c->stream>>>(H, c->hk_tab.p, c->no1.p, sbuf1, c->no2.p, sbuf2, c->hk_lev.p, c->hk_vals.p);
     LAUNCH_CHECK();
-    k_hankel_cheb<<<nblk(2 * (H.q_hi - H.q_lo + 1) * SK_HK_NCH, 128), 128, 0, c->stream>>>(H, c->hk_vals.p, c->hk_cheb.p);
+    dim3 gc(H.q_hi - H.q_lo + 1, 2);
+    k_hankel_cheb<<<gc, SK_HK_NCH, 0, c->stream>>>(H, c->hk_vals.p, c->hk_cheb.p);
     LAUNCH_CHECK();
     // the levels an octave needs, summed once into a piecewise expansion of the octave
     const int t_need = sk_hk_octave(c->r_hi, c->r_lo);
     dim3 gl(SK_HK_NSUB, (t_need < H.q_hi ? t_need : H.q_hi) + 1);
-    k_hankel_local_poly<<<gl, 32, 0, c->stream>>>(H, c->hk_cheb.p, c->hk_loc.p);
+    k_hankel_local_poly<<<gl, 256, 0, c->stream>>>(H, c->hk_cheb.p, c->hk_loc.p);
     LAUNCH_CHECK();
   }
   // asymptotic part: one batched transform (K terms x 2 rules) per group

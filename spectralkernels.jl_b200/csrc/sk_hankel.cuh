@@ -30,8 +30,12 @@ __global__ void k_hankel_levels(double wT, const double *__restrict__ no1, long 
     for (int q = l + 1; q <= SK_HK_NLEV; ++q) ls[q] = M;
 }
 
-// grid (SK_HK_NCH nodes, levels q_lo..q_hi, 2 rules x SK_HK_FITSPLIT slices of the level's sources); fixed-order
-// tree reduction per slice, the slices are added in order by k_hankel_cheb (bitwise reproducible)
+// Direct sums of each level at the SK_HK_NCH Chebyshev nodes of its local interval.  grid (SK_HK_NCH nodes, levels
+// q_lo..q_hi, 2 rules x SK_HK_FITSPLIT slices of the level's sources): all threads of a block share the node, so
+// consecutive sources fall into the same interval of the Bessel table (one L1 wavefront per coefficient load).
+// Fixed-order tree reduction per slice, the slices are added in order by k_hankel_cheb: bitwise reproducible.
+// (Measured alternatives, profiles/r1_k: one block per source slice with a thread per node is 8x slower -- the
+// lanes of a warp then hit 32 different table rows; a warp per 8 nodes with lanes over sources is no faster.)
 #define SK_HK_FITSPLIT 8
 __global__ void __launch_bounds__(256)
 k_hankel_fit(const __grid_constant__ SkHankelPlan H, const double *__restrict__ tab, const double *__restrict__ no1,
@@ -56,33 +60,43 @@ k_hankel_fit(const __grid_constant__ SkHankelPlan H, const double *__restrict__ 
   if (threadIdx.x == 0) vals[(((size_t)z * 2 + rule) * SK_HK_NLEV + q) * SK_HK_NCH + i] = sr[0];
 }
 
-__global__ void k_hankel_cheb(const __grid_constant__ SkHankelPlan H, const double *__restrict__ vals,
-                              double *__restrict__ cheb) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nq = H.q_hi - H.q_lo + 1;
-  if (t >= 2 * nq * SK_HK_NCH) return;
-  const int m = t % SK_HK_NCH, q = H.q_lo + (t / SK_HK_NCH) % nq, rule = t / (SK_HK_NCH * nq);
-  const size_t base = ((size_t)rule * SK_HK_NLEV + q) * SK_HK_NCH;
-  double v[SK_HK_NCH];
-  for (int i = 0; i < SK_HK_NCH; ++i) {
-    double a = 0.0;
-    for (int z = 0; z < SK_HK_FITSPLIT; ++z) a += vals[(size_t)z * 2 * SK_HK_NLEV * SK_HK_NCH + base + i];
-    v[i] = a;
-  }
-  cheb[((size_t)q * SK_HK_NCH + m) * 2 + rule] = sk_hk_cheb_coef(v, m);      // layout [NLEV][NCH][2 rules]
+// node values (slices added in order) -> Chebyshev coefficients; grid (levels, 2 rules), SK_HK_NCH threads
+__global__ void __launch_bounds__(SK_HK_NCH)
+k_hankel_cheb(const __grid_constant__ SkHankelPlan H, const double *__restrict__ vals, double *__restrict__ cheb) {
+  const int q = H.q_lo + blockIdx.x, rule = blockIdx.y, i = threadIdx.x;
+  __shared__ double v[SK_HK_NCH];
+  double a = 0.0;
+  for (int z = 0; z < SK_HK_FITSPLIT; ++z) a += vals[(((size_t)z * 2 + rule) * SK_HK_NLEV + q) * SK_HK_NCH + i];
+  v[i] = a;
+  __syncthreads();
+  cheb[((size_t)q * SK_HK_NCH + i) * 2 + rule] = sk_hk_cheb_coef(v, i);       // layout [NLEV][NCH][2 rules]
 }
 
-// per-octave piecewise expansions (sk_hk_local2) from the per-level coefficients: grid (SK_HK_NSUB, q_hi + 1),
-// 32 threads = (node or coefficient index, rule)
-__global__ void __launch_bounds__(32)
+// per-octave piecewise expansions (sk_hk_local2) from the per-level coefficients: grid (SK_HK_NSUB, q_hi + 1);
+// 256 threads = 16 nodes x 16 level lanes: every level's interpolant is evaluated by its own thread, the levels
+// are then added in level order (the order of sk_hk_local)
+__global__ void __launch_bounds__(256)
 k_hankel_local_poly(const __grid_constant__ SkHankelPlan H, const double *__restrict__ cheb, double *__restrict__ loc) {
   const int s = blockIdx.x, tt = blockIdx.y;
+  __shared__ double part[SK_HK_NLEV][SK_HK_NLOC][2];
   __shared__ double vals[SK_HK_NLOC * 2];
-  if (threadIdx.x < SK_HK_NLOC)
-    sk_hk_local(H, cheb, sk_hk_local_node(H, tt, s, threadIdx.x), tt < H.q_hi ? tt : 4096, &vals[2 * threadIdx.x]);
+  const int i = threadIdx.x & (SK_HK_NLOC - 1), ql = threadIdx.x / SK_HK_NLOC;
+  const int t_eff = tt < H.q_hi ? tt : 4096;
+  const int qe = (t_eff + 1 < H.q_hi) ? t_eff + 1 : H.q_hi;
+  const double r = sk_hk_local_node(H, tt, s, i);
+  for (int q = H.q_lo + ql; q <= qe; q += 16) sk_hk_local_level(H, cheb, r, q, part[q][i]);
   __syncthreads();
-  const int m = threadIdx.x >> 1, rule = threadIdx.x & 1;
-  loc[(((size_t)tt * SK_HK_NSUB + s) * SK_HK_NLOC + m) * 2 + rule] = sk_hk_local_coef(vals + rule, m);
+  if (threadIdx.x < SK_HK_NLOC * 2) {
+    const int ii = threadIdx.x >> 1, rule = threadIdx.x & 1;
+    double a = 0.0;
+    for (int q = H.q_lo; q <= qe; ++q) a += part[q][ii][rule];
+    vals[2 * ii + rule] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < SK_HK_NLOC * 2) {
+    const int m = threadIdx.x >> 1, rule = threadIdx.x & 1;
+    loc[(((size_t)tt * SK_HK_NSUB + s) * SK_HK_NLOC + m) * 2 + rule] = sk_hk_local_coef(vals + rule, m);
+  }
 }
 
 struct SkHkSrc {
@@ -443,6 +457,7 @@ k_hankel_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHan
   static_assert(W == 16, "the lane <-> (window point, rule) map of the build assumes 16 taps");
   __shared__ double sE[(W / 2) * (SK_NC / 2)], sO[(W / 2) * (SK_NC / 2)];
   __shared__ SkHkWarpScratch sW[8];
+  __shared__ sk_cplx sTab[65];
   __shared__ unsigned long long s_max;
   __shared__ unsigned int s_fl, s_cnt;
   for (int t = threadIdx.x; t < (W / 2) * (SK_NC / 2); t += blockDim.x) {
@@ -450,6 +465,7 @@ k_hankel_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHan
     sO[t] = P.O[t / (SK_NC / 2)][t % (SK_NC / 2)];
   }
   if (threadIdx.x == 0) { s_max = 0ull; s_fl = 0u; s_cnt = 0u; }
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + 65) sk_sincos2pi_table_fill(sTab, threadIdx.x - 128);
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   SkHkWarpScratch &S = sW[wid];
@@ -476,7 +492,7 @@ k_hankel_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHan
       if (gi >= H.ngroups) gi = -1;
       if (gi >= 0) {
         tc = sk_target_coord<W>(groups[gi].G, x);
-        cellpath = sk_hk_cell_setup<W>(H, groups[gi], tc.l0).ok != 0;
+        cellpath = sk_hk_cell_ok<W>(groups[gi], tc.l0);
         if (!cellpath) sk_hk_interp_point<W>(P, H, groups[gi], grid + groups[gi].grid_off, x, f);
       }
     }
@@ -524,7 +540,7 @@ k_hankel_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHan
         cur_g = gL;
         cur_l0 = cellL;
       }
-      if (grp & (1u << lane)) sk_hk_cell_eval(S.coef, groups[gL].G, x, tc.s, f);
+      if (grp & (1u << lane)) sk_hk_cell_eval(S.coef, sTab, groups[gL].G, x, tc.s, f);
       remaining &= ~grp;
     }
     if (have) {

@@ -121,23 +121,30 @@ SK_HD double sk_hk_cheb_coef(const double *vals, int m) {
   }
   return acc * (m == 0 ? 1.0 : 2.0) / (double)SK_HK_NCH;
 }
-// sum over the local levels of a target in octave t; cheb layout [SK_HK_NLEV][SK_HK_NCH][2 rules]
+// value of level q's interpolant at distance r (both rules); cheb layout [SK_HK_NLEV][SK_HK_NCH][2 rules]
+SK_HD void sk_hk_local_level(const SkHankelPlan &H, const double *cheb, double r, int q, double *out) {
+  const double R = sk_hk_level_radius(H.r_hi, q);
+  const double x2 = 2.0 * sk_fma(r, 2.0 / R, -1.0);             // 2x, x in [-1, 1]
+  const double *c = cheb + (size_t)q * (SK_HK_NCH * 2);
+  double b1 = 0.0, b2 = 0.0, d1 = 0.0, d2 = 0.0;
+  for (int j = SK_HK_NCH - 1; j >= 1; --j) {
+    const double b0 = sk_fma(x2, b1, c[2 * j] - b2);
+    const double d0 = sk_fma(x2, d1, c[2 * j + 1] - d2);
+    b2 = b1; b1 = b0;
+    d2 = d1; d1 = d0;
+  }
+  out[0] = sk_fma(0.5 * x2, b1, c[0] - b2);
+  out[1] = sk_fma(0.5 * x2, d1, c[1] - d2);
+}
+// sum over the local levels of a target in octave t, in level order
 SK_HD void sk_hk_local(const SkHankelPlan &H, const double *cheb, double r, int t, double *out) {
   out[0] = out[1] = 0.0;
   const int qe = (t + 1 < H.q_hi) ? t + 1 : H.q_hi;
   for (int q = H.q_lo; q <= qe; ++q) {
-    const double R = sk_hk_level_radius(H.r_hi, q);
-    const double x2 = 2.0 * sk_fma(r, 2.0 / R, -1.0);             // 2x, x in [-1, 1]
-    const double *c = cheb + (size_t)q * (SK_HK_NCH * 2);
-    double b1 = 0.0, b2 = 0.0, d1 = 0.0, d2 = 0.0;
-    for (int j = SK_HK_NCH - 1; j >= 1; --j) {
-      const double b0 = sk_fma(x2, b1, c[2 * j] - b2);
-      const double d0 = sk_fma(x2, d1, c[2 * j + 1] - d2);
-      b2 = b1; b1 = b0;
-      d2 = d1; d1 = d0;
-    }
-    out[0] += sk_fma(0.5 * x2, b1, c[0] - b2);
-    out[1] += sk_fma(0.5 * x2, d1, c[1] - d2);
+    double v[2];
+    sk_hk_local_level(H, cheb, r, q, v);
+    out[0] += v[0];
+    out[1] += v[1];
   }
 }
 
@@ -308,6 +315,13 @@ struct SkHkCell {
   int ok;           // eps small enough for the truncated binomial series
 };
 
+// only the admission test of sk_hk_cell_setup (what a target needs to know about its cell)
+template <int W>
+SK_HD bool sk_hk_cell_ok(const SkHankelGroup &g, long long l0) {
+  const double ymid = (double)(l0 - g.G.nf2 / 2) + (0.5 * W - 0.5);
+  return sk_fma(g.G.D, g.G.kap_hi, ymid) >= SK_HK_CELL_MIN;
+}
+
 template <int W>
 SK_HD SkHkCell sk_hk_cell_setup(const SkHankelPlan &H, const SkHankelGroup &g, long long l0) {
   SkHkCell c;
@@ -387,12 +401,13 @@ SK_HD void sk_hk_cell_build(const SkEsPlan &P, const SkHankelPlan &H, const SkHa
   for (int comp = 0; comp < 4; ++comp) sk_cell_fold(coef + comp, 4, a);
 }
 
-// one target through its cell polynomial (asymptotic part only): Horner, post-phase, real part
-SK_HD void sk_hk_cell_eval(const double *coef, const SkGeom &G, double r, double s, double *out) {
+// one target through its cell polynomial (asymptotic part only): Horner, post-phase exp(2 pi i wc r) with the
+// product formed exactly and the lean table sincos of K4 (tab: sk_sincos2pi_table_fill), real part
+SK_HD void sk_hk_cell_eval(const double *coef, const sk_cplx *tab, const SkGeom &G, double r, double s, double *out) {
   double a[4];
   sk_cell_horner<4>(coef, s, a);
   double sn, cs;
-  sk_post_phase(G, r, &sn, &cs);
+  sk_sincos2pi(tab, sk_frac_prod(G.wc, r, 0.0), &sn, &cs);
   out[0] = sk_fma(a[0], cs, -sk_mul(a[1], sn));
   out[1] = sk_fma(a[2], cs, -sk_mul(a[3], sn));
 }

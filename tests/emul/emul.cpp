@@ -256,6 +256,8 @@ void emul_hk_eval_cells(const SkEsPlan *P, const SkHankelPlan *H, const SkHankel
   std::vector<double> E(8 * 8), O(8 * 8);
   for (int i = 0; i < 8; ++i) for (int q = 0; q < 8; ++q) { E[i * 8 + q] = P->E[i][q]; O[i * 8 + q] = P->O[i][q]; }
   long long cnt = 0;
+  sk_cplx tab[65];
+  for (int k = 0; k < 65; ++k) sk_sincos2pi_table_fill(tab, k);
 #pragma omp parallel for schedule(static) reduction(+ : cnt)
   for (long long j = 0; j < N; ++j) {
     const int t = sk_hk_octave(H->r_hi, r[j]);
@@ -266,10 +268,10 @@ void emul_hk_eval_cells(const SkEsPlan *P, const SkHankelPlan *H, const SkHankel
       const SkHankelGroup &g = groups[gi];
       const sk_cplx *gg = reinterpret_cast<const sk_cplx *>(grid) + g.grid_off;
       const SkTargetCoord tc = sk_target_coord<16>(g.G, r[j]);
-      if (sk_hk_cell_setup<16>(*H, g, tc.l0).ok) {
+      if (sk_hk_cell_ok<16>(g, tc.l0)) {
         double coef[SK_NC * 4];
         sk_hk_cell_build<16>(*P, *H, g, gg, tc.l0, E.data(), O.data(), coef);
-        sk_hk_cell_eval(coef, g.G, r[j], tc.s, asy);
+        sk_hk_cell_eval(coef, tab, g.G, r[j], tc.s, asy);
         ++cnt;
       } else {
         sk_hk_interp_point<16>(*P, *H, g, gg, r[j], asy);
