@@ -660,7 +660,11 @@ int upload_rule(sk_ctx *c, DevBuf<double> &dst, const double *src, int n) {
   return SK_OK;
 }
 
-int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, bool two_level = true) {
+// sort_bits: radix-sorted key bits of the two-level sort (24: 3 digit passes, for up to ~1.2e7 distances; 32: 4
+// passes); 0: full 63-bit sort (the fall-back when a run of equal sorted bits outgrows the run-rank tile)
+int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, int sort_bits = -1) {
+  if (sort_bits < 0) sort_bits = n_in <= 12000000LL ? 24 : 32;
+  const bool two_level = sort_bits > 0;
   // c->in holds the n_in raw distances
   c->have_targets = false;
   if (n_in > 0x7ffffff0LL) return fail(c, SK_ERR_ARG, "n_in too large");
@@ -706,9 +710,9 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
     int top = 0;                                         // number of low bits that can differ
     while (top < 64 && (varying >> top) != 0ull) ++top;
     const int end_bit = top < 1 ? 1 : top;
-    const int begin_bit = end_bit > 32 ? end_bit - 32 : 0;   // 4 radix passes of 8 bits
+    const int begin_bit = end_bit > sort_bits ? end_bit - sort_bits : 0;   // 3 or 4 radix passes of 8 bits
     CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, begin_bit, end_bit, c->stream));
-    c->stats.kernel_launches += 5;
+    c->stats.kernel_launches += 1 + sort_bits / 8;
     const unsigned long long mask = begin_bit == 0 ? ~0ull : ~((1ull << begin_bit) - 1ull);
     k_run_rank<<<nblk(n_in, SK_RR_TILE), 256, 0, c->stream>>>(dk.Current(), dv.Current(), n_in, mask, dk.Alternate(),
                                                               dv.Alternate(), c->head.p, &c->d_kb->overflow);
@@ -741,7 +745,8 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   CK(cudaStreamSynchronize(c->stream));
   const SkTargetSummary sm = c->h_scal->sum;
   if (sm.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
-  if (two_level && sm.overflow) return targets_from_device_buffer(c, n_in, info, false);   // heavily clustered input
+  if (two_level && sm.overflow)                       // clustered input: more sorted bits, then the full sort
+    return targets_from_device_buffer(c, n_in, info, sort_bits < 32 ? 32 : 0);
   const long long nu = sm.n_unique;
   c->sidx = sidx;                       // sorted position -> original position, for the final scatter
   c->n_in = n_in;
