@@ -18,7 +18,7 @@ import SpectralKernels: AdaptiveKernelConfig, compute_k0, estimate_tail_decay, u
 
 const libsk = get(ENV, "SK_B200_LIB", "libsk_b200.so")
 
-const SK_KERNEL_COS, SK_KERNEL_SIN = Cint(0), Cint(1)
+const SK_KERNEL_COS, SK_KERNEL_SIN, SK_KERNEL_BESSEL = Cint(0), Cint(1), Cint(2)
 const SK_CRIT = Dict(:panel => Cint(0), :tails => Cint(1), :both => Cint(2))
 const SK_SDF_MATERN, SK_SDF_EXPONENTIAL = Cint(1), Cint(2)
 
@@ -95,8 +95,16 @@ function kernel_values_b200(config::AdaptiveKernelConfig, xs::AbstractVector{Flo
   hi, r_hi   = n, (n >= ix1 ? info[].r_max : 0.0)
   conv_crit  = config.convergence_criteria
   (a, b)     = (0.0, 0.0)
-  kernel     = config.derivative ? SK_KERNEL_SIN : SK_KERNEL_COS           # quadrature.jl:177
-  opts       = Ref(SubintervalOpts(config.c, config.p, kernel, config.logw ? 1 : 0, 0, 0, 0.0, C_NULL))
+  dim        = config.dim
+  if dim == 1
+    (kernel, nu, xdiv) = (config.derivative ? SK_KERNEL_SIN : SK_KERNEL_COS, 0, 0.0)   # quadrature.jl:177
+  else
+    # (:J, dim/2) or (:J, dim/2-1), quadrature.jl:179; Int64(...) throws for odd dim as in the reference (:138).
+    # The library replaces FastHankelTransform's nufht (:139-143) by its own O(N) nonuniform Hankel transform
+    # (orders 0..3) and takes the direct Bessel summation (:145-160) for small active sets.
+    (kernel, nu, xdiv) = (SK_KERNEL_BESSEL, Int64(config.derivative ? dim/2 : dim/2 - 1), dim/2 - 1)
+  end
+  opts       = Ref(SubintervalOpts(config.c, config.p, kernel, config.logw ? 1 : 0, nu, 0, xdiv, C_NULL))
   # (optional optimisation, see sk_subinterval_opts.speculate: evaluate estimate_tail_decay(config, a, b)
   #  before the panel and pass pointer_from_objref/Ref of the ScanArgs with the panel's first sub-interval)
   tau        = config.tol*abs(k0)/2
@@ -110,7 +118,26 @@ function kernel_values_b200(config::AdaptiveKernelConfig, xs::AbstractVector{Flo
     while !isempty(stack)
       (_a, _b, _tol) = pop!(stack)
       mx = Ref(0.0)
-      if isnothing(builtin)
+      if _a == 0.0 && config.p != 0.0 && config.logw
+        # log-weighted origin sub-interval by parts (quadrature.jl:186-228): Julia owns f and df and evaluates both
+        # integrands with updatequadbufs!; the device does the transforms (:cis for dim = 1; Bessel orders dim/2-1 and
+        # dim/2 for dim = 2) and I = (I0 - A + 2 pi x B)/(dim - alpha)
+        dim <= 2 || error("singularity derivative not implemented in d > 2")                      # :222-223
+        (f, df) = (config.f, config.df)
+        (no1, ba1, no2, ba2) = updatequadbufs!(config.buffers, config.legrule, config.jacrule,
+                                               w -> f(w) + w*log(w)*df(w), _a, _b; p=config.p)
+        (no1, ra1, no2, ra2) = (copy(no1), real.(ba1), copy(no2), real.(ba2))
+        (_, bb1, _, bb2)     = updatequadbufs!(config.buffers, config.legrule, config.jacrule,
+                                               w -> w*log(w)*f(w), _a, _b; p=config.p)
+        (rb1, rb2) = (real.(bb1), real.(bb2))
+        i0   = _b^(dim/2 + 1 - config.alpha)*log(_b)*f(_b)                                          # :189
+        lopt = Ref(SubintervalOpts(config.c, config.p, dim == 1 ? SK_KERNEL_COS : SK_KERNEL_BESSEL, 1,
+                                   dim == 1 ? 0 : Int64(dim/2 - 1), 0, dim/2 - 1, C_NULL))
+        GC.@preserve no1 ra1 rb1 no2 ra2 rb2 ck(c, ccall((:sk_subinterval_logw_host, libsk), Cint,
+            (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ref{SubintervalOpts}, Float64, Float64, Ref{Float64}),
+            c.h, _a, _b, no1, ra1, rb1, no2, ra2, rb2, lopt, i0, dim - config.alpha, mx))
+      elseif isnothing(builtin)
         origin = (_a == 0.0 && config.p != 0.0)
         f = origin ? config.f : (w -> w^config.p * (config.logw ? log(w) : 1) * config.f(w))
         (no1, buf1, no2, buf2) = updatequadbufs!(config.buffers, config.legrule, config.jacrule, f, _a, _b;
@@ -134,7 +161,6 @@ function kernel_values_b200(config::AdaptiveKernelConfig, xs::AbstractVector{Flo
     ck(c, ccall((:sk_panel_commit, libsk), Cint, (Ptr{Cvoid},), c.h))      # adaptive.jl:163-164
     (cc, d) = (conv_crit == :panel) ? (NaN, NaN) : estimate_tail_decay(config, a, b, d=config.tail)
     if (isnan(cc) || isnan(d)) && conv_crit != :panel; conv_crit = :panel; end
-    dim = config.dim
     sa = conv_crit == :panel ? ScanArgs(0.0, 0.0, (dim+1)/2, tau, SK_CRIT[:panel], 0) :
          ScanArgs(-cc/(d+dim)*b^(d+dim), cc*b^(d+(dim-1)/2), (dim+1)/2, tau, SK_CRIT[conv_crit], 0)
     newhi, rstop = Ref{Int64}(0), Ref(0.0)
