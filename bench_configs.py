@@ -124,7 +124,35 @@ def config2_dim2():
             "max_err_over_k0": float(np.max(np.abs(host_v.array - true)) / k0)}
 
 
+def config2_variants():
+    """SURVEY 8(d) secondary sweeps on config 2 (1e7 distances, Matern nu = 1.5, K(0) = 1, end to end from pinned host
+    memory): sorted-unique input (no sort: separates the K8 cost), r ~ U(0, 1e3) and log-uniform r in [1e-6, 1]
+    (shrinking active sets: more, smaller panels)."""
+    rng = np.random.default_rng(0)
+    n = 10_000_000
+    S = sk.Matern(1.0 / (np.pi / 2), 1.0, 1.5)
+    out = []
+    for name, gen in (("uniform (0,1), unsorted", lambda: rng.uniform(0, 1, n)),
+                      ("uniform (0,1), sorted unique", lambda: np.unique(rng.uniform(0, 1, n))),
+                      ("uniform (0,1e3)", lambda: rng.uniform(0, 1e3, n)),
+                      ("log-uniform [1e-6,1]", lambda: 10 ** rng.uniform(-6, 0, n))):
+        x = gen()
+        pin, hv, he = sk.PinnedArray(x.size), sk.PinnedArray(x.size), sk.PinnedArray(x.size)
+        pin.array[:] = x
+        cfg = sk.AdaptiveKernelConfig(S)
+        tr = []
+        dt, _ = timed(lambda: sk.kernel_values(cfg, pin.array, k0=1.0, out_vals=hv.array, out_errs=he.array, trace=tr),
+                      warm=2, reps=5)
+        st = cfg.engine.stats()
+        true = (1 + 2 * np.pi * x) * np.exp(-2 * np.pi * x)
+        out.append({"input": name, "n": int(x.size), "ms": 1e3 * dt, "evals_per_s": x.size / dt, "units": st["units"],
+                    "subintervals": st["n_subintervals"], "sort_path": st["sort_two_level"],
+                    "panels": [(t["hi_before"], t["hi_after"]) for t in tr if t["kind"] == "panel"][-6:],
+                    "max_err": float(np.max(np.abs(hv.array - true)))})
+    return {"config": "2-variants", "workload": "config 2 secondary sweeps, end to end", "runs": out}
+
+
 if __name__ == "__main__":
     which = [int(a) for a in sys.argv[1:]] or [1, 4, 3]
     for c in which:
-        print(json.dumps({1: config1, 3: config3, 4: config4, 32: config3_dim2, 22: config2_dim2}[c]()), flush=True)
+        print(json.dumps({1: config1, 3: config3, 4: config4, 32: config3_dim2, 22: config2_dim2, 20: config2_variants}[c]()), flush=True)

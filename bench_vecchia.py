@@ -11,8 +11,8 @@ path and is not built: this measures gen_kernel only.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench_vecchia.py --gpus N
 
-Per hyperparameter vector: lags of the index pairs are computed, sorted and de-duplicated on the device ONCE
-(sk_targets_set_pairs; later vectors reuse them), the adaptive panel loop runs (dim = 2: J_0 kernel through the O(N)
+The lags of the index pairs are computed, sorted and de-duplicated on the device ONCE per fit (sk_targets_set_pairs,
+reported as setup); per hyperparameter vector the adaptive panel loop runs (dim = 2: J_0 kernel through the O(N)
 nonuniform Hankel transform), and the values come back to pinned host memory in pair order (the flat equivalent of
 the Dict of src/model.jl:77).  One JSON line from rank 0; `value` = pair evaluations per second over all GPUs.
 """
@@ -78,6 +78,7 @@ def main():
     ap.add_argument("--batch", type=int, default=24, help="hyperparameter vectors in the job (8 x P, P = 3)")
     ap.add_argument("--dim", type=int, default=2)
     ap.add_argument("--alpha", type=float, default=0.0)
+    ap.add_argument("--sync-copies", action="store_true", help="copy results back synchronously (no overlap with the next vector)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -97,29 +98,37 @@ def main():
     hp = np.stack([1.0 + 0.05 * rng.standard_normal(args.batch), 4.0 * np.exp(0.1 * rng.standard_normal(args.batch)),
                    1.5 + 0.05 * rng.standard_normal(args.batch)], axis=1)
     mine = list(range(rank, args.batch, world))
-    out = sk.PinnedArray(npairs)
+    outs = [sk.PinnedArray(npairs), sk.PinnedArray(npairs)]      # double buffered: the copy of vector b overlaps b + 1
     eng = sk.Session(local)
 
-    def run(h, reuse):
+    def run(h, reuse, slot):
         cfg = sk.AdaptiveKernelConfig(sk.Matern(h[0], h[1], h[2], d=args.dim), dim=args.dim, alpha=args.alpha, device=local,
                                       engine=eng)
         k0 = sk.compute_k0(cfg)
         sk.kernel_values(cfg, None, k0=k0, points=pts, pairs=pairs, reuse_targets=reuse, want_errors=False,
-                         out_vals=out.array)
+                         out_vals=outs[slot].array, async_results=not args.sync_copies)
         return k0
 
-    run(hp[mine[0]], False)                               # warm-up: pair upload + sort + plans
-    run(hp[mine[0]], True)
+    ts = time.perf_counter()
+    run(hp[mine[0]], False, 0)                            # once per fit: pair upload, lags, sort / unique (+ plans, tables)
+    eng.results_wait()
+    setup_first = time.perf_counter() - ts
+    ts = time.perf_counter()
+    run(hp[mine[0]], False, 1)                            # the same again, warm: what a new pair list costs
+    eng.results_wait()
+    setup_warm = time.perf_counter() - ts
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
-    first = True
-    for b in mine:
-        k0 = run(hp[b], not first)                        # the first vector of the timed region pays the pair sort
-        first = False
+    for i, b in enumerate(mine):
+        k0 = run(hp[b], True, i & 1)                      # the pair list is resident: only the panel loop and the copy
+        # (a consumer -- Vecchia's sparse Cholesky -- would take outs[(i - 1) & 1] here, complete since the wait
+        #  inside sk_results_get_async two calls back / the final results_wait)
+    eng.results_wait()
     dt = time.perf_counter() - t0
     st = eng.stats()
-    ok = bool(np.all(np.isfinite(out.array)) and abs(out.array[np.flatnonzero(pairs[:, 0] == pairs[:, 1])[0]] - k0) < 1e-12 * abs(k0))
+    last = outs[(len(mine) - 1) & 1].array
+    ok = bool(np.all(np.isfinite(last)) and abs(last[np.flatnonzero(pairs[:, 0] == pairs[:, 1])[0]] - k0) < 1e-12 * abs(k0))
     if dist is not None:
         import torch
         t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
@@ -132,7 +141,9 @@ def main():
                           "metric": "pair evaluations/s (all GPUs)", "value": args.batch * npairs / dt, "n_gpus": world,
                           "ms_per_vector_per_gpu": 1e3 * dt / len(mine), "seconds": dt, "vectors_per_gpu": len(mine),
                           "n_pairs": npairs, "n_hankel_last": st["n_hankel"], "subintervals_last": st["n_subintervals"],
-                          "scaling": "strong (fixed batch)", "check_finite_and_k0": ok}), flush=True)
+                          "setup_ms_first_call": 1e3 * setup_first, "setup_plus_one_vector_ms_warm": 1e3 * setup_warm,
+                          "scaling": "strong (fixed batch)", "result_copies": "sync" if args.sync_copies else "async (second stream)",
+                          "check_finite_and_k0": ok}), flush=True)
 
 
 if __name__ == "__main__":

@@ -248,6 +248,12 @@ int sk_target_upper_index(sk_ctx *ctx, double r, int64_t *idx);
 /* values and errors in the ORIGINAL input order, duplicates included (src/adaptive.jl:105-107);
  * HOST arrays of length n_in; errs may be NULL */
 int sk_results_get(sk_ctx *ctx, double *vals, double *errs);
+/* Asynchronous variant for batched evaluations over the same targets (hyperparameter sweeps of a fitting loop, the
+ * P_sdf + 2 derivative runs of src/derivatives.jl:86-112): the results are gathered on the compute stream and copied
+ * to the (pinned) HOST arrays on a second stream while the next run computes.  Two copies can be in flight; the host
+ * arrays must stay alive and untouched until sk_results_wait returns. */
+int sk_results_get_async(sk_ctx *ctx, double *vals, double *errs);
+int sk_results_wait(sk_ctx *ctx);
 /* same into DEVICE arrays (no PCIe traffic) */
 int sk_results_get_device(sk_ctx *ctx, double *vals_dev, double *errs_dev);
 int sk_stats_get(sk_ctx *ctx, sk_stats *out);

@@ -103,6 +103,8 @@ SIGNATURES = {
     "sk_converge_apply": (c_int, [c_void_p, POINTER(ScanArgs), c_int64]),
     "sk_target_upper_index": (c_int, [c_void_p, c_double, POINTER(c_int64)]),
     "sk_results_get": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "sk_results_get_async": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "sk_results_wait": (c_int, [c_void_p]),
     "sk_results_get_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "sk_stats_get": (c_int, [c_void_p, POINTER(Stats)]),
     "sk_host_gauss_rule": (c_int, [c_int32, c_double, _dp, _dp]),
@@ -399,6 +401,13 @@ class Session:
         errs = (out_errs if out_errs is not None else np.empty(n_in)) if want_errors else None
         self._ck(self._L.sk_results_get(self._h, vals.ctypes.data, errs.ctypes.data if errs is not None else None))
         return vals, errs
+
+    def results_get_async(self, out_vals, out_errs=None):
+        """Gather on the compute stream, copy to the (pinned) host arrays on a second stream; `results_wait` blocks."""
+        self._ck(self._L.sk_results_get_async(self._h, out_vals.ctypes.data, out_errs.ctypes.data if out_errs is not None else None))
+
+    def results_wait(self):
+        self._ck(self._L.sk_results_wait(self._h))
 
     def results_get_device(self, vals_ptr: int, errs_ptr: int = 0):
         self._ck(self._L.sk_results_get_device(self._h, c_void_p(vals_ptr), c_void_p(errs_ptr) if errs_ptr else None))

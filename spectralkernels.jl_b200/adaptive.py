@@ -337,7 +337,7 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
                   verbose: bool = False, trace: Optional[list] = None, comm=None, want_errors: bool = True,
                   out_vals=None, out_errs=None, xs_device: Optional[Tuple[int, int]] = None,
                   out_device: Optional[Tuple[int, int]] = None, reuse_targets: bool = False,
-                  points=None, pairs=None):
+                  points=None, pairs=None, async_results: bool = False):
     """`kernel_values(config, xs; k0, param_derivative, verbose)` (src/adaptive.jl:95-108): returns
     (values, errors) in the order of `xs`, duplicates included.
 
@@ -348,7 +348,9 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
     P_sdf + 2 derivative runs of src/derivatives.jl:86-112 all use the same lags -- so the upload and the
     sort/unique are skipped), `points` (+ optional `pairs`): evaluate at lag = ||points[i] - points[j]|| for the
     given index pairs (default: all i < j), computed on the device (src/model.jl:53-68 with NoWarping); `xs` is
-    ignored and the results come back in pair order."""
+    ignored and the results come back in pair order; `async_results` (with pinned `out_vals` / `out_errs`): return as
+    soon as the copy of the results is queued on the copy stream -- the next kernel_values call on the same engine
+    overlaps with it; `cfg.engine.results_wait()` blocks until the arrays are complete."""
     eng = cfg.engine
     comm = comm or _NoComm()
     if k0 is None:
@@ -475,4 +477,9 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
     if out_device is not None:
         eng.results_get_device(*out_device)
         return None, None
+    if async_results:
+        if out_vals is None:
+            raise ValueError("async_results needs out_vals (pinned host memory)")
+        eng.results_get_async(out_vals, out_errs if want_errors else None)
+        return out_vals, (out_errs if want_errors else None)
     return eng.results_get(n_in, want_errors=want_errors, out_vals=out_vals, out_errs=out_errs)   # :105-107

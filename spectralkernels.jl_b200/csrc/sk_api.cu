@@ -128,6 +128,12 @@ struct sk_ctx {
   long long n_in = 0, n_unique = 0;
   bool has_zero = false;
   DevBuf<double> in, uxs, out_v, out_e;
+  // asynchronous result copies (sk_results_get_async): two slots, a copy stream, events
+  DevBuf<double> aout_v[2], aout_e[2];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_gather[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+  bool copy_pending[2] = {false, false};
+  int aslot = 0;
   DevBuf<sk_cplx> res, pan, stage;   // (ks, errs), (I, err), (I2, |I2-I1|) per unique target
   DevBuf<unsigned long long> keys, keys_alt;
   DevBuf<unsigned int> idx, idx_alt, head, uid, inv;
@@ -844,6 +850,15 @@ int sk_ctx_destroy(sk_ctx *c) {
   c->cs1.release(); c->cs2.release(); c->fft.release(); c->dsum.release();
   c->res.release(); c->pan.release(); c->stage.release();
   c->fftB.release(); c->dsumB.release(); c->bufb1.release(); c->bufb2.release();
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+  }
+  for (int i = 0; i < 2; ++i) {
+    c->aout_v[i].release(); c->aout_e[i].release();
+    if (c->ev_gather[i]) cudaEventDestroy(c->ev_gather[i]);
+    if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+  }
   c->hk_tab.release(); c->hk_vals.release(); c->hk_cheb.release(); c->hk_loc.release(); c->hk_lam1.release(); c->hk_lam2.release();
   c->hk_lev.release(); c->hk_groups.release(); c->hk_grid.release(); c->hk_part.release();
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
@@ -1592,6 +1607,50 @@ int sk_results_get(sk_ctx *c, double *vals, double *errs) {
   CK(cudaMemcpyAsync(vals, c->out_v.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
   if (errs) CK(cudaMemcpyAsync(errs, c->out_e.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  return SK_OK;
+}
+
+// Batched evaluations (hyperparameter sweeps over the same targets): gather on the compute stream, copy on a second
+// stream while the next run computes.
+int sk_results_get_async(sk_ctx *c, double *vals, double *errs) {
+  if (!c || !vals) return SK_ERR_ARG;
+  if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
+  CK(cudaSetDevice(c->device));
+  int rc = rollback_speculation(c);
+  if (rc != SK_OK) return rc;
+  rc = flush_commit(c);
+  if (rc != SK_OK) return rc;
+  if (!c->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&c->ev_gather[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+    }
+  }
+  const int slot = c->aslot;
+  c->aslot ^= 1;
+  if (c->copy_pending[slot]) {                 // the copy issued two runs ago from this slot
+    CK(cudaEventSynchronize(c->ev_copy[slot]));
+    c->copy_pending[slot] = false;
+  }
+  CK(c->aout_v[slot].ensure(c->n_in));
+  if (errs) CK(c->aout_e[slot].ensure(c->n_in));
+  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, c->aout_v[slot].p,
+                                                     errs ? c->aout_e[slot].p : nullptr);
+  LAUNCH_CHECK();
+  CK(cudaEventRecord(c->ev_gather[slot], c->stream));
+  CK(cudaStreamWaitEvent(c->copy_stream, c->ev_gather[slot], 0));
+  CK(cudaMemcpyAsync(vals, c->aout_v[slot].p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->copy_stream));
+  if (errs) CK(cudaMemcpyAsync(errs, c->aout_e[slot].p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->copy_stream));
+  CK(cudaEventRecord(c->ev_copy[slot], c->copy_stream));
+  c->copy_pending[slot] = true;
+  return SK_OK;
+}
+
+int sk_results_wait(sk_ctx *c) {
+  if (!c) return SK_ERR_ARG;
+  if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
+  c->copy_pending[0] = c->copy_pending[1] = false;
   return SK_OK;
 }
 

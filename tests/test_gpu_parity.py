@@ -560,6 +560,34 @@ def test_hankel_full_size_properties(sk):
     assert np.max(np.abs(v[3::4001][order] - vd)) <= 2e-11 * k0
 
 
+def test_async_result_copies(sk):
+    """sk_results_get_async / sk_results_wait: a sweep of hyperparameter vectors over the same targets with the copy of
+    run b overlapping run b + 1 (second stream, two slots) returns exactly what the synchronous copies return."""
+    rng = np.random.default_rng(8)
+    xs = rng.uniform(0, 1, 200_000)
+    eng = sk.Session(0)
+    hp = [(1.0, 1.0 + 0.2 * i, 1.5) for i in range(5)]
+    sync = []
+    for i, h in enumerate(hp):
+        cfg = sk.AdaptiveKernelConfig(sk.Matern(*h), engine=eng)
+        sync.append(sk.kernel_values(cfg, xs, k0=1.0, reuse_targets=i > 0))
+    bufs = [(sk.PinnedArray(xs.size), sk.PinnedArray(xs.size)) for _ in range(2)]
+    got = []
+    for i, h in enumerate(hp):
+        cfg = sk.AdaptiveKernelConfig(sk.Matern(*h), engine=eng)
+        v, e = bufs[i & 1]
+        sk.kernel_values(cfg, xs, k0=1.0, reuse_targets=True, out_vals=v.array, out_errs=e.array, async_results=True)
+        if i >= 1:                          # run i-1's arrays: complete once run i+1 reuses the slot, or after a wait
+            eng.results_wait()
+            pv, pe = bufs[(i - 1) & 1]
+            got.append((pv.array.copy(), pe.array.copy()))
+    eng.results_wait()
+    got.append((bufs[(len(hp) - 1) & 1][0].array.copy(), bufs[(len(hp) - 1) & 1][1].array.copy()))
+    for (sv, se), (gv, ge) in zip(sync, got):
+        assert np.array_equal(sv, gv) and np.array_equal(se, ge)
+    eng.close()
+
+
 def test_errors(sk):
     cfg = sk.AdaptiveKernelConfig(sk.Matern())
     with pytest.raises(sk.SkError):
