@@ -666,11 +666,11 @@ int upload_rule(sk_ctx *c, DevBuf<double> &dst, const double *src, int n) {
   return SK_OK;
 }
 
-// sort_bits: radix-sorted key bits of the two-level sort (24: 3 digit passes, for up to ~1.2e7 distances; 32: 4
-// passes); 0: full 63-bit sort (the fall-back when a run of equal sorted bits outgrows the run-rank tile)
+// sort_bits: radix-sorted key bits of the two-level sort (24 / 32 / 40: 3 / 4 / 5 digit passes); -1: chosen from the
+// key statistics (below); 0: full 63-bit sort (the fall-back when a run of equal sorted bits outgrows the run-rank
+// halo)
 int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, int sort_bits = -1) {
-  if (sort_bits < 0) sort_bits = n_in <= 12000000LL ? 24 : 32;
-  const bool two_level = sort_bits > 0;
+  const bool two_level = sort_bits != 0;
   // c->in holds the n_in raw distances
   c->have_targets = false;
   if (n_in > 0x7ffffff0LL) return fail(c, SK_ERR_ARG, "n_in too large");
@@ -716,6 +716,16 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
     int top = 0;                                         // number of low bits that can differ
     while (top < 64 && (varying >> top) != 0ull) ++top;
     const int end_bit = top < 1 ? 1 : top;
+    if (sort_bits < 0) {
+      // Enough sorted bits for runs of ~32 equal prefixes in the densest binade: the varying exponent bits (5 for
+      // U(0,1); all 11 when the distances straddle 1.0, where the biased exponent carries from 01111111111 to
+      // 10000000000) plus log2(n / 64) mantissa bits.
+      const int nexp = top > 52 ? top - 52 : 0;
+      int lg = 0;
+      while ((1LL << lg) < n_in) ++lg;
+      const int need = nexp + (lg > 6 ? lg - 6 : 0);
+      sort_bits = need <= 24 ? 24 : (need <= 32 ? 32 : 40);
+    }
     const int begin_bit = end_bit > sort_bits ? end_bit - sort_bits : 0;   // 3 or 4 radix passes of 8 bits
     CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, begin_bit, end_bit, c->stream));
     c->stats.kernel_launches += 1 + sort_bits / 8;
@@ -752,7 +762,7 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   const SkTargetSummary sm = c->h_scal->sum;
   if (sm.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
   if (two_level && sm.overflow)                       // clustered input: more sorted bits, then the full sort
-    return targets_from_device_buffer(c, n_in, info, sort_bits < 32 ? 32 : 0);
+    return targets_from_device_buffer(c, n_in, info, sort_bits < 32 ? 32 : (sort_bits < 40 ? 40 : 0));
   const long long nu = sm.n_unique;
   c->sidx = sidx;                       // sorted position -> original position, for the final scatter
   c->n_in = n_in;

@@ -887,19 +887,24 @@ k_run_rank(const unsigned long long *__restrict__ keys, const unsigned int *__re
     const unsigned long long hw = k & mask;
     long long rank = 0;
     bool first = true, over = false;
+    // a run longer than the halo cannot be ranked inside the tile: stop walking there (bounded work per element)
     long long s = i;
-    while (s > lo_g && (sk[s - 1 - g0] & mask) == hw) {
+    const long long s_min = (i - SK_RR_HALO) > lo_g ? (i - SK_RR_HALO) : lo_g;
+    while (s > s_min && (sk[s - 1 - g0] & mask) == hw) {
       --s;
       const unsigned long long o = sk[s - g0];
       if (o <= k) ++rank;                  // earlier position wins ties
       if (o == k) first = false;
     }
+    if (s == s_min && s > 0 && (sk[s - 1 - g0] & mask) == hw && s > lo_g) over = true;   // still inside the run after HALO steps
     if (s == lo_g && s > 0) over = true;   // the run may continue beyond the halo
     long long e = i + 1;
-    while (e < hi_g && (sk[e - g0] & mask) == hw) {
+    const long long e_max = (i + 1 + SK_RR_HALO) < hi_g ? (i + 1 + SK_RR_HALO) : hi_g;
+    while (e < e_max && (sk[e - g0] & mask) == hw) {
       if (sk[e - g0] < k) ++rank;
       ++e;
     }
+    if (e == e_max && e < hi_g && (sk[e - g0] & mask) == hw) over = true;
     if (e == hi_g && e < n) over = true;
     if (over) { atomicOr(overflow, 1u); continue; }
     const long long pos = s + rank;
