@@ -717,13 +717,14 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
     while (top < 64 && (varying >> top) != 0ull) ++top;
     const int end_bit = top < 1 ? 1 : top;
     if (sort_bits < 0) {
-      // Enough sorted bits for runs of ~32 equal prefixes in the densest binade: the varying exponent bits (5 for
-      // U(0,1); all 11 when the distances straddle 1.0, where the biased exponent carries from 01111111111 to
-      // 10000000000) plus log2(n / 64) mantissa bits.
+      // Enough sorted bits for runs of at most ~8 equal prefixes even if every distance fell into one binade
+      // (k_run_rank walks its run: measured, a mean run of 10 costs more than the radix pass it saves): the varying
+      // exponent bits (5 for U(0,1); all 11 when the distances straddle 1.0, where the biased exponent carries from
+      // 01111111111 to 10000000000) plus log2(n) - 3 mantissa bits.
       const int nexp = top > 52 ? top - 52 : 0;
       int lg = 0;
-      while ((1LL << lg) < n_in) ++lg;
-      const int need = nexp + (lg > 6 ? lg - 6 : 0);
+      while ((2LL << lg) <= n_in) ++lg;                  // floor(log2 n)
+      const int need = nexp + (lg > 3 ? lg - 3 : 0);
       sort_bits = need <= 24 ? 24 : (need <= 32 ? 32 : 40);
     }
     const int begin_bit = end_bit > sort_bits ? end_bit - sort_bits : 0;   // 3 or 4 radix passes of 8 bits
