@@ -157,7 +157,7 @@ struct sk_ctx {
   DevBuf<double> hk_tab, hk_vals, hk_cheb, hk_loc, hk_lam1, hk_lam2;
   DevBuf<long long> hk_lev;
   DevBuf<SkHankelGroup> hk_groups;
-  DevBuf<sk_cplx> hk_grid, hk_part;
+  DevBuf<sk_cplx> hk_grid, hk_part, hk_modes;
   bool smem_attr_set[SK_WMAX + 1] = {false};
   // target-sharded multi-GPU: scalar NCCL all-reduces on the context's stream
   ncclComm_t comm = nullptr;
@@ -441,8 +441,17 @@ int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, con
   S.cs[0] = c->cs1.p; S.cs[1] = c->cs2.p; S.lam[0] = c->hk_lam1.p; S.lam[1] = c->hk_lam2.p;
   S.M[0] = M1; S.M[1] = M2;
   if (total > 0) CK(cudaMemsetAsync(c->hk_grid.p, 0, sizeof(sk_cplx) * (size_t)total, c->stream));   // zero padding
-  for (int gi = 0; gi < H.ngroups; ++gi) {
+  // deepest octave first: the groups of a shared set add their own levels to a running mode buffer
+  for (int gi = H.ngroups - 1; gi >= 0; --gi) {
     const SkGeom &G = hg[gi].G;
+    const bool shared = hg[gi].shared != 0;
+    sk_cplx *grid_g = c->hk_grid.p + hg[gi].grid_off;
+    sk_cplx *dst = grid_g;
+    if (shared) {
+      CK(c->hk_modes.ensure((size_t)G.nf2 * 2 * SK_HK_K));
+      if (hg[gi].shared == 1) CK(cudaMemsetAsync(c->hk_modes.p, 0, sizeof(sk_cplx) * (size_t)G.nf2 * 2 * SK_HK_K, c->stream));
+      dst = c->hk_modes.p;
+    }
     k_hankel_prep<<<nblk(M1 + M2, 256), 256, 0, c->stream>>>(c->hk_groups.p, gi, H.wT, S);
     LAUNCH_CHECK();
     // enough blocks to fill the GPU: small grids split each cell block's source range (split-K)
@@ -451,18 +460,18 @@ int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, con
     nsplit = nsplit < 1 ? 1 : (nsplit > 64 ? 64 : nsplit);
     if (nsplit > 1) CK(c->hk_part.ensure((size_t)nsplit * G.nf * 2 * SK_HK_K));
     dim3 grid(bx, 2, nsplit);
-    k_spread_hankel<16><<<grid, 256, 0, c->stream>>>(c->plan, c->hk_groups.p, gi, H, S, c->hk_grid.p, c->hk_part.p);
+    k_spread_hankel<16><<<grid, 256, 0, c->stream>>>(c->plan, c->hk_groups.p, gi, H, S, c->hk_lev.p, dst, shared ? 1 : 0,
+                                                     c->hk_part.p);
     LAUNCH_CHECK();
     if (nsplit > 1) {
       k_spread_hankel_reduce<<<nblk(G.nf * 2 * SK_HK_K, 256), 256, 0, c->stream>>>(c->plan, c->hk_groups.p, gi, nsplit,
-                                                                                  c->hk_part.p, c->hk_grid.p);
+                                                                                  c->hk_part.p, dst, shared ? 1 : 0);
       LAUNCH_CHECK();
     }
     cufftHandle h;
     int rc = get_fft_plan(c, G.nf2, 2 * SK_HK_K, &h);
     if (rc != SK_OK) return rc;
-    cufftDoubleComplex *gp = (cufftDoubleComplex *)(c->hk_grid.p + hg[gi].grid_off);
-    cufftResult fr = cufftExecZ2Z(h, gp, gp, CUFFT_INVERSE);
+    cufftResult fr = cufftExecZ2Z(h, (cufftDoubleComplex *)dst, (cufftDoubleComplex *)grid_g, CUFFT_INVERSE);   // shared: out of place
     if (fr != CUFFT_SUCCESS) return fail(c, SK_ERR_CUFFT, "cufftExecZ2Z failed: %d", (int)fr);
     c->stats.kernel_launches++;
     c->stats.last_nf = G.nf;
@@ -871,7 +880,7 @@ int sk_ctx_destroy(sk_ctx *c) {
     if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
   }
   c->hk_tab.release(); c->hk_vals.release(); c->hk_cheb.release(); c->hk_loc.release(); c->hk_lam1.release(); c->hk_lam2.release();
-  c->hk_lev.release(); c->hk_groups.release(); c->hk_grid.release(); c->hk_part.release();
+  c->hk_lev.release(); c->hk_groups.release(); c->hk_grid.release(); c->hk_part.release(); c->hk_modes.release();
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   if (c->d_ga) cudaFree(c->d_ga);
   if (c->d_gb) cudaFree(c->d_gb);

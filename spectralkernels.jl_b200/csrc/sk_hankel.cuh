@@ -114,8 +114,8 @@ __global__ void k_hankel_prep(const SkHankelGroup *__restrict__ groups, int gi, 
   if (t >= S.M[0] + S.M[1]) return;
   const int rule = t < S.M[0] ? 0 : 1;
   const long long k = rule ? t - S.M[0] : t;
-  sk_hk_source_prep(groups[gi], wT, S.no[rule][k], S.buf[rule][k], &S.pos_hi[rule][k], &S.pos_lo[rule][k], &S.cs[rule][k],
-                    &S.lam[rule][k]);
+  sk_hk_source_prep(groups[gi], wT, groups[gi].q_from, groups[gi].q_to, S.no[rule][k], S.buf[rule][k], &S.pos_hi[rule][k],
+                    &S.pos_lo[rule][k], &S.cs[rule][k], &S.lam[rule][k]);
 }
 
 // Same deterministic gather as k_spread_modes (sk_kernels.cuh), carrying the K terms of the expansion: the
@@ -123,10 +123,10 @@ __global__ void k_hankel_prep(const SkHankelGroup *__restrict__ groups, int gi, 
 template <int W>
 __global__ void __launch_bounds__(256)
 k_spread_hankel(const __grid_constant__ SkEsPlan P, const SkHankelGroup *__restrict__ groups, int gi,
-                const __grid_constant__ SkHankelPlan H, const __grid_constant__ SkHkSrc src, sk_cplx *__restrict__ grid_all,
+                const __grid_constant__ SkHankelPlan H, const __grid_constant__ SkHkSrc src,
+                const long long *__restrict__ lev_start, sk_cplx *__restrict__ fft_io /*FFT input of the group*/, int accumulate,
                 sk_cplx *__restrict__ part /*[gridDim.z][nf][K][2] when gridDim.z > 1*/) {
   const SkGeom G = groups[gi].G;
-  sk_cplx *__restrict__ fft_io = grid_all + groups[gi].grid_off;
   const int r = blockIdx.y;
   const double *__restrict__ ph = src.pos_hi[r];
   const double *__restrict__ pl = src.pos_lo[r];
@@ -152,6 +152,14 @@ k_spread_hankel(const __grid_constant__ SkEsPlan P, const SkHankelGroup *__restr
   // small grids hold many sources per cell: gridDim.z blocks share a cell block's source range (split-K); their
   // partial sums are added in slice order by k_spread_hankel_reduce, so the result stays reproducible
   long long s0 = s_range[0], s1 = s_range[1];
+  {
+    // only the sources of the group's levels [q_from, q_to) (everything else has strength 0)
+    const long long k_lo = lev_start[r * (SK_HK_NLEV + 1) + groups[gi].q_from];
+    const long long k_hi = lev_start[r * (SK_HK_NLEV + 1) + groups[gi].q_to];
+    s0 = s0 > k_lo ? s0 : k_lo;
+    s1 = s1 < k_hi ? s1 : k_hi;
+    if (s1 < s0) s1 = s0;
+  }
   if (gridDim.z > 1) {
     const long long len = (s1 - s0 + gridDim.z - 1) / gridDim.z;
     s0 += (long long)blockIdx.z * len;
@@ -231,7 +239,13 @@ k_spread_hankel(const __grid_constant__ SkEsPlan P, const SkHankelGroup *__restr
       } else {
         o.x = vr * q;
         o.y = vi * q;
-        fft_io[(jout * SK_HK_K + n) * 2 + r] = o;
+        sk_cplx *dst = &fft_io[(jout * SK_HK_K + n) * 2 + r];
+        if (accumulate) {                   // running modes of a shared set: one writer per element, fixed order
+          const sk_cplx prev = *dst;
+          o.x += prev.x;
+          o.y += prev.y;
+        }
+        *dst = o;
       }
     }
   }
@@ -239,9 +253,9 @@ k_spread_hankel(const __grid_constant__ SkEsPlan P, const SkHankelGroup *__restr
 
 // second half of the split-K spread: add the slices in order, deconvolve the mode, write the FFT input
 __global__ void k_spread_hankel_reduce(const __grid_constant__ SkEsPlan P, const SkHankelGroup *__restrict__ groups, int gi,
-                                       int nsplit, const sk_cplx *__restrict__ part, sk_cplx *__restrict__ grid_all) {
+                                       int nsplit, const sk_cplx *__restrict__ part, sk_cplx *__restrict__ fft_io,
+                                       int accumulate) {
   const SkGeom G = groups[gi].G;
-  sk_cplx *__restrict__ fft_io = grid_all + groups[gi].grid_off;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= G.nf * (SK_HK_K * 2)) return;
   const long long l = t / (SK_HK_K * 2);
@@ -259,6 +273,11 @@ __global__ void k_spread_hankel_reduce(const __grid_constant__ SkEsPlan P, const
   sk_cplx o;
   o.x = vr * q;
   o.y = vi * q;
+  if (accumulate) {
+    const sk_cplx prev = fft_io[jout * (SK_HK_K * 2) + nr];
+    o.x += prev.x;
+    o.y += prev.y;
+  }
   fft_io[jout * (SK_HK_K * 2) + nr] = o;
 }
 

@@ -40,9 +40,16 @@ struct SkHankelGroup {       // one batched transform: a suffix of the sources a
   SkGeom G;
   double w_ref;              // strengths carry (w_ref / w)^(n + 1/2), targets (2 pi w_ref r)^(-n - 1/2)
   int q_cut;                 // sources of level >= q_cut belong to the group
-  int _pad;
+  // Incremental spreading.  The groups of the small octaves (t >= SK_HK_T_SHARE) share one geometry and one w_ref;
+  // they are processed from the deepest octave up and each adds only the levels [q_from, q_to) to a running mode
+  // buffer (modes of octave t = modes of octave t+1 + level t+2), which is then transformed into the group's own
+  // grids: one full pass over the sources for the whole set instead of one per octave.  A standalone group has
+  // [q_from, q_to) = [q_cut, SK_HK_NLEV) and shared = 0.
+  int q_from, q_to;
+  int shared;                // 0: standalone; 1: first (deepest) group of the shared set; 2: later group of the set
   long long grid_off;        // offset (in sk_cplx) of the group's grids; layout [nf2][K][2 rules]
 };
+#define SK_HK_T_SHARE 3
 
 struct SkHankelPlan {
   int nu;
@@ -203,9 +210,11 @@ SK_HD void sk_hk_local2(const SkHankelPlan &H, const double *loc, double r, int 
 // ---- asymptotic part ---------------------------------------------------------------------------------------
 // position on the group's spread grid, term-0 strength c_k (w_ref/w_k)^(1/2) (pre-phased), and the ratio
 // lam = w_ref / w_k that advances the strength from one term to the next
-SK_HD void sk_hk_source_prep(const SkHankelGroup &g, double wT, double no, double buf, double *pos_hi, double *pos_lo,
-                             sk_cplx *cs, double *lam) {
-  const bool in = sk_hk_level(wT, no) >= g.q_cut && no > 0.0;
+// (levels [q_from, q_to): the emulation spreads every group in one go and passes [g.q_cut, SK_HK_NLEV))
+SK_HD void sk_hk_source_prep(const SkHankelGroup &g, double wT, int q_from, int q_to, double no, double buf, double *pos_hi,
+                             double *pos_lo, sk_cplx *cs, double *lam) {
+  const int lev = sk_hk_level(wT, no);
+  const bool in = lev >= q_from && lev < q_to && no > 0.0;
   const double l = in ? g.w_ref / no : 0.0;
   sk_source_prep(g.G, no, in ? sk_mul(buf, sqrt(l)) : 0.0, 0.0, pos_hi, pos_lo, &cs->x, &cs->y);
   *lam = l;

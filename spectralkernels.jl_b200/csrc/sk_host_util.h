@@ -104,13 +104,17 @@ static inline long long sk_hk_make_plan(const SkEsPlan &P, int nu, double a, dou
   const int t_need = sk_hk_octave(r_hi, r_lo);
   long long total = 0;
   int ng = 0;
-  auto add = [&](double w_lo, double rl, double rh, double w_ref, int q_cut, bool center) -> bool {
+  auto add = [&](const SkGeom *share, double w_lo, double rl, double rh, double w_ref, int q_cut, bool center) -> bool {
     if (ng >= SK_HK_NGRP) return false;
     SkHankelGroup &g = groups[ng];
     std::memset(&g, 0, sizeof(g));
-    if (sk_make_geom(P, w_lo, b, rl, rh, &g.G, center) != 0) return false;
+    if (share) g.G = *share;
+    else if (sk_make_geom(P, w_lo, b, rl, rh, &g.G, center) != 0) return false;
     g.w_ref = w_ref;
     g.q_cut = q_cut;
+    g.q_from = q_cut;
+    g.q_to = SK_HK_NLEV;
+    g.shared = 0;
     g.grid_off = total;
     total += g.G.nf2 * (long long)(2 * SK_HK_K);
     ++ng;
@@ -119,11 +123,29 @@ static inline long long sk_hk_make_plan(const SkEsPlan &P, int nu, double a, dou
   if (H->t_full >= 0) {
     const int tm = H->t_full < t_need ? H->t_full : t_need;
     const double rl = std::fmax(r_lo, std::ldexp(r_hi, -(tm + 1)));
-    if (!add(a, rl, r_hi, std::ldexp(H->wT, H->q_lo - 1), 0, false)) return -1;
+    if (!add(nullptr, a, rl, r_hi, std::ldexp(H->wT, H->q_lo - 1), 0, false)) return -1;
   }
-  for (int t = H->t_full + 1; t <= H->t_last && t <= t_need; ++t) {
-    const double w_ref = std::ldexp(H->wT, t + 1);               // lower boundary of level t+2
-    if (!add(w_ref, std::ldexp(r_hi, -(t + 1)), std::ldexp(r_hi, -t), w_ref, t + 2, true)) return -1;
+  const int t_first = H->t_full + 1, t_end = H->t_last < t_need ? H->t_last : t_need;      // octaves with own groups
+  // the small octaves share one geometry and one w_ref (see SkHankelGroup): t_share .. t_end
+  const int t_share = t_first > SK_HK_T_SHARE ? t_first : SK_HK_T_SHARE;
+  const bool sharing = t_end - t_share >= 1;
+  SkGeom Gs;
+  double w_ref_s = 0.0;
+  if (sharing) {
+    w_ref_s = std::ldexp(H->wT, t_share + 1);
+    const double rl = std::fmax(r_lo, std::ldexp(r_hi, -(t_end + 1)));
+    if (sk_make_geom(P, w_ref_s, b, rl, std::ldexp(r_hi, -t_share), &Gs, false) != 0) return -1;
+  }
+  for (int t = t_first; t <= t_end; ++t) {
+    if (sharing && t >= t_share) {
+      if (!add(&Gs, 0.0, 0.0, 0.0, w_ref_s, t + 2, false)) return -1;
+      SkHankelGroup &g = groups[ng - 1];
+      g.q_to = (t == t_end) ? SK_HK_NLEV : t + 3;          // the deepest octave takes everything above its cut
+      g.shared = (t == t_end) ? 1 : 2;
+    } else {
+      const double w_ref = std::ldexp(H->wT, t + 1);             // lower boundary of level t+2
+      if (!add(nullptr, w_ref, std::ldexp(r_hi, -(t + 1)), std::ldexp(r_hi, -t), w_ref, t + 2, true)) return -1;
+    }
   }
   H->ngroups = ng;
   if (total > (1LL << 31)) return -1;

@@ -230,7 +230,7 @@ void emul_hk_spread(const SkEsPlan *P, const SkHankelPlan *H, const SkHankelGrou
   const SkHankelGroup &g = groups[gi];
   std::vector<double> ph(M), pl(M), lam(M);
   std::vector<sk_cplx> cs(M);
-  for (long long k = 0; k < M; ++k) sk_hk_source_prep(g, H->wT, no[k], buf[k], &ph[k], &pl[k], &cs[k], &lam[k]);
+  for (long long k = 0; k < M; ++k) sk_hk_source_prep(g, H->wT, g.q_cut, SK_HK_NLEV, no[k], buf[k], &ph[k], &pl[k], &cs[k], &lam[k]);
 #pragma omp parallel for schedule(static)
   for (long long j = 0; j < g.G.nf2; ++j) {
     sk_cplx o[SK_HK_K];
