@@ -188,6 +188,8 @@ def run(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    # one process per GPU: stay on the CPUs (NUMA node) of this rank's GPU before any pinned buffer is allocated
+    numa_bound = sk.bind_to_gpu_cpus(local_rank) if (world > 1 and not os.environ.get("SK_NO_NUMA_BIND")) else False
     comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -305,6 +307,7 @@ def run(args):
                        "parallelism": ("target-sharded, scalar NCCL all-reduces only ("
                                        + ("in-library, on the compute stream" if getattr(comm, "fused", False) else "torch.distributed")
                                        + ")") if world > 1 else "single GPU",
+                       "cpu_affinity": "each rank pinned to its GPU's local CPUs (NVML)" if numa_bound else "default",
                        "panels": [(t["a"], t["b"], t["hi_before"], t["hi_after"]) for t in trace if t["kind"] == "panel"]},
             "e2e": {"value": world * n * K / (e2e_ms * 1e-3), "unit": "evals/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 16 * n,

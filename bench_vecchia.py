@@ -89,6 +89,8 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1:
+        sk.bind_to_gpu_cpus(local)                     # pinned buffers and copies stay on the GPU's own socket
     rng = np.random.default_rng(0)
     pts = rng.uniform(0, 1, (args.npts, 2))
     pairs = knn_pairs(pts)

@@ -13,12 +13,12 @@ The directory name contains a dot, so import it through the loader module at the
     import spectralkernels_jl_b200 as sk
 """
 from . import _capi, sdf
-from ._capi import PinnedArray, Session, SkError, host_gauss_rule, load
+from ._capi import PinnedArray, Session, SkError, bind_to_gpu_cpus, host_gauss_rule, load
 from .adaptive import (AdaptiveKernelConfig, compute_k0, estimate_tail_decay, gen_derivative_config,
                        gen_new_sdf_config, kernel_values)
 from .derivatives import kernel_derivative, kernel_sdf_derivatives, kernel_singularity_derivative
 from .sdf import Exponential, Matern
 
 __all__ = ["AdaptiveKernelConfig", "kernel_values", "compute_k0", "estimate_tail_decay", "gen_derivative_config",
-           "gen_new_sdf_config", "kernel_derivative", "kernel_sdf_derivatives", "kernel_singularity_derivative", "Matern", "Exponential", "Session", "SkError", "PinnedArray", "host_gauss_rule",
+           "gen_new_sdf_config", "kernel_derivative", "kernel_sdf_derivatives", "kernel_singularity_derivative", "Matern", "Exponential", "Session", "SkError", "PinnedArray", "host_gauss_rule", "bind_to_gpu_cpus",
            "load", "sdf"]

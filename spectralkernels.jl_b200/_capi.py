@@ -418,6 +418,21 @@ class Session:
         return st.as_dict()
 
 
+def bind_to_gpu_cpus(device: int = 0) -> bool:
+    """Pin the calling process to the CPUs NVML reports as local to GPU `device` (its NUMA node / PCIe root), so that
+    the pinned host buffers allocated afterwards and the staging copies stay on the GPU's own socket.  With one process
+    per GPU on a two-socket box this is what keeps eight concurrent H2D / D2H streams from crossing the inter-socket
+    link.  Returns False (and changes nothing) when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False
+
+
 def host_gauss_rule(n: int, p: float = 0.0):
     no, wt = np.empty(n), np.empty(n)
     rc = load().sk_host_gauss_rule(int(n), float(p), _p(no), _p(wt))
