@@ -188,6 +188,12 @@ void emul_hk_plan_info(const SkHankelPlan *H, int *out /*q_lo q_hi t_full t_last
 void emul_hk_group_info(const SkHankelGroup *g, int gi, long long *nf2, long long *off, double *D) {
   *nf2 = g[gi].G.nf2; *off = g[gi].grid_off; *D = g[gi].G.D;
 }
+// fields of group gi: out = {q_cut, q_from, q_to, shared, nf, nf2}; geo = {w_ref, wc, D, inv_hu}
+void emul_hk_group_fields(const SkHankelGroup *g, int gi, long long *out, double *geo) {
+  out[0] = g[gi].q_cut; out[1] = g[gi].q_from; out[2] = g[gi].q_to; out[3] = g[gi].shared;
+  out[4] = g[gi].G.nf; out[5] = g[gi].G.nf2;
+  geo[0] = g[gi].w_ref; geo[1] = g[gi].G.wc; geo[2] = g[gi].G.D; geo[3] = g[gi].G.inv_hu;
+}
 int emul_hk_level(double wT, double w) { return sk_hk_level(wT, w); }
 int emul_hk_octave(double r_hi, double r) { return sk_hk_octave(r_hi, r); }
 // Chebyshev coefficients of every level's partial sum for one rule: cheb[NLEV][NCH][2 rules], column `rule`

@@ -277,7 +277,69 @@ def test_bessel_table_and_dyadic_cuts(emul):
         assert L.emul_hk_octave(r_hi, edge) == t and L.emul_hk_octave(r_hi, np.nextafter(edge, 1)) == max(t - 1, 0)
 
 
-@pytest.mark.parametrize("nu,alpha", [(0, 0.0), (1, 0.0), (0, 0.5)])
+def test_hankel_plan_invariants(emul):
+    """sk_hk_make_plan: every octave that needs an asymptotic part has exactly one group; the levels the groups of a
+    shared set spread incrementally partition the levels above the set's first cut; every group's grid covers its
+    sources and targets."""
+    L, P = emul
+    plan_b, grp_b, K, NLEV, NCH, NGRP = _hk_api(L)
+    L.emul_hk_group_fields.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(12)
+    for case in range(40):
+        r_hi = float(10 ** rng.uniform(-3, 3))
+        r_lo = r_hi * float(10 ** rng.uniform(-7, 0))
+        npan = int(rng.integers(0, 4))
+        a = npan * 32768.0 / r_hi * float(rng.uniform(0.5, 1.0)) if npan else 0.0
+        b = a + 32768.0 / r_hi * float(rng.uniform(0.3, 3.0))
+        H = ctypes.create_string_buffer(plan_b)
+        G = ctypes.create_string_buffer(grp_b * NGRP)
+        total = L.emul_hk_plan(ctypes.byref(P), int(rng.integers(0, 4)), a, b, r_lo, r_hi, H, G)
+        assert total >= 0
+        info = (ctypes.c_int * 5)()
+        L.emul_hk_plan_info(H, info)
+        q_lo, q_hi, t_full, t_last, ng = list(info)
+        wT = 32.0 / (2 * np.pi * r_hi)
+        assert q_lo == L.emul_hk_level(wT, a) and q_hi == L.emul_hk_level(wT, b)
+        t_need = L.emul_hk_octave(r_hi, r_lo)
+        n_oct = max(0, min(t_last, t_need) - (t_full + 1) + 1)
+        assert ng == n_oct + (1 if t_full >= 0 else 0)
+        fields = []
+        for gi in range(ng):
+            out = (ctypes.c_longlong * 6)()
+            geo = (ctypes.c_double * 4)()
+            L.emul_hk_group_fields(G, gi, out, geo)
+            fields.append((list(out), list(geo)))
+        off = 1 if t_full >= 0 else 0
+        if t_full >= 0:
+            (q_cut, q_from, q_to, shared, nf, nf2), (w_ref, wc, D, inv_hu) = fields[0]
+            assert (q_cut, q_from, q_to, shared) == (0, 0, NLEV, 0) and w_ref <= max(a, wT)
+        covered = None
+        for i, gi in enumerate(range(off, ng)):
+            t = t_full + 1 + i
+            (q_cut, q_from, q_to, shared, nf, nf2), (w_ref, wc, D, inv_hu) = fields[gi]
+            assert q_cut == t + 2 and q_from == q_cut
+            assert w_ref <= wT * 2.0 ** (t + 1) * (1 + 1e-15)              # lam = w_ref / w <= 1 for every source of the group
+            assert nf2 >= 1.999 * nf and (nf2 & (nf2 - 1) == 0 or (nf2 // 3) & (nf2 // 3 - 1) == 0)
+            # the spread grid covers the sources [first cut, b] ...
+            w_first = wT * 2.0 ** (t + 1)
+            assert abs((w_first - wc) * inv_hu) <= nf / 2 and abs((b - wc) * inv_hu) <= nf / 2
+            # ... and the fine grid the targets of the octave
+            kappa = nf2 / inv_hu
+            for r in (max(r_lo, r_hi * 2.0 ** -(t + 1)), r_hi * 2.0 ** -t):
+                assert abs((r - D) * kappa) <= nf2 / 2 - 8
+            if shared == 0:
+                assert q_to == NLEV
+            else:
+                assert t >= 3
+                nxt = fields[gi + 1][0] if gi + 1 < ng else None
+                if shared == 1:
+                    assert gi == ng - 1 and q_to == NLEV                       # the deepest octave takes everything above
+                else:
+                    assert nxt is not None and nxt[3] in (1, 2) and q_to == nxt[1] == q_cut + 1
+                    assert fields[gi + 1][1] == fields[gi][1]                   # same w_ref and geometry across the set
+
+
+@pytest.mark.parametrize("nu,alpha", [(0, 0.0), (1, 0.0), (0, 0.5), (2, 0.0)])
 def test_hankel_transform_math(emul, nu, alpha):
     """The O(N) nonuniform Hankel transform (dyadic levels x octaves: Hankel expansion through batched type-3
     NUFFTs + local Chebyshev expansions) against the reference's direct Bessel summation
@@ -287,7 +349,7 @@ def test_hankel_transform_math(emul, nu, alpha):
     tab = np.zeros(4 * 32 * 16)
     assert L.emul_bessel_table(_ptr(tab)) == 0
     S = lambda w: (1 + w ** 2) ** -2.5
-    cfg = so.OracleConfig(S, dim=2, alpha=alpha, derivative=(nu == 1))
+    cfg = so.OracleConfig(S, dim=2, alpha=alpha, derivative=(nu == 1))      # (the strengths only; nu = 2 is dim = 4's K')
     rng = np.random.default_rng(nu + 1)
     xs = np.sort(np.concatenate([rng.uniform(0, 1, 40), 10 ** rng.uniform(-6, 0, 40), [1.0, 0.5, 0.25]]))
     for (a, b) in ((0.0, 32768.0), (32768.0, 65536.0), (2.0e6, 2.0e6 + 32768.0)):

@@ -513,6 +513,32 @@ def test_singularity_derivative_logw_dim2(sk, mode):
     cfg.engine.set_hankel_mode(0)
 
 
+@pytest.mark.parametrize("derivative", [False, True])
+def test_hankel_dim4(sk, derivative):
+    """dim = 4: Bessel orders 1 (K) and 2 (K'), p = 2, the integrals divided by x^(dim/2-1) = x
+    (src/quadrature.jl:252-254), through the O(N) transform: oracle, closed form and the direct summation."""
+    parms = (1.7, 0.9, 1.2)
+    rng = np.random.default_rng(13)
+    xs = np.concatenate([[0.0], rng.uniform(0, 1.6, 120), 10 ** rng.uniform(-3, 0, 60)])
+    cfg = sk.AdaptiveKernelConfig(sk.Matern(*parms, d=4), dim=4, derivative=derivative)
+    ocfg = so.OracleConfig(lambda w: cf.matern_sdf(w, parms, d=4), dim=4, derivative=derivative)
+    k0 = float(cf.matern_cov(0.0, parms, d=4)[0])
+    cfg.engine.set_hankel_mode(2)
+    tg, to = [], []
+    vg, eg = sk.kernel_values(cfg, xs, k0=k0, trace=tg)
+    st = cfg.engine.stats()
+    vo, eo = so.kernel_values(ocfg, xs, k0=k0, trace=to)
+    assert st["n_hankel"] == st["n_subintervals"] > 0
+    assert np.max(np.abs(vg - vo)) <= 1e-10 * k0        # small x: both sides divide ~1e-13 sum|c| by x
+    assert _trace_key(tg) == _trace_key(to)
+    true = cf.matern_dcov(xs, parms, d=4) if derivative else cf.matern_cov(xs, parms, d=4)
+    assert np.max(np.abs(vg - true)) <= 10 * 1e-8 * k0
+    cfg.engine.set_hankel_mode(1)
+    vd, _ = sk.kernel_values(cfg, xs, k0=k0)
+    assert np.max(np.abs(vg - vd)) <= 1e-10 * k0
+    cfg.engine.set_hankel_mode(0)
+
+
 def test_hankel_interp_variants_agree(sk):
     """The three interpolation kernels of the O(N) Hankel transform.  k_hankel_interp2 (interp_mode 2: two targets per
     thread, 256-bit loads) executes the operations of k_hankel_interp (mode 1, the plain restatement of sk_hk_point)
