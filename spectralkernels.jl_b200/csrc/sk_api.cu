@@ -107,7 +107,7 @@ struct sk_ctx {
   // rules
   int m = 0, k = 0;
   double p = 0.0;
-  bool have_rule = false, have_jac = false;
+  bool have_rule = false, have_jac = false, rule_generated = false;
   DevBuf<double> leg_no1, leg_wt1, leg_no2, leg_wt2, jac_no1, jac_wt1, jac_no2, jac_wt2;
   std::vector<double> h_rule[8];
   // generated rules, kept for the life of the context: (n, p) -> (nodes, weights).  Derivative configs flip
@@ -1112,6 +1112,9 @@ int sk_rule_set(sk_ctx *c, int32_t m, int32_t k, double p, const double *leg_no1
   CK(cudaSetDevice(c->device));
   const bool given_leg = leg_no1 && leg_wt1 && leg_no2 && leg_wt2;
   const bool given_jac = jac_no1 && jac_wt1 && jac_no2 && jac_wt2;
+  // library-generated rules for the same (m, k, p) are already resident: nothing to do (every kernel_values call
+  // of a fitting loop comes through here)
+  if (!given_leg && !given_jac && c->have_rule && c->rule_generated && c->m == m && c->k == k && c->p == p) return SK_OK;
   const int sizes[8] = {m, m, 2 * m, 2 * m, m, m, 2 * m, 2 * m};
   for (int i = 0; i < 8; ++i) c->h_rule[i].assign(sizes[i], 0.0);
   if (given_leg) {
@@ -1145,6 +1148,7 @@ int sk_rule_set(sk_ctx *c, int32_t m, int32_t k, double p, const double *leg_no1
   CK(cudaStreamSynchronize(c->stream));
   c->m = m; c->k = k; c->p = p;
   c->have_rule = true;
+  c->rule_generated = !given_leg && !(c->have_jac && given_jac);
   return SK_OK;
 }
 
