@@ -255,9 +255,9 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
     if cfg.dim == 1:
         kernel = SK_KERNEL_SIN if cfg.derivative else SK_KERNEL_COS              # :177
     else:
-        # (:J, dim/2) or (:J, dim/2-1), :179; only even dims are usable (Int64(kernel[2]), :138).  The device
-        # evaluates the reference's direct Bessel summation (:145-160) at every size: the O(N) NUFHT of
-        # FastHankelTransform.jl is not built.
+        # (:J, dim/2) or (:J, dim/2-1), :179; only even dims are usable (Int64(kernel[2]), :138).  Where the reference
+        # calls FastHankelTransform.jl's nufht (:139-143) the library runs its own O(N) nonuniform Hankel transform
+        # (orders 0..3, csrc/sk_hankel.h); small active sets take the direct Bessel summation (:145-160).
         order = cfg.dim / 2 if cfg.derivative else cfg.dim / 2 - 1
         if order != int(order):
             raise ValueError(f"InexactError: Int64({order})")                    # :138
