@@ -78,6 +78,8 @@ def main():
     ap.add_argument("--batch", type=int, default=24, help="hyperparameter vectors in the job (8 x P, P = 3)")
     ap.add_argument("--dim", type=int, default=2)
     ap.add_argument("--alpha", type=float, default=0.0)
+    ap.add_argument("--warp", action="store_true", help="the range enters through the warping x -> x / rho (sk_targets_scale) "
+                                                        "instead of the spectral density")
     ap.add_argument("--sync-copies", action="store_true", help="copy results back synchronously (no overlap with the next vector)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -104,7 +106,10 @@ def main():
     eng = sk.Session(local)
 
     def run(h, reuse, slot):
-        cfg = sk.AdaptiveKernelConfig(sk.Matern(h[0], h[1], h[2], d=args.dim), dim=args.dim, alpha=args.alpha, device=local,
+        if args.warp and reuse:                            # src/model.jl:62-66: lags of the warped points, same sort
+            eng.targets_scale(1.0 / h[1])
+        rho_sdf = 1.0 if args.warp else h[1]
+        cfg = sk.AdaptiveKernelConfig(sk.Matern(h[0], rho_sdf, h[2], d=args.dim), dim=args.dim, alpha=args.alpha, device=local,
                                       engine=eng)
         k0 = sk.compute_k0(cfg)
         sk.kernel_values(cfg, None, k0=k0, points=pts, pairs=pairs, reuse_targets=reuse, want_errors=False,
@@ -145,6 +150,7 @@ def main():
                           "n_pairs": npairs, "n_hankel_last": st["n_hankel"], "subintervals_last": st["n_subintervals"],
                           "setup_ms_first_call": 1e3 * setup_first, "setup_plus_one_vector_ms_warm": 1e3 * setup_warm,
                           "scaling": "strong (fixed batch)", "result_copies": "sync" if args.sync_copies else "async (second stream)",
+                          "range_parameter": "warping x -> x / rho (sk_targets_scale)" if args.warp else "in the spectral density",
                           "check_finite_and_k0": ok}), flush=True)
 
 

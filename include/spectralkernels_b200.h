@@ -192,6 +192,12 @@ int sk_targets_set_device(sk_ctx *ctx, const double *xs_dev, int64_t n_in, sk_ta
  * sk_results_get are then in pair order.  Replaces the host-side lag list and its upload. */
 int sk_targets_set_pairs(sk_ctx *ctx, const double *pts_host, int64_t npts, int32_t dim, const int64_t *pairs_host,
                          int64_t npairs, sk_target_info *info);
+/* Linear warping of the lags, warp(params, x) = x / rho (src/model.jl:62-66; the range parameter of
+ * scripts/fit_vecchia_demo.jl:15): every unique distance becomes (original distance) * factor, factor > 0.  Order,
+ * uniqueness and the inverse map are unchanged, so a fitting loop re-uses the sort of sk_targets_set* for every
+ * range value.  The factor always applies to the distances as they were set.  info (may be NULL) receives the scaled
+ * r_min_pos / r_max. */
+int sk_targets_scale(sk_ctx *ctx, double factor, sk_target_info *info);
 /* sorted unique value at 1-based index idx */
 int sk_target_value(sk_ctx *ctx, int64_t idx, double *out);
 

@@ -87,6 +87,7 @@ SIGNATURES = {
     "sk_targets_set": (c_int, [c_void_p, c_void_p, c_int64, POINTER(TargetInfo)]),
     "sk_targets_set_device": (c_int, [c_void_p, c_void_p, c_int64, POINTER(TargetInfo)]),
     "sk_targets_set_pairs": (c_int, [c_void_p, _dp, c_int64, c_int32, POINTER(c_int64), c_int64, POINTER(TargetInfo)]),
+    "sk_targets_scale": (c_int, [c_void_p, c_double, c_void_p]),
     "sk_target_value": (c_int, [c_void_p, c_int64, _dp]),
     "sk_run_begin": (c_int, [c_void_p]),
     "sk_zero_lag_set": (c_int, [c_void_p, c_double]),
@@ -303,11 +304,13 @@ class Session:
         xs = _f64(xs)
         info = TargetInfo()
         self._ck(self._L.sk_targets_set(self._h, xs.ctypes.data, xs.size, byref(info)))
+        self._last_targets = (info, int(info.n_in))          # what kernel_values(reuse_targets=True) picks up
         return info
 
     def targets_set_device(self, dev_ptr: int, n: int) -> TargetInfo:
         info = TargetInfo()
         self._ck(self._L.sk_targets_set_device(self._h, c_void_p(dev_ptr), int(n), byref(info)))
+        self._last_targets = (info, int(info.n_in))
         return info
 
     def targets_set_pairs(self, pts, pairs=None) -> TargetInfo:
@@ -323,6 +326,15 @@ class Session:
             pr = np.ascontiguousarray(pairs, dtype=np.int64)
             self._ck(self._L.sk_targets_set_pairs(self._h, _p(pts), pts.shape[0], pts.shape[1],
                                                   pr.ctypes.data_as(POINTER(c_int64)), pr.shape[0], byref(info)))
+        self._last_targets = (info, int(info.n_in))
+        return info
+
+    def targets_scale(self, factor: float) -> "TargetInfo":
+        """Lags under the linear warping x -> x * factor (range parameter): re-uses the sort of the last targets_set*."""
+        info = TargetInfo()
+        self._ck(self._L.sk_targets_scale(self._h, float(factor), byref(info)))
+        if getattr(self, "_last_targets", None) is not None:
+            self._last_targets = (info, self._last_targets[1])
         return info
 
     def target_value(self, idx: int) -> float:

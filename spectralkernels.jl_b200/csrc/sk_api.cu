@@ -127,7 +127,9 @@ struct sk_ctx {
   // targets
   long long n_in = 0, n_unique = 0;
   bool has_zero = false;
-  DevBuf<double> in, uxs, out_v, out_e;
+  DevBuf<double> in, uxs, uxs_orig, out_v, out_e;
+  bool have_orig = false;                     // uxs_orig holds the unscaled unique distances (sk_targets_scale)
+  double r0_orig = 0, r1_orig = 0, r_last_orig = 0;
   // asynchronous result copies (sk_results_get_async): two slots, a copy stream, events
   DevBuf<double> aout_v[2], aout_e[2];
   cudaStream_t copy_stream = nullptr;
@@ -778,6 +780,7 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   c->n_in = n_in;
   c->n_unique = nu;
   c->r0 = sm.r0; c->r1 = sm.r1; c->r_last = sm.r_last;
+  c->have_orig = false;
   c->has_zero = (sm.r0 == 0.0);
   c->have_targets = true;
   c->in_panel = false;
@@ -865,7 +868,7 @@ int sk_ctx_destroy(sk_ctx *c) {
   for (auto &kv : c->fft_plans) cufftDestroy(kv.second);
   DevBuf<double> *dbl[] = {&c->leg_no1, &c->leg_wt1, &c->leg_no2, &c->leg_wt2, &c->jac_no1, &c->jac_wt1, &c->jac_no2,
                            &c->jac_wt2, &c->no1, &c->buf1, &c->no2, &c->buf2, &c->pos_hi1, &c->pos_lo1, &c->pos_hi2,
-                           &c->pos_lo2, &c->imz, &c->in, &c->uxs, &c->out_v, &c->out_e};
+                           &c->pos_lo2, &c->imz, &c->in, &c->uxs, &c->uxs_orig, &c->out_v, &c->out_e};
   for (auto *b : dbl) b->release();
   c->cs1.release(); c->cs2.release(); c->fft.release(); c->dsum.release();
   c->res.release(); c->pan.release(); c->stage.release();
@@ -1216,6 +1219,39 @@ int sk_targets_set_pairs(sk_ctx *c, const double *pts_host, int64_t npts, int32_
   d_pts.release();
   d_pairs.release();
   return rc;
+}
+
+// Linear warping of the lags: every unique distance becomes (original distance) * factor.  The sort, the unique
+// table's order and the inverse map stay valid, so a fitting loop whose range parameter enters through the
+// warping function x -> x / rho (src/model.jl:62-66, scripts/fit_vecchia_demo.jl:15) re-uses the sorted lags of
+// sk_targets_set* for every hyperparameter vector.  The factor always applies to the ORIGINAL distances.
+int sk_targets_scale(sk_ctx *c, double factor, sk_target_info *info) {
+  if (!c) return SK_ERR_ARG;
+  if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
+  if (!(factor > 0.0) || std::isinf(factor)) return fail(c, SK_ERR_ARG, "the scale factor must be positive and finite");
+  CK(cudaSetDevice(c->device));
+  if (!c->have_orig) {
+    CK(c->uxs_orig.ensure(c->n_unique));
+    CK(cudaMemcpyAsync(c->uxs_orig.p, c->uxs.p, sizeof(double) * c->n_unique, cudaMemcpyDeviceToDevice, c->stream));
+    c->r0_orig = c->r0; c->r1_orig = c->r1; c->r_last_orig = c->r_last;
+    c->have_orig = true;
+  }
+  k_scale_targets<<<nblk(c->n_unique, 256), 256, 0, c->stream>>>(c->uxs_orig.p, c->uxs.p, c->n_unique, factor);
+  LAUNCH_CHECK();
+  c->r0 = c->r0_orig * factor; c->r1 = c->r1_orig * factor; c->r_last = c->r_last_orig * factor;   // same rounding as the kernel
+  c->in_panel = false;
+  c->staged = false;
+  c->commit_pending = false;
+  c->scan_hi = -1;
+  if (info) {
+    info->n_in = c->n_in;
+    info->n_unique = c->n_unique;
+    info->has_zero = c->has_zero ? 1 : 0;
+    info->_pad = 0;
+    info->r_min_pos = c->has_zero ? c->r1 : c->r0;
+    info->r_max = c->r_last;
+  }
+  return SK_OK;
 }
 
 int sk_target_value(sk_ctx *c, int64_t idx, double *out) {

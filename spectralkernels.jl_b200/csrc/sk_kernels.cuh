@@ -996,6 +996,14 @@ __global__ void k_pair_lags(const double *__restrict__ pts, long long npts, int 
   lags[t] = dim == 1 ? fabs(sk_add(pts[i], -pts[j])) : sqrt(acc);
 }
 
+// lags under a linear warping x -> x / rho (src/model.jl:62-66 with warp(params, x) = x / params[1], the range
+// parameter of scripts/fit_vecchia_demo.jl:15): the sorted unique table is the original one times a positive factor
+// (monotone: order and the inverse map are unchanged)
+__global__ void k_scale_targets(const double *__restrict__ orig, double *__restrict__ uxs, long long n, double f) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) uxs[j] = sk_mul(orig[j], f);
+}
+
 // number of sorted values <= r (== the largest 1-based index with xs[idx] <= r)
 __global__ void k_upper_bound(const double *__restrict__ xs, long long n, double r, long long *__restrict__ out) {
   long long a = 0, b = n;

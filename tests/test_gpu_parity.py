@@ -586,6 +586,29 @@ def test_hankel_full_size_properties(sk):
     assert np.max(np.abs(v[3::4001][order] - vd)) <= 2e-11 * k0
 
 
+def test_lag_warping_reuses_the_sort(sk):
+    """sk_targets_scale: lags under the linear warping x -> x / rho (src/model.jl:62-66 with the range parameter of
+    scripts/fit_vecchia_demo.jl:15) re-use the sorted / de-duplicated lags; values equal a fresh evaluation at the
+    scaled distances bit for bit, for several range values in a row (the factor applies to the original lags)."""
+    rng = np.random.default_rng(17)
+    xs = np.concatenate([[0.0], rng.uniform(0, 1, 100_000)])
+    xs[500:600] = xs[100:200]
+    S = sk.Matern(1.0 / (np.pi / 2), 1.0, 1.5)
+    cfg = sk.AdaptiveKernelConfig(S)
+    eng = cfg.engine
+    eng.targets_set(xs)
+    for rho in (2.7, 0.31, 1.0):
+        info = eng.targets_scale(1.0 / rho)
+        assert info.r_max == np.max(xs * (1.0 / rho)) and info.has_zero == 1
+        v, e = sk.kernel_values(cfg, xs, k0=1.0, reuse_targets=True)
+        cfg2 = sk.AdaptiveKernelConfig(S)
+        v2, e2 = sk.kernel_values(cfg2, xs * (1.0 / rho), k0=1.0)
+        assert np.array_equal(v, v2) and np.array_equal(e[1:], e2[1:])
+        cfg2.engine.close()
+    with pytest.raises(sk.SkError):
+        eng.targets_scale(-1.0)
+
+
 def test_async_result_copies(sk):
     """sk_results_get_async / sk_results_wait: a sweep of hyperparameter vectors over the same targets with the copy of
     run b overlapping run b + 1 (second stream, two slots) returns exactly what the synchronous copies return."""
