@@ -513,6 +513,33 @@ def test_singularity_derivative_logw_dim2(sk, mode):
     cfg.engine.set_hankel_mode(0)
 
 
+def test_hankel_bisection_and_host_closure(sk):
+    """dim = 2 with a sharply peaked density (S = exp(-2000|w|), K(r) = 2 pi a / (a^2 + (2 pi r)^2)^(3/2)): rejected
+    sub-intervals and the LIFO bisection (src/quadrature.jl:263-271) through the O(N) Hankel transform -- sub-intervals
+    [a, b] with a > 0 inside the first panel, accept / add passes -- for the device generator and for a host closure
+    (sk_subinterval_host); traces and values against the oracle, values against the closed form."""
+    al = 2000.0
+    xs = np.linspace(0.001, 0.05, 150)
+    k0 = 2 * np.pi / al ** 2
+    ocfg = so.OracleConfig(lambda w: np.exp(-al * np.abs(w)), dim=2)
+    to = []
+    vo, eo = so.kernel_values(ocfg, xs, k0=k0, trace=to)
+    assert sum(1 for t in to if t["kind"] == "subinterval" and not t["accepted"]) >= 3
+    true = 2 * np.pi * al / (al ** 2 + (2 * np.pi * xs) ** 2) ** 1.5
+    for f in (sk.Exponential(1.0, al), lambda w: np.exp(-al * np.abs(w))):
+        cfg = sk.AdaptiveKernelConfig(f, dim=2)
+        cfg.engine.set_hankel_mode(2)
+        tg = []
+        vg, eg = sk.kernel_values(cfg, xs, k0=k0, trace=tg)
+        st = cfg.engine.stats()
+        assert st["n_hankel"] == st["n_subintervals"] > st["n_accepted"]
+        assert _trace_key(tg) == _trace_key(to)
+        assert np.max(np.abs(vg - vo)) <= 1e-10 * k0
+        assert np.max(np.abs(vg - true)) <= 10 * 1e-8 * k0
+        assert np.allclose(eg, eo, rtol=1e-3, atol=1e-10 * k0)
+        cfg.engine.close()
+
+
 @pytest.mark.parametrize("derivative", [False, True])
 def test_hankel_dim4(sk, derivative):
     """dim = 4: Bessel orders 1 (K) and 2 (K'), p = 2, the integrals divided by x^(dim/2-1) = x
