@@ -2,15 +2,21 @@
 // path: src/quadrature.jl:137-161, where the reference calls FastHankelTransform.jl's `nufht`).
 // The arithmetic is in sk_hankel.h; these are the launch wrappers plus block-level cooperation.
 //
-//   K9a k_hankel_levels   first source of every dyadic frequency level (both rules)
-//   K9b k_hankel_fit      direct sums of each level at the Chebyshev nodes of its local interval
-//       k_hankel_cheb     node values -> Chebyshev coefficients
-//   K9c k_hankel_prep     per group: grid positions, term-0 strengths, term ratios
-//       k_spread_hankel   deterministic gather spread of all K terms of a rule in one pass + mode
-//                         deconvolution + zero pad (taps evaluated once per source, not once per term)
-//       cuFFT Z2Z         batch 2K interleaved (sk_api.cu)
-//   K9d k_hankel_interp   per target: octave -> group; w taps once, K x 2 grids, Horner in i/z_ref, local
-//                         Chebyshev levels, *c, / x^(dim/2-1), stage (I2, |I2-I1|), block max
+//   K9a k_hankel_levels      first source of every dyadic frequency level (both rules)
+//   K9b k_hankel_fit         direct sums of each level at the Chebyshev nodes of its local interval
+//       k_hankel_cheb        node values -> Chebyshev coefficients of the level
+//       k_hankel_local_poly  levels an octave needs -> piecewise expansion of the octave (16 pieces x 16 terms)
+//   K9c k_hankel_prep        per group: grid positions, term-0 strengths, term ratios (levels [q_from, q_to))
+//       k_spread_hankel      deterministic gather spread of all K terms of a rule in one pass + mode deconvolution
+//                            + zero pad (taps evaluated once per source, not once per term); split-K over the source
+//                            range for small grids (k_spread_hankel_reduce); accumulating into the running mode
+//                            buffer of the shared set of small octaves
+//       cuFFT Z2Z            batch 2K interleaved (sk_api.cu)
+//   K9d k_hankel_cells       (default) one polynomial per fine-grid cell across the K terms, built per warp; four
+//                            Horner chains per target + the octave's local expansion, *c, / x^(dim/2-1), stage
+//                            (I2, |I2-I1|), max
+//       k_hankel_interp      A/B: one target per thread, per-target taps (the plain restatement of sk_hk_point)
+//       k_hankel_interp2     A/B: two targets per thread sharing 256-bit loads; bit-identical to k_hankel_interp
 #pragma once
 #include "sk_hankel.h"
 #include "sk_kernels.cuh"

@@ -20,7 +20,10 @@
 // [0, 64] fitted in quad precision).  Nothing is evaluated per (source, target) pair: the work per target is
 // K * 4 * w FMAs (interpolation) plus one short Clenshaw recurrence: the local levels of an octave are summed
 // once per sub-interval into a piecewise expansion of the octave (SK_HK_NSUB pieces x SK_HK_NLOC terms).
-// Octaves t with t+2 <= level(a) see the whole sub-interval [a, b] asymptotically and share one transform.
+// Octaves t with t+2 <= level(a) see the whole sub-interval [a, b] asymptotically and share one transform; the
+// small octaves (t >= SK_HK_T_SHARE) share one geometry and are spread incrementally.  In the default
+// interpolation kernel the K terms are folded into one polynomial per fine-grid cell (see "cell polynomials
+// across the K terms" below), so a target costs four Horner chains.
 #pragma once
 #include "sk_math.h"
 
