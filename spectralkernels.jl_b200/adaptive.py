@@ -175,9 +175,12 @@ def _scan_args(cfg, b, c, d, tau, crit) -> ScanArgs:
     if crit == "panel":
         ta = tn = 0.0
     else:
+        # IEEE arithmetic throughout, as in Julia: d + dim == 0 gives -c/0 = -+Inf (converged by the tail bound),
+        # never a Python ZeroDivisionError
+        c64, d64, b64 = np.float64(c), np.float64(d), np.float64(b)
         with np.errstate(all="ignore"):
-            ta = float(-c / (d + dim) * np.float64(b) ** (d + dim))
-            tn = float(c * np.float64(b) ** (d + (dim - 1) / 2))
+            ta = float(-c64 / (d64 + dim) * b64 ** (d64 + dim))
+            tn = float(c64 * b64 ** (d64 + (dim - 1) / 2))
     return ScanArgs(ta, tn, (dim + 1) / 2, float(tau), SK_CRIT[crit], 0)
 
 

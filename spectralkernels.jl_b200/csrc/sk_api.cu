@@ -129,6 +129,8 @@ struct sk_ctx {
   bool has_zero = false;
   DevBuf<double> in, uxs, uxs_orig, out_v, out_e;
   bool have_orig = false;                     // uxs_orig holds the unscaled unique distances (sk_targets_scale)
+  double in_scale = 1.0;                      // unique distance = input distance * in_scale (sk_targets_scale)
+  SkTailList tails;                           // converged tails whose 2 trunc_err is added by the gather (k_gather)
   double r0_orig = 0, r1_orig = 0, r_last_orig = 0;
   // asynchronous result copies (sk_results_get_async): two slots, a copy stream, events
   DevBuf<double> aout_v[2], aout_e[2];
@@ -141,7 +143,12 @@ struct sk_ctx {
   DevBuf<unsigned int> idx, idx_alt, head, uid, inv;
   DevBuf<unsigned char> cub_tmp;
   SkKeyBits *d_kb = nullptr;
-  const unsigned int *sidx = nullptr;        // sorted position -> original position (one of idx / idx_alt)
+  // K8 (sk_k8.cuh): control block (state, coarse histogram, look-back descriptors, fill counters), the
+  // piecewise-linear distribution estimate, and the fine-bin slots
+  DevBuf<unsigned char> k8_ctl;
+  DevBuf<uint2> k8_ctab;
+  DevBuf<unsigned long long> k8_skeys;
+  DevBuf<unsigned int> k8_sidx;
   bool have_targets = false;
 
   // panel state (0-based half-open [lo, hi))
@@ -677,14 +684,9 @@ int upload_rule(sk_ctx *c, DevBuf<double> &dst, const double *src, int n) {
   return SK_OK;
 }
 
-// sort_bits: radix-sorted key bits of the two-level sort (24 / 32 / 40: 3 / 4 / 5 digit passes); -1: chosen from the
-// key statistics (below); 0: full 63-bit sort (the fall-back when a run of equal sorted bits outgrows the run-rank
-// halo)
-int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, int sort_bits = -1) {
-  const bool two_level = sort_bits != 0;
-  // c->in holds the n_in raw distances
-  c->have_targets = false;
-  if (n_in > 0x7ffffff0LL) return fail(c, SK_ERR_ARG, "n_in too large");
+// General sort for inputs the bin scheme of K8 cannot take (heavily clustered or duplicated distances overflow a fine
+// bin): full radix sort of the keys, first-of-value flags, scan, scatter.  Rare path.
+int targets_sort_general(sk_ctx *c, long long n_in) {
   CK(c->keys.ensure(n_in));
   CK(c->keys_alt.ensure(n_in));
   CK(c->idx.ensure(n_in));
@@ -704,90 +706,89 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   CK(cub::DeviceScan::InclusiveSum(nullptr, tmp2, c->head.p, c->uid.p, (int)n_in, c->stream));
   CK(c->cub_tmp.ensure(std::max(tmp_bytes, tmp2)));
   tmp_bytes = tmp2 = c->cub_tmp.cap;
-  const unsigned long long *skeys;
-  const unsigned int *sidx;
-  bool presorted = false;
-  if (two_level) {
-    // Which key bits differ at all?  (one 24-byte read-back; the keys are non-negative doubles, so the
-    // sign bit never varies and for a distance set spanning a few binades neither do the top exponent bits)
-    CK(cudaMemcpyAsync(&c->h_scal->kb, c->d_kb, sizeof(SkKeyBits), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (c->h_scal->kb.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
-    presorted = c->h_scal->kb.unsorted == 0;       // strictly increasing input: nothing to sort or de-duplicate
-  }
-  if (presorted) {
-    CK(c->uxs.ensure(n_in));
-    CK(c->inv.ensure(n_in));
-    k_identity_targets<<<nblk(n_in, 256), 256, 0, c->stream>>>(c->keys.p, n_in, c->uxs.p, c->inv.p, c->uid.p);
-    LAUNCH_CHECK();
-    skeys = c->keys.p;
-    sidx = c->idx.p;
-  } else if (two_level) {
-    const unsigned long long varying = c->h_scal->kb.bits_or ^ c->h_scal->kb.bits_and;
-    int top = 0;                                         // number of low bits that can differ
-    while (top < 64 && (varying >> top) != 0ull) ++top;
-    const int end_bit = top < 1 ? 1 : top;
-    if (sort_bits < 0) {
-      // Enough sorted bits for runs of at most ~8 equal prefixes even if every distance fell into one binade
-      // (k_run_rank walks its run: measured, a mean run of 10 costs more than the radix pass it saves): the varying
-      // exponent bits (5 for U(0,1); all 11 when the distances straddle 1.0, where the biased exponent carries from
-      // 01111111111 to 10000000000) plus log2(n) - 3 mantissa bits.
-      const int nexp = top > 52 ? top - 52 : 0;
-      int lg = 0;
-      while ((2LL << lg) <= n_in) ++lg;                  // floor(log2 n)
-      const int need = nexp + (lg > 3 ? lg - 3 : 0);
-      sort_bits = need <= 24 ? 24 : (need <= 32 ? 32 : 40);
-    }
-    const int begin_bit = end_bit > sort_bits ? end_bit - sort_bits : 0;   // 3 or 4 radix passes of 8 bits
-    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, begin_bit, end_bit, c->stream));
-    c->stats.kernel_launches += 1 + sort_bits / 8;
-    const unsigned long long mask = begin_bit == 0 ? ~0ull : ~((1ull << begin_bit) - 1ull);
-    k_run_rank<<<nblk(n_in, SK_RR_TILE), 256, 0, c->stream>>>(dk.Current(), dv.Current(), n_in, mask, dk.Alternate(),
-                                                              dv.Alternate(), c->head.p, &c->d_kb->overflow);
-    LAUNCH_CHECK();
-    skeys = dk.Alternate();
-    sidx = dv.Alternate();
-  } else {
-    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, 0, 63, c->stream));
-    c->stats.kernel_launches += 9;
-    skeys = dk.Current();
-    sidx = dv.Current();
-    k_flag_heads<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, n_in, c->head.p);
-    LAUNCH_CHECK();
-  }
-  if (!presorted) {
-    CK(cub::DeviceScan::InclusiveSum(c->cub_tmp.p, tmp2, c->head.p, c->uid.p, (int)n_in, c->stream));
-    c->stats.kernel_launches += 2;
-    // unique table sized for the worst case (n_unique <= n_in): no host round trip before the compaction
-    CK(c->uxs.ensure(n_in));
-    CK(c->inv.ensure(n_in));
-    k_scatter_unique<<<nblk(n_in, 256), 256, 0, c->stream>>>(skeys, sidx, c->head.p, c->uid.p, n_in, c->uxs.p, c->inv.p);
-    LAUNCH_CHECK();
-  }
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_in, 0, 63, c->stream));
+  c->stats.kernel_launches += 9;
+  k_flag_heads<<<nblk(n_in, 256), 256, 0, c->stream>>>(dk.Current(), n_in, c->head.p);
+  LAUNCH_CHECK();
+  CK(cub::DeviceScan::InclusiveSum(c->cub_tmp.p, tmp2, c->head.p, c->uid.p, (int)n_in, c->stream));
+  c->stats.kernel_launches += 2;
+  k_scatter_unique<<<nblk(n_in, 256), 256, 0, c->stream>>>(dk.Current(), dv.Current(), c->head.p, c->uid.p, n_in, c->uxs.p, c->inv.p);
+  LAUNCH_CHECK();
   k_target_summary<<<1, 1, 0, c->stream>>>(c->uxs.p, c->uid.p, n_in, c->d_kb, c->d_sum);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return SK_OK;
+}
+
+// K8 (sk_k8.cuh): c->in holds the n_in raw distances -> sorted unique table c->uxs, inverse map c->inv.  One host
+// synchronisation, at the end (the summary); an already strictly increasing input is detected on the device and
+// costs one read pass.  force_general: take the general sort (tests).
+int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, bool force_general = false) {
+  c->have_targets = false;
+  if (n_in > 0x7ffffff0LL) return fail(c, SK_ERR_ARG, "n_in too large");
+  const size_t nfine_max = (size_t)(n_in >> SK_K8_TARGET_LOG) + 2;
+  // control block: state | coarse histogram | look-back descriptors | fill counters -- cleared by one memset
+  const size_t off_hist = 256, off_desc = off_hist + sizeof(unsigned int) * SK_K8_NC;
+  const size_t off_fill = off_desc + sizeof(unsigned long long) * nfine_max;
+  const size_t ctl_bytes = off_fill + sizeof(unsigned int) * nfine_max;
+  static_assert(sizeof(SkK8State) <= 256, "control block layout");
+  CK(c->k8_ctl.ensure(ctl_bytes));
+  CK(c->k8_ctab.ensure(SK_K8_NC));
+  CK(c->k8_skeys.ensure(nfine_max * SK_K8_CAP));
+  CK(c->k8_sidx.ensure(nfine_max * SK_K8_CAP));
+  CK(c->uxs.ensure(n_in));               // sized for the worst case (n_unique <= n_in): no host round trip
+  CK(c->inv.ensure(n_in));
   CK(c->res.ensure(n_in));
   CK(c->pan.ensure(n_in));
   CK(c->stage.ensure(n_in));
-  CK(cudaStreamSynchronize(c->stream));
+  SkK8State *st = (SkK8State *)c->k8_ctl.p;
+  unsigned int *chist = (unsigned int *)(c->k8_ctl.p + off_hist);
+  unsigned long long *desc = (unsigned long long *)(c->k8_ctl.p + off_desc);
+  unsigned int *fill = (unsigned int *)(c->k8_ctl.p + off_fill);
+  bool general = force_general;
+  if (!general) {
+    CK(cudaMemsetAsync(c->k8_ctl.p, 0, ctl_bytes, c->stream));
+    const unsigned int gs = std::min<unsigned int>(nblk(n_in, 256), 148u * 8u);    // grid-stride passes: 2048 threads per SM
+    k_k8_stats<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st);
+    LAUNCH_CHECK();
+    k_k8_sample<<<std::min<unsigned int>(nblk(n_in, 256), 148u * 2u), 256, 0, c->stream>>>(c->in.p, n_in, st, chist);
+    LAUNCH_CHECK();
+    k_k8_plan<<<1, 1024, 0, c->stream>>>(st, chist, n_in, c->k8_ctab.p);
+    LAUNCH_CHECK();
+    k_k8_scatter<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->k8_ctab.p, fill, c->k8_skeys.p, c->k8_sidx.p, c->inv.p);
+    LAUNCH_CHECK();
+    k_k8_finish<<<(unsigned int)nfine_max, SK_K8_TPB, 0, c->stream>>>(st, fill, c->k8_skeys.p, c->k8_sidx.p, desc, c->uxs.p, c->inv.p);
+    LAUNCH_CHECK();
+    k_k8_identity<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->uxs.p, c->inv.p);
+    LAUNCH_CHECK();
+    k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, n_in, c->d_sum);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->h_scal->sum.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
+    general = c->h_scal->sum.overflow != 0;
+  }
+  if (general) {
+    int rc = targets_sort_general(c, n_in);
+    if (rc != SK_OK) return rc;
+  }
   const SkTargetSummary sm = c->h_scal->sum;
   if (sm.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
-  if (two_level && sm.overflow)                       // clustered input: more sorted bits, then the full sort
-    return targets_from_device_buffer(c, n_in, info, sort_bits < 32 ? 32 : (sort_bits < 40 ? 40 : 0));
   const long long nu = sm.n_unique;
-  c->sidx = sidx;                       // sorted position -> original position, for the final scatter
   c->n_in = n_in;
   c->n_unique = nu;
   c->r0 = sm.r0; c->r1 = sm.r1; c->r_last = sm.r_last;
   c->have_orig = false;
+  c->in_scale = 1.0;
+  c->tails.n = 0;
   c->has_zero = (sm.r0 == 0.0);
   c->have_targets = true;
   c->in_panel = false;
   c->staged = false;
   c->commit_pending = false;
   c->scan_hi = -1;
-  c->stats.sort_two_level = presorted ? 2 : (two_level ? 1 : 0);
+  c->stats.sort_two_level = general ? 0 : (sm.presorted ? 2 : 1);
   if (info) {
     info->n_in = n_in;
     info->n_unique = nu;
@@ -843,6 +844,7 @@ int sk_ctx_create(int device, sk_ctx **out) {
   sk_ctx *c = new sk_ctx();
   c->device = device;
   std::memset(&c->stats, 0, sizeof(c->stats));
+  std::memset(&c->tails, 0, sizeof(c->tails));
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc((void **)&c->d_red, sizeof(SkReduceOut)) != cudaSuccess ||
       cudaMalloc((void **)&c->d_sum, sizeof(SkTargetSummary)) != cudaSuccess ||
@@ -853,6 +855,7 @@ int sk_ctx_create(int device, sk_ctx **out) {
   }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
   for (int i = 0; i < 2; ++i) cudaEventCreate(&c->ev_user[i]);
+  if (const char *g = getenv("SK_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment
   if (sk_plan_make_es(width_from_eps(c->eps), &c->plan) != 0) {
     delete c;
     return SK_ERR_ARG;
@@ -892,6 +895,7 @@ int sk_ctx_destroy(sk_ctx *c) {
   if (c->d_kb) cudaFree(c->d_kb);
   c->keys.release(); c->keys_alt.release(); c->idx.release(); c->idx_alt.release();
   c->head.release(); c->uid.release(); c->inv.release(); c->cub_tmp.release();
+  c->k8_ctl.release(); c->k8_ctab.release(); c->k8_skeys.release(); c->k8_sidx.release();
   if (c->d_red) cudaFree(c->d_red);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -1239,6 +1243,8 @@ int sk_targets_scale(sk_ctx *c, double factor, sk_target_info *info) {
   k_scale_targets<<<nblk(c->n_unique, 256), 256, 0, c->stream>>>(c->uxs_orig.p, c->uxs.p, c->n_unique, factor);
   LAUNCH_CHECK();
   c->r0 = c->r0_orig * factor; c->r1 = c->r1_orig * factor; c->r_last = c->r_last_orig * factor;   // same rounding as the kernel
+  c->in_scale = factor;
+  c->tails.n = 0;
   c->in_panel = false;
   c->staged = false;
   c->commit_pending = false;
@@ -1275,6 +1281,7 @@ int sk_run_begin(sk_ctx *c) {
   c->stats.timing_enabled = t;
   c->stats.sort_two_level = two;
   CK(cudaMemsetAsync(c->res.p, 0, sizeof(sk_cplx) * c->n_unique, c->stream));   // ks = errs = 0, src/adaptive.jl:122
+  c->tails.n = 0;
   c->in_panel = false;
   c->staged = false;
   c->commit_pending = false;
@@ -1619,9 +1626,17 @@ int sk_converge_apply(sk_ctx *c, const sk_scan_args *a, int64_t new_hi) {
   if (rc != SK_OK) return rc;
   const long long nconv = c->hi - new_hi;                 // 0-based indices new_hi .. hi-1
   if (nconv > 0 && a->criteria != SK_CRIT_PANEL) {
-    k_scan_add<<<nblk(nconv, 256), 256, 0, c->stream>>>(c->uxs.p + new_hi, c->res.p + new_hi, nconv, a->trunc_a, a->trunc_num,
-                                                        a->xpow, a->criteria);
-    LAUNCH_CHECK();
+    if (c->tails.n < SK_MAX_TAILS) {
+      // errs[ix] += 2 trunc_err (src/adaptive.jl:194) rides along with the final gather: no pass of its own
+      SkTailSeg &t = c->tails.seg[c->tails.n++];
+      t.lo = new_hi; t.hi = c->hi;
+      t.trunc_a = a->trunc_a; t.trunc_num = a->trunc_num; t.xpow = a->xpow;
+      t.criteria = a->criteria; t._pad = 0;
+    } else {
+      k_scan_add<<<nblk(nconv, 256), 256, 0, c->stream>>>(c->uxs.p + new_hi, c->res.p + new_hi, nconv, a->trunc_a, a->trunc_num,
+                                                          a->xpow, a->criteria);
+      LAUNCH_CHECK();
+    }
   }
   c->in_panel = false;
   c->spec_active = false;
@@ -1646,7 +1661,7 @@ int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
   if (rc != SK_OK) return rc;
   rc = flush_commit(c);
   if (rc != SK_OK) return rc;
-  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, vals_dev, errs_dev);
+  k_gather<<<nblk(c->n_in, 1024), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, vals_dev, errs_dev, c->in.p, c->in_scale, c->tails);
   LAUNCH_CHECK();
   CK(cudaStreamSynchronize(c->stream));
   return SK_OK;
@@ -1662,7 +1677,8 @@ int sk_results_get(sk_ctx *c, double *vals, double *errs) {
   if (rc != SK_OK) return rc;
   CK(c->out_v.ensure(c->n_in));
   if (errs) CK(c->out_e.ensure(c->n_in));
-  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, c->out_v.p, errs ? c->out_e.p : nullptr);
+  k_gather<<<nblk(c->n_in, 1024), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, c->out_v.p, errs ? c->out_e.p : nullptr, c->in.p,
+                                                       c->in_scale, c->tails);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(vals, c->out_v.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
   if (errs) CK(cudaMemcpyAsync(errs, c->out_e.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
@@ -1695,8 +1711,8 @@ int sk_results_get_async(sk_ctx *c, double *vals, double *errs) {
   }
   CK(c->aout_v[slot].ensure(c->n_in));
   if (errs) CK(c->aout_e[slot].ensure(c->n_in));
-  k_gather<<<nblk(c->n_in, 256), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, c->aout_v[slot].p,
-                                                     errs ? c->aout_e[slot].p : nullptr);
+  k_gather<<<nblk(c->n_in, 1024), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, c->aout_v[slot].p,
+                                                       errs ? c->aout_e[slot].p : nullptr, c->in.p, c->in_scale, c->tails);
   LAUNCH_CHECK();
   CK(cudaEventRecord(c->ev_gather[slot], c->stream));
   CK(cudaStreamWaitEvent(c->copy_stream, c->ev_gather[slot], 0));

@@ -16,12 +16,14 @@
 //                                                                 src/adaptive.jl:163-164, :183-199
 //       k_scan_add          errs += 2 trunc_err for the converged tail   src/adaptive.jl:194
 //   K7  k_direct            direct Fourier summation              src/quadrature.jl:113-128
-//   K8  k_make_keys, k_run_rank, k_scatter_unique, k_target_summary, k_gather
-//                           unique/sort/scatter                   src/adaptive.jl:99-120
+//   K8  sk_k8.cuh (unique / sort / inverse map without a radix sort), k_gather
+//       k_make_keys, k_flag_heads, k_scatter_unique, k_target_summary: the general sort for inputs the bin
+//       scheme cannot take                                    src/adaptive.jl:99-120
 #pragma once
 #include <cuda_runtime.h>
 
 #include "sk_math.h"
+#include "sk_k8.cuh"
 
 #define SK_FLAG_NAN1 1u
 #define SK_FLAG_NAN2 2u
@@ -35,12 +37,6 @@ struct SkReduceOut {            // device scalars written by the reductions
   unsigned long long rbits;     // bit pattern of the distance at that index (0 if none)
 };
 
-struct SkTargetSummary {        // written by k_target_summary
-  long long n_unique;
-  double r0, r1, r_last;        // smallest, second smallest and largest unique distance
-  unsigned int bad;
-  unsigned int overflow;        // a run of equal high words was too long for the two-level sort
-};
 
 // Speculative commit (the common case: the first sub-interval of a panel is accepted and is the whole
 // panel).  The interpolation kernel then also does  ks += I2, errs += |I2-I1|  in place (keeping the old
@@ -856,64 +852,6 @@ k_make_keys(const double *__restrict__ xs, long long n, unsigned long long *__re
   }
 }
 
-// Second half of the two-level sort.  The radix sort ordered the pairs by 32 key bits only (4 digit
-// passes instead of 8, stable); `mask` selects those bits and everything above them (the bits above are
-// equal in all keys).  Runs of equal masked keys are short for real distance sets (a handful of elements),
-// so every element finds its run by walking left/right in a shared-memory tile (with a halo of SK_RR_HALO
-// keys on both sides) and ranks itself inside it on the full 64-bit key (ties: earlier position first =>
-// stable).  It writes itself to its final sorted position together with its "first of its value" flag.
-// A run that reaches the end of the halo raises *overflow and the caller falls back to the full sort.
-#define SK_RR_TILE 2048
-#define SK_RR_HALO 128
-__global__ void __launch_bounds__(256)
-k_run_rank(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ idx, long long n,
-           unsigned long long mask, unsigned long long *__restrict__ keys_out, unsigned int *__restrict__ idx_out,
-           unsigned int *__restrict__ head_out, unsigned int *__restrict__ overflow) {
-  __shared__ unsigned long long sk[SK_RR_TILE + 2 * SK_RR_HALO];
-  const long long t0 = (long long)blockIdx.x * SK_RR_TILE;          // first element of the tile
-  const long long g0 = t0 - SK_RR_HALO;                             // global index of sk[0]
-  for (int t = threadIdx.x; t < SK_RR_TILE + 2 * SK_RR_HALO; t += blockDim.x) {
-    const long long g = g0 + t;
-    sk[t] = (g >= 0 && g < n) ? keys[g] : 0ull;
-  }
-  __syncthreads();
-  const long long lo_g = g0 < 0 ? 0 : g0;                           // valid global range held in smem
-  const long long hi_g = (g0 + SK_RR_TILE + 2 * SK_RR_HALO) < n ? (g0 + SK_RR_TILE + 2 * SK_RR_HALO) : n;
-#pragma unroll 1
-  for (int u = 0; u < SK_RR_TILE / 256; ++u) {
-    const long long i = t0 + threadIdx.x + u * 256;
-    if (i >= n) break;
-    const unsigned long long k = sk[i - g0];
-    const unsigned long long hw = k & mask;
-    long long rank = 0;
-    bool first = true, over = false;
-    // a run longer than the halo cannot be ranked inside the tile: stop walking there (bounded work per element)
-    long long s = i;
-    const long long s_min = (i - SK_RR_HALO) > lo_g ? (i - SK_RR_HALO) : lo_g;
-    while (s > s_min && (sk[s - 1 - g0] & mask) == hw) {
-      --s;
-      const unsigned long long o = sk[s - g0];
-      if (o <= k) ++rank;                  // earlier position wins ties
-      if (o == k) first = false;
-    }
-    if (s == s_min && s > 0 && (sk[s - 1 - g0] & mask) == hw && s > lo_g) over = true;   // still inside the run after HALO steps
-    if (s == lo_g && s > 0) over = true;   // the run may continue beyond the halo
-    long long e = i + 1;
-    const long long e_max = (i + 1 + SK_RR_HALO) < hi_g ? (i + 1 + SK_RR_HALO) : hi_g;
-    while (e < e_max && (sk[e - g0] & mask) == hw) {
-      if (sk[e - g0] < k) ++rank;
-      ++e;
-    }
-    if (e == e_max && e < hi_g && (sk[e - g0] & mask) == hw) over = true;
-    if (e == hi_g && e < n) over = true;
-    if (over) { atomicOr(overflow, 1u); continue; }
-    const long long pos = s + rank;
-    keys_out[pos] = k;
-    idx_out[pos] = idx[i];
-    head_out[pos] = first ? 1u : 0u;
-  }
-}
-
 __global__ void k_flag_heads(const unsigned long long *__restrict__ keys, long long n, unsigned int *__restrict__ head) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -933,16 +871,6 @@ __global__ void k_scatter_unique(const unsigned long long *__restrict__ keys, co
   if ((long long)idx[j] < n) inv[idx[j]] = u;
 }
 
-// already sorted and unique input: the unique table is the input itself and the inverse map is the identity
-__global__ void k_identity_targets(const unsigned long long *__restrict__ keys, long long n, double *__restrict__ uxs,
-                                   unsigned int *__restrict__ inv, unsigned int *__restrict__ uid_incl) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  uxs[j] = __longlong_as_double((long long)keys[j]);
-  inv[j] = (unsigned int)j;
-  if (j == n - 1) uid_incl[j] = (unsigned int)n;       // what k_target_summary reads
-}
-
 __global__ void k_target_summary(const double *__restrict__ uxs, const unsigned int *__restrict__ uid_incl, long long n,
                                  const SkKeyBits *__restrict__ kb, SkTargetSummary *__restrict__ out) {
   long long nu = uid_incl[n - 1];
@@ -953,18 +881,66 @@ __global__ void k_target_summary(const double *__restrict__ uxs, const unsigned 
   out->r1 = nu > 1 ? uxs[1] : 0.0;
   out->r_last = uxs[nu - 1];
   out->bad = kb->bad;
+  out->presorted = 0u;
+  out->_pad = 0u;
 }
 
 // values and errors back in the ORIGINAL input order (src/adaptive.jl:105-107) from res = (ks, errs): one
 // 16-byte random read per target (random reads are ~2.5x cheaper than the random 8-byte writes of a
-// scatter from sorted order, measured: profiles/r1_c_launches.txt)
-__global__ void k_gather(const unsigned int *__restrict__ inv, const sk_cplx *__restrict__ res, long long n,
-                         double *__restrict__ out_v, double *__restrict__ out_e) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const sk_cplx r = res[inv[j]];
-  out_v[j] = r.x;
-  if (out_e) out_e[j] = r.y;
+// scatter from sorted order, measured: profiles/r1_c_launches.txt).
+//
+// The truncation term of the error estimate, errs[ix] += 2 trunc_err for the targets a panel's scan found converged
+// (src/adaptive.jl:194), is applied HERE instead of in a pass of its own: every unique target belongs to at most one
+// converged tail [lo, hi) (the panel after which it left the active set), nothing touches it afterwards, and the
+// bound depends on the target only through its distance -- which is the input distance x[j] itself (times the
+// warping factor of sk_targets_scale), read coalesced.  Same operands, same operations, same rounding as k_scan_add.
+#define SK_MAX_TAILS 48
+struct SkTailSeg {
+  long long lo, hi;                       // 0-based unique ids [lo, hi)
+  double trunc_a, trunc_num, xpow;
+  int criteria, _pad;
+};
+struct SkTailList {
+  int n, _pad;
+  SkTailSeg seg[SK_MAX_TAILS];
+};
+__global__ void __launch_bounds__(256)
+k_gather(const unsigned int *__restrict__ inv, const sk_cplx *__restrict__ res, long long n,
+         double *__restrict__ out_v, double *__restrict__ out_e, const double *__restrict__ xin, double xscale,
+         const __grid_constant__ SkTailList T) {
+  // 4 independent random reads in flight per thread (the kernel is bound by the latency of the 16-byte reads)
+  const long long j0 = ((long long)blockIdx.x * blockDim.x) * 4 + threadIdx.x;
+  unsigned int u[4];
+  sk_cplx r[4];
+  double x[4];
+  const bool tails = out_e != nullptr && T.n > 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long j = j0 + (long long)i * 256;
+    u[i] = j < n ? __ldg(&inv[j]) : 0u;
+    x[i] = (tails && j < n) ? xin[j] : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = res[u[i]];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long j = j0 + (long long)i * 256;
+    if (j < n) {
+      out_v[j] = r[i].x;
+      if (out_e) {
+        double e = r[i].y;
+        if (tails) {
+          for (int s = 0; s < T.n; ++s)
+            if ((long long)u[i] >= T.seg[s].lo && (long long)u[i] < T.seg[s].hi) {
+              const double xx = xscale == 1.0 ? x[i] : sk_mul(x[i], xscale);     // the unique table's own rounding
+              e += 2 * sk_trunc_err(T.seg[s].trunc_a, T.seg[s].trunc_num, T.seg[s].xpow, xx, T.seg[s].criteria == 0);
+              break;
+            }
+        }
+        out_e[j] = e;
+      }
+    }
+  }
 }
 
 // lags of point pairs, computed where they are consumed (src/model.jl:53-68: warp_lags = norm(x_j - x_k) for

@@ -424,7 +424,10 @@ SK_HD double sk_trunc_err(double trunc_a, double trunc_num, double xpow, double 
   if (criteria_panel) return 0.0;  // src/adaptive.jl:186
   const double xp = (xpow == 1.0) ? x : pow(x, xpow);
   const double t2 = trunc_num / sk_mul(6.283185307179586, xp);   // 2pi*x^((dim+1)/2)
-  return fmin(trunc_a, t2);        // Julia's min(a, b); NaN handling: see sk_converged
+  // Julia's min(a, b) propagates a NaN operand (C's fmin drops it): a NaN bound then fails `trunc_err < tol`
+  // in sk_converged, i.e. the target stays active, exactly as in src/adaptive.jl:185-197
+  if (trunc_a != trunc_a || t2 != t2) return trunc_a + t2;
+  return fmin(trunc_a, t2);
 }
 SK_HD bool sk_converged(double trunc_err, double panel_k, double tau, int criteria) {
   // (criteria == :panel || trunc_err < tol) && (criteria == :tails || abs(panel_k) < tol)

@@ -4,6 +4,7 @@
 // a machine without a GPU.  It is not a product path: nothing in spectralkernels.jl_b200/ loads it.
 #include "sk_host_util.h"
 #include "sk_rules.cuh"
+#include "sk_k8.h"
 
 #include <algorithm>
 #include <cstring>
@@ -288,4 +289,126 @@ void emul_hk_eval_cells(const SkEsPlan *P, const SkHankelPlan *H, const SkHankel
   }
   *ncell_path = cnt;
 }
+
+// K8 (csrc/sk_k8.cuh) in plain loops with the index arithmetic of csrc/sk_k8.h: stats, sampled coarse histogram,
+// plan, scatter into fine bins, per-bin counting sort + group ranks + heads, sequential prefix instead of the
+// look-back.  Returns 0 (ok), 1 (a fine bin overflowed: the product then takes the general sort), 2 (invalid input),
+// 3 / 4 (a bug: fine bin out of range / fine-bin map not monotone).
+// diag[0] = number of fine bins, diag[1] = largest fill, diag[2] = largest sub-bin group, diag[3] = presorted.
+int emul_k8(const double *xs, long long n, unsigned int samp, double *uxs, unsigned int *inv, long long *n_unique,
+            long long *diag) {
+  auto keyof = [](double x, bool *bad) -> unsigned long long {
+    if (!(x >= 0.0) || std::isinf(x)) { *bad = true; x = 0.0; }
+    if (x == 0.0) x = 0.0;
+    unsigned long long k;
+    std::memcpy(&k, &x, 8);
+    return k;
+  };
+  bool bad = false;
+  unsigned long long kmin = ~0ull, kmax = 0ull, nzero = 0ull, ndesc = 0ull;
+  for (long long j = 0; j < n; ++j) {
+    const unsigned long long k = keyof(xs[j], &bad);
+    if (j > 0 && !(xs[j] > xs[j - 1])) ++ndesc;
+    if (k == 0ull) ++nzero; else { kmin = std::min(kmin, k); kmax = std::max(kmax, k); }
+  }
+  if (bad) return 2;
+  diag[0] = diag[1] = diag[2] = 0;
+  const bool unsorted = ndesc != 0ull;
+  if (samp == 0u) samp = sk_k8_samp((unsigned long long)n, ndesc);     // 0: the product's choice
+  diag[3] = unsorted ? 0 : 1;
+  if (!unsorted) {
+    for (long long j = 0; j < n; ++j) { uxs[j] = xs[j] == 0.0 ? 0.0 : xs[j]; inv[j] = (unsigned int)j; }
+    *n_unique = n;
+    return 0;
+  }
+  const unsigned long long npos = (unsigned long long)n - nzero;
+  std::vector<unsigned int> chist(SK_K8_NC, 0u), ccum(SK_K8_NC), ccnt(SK_K8_NC);
+  unsigned long long mul = 0;
+  unsigned int nfine = 0;
+  if (npos) {
+    mul = sk_k8_mul(kmin, kmax);
+    unsigned long long sampled = 0;
+    for (long long s = 0; s < (n + 31) / 32; ++s) {
+      if (!sk_k8_sampled((unsigned long long)s, samp)) continue;
+      for (long long j = s * 32; j < std::min<long long>(n, s * 32 + 32); ++j) {
+        bool b2 = false;
+        const unsigned long long k = keyof(xs[j], &b2);
+        if (k) {
+          unsigned int cb;
+          unsigned long long frac;
+          sk_k8_coarse(k, kmin, mul, &cb, &frac);
+          if (cb >= (unsigned int)SK_K8_NC) return 3;
+          ++chist[cb];
+          ++sampled;
+        }
+      }
+    }
+    const bool single = npos <= (unsigned long long)SK_K8_CAP;
+    auto scaled = [&](unsigned long long cum) { return sampled ? cum * npos / sampled : 0ull; };
+    unsigned long long run = 0;
+    for (int c = 0; c < SK_K8_NC; ++c) {
+      const unsigned long long lo = scaled(run), hi = scaled(run + chist[c]);
+      run += chist[c];
+      ccum[c] = single ? 0u : (unsigned int)lo;
+      ccnt[c] = single ? 0u : (unsigned int)(hi - lo);
+    }
+    nfine = single ? 1u : (unsigned int)((scaled(sampled) >> SK_K8_TARGET_LOG) + 1ull);
+  }
+  diag[0] = nfine;
+  if ((unsigned long long)nfine > (unsigned long long)(n >> SK_K8_TARGET_LOG) + 2ull) return 3;   // the host's bound
+  std::vector<std::vector<std::pair<unsigned long long, unsigned int>>> bins(nfine);
+  for (long long j = 0; j < n; ++j) {
+    bool b2 = false;
+    const unsigned long long k = keyof(xs[j], &b2);
+    if (k == 0ull) { inv[j] = 0u; continue; }
+    const unsigned int f = sk_k8_fine_bin(k, kmin, mul, ccum.data(), ccnt.data());
+    if (f >= nfine) return 3;                                        // would be out of bounds on the device
+    bins[f].push_back({k, (unsigned int)j});
+  }
+  int rc = 0;
+  unsigned long long uoff = nzero ? 1ull : 0ull;
+  if (nzero) uxs[0] = 0.0;
+  unsigned long long last_hi = 0ull;
+  for (unsigned int f = 0; f < nfine; ++f) {
+    auto &B = bins[f];
+    const int cnt = (int)B.size();
+    diag[1] = std::max<long long>(diag[1], cnt);
+    if (cnt > SK_K8_CAP) { rc = 1; continue; }
+    if (cnt == 0) continue;
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (auto &e : B) { lo = std::min(lo, e.first); hi = std::max(hi, e.first); }
+    if (lo < last_hi) return 4;                                      // the fine-bin map is not monotone
+    last_hi = hi;
+    const double scale = sk_k8_ssb_scale(lo, hi);
+    std::vector<int> off(SK_K8_NSSB + 1, 0), ssb(cnt), rk(cnt);
+    for (int t = 0; t < cnt; ++t) { ssb[t] = sk_k8_ssb(B[t].first, lo, scale); rk[t] = off[ssb[t]]++; }
+    int run = 0;
+    for (int i = 0; i <= SK_K8_NSSB; ++i) { const int c = i < SK_K8_NSSB ? off[i] : 0; off[i] = run; run += c; }
+    std::vector<unsigned long long> placed(cnt), fin_key(cnt);
+    std::vector<unsigned char> head(cnt);
+    std::vector<int> fin(cnt);
+    for (int t = 0; t < cnt; ++t) placed[off[ssb[t]] + rk[t]] = B[t].first;
+    for (int t = 0; t < cnt; ++t) {
+      const int o = off[ssb[t]], ge = off[ssb[t] + 1], me = o + rk[t];
+      diag[2] = std::max<long long>(diag[2], ge - o);
+      int less = 0, eqb = 0;
+      for (int p = o; p < ge; ++p) { less += placed[p] < B[t].first; eqb += (placed[p] == B[t].first) && (p < me); }
+      fin[t] = o + less + eqb;
+      fin_key[fin[t]] = B[t].first;
+      head[fin[t]] = eqb == 0;
+    }
+    std::vector<int> luid(cnt);
+    int h = 0;
+    for (int p = 0; p < cnt; ++p) {
+      h += head[p];
+      luid[p] = h;
+      if (head[p]) std::memcpy(&uxs[uoff + h - 1], &fin_key[p], 8);
+    }
+    for (int t = 0; t < cnt; ++t) inv[B[t].second] = (unsigned int)(uoff + luid[fin[t]] - 1);
+    uoff += h;
+  }
+  *n_unique = (long long)uoff;
+  return rc;
 }
+
+}  // extern "C"

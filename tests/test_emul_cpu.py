@@ -193,6 +193,14 @@ def test_convergence_predicate(emul):
     tn = c * b ** (d + (dim - 1) / 2)
     for x in (1e-6, 1e-3, 0.5, 1.0):
         assert L.emul_trunc_err(ta, tn, 1.0, x, 0) == so.truncation_error_estimate(b, x, c, d, dim)
+    # Julia's min propagates NaN (src/adaptive.jl:225-228): a NaN bound keeps the target active; +-Inf order normally
+    nan, inf = float("nan"), float("inf")
+    for ta_, tn_ in ((nan, 1.0), (1.0, nan), (nan, nan), (inf, nan), (nan, -inf)):
+        assert np.isnan(L.emul_trunc_err(ta_, tn_, 1.0, 0.5, 0))
+        assert not L.emul_converged(L.emul_trunc_err(ta_, tn_, 1.0, 0.5, 0), 0.0, 5e-9, 1)
+    assert L.emul_trunc_err(inf, 1.0, 1.0, 0.5, 0) == 1.0 / np.pi
+    assert L.emul_trunc_err(-inf, 1.0, 1.0, 0.5, 0) == -inf
+    assert L.emul_trunc_err(1.0, inf, 1.0, 0.5, 0) == 1.0
     for crit, name in ((0, "panel"), (1, "tails"), (2, "both")):
         for te in (1e-10, 1e-7):
             for pk in (1e-10, -1e-7):
@@ -377,3 +385,77 @@ def test_hankel_transform_math(emul, nu, alpha):
         ref = so.direct_bessel(nu, no2, b2, xs3)
         assert np.max(np.abs(got[:, 1] - ref)) <= 5e-15 * np.sum(np.abs(b2))
         assert np.max(np.abs(info[6][:, 1] - got[:, 1])) <= 1e-15 * np.sum(np.abs(b2))
+
+
+# ---- K8: unique / sort / inverse map (csrc/sk_k8.h index arithmetic, csrc/sk_k8.cuh steps) ---------------------
+def _k8(emul, xs, samp=None):
+    L, _ = emul
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    n = xs.size
+    if samp is None:
+        samp = 0                                   # the product's choice (sk_k8_samp)
+    uxs = np.empty(n)
+    inv = np.empty(n, dtype=np.uint32)
+    nu = ctypes.c_longlong()
+    diag = (ctypes.c_longlong * 4)()
+    L.emul_k8.argtypes = [dp, ctypes.c_longlong, ctypes.c_uint, dp, ctypes.POINTER(ctypes.c_uint32),
+                          ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]
+    rc = L.emul_k8(_ptr(xs), n, samp, _ptr(uxs), inv.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.byref(nu), diag)
+    return rc, uxs[: nu.value], inv, list(diag)
+
+
+def _k8_check(emul, xs, samp=None, expect_rc=0):
+    rc, uxs, inv, diag = _k8(emul, xs, samp)
+    assert rc == expect_rc, (rc, diag)
+    if rc == 0:
+        ref, rinv = np.unique(np.where(xs == 0, 0.0, xs), return_inverse=True)
+        assert np.array_equal(uxs, ref)
+        assert np.array_equal(inv, rinv.astype(np.uint32))
+    return diag
+
+
+def test_k8_distributions(emul):
+    """The bin scheme sorts and de-duplicates exactly (vs numpy.unique) on the distance sets of the BASELINE configs
+    and stays inside its slots: uniform, log-uniform, pairwise distances of random 2-D points, a pair list with a
+    heavy zero lag and duplicated lags, tiny inputs, presorted input, constant input."""
+    rng = np.random.default_rng(0)
+    d = _k8_check(emul, rng.uniform(0, 1, 2_000_000))                       # config 2 (sampled histogram)
+    assert d[1] <= 1400 and d[2] <= 12 and d[3] == 0
+    d = _k8_check(emul, rng.uniform(0, 1e3, 300_000))
+    assert d[1] <= 1400
+    d = _k8_check(emul, 10 ** rng.uniform(-6, 0, 1_500_000))                # log-uniform (shrinking active sets)
+    assert d[1] <= 1500
+    pts = rng.uniform(0, 1, (1500, 2))                                      # config 3: all pairwise distances
+    iu = np.triu_indices(1500, 1)
+    lag = np.sqrt(((pts[iu[0]] - pts[iu[1]]) ** 2).sum(1))
+    d = _k8_check(emul, lag)
+    assert d[1] <= 1500
+    # config 5: a pair list with ~12% zero lags (the diagonal of every block) and every lag repeated a few times
+    base = rng.uniform(0, 0.05, 150_000)
+    lagv = np.concatenate([np.zeros(60_000), np.repeat(base, 3), base[:30_000]])
+    rng.shuffle(lagv)
+    d = _k8_check(emul, lagv)
+    assert d[1] <= 1500
+    for n in (1, 2, 3, 100, 2048, 2049, 5000):                              # small inputs, around the single-bin limit
+        _k8_check(emul, rng.uniform(0, 2, n))
+    _k8_check(emul, np.zeros(7))
+    _k8_check(emul, np.array([0.0, 0.3, 0.0, 0.3, 1e-300, 5e-324, 1.7e308]))
+    _k8_check(emul, np.full(1000, 0.25))                                    # one value, 1000 times: one group of 1000
+    d = _k8_check(emul, np.sort(rng.uniform(0, 1, 5000)))
+    assert d[3] == 1                                                        # presorted: identity
+    srt = np.sort(rng.uniform(0, 1, 3_000_000))
+    srt[1000] = srt[999]                                                    # sorted but not unique: the bins must cope
+    d = _k8_check(emul, srt)
+    assert d[3] == 0 and d[1] <= 1500
+    per = np.tile(rng.uniform(0, 1, 256), 8192)                             # periodic input, period = 256 = 8 segments
+    _k8_check(emul, per, expect_rc=1)                                       # 256 values x 8192 copies: general sort
+    assert _k8(emul, np.array([0.5, -1.0]))[0] == 2 and _k8(emul, np.array([0.5, np.nan]))[0] == 2
+
+
+def test_k8_clustered_input_overflows_cleanly(emul):
+    """Heavily clustered distances outgrow a fine bin: reported (the product then takes the general sort), never wrong."""
+    rng = np.random.default_rng(4)
+    spread = rng.uniform(0, 2.0, 5000)
+    clustered = 0.5 + rng.uniform(0, 1e-9, 3000)
+    rc, _, _, diag = _k8(emul, np.concatenate([spread, clustered]))
+    assert rc == 1 and diag[1] > 2048
