@@ -37,15 +37,27 @@ import numpy as np  # noqa: E402
 # algorithmic work per unit = one (active target, sub-interval) pair
 FLOPS_PER_UNIT_SURVEY = 764     # F_fused: per-target tap polynomials shared by the m- and 2m-rule grids
 # FP64 flops k_interp_cells actually executes per unit at the benchmark's density (ncu op counters:
-# 87.6 DFMA + 21.4 DADD + 16.1 DMUL per target, profiles/r1_d_interp_cells_ncu.txt): cell polynomials
+# DFMA, DADD, DMUL per target; refreshed from profiles/r2_traffic.json when that file is present): cell polynomials
 # replace the per-target tap evaluation, so far fewer flops are needed for the same result
 FLOPS_PER_UNIT_EXECUTED = 2 * 87.6 + 21.4 + 16.1
 # interpolation kernel with the fused (speculative) commit: read r (8) + read (ks,errs) (16) + write (ks,errs)
 # (16) + write the roll-back copy (16)
 BYTES_PER_UNIT_K4 = 56
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_interp_cells launch over 1e7 targets (ncu --set full,
-# profiles/r1_d_interp_cells_ncu.txt)
-K4_DRAM_TRAFFIC_BYTES_1E7 = 242.2e6 + 263.7e6
+# K8 (unique / sort / inverse map, csrc/sk_k8.cuh) per input distance: stats 8 + sample 1 + scatter 8 + 12 + finish
+# 12 + 8 + 4; gather to the input order: inv 4 + (ks, errs) 16 + distance 8 + values and errors 16
+BYTES_PER_INPUT_K8 = 53
+BYTES_PER_INPUT_GATHER = 44
+WORKLOAD = ("matern nu=1.5 rho=1 K(0)=1, r~U(0,1) seed=rank unsorted, tol=1e-8, quadspec (4096,16), :both "
+            "(BASELINE config 2)")
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture
+    of this same command (scripts/ncu_summary.py writes profiles/r2_traffic.json); None when no capture is committed."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    except Exception:
+        return None
 
 
 def parse():
@@ -58,6 +70,10 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=10_000_000, help="distances in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--interp-mode", type=int, default=0, help="0 cells (default), 1 per-target taps, 2 cells @4 blocks/SM")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: n distances per GPU (the headline line); strong: the n distances of the BASELINE workload "
+                         "split over the GPUs.  The weak line always carries the strong-scaling leg as well (key 'strong')")
+    ap.add_argument("--no-strong-leg", action="store_true")
     return ap.parse_args()
 
 
@@ -138,15 +154,15 @@ def oracle_cpu_run(n_sample: int, steps: int, warmup: int):
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return None
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(3, args.warmup)       # the same K and W as the repo's arm
     r = oracle_cpu_run(args.cpu_sample, steps, warmup)
     line = {
         "impl": "reference", "metric": "K(r) evals/sec at tol=1e-8 (Matern S, 1e7 r)", "value": r["evals_per_s"],
         "unit": "evals/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "matern nu=1.5 rho=1 K(0)=1, r~U(0,1) seed 0, tol=1e-8, quadspec (4096,16), :both",
-                   "n_per_step": args.cpu_sample, "full_n": 10_000_000,
+        "config": {"workload": WORKLOAD, "n_per_gpu": args.cpu_sample, "n_per_step": args.cpu_sample, "full_n": 10_000_000,
+                   "warmup_note": "warm-up steps run on a 1/50 sample (untimed; they only fault the pages in)",
                    "note": "reference (Julia+FINUFFT) cannot run in this image; this is the oracle port of its CPU "
                            "path (CPU restatement, not FINUFFT), all host threads, bounded sample per step"},
         "cpu_baseline": {"value": r["evals_per_s"], "unit": "evals/s", "cores": r["threads"], "kind": "port",
@@ -202,7 +218,6 @@ def run(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n = args.n
     W = max(3, args.warmup)
     K = max(1, args.steps)
     phi, rho, nu = workload_sdf_params()
@@ -215,71 +230,94 @@ def run(args):
     if args.interp_mode:
         eng.set_interp_mode(args.interp_mode)
     k0 = 1.0
-
-    # synthetic distances: pinned host copy (e2e) and device copy (resident)
-    host_in = sk.PinnedArray(n)
-    host_in.array[:] = make_distances(n, rank)
-    host_v, host_e = sk.PinnedArray(n), sk.PinnedArray(n)
-    d_in = torch.from_numpy(host_in.array).to(f"cuda:{local_rank}")
-    d_v = torch.empty(n, dtype=torch.float64, device=d_in.device)
-    d_e = torch.empty(n, dtype=torch.float64, device=d_in.device)
-    torch.cuda.synchronize()
-
-    def step_resident(trace=None):
-        sk.kernel_values(cfg, None, k0=k0, xs_device=(d_in.data_ptr(), n), out_device=(d_v.data_ptr(), d_e.data_ptr()),
-                         comm=comm, trace=trace)
-
-    def step_e2e():
-        sk.kernel_values(cfg, host_in.array, k0=k0, comm=comm, out_vals=host_v.array, out_errs=host_e.array)
-
-    # ---- device-resident: warm-up, then K timed steps ------------------------------------------------
-    trace = []
-    step_resident(trace)
-    for _ in range(W - 1):
-        step_resident()
-    eng.set_timing(True)
     import gc
-    gc.collect()
-    gc.disable()                      # no collector pauses inside the timed regions (ranks wait for each other)
-    sampler = ClockSampler(local_rank if rank == 0 else -1)   # one sampler per job: nvidia-smi queries take a driver lock
-    agg = {"units": 0, "interp_ms": 0.0, "source_ms": 0.0, "launches": 0, "subintervals": 0}
-    barrier()
-    sampler.start()
-    eng.timer_begin()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        step_resident()
-        st = eng.stats()
-        agg["units"] += st["units"]; agg["interp_ms"] += st["interp_ms"]; agg["source_ms"] += st["source_ms"]
-        agg["launches"] += st["kernel_launches"]; agg["subintervals"] += st["n_subintervals"]
-    dev_ms = eng.timer_end()
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    clocks = sampler.stop()
-    eng.set_timing(False)
-    res_ms = max(dev_ms, 0.0)
 
-    # ---- end to end (host buffers) ---------------------------------------------------------------------
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        step_e2e()
-    barrier()
-    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    def measure(xs_local: np.ndarray, sample_clocks: bool):
+        """W warm-up + K timed resident steps, then K timed end-to-end steps, on this rank's distances."""
+        n = xs_local.size
+        host_in = sk.PinnedArray(n)
+        host_in.array[:] = xs_local
+        host_v, host_e = sk.PinnedArray(n), sk.PinnedArray(n)
+        d_in = torch.from_numpy(host_in.array).to(f"cuda:{local_rank}")
+        d_v = torch.empty(n, dtype=torch.float64, device=d_in.device)
+        d_e = torch.empty(n, dtype=torch.float64, device=d_in.device)
+        torch.cuda.synchronize()
 
-    # max over ranks
-    if world > 1:
-        t = torch.tensor([res_ms, e2e_ms, wall_ms], dtype=torch.float64, device=d_in.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        res_ms, e2e_ms, wall_ms = t.tolist()
+        def step_resident(trace=None):
+            sk.kernel_values(cfg, None, k0=k0, xs_device=(d_in.data_ptr(), n), out_device=(d_v.data_ptr(), d_e.data_ptr()),
+                             comm=comm, trace=trace)
 
-    # parity spot check of the timed configuration (closed form of Matern nu = 3/2)
-    true = (1 + 2 * np.pi * host_in.array) * np.exp(-2 * np.pi * host_in.array)
-    max_err = float(np.max(np.abs(host_v.array - true)))
-    same = bool(torch.equal(d_v.cpu(), torch.from_numpy(host_v.array)))
+        def step_e2e():
+            sk.kernel_values(cfg, host_in.array, k0=k0, comm=comm, out_vals=host_v.array, out_errs=host_e.array)
 
+        trace = []
+        step_resident(trace)
+        for _ in range(W - 1):
+            step_resident()
+        eng.set_timing(True)
+        gc.collect()
+        gc.disable()                  # no collector pauses inside the timed regions (ranks wait for each other)
+        sampler = ClockSampler(local_rank if (rank == 0 and sample_clocks) else -1)   # nvidia-smi takes a driver lock
+        agg = {"units": 0, "interp_ms": 0.0, "source_ms": 0.0, "sort_ms": 0.0, "gather_ms": 0.0, "launches": 0,
+               "subintervals": 0}
+        barrier()
+        sampler.start()
+        t0 = time.perf_counter()
+        eng.timer_begin()
+        for _ in range(K):
+            step_resident()
+            st = eng.stats()
+            for key_, src in (("units", "units"), ("interp_ms", "interp_ms"), ("source_ms", "source_ms"), ("sort_ms", "sort_ms"),
+                              ("gather_ms", "gather_ms"), ("launches", "kernel_launches"), ("subintervals", "n_subintervals")):
+                agg[key_] += st[src]
+        dev_ms = eng.timer_end()
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        clocks = sampler.stop()
+        eng.set_timing(False)
+        # the per-stage timers add event synchronisations to the step: time the same K steps once more without them
+        barrier()
+        eng.timer_begin()
+        for _ in range(K):
+            step_resident()
+        res_ms = max(eng.timer_end(), 0.0)
+        barrier()
+        # end to end (host buffers)
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_e2e()
+        barrier()
+        e2e_ms = 1e3 * (time.perf_counter() - t0)
+        gc.enable()
+        if world > 1:
+            t = torch.tensor([res_ms, e2e_ms, wall_ms, dev_ms], dtype=torch.float64, device=d_in.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res_ms, e2e_ms, wall_ms, dev_ms = t.tolist()
+        true = (1 + 2 * np.pi * host_in.array) * np.exp(-2 * np.pi * host_in.array)
+        max_err = float(np.max(np.abs(host_v.array - true)))
+        same = bool(torch.equal(d_v.cpu(), torch.from_numpy(host_v.array)))
+        out = {"n": n, "res_ms": res_ms, "timed_stage_ms": dev_ms, "e2e_ms": e2e_ms, "wall_ms": wall_ms, "agg": agg,
+               "clocks": clocks, "trace": trace, "max_err": max_err, "same": same}
+        del d_in, d_v, d_e
+        host_in.free(); host_v.free(); host_e.free()
+        return out
+
+    n = args.n
+    strong_only = args.scaling == "strong"
+    weak = None if strong_only else measure(make_distances(n, rank), True)
+    strong = None
+    if (world > 1 or strong_only) and not args.no_strong_leg:
+        # the BASELINE workload itself (n distances, seed 0) split over the GPUs: contiguous chunks of the drawn order
+        full = make_distances(n, 0)
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        strong = measure(full[lo:hi].copy(), strong_only)
+        del full
+    main_ = strong if strong_only else weak
+
+    line = None
     if rank == 0:
         peaks = {}
         try:
@@ -288,51 +326,79 @@ def run(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        fp64_tf, _ = eng.fp64_peak()
+        fp64_tf, fp64_ms = eng.fp64_peak()
+        agg, res_ms, e2e_ms = main_["agg"], main_["res_ms"], main_["e2e_ms"]
+        nloc = main_["n"]
+        total = nloc * world if not strong_only else n
         n_launch = max(1, agg["subintervals"])
         units_per_launch = agg["units"] / n_launch
         k4_ms = agg["interp_ms"] / n_launch
-        ach_tf = units_per_launch * FLOPS_PER_UNIT_SURVEY / (k4_ms * 1e-3) / 1e12 if k4_ms > 0 else None
-        exe_tf = units_per_launch * FLOPS_PER_UNIT_EXECUTED / (k4_ms * 1e-3) / 1e12 if k4_ms > 0 else None
+        tr = measured_traffic() or {}
+        exe_fpu = float(tr.get("executed_flops_per_unit", FLOPS_PER_UNIT_EXECUTED))
+        alg_tf = units_per_launch * FLOPS_PER_UNIT_SURVEY / (k4_ms * 1e-3) / 1e12 if k4_ms > 0 else None
+        exe_tf = units_per_launch * exe_fpu / (k4_ms * 1e-3) / 1e12 if k4_ms > 0 else None
         ach_gbs = units_per_launch * BYTES_PER_UNIT_K4 / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else None
+        ms_step = res_ms / K
+        # step level: every (target, sub-interval) unit of the step at SURVEY's algorithmic 764 flops against the FP64 peak,
+        # over the whole resident step (sort, source side, interpolation, gather, host round trips)
+        step_roof_ms = (agg["units"] / K) * FLOPS_PER_UNIT_SURVEY / (fp64_tf * 1e12) * 1e3
+        sort_ms, gather_ms = agg["sort_ms"] / K, agg["gather_ms"] / K
+        k8 = {"kernel": "K8 unique/sort/inverse map (sk_k8.cuh) + gather", "bound": "hbm", "unit": "GB/s", "peak": hbm_peak,
+              "sort_ms": sort_ms, "gather_ms": gather_ms,
+              "achieved": nloc * (BYTES_PER_INPUT_K8 + BYTES_PER_INPUT_GATHER) / ((sort_ms + gather_ms) * 1e-3) / 1e9
+              if (sort_ms + gather_ms) > 0 else None,
+              "bytes_per_input": BYTES_PER_INPUT_K8 + BYTES_PER_INPUT_GATHER}
+        k8["frac"] = k8["achieved"] / hbm_peak if k8["achieved"] else None
         line = {
             "metric": "K(r) evals/sec at tol=1e-8 (Matern S, 1e7 r)",
-            "value": world * n * K / (res_ms * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": res_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "matern nu=1.5 rho=1 K(0)=1, r~U(0,1) seed=rank unsorted, tol=1e-8, "
-                                   "quadspec (4096,16), :both (BASELINE config 2)",
-                       "n_per_gpu": n, "k0": "passed (=1.0) in both arms", "nufft_eps": 1e-15,
+            "value": total * K / (res_ms * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong_only else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD,
+                       "n_per_gpu": nloc, "k0": "passed (=1.0) in both arms", "nufft_eps": 1e-15,
                        "l2": "inputs + work arrays (>1 GB per step) exceed the 126 MB L2; no explicit flush",
                        "parallelism": ("target-sharded, scalar NCCL all-reduces only ("
                                        + ("in-library, on the compute stream" if getattr(comm, "fused", False) else "torch.distributed")
                                        + ")") if world > 1 else "single GPU",
                        "cpu_affinity": "each rank pinned to its GPU's local CPUs (NVML)" if numa_bound else "default",
-                       "panels": [(t["a"], t["b"], t["hi_before"], t["hi_after"]) for t in trace if t["kind"] == "panel"]},
-            "e2e": {"value": world * n * K / (e2e_ms * 1e-3), "unit": "evals/s", "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 16 * n,
+                       "panels": [(t["a"], t["b"], t["hi_before"], t["hi_after"]) for t in main_["trace"] if t["kind"] == "panel"]},
+            "e2e": {"value": total * K / (e2e_ms * 1e-3), "unit": "evals/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": 8 * nloc, "d2h_bytes_per_step": 16 * nloc,
                     "note": "kernel_values with pinned host buffers; values and errors both copied back"},
             "gpu_launches": int(agg["launches"]),
-            "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "k_interp_cells<16>", "achieved": ach_tf, "peak": fp64_tf,
-                         "unit": "TFLOP/s", "frac": (ach_tf / fp64_tf) if ach_tf else None,
-                         "traffic": K4_DRAM_TRAFFIC_BYTES_1E7 * units_per_launch / 1e7,
-                         "flops_per_unit": FLOPS_PER_UNIT_SURVEY,
-                         "note": "achieved/frac use SURVEY 8(d)'s ALGORITHMIC figure (764 flops per unit, per-target "
-                                 "tap evaluation); the kernel reaches the same result with cell polynomials, so "
-                                 "fewer flops are executed: see executed_*",
-                         "executed_flops_per_unit": FLOPS_PER_UNIT_EXECUTED, "executed_achieved": exe_tf,
-                         "executed_frac": (exe_tf / fp64_tf) if exe_tf else None,
+            "clocks": main_["clocks"],
+            "roofline": {"bound": "fp64", "kernel": "k_interp_cells<16>", "achieved": exe_tf, "peak": fp64_tf,
+                         "unit": "TFLOP/s", "frac": (exe_tf / fp64_tf) if exe_tf else None,
+                         "traffic": tr.get("interp_cells_dram_bytes_per_launch"),
+                         "traffic_source": tr.get("source", "no ncu capture committed for this build (profiles/r2_traffic.json)"),
+                         "flops_per_unit": exe_fpu,
+                         "note": "achieved/frac count the FP64 flops the kernel EXECUTES per unit (ncu op counters): it "
+                                 "evaluates cell polynomials, not SURVEY 8(d)'s per-target taps (764 flops/unit), so the "
+                                 "algorithmic figure is reported separately (algorithmic_*) and at step level (step)",
+                         "algorithmic_flops_per_unit": FLOPS_PER_UNIT_SURVEY, "algorithmic_achieved": alg_tf,
+                         "algorithmic_frac": (alg_tf / fp64_tf) if alg_tf else None,
                          "units_per_launch": units_per_launch, "avg_launch_ms": k4_ms,
-                         "kernel_share_of_step": agg["interp_ms"] / res_ms,
-                         "peak_source": "measured live: sk_fp64_peak DFMA micro-benchmark (MEASURED_PEAKS.json has no FP64 figure)",
+                         "kernel_share_of_step": (agg["interp_ms"] / K) / (main_["timed_stage_ms"] / K),
+                         "peak_source": f"measured live: sk_fp64_peak DFMA micro-benchmark ({fp64_ms:.3f} ms, SM clock "
+                                        f"{main_['clocks'].get('sm_mhz')} MHz under load; MEASURED_PEAKS.json has no FP64 figure)",
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": (ach_gbs / hbm_peak) if ach_gbs else None, "bytes_per_unit": BYTES_PER_UNIT_K4,
-                                 "peak_source": hbm_src}},
+                                 "peak_source": hbm_src},
+                         "step": {"units": agg["units"] / K, "flops_per_unit": FLOPS_PER_UNIT_SURVEY, "roofline_ms": step_roof_ms,
+                                  "ms_per_step": ms_step, "frac": step_roof_ms / ms_step,
+                                  "note": "whole resident step against the FP64 roofline at SURVEY 8(d)'s algorithmic count"},
+                         "sort": k8},
             "source_side_ms_per_step": agg["source_ms"] / K, "interp_ms_per_step": agg["interp_ms"] / K,
-            "units_per_step": agg["units"] / K, "wall_ms_per_step": wall_ms / K,
-            "parity": {"max_abs_err_vs_closed_form": max_err, "resident_equals_e2e_bitwise": same},
+            "sort_ms_per_step": sort_ms, "gather_ms_per_step": gather_ms,
+            "units_per_step": agg["units"] / K, "wall_ms_per_step": main_["wall_ms"] / K,
+            "parity": {"max_abs_err_vs_closed_form": main_["max_err"], "resident_equals_e2e_bitwise": main_["same"]},
         }
+        if strong is not None and not strong_only:
+            line["strong"] = {"workload": f"the {n} distances of the BASELINE workload (seed 0) split over {world} GPUs",
+                              "value": n * K / (strong["res_ms"] * 1e-3), "ms_per_step": strong["res_ms"] / K,
+                              "e2e_value": n * K / (strong["e2e_ms"] * 1e-3), "e2e_ms_per_step": strong["e2e_ms"] / K,
+                              "unit": "evals/s", "n_per_gpu": strong["n"],
+                              "max_abs_err_vs_closed_form": strong["max_err"]}
         if world == 1 and not args.no_cpu_baseline:
             r = oracle_cpu_run(args.cpu_sample, 1, 1)
             line["cpu_baseline"] = {"value": r["evals_per_s"], "unit": "evals/s", "cores": r["threads"], "kind": "port",

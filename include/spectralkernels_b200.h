@@ -110,8 +110,10 @@ typedef struct sk_stats {
   double interp_ms;         /* device time in the interpolation kernel since sk_run_begin      */
   double source_ms;         /* device time in node/strength/spread/FFT since sk_run_begin      */
   int32_t timing_enabled;
-  int32_t sort_two_level;   /* last sk_targets_set: 2 = input was already sorted and unique (no sort), 1 = 4-pass + run-rank sort, 0 = full 8-pass sort */
+  int32_t sort_two_level;   /* last sk_targets_set*: 2 = input was already sorted and unique (no sort), 1 = the bin scheme of K8 (csrc/sk_k8.cuh), 0 = the general sort (clustered / heavily duplicated input) */
   int64_t n_hankel;         /* sub-intervals that took the O(N) nonuniform Hankel transform (dim >= 2) */
+  double sort_ms;           /* device time of the last sk_targets_set* (unique / sort / inverse map), timing enabled */
+  double gather_ms;         /* device time in the gather to the input order since sk_run_begin  */
 } sk_stats;
 
 /* ---- library --------------------------------------------------------------------------------- */

@@ -747,6 +747,7 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   unsigned long long *desc = (unsigned long long *)(c->k8_ctl.p + off_desc);
   unsigned int *fill = (unsigned int *)(c->k8_ctl.p + off_fill);
   bool general = force_general;
+  if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
   if (!general) {
     CK(cudaMemsetAsync(c->k8_ctl.p, 0, ctl_bytes, c->stream));
     const unsigned int gs = std::min<unsigned int>(nblk(n_in, 256), 148u * 8u);    // grid-stride passes: 2048 threads per SM
@@ -758,7 +759,7 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
     LAUNCH_CHECK();
     k_k8_scatter<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->k8_ctab.p, fill, c->k8_skeys.p, c->k8_sidx.p, c->inv.p);
     LAUNCH_CHECK();
-    k_k8_finish<<<(unsigned int)nfine_max, SK_K8_TPB, 0, c->stream>>>(st, fill, c->k8_skeys.p, c->k8_sidx.p, desc, c->uxs.p, c->inv.p);
+    k_k8_finish<<<(unsigned int)nfine_max, SK_K8_TPB, 0, c->stream>>>(st, fill, c->k8_skeys.p, c->k8_sidx.p, desc, c->uxs.p, c->inv.p, getenv("SK_K8_DBG") ? atoi(getenv("SK_K8_DBG")) : 0);
     LAUNCH_CHECK();
     k_k8_identity<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->uxs.p, c->inv.p);
     LAUNCH_CHECK();
@@ -775,6 +776,13 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   }
   const SkTargetSummary sm = c->h_scal->sum;
   if (sm.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
+  if (c->timing) {
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    CK(cudaEventSynchronize(c->ev[1]));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->stats.sort_ms = ms;
+  }
   const long long nu = sm.n_unique;
   c->n_in = n_in;
   c->n_unique = nu;
@@ -1277,9 +1285,11 @@ int sk_run_begin(sk_ctx *c) {
   CK(cudaSetDevice(c->device));
   const bool t = c->timing;
   const int two = c->stats.sort_two_level;
+  const double sort_ms = c->stats.sort_ms;
   std::memset(&c->stats, 0, sizeof(c->stats));
   c->stats.timing_enabled = t;
   c->stats.sort_two_level = two;
+  c->stats.sort_ms = sort_ms;
   CK(cudaMemsetAsync(c->res.p, 0, sizeof(sk_cplx) * c->n_unique, c->stream));   // ks = errs = 0, src/adaptive.jl:122
   c->tails.n = 0;
   c->in_panel = false;
@@ -1661,9 +1671,16 @@ int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
   if (rc != SK_OK) return rc;
   rc = flush_commit(c);
   if (rc != SK_OK) return rc;
+  if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
   k_gather<<<nblk(c->n_in, 1024), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, vals_dev, errs_dev, c->in.p, c->in_scale, c->tails);
   LAUNCH_CHECK();
+  if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (c->timing) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->stats.gather_ms += ms;
+  }
   return SK_OK;
 }
 

@@ -191,9 +191,9 @@ def test_truncation_bound_nan_semantics_on_device(sk):
     eng.sdf_builtin(S.family, S.params, 0)
     info = eng.targets_set(xs)
     n = int(info.n_unique)
-    tau = 1.0                                   # every |panel_k| < tau: the decision rests on the truncation bound
+    tau = 10.0                                  # every |panel_k| < tau (K(0) = pi/2): the decision rests on the truncation bound
     cases = [(nan, 1e-3, n), (1e-3, nan, n), (nan, nan, n), (inf, nan, n), (nan, -inf, n),
-             (inf, 1e-3, None), (1e-3, inf, 0), (-inf, 1e-3, 0), (1e-30, 1e-30, 0), (inf, inf, n)]
+             (inf, 1e-3, 0), (1e-3, inf, 0), (-inf, 1e-3, 0), (1e-30, 1e-30, 0), (inf, inf, n), (inf, 50.0, None)]
     for crit in ("both", "tails"):
         for ta, tn, expect in cases:
             args = ScanArgs(ta, tn, 1.0, tau, SK_CRIT[crit], 0)
