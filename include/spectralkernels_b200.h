@@ -266,6 +266,47 @@ int sk_results_wait(sk_ctx *ctx);
 int sk_results_get_device(sk_ctx *ctx, double *vals_dev, double *errs_dev);
 int sk_stats_get(sk_ctx *ctx, sk_stats *out);
 
+/* ---- device group: ONE caller, several GPUs -------------------------------------------------------------
+ * The reference's API is a single task calling kernel_values(cfg, xs) (src/adaptive.jl:95-108); a group gives that
+ * caller N devices behind the same sequence of calls as a single context (sk_group_X has the contract of sk_X).
+ * The distances are cut into N contiguous chunks of the caller's array, one per device; each device sorts and
+ * de-duplicates its chunk (src/adaptive.jl:99, :113-120) and runs the adaptive loop on it in lock step with the
+ * others.  Every call enqueues its work on all devices before it reads anything back, so the devices -- and, with
+ * host arrays from sk_host_alloc, their PCIe links -- work concurrently under one host thread.  The only exchange is
+ * the host-side maximum of the per-device scalars (max |I2-I1| of src/quadrature.jl:258, the NaN flags of :165, the
+ * largest unconverged distance of src/adaptive.jl:183-198): no collective library is involved.  All devices build the
+ * transform geometry from the global distance range, so values and error estimates equal a one-device run over the
+ * same distances bit for bit.  ix1 / hi / new_hi count over the concatenation of the devices' unique tables (equal
+ * distances in different chunks count once per chunk); pass them back as returned.  A device may be listed more
+ * than once (several chunks on one GPU).                                                                          */
+typedef struct sk_group sk_group;
+int sk_group_create(const int32_t *devices, int32_t ndev, sk_group **out);
+int sk_group_destroy(sk_group *g);
+int sk_group_size(const sk_group *g);
+int sk_group_ctx(sk_group *g, int32_t i, sk_ctx **out);          /* the i-th device's context (stays owned by g) */
+const char *sk_group_last_error(const sk_group *g);
+int sk_group_set_timing(sk_group *g, int enabled);
+int sk_group_set_nufft_eps(sk_group *g, double eps);
+int sk_group_synchronize(sk_group *g);
+int sk_group_rule_set(sk_group *g, int32_t m, int32_t k, double p, const double *leg_no1, const double *leg_wt1,
+                      const double *leg_no2, const double *leg_wt2, const double *jac_no1, const double *jac_wt1,
+                      const double *jac_no2, const double *jac_wt2);
+int sk_group_rule_get(sk_group *g, int32_t which, double *no, double *wt);
+int sk_group_sdf_builtin(sk_group *g, int32_t family, const double *params, int32_t nparams, int32_t deriv_index);
+int sk_group_targets_set(sk_group *g, const double *xs_host, int64_t n_in, sk_target_info *info);
+int sk_group_run_begin(sk_group *g);
+int sk_group_zero_lag_set(sk_group *g, double value);
+int sk_group_panel_begin(sk_group *g, int64_t ix1, int64_t hi, double *r_lo, double *r_hi);
+int sk_group_subinterval(sk_group *g, double a, double b, const sk_subinterval_opts *opts, double *max_abs_diff);
+int sk_group_subinterval_host(sk_group *g, double a, double b, const double *no1, const double *buf1, const double *no2,
+                              const double *buf2, const sk_subinterval_opts *opts, double *max_abs_diff);
+int sk_group_subinterval_accept(sk_group *g);
+int sk_group_panel_commit(sk_group *g);
+int sk_group_converge_scan(sk_group *g, const sk_scan_args *args, int64_t *new_hi, double *r_at_new_hi);
+int sk_group_converge_apply(sk_group *g, const sk_scan_args *args, int64_t new_hi);
+int sk_group_results_get(sk_group *g, double *vals, double *errs);
+int sk_group_stats_get(sk_group *g, sk_stats *out);               /* counters of the step; work and launches summed */
+
 /* ---- host-side plan helpers exported for tests (no GPU needed) --------------------------------- */
 /* Gauss-Legendre (p == 0) / Gauss-Jacobi(0,p) on [-1,1], ascending; 0 on success */
 int sk_host_gauss_rule(int32_t n, double p, double *no, double *wt);

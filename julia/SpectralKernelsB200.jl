@@ -1,20 +1,31 @@
-# SpectralKernelsB200.jl -- the reference-side binding a maintainer of SpectralKernels.jl would add to
-# run `kernel_values` on a B200 through libsk_b200.so (C ABI: include/spectralkernels_b200.h).
+# SpectralKernelsB200.jl -- the reference-side binding a maintainer of SpectralKernels.jl adds so that the package's
+# OWN public API runs on B200s through libsk_b200.so (C ABI: include/spectralkernels_b200.h).
 #
-# NOT EXECUTED in this repository's CI: the build image has no Julia.  The identical C ABI is exercised
-# through ctypes by spectralkernels.jl_b200/_capi.py + adaptive.py, which is a line-for-line twin of the
-# control flow below.  Keep this file thin: scalars only cross the boundary inside the loops.
+# NOT EXECUTED in this repository: the build image has no Julia.  The identical C ABI is exercised through ctypes by
+# spectralkernels.jl_b200/_capi.py + adaptive.py, which follows the same control flow call for call.  Keep this file
+# thin: only scalars cross the boundary inside the loops.
 #
-# Usage:
-#   using SpectralKernels, SpectralKernelsB200
-#   cfg = AdaptiveKernelConfig(S)                       # unchanged public API (src/adaptive.jl:24-59)
-#   Ks, errs = kernel_values_b200(cfg, rs)              # same return as kernel_values (src/adaptive.jl:95-108)
-#   # or, for the shipped families, without evaluating S on the host:
-#   Ks, errs = kernel_values_b200(cfg, rs; builtin=(SK_SDF_MATERN, [phi, rho, nu, 1.0]))
+# How the dispatch works (no method of the package is overwritten, nothing is pirated): wrap the spectral density,
+#
+#     using SpectralKernels, SpectralKernelsB200
+#     S   = B200(w -> (1 + w^2)^(-2))                        # any closure: evaluated in Julia, strengths uploaded
+#     S   = B200(matern_sdf; builtin=SK_SDF_MATERN)          # f(w, phi, rho, nu): evaluated by the device generator
+#     S   = B200(f; devices=[0, 1, 2, 3])                    # one caller, four GPUs (the C ABI's device group)
+#     cfg = AdaptiveKernelConfig(S; tol=1e-8)                # unchanged constructor (src/adaptive.jl:24-59)
+#     Ks, errs = kernel_values(cfg, rs)                      # unchanged call      (src/adaptive.jl:95-108)
+#
+# `AdaptiveKernelConfig{S,dS}` carries the type of `f`, so the method below -- defined on configs whose density is a
+# `B200`, a `ParametricFunction` of one or a `ParametricDerivative` of one -- is what Julia selects for
+# `kernel_values(cfg, xs)`.  Everything above that call keeps working unchanged and now runs on the GPU, because it
+# only ever calls `kernel_values`: `gen_kernel` (src/model.jl:73-77, via `ParametricFunction(sm.cfg.f, params)`),
+# `kernel_sdf_derivatives` / `kernel_warping_gradients` / `kernel_singularity_derivative` (src/derivatives.jl:51-81),
+# the ForwardDiff and ChainRules extensions (ext/SpectralKernelsForwardDiffExt.jl:7-22) and the Vecchia extension
+# (ext/SpectralKernelsVecchiaExt.jl:19-27).
 module SpectralKernelsB200
 
 using SpectralKernels
-import SpectralKernels: AdaptiveKernelConfig, compute_k0, estimate_tail_decay, updatequadbufs!, quadsz
+import SpectralKernels: AdaptiveKernelConfig, ParametricFunction, ParametricDerivative, compute_k0,
+                        estimate_tail_decay, updatequadbufs!, quadsz, kernel_values, build_dense_cov_matrix
 
 const libsk = get(ENV, "SK_B200_LIB", "libsk_b200.so")
 
@@ -35,62 +46,117 @@ struct SubintervalOpts       # sk_subinterval_opts
   speculate::Ptr{ScanArgs}   # C_NULL, or the panel's scan arguments on the panel's first sub-interval
 end
 
-mutable struct Ctx
-  h::Ptr{Cvoid}
-  function Ctx(device::Integer=0)
-    r = Ref{Ptr{Cvoid}}(C_NULL)
-    rc = ccall((:sk_ctx_create, libsk), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r)
-    rc == 0 || error("sk_ctx_create failed ($rc): no CUDA device?  There is no CPU fallback.")
-    c = new(r[])
-    finalizer(x -> ccall((:sk_ctx_destroy, libsk), Cint, (Ptr{Cvoid},), x.h), c)
-    c
-  end
+# ---- the wrapper that selects the backend ---------------------------------------------------------------------
+struct B200{F} <: Function
+  fn::F
+  devices::Vector{Int32}                 # one entry: a single context; several: a device group (sk_group_*)
+  builtin::Cint                          # 0: evaluate fn in Julia; SK_SDF_MATERN / SK_SDF_EXPONENTIAL: device generator
+end
+B200(fn; devices=[0], builtin=Cint(0)) = B200(fn, Int32.(collect(devices)), Cint(builtin))
+(b::B200)(w, params...) = b.fn(w, params...)
+
+const OnB200 = Union{B200, ParametricFunction{<:B200}, ParametricDerivative{<:B200}}
+backend_of(f::B200) = f
+backend_of(f::ParametricFunction{<:B200}) = f.fn
+backend_of(f::ParametricDerivative{<:B200}) = f.swap_sdf.fn.fn
+# device generator for this integrand?  (family, parameters, which parameter derivative); only for a ParametricFunction
+# of a built-in family with d = 1 Matern parameters (phi, rho, nu) or exponential parameters (phi, alpha)
+builtin_of(f::B200) = nothing
+function builtin_of(f::ParametricFunction{<:B200})
+  fam = f.fn.builtin
+  fam == 0 && return nothing
+  prm = collect(Float64, f.params)
+  fam == SK_SDF_MATERN && length(prm) == 3 && push!(prm, 1.0)          # (phi, rho, nu, d)
+  (fam, prm, Cint(0))
+end
+function builtin_of(f::ParametricDerivative{F,P,J}) where {F<:B200,P,J}
+  b = builtin_of(f.swap_sdf.fn)
+  isnothing(b) ? nothing : (b[1], b[2], Cint(J - 1))                   # J - 1: args[1] is the frequency (wrappers.jl:24)
 end
 
-function ck(c::Ctx, rc::Cint)
+# ---- one session (context or group) per task and device list ----------------------------------------------------
+mutable struct Session
+  h::Ptr{Cvoid}
+  group::Bool
+  function Session(devices::Vector{Int32})
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    grp = length(devices) > 1
+    rc = grp ? ccall((:sk_group_create, libsk), Cint, (Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}), devices, length(devices), r) :
+               ccall((:sk_ctx_create, libsk), Cint, (Cint, Ref{Ptr{Cvoid}}), devices[1], r)
+    rc == 0 || error("libsk_b200: cannot open device(s) $devices ($rc).  There is no CPU fallback.")
+    s = new(r[], grp)
+    finalizer(x -> x.group ? ccall((:sk_group_destroy, libsk), Cint, (Ptr{Cvoid},), x.h) :
+                             ccall((:sk_ctx_destroy, libsk), Cint, (Ptr{Cvoid},), x.h), s)
+    s
+  end
+end
+# cfg.buffers / cfg.splittingheap are per-config scratch that must not be shared between tasks (src/adaptive.jl:17-21);
+# the device scratch follows the same rule: one session per task and device list
+session(devices::Vector{Int32}) = get!(() -> Session(devices), task_local_storage(), (:sk_b200, Tuple(devices)))::Session
+
+function ck(s::Session, rc::Cint)
   rc == 0 && return
-  msg = unsafe_string(ccall((:sk_last_error, libsk), Cstring, (Ptr{Cvoid},), c.h))
+  msg = s.group ? unsafe_string(ccall((:sk_group_last_error, libsk), Cstring, (Ptr{Cvoid},), s.h)) :
+                  unsafe_string(ccall((:sk_last_error, libsk), Cstring, (Ptr{Cvoid},), s.h))
   error("libsk_b200 [$rc]: $msg")     # never throws across the ABI: the C side only returns codes
+end
+# sk_X for a context, sk_group_X for a group: same arguments
+macro sk(s, name, argtypes, args...)
+  g = QuoteNode(Symbol("sk_group_", name)); c = QuoteNode(Symbol("sk_", name))
+  esc(quote
+    ck($s, $s.group ? ccall(($g, libsk), Cint, (Ptr{Cvoid}, $(argtypes.args...)), $s.h, $(args...)) :
+                      ccall(($c, libsk), Cint, (Ptr{Cvoid}, $(argtypes.args...)), $s.h, $(args...)))
+  end)
 end
 
 # --- Level 0: replaces src/utils.jl:10 -----------------------------------------------------------------
-function finufft1d3_b200(c::Ctx, w::Vector{Float64}, s::Vector{ComplexF64}, x::Vector{Float64})
+function finufft1d3_b200(s::Session, w::Vector{Float64}, c::Vector{ComplexF64}, x::Vector{Float64})
+  s.group && error("sk_nufft1d3 takes a single context")
   out = Vector{ComplexF64}(undef, length(x))
-  GC.@preserve w s x out ck(c, ccall((:sk_nufft1d3, libsk), Cint,
+  GC.@preserve w c x out ck(s, ccall((:sk_nufft1d3, libsk), Cint,
       (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{ComplexF64}, Int64, Ptr{Float64}, Ptr{ComplexF64}, Float64),
-      c.h, length(w), w, s, length(x), x, out, 1e-15))
+      s.h, length(w), w, c, length(x), x, out, 1e-15))
   out
 end
 
-# --- Level 1: kernel_values with every O(N) pass on the device ---------------------------------------------
-function kernel_values_b200(config::AdaptiveKernelConfig, xs::AbstractVector{Float64};
-                            k0=compute_k0(config), param_derivative=false, verbose=false,
-                            builtin=nothing, ctx::Ctx=Ctx())
-  config.dim == 1 || error("dim > 1 is not built yet in libsk_b200")
-  c = ctx
+# target-independent pieces of truncation_error_estimate (src/adaptive.jl:222-229), IEEE arithmetic throughout
+scan_args(config, b, cc, d, tau, crit) = crit == :panel ?
+  ScanArgs(0.0, 0.0, (config.dim + 1)/2, tau, SK_CRIT[:panel], 0) :
+  ScanArgs(-cc/(d + config.dim)*b^(d + config.dim), cc*b^(d + (config.dim - 1)/2), (config.dim + 1)/2, tau, SK_CRIT[crit], 0)
+
+# --- Level 1: kernel_values with every O(N) pass on the device ---------------------------------------------------
+# `targets`: nothing (upload xs), or a closure that sets the targets itself (pair lists: see build_dense_cov_matrix)
+function kernel_values(config::AdaptiveKernelConfig{<:OnB200}, xs::AbstractVector{Float64};
+                       k0=compute_k0(config), param_derivative=false, verbose=false, targets=nothing)
+  be = backend_of(config.f)
+  s  = session(be.devices)
   (m, k) = config.quadspec
   lr, jr = config.legrule, config.jacrule
   # QuadRule (src/quadrature.jl:27-47): pass FastGaussQuadrature's own nodes so both paths share them
-  GC.@preserve lr jr ck(c, ccall((:sk_rule_set, libsk), Cint,
-      (Ptr{Cvoid}, Int32, Int32, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-       Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-      c.h, m, k, config.p, lr.no1, lr.wt1, lr.no2, lr.wt2, jr.no1, jr.wt1, jr.no2, jr.wt2))
+  GC.@preserve lr jr @sk(s, rule_set, (Int32, Int32, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                                       Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                         m, k, config.p, lr.no1, lr.wt1, lr.no2, lr.wt2, jr.no1, jr.wt1, jr.no2, jr.wt2)
+  builtin = builtin_of(config.f)
   if !isnothing(builtin)
-    (fam, prm) = builtin
-    ck(c, ccall((:sk_sdf_builtin, libsk), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Int32),
-                c.h, fam, prm, length(prm), 0))
+    (fam, prm, dj) = builtin
+    @sk(s, sdf_builtin, (Int32, Ptr{Float64}, Int32, Int32), fam, prm, length(prm), dj)
   end
-  xv = convert(Vector{Float64}, xs)
   info = Ref(TargetInfo(0, 0, 0, 0, 0.0, 0.0))
-  GC.@preserve xv ck(c, ccall((:sk_targets_set, libsk), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ref{TargetInfo}),
-                              c.h, xv, length(xv), info))               # unique + sort + inverse map (adaptive.jl:99,113-120)
-  ck(c, ccall((:sk_run_begin, libsk), Cint, (Ptr{Cvoid},), c.h))
+  n_out = length(xs)
+  if isnothing(targets)
+    xv = convert(Vector{Float64}, xs)
+    GC.@preserve xv @sk(s, targets_set, (Ptr{Float64}, Int64, Ref{TargetInfo}), xv, length(xv), info)   # adaptive.jl:99,113-120
+  else
+    n_out = targets(s, info)
+  end
+  verbose && println("Reducing $(info[].n_in) to $(info[].n_unique) unique lags for evaluation...")
+  @sk(s, run_begin, ())
   n   = info[].n_unique
   ix1 = 1
   if info[].has_zero != 0                                                  # adaptive.jl:133-146
     ix1 = 2
     z = config.derivative ? 0.0 : (param_derivative ? compute_k0(config) : k0)
-    ck(c, ccall((:sk_zero_lag_set, libsk), Cint, (Ptr{Cvoid}, Float64), c.h, z))
+    @sk(s, zero_lag_set, (Float64,), z)
   end
   hi, r_hi   = n, (n >= ix1 ? info[].r_max : 0.0)
   conv_crit  = config.convergence_criteria
@@ -104,25 +170,32 @@ function kernel_values_b200(config::AdaptiveKernelConfig, xs::AbstractVector{Flo
     # (orders 0..3) and takes the direct Bessel summation (:145-160) for small active sets.
     (kernel, nu, xdiv) = (SK_KERNEL_BESSEL, Int64(config.derivative ? dim/2 : dim/2 - 1), dim/2 - 1)
   end
-  opts       = Ref(SubintervalOpts(config.c, config.p, kernel, config.logw ? 1 : 0, nu, 0, xdiv, C_NULL))
-  # (optional optimisation, see sk_subinterval_opts.speculate: evaluate estimate_tail_decay(config, a, b)
-  #  before the panel and pass pointer_from_objref/Ref of the ScanArgs with the panel's first sub-interval)
-  tau        = config.tol*abs(k0)/2
+  tau = config.tol*abs(k0)/2
   while r_hi > 0                                                           # adaptive.jl:149
     (a, b) = (b, b + quadsz(config)/(2*r_hi))                              # adaptive.jl:152
-    rlo, rhi = Ref(0.0), Ref(0.0)
-    ck(c, ccall((:sk_panel_begin, libsk), Cint, (Ptr{Cvoid}, Int64, Int64, Ref{Float64}, Ref{Float64}),
-                c.h, ix1, hi, rlo, rhi))
+    verbose && println("\nintegrating panel w ∈ [$a, $b] (length $(b - a)) to resolve $hi points x ≤ $r_hi")   # utils.jl:12-15
+    @sk(s, panel_begin, (Int64, Int64, Ptr{Float64}, Ptr{Float64}), ix1, hi, C_NULL, C_NULL)
+    # The tail fit depends on (a, b) only, so it is evaluated BEFORE the panel is integrated (the reference does it
+    # after, adaptive.jl:168): the scan arguments then ride along with the panel's first sub-interval and the device
+    # fuses accept / commit / scan into the interpolation kernel (sk_subinterval_opts.speculate)
+    (cc, d) = (conv_crit == :panel) ? (NaN, NaN) : estimate_tail_decay(config, a, b, d=config.tail)
+    if (isnan(cc) || isnan(d)) && conv_crit != :panel; conv_crit = :panel; end     # adaptive.jl:170-175
+    sa = Ref(scan_args(config, b, cc, d, tau, conv_crit))
     # ---- fourier_integrate_interval (quadrature.jl:169-275): scalar control flow only ----
     stack = [(a, b, config.tol)]
-    while !isempty(stack)
+    first = true
+    GC.@preserve sa while !isempty(stack)
       (_a, _b, _tol) = pop!(stack)
-      mx = Ref(0.0)
+      spec  = first ? Base.unsafe_convert(Ptr{ScanArgs}, sa) : Ptr{ScanArgs}(C_NULL)
+      first = false
+      opts  = Ref(SubintervalOpts(config.c, config.p, kernel, config.logw ? 1 : 0, nu, 0, xdiv, spec))
+      mx    = Ref(0.0)
       if _a == 0.0 && config.p != 0.0 && config.logw
         # log-weighted origin sub-interval by parts (quadrature.jl:186-228): Julia owns f and df and evaluates both
         # integrands with updatequadbufs!; the device does the transforms (:cis for dim = 1; Bessel orders dim/2-1 and
         # dim/2 for dim = 2) and I = (I0 - A + 2 pi x B)/(dim - alpha)
         dim <= 2 || error("singularity derivative not implemented in d > 2")                      # :222-223
+        s.group && error("the log-weighted origin sub-interval takes a single context")
         (f, df) = (config.f, config.df)
         (no1, ba1, no2, ba2) = updatequadbufs!(config.buffers, config.legrule, config.jacrule,
                                                w -> f(w) + w*log(w)*df(w), _a, _b; p=config.p)
@@ -133,47 +206,66 @@ function kernel_values_b200(config::AdaptiveKernelConfig, xs::AbstractVector{Flo
         i0   = _b^(dim/2 + 1 - config.alpha)*log(_b)*f(_b)                                          # :189
         lopt = Ref(SubintervalOpts(config.c, config.p, dim == 1 ? SK_KERNEL_COS : SK_KERNEL_BESSEL, 1,
                                    dim == 1 ? 0 : Int64(dim/2 - 1), 0, dim/2 - 1, C_NULL))
-        GC.@preserve no1 ra1 rb1 no2 ra2 rb2 ck(c, ccall((:sk_subinterval_logw_host, libsk), Cint,
+        GC.@preserve no1 ra1 rb1 no2 ra2 rb2 ck(s, ccall((:sk_subinterval_logw_host, libsk), Cint,
             (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
              Ptr{Float64}, Ref{SubintervalOpts}, Float64, Float64, Ref{Float64}),
-            c.h, _a, _b, no1, ra1, rb1, no2, ra2, rb2, lopt, i0, dim - config.alpha, mx))
+            s.h, _a, _b, no1, ra1, rb1, no2, ra2, rb2, lopt, i0, dim - config.alpha, mx))
       elseif isnothing(builtin)
         origin = (_a == 0.0 && config.p != 0.0)
         f = origin ? config.f : (w -> w^config.p * (config.logw ? log(w) : 1) * config.f(w))
         (no1, buf1, no2, buf2) = updatequadbufs!(config.buffers, config.legrule, config.jacrule, f, _a, _b;
                                                  p=(origin ? config.p : 0))
         rb1, rb2 = real.(buf1), real.(buf2)
-        GC.@preserve no1 rb1 no2 rb2 ck(c, ccall((:sk_subinterval_host, libsk), Cint,
-            (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-             Ref{SubintervalOpts}, Ref{Float64}), c.h, _a, _b, no1, rb1, no2, rb2, opts, mx))
+        GC.@preserve no1 rb1 no2 rb2 @sk(s, subinterval_host, (Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                                                             Ptr{Float64}, Ref{SubintervalOpts}, Ref{Float64}),
+                                         _a, _b, no1, rb1, no2, rb2, opts, mx)
       else
-        ck(c, ccall((:sk_subinterval, libsk), Cint, (Ptr{Cvoid}, Float64, Float64, Ref{SubintervalOpts}, Ref{Float64}),
-                    c.h, _a, _b, opts, mx))
+        @sk(s, subinterval, (Float64, Float64, Ref{SubintervalOpts}, Ref{Float64}), _a, _b, opts, mx)
       end
+      verbose && SpectralKernels.print_panel_convergence(mx[]/abs(k0), _tol, _a, _b)
       if mx[] < config.tol*abs(k0)                                         # quadrature.jl:260
-        ck(c, ccall((:sk_subinterval_accept, libsk), Cint, (Ptr{Cvoid},), c.h))
+        @sk(s, subinterval_accept, ())
       else                                                                 # quadrature.jl:268-270
         (tl, tr) = (_a == 0) ? (9_tol/10, _tol/10) : (_tol/2, _tol/2)
         (_a < (_a + _b)/2 < _b) || error("sub-interval ($_a, $_b) cannot be split any further")
         push!(stack, (_a, (_a + _b)/2, tl)); push!(stack, ((_a + _b)/2, _b, tr))
       end
     end
-    ck(c, ccall((:sk_panel_commit, libsk), Cint, (Ptr{Cvoid},), c.h))      # adaptive.jl:163-164
-    (cc, d) = (conv_crit == :panel) ? (NaN, NaN) : estimate_tail_decay(config, a, b, d=config.tail)
-    if (isnan(cc) || isnan(d)) && conv_crit != :panel; conv_crit = :panel; end
-    sa = conv_crit == :panel ? ScanArgs(0.0, 0.0, (dim+1)/2, tau, SK_CRIT[:panel], 0) :
-         ScanArgs(-cc/(d+dim)*b^(d+dim), cc*b^(d+(dim-1)/2), (dim+1)/2, tau, SK_CRIT[conv_crit], 0)
+    @sk(s, panel_commit, ())                                               # adaptive.jl:163-164
     newhi, rstop = Ref{Int64}(0), Ref(0.0)
-    ck(c, ccall((:sk_converge_scan, libsk), Cint, (Ptr{Cvoid}, Ref{ScanArgs}, Ref{Int64}, Ref{Float64}),
-                c.h, Ref(sa), newhi, rstop))                               # adaptive.jl:183-198
-    ck(c, ccall((:sk_converge_apply, libsk), Cint, (Ptr{Cvoid}, Ref{ScanArgs}, Int64), c.h, Ref(sa), newhi[]))
+    @sk(s, converge_scan, (Ref{ScanArgs}, Ref{Int64}, Ref{Float64}), sa, newhi, rstop)          # adaptive.jl:183-198
+    @sk(s, converge_apply, (Ref{ScanArgs}, Int64), sa, newhi[])                                 # adaptive.jl:194
     hi, r_hi = newhi[], rstop[]
   end
-  vals = Vector{Float64}(undef, length(xv)); errs = similar(vals)
-  GC.@preserve vals errs ck(c, ccall((:sk_results_get, libsk), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
-                                     c.h, vals, errs))                     # adaptive.jl:105-107
+  vals = Vector{Float64}(undef, n_out); errs = similar(vals)
+  GC.@preserve vals errs @sk(s, results_get, (Ptr{Float64}, Ptr{Float64}), vals, errs)         # adaptive.jl:105-107
   (vals, errs)
 end
 
-export Ctx, kernel_values_b200, finufft1d3_b200, SK_SDF_MATERN, SK_SDF_EXPONENTIAL
+# src/utils.jl:41-64 on the device: the pairwise lags |pts[i] - pts[j]|, j > i, are formed, sorted and de-duplicated
+# by sk_targets_set_pairs (its default pair order -- strict upper triangle, row-major -- is the order of :44-45), and
+# the matrix is filled from the flat result.  The reference's sortperm / invperm disappear.
+function build_dense_cov_matrix(cfg::AdaptiveKernelConfig{<:OnB200}, pts::AbstractVector{Float64})
+  npt = length(pts)
+  pv  = convert(Vector{Float64}, pts)
+  set_pairs = (s, info) -> begin
+    s.group && error("pair lists take a single context")
+    GC.@preserve pv ck(s, ccall((:sk_targets_set_pairs, libsk), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Int64}, Int64, Ref{TargetInfo}), s.h, pv, npt, 1, C_NULL, 0, info))
+    Int(info[].n_in)
+  end
+  vals = kernel_values(cfg, Float64[]; targets=set_pairs)[1]
+  k00  = kernel_values(cfg, [0.0])[1][1]
+  M = Matrix{Float64}(undef, npt, npt)
+  j = 0
+  for i in 1:npt
+    M[i, i] = k00
+    M[i, i+1:end] .= vals[(j+1):(j+npt-i)]
+    M[i+1:end, i] .= vals[(j+1):(j+npt-i)]
+    j += npt - i
+  end
+  M
+end
+
+export B200, Session, finufft1d3_b200, SK_SDF_MATERN, SK_SDF_EXPONENTIAL
 end # module

@@ -13,12 +13,15 @@ The directory name contains a dot, so import it through the loader module at the
     import spectralkernels_jl_b200 as sk
 """
 from . import _capi, sdf
-from ._capi import PinnedArray, Session, SkError, bind_to_gpu_cpus, host_gauss_rule, load
+from ._capi import GroupSession, PinnedArray, Session, SkError, bind_to_gpu_cpus, host_gauss_rule, load
 from .adaptive import (AdaptiveKernelConfig, compute_k0, estimate_tail_decay, gen_derivative_config,
                        gen_new_sdf_config, kernel_values)
 from .derivatives import kernel_derivative, kernel_sdf_derivatives, kernel_singularity_derivative
+from .model import (NoWarping, SpectralKernel, SpectralModel, build_dense_cov_matrix, dense_index_pairs, gen_kernel,
+                    gen_kernel_dual, gen_kernel_jacobian, gen_kernel_setup)
 from .sdf import Exponential, Matern
 
 __all__ = ["AdaptiveKernelConfig", "kernel_values", "compute_k0", "estimate_tail_decay", "gen_derivative_config",
-           "gen_new_sdf_config", "kernel_derivative", "kernel_sdf_derivatives", "kernel_singularity_derivative", "Matern", "Exponential", "Session", "SkError", "PinnedArray", "host_gauss_rule", "bind_to_gpu_cpus",
-           "load", "sdf"]
+           "gen_new_sdf_config", "kernel_derivative", "kernel_sdf_derivatives", "kernel_singularity_derivative", "Matern", "Exponential", "Session", "GroupSession", "SkError", "PinnedArray", "host_gauss_rule", "bind_to_gpu_cpus",
+           "load", "sdf", "NoWarping", "SpectralModel", "SpectralKernel", "dense_index_pairs", "gen_kernel_setup", "gen_kernel",
+           "gen_kernel_jacobian", "gen_kernel_dual", "build_dense_cov_matrix"]

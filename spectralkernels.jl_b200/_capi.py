@@ -109,6 +109,29 @@ SIGNATURES = {
     "sk_results_wait": (c_int, [c_void_p]),
     "sk_results_get_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "sk_stats_get": (c_int, [c_void_p, POINTER(Stats)]),
+    "sk_group_create": (c_int, [POINTER(c_int32), c_int32, POINTER(c_void_p)]),
+    "sk_group_destroy": (c_int, [c_void_p]),
+    "sk_group_size": (c_int, [c_void_p]),
+    "sk_group_ctx": (c_int, [c_void_p, c_int32, POINTER(c_void_p)]),
+    "sk_group_last_error": (c_char_p, [c_void_p]),
+    "sk_group_set_timing": (c_int, [c_void_p, c_int]),
+    "sk_group_set_nufft_eps": (c_int, [c_void_p, c_double]),
+    "sk_group_synchronize": (c_int, [c_void_p]),
+    "sk_group_rule_set": (c_int, [c_void_p, c_int32, c_int32, c_double] + [_dp] * 8),
+    "sk_group_rule_get": (c_int, [c_void_p, c_int32, _dp, _dp]),
+    "sk_group_sdf_builtin": (c_int, [c_void_p, c_int32, _dp, c_int32, c_int32]),
+    "sk_group_targets_set": (c_int, [c_void_p, c_void_p, c_int64, POINTER(TargetInfo)]),
+    "sk_group_run_begin": (c_int, [c_void_p]),
+    "sk_group_zero_lag_set": (c_int, [c_void_p, c_double]),
+    "sk_group_panel_begin": (c_int, [c_void_p, c_int64, c_int64, _dp, _dp]),
+    "sk_group_subinterval": (c_int, [c_void_p, c_double, c_double, POINTER(SubintervalOpts), _dp]),
+    "sk_group_subinterval_host": (c_int, [c_void_p, c_double, c_double, _dp, _dp, _dp, _dp, POINTER(SubintervalOpts), _dp]),
+    "sk_group_subinterval_accept": (c_int, [c_void_p]),
+    "sk_group_panel_commit": (c_int, [c_void_p]),
+    "sk_group_converge_scan": (c_int, [c_void_p, POINTER(ScanArgs), POINTER(c_int64), _dp]),
+    "sk_group_converge_apply": (c_int, [c_void_p, POINTER(ScanArgs), c_int64]),
+    "sk_group_results_get": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "sk_group_stats_get": (c_int, [c_void_p, POINTER(Stats)]),
     "sk_host_gauss_rule": (c_int, [c_int32, c_double, _dp, _dp]),
     "sk_host_es_plan": (c_int, [c_int32, _dp, POINTER(c_int32), _dp, POINTER(c_int32), _dp, _dp]),
 }
@@ -428,6 +451,147 @@ class Session:
     def stats(self) -> dict:
         st = Stats()
         self._ck(self._L.sk_stats_get(self._h, byref(st)))
+        return st.as_dict()
+
+
+class GroupSession:
+    """Owns one sk_group: several GPUs behind the call sequence of a single Session (include/spectralkernels_b200.h,
+    "device group").  The distances of `targets_set` are cut into contiguous chunks, one per device; every step is
+    enqueued on all devices before anything is read back.  Only the entry points the host-array path of
+    `kernel_values` uses exist on a group (no device-pointer / pair-list / log-weighted variants)."""
+
+    def __init__(self, devices, timing: bool = False):
+        self._L = load()
+        self._h = c_void_p()
+        devs = (c_int32 * len(devices))(*[int(d) for d in devices])
+        rc = self._L.sk_group_create(devs, len(devices), byref(self._h))
+        if rc != SK_OK:
+            raise SkError(rc, "sk_group_create failed (are these CUDA devices visible? there is no CPU fallback)")
+        self.devices = [int(d) for d in devices]
+        self.device = self.devices[0]
+        if timing:
+            self.set_timing(True)
+        self.rule_key = None
+        self.sdf_key = None
+
+    def _ck(self, rc: int):
+        if rc != SK_OK:
+            detail = self._L.sk_group_last_error(self._h)
+            base = self._L.sk_error_string(rc)
+            raise SkError(rc, (detail or base or b"").decode())
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self._L.sk_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._ck(self._L.sk_group_synchronize(self._h))
+
+    def set_timing(self, on: bool):
+        self._ck(self._L.sk_group_set_timing(self._h, 1 if on else 0))
+
+    def set_nufft_eps(self, eps: float):
+        self._ck(self._L.sk_group_set_nufft_eps(self._h, float(eps)))
+
+    def rule_set(self, m: int, k: int, p: float, leg=None, jac=None):
+        key = (int(m), int(k), float(p), leg is None, jac is None)
+        if leg is None and jac is None and key == self.rule_key:
+            return
+        args, keep = [], []
+        for rule in (leg, jac):
+            if rule is None:
+                args += [None] * 4
+            else:
+                arrs = [_f64(a) for a in rule]
+                keep += arrs
+                args += [_p(a) for a in arrs]
+        self._ck(self._L.sk_group_rule_set(self._h, int(m), int(k), float(p), *args))
+        self.rule_key = key
+        self.m, self.k, self.p = int(m), int(k), float(p)
+
+    def rule_get(self, which: int):
+        n = self.m * (2 if which in (1, 3) else 1)
+        no, wt = np.empty(n), np.empty(n)
+        self._ck(self._L.sk_group_rule_get(self._h, int(which), _p(no), _p(wt)))
+        return no, wt
+
+    def sdf_builtin(self, family: int, params, deriv_index: int = 0):
+        pr = _f64(params)
+        self._ck(self._L.sk_group_sdf_builtin(self._h, int(family), _p(pr) if pr.size else None, pr.size, int(deriv_index)))
+        self.sdf_key = (int(family), tuple(pr.tolist()), int(deriv_index))
+
+    def targets_set(self, xs: np.ndarray) -> TargetInfo:
+        xs = _f64(xs)
+        info = TargetInfo()
+        self._ck(self._L.sk_group_targets_set(self._h, xs.ctypes.data, xs.size, byref(info)))
+        self._last_targets = (info, int(info.n_in))
+        return info
+
+    def _unsupported(self, *a, **k):
+        raise NotImplementedError("a device group takes host arrays of distances only (sk_group_targets_set)")
+
+    targets_set_device = targets_set_pairs = targets_scale = subinterval_logw_host = results_get_device = \
+        results_get_async = _unsupported
+
+    def run_begin(self):
+        self._ck(self._L.sk_group_run_begin(self._h))
+
+    def zero_lag_set(self, value: float):
+        self._ck(self._L.sk_group_zero_lag_set(self._h, float(value)))
+
+    def panel_begin(self, ix1: int, hi: int):
+        lo, hi_ = c_double(), c_double()
+        self._ck(self._L.sk_group_panel_begin(self._h, int(ix1), int(hi), byref(lo), byref(hi_)))
+        return lo.value, hi_.value
+
+    def subinterval(self, a: float, b: float, cmul: float, p: float, kernel: int, logw: bool, speculate=None,
+                    nu: int = 0, xdiv_pow: float = 0.0) -> float:
+        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0, int(nu), 0, float(xdiv_pow),
+                            ctypes.pointer(speculate) if speculate is not None else None)
+        out = c_double()
+        self._ck(self._L.sk_group_subinterval(self._h, float(a), float(b), byref(o), byref(out)))
+        return out.value
+
+    def subinterval_host(self, a, b, no1, buf1, no2, buf2, cmul, p, kernel, logw, speculate=None,
+                         nu: int = 0, xdiv_pow: float = 0.0) -> float:
+        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0, int(nu), 0, float(xdiv_pow),
+                            ctypes.pointer(speculate) if speculate is not None else None)
+        out = c_double()
+        no1, buf1, no2, buf2 = _f64(no1), _f64(buf1), _f64(no2), _f64(buf2)
+        self._ck(self._L.sk_group_subinterval_host(self._h, float(a), float(b), _p(no1), _p(buf1), _p(no2), _p(buf2),
+                                                   byref(o), byref(out)))
+        return out.value
+
+    def subinterval_accept(self):
+        self._ck(self._L.sk_group_subinterval_accept(self._h))
+
+    def panel_commit(self):
+        self._ck(self._L.sk_group_panel_commit(self._h))
+
+    def converge_scan(self, args: ScanArgs):
+        new_hi, r = c_int64(), c_double()
+        self._ck(self._L.sk_group_converge_scan(self._h, byref(args), byref(new_hi), byref(r)))
+        return new_hi.value, r.value
+
+    def converge_apply(self, args: ScanArgs, new_hi: int):
+        self._ck(self._L.sk_group_converge_apply(self._h, byref(args), int(new_hi)))
+
+    def results_get(self, n_in: int, want_errors: bool = True, out_vals=None, out_errs=None):
+        vals = out_vals if out_vals is not None else np.empty(n_in)
+        errs = (out_errs if out_errs is not None else np.empty(n_in)) if want_errors else None
+        self._ck(self._L.sk_group_results_get(self._h, vals.ctypes.data, errs.ctypes.data if errs is not None else None))
+        return vals, errs
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._ck(self._L.sk_group_stats_get(self._h, byref(st)))
         return st.as_dict()
 
 

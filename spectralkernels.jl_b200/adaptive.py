@@ -20,7 +20,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _capi
-from ._capi import SK_CRIT, SK_KERNEL_BESSEL, SK_KERNEL_COS, SK_KERNEL_SIN, ScanArgs, Session, SkError
+from ._capi import SK_CRIT, SK_KERNEL_BESSEL, SK_KERNEL_COS, SK_KERNEL_SIN, GroupSession, ScanArgs, Session, SkError
 from .sdf import is_builtin
 
 _CRITERIA = ("panel", "tails", "both")
@@ -34,15 +34,17 @@ class AdaptiveKernelConfig:
     """Mirror of `AdaptiveKernelConfig` (src/adaptive.jl:2-59).
 
     `f` is a callable S(w) accepting numpy arrays, or a built-in family from `sdf` (device-evaluated).
-    Extra, optional keywords (reference-compatible defaults): `device` (CUDA ordinal), `nufft_eps`
-    (the reference hard-wires 1e-15 in src/utils.jl:10), `engine` (an object implementing the Session
-    interface; used by the multi-process tests)."""
+    Extra, optional keywords (reference-compatible defaults): `device` (CUDA ordinal), `devices` (a list of CUDA
+    ordinals: the same single-caller `kernel_values(cfg, xs)` then spreads the distances over these GPUs -- one
+    process, one host thread, no collective library: the C ABI's "device group"), `nufft_eps` (the reference
+    hard-wires 1e-15 in src/utils.jl:10), `engine` (an object implementing the Session interface; used by the
+    multi-process tests)."""
 
     def __init__(self, f: Callable, *, df: Optional[Callable] = None, dim: int = 1, alpha: float = 0.0,
                  tol: float = 1e-8, derivative: bool = False, logw: bool = False,
                  convergence_criteria="both", tail: Optional[float] = None,
                  quadspec: Tuple[int, int] = (2 ** 12, 2 ** 4), device: int = 0, nufft_eps: float = 1e-15,
-                 engine=None):
+                 engine=None, devices: Optional[Sequence[int]] = None):
         crit = _sym(convergence_criteria)
         if crit not in _CRITERIA:                                              # adaptive.jl:29-31
             raise ValueError("Argument convergence_criteria must be one of :panel, :tails, :both.")
@@ -64,7 +66,8 @@ class AdaptiveKernelConfig:
         if self.logw:
             c *= -1                                                             # :45
         self.c = c
-        self.device, self.nufft_eps = int(device), float(nufft_eps)
+        self.devices = [int(d) for d in devices] if devices is not None else None
+        self.device, self.nufft_eps = (self.devices[0] if self.devices else int(device)), float(nufft_eps)
         self._engine = engine
         self._rules = None       # host copies of the canonical rules (for host-evaluated integrands)
 
@@ -72,7 +75,7 @@ class AdaptiveKernelConfig:
     @property
     def engine(self):
         if self._engine is None:
-            self._engine = Session(self.device)
+            self._engine = GroupSession(self.devices) if (self.devices and len(self.devices) > 1) else Session(self.device)
             if self.nufft_eps != 1e-15:
                 self._engine.set_nufft_eps(self.nufft_eps)
         return self._engine

@@ -179,6 +179,9 @@ struct sk_ctx {
   long long g_n_lb = 0;
   // speculative commit of the panel's first sub-interval (see sk_subinterval_opts::speculate)
   bool spec_active = false, spec_accepted = false;
+  bool pend_timed = false, pend_spec = false;  // between transform_and_stage_enqueue and _finish
+  bool scan_from_spec = false;                 // between converge_scan_enqueue and _finish
+  int pend_rc = 0;                             // local result of transform_and_stage_enqueue in a sharded run
   long long panel_subs = 0;                  // sub-intervals evaluated in the open panel
   long long n_act_global = 0;                // active targets over all ranks (0: this rank only)
   sk_scan_args spec_args;
@@ -250,12 +253,15 @@ int flush_commit(sk_ctx *c);
 
 // collective A (after a sub-interval): MAX of max|I2-I1| and of the NaN flags.  Enqueued on the stream
 // right behind the kernel that filled d_red; the caller's read-back then also fetches h_scal->ga.
-int comm_reduce_a(sk_ctx *c, int idle) {
+// err != 0: this rank could not evaluate the sub-interval (allocation failure, geometry out of range, ...).  It still
+// joins the collective -- its peers are already waiting in it -- with neutral values and the error word set, so that
+// every rank sees the failure and raises instead of blocking in the all-reduce for ever.
+int comm_reduce_a(sk_ctx *c, int idle, int err = 0) {
   if (!c->comm) return SK_OK;
   NcclApi *N = nccl_api();
-  k_pack_global_a<<<1, 1, 0, c->stream>>>(c->d_red, c->d_ga, idle);
+  k_pack_global_a<<<1, 1, 0, c->stream>>>(c->d_red, c->d_ga, (idle || err) ? 1 : 0, err);
   LAUNCH_CHECK();
-  NCK(N->AllReduce(c->d_ga, c->d_ga, 4, ncclUint64, ncclMax, c->comm, c->stream));
+  NCK(N->AllReduce(c->d_ga, c->d_ga, 5, ncclUint64, ncclMax, c->comm, c->stream));
   CK(cudaMemcpyAsync(&c->h_scal->ga, c->d_ga, sizeof(SkGlobalA), cudaMemcpyDeviceToHost, c->stream));
   return SK_OK;
 }
@@ -505,8 +511,11 @@ int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, con
   return SK_OK;
 }
 
-// transform + stage for the sub-interval whose sources are in no1/buf1/no2/buf2
-int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, double *max_abs_diff) {
+// transform + stage for the sub-interval whose sources are in no1/buf1/no2/buf2, in two halves: everything that is
+// enqueued on the context's stream, and the read-back of the reduced scalars after the stream has drained.  One
+// context runs the halves back to back (transform_and_stage); a device group (sk_group_*) enqueues on every device
+// first and reads back afterwards, so that the devices work concurrently under a single host thread.
+int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_subinterval_opts *o) {
   const long long n_act = c->hi - c->lo;
   const long long M1 = (long long)c->m * c->k, M2 = 2 * M1;
   const int ksin = o->kernel == SK_KERNEL_SIN;
@@ -578,12 +587,34 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
     c->stats.n_direct++;
   }
   CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
-  {
-    int rcc = comm_reduce_a(c, 0);
-    if (rcc != SK_OK) return rcc;
-  }
+  c->pend_timed = c->timing && (fast || hk_timed);
+  c->pend_spec = spec_on;
+  if (spec_on) c->spec_args = *o->speculate;
+  return SK_OK;
+}
+
+int transform_and_stage_enqueue(sk_ctx *c, double a, double b, const sk_subinterval_opts *o) {
+  c->pend_timed = c->pend_spec = false;
+  const int rc = transform_and_stage_enqueue_local(c, a, b, o);
+  c->pend_rc = rc;
+  if (!c->comm) return rc;
+  // sharded run: a rank that failed locally still joins the collective (its peers are waiting in it)
+  const std::string msg = c->errmsg;
+  const int rcc = comm_reduce_a(c, 0, rc != SK_OK);
+  if (rc != SK_OK) c->errmsg = msg;
+  return rcc != SK_OK ? rcc : SK_OK;                     // a local failure is reported by _finish, after the collective
+}
+
+// flags_out != nullptr: hand the NaN flags to the caller (a device group applies the rule of src/quadrature.jl:165
+// to the flags of all devices) instead of raising SK_ERR_NAN here
+int transform_and_stage_finish(sk_ctx *c, double *max_abs_diff, unsigned int *flags_out) {
+  const long long n_act = c->hi - c->lo;
   CK(cudaStreamSynchronize(c->stream));
-  if (c->timing && (fast || hk_timed)) {
+  if (c->comm) {
+    if (c->pend_rc != SK_OK) return c->pend_rc;                     // this rank's own failure (message already set)
+    if (c->h_scal->ga.err) return fail(c, SK_ERR_STATE, "another rank failed in this sub-interval");
+  }
+  if (c->pend_timed) {
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
     c->stats.source_ms += ms;
@@ -601,19 +632,25 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
   c->panel_subs++;
   c->stats.n_subintervals++;
   c->stats.units += n_act;
-  if (spec_on) {
+  if (c->pend_spec) {
     c->spec_active = true;
     c->spec_accepted = false;
-    c->spec_args = *o->speculate;
     const long long top = c->h_scal->red.max_unconv;
     c->spec_new_hi = top + 1;
     c->spec_r = 0.0;
     if (top >= c->lo) std::memcpy(&c->spec_r, &c->h_scal->red.rbits, sizeof(double));
     c->stats.n_speculated++;
   }
+  if (flags_out) { *flags_out = fl; return SK_OK; }
   // any(isnan, int1) || any(isnan, int2) && throw(...)   (src/quadrature.jl:165)
   if (!(fl & SK_FLAG_NAN1) && (fl & SK_FLAG_NAN2)) return fail(c, SK_ERR_NAN, "NaN detected in panel integral...");
   return SK_OK;
+}
+
+int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, double *max_abs_diff) {
+  int rc = transform_and_stage_enqueue(c, a, b, o);
+  if (rc != SK_OK) return rc;
+  return transform_and_stage_finish(c, max_abs_diff, nullptr);
 }
 
 // a speculative commit that was not accepted is rolled back before anything else touches the panel
@@ -723,8 +760,8 @@ int targets_sort_general(sk_ctx *c, long long n_in) {
 
 // K8 (sk_k8.cuh): c->in holds the n_in raw distances -> sorted unique table c->uxs, inverse map c->inv.  One host
 // synchronisation, at the end (the summary); an already strictly increasing input is detected on the device and
-// costs one read pass.  force_general: take the general sort (tests).
-int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, bool force_general = false) {
+// costs one read pass.  Two halves like transform_and_stage (a device group sorts all chunks concurrently).
+int targets_enqueue(sk_ctx *c, long long n_in) {
   c->have_targets = false;
   if (n_in > 0x7ffffff0LL) return fail(c, SK_ERR_ARG, "n_in too large");
   const size_t nfine_max = (size_t)(n_in >> SK_K8_TARGET_LOG) + 2;
@@ -746,30 +783,31 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   unsigned int *chist = (unsigned int *)(c->k8_ctl.p + off_hist);
   unsigned long long *desc = (unsigned long long *)(c->k8_ctl.p + off_desc);
   unsigned int *fill = (unsigned int *)(c->k8_ctl.p + off_fill);
-  bool general = force_general;
   if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
-  if (!general) {
-    CK(cudaMemsetAsync(c->k8_ctl.p, 0, ctl_bytes, c->stream));
-    const unsigned int gs = std::min<unsigned int>(nblk(n_in, 256), 148u * 8u);    // grid-stride passes: 2048 threads per SM
-    k_k8_stats<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st);
-    LAUNCH_CHECK();
-    k_k8_sample<<<std::min<unsigned int>(nblk(n_in, 256), 148u * 2u), 256, 0, c->stream>>>(c->in.p, n_in, st, chist);
-    LAUNCH_CHECK();
-    k_k8_plan<<<1, 1024, 0, c->stream>>>(st, chist, n_in, c->k8_ctab.p);
-    LAUNCH_CHECK();
-    k_k8_scatter<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->k8_ctab.p, fill, c->k8_skeys.p, c->k8_sidx.p, c->inv.p);
-    LAUNCH_CHECK();
-    k_k8_finish<<<(unsigned int)nfine_max, SK_K8_TPB, 0, c->stream>>>(st, fill, c->k8_skeys.p, c->k8_sidx.p, desc, c->uxs.p, c->inv.p, getenv("SK_K8_DBG") ? atoi(getenv("SK_K8_DBG")) : 0);
-    LAUNCH_CHECK();
-    k_k8_identity<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->uxs.p, c->inv.p);
-    LAUNCH_CHECK();
-    k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, n_in, c->d_sum);
-    LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (c->h_scal->sum.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
-    general = c->h_scal->sum.overflow != 0;
-  }
+  CK(cudaMemsetAsync(c->k8_ctl.p, 0, ctl_bytes, c->stream));
+  const unsigned int gs = std::min<unsigned int>(nblk(n_in, 256), 148u * 8u);    // grid-stride passes: 2048 threads per SM
+  k_k8_stats<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st);
+  LAUNCH_CHECK();
+  k_k8_sample<<<std::min<unsigned int>(nblk(n_in, 256), 148u * 2u), 256, 0, c->stream>>>(c->in.p, n_in, st, chist);
+  LAUNCH_CHECK();
+  k_k8_plan<<<1, 1024, 0, c->stream>>>(st, chist, n_in, c->k8_ctab.p);
+  LAUNCH_CHECK();
+  k_k8_scatter<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->k8_ctab.p, fill, c->k8_skeys.p, c->k8_sidx.p, c->inv.p);
+  LAUNCH_CHECK();
+  k_k8_finish<<<(unsigned int)nfine_max, SK_K8_TPB, 0, c->stream>>>(st, fill, c->k8_skeys.p, c->k8_sidx.p, desc, c->uxs.p, c->inv.p);
+  LAUNCH_CHECK();
+  k_k8_identity<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->uxs.p, c->inv.p);
+  LAUNCH_CHECK();
+  k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, n_in, c->d_sum);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
+  return SK_OK;
+}
+
+int targets_finish(sk_ctx *c, long long n_in, sk_target_info *info, bool force_general) {
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->h_scal->sum.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
+  const bool general = force_general || c->h_scal->sum.overflow != 0;
   if (general) {
     int rc = targets_sort_general(c, n_in);
     if (rc != SK_OK) return rc;
@@ -806,6 +844,12 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
     info->r_max = sm.r_last;
   }
   return SK_OK;
+}
+
+int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, bool force_general = false) {
+  int rc = targets_enqueue(c, n_in);
+  if (rc != SK_OK) return rc;
+  return targets_finish(c, n_in, info, force_general);
 }
 
 // the lazy commit of the last panel, when no scan consumed it
@@ -1048,6 +1092,9 @@ int sk_comm_idle(sk_ctx *c, int32_t which) {
     comm_take_a(c, &fl, &mx);
     if (fl & SK_FLAG_NAND) mx = std::nan("");
     c->g_max_abs = mx;
+    // the idle rank raises what the active ranks raise, so that all ranks leave the adaptive loop together
+    if (c->h_scal->ga.err) return fail(c, SK_ERR_STATE, "another rank failed in this sub-interval");
+    if (!(fl & SK_FLAG_NAN1) && (fl & SK_FLAG_NAN2)) return fail(c, SK_ERR_NAN, "NaN detected in panel integral...");
   } else {
     int rc = comm_reduce_b(c, false, 0ull, 0);
     if (rc != SK_OK) return rc;
@@ -1372,10 +1419,9 @@ static int subinterval_prologue(sk_ctx *c, double a, double b, const sk_subinter
   return rollback_speculation(c);
 }
 
-int sk_subinterval(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, double *max_abs_diff) {
+static int subinterval_builtin_enqueue(sk_ctx *c, double a, double b, const sk_subinterval_opts *o) {
   int rc = subinterval_prologue(c, a, b, o);
   if (rc != SK_OK) return rc;
-  if (!max_abs_diff) return fail(c, SK_ERR_ARG, "null output");
   if (c->family == SK_SDF_HOST) return fail(c, SK_ERR_STATE, "no built-in spectral density set: use sk_subinterval_host");
   if (o->p != c->p) return fail(c, SK_ERR_ARG, "opts.p (%g) differs from the rule's p (%g)", o->p, c->p);
   const bool origin = (a == 0.0 && c->p != 0.0);                    // src/quadrature.jl:185
@@ -1399,32 +1445,44 @@ int sk_subinterval(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, 
                                                           c->no1.p, c->buf1.p, c->no2.p, c->buf2.p);
   LAUNCH_CHECK();
   c->have_sources = true;
-  return transform_and_stage(c, a, b, o, max_abs_diff);
+  return transform_and_stage_enqueue(c, a, b, o);
 }
 
-int sk_subinterval_host(sk_ctx *c, double a, double b, const double *no1, const double *buf1, const double *no2,
-                        const double *buf2, const sk_subinterval_opts *o, double *max_abs_diff) {
+int sk_subinterval(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, double *max_abs_diff) {
+  if (c && !max_abs_diff) return fail(c, SK_ERR_ARG, "null output");
+  int rc = subinterval_builtin_enqueue(c, a, b, o);
+  if (rc != SK_OK) return rc;
+  return transform_and_stage_finish(c, max_abs_diff, nullptr);
+}
+
+static int subinterval_host_enqueue(sk_ctx *c, double a, double b, const double *no1, const double *buf1, const double *no2,
+                                    const double *buf2, const sk_subinterval_opts *o) {
   int rc = subinterval_prologue(c, a, b, o);
   if (rc != SK_OK) return rc;
-  if (!no1 || !buf1 || !no2 || !buf2 || !max_abs_diff) return fail(c, SK_ERR_ARG, "null pointer");
+  if (!no1 || !buf1 || !no2 || !buf2) return fail(c, SK_ERR_ARG, "null pointer");
   const long long M1 = (long long)c->m * c->k;
   CK(cudaMemcpyAsync(c->no1.p, no1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->buf1.p, buf1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->no2.p, no2, sizeof(double) * 2 * M1, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->buf2.p, buf2, sizeof(double) * 2 * M1, cudaMemcpyHostToDevice, c->stream));
   c->have_sources = true;
-  return transform_and_stage(c, a, b, o, max_abs_diff);
+  return transform_and_stage_enqueue(c, a, b, o);
+}
+
+int sk_subinterval_host(sk_ctx *c, double a, double b, const double *no1, const double *buf1, const double *no2,
+                        const double *buf2, const sk_subinterval_opts *o, double *max_abs_diff) {
+  if (c && !max_abs_diff) return fail(c, SK_ERR_ARG, "null pointer");
+  int rc = subinterval_host_enqueue(c, a, b, no1, buf1, no2, buf2, o);
+  if (rc != SK_OK) return rc;
+  return transform_and_stage_finish(c, max_abs_diff, nullptr);
 }
 
 // Log-weighted origin sub-interval (src/quadrature.jl:186-228, dim = 1): the host evaluates both
 // integrands of the integration by parts (it owns f and df) and the boundary-term coefficient.
-int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, const double *bufa1, const double *bufb1,
-                             const double *no2, const double *bufa2, const double *bufb2, const sk_subinterval_opts *o,
-                             double i0_coef, double denom, double *max_abs_diff) {
-  int rc = subinterval_prologue(c, a, b, o);
-  if (rc != SK_OK) return rc;
-  if (!no1 || !bufa1 || !bufb1 || !no2 || !bufa2 || !bufb2 || !max_abs_diff) return fail(c, SK_ERR_ARG, "null pointer");
-  if (a != 0.0) return fail(c, SK_ERR_ARG, "the integration-by-parts branch applies to a == 0 only");
+static int logw_host_enqueue_local(sk_ctx *c, double a, double b, const double *no1, const double *bufa1, const double *bufb1,
+                                   const double *no2, const double *bufa2, const double *bufb2, const sk_subinterval_opts *o,
+                                   double i0_coef, double denom) {
+  int rc = SK_OK;
   const long long M1 = (long long)c->m * c->k, M2 = 2 * M1;
   const long long n_act = c->hi - c->lo;
   CK(c->bufb1.ensure(M1));
@@ -1497,11 +1555,29 @@ int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, c
     c->stats.n_direct++;
   }
   CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
-  {
-    int rcc = comm_reduce_a(c, 0);
+  return SK_OK;
+}
+
+int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, const double *bufa1, const double *bufb1,
+                             const double *no2, const double *bufa2, const double *bufb2, const sk_subinterval_opts *o,
+                             double i0_coef, double denom, double *max_abs_diff) {
+  int rc = subinterval_prologue(c, a, b, o);
+  if (rc != SK_OK) return rc;
+  if (!no1 || !bufa1 || !bufb1 || !no2 || !bufa2 || !bufb2 || !max_abs_diff) return fail(c, SK_ERR_ARG, "null pointer");
+  if (a != 0.0) return fail(c, SK_ERR_ARG, "the integration-by-parts branch applies to a == 0 only");
+  const long long n_act = c->hi - c->lo;
+  rc = logw_host_enqueue_local(c, a, b, no1, bufa1, bufb1, no2, bufa2, bufb2, o, i0_coef, denom);
+  if (c->comm) {          // a rank that failed locally still joins the collective (its peers are waiting in it)
+    const std::string msg = c->errmsg;
+    const int rcc = comm_reduce_a(c, 0, rc != SK_OK);
     if (rcc != SK_OK) return rcc;
+    CK(cudaStreamSynchronize(c->stream));
+    if (rc != SK_OK) { c->errmsg = msg; return rc; }
+    if (c->h_scal->ga.err) return fail(c, SK_ERR_STATE, "another rank failed in this sub-interval");
+  } else {
+    if (rc != SK_OK) return rc;
+    CK(cudaStreamSynchronize(c->stream));
   }
-  CK(cudaStreamSynchronize(c->stream));
   unsigned int fl = c->h_scal->red.flags;
   double mx;
   std::memcpy(&mx, &c->h_scal->red.maxbits, sizeof(double));
@@ -1572,27 +1648,26 @@ int sk_panel_commit(sk_ctx *c) {
   return SK_OK;
 }
 
-int sk_converge_scan(sk_ctx *c, const sk_scan_args *a, int64_t *new_hi, double *r_at_new_hi) {
-  if (!c || !a || !new_hi) return SK_ERR_ARG;
+// the scan in two halves (see transform_and_stage_enqueue): enqueue the fused commit + predicate pass (nothing at all
+// when the panel was committed speculatively), then read the reduced scalars back
+static int converge_scan_enqueue(sk_ctx *c, const sk_scan_args *a) {
+  if (!c || !a) return SK_ERR_ARG;
   if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
   if (a->criteria < 0 || a->criteria > 2) return fail(c, SK_ERR_ARG, "bad criteria");
+  CK(cudaSetDevice(c->device));
+  c->scan_from_spec = false;
   if (c->spec_active && c->spec_accepted) {
     const sk_scan_args &s0 = c->spec_args;
     const bool same = s0.criteria == a->criteria && std::memcmp(&s0.trunc_a, &a->trunc_a, sizeof(double)) == 0 &&
                       std::memcmp(&s0.trunc_num, &a->trunc_num, sizeof(double)) == 0 && s0.xpow == a->xpow && s0.tau == a->tau;
     if (!same) return fail(c, SK_ERR_STATE, "scan arguments differ from the ones the panel was speculated with");
-    *new_hi = c->spec_new_hi;
-    if (r_at_new_hi) *r_at_new_hi = c->spec_r;
-    c->scan_hi = c->spec_new_hi;
-    c->scan_r = c->spec_r;
+    c->scan_from_spec = true;
     if (c->comm) {   // sharded run: the scan is a collective point for every rank
       unsigned long long rb = 0ull;
       std::memcpy(&rb, &c->spec_r, sizeof(double));
       const long long nlb = c->spec_new_hi - c->lo > 0 ? c->spec_new_hi - c->lo : 0;
       int rcc = comm_reduce_b(c, false, rb, nlb);
       if (rcc != SK_OK) return rcc;
-      CK(cudaStreamSynchronize(c->stream));
-      comm_take_b(c);
     }
     return SK_OK;
   }
@@ -1612,9 +1687,20 @@ int sk_converge_scan(sk_ctx *c, const sk_scan_args *a, int64_t *new_hi, double *
   LAUNCH_CHECK();
   c->commit_pending = false;
   CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
-  {
-    int rcc = comm_reduce_b(c, true, 0ull, 0);
-    if (rcc != SK_OK) return rcc;
+  return comm_reduce_b(c, true, 0ull, 0);
+}
+
+static int converge_scan_finish(sk_ctx *c, int64_t *new_hi, double *r_at_new_hi) {
+  if (c->scan_from_spec) {
+    *new_hi = c->spec_new_hi;
+    if (r_at_new_hi) *r_at_new_hi = c->spec_r;
+    c->scan_hi = c->spec_new_hi;
+    c->scan_r = c->spec_r;
+    if (c->comm) {
+      CK(cudaStreamSynchronize(c->stream));
+      comm_take_b(c);
+    }
+    return SK_OK;
   }
   CK(cudaStreamSynchronize(c->stream));
   comm_take_b(c);
@@ -1626,6 +1712,13 @@ int sk_converge_scan(sk_ctx *c, const sk_scan_args *a, int64_t *new_hi, double *
   c->scan_hi = top + 1;
   c->scan_r = r;
   return SK_OK;
+}
+
+int sk_converge_scan(sk_ctx *c, const sk_scan_args *a, int64_t *new_hi, double *r_at_new_hi) {
+  if (!c || !a || !new_hi) return SK_ERR_ARG;
+  int rc = converge_scan_enqueue(c, a);
+  if (rc != SK_OK) return rc;
+  return converge_scan_finish(c, new_hi, r_at_new_hi);
 }
 
 int sk_converge_apply(sk_ctx *c, const sk_scan_args *a, int64_t new_hi) {
@@ -1684,7 +1777,7 @@ int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
   return SK_OK;
 }
 
-int sk_results_get(sk_ctx *c, double *vals, double *errs) {
+static int results_enqueue(sk_ctx *c, double *vals, double *errs) {
   if (!c || !vals) return SK_ERR_ARG;
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
   CK(cudaSetDevice(c->device));
@@ -1694,13 +1787,29 @@ int sk_results_get(sk_ctx *c, double *vals, double *errs) {
   if (rc != SK_OK) return rc;
   CK(c->out_v.ensure(c->n_in));
   if (errs) CK(c->out_e.ensure(c->n_in));
+  if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
   k_gather<<<nblk(c->n_in, 1024), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, c->out_v.p, errs ? c->out_e.p : nullptr, c->in.p,
                                                        c->in_scale, c->tails);
   LAUNCH_CHECK();
+  if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
   CK(cudaMemcpyAsync(vals, c->out_v.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
   if (errs) CK(cudaMemcpyAsync(errs, c->out_e.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
   return SK_OK;
+}
+static int results_finish(sk_ctx *c) {
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->timing) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->stats.gather_ms += ms;
+  }
+  return SK_OK;
+}
+
+int sk_results_get(sk_ctx *c, double *vals, double *errs) {
+  int rc = results_enqueue(c, vals, errs);
+  if (rc != SK_OK) return rc;
+  return results_finish(c);
 }
 
 // Batched evaluations (hyperparameter sweeps over the same targets): gather on the compute stream, copy on a second
@@ -1762,6 +1871,407 @@ int sk_ctx_set_hankel_mode(sk_ctx *c, int mode) {
 int sk_stats_get(sk_ctx *c, sk_stats *out) {
   if (!c || !out) return SK_ERR_ARG;
   *out = c->stats;
+  return SK_OK;
+}
+
+// ---- device group: ONE caller, several GPUs -------------------------------------------------------------------
+// The reference's API is a single task calling kernel_values(cfg, xs) (src/adaptive.jl:95-108).  A group gives that
+// caller N devices behind the same sequence of calls: the distances are cut into N contiguous chunks, every device
+// sorts / de-duplicates its own chunk and runs the same adaptive loop on it; each step is enqueued on all devices
+// first and read back afterwards, so one host thread keeps N GPUs (and N PCIe links for the upload of the distances
+// and the download of the results) busy.  The only exchange is the host-side max of the per-device scalars (max |I2-I1|,
+// NaN flags, largest unconverged distance) -- no NCCL, no peer copies.  Every device builds the transform geometry from
+// the GLOBAL distance range (sk_panel_set_range), so values and error estimates are bit-identical to a one-device run
+// over the same distances.  Indices crossing this API (ix1, hi, new_hi) count over the concatenation of the devices'
+// unique tables; equal distances in different chunks count once per chunk.
+struct sk_group {
+  std::vector<sk_ctx *> ctx;
+  std::string errmsg;
+  int nuse = 0;                                   // devices holding a chunk (n_in may be smaller than the group)
+  long long n_in = 0;
+  std::vector<long long> off, cnt, ix1, hi, new_hi;
+  std::vector<char> active;
+  std::vector<sk_target_info> info;
+  bool have_targets = false, has_zero = false, in_panel = false;
+  double r_min_pos = 0, r_max = 0, r_hi_g = 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+namespace {
+int gfail(sk_group *g, int dev, int rc) {
+  if (g && dev >= 0 && dev < (int)g->ctx.size())
+    g->errmsg = "device " + std::to_string(g->ctx[dev]->device) + ": " + g->ctx[dev]->errmsg;
+  return rc;
+}
+int gfailmsg(sk_group *g, int rc, const char *msg) {
+  if (g) g->errmsg = msg;
+  return rc;
+}
+long long group_global_hi(const sk_group *g) {
+  long long h = g->has_zero ? 1 : 0;
+  for (int i = 0; i < g->nuse; ++i) h += std::max<long long>(g->hi[i] - (g->ix1[i] - 1), 0);
+  return h;
+}
+}  // namespace
+
+int sk_group_create(const int32_t *devices, int32_t ndev, sk_group **out) {
+  if (!out || !devices || ndev < 1) return SK_ERR_ARG;
+  *out = nullptr;
+  sk_group *g = new sk_group();
+  for (int i = 0; i < ndev; ++i) {            // (a device may be listed more than once: two chunks on one GPU)
+    sk_ctx *c = nullptr;
+    int rc = sk_ctx_create(devices[i], &c);
+    if (rc != SK_OK) { sk_group_destroy(g); return rc; }
+    g->ctx.push_back(c);
+  }
+  const size_t n = g->ctx.size();
+  g->off.assign(n, 0); g->cnt.assign(n, 0); g->ix1.assign(n, 1); g->hi.assign(n, 0); g->new_hi.assign(n, 0);
+  g->active.assign(n, 0);
+  g->info.resize(n);
+  *out = g;
+  return SK_OK;
+}
+
+int sk_group_destroy(sk_group *g) {
+  if (!g) return SK_OK;
+  for (sk_ctx *c : g->ctx) sk_ctx_destroy(c);
+  delete g;
+  return SK_OK;
+}
+
+int sk_group_size(const sk_group *g) { return g ? (int)g->ctx.size() : 0; }
+const char *sk_group_last_error(const sk_group *g) { return g ? g->errmsg.c_str() : "null group"; }
+
+int sk_group_ctx(sk_group *g, int32_t i, sk_ctx **out) {
+  if (!g || !out || i < 0 || i >= (int)g->ctx.size()) return SK_ERR_ARG;
+  *out = g->ctx[i];
+  return SK_OK;
+}
+
+int sk_group_set_timing(sk_group *g, int enabled) {
+  if (!g) return SK_ERR_ARG;
+  for (sk_ctx *c : g->ctx) sk_ctx_set_timing(c, enabled);
+  return SK_OK;
+}
+
+int sk_group_set_nufft_eps(sk_group *g, double eps) {
+  if (!g) return SK_ERR_ARG;
+  for (size_t i = 0; i < g->ctx.size(); ++i) {
+    int rc = sk_ctx_set_nufft_eps(g->ctx[i], eps);
+    if (rc != SK_OK) return gfail(g, (int)i, rc);
+  }
+  return SK_OK;
+}
+
+int sk_group_synchronize(sk_group *g) {
+  if (!g) return SK_ERR_ARG;
+  for (size_t i = 0; i < g->ctx.size(); ++i) {
+    cudaSetDevice(g->ctx[i]->device);
+    int rc = sk_ctx_synchronize(g->ctx[i]);
+    if (rc != SK_OK) return gfail(g, (int)i, rc);
+  }
+  return SK_OK;
+}
+
+int sk_group_rule_set(sk_group *g, int32_t m, int32_t k, double p, const double *leg_no1, const double *leg_wt1,
+                      const double *leg_no2, const double *leg_wt2, const double *jac_no1, const double *jac_wt1,
+                      const double *jac_no2, const double *jac_wt2) {
+  if (!g) return SK_ERR_ARG;
+  // device 0 generates (or receives) the rules; the others receive device 0's, so that all devices integrate with
+  // bit-identical nodes and weights
+  int rc = sk_rule_set(g->ctx[0], m, k, p, leg_no1, leg_wt1, leg_no2, leg_wt2, jac_no1, jac_wt1, jac_no2, jac_wt2);
+  if (rc != SK_OK) return gfail(g, 0, rc);
+  sk_ctx *c0 = g->ctx[0];
+  for (size_t i = 1; i < g->ctx.size(); ++i) {
+    sk_ctx *c = g->ctx[i];
+    if (c->have_rule && c->m == m && c->k == k && c->p == p && c->h_rule[0] == c0->h_rule[0] && c->h_rule[4] == c0->h_rule[4] &&
+        c->h_rule[1] == c0->h_rule[1] && c->h_rule[5] == c0->h_rule[5])
+      continue;
+    const bool jac = p != 0.0;
+    rc = sk_rule_set(c, m, k, p, c0->h_rule[0].data(), c0->h_rule[1].data(), c0->h_rule[2].data(), c0->h_rule[3].data(),
+                     jac ? c0->h_rule[4].data() : nullptr, jac ? c0->h_rule[5].data() : nullptr,
+                     jac ? c0->h_rule[6].data() : nullptr, jac ? c0->h_rule[7].data() : nullptr);
+    if (rc != SK_OK) return gfail(g, (int)i, rc);
+  }
+  return SK_OK;
+}
+
+int sk_group_rule_get(sk_group *g, int32_t which, double *no, double *wt) {
+  if (!g) return SK_ERR_ARG;
+  int rc = sk_rule_get(g->ctx[0], which, no, wt);
+  return rc == SK_OK ? rc : gfail(g, 0, rc);
+}
+
+int sk_group_sdf_builtin(sk_group *g, int32_t family, const double *params, int32_t nparams, int32_t deriv_index) {
+  if (!g) return SK_ERR_ARG;
+  for (size_t i = 0; i < g->ctx.size(); ++i) {
+    int rc = sk_sdf_builtin(g->ctx[i], family, params, nparams, deriv_index);
+    if (rc != SK_OK) return gfail(g, (int)i, rc);
+  }
+  return SK_OK;
+}
+
+int sk_group_targets_set(sk_group *g, const double *xs_host, int64_t n_in, sk_target_info *info) {
+  if (!g || !xs_host || n_in < 1) return gfailmsg(g, SK_ERR_ARG, "need at least one distance");
+  g->have_targets = false;
+  const int nd = (int)g->ctx.size();
+  g->nuse = (int)std::min<long long>(nd, n_in);
+  g->n_in = n_in;
+  // upload + sort of all chunks enqueued first (N PCIe links when xs_host is pinned memory: sk_host_alloc), read back after
+  for (int i = 0; i < g->nuse; ++i) {
+    sk_ctx *c = g->ctx[i];
+    g->off[i] = (long long)i * n_in / g->nuse;
+    g->cnt[i] = (long long)(i + 1) * n_in / g->nuse - g->off[i];
+    if (cudaSetDevice(c->device) != cudaSuccess || c->in.ensure(g->cnt[i]) != cudaSuccess ||
+        cudaMemcpyAsync(c->in.p, xs_host + g->off[i], sizeof(double) * g->cnt[i], cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+      c->errmsg = "upload of the distances failed";
+      return gfail(g, i, SK_ERR_CUDA);
+    }
+    int rc = targets_enqueue(c, g->cnt[i]);
+    if (rc != SK_OK) return gfail(g, i, rc);
+  }
+  g->has_zero = false;
+  g->r_min_pos = 0.0;
+  g->r_max = 0.0;
+  long long nu = 0;
+  for (int i = 0; i < g->nuse; ++i) {
+    sk_ctx *c = g->ctx[i];
+    cudaSetDevice(c->device);
+    int rc = targets_finish(c, g->cnt[i], &g->info[i], false);
+    if (rc != SK_OK) return gfail(g, i, rc);
+    const sk_target_info &t = g->info[i];
+    g->ix1[i] = t.has_zero ? 2 : 1;
+    g->hi[i] = t.n_unique;
+    if (t.has_zero) g->has_zero = true;
+    if (t.r_min_pos > 0 && (g->r_min_pos == 0.0 || t.r_min_pos < g->r_min_pos)) g->r_min_pos = t.r_min_pos;
+    if (t.r_max > g->r_max) g->r_max = t.r_max;
+    nu += t.n_unique - (t.has_zero ? 1 : 0);
+  }
+  g->r_hi_g = g->r_max;
+  g->have_targets = true;
+  g->in_panel = false;
+  if (info) {
+    info->n_in = n_in;
+    info->n_unique = nu + (g->has_zero ? 1 : 0);
+    info->has_zero = g->has_zero ? 1 : 0;
+    info->_pad = 0;
+    info->r_min_pos = g->r_min_pos;
+    info->r_max = g->r_max;
+  }
+  return SK_OK;
+}
+
+int sk_group_run_begin(sk_group *g) {
+  if (!g) return SK_ERR_ARG;
+  if (!g->have_targets) return gfailmsg(g, SK_ERR_STATE, "sk_group_targets_set first");
+  for (int i = 0; i < g->nuse; ++i) {
+    int rc = sk_run_begin(g->ctx[i]);
+    if (rc != SK_OK) return gfail(g, i, rc);
+    g->ix1[i] = g->info[i].has_zero ? 2 : 1;
+    g->hi[i] = g->info[i].n_unique;
+  }
+  g->r_hi_g = g->r_max;
+  g->in_panel = false;
+  return SK_OK;
+}
+
+int sk_group_zero_lag_set(sk_group *g, double value) {
+  if (!g) return SK_ERR_ARG;
+  for (int i = 0; i < g->nuse; ++i) {
+    cudaSetDevice(g->ctx[i]->device);
+    int rc = sk_zero_lag_set(g->ctx[i], value);
+    if (rc != SK_OK) return gfail(g, i, rc);
+  }
+  return SK_OK;
+}
+
+int sk_group_panel_begin(sk_group *g, int64_t ix1, int64_t hi, double *r_lo, double *r_hi) {
+  if (!g) return SK_ERR_ARG;
+  if (!g->have_targets) return gfailmsg(g, SK_ERR_STATE, "sk_group_targets_set first");
+  if (ix1 != (g->has_zero ? 2 : 1) || hi != group_global_hi(g))
+    return gfailmsg(g, SK_ERR_ARG, "a group follows the active range of its own scans: pass ix1 / hi as returned");
+  long long n_act = 0;
+  for (int i = 0; i < g->nuse; ++i) {
+    g->active[i] = g->hi[i] >= g->ix1[i];
+    if (g->active[i]) n_act += g->hi[i] - g->ix1[i] + 1;
+  }
+  for (int i = 0; i < g->nuse; ++i) {
+    if (!g->active[i]) continue;
+    sk_ctx *c = g->ctx[i];
+    int rc = sk_panel_begin(c, g->ix1[i], g->hi[i], nullptr, nullptr);
+    if (rc != SK_OK) return gfail(g, i, rc);
+    if (g->ctx.size() > 1) {
+      rc = sk_panel_set_range(c, g->r_min_pos, g->r_hi_g, n_act);
+      if (rc != SK_OK) return gfail(g, i, rc);
+    }
+  }
+  if (r_lo) *r_lo = g->r_min_pos;
+  if (r_hi) *r_hi = g->r_hi_g;
+  g->in_panel = true;
+  return SK_OK;
+}
+
+namespace {
+// read the staged scalars of all active devices back and combine them (src/quadrature.jl:258, :165)
+int group_subinterval_finish(sk_group *g, double *max_abs_diff) {
+  double mx = 0.0;
+  unsigned int fl = 0;
+  bool nan = false;
+  for (int i = 0; i < g->nuse; ++i) {
+    if (!g->active[i]) continue;
+    cudaSetDevice(g->ctx[i]->device);
+    double m1 = 0.0;
+    unsigned int f1 = 0;
+    int rc = transform_and_stage_finish(g->ctx[i], &m1, &f1);
+    if (rc != SK_OK) return gfail(g, i, rc);
+    fl |= f1;
+    if (m1 != m1) nan = true; else mx = std::max(mx, m1);
+  }
+  *max_abs_diff = nan ? std::nan("") : mx;
+  if (!(fl & SK_FLAG_NAN1) && (fl & SK_FLAG_NAN2)) return gfailmsg(g, SK_ERR_NAN, "NaN detected in panel integral...");
+  return SK_OK;
+}
+}  // namespace
+
+int sk_group_subinterval(sk_group *g, double a, double b, const sk_subinterval_opts *o, double *max_abs_diff) {
+  if (!g || !o || !max_abs_diff) return gfailmsg(g, SK_ERR_ARG, "null argument");
+  if (!g->in_panel) return gfailmsg(g, SK_ERR_STATE, "sk_group_panel_begin first");
+  for (int i = 0; i < g->nuse; ++i) {
+    if (!g->active[i]) continue;
+    int rc = subinterval_builtin_enqueue(g->ctx[i], a, b, o);
+    if (rc != SK_OK) return gfail(g, i, rc);
+  }
+  return group_subinterval_finish(g, max_abs_diff);
+}
+
+int sk_group_subinterval_host(sk_group *g, double a, double b, const double *no1, const double *buf1, const double *no2,
+                              const double *buf2, const sk_subinterval_opts *o, double *max_abs_diff) {
+  if (!g || !o || !max_abs_diff) return gfailmsg(g, SK_ERR_ARG, "null argument");
+  if (!g->in_panel) return gfailmsg(g, SK_ERR_STATE, "sk_group_panel_begin first");
+  for (int i = 0; i < g->nuse; ++i) {
+    if (!g->active[i]) continue;
+    int rc = subinterval_host_enqueue(g->ctx[i], a, b, no1, buf1, no2, buf2, o);
+    if (rc != SK_OK) return gfail(g, i, rc);
+  }
+  return group_subinterval_finish(g, max_abs_diff);
+}
+
+int sk_group_subinterval_accept(sk_group *g) {
+  if (!g) return SK_ERR_ARG;
+  for (int i = 0; i < g->nuse; ++i) {
+    if (!g->active[i]) continue;
+    cudaSetDevice(g->ctx[i]->device);
+    int rc = sk_subinterval_accept(g->ctx[i]);
+    if (rc != SK_OK) return gfail(g, i, rc);
+  }
+  return SK_OK;
+}
+
+int sk_group_panel_commit(sk_group *g) {
+  if (!g) return SK_ERR_ARG;
+  for (int i = 0; i < g->nuse; ++i) {
+    if (!g->active[i]) continue;
+    cudaSetDevice(g->ctx[i]->device);
+    int rc = sk_panel_commit(g->ctx[i]);
+    if (rc != SK_OK) return gfail(g, i, rc);
+  }
+  return SK_OK;
+}
+
+int sk_group_converge_scan(sk_group *g, const sk_scan_args *a, int64_t *new_hi, double *r_at_new_hi) {
+  if (!g || !a || !new_hi) return SK_ERR_ARG;
+  if (!g->in_panel) return gfailmsg(g, SK_ERR_STATE, "no open panel");
+  for (int i = 0; i < g->nuse; ++i) {
+    if (!g->active[i]) continue;
+    int rc = converge_scan_enqueue(g->ctx[i], a);
+    if (rc != SK_OK) return gfail(g, i, rc);
+  }
+  std::vector<double> r(g->nuse, 0.0);
+  double r_g = 0.0;
+  for (int i = 0; i < g->nuse; ++i) {
+    g->new_hi[i] = g->hi[i];
+    if (!g->active[i]) continue;
+    cudaSetDevice(g->ctx[i]->device);
+    int64_t nh = 0;
+    int rc = converge_scan_finish(g->ctx[i], &nh, &r[i]);
+    if (rc != SK_OK) return gfail(g, i, rc);
+    g->new_hi[i] = nh;
+    r_g = std::max(r_g, r[i]);
+  }
+  // the reference walks down from the largest distance while converged: everything up to the largest unconverged
+  // distance of ANY device stays active on every device
+  for (int i = 0; i < g->nuse; ++i) {
+    if (!g->active[i] || !(r_g > r[i])) continue;
+    cudaSetDevice(g->ctx[i]->device);
+    int64_t nh = 0;
+    int rc = sk_target_upper_index(g->ctx[i], r_g, &nh);
+    if (rc != SK_OK) return gfail(g, i, rc);
+    g->new_hi[i] = std::min<long long>(nh, g->hi[i]);
+  }
+  long long h = g->has_zero ? 1 : 0;
+  for (int i = 0; i < g->nuse; ++i) h += std::max<long long>(g->new_hi[i] - (g->ix1[i] - 1), 0);
+  *new_hi = h;
+  if (r_at_new_hi) *r_at_new_hi = r_g;
+  g->r_hi_g = r_g;
+  return SK_OK;
+}
+
+int sk_group_converge_apply(sk_group *g, const sk_scan_args *a, int64_t new_hi) {
+  if (!g || !a) return SK_ERR_ARG;
+  if (!g->in_panel) return gfailmsg(g, SK_ERR_STATE, "no open panel");
+  long long h = g->has_zero ? 1 : 0;
+  for (int i = 0; i < g->nuse; ++i) h += std::max<long long>(g->new_hi[i] - (g->ix1[i] - 1), 0);
+  if (new_hi != h) return gfailmsg(g, SK_ERR_ARG, "new_hi is not the value sk_group_converge_scan returned");
+  for (int i = 0; i < g->nuse; ++i) {
+    if (!g->active[i]) continue;
+    cudaSetDevice(g->ctx[i]->device);
+    int rc = sk_converge_apply(g->ctx[i], a, g->new_hi[i]);
+    if (rc != SK_OK) return gfail(g, i, rc);
+    g->hi[i] = g->new_hi[i];
+  }
+  g->in_panel = false;
+  return SK_OK;
+}
+
+int sk_group_results_get(sk_group *g, double *vals, double *errs) {
+  if (!g || !vals) return SK_ERR_ARG;
+  if (!g->have_targets) return gfailmsg(g, SK_ERR_STATE, "no targets set");
+  for (int i = 0; i < g->nuse; ++i) {
+    int rc = results_enqueue(g->ctx[i], vals + g->off[i], errs ? errs + g->off[i] : nullptr);
+    if (rc != SK_OK) return gfail(g, i, rc);
+  }
+  for (int i = 0; i < g->nuse; ++i) {
+    cudaSetDevice(g->ctx[i]->device);
+    int rc = results_finish(g->ctx[i]);
+    if (rc != SK_OK) return gfail(g, i, rc);
+  }
+  return SK_OK;
+}
+
+int sk_group_stats_get(sk_group *g, sk_stats *out) {
+  if (!g || !out) return SK_ERR_ARG;
+  std::memset(out, 0, sizeof(*out));
+  for (int i = 0; i < std::max(g->nuse, 1); ++i) {
+    const sk_stats &s = g->ctx[i]->stats;
+    // per-step counters are the same on every device that took part: report the largest; work adds up
+    out->n_subintervals = std::max(out->n_subintervals, s.n_subintervals);
+    out->n_accepted = std::max(out->n_accepted, s.n_accepted);
+    out->n_panels = std::max(out->n_panels, s.n_panels);
+    out->n_fast = std::max(out->n_fast, s.n_fast);
+    out->n_direct = std::max(out->n_direct, s.n_direct);
+    out->n_hankel = std::max(out->n_hankel, s.n_hankel);
+    out->n_speculated = std::max(out->n_speculated, s.n_speculated);
+    out->n_spec_rollbacks = std::max(out->n_spec_rollbacks, s.n_spec_rollbacks);
+    out->units += s.units;
+    out->kernel_launches += s.kernel_launches;
+    out->last_nf = s.last_nf; out->last_nf2 = s.last_nf2;
+    out->interp_ms = std::max(out->interp_ms, s.interp_ms);
+    out->source_ms = std::max(out->source_ms, s.source_ms);
+    out->sort_ms = std::max(out->sort_ms, s.sort_ms);
+    out->gather_ms = std::max(out->gather_ms, s.gather_ms);
+    out->timing_enabled = s.timing_enabled;
+    out->sort_two_level = i == 0 ? s.sort_two_level : std::min(out->sort_two_level, s.sort_two_level);
+  }
   return SK_OK;
 }
 

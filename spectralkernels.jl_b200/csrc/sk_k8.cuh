@@ -241,7 +241,7 @@ k_k8_scatter(const double *__restrict__ xs, long long n, SkK8State *__restrict__
 __global__ void __launch_bounds__(SK_K8_TPB)
 k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, const unsigned long long *__restrict__ skeys,
             const unsigned int *__restrict__ sidx, unsigned long long *__restrict__ desc, double *__restrict__ uxs,
-            unsigned int *__restrict__ inv, int dbg) {
+            unsigned int *__restrict__ inv) {
   if (!st->ndesc) return;
   __shared__ unsigned long long s_key[SK_K8_CAP];        // placed order, later final (sorted) order
   __shared__ int s_off[SK_K8_NSSB + 1];                  // sub-bin counts, then exclusive offsets (+ total)
@@ -330,7 +330,7 @@ k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, c
     if (t < cnt) {
       const int o = s_off[ssb[e]], g_end = s_off[ssb[e] + 1], me = o + rk[e];
       int less = 0, eqb = 0;
-      if (g_end - o > 1 && !(dbg & 2)) {                      // most groups hold one element
+      if (g_end - o > 1) {                                    // most groups hold one element
         for (int p = o; p < g_end; ++p) {
           const unsigned long long k2 = s_key[p];
           less += k2 < key[e];
@@ -377,8 +377,7 @@ k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, c
   if (wid == 0) {
     const unsigned long long zbase = st->nzero ? 1ull : 0ull;   // unique id 0 is the zero distance when there is one
     unsigned long long prev = zbase;
-    if (dbg & 1) prev = (unsigned long long)bin * 1000ull;
-    else if (bin > 0) {
+    if (bin > 0) {
       if (lane == 0) atomicExch(&desc[bin], (1ull << 62) | (unsigned long long)nuniq);
       prev = 0ull;
       long long p = (long long)bin - 1;                         // nearest predecessor not yet accounted for
@@ -417,7 +416,6 @@ k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, c
   }
   __syncthreads();
   const unsigned int uoff = s_uoff;
-  if (dbg & 4) return;
 #pragma unroll
   for (int i = 0; i < SK_K8_EPT; ++i) {
     const int p = threadIdx.x * SK_K8_EPT + i;

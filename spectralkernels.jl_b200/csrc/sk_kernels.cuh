@@ -709,12 +709,14 @@ __global__ void k_accept_add(sk_cplx *__restrict__ pan, const sk_cplx *__restric
 struct SkGlobalA {                 // after a sub-interval: MAX over ranks
   unsigned long long maxbits;      // bit pattern of max |I2-I1|
   unsigned long long nan1, nan2, nand;
+  unsigned long long err;          // a rank failed before it could evaluate the sub-interval: every rank raises
 };
 struct SkGlobalB {                 // after a convergence scan
   unsigned long long rbits;        // MAX: bit pattern of the stopping distance
   long long n_lb;                  // SUM: targets each rank keeps active if the walk stopped at its own distance
 };
-__global__ void k_pack_global_a(const SkReduceOut *__restrict__ red, SkGlobalA *__restrict__ g, int idle) {
+__global__ void k_pack_global_a(const SkReduceOut *__restrict__ red, SkGlobalA *__restrict__ g, int idle, int err) {
+  g->err = err ? 1ull : 0ull;
   g->maxbits = idle ? 0ull : red->maxbits;
   const unsigned int fl = idle ? 0u : red->flags;
   g->nan1 = (fl & SK_FLAG_NAN1) ? 1ull : 0ull;
