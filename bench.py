@@ -43,9 +43,9 @@ FLOPS_PER_UNIT_EXECUTED = 2 * 87.6 + 21.4 + 16.1
 # interpolation kernel with the fused (speculative) commit: read r (8) + read (ks,errs) (16) + write (ks,errs)
 # (16) + write the roll-back copy (16)
 BYTES_PER_UNIT_K4 = 56
-# K8 (unique / sort / inverse map, csrc/sk_k8.cuh) per input distance: stats 8 + sample 1 + scatter 8 + 12 + finish
-# 12 + 8 + 4; gather to the input order: inv 4 + (ks, errs) 16 + distance 8 + values and errors 16
-BYTES_PER_INPUT_K8 = 53
+# K8 (unique / sort / inverse map, csrc/sk_k8.cuh) per input distance: stats 8 + sample 1 + scatter 8 + 16 + finish
+# 16 + 8 + 4; gather to the input order: inv 4 + (ks, errs) 16 + distance 8 + values and errors 16
+BYTES_PER_INPUT_K8 = 61
 BYTES_PER_INPUT_GATHER = 44
 WORKLOAD = ("matern nu=1.5 rho=1 K(0)=1, r~U(0,1) seed=rank unsorted, tol=1e-8, quadspec (4096,16), :both "
             "(BASELINE config 2)")

@@ -114,6 +114,9 @@ typedef struct sk_stats {
   int64_t n_hankel;         /* sub-intervals that took the O(N) nonuniform Hankel transform (dim >= 2) */
   double sort_ms;           /* device time of the last sk_targets_set* (unique / sort / inverse map), timing enabled */
   double gather_ms;         /* device time in the gather to the input order since sk_run_begin  */
+  int64_t n_prefetch_issued;/* sub-intervals whose source side (nodes, strengths, spread, FFT) was computed ahead on the
+                               second stream, since the context was created ...                 */
+  int64_t n_prefetch_hits;  /* ... and how many of them the driver then actually asked for      */
 } sk_stats;
 
 /* ---- library --------------------------------------------------------------------------------- */
@@ -155,9 +158,14 @@ int sk_fp64_peak(sk_ctx *ctx, double *tflops, double *ms);
 int sk_comm_unique_id(void *out128);
 int sk_comm_init(sk_ctx *ctx, const void *id128, int32_t rank, int32_t nranks);
 int sk_comm_destroy(sk_ctx *ctx);
-/* all-reduce of up to 8 host doubles (op: 0 max, 1 min, 2 sum); synchronous; no-op without a communicator */
+/* all-reduce of up to 32 host doubles (op: 0 max, 1 min, 2 sum); synchronous; no-op without a communicator */
 int sk_comm_allreduce(sk_ctx *ctx, double *vals, int32_t n, int32_t op);
-/* a rank whose active set is empty joins the others' collective points: which = 0 sub-interval, 1 scan */
+/* a rank whose active set is empty joins the others' collective points: which = 0 sub-interval, 1 scan,
+ * 2 a sub-interval that carries the scan's scalars too -- the first sub-interval of a panel when opts.speculate is
+ * given and the NUFFT branch is taken (2 m k n_active_global > 2^18, kernel cos / sin): its collective then also
+ * reduces (stopping distance, active count), and when that sub-interval is accepted the scan is no collective point
+ * any more (an idle rank skips its which = 1 call for that panel).  A rank that fails locally still joins the
+ * collective with an error word set, so that every rank returns an error instead of blocking. */
 int sk_comm_idle(sk_ctx *ctx, int32_t which);
 int sk_comm_last(sk_ctx *ctx, double *max_abs_diff, double *r_stop, int64_t *n_active_lb);
 

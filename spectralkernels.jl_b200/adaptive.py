@@ -253,7 +253,8 @@ def _host_strengths(cfg: AdaptiveKernelConfig, eng, a: float, b: float, origin: 
 
 
 def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: float, k0: float, comm, active: bool,
-                               verbose: bool = False, trace: Optional[list] = None, speculate=None):
+                               verbose: bool = False, trace: Optional[list] = None, speculate=None,
+                               n_act_g: Optional[int] = None, spec_state: Optional[dict] = None):
     """Scalar control flow of src/quadrature.jl:169-275: LIFO bisection, accept test against
     config.tol*k0 (not the split tolerance), 9:1 tolerance split at the origin.  The per-target work of
     every pass happens inside sk_subinterval / sk_subinterval_accept."""
@@ -271,6 +272,9 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
     stack = [(a, b, cfg.tol)]                                                    # :173
     builtin = is_builtin(cfg.f)
     first = True
+    spec_state = spec_state if spec_state is not None else {}
+    spec_state["ab"] = False            # an idle rank: did the panel's first collective carry the scan's scalars?
+    spec_state["first_accepted"] = None
     while stack:
         _a, _b, _tol = stack.pop()                                               # :183
         # the first interval popped is the whole panel: let the device fuse accept / commit / scan into
@@ -311,13 +315,20 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
         if getattr(comm, "fused", False):
             # the library reduced over the ranks on its stream (sk_comm_init); idle ranks join the collective
             if not active:
-                eng.comm_idle(0)
+                # the active ranks' collective carries the scan's scalars too when they speculate (sk_comm_idle)
+                ab = spec is not None and kernel != SK_KERNEL_BESSEL and n_act_g is not None and \
+                    2 * cfg.quadsz * n_act_g > 2 ** 18 and n_act_g > 1
+                eng.comm_idle(2 if ab else 0)
+                if ab:
+                    spec_state["ab"] = True
                 mx = eng.comm_last()[0]
             mx_g = math.inf if math.isnan(mx) else mx
         else:
             # max over all ranks; NaN travels as +inf (both fail the accept test, quadrature.jl:260)
             mx_g = comm.max([math.inf if math.isnan(mx) else mx])[0]
         accepted = mx_g < cfg.tol * k0                                           # :260
+        if spec_state["first_accepted"] is None:
+            spec_state["first_accepted"] = bool(accepted)
         if verbose:
             word = "converged" if mx_g / k0 <= _tol else "did not converge"
             print(f"\tsubpanel w ∈ [{_a:.2e}, {_b:.2e}] {word} to tolerance {_tol:.2e} with max error {mx_g / k0:.2e}")
@@ -404,15 +415,12 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
     # one gather of (smallest positive distance, largest distance, active count) per rank
     fused = getattr(comm, "fused", False)
     rmin_local = info.r_min_pos if info.r_min_pos > 0 else math.inf
-    if fused:
-        mxs = comm.max([-rmin_local, r_hi_local])
-        r_lo_g, r_hi_g = -mxs[0], mxs[1]
-        n_act_g = int(comm.sum([float(max(n - ix1 + 1, 0))])[0])
-    else:
-        g0 = comm.gather([rmin_local, r_hi_local, float(max(n - ix1 + 1, 0))])
-        r_lo_g = min(v[0] for v in g0)
-        r_hi_g = max(v[1] for v in g0)
-        n_act_g = int(sum(v[2] for v in g0))
+    # (+-inf would turn into NaN in a one-hot sum: a rank without positive distances sends the largest double)
+    g0 = comm.gather([rmin_local if math.isfinite(rmin_local) else 1.7976931348623157e308, r_hi_local,
+                      float(max(n - ix1 + 1, 0))])
+    r_lo_g = min(v[0] for v in g0)
+    r_hi_g = max(v[1] for v in g0)
+    n_act_g = int(sum(v[2] for v in g0))
     m2 = 2 * cfg.quadsz
     ipanel = 0
     tau = cfg.tol * abs(k0) / 2                                                  # :191
@@ -441,8 +449,9 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
         else:
             crit_msg = None
         sargs = _scan_args(cfg, b, c, d, tau, crit)
+        spec_state = {}
         fourier_integrate_interval(cfg, eng, a, b, abs(k0), comm, active, verbose=verbose, trace=trace,
-                                   speculate=sargs)                              # :157-159
+                                   speculate=sargs, n_act_g=n_act_g, spec_state=spec_state)   # :157-159
         if active:
             eng.panel_commit()                                                   # :163-164
         if verbose and crit_msg:
@@ -455,7 +464,8 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
         # one gather per panel: every rank's stopping distance and the number of targets it keeps active if
         # the walk stopped at ITS OWN stopping distance (a lower bound of what it keeps for the global one)
         if fused:
-            if not active:
+            # (no collective when the scan's scalars travelled with the panel's accepted first sub-interval)
+            if not active and not (spec_state.get("ab") and spec_state.get("first_accepted")):
                 eng.comm_idle(1)
             _, r_g, n_lb_g = eng.comm_last()
             g1 = [[r_g, float(n_lb_g)]]

@@ -8,6 +8,7 @@
 #include <cufft.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -18,6 +19,7 @@
 #include <map>
 #include <numeric>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/spectralkernels_b200.h"
@@ -26,7 +28,17 @@
 #include "sk_hankel.cuh"
 #include "sk_rules.cuh"
 
+#define SK_GATHER_SLICES 8
+
 namespace {
+
+// NVTX ranges named after the reference's TimerOutputs stages (src/quadrature.jl:99,108,113,140,145,
+// src/adaptive.jl:156,162,182), so that a timeline of the GPU path reads like `SpectralKernels.TIMER`.
+// Header-only NVTX3: no cost unless a profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 template <class T>
 struct DevBuf {
@@ -86,10 +98,11 @@ NcclApi *nccl_api() {
 struct HostScalars {          // pinned mirror of the device scalars
   SkReduceOut red;
   SkTargetSummary sum;
+  SkK8State k8;
   SkKeyBits kb;
   SkGlobalA ga;
   SkGlobalB gb;
-  double hv[8];               // generic host-value collectives
+  double hv[32];              // generic host-value collectives
   double r[2];
   SkHankelGroup grp[SK_HK_NGRP];   // transform groups of the current Hankel sub-interval
 };
@@ -102,7 +115,7 @@ struct sk_ctx {
   std::string errmsg;
   double eps = 1e-15;
   SkEsPlan plan;
-  std::map<std::pair<long long, int>, cufftHandle> fft_plans;
+  std::map<std::tuple<long long, int, int>, cufftHandle> fft_plans;      // (size, batch, 0 compute stream / 1 prefetch stream)
 
   // rules
   int m = 0, k = 0;
@@ -121,6 +134,25 @@ struct sk_ctx {
   // sources of the current sub-interval
   DevBuf<double> no1, buf1, no2, buf2, pos_hi1, pos_lo1, pos_hi2, pos_lo2, imz;
   DevBuf<sk_cplx> cs1, cs2, fft, fftB, dsum, dsumB;
+  // Source-side prefetch: nodes, strengths, spread and FFT of a sub-interval the driver is about to ask for (the first
+  // panel while the distances are still being sorted; the second panel while the first is interpolated) are computed
+  // ahead on a second stream into a second buffer set.  A request is served from it only if its panel spec and its
+  // transform geometry equal the prefetched ones bit for bit -- otherwise the prefetch is simply dropped.
+  struct SrcSet {
+    DevBuf<double> no1, buf1, no2, buf2, pos_hi1, pos_lo1, pos_hi2, pos_lo2;
+    DevBuf<sk_cplx> cs1, cs2, fft;
+  } pf;
+  bool pf_valid = false, need_gen = false, prefetch_on = true;
+  SkPanelSpec pf_S, pend_S;
+  SkGeom pf_G;
+  cudaStream_t stream_main = nullptr, stream2 = nullptr;
+  cudaEvent_t pf_ev = nullptr;
+  cudaEvent_t k8_ev = nullptr;
+  cudaEvent_t ev_slice[SK_GATHER_SLICES] = {nullptr};
+  bool results_sliced = false;
+  int last_logw = 0;
+  bool in_group = false;
+  long long n_pf_hits = 0, n_pf_issued = 0;
   DevBuf<double> bufb1, bufb2;               // second integrand of the log-weighted origin sub-interval
   bool have_sources = false;
 
@@ -147,8 +179,7 @@ struct sk_ctx {
   // piecewise-linear distribution estimate, and the fine-bin slots
   DevBuf<unsigned char> k8_ctl;
   DevBuf<uint2> k8_ctab;
-  DevBuf<unsigned long long> k8_skeys;
-  DevBuf<unsigned int> k8_sidx;
+  DevBuf<ulonglong2> k8_slots;
   bool have_targets = false;
 
   // panel state (0-based half-open [lo, hi))
@@ -182,6 +213,7 @@ struct sk_ctx {
   bool pend_timed = false, pend_spec = false;  // between transform_and_stage_enqueue and _finish
   bool scan_from_spec = false;                 // between converge_scan_enqueue and _finish
   int pend_rc = 0;                             // local result of transform_and_stage_enqueue in a sharded run
+  bool pend_ab = false;                        // the sub-interval's collective carried the scan's scalars as well
   long long panel_subs = 0;                  // sub-intervals evaluated in the open panel
   long long n_act_global = 0;                // active targets over all ranks (0: this rank only)
   sk_scan_args spec_args;
@@ -265,6 +297,26 @@ int comm_reduce_a(sk_ctx *c, int idle, int err = 0) {
   CK(cudaMemcpyAsync(&c->h_scal->ga, c->d_ga, sizeof(SkGlobalA), cudaMemcpyDeviceToHost, c->stream));
   return SK_OK;
 }
+// collectives A and B of a speculated sub-interval in ONE launch: the interpolation kernel produced max |I2-I1| and
+// the scan's (stopping distance, active count) together, so they travel together; the scan that follows then needs
+// no collective at all.  Idle ranks contribute neutral values.
+int comm_reduce_ab(sk_ctx *c, int idle, int err) {
+  if (!c->comm) return SK_OK;
+  NcclApi *N = nccl_api();
+  k_pack_global_a<<<1, 1, 0, c->stream>>>(c->d_red, c->d_ga, (idle || err) ? 1 : 0, err);
+  LAUNCH_CHECK();
+  if (idle || err) k_pack_global_b<<<1, 1, 0, c->stream>>>(c->d_gb, 0ull, 0);
+  else k_pack_global_b_from_red<<<1, 1, 0, c->stream>>>(c->d_red, c->lo, c->d_gb);
+  LAUNCH_CHECK();
+  NCK(N->GroupStart());
+  NCK(N->AllReduce(c->d_ga, c->d_ga, 5, ncclUint64, ncclMax, c->comm, c->stream));
+  NCK(N->AllReduce(&c->d_gb->rbits, &c->d_gb->rbits, 1, ncclUint64, ncclMax, c->comm, c->stream));
+  NCK(N->AllReduce(&c->d_gb->n_lb, &c->d_gb->n_lb, 1, ncclInt64, ncclSum, c->comm, c->stream));
+  NCK(N->GroupEnd());
+  CK(cudaMemcpyAsync(&c->h_scal->ga, c->d_ga, sizeof(SkGlobalA), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&c->h_scal->gb, c->d_gb, sizeof(SkGlobalB), cudaMemcpyDeviceToHost, c->stream));
+  return SK_OK;
+}
 // collective B (after a scan): MAX of the stopping distance, SUM of the per-rank lower bounds of the
 // number of targets that stay active.  from_red: take the values from d_red (lo = first index of the panel).
 int comm_reduce_b(sk_ctx *c, bool from_red, unsigned long long rbits, long long n_lb) {
@@ -301,7 +353,7 @@ int width_from_eps(double eps) {
 }
 
 int get_fft_plan(sk_ctx *c, long long nf2, int batch, cufftHandle *out) {
-  auto key = std::make_pair(nf2, batch);
+  auto key = std::make_tuple(nf2, batch, c->stream == c->stream_main ? 0 : 1);
   auto it = c->fft_plans.find(key);
   if (it != c->fft_plans.end()) {
     *out = it->second;
@@ -330,18 +382,17 @@ int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long lon
     return 0;
   }
   // cells the active targets span -> average targets per cell -> how many cells a block may hold
-  static const int tpt_env = getenv("SK_TPT") ? atoi(getenv("SK_TPT")) : 0;     // tuning knob (4, 8, 16)
-  const int tpt = (tpt_env == 4 || tpt_env == 8 || tpt_env == 16) ? tpt_env : (n >= 8000000 ? 16 : (n >= 2000000 ? 8 : 4));
+  const int tpt = n >= 8000000 ? 16 : (n >= 2000000 ? 8 : 4);
   const int tpb = 256 * tpt;
   const double span = (c->r_hi - c->r_lo) * G.kap_hi + 1.0;
   const double per_block = span * (double)tpb / (double)n;
   const int cmax = per_block <= 24.0 ? 32 : 96;
-  const size_t smem = sizeof(double) * (size_t)(2 * (W / 2) * (SK_NC / 2) + (cmax + W) * 4 + cmax * 4 + cmax * SK_NC * 4);
+  const size_t smem = sizeof(double) * (size_t)(2 * (W / 2) * (SK_NC / 2) + (cmax + W) * 4 + cmax * 4 + cmax * SK_CELL_STRIDE);
   // function attributes are per device: remember per context (one context = one device)
   bool &attr_set = c->smem_attr_set[W];
   if (!attr_set) {
-    cudaFuncSetAttribute(k_interp_cells<W, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_interp_cells<W, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_interp_cells<W, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_interp_cells<W, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_interp_cells<W, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_interp_cells<W, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;
@@ -352,7 +403,7 @@ int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long lon
   if (c->interp_mode == 2) {           // A/B variant: 4 resident blocks per SM (<= 64 registers)
     if (spec.on) SK_LAUNCH_CELLS(true, 4); else SK_LAUNCH_CELLS(false, 4);
   } else {
-    if (spec.on) SK_LAUNCH_CELLS(true, 3); else SK_LAUNCH_CELLS(false, 3);
+    if (spec.on) SK_LAUNCH_CELLS(true, 2); else SK_LAUNCH_CELLS(false, 2);
   }
 #undef SK_LAUNCH_CELLS
   return 0;
@@ -410,6 +461,7 @@ int run_source_side(sk_ctx *c, const SkGeom &G, int nrule, long long M1, const d
 // per target (raw[2j + rule].x) instead of staging.
 int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, const double *sbuf2, double cmul, double xdiv,
                  long long n_act, long long M1, long long M2, sk_cplx *raw) {
+  NvtxRange nvtx("NUFHT call");
   SkHankelPlan H;
   SkHankelGroup *hg = c->h_scal->grp;
   const long long total = sk_hk_make_plan(c->plan, nu, a, b, c->r_lo, c->r_hi, &H, hg);
@@ -511,6 +563,60 @@ int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, con
   return SK_OK;
 }
 
+// ---- source-side prefetch (see sk_ctx::pf) -------------------------------------------------------------------
+void swap_src_sets(sk_ctx *c) {
+  std::swap(c->no1, c->pf.no1); std::swap(c->buf1, c->pf.buf1); std::swap(c->no2, c->pf.no2); std::swap(c->buf2, c->pf.buf2);
+  std::swap(c->pos_hi1, c->pf.pos_hi1); std::swap(c->pos_lo1, c->pf.pos_lo1);
+  std::swap(c->pos_hi2, c->pf.pos_hi2); std::swap(c->pos_lo2, c->pf.pos_lo2);
+  std::swap(c->cs1, c->pf.cs1); std::swap(c->cs2, c->pf.cs2); std::swap(c->fft, c->pf.fft);
+}
+
+// updatequadbufs! (src/quadrature.jl:49-95) for a built-in density: the panel spec of the sub-interval [a, b]
+void make_panel_spec(const sk_ctx *c, double a, double b, int logw, SkPanelSpec *out) {
+  SkPanelSpec &S = *out;
+  std::memset(&S, 0, sizeof(S));
+  const bool origin = (a == 0.0 && c->p != 0.0);                    // src/quadrature.jl:185
+  S.m = c->m; S.k = c->k;
+  S.origin_jacobi = origin ? 1 : 0;
+  S.weight_in_f = origin ? 0 : 1;                                   // :230-238 vs :240-247
+  S.logw = logw ? 1 : 0;
+  S.family = c->family; S.deriv = c->deriv; S.nparam = c->nparam;
+  S.p = c->p;
+  for (int i = 0; i < c->nparam; ++i) S.params[i] = c->params[i];
+  sk_fill_subpanels(a, b, c->k, S.bmad2, S.bpad2);
+  S.jac_scale = std::pow(S.bmad2[0], c->p + 1);
+}
+
+int launch_gen_sources(sk_ctx *c, const SkPanelSpec &S) {
+  NvtxRange nvtx("update quadrature buffers");
+  const long long M1 = (long long)c->m * c->k;
+  CK(c->no1.ensure(M1)); CK(c->buf1.ensure(M1)); CK(c->no2.ensure(2 * M1)); CK(c->buf2.ensure(2 * M1));
+  k_gen_sources<<<nblk(3 * M1, 256), 256, 0, c->stream>>>(S, c->leg_no1.p, c->leg_wt1.p, c->leg_no2.p, c->leg_wt2.p,
+                                                          c->jac_no1.p, c->jac_wt1.p, c->jac_no2.p, c->jac_wt2.p,
+                                                          c->no1.p, c->buf1.p, c->no2.p, c->buf2.p);
+  LAUNCH_CHECK();
+  return SK_OK;
+}
+
+// nodes, strengths, spread and FFT of (S, G) on the prefetch stream, into the second buffer set
+int prefetch_sources(sk_ctx *c, const SkPanelSpec &S, const SkGeom &G) {
+  c->pf_valid = false;
+  swap_src_sets(c);
+  c->stream = c->stream2;
+  const long long M1 = (long long)c->m * c->k;
+  int rc = launch_gen_sources(c, S);
+  if (rc == SK_OK) rc = run_source_side(c, G, 2, M1, c->buf1.p, nullptr, 2 * M1, c->buf2.p, c->fft);
+  if (rc == SK_OK && cudaEventRecord(c->pf_ev, c->stream2) != cudaSuccess) rc = SK_ERR_CUDA;
+  c->stream = c->stream_main;
+  swap_src_sets(c);
+  if (rc != SK_OK) return rc;
+  c->pf_S = S;
+  c->pf_G = G;
+  c->pf_valid = true;
+  c->n_pf_issued++;
+  return SK_OK;
+}
+
 // transform + stage for the sub-interval whose sources are in no1/buf1/no2/buf2, in two halves: everything that is
 // enqueued on the context's stream, and the read-back of the reduced scalars after the stream has drained.  One
 // context runs the halves back to back (transform_and_stage); a device group (sk_group_*) enqueues on every device
@@ -538,6 +644,27 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
     spec.trunc_num = o->speculate->trunc_num;
     spec.xpow = o->speculate->xpow;
     spec.tau = o->speculate->tau;
+    // exact threshold distance of the truncation half of the predicate (SkSpec::xstar), dim = 1 (x^1: no pow())
+    spec.use_xstar = 0;
+    spec.xstar = 0.0;
+    if (spec.criteria != 0 && spec.xpow == 1.0 && spec.trunc_num > 0.0 && std::isfinite(spec.trunc_num) &&
+        spec.trunc_a == spec.trunc_a && spec.tau == spec.tau) {
+      auto pred = [&](double x) { return sk_trunc_err(spec.trunc_a, spec.trunc_num, 1.0, x, 0) < spec.tau; };
+      const double dmax = 1.7976931348623157e308, dmin = 4.9406564584124654e-324;
+      if (pred(dmin)) { spec.use_xstar = 1; spec.xstar = 0.0; }                 // every positive distance passes
+      else if (!pred(dmax)) { spec.use_xstar = 1; spec.xstar = INFINITY; }      // none does
+      else {
+        unsigned long long lo_b = 1ull, hi_b = 0x7fefffffffffffffull;          // pred(lo) false, pred(hi) true
+        while (hi_b - lo_b > 1ull) {
+          const unsigned long long mid = lo_b + (hi_b - lo_b) / 2;
+          double xm;
+          std::memcpy(&xm, &mid, sizeof(double));
+          if (pred(xm)) hi_b = mid; else lo_b = mid;
+        }
+        std::memcpy(&spec.xstar, &hi_b, sizeof(double));
+        spec.use_xstar = 1;
+      }
+    }
     spec.res = c->res.p + c->lo;
     spec.backup = c->stage.p + c->lo;
   }
@@ -547,6 +674,31 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
   c->h_scal->red = init;
   CK(cudaMemcpyAsync(c->d_red, &c->h_scal->red, sizeof(init), cudaMemcpyHostToDevice, c->stream));
   if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+  SkGeom G;
+  std::memset(&G, 0, sizeof(G));
+  if (fast && sk_make_geom(c->plan, a, b, c->r_lo, c->r_hi, &G) != 0)
+    return fail(c, SK_ERR_ARG, "type-3 grid too large for [a,b]=[%g,%g], r in [%g,%g]", a, b, c->r_lo, c->r_hi);
+  // built-in density: the sources either wait in the prefetch set (same panel spec, same geometry, bit for bit) or
+  // are generated now
+  const bool builtin_req = c->need_gen;
+  bool served = false;
+  if (c->need_gen) {
+    c->need_gen = false;
+    if (fast && c->pf_valid && std::memcmp(&c->pf_S, &c->pend_S, sizeof(SkPanelSpec)) == 0 &&
+        std::memcmp(&c->pf_G, &G, sizeof(SkGeom)) == 0) {
+      CK(cudaStreamWaitEvent(c->stream, c->pf_ev, 0));
+      swap_src_sets(c);
+      served = true;
+      c->n_pf_hits++;
+      c->stats.last_nf = G.nf;
+      c->stats.last_nf2 = G.nf2;
+    } else {
+      int rc = launch_gen_sources(c, c->pend_S);
+      if (rc != SK_OK) return rc;
+    }
+    c->have_sources = true;
+  }
+  c->pf_valid = false;                       // a prefetch is good for the very next request only
   // dim >= 2: the reference calls nufht whenever its NUFFT cutoff holds (src/quadrature.jl:139-143); here the
   // O(N) scheme is taken when it is cheaper than the direct Bessel summation (more than ~4096 active targets)
   int hk_rc = SK_ERR_UNSUPPORTED;
@@ -558,11 +710,11 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
     hk_timed = hk_rc == SK_OK;
   }
   if (fast) {
-    SkGeom G;
-    if (sk_make_geom(c->plan, a, b, c->r_lo, c->r_hi, &G) != 0)
-      return fail(c, SK_ERR_ARG, "type-3 grid too large for [a,b]=[%g,%g], r in [%g,%g]", a, b, c->r_lo, c->r_hi);
-    int rc = run_source_side(c, G, 2, M1, c->buf1.p, nullptr, M2, c->buf2.p, c->fft);
-    if (rc != SK_OK) return rc;
+    NvtxRange nvtx("FINUFFT call");
+    if (!served) {
+      int rc = run_source_side(c, G, 2, M1, c->buf1.p, nullptr, M2, c->buf2.p, c->fft);
+      if (rc != SK_OK) return rc;
+    }
     if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
 #define CALL(WW) launch_interp_session<WW>(c, G, c->uxs.p + c->lo, n_act, o->cmul, ksin, spec)
     DISPATCH_W(c->plan.w, CALL)
@@ -570,9 +722,22 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
     LAUNCH_CHECK();
     if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
     c->stats.n_fast++;
+    // the first panel of a run rarely converges anything: the next panel is then (b, b + quadm / (2 r_hi)) over the same
+    // targets (src/adaptive.jl:152).  Its source side starts now, next to the interpolation of this one.
+    if (c->prefetch_on && builtin_req && spec_on && c->stats.n_panels == 0 && c->r_hi > 0.0) {
+      const double a2 = b, b2 = b + (double)((long long)c->m * c->k) / (2 * c->r_hi);
+      SkGeom G2;
+      if (std::isfinite(b2) && b2 > a2 && sk_make_geom(c->plan, a2, b2, c->r_lo, c->r_hi, &G2) == 0) {
+        SkPanelSpec S2;
+        make_panel_spec(c, a2, b2, o->logw, &S2);
+        int rc = prefetch_sources(c, S2, G2);
+        if (rc != SK_OK) return rc;
+      }
+    }
   } else if (bessel && hk_rc == SK_OK) {
     // staged by hankel_stage above
   } else {
+    NvtxRange nvtx(bessel ? "direct Bessel summation" : "direct Fourier summation");
     if (n_act > 2000000000LL) return fail(c, SK_ERR_ARG, "too many targets for the direct branch");
     CK(c->dsum.ensure((size_t)n_act * 2));
     dim3 grid((unsigned int)n_act, 2);
@@ -594,13 +759,21 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
 }
 
 int transform_and_stage_enqueue(sk_ctx *c, double a, double b, const sk_subinterval_opts *o) {
+  NvtxRange nvtx("panel integral");
   c->pend_timed = c->pend_spec = false;
+  {
+    // does this sub-interval speculate (first of its panel, NUFFT branch, scan arguments given)?  Decided from the
+    // arguments and the GLOBAL active count only, so that every rank -- also an idle one -- issues the same collectives
+    const long long M2 = 2LL * c->m * c->k, n_cut = c->n_act_global > 0 ? c->n_act_global : (c->hi - c->lo);
+    c->pend_ab = c->comm != nullptr && o->kernel != SK_KERNEL_BESSEL && (M2 * n_cut > (1LL << 18)) && n_cut > 1 &&
+                 o->speculate != nullptr && c->panel_subs == 0 && o->speculate->criteria >= 0 && o->speculate->criteria <= 2;
+  }
   const int rc = transform_and_stage_enqueue_local(c, a, b, o);
   c->pend_rc = rc;
   if (!c->comm) return rc;
   // sharded run: a rank that failed locally still joins the collective (its peers are waiting in it)
   const std::string msg = c->errmsg;
-  const int rcc = comm_reduce_a(c, 0, rc != SK_OK);
+  const int rcc = c->pend_ab ? comm_reduce_ab(c, 0, rc != SK_OK) : comm_reduce_a(c, 0, rc != SK_OK);
   if (rc != SK_OK) c->errmsg = msg;
   return rcc != SK_OK ? rcc : SK_OK;                     // a local failure is reported by _finish, after the collective
 }
@@ -625,6 +798,7 @@ int transform_and_stage_finish(sk_ctx *c, double *max_abs_diff, unsigned int *fl
   double mx;
   std::memcpy(&mx, &c->h_scal->red.maxbits, sizeof(double));
   comm_take_a(c, &fl, &mx);                 // sharded run: the maximum and the NaN flags over all ranks
+  if (c->comm && c->pend_ab) comm_take_b(c);
   if (fl & SK_FLAG_NAND) mx = std::nan("");
   *max_abs_diff = mx;
   c->g_max_abs = mx;
@@ -762,18 +936,18 @@ int targets_sort_general(sk_ctx *c, long long n_in) {
 // synchronisation, at the end (the summary); an already strictly increasing input is detected on the device and
 // costs one read pass.  Two halves like transform_and_stage (a device group sorts all chunks concurrently).
 int targets_enqueue(sk_ctx *c, long long n_in) {
+  NvtxRange nvtx("unique / sort (K8)");
   c->have_targets = false;
   if (n_in > 0x7ffffff0LL) return fail(c, SK_ERR_ARG, "n_in too large");
   const size_t nfine_max = (size_t)(n_in >> SK_K8_TARGET_LOG) + 2;
   // control block: state | coarse histogram | look-back descriptors | fill counters -- cleared by one memset
   const size_t off_hist = 256, off_desc = off_hist + sizeof(unsigned int) * SK_K8_NC;
   const size_t off_fill = off_desc + sizeof(unsigned long long) * nfine_max;
-  const size_t ctl_bytes = off_fill + sizeof(unsigned int) * nfine_max;
+  const size_t ctl_bytes = off_fill + sizeof(unsigned int) * nfine_max * SK_K8_FILL_STRIDE;
   static_assert(sizeof(SkK8State) <= 256, "control block layout");
   CK(c->k8_ctl.ensure(ctl_bytes));
   CK(c->k8_ctab.ensure(SK_K8_NC));
-  CK(c->k8_skeys.ensure(nfine_max * SK_K8_CAP));
-  CK(c->k8_sidx.ensure(nfine_max * SK_K8_CAP));
+  CK(c->k8_slots.ensure(nfine_max * SK_K8_CAP));
   CK(c->uxs.ensure(n_in));               // sized for the worst case (n_unique <= n_in): no host round trip
   CK(c->inv.ensure(n_in));
   CK(c->res.ensure(n_in));
@@ -788,19 +962,44 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   const unsigned int gs = std::min<unsigned int>(nblk(n_in, 256), 148u * 8u);    // grid-stride passes: 2048 threads per SM
   k_k8_stats<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st);
   LAUNCH_CHECK();
+  // the first panel is (0, quadm / (2 r_max)) (src/adaptive.jl:152) and r_max is known after this first pass: fetch the
+  // key range now, and start the panel's source side on the prefetch stream while the sort runs
+  const bool early = c->prefetch_on && !c->in_group && c->have_rule && c->family != SK_SDF_HOST && n_in >= 65536 && c->plan.w > 0;
+  if (early) {
+    CK(cudaMemcpyAsync(&c->h_scal->k8, st, sizeof(SkK8State), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->k8_ev, c->stream));
+  }
   k_k8_sample<<<std::min<unsigned int>(nblk(n_in, 256), 148u * 2u), 256, 0, c->stream>>>(c->in.p, n_in, st, chist);
   LAUNCH_CHECK();
   k_k8_plan<<<1, 1024, 0, c->stream>>>(st, chist, n_in, c->k8_ctab.p);
   LAUNCH_CHECK();
-  k_k8_scatter<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->k8_ctab.p, fill, c->k8_skeys.p, c->k8_sidx.p, c->inv.p);
+  k_k8_scatter<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->k8_ctab.p, fill, c->k8_slots.p, c->inv.p);
   LAUNCH_CHECK();
-  k_k8_finish<<<(unsigned int)nfine_max, SK_K8_TPB, 0, c->stream>>>(st, fill, c->k8_skeys.p, c->k8_sidx.p, desc, c->uxs.p, c->inv.p);
+  k_k8_finish<<<(unsigned int)nfine_max, SK_K8_TPB, 0, c->stream>>>(st, fill, c->k8_slots.p, desc, c->uxs.p, c->inv.p);
   LAUNCH_CHECK();
   k_k8_identity<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->uxs.p, c->inv.p);
   LAUNCH_CHECK();
   k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, n_in, c->d_sum);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
+  if (early) {
+    CK(cudaEventSynchronize(c->k8_ev));
+    const SkK8State &k8 = c->h_scal->k8;
+    if (!k8.bad && k8.kmin_inv != 0ull && k8.kmax != 0ull) {
+      double r_lo, r_hi;
+      const unsigned long long kmin = ~k8.kmin_inv;
+      std::memcpy(&r_lo, &kmin, sizeof(double));
+      std::memcpy(&r_hi, &k8.kmax, sizeof(double));
+      const double b1 = 0.0 + (double)((long long)c->m * c->k) / (2 * r_hi);
+      SkGeom G1;
+      if (std::isfinite(b1) && b1 > 0.0 && sk_make_geom(c->plan, 0.0, b1, r_lo, r_hi, &G1) == 0) {
+        SkPanelSpec S1;
+        make_panel_spec(c, 0.0, b1, c->last_logw, &S1);
+        int rc = prefetch_sources(c, S1, G1);
+        if (rc != SK_OK) return rc;
+      }
+    }
+  }
   return SK_OK;
 }
 
@@ -907,7 +1106,13 @@ int sk_ctx_create(int device, sk_ctx **out) {
   }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
   for (int i = 0; i < 2; ++i) cudaEventCreate(&c->ev_user[i]);
-  if (const char *g = getenv("SK_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment
+  c->stream_main = c->stream;
+  if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->pf_ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->k8_ev, cudaEventDisableTiming) != cudaSuccess) {
+    delete c;
+    return SK_ERR_CUDA;
+  }
   if (sk_plan_make_es(width_from_eps(c->eps), &c->plan) != 0) {
     delete c;
     return SK_ERR_ARG;
@@ -947,7 +1152,14 @@ int sk_ctx_destroy(sk_ctx *c) {
   if (c->d_kb) cudaFree(c->d_kb);
   c->keys.release(); c->keys_alt.release(); c->idx.release(); c->idx_alt.release();
   c->head.release(); c->uid.release(); c->inv.release(); c->cub_tmp.release();
-  c->k8_ctl.release(); c->k8_ctab.release(); c->k8_skeys.release(); c->k8_sidx.release();
+  c->k8_ctl.release(); c->k8_ctab.release(); c->k8_slots.release();
+  if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+  if (c->pf_ev) cudaEventDestroy(c->pf_ev);
+  if (c->k8_ev) cudaEventDestroy(c->k8_ev);
+  for (int i = 0; i < SK_GATHER_SLICES; ++i) if (c->ev_slice[i]) cudaEventDestroy(c->ev_slice[i]);
+  c->pf.no1.release(); c->pf.buf1.release(); c->pf.no2.release(); c->pf.buf2.release();
+  c->pf.pos_hi1.release(); c->pf.pos_lo1.release(); c->pf.pos_hi2.release(); c->pf.pos_lo2.release();
+  c->pf.cs1.release(); c->pf.cs2.release(); c->pf.fft.release();
   if (c->d_red) cudaFree(c->d_red);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -967,6 +1179,7 @@ int sk_ctx_set_timing(sk_ctx *c, int enabled) {
 int sk_ctx_set_nufft_eps(sk_ctx *c, double eps) {
   if (!c || !(eps > 0) || !(eps < 1)) return fail(c, SK_ERR_ARG, "eps must be in (0,1)");
   c->eps = eps;
+  c->pf_valid = false;
   if (sk_plan_make_es(width_from_eps(eps), &c->plan) != 0) return fail(c, SK_ERR_ARG, "cannot plan for eps=%g", eps);
   return SK_OK;
 }
@@ -1047,7 +1260,7 @@ int sk_comm_init(sk_ctx *c, const void *id128, int32_t rank, int32_t nranks) {
   c->comm_size = nranks;
   if (!c->d_ga) CK(cudaMalloc((void **)&c->d_ga, sizeof(SkGlobalA)));
   if (!c->d_gb) CK(cudaMalloc((void **)&c->d_gb, sizeof(SkGlobalB)));
-  if (!c->d_hv) CK(cudaMalloc((void **)&c->d_hv, 8 * sizeof(double)));
+  if (!c->d_hv) CK(cudaMalloc((void **)&c->d_hv, 32 * sizeof(double)));
   return SK_OK;
 }
 
@@ -1065,7 +1278,7 @@ int sk_comm_destroy(sk_ctx *c) {
 // generic collective on up to 8 host doubles (op: 0 max, 1 min, 2 sum); synchronous.  Used once per
 // kernel_values call (global distance range / counts) and for the rare exact count.
 int sk_comm_allreduce(sk_ctx *c, double *vals, int32_t n, int32_t op) {
-  if (!c || !vals || n < 1 || n > 8 || op < 0 || op > 2) return fail(c, SK_ERR_ARG, "bad allreduce arguments");
+  if (!c || !vals || n < 1 || n > 32 || op < 0 || op > 2) return fail(c, SK_ERR_ARG, "bad allreduce arguments");
   if (!c->comm) return SK_OK;
   NcclApi *N = nccl_api();
   for (int i = 0; i < n; ++i) c->h_scal->hv[i] = vals[i];
@@ -1083,13 +1296,14 @@ int sk_comm_idle(sk_ctx *c, int32_t which) {
   if (!c) return SK_ERR_ARG;
   if (!c->comm) return SK_OK;
   CK(cudaSetDevice(c->device));
-  if (which == 0) {
-    int rc = comm_reduce_a(c, 1);
+  if (which == 0 || which == 2) {
+    int rc = which == 2 ? comm_reduce_ab(c, 1, 0) : comm_reduce_a(c, 1);
     if (rc != SK_OK) return rc;
     CK(cudaStreamSynchronize(c->stream));
     unsigned int fl = 0;
     double mx = 0.0;
     comm_take_a(c, &fl, &mx);
+    if (which == 2) comm_take_b(c);
     if (fl & SK_FLAG_NAND) mx = std::nan("");
     c->g_max_abs = mx;
     // the idle rank raises what the active ranks raise, so that all ranks leave the adaptive loop together
@@ -1159,6 +1373,7 @@ int sk_nufft1d3(sk_ctx *c, int64_t M, const double *w, const double *s, int64_t 
   };
   if (rc == SK_OK) rc = body();
   c->plan = saved;
+  c->pf_valid = false;
   c->have_sources = false;
   c->have_targets = false;  // the target buffer was reused
   return rc;
@@ -1209,6 +1424,7 @@ int sk_rule_set(sk_ctx *c, int32_t m, int32_t k, double p, const double *leg_no1
   CK(c->no1.ensure(M1)); CK(c->buf1.ensure(M1)); CK(c->no2.ensure(2 * M1)); CK(c->buf2.ensure(2 * M1));
   CK(cudaStreamSynchronize(c->stream));
   c->m = m; c->k = k; c->p = p;
+  c->pf_valid = false;
   c->have_rule = true;
   c->rule_generated = !given_leg && !(c->have_jac && given_jac);
   return SK_OK;
@@ -1427,24 +1643,10 @@ static int subinterval_builtin_enqueue(sk_ctx *c, double a, double b, const sk_s
   const bool origin = (a == 0.0 && c->p != 0.0);                    // src/quadrature.jl:185
   if (origin && o->logw)
     return fail(c, SK_ERR_UNSUPPORTED, "log-weighted origin sub-interval needs df: use sk_subinterval_logw_host (src/quadrature.jl:186-228)");
-  SkPanelSpec S;
-  std::memset(&S, 0, sizeof(S));
-  S.m = c->m; S.k = c->k;
-  S.origin_jacobi = origin ? 1 : 0;
-  S.weight_in_f = origin ? 0 : 1;                                   // :230-238 vs :240-247
-  S.logw = o->logw ? 1 : 0;
-  S.family = c->family; S.deriv = c->deriv; S.nparam = c->nparam;
-  S.p = c->p;
-  for (int i = 0; i < c->nparam; ++i) S.params[i] = c->params[i];
-  sk_fill_subpanels(a, b, c->k, S.bmad2, S.bpad2);
-  S.jac_scale = std::pow(S.bmad2[0], c->p + 1);
-  const long long M1 = (long long)c->m * c->k;
+  make_panel_spec(c, a, b, o->logw, &c->pend_S);
+  c->need_gen = true;                       // generated -- or taken from the prefetch set -- in transform_and_stage
+  c->last_logw = o->logw ? 1 : 0;
   if (c->timing) CK(cudaEventRecord(c->ev[3], c->stream));
-  k_gen_sources<<<nblk(3 * M1, 256), 256, 0, c->stream>>>(S, c->leg_no1.p, c->leg_wt1.p, c->leg_no2.p, c->leg_wt2.p,
-                                                          c->jac_no1.p, c->jac_wt1.p, c->jac_no2.p, c->jac_wt2.p,
-                                                          c->no1.p, c->buf1.p, c->no2.p, c->buf2.p);
-  LAUNCH_CHECK();
-  c->have_sources = true;
   return transform_and_stage_enqueue(c, a, b, o);
 }
 
@@ -1466,6 +1668,7 @@ static int subinterval_host_enqueue(sk_ctx *c, double a, double b, const double 
   CK(cudaMemcpyAsync(c->no2.p, no2, sizeof(double) * 2 * M1, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->buf2.p, buf2, sizeof(double) * 2 * M1, cudaMemcpyHostToDevice, c->stream));
   c->have_sources = true;
+  c->need_gen = false;
   return transform_and_stage_enqueue(c, a, b, o);
 }
 
@@ -1630,6 +1833,7 @@ int sk_subinterval_accept(sk_ctx *c) {
 }
 
 int sk_panel_commit(sk_ctx *c) {
+  NvtxRange nvtx("add panels to integral");
   if (!c) return SK_ERR_ARG;
   if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
   const long long n = c->hi - c->lo;
@@ -1651,6 +1855,7 @@ int sk_panel_commit(sk_ctx *c) {
 // the scan in two halves (see transform_and_stage_enqueue): enqueue the fused commit + predicate pass (nothing at all
 // when the panel was committed speculatively), then read the reduced scalars back
 static int converge_scan_enqueue(sk_ctx *c, const sk_scan_args *a) {
+  NvtxRange nvtx("check convergence");
   if (!c || !a) return SK_ERR_ARG;
   if (!c->in_panel) return fail(c, SK_ERR_STATE, "no open panel");
   if (a->criteria < 0 || a->criteria > 2) return fail(c, SK_ERR_ARG, "bad criteria");
@@ -1662,7 +1867,7 @@ static int converge_scan_enqueue(sk_ctx *c, const sk_scan_args *a) {
                       std::memcmp(&s0.trunc_num, &a->trunc_num, sizeof(double)) == 0 && s0.xpow == a->xpow && s0.tau == a->tau;
     if (!same) return fail(c, SK_ERR_STATE, "scan arguments differ from the ones the panel was speculated with");
     c->scan_from_spec = true;
-    if (c->comm) {   // sharded run: the scan is a collective point for every rank
+    if (c->comm && !c->pend_ab) {   // sharded run: the scan is a collective point for every rank
       unsigned long long rb = 0ull;
       std::memcpy(&rb, &c->spec_r, sizeof(double));
       const long long nlb = c->spec_new_hi - c->lo > 0 ? c->spec_new_hi - c->lo : 0;
@@ -1696,7 +1901,7 @@ static int converge_scan_finish(sk_ctx *c, int64_t *new_hi, double *r_at_new_hi)
     if (r_at_new_hi) *r_at_new_hi = c->spec_r;
     c->scan_hi = c->spec_new_hi;
     c->scan_r = c->spec_r;
-    if (c->comm) {
+    if (c->comm && !c->pend_ab) {
       CK(cudaStreamSynchronize(c->stream));
       comm_take_b(c);
     }
@@ -1778,6 +1983,7 @@ int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
 }
 
 static int results_enqueue(sk_ctx *c, double *vals, double *errs) {
+  NvtxRange nvtx("scatter to input order");
   if (!c || !vals) return SK_ERR_ARG;
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
   CK(cudaSetDevice(c->device));
@@ -1788,16 +1994,36 @@ static int results_enqueue(sk_ctx *c, double *vals, double *errs) {
   CK(c->out_v.ensure(c->n_in));
   if (errs) CK(c->out_e.ensure(c->n_in));
   if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
-  k_gather<<<nblk(c->n_in, 1024), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, c->out_v.p, errs ? c->out_e.p : nullptr, c->in.p,
-                                                       c->in_scale, c->tails);
-  LAUNCH_CHECK();
-  if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
-  CK(cudaMemcpyAsync(vals, c->out_v.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
-  if (errs) CK(cudaMemcpyAsync(errs, c->out_e.p, sizeof(double) * c->n_in, cudaMemcpyDeviceToHost, c->stream));
+  // Large outputs are gathered and copied in slices: the copy of slice k (stream2) overlaps the gather of slice k+1
+  // (compute stream), so the PCIe link is busy from the first slice on.  (stream2 is otherwise the prefetch stream and
+  // idle at this point.)
+  const long long n = c->n_in;
+  const int nslice = n >= (1LL << 21) ? SK_GATHER_SLICES : 1;
+  for (int k = 0; k < nslice; ++k) {
+    const long long o = (n * k / nslice) & ~1023LL, e = k + 1 == nslice ? n : ((n * (k + 1) / nslice) & ~1023LL);
+    if (e <= o) continue;
+    k_gather<<<nblk(e - o, 1024), 256, 0, c->stream>>>(c->inv.p + o, c->res.p, e - o, c->out_v.p + o,
+                                                        errs ? c->out_e.p + o : nullptr, c->in.p + o, c->in_scale, c->tails);
+    LAUNCH_CHECK();
+    if (nslice == 1) {
+      if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
+      CK(cudaMemcpyAsync(vals, c->out_v.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+      if (errs) CK(cudaMemcpyAsync(errs, c->out_e.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+      if (!c->ev_slice[k]) CK(cudaEventCreateWithFlags(&c->ev_slice[k], cudaEventDisableTiming));
+      CK(cudaEventRecord(c->ev_slice[k], c->stream));
+      CK(cudaStreamWaitEvent(c->stream2, c->ev_slice[k], 0));
+      CK(cudaMemcpyAsync(vals + o, c->out_v.p + o, sizeof(double) * (e - o), cudaMemcpyDeviceToHost, c->stream2));
+      if (errs) CK(cudaMemcpyAsync(errs + o, c->out_e.p + o, sizeof(double) * (e - o), cudaMemcpyDeviceToHost, c->stream2));
+    }
+  }
+  if (nslice > 1 && c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
+  c->results_sliced = nslice > 1;
   return SK_OK;
 }
 static int results_finish(sk_ctx *c) {
   CK(cudaStreamSynchronize(c->stream));
+  if (c->results_sliced) CK(cudaStreamSynchronize(c->stream2));
   if (c->timing) {
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
@@ -1870,6 +2096,8 @@ int sk_ctx_set_hankel_mode(sk_ctx *c, int mode) {
 
 int sk_stats_get(sk_ctx *c, sk_stats *out) {
   if (!c || !out) return SK_ERR_ARG;
+  c->stats.n_prefetch_issued = c->n_pf_issued;
+  c->stats.n_prefetch_hits = c->n_pf_hits;
   *out = c->stats;
   return SK_OK;
 }
@@ -1922,6 +2150,7 @@ int sk_group_create(const int32_t *devices, int32_t ndev, sk_group **out) {
     sk_ctx *c = nullptr;
     int rc = sk_ctx_create(devices[i], &c);
     if (rc != SK_OK) { sk_group_destroy(g); return rc; }
+    c->in_group = ndev > 1;               // chunks: the first panel's geometry comes from the global range
     g->ctx.push_back(c);
   }
   const size_t n = g->ctx.size();
@@ -2269,6 +2498,8 @@ int sk_group_stats_get(sk_group *g, sk_stats *out) {
     out->source_ms = std::max(out->source_ms, s.source_ms);
     out->sort_ms = std::max(out->sort_ms, s.sort_ms);
     out->gather_ms = std::max(out->gather_ms, s.gather_ms);
+    out->n_prefetch_issued += g->ctx[i]->n_pf_issued;
+    out->n_prefetch_hits += g->ctx[i]->n_pf_hits;
     out->timing_enabled = s.timing_enabled;
     out->sort_two_level = i == 0 ? s.sort_two_level : std::min(out->sort_two_level, s.sort_two_level);
   }

@@ -326,7 +326,7 @@ k_hankel_interp(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHa
 // and feeds 8 FMAs.
 // The arithmetic per target is the sequence of sk_hk_point, operation for operation: results are bit-identical
 // to k_hankel_interp whatever the pairing (tests: test_hankel_interp_variants_agree).
-__device__ __forceinline__ void sk_ld256(const void *p, double &a, double &b, double &c, double &d) {
+__device__ __forceinline__ void sk_ld256_nc(const void *p, double &a, double &b, double &c, double &d) {
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
@@ -350,7 +350,7 @@ __device__ __forceinline__ void sk_hk_interp_pair(const SkEsPlan &P, const SkHan
 #pragma unroll
     for (int i = 0; i < W; ++i) {
       double v0, v1, v2, v3;
-      sk_ld256(gp + (i * SK_HK_K + n) * 2, v0, v1, v2, v3);
+      sk_ld256_nc(gp + (i * SK_HK_K + n) * 2, v0, v1, v2, v3);
       aA[0] = sk_fma(tapA[i], v0, aA[0]); aA[1] = sk_fma(tapA[i], v1, aA[1]);
       aA[2] = sk_fma(tapA[i], v2, aA[2]); aA[3] = sk_fma(tapA[i], v3, aA[3]);
       aB[0] = sk_fma(tapB[i], v0, aB[0]); aB[1] = sk_fma(tapB[i], v1, aB[1]);

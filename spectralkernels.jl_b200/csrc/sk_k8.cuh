@@ -6,13 +6,13 @@
 //                 segments (of everything below SK_K8_SAMPLE_MIN inputs)
 //   k_k8_plan     one block: scan of the coarse histogram -> piecewise-linear estimate of the key distribution
 //   k_k8_scatter  every element -> its fine bin (~SK_K8_TARGET elements each, SK_K8_CAP slots): one global atomic for
-//                 the slot, one 8-byte + one 4-byte store; zeros are answered directly (inv = 0)
+//                 the slot (one counter per 32-byte sector), one 16-byte (key, index) store; zeros are answered directly
 //   k_k8_finish   one block per fine bin, in shared memory: counting sort on SK_K8_NSSB sub-bins, exact rank inside
 //                 the (tiny) sub-bin groups, first-of-value flags, block scan; the unique offset of the bin comes from
 //                 a decoupled look-back over the preceding bins; emits the sorted unique table and the inverse map
 //   k_k8_summary  n_unique, the two smallest and the largest unique distance, flags -> one read-back
 //
-// HBM traffic per input distance: 8 (stats) + 1 (sample) + 8 + 12 (scatter) + 12 + 8 + 4 (finish) = 53 bytes; the
+// HBM traffic per input distance: 8 (stats) + 1 (sample) + 8 + 16 (scatter) + 16 + 8 + 4 (finish) = 61 bytes; the
 // radix-sort pipeline this replaces moved ~150.  Nothing here depends on the order in which atomics resolve: the
 // unique table is the sorted set and inv[j] is the rank of x[j] in it, whatever slot the element landed in.
 #pragma once
@@ -208,8 +208,7 @@ k_k8_plan(SkK8State *__restrict__ st, const unsigned int *__restrict__ chist, lo
 // ---- pass 2: scatter into the fine bins ------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_k8_scatter(const double *__restrict__ xs, long long n, SkK8State *__restrict__ st, const uint2 *__restrict__ ctab,
-             unsigned int *__restrict__ fill, unsigned long long *__restrict__ skeys, unsigned int *__restrict__ sidx,
-             unsigned int *__restrict__ inv) {
+             unsigned int *__restrict__ fill, ulonglong2 *__restrict__ slots, unsigned int *__restrict__ inv) {
   if (!st->ndesc) return;
   const unsigned long long kmin = ~st->kmin_inv;
   const unsigned long long mul = st->mul;
@@ -223,11 +222,9 @@ k_k8_scatter(const double *__restrict__ xs, long long n, SkK8State *__restrict__
     sk_k8_coarse(k, kmin, mul, &cb, &frac);
     const uint2 e = __ldg(&ctab[cb]);
     const unsigned int f = (unsigned int)(((unsigned long long)e.x + __umul64hi(frac, (unsigned long long)e.y)) >> SK_K8_TARGET_LOG);
-    const unsigned int slot = atomicAdd(&fill[f], 1u);
+    const unsigned int slot = atomicAdd(&fill[(size_t)f * SK_K8_FILL_STRIDE], 1u);
     if (slot < (unsigned int)SK_K8_CAP) {
-      const size_t at = (size_t)f * SK_K8_CAP + slot;
-      skeys[at] = k;
-      sidx[at] = (unsigned int)j;
+      slots[(size_t)f * SK_K8_CAP + slot] = make_ulonglong2(k, (unsigned long long)j);   // (key, index): one 16-byte store
     } else {
       over = 1u;
     }
@@ -238,10 +235,9 @@ k_k8_scatter(const double *__restrict__ xs, long long n, SkK8State *__restrict__
 // ---- pass 3: finish every fine bin in shared memory ----------------------------------------------------------
 // desc[b]: bits 63..62 = 0 nothing yet, 1 = unique count of bin b, 2 = unique count of bins 0..b; low 32 bits = count
 #define SK_K8_SPIN_LIMIT (1 << 18)
-__global__ void __launch_bounds__(SK_K8_TPB)
-k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, const unsigned long long *__restrict__ skeys,
-            const unsigned int *__restrict__ sidx, unsigned long long *__restrict__ desc, double *__restrict__ uxs,
-            unsigned int *__restrict__ inv) {
+__global__ void __launch_bounds__(SK_K8_TPB, 4)
+k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, const ulonglong2 *__restrict__ slots,
+            unsigned long long *__restrict__ desc, double *__restrict__ uxs, unsigned int *__restrict__ inv) {
   if (!st->ndesc) return;
   __shared__ unsigned long long s_key[SK_K8_CAP];        // placed order, later final (sorted) order
   __shared__ int s_off[SK_K8_NSSB + 1];                  // sub-bin counts, then exclusive offsets (+ total)
@@ -254,18 +250,26 @@ k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, c
   // (the bounded spin below turns a violation of that into the general-sort fall-back, never into a hang)
   const unsigned int bin = blockIdx.x;
   if (bin >= st->nfine) return;
-  const unsigned int fl = fill[bin];
+  const unsigned int fl = fill[(size_t)bin * SK_K8_FILL_STRIDE];
   const int cnt = (int)(fl < (unsigned int)SK_K8_CAP ? fl : (unsigned int)SK_K8_CAP);
   const size_t base = (size_t)bin * SK_K8_CAP;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
   unsigned long long key[SK_K8_EPT];
+  unsigned int oidx[SK_K8_EPT];
   unsigned long long lo = ~0ull, hi = 0ull;
 #pragma unroll
   for (int e = 0; e < SK_K8_EPT; ++e) {
     const int t = threadIdx.x + e * SK_K8_TPB;
-    key[e] = t < cnt ? skeys[base + t] : 0ull;
-    if (t < cnt) { lo = lo < key[e] ? lo : key[e]; hi = hi > key[e] ? hi : key[e]; }
+    key[e] = 0ull;
+    oidx[e] = 0u;
+    if (t < cnt) {
+      const ulonglong2 rec = slots[base + t];
+      key[e] = rec.x;
+      oidx[e] = (unsigned int)rec.y;
+      lo = lo < key[e] ? lo : key[e];
+      hi = hi > key[e] ? hi : key[e];
+    }
   }
   for (int t = threadIdx.x; t <= SK_K8_NSSB; t += SK_K8_TPB) s_off[t] = 0;
 #pragma unroll
@@ -424,7 +428,7 @@ k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, c
 #pragma unroll
   for (int e = 0; e < SK_K8_EPT; ++e) {
     const int t = threadIdx.x + e * SK_K8_TPB;
-    if (t < cnt) inv[sidx[base + t]] = uoff + s_luid[fin[e]] - 1u;
+    if (t < cnt) inv[oidx[e]] = uoff + s_luid[fin[e]] - 1u;
   }
 }
 

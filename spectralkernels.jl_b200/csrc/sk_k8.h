@@ -23,6 +23,8 @@
 #define SK_K8_CAP 2048                        // slots per fine bin (2x slack over the estimate)
 #define SK_K8_NSSB 2048                       // sub-bins of the in-block counting sort
 #define SK_K8_SAMPLE_MIN (1 << 20)            // below this many inputs the coarse histogram sees every element
+#define SK_K8_FILL_STRIDE 8                   // one fill counter per 32-byte sector (measured: the L2 atomic units
+                                              // serialise per sector; eight counters per sector cost 45 % more time)
 
 struct SkK8State {              // device scalars of one sk_targets_set (zero-initialised by a memset)
   unsigned long long kmin_inv;  // ~min key over the positive inputs (atomicMax of ~key; 0 = no positive input)

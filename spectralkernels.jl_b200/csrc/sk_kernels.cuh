@@ -48,6 +48,12 @@ struct SkSpec {
   int criteria;
   long long lo0;          // global 0-based index of element 0
   double trunc_a, trunc_num, xpow, tau;
+  // The truncation half of the predicate, trunc_err(x) < tau, is monotone in the distance x (for trunc_num > 0 the
+  // bound min(trunc_a, trunc_num / (2 pi x)) does not increase with x, and IEEE rounding preserves that): the host
+  // finds the smallest double xstar with trunc_err(xstar) < tau by bisection on the SAME function (sk_trunc_err), so
+  // "x >= xstar" is the same decision for every double x -- one compare per target instead of a division.
+  int use_xstar, _pad;
+  double xstar;
   sk_cplx *res;           // (ks, errs), pre-offset to element 0
   sk_cplx *backup;        // old (ks, errs), pre-offset
 };
@@ -104,33 +110,65 @@ struct SkAcc {
   unsigned long long rb;    // bit pattern of its distance
 };
 
-// stage (SPEC == false) or commit speculatively (SPEC == true) the target with local index j, distance x
+// the arithmetic of one target's result, without the stores: (SPEC == false) out = (I2, |I2-I1|) for the staging
+// buffer; (SPEC == true) out = new (ks, errs) for `res` (the old pair goes to `backup`), plus the convergence
+// predicate of src/adaptive.jl:185-197 on panel_ks = I2
 template <bool SPEC>
-__device__ __forceinline__ void sk_emit(const SkSpec &spec, double f1, double f2, double cmul, double x, long long j,
-                                        sk_cplx *stage, SkAcc &acc, const sk_cplx old) {
-  if (!SPEC) {
-    sk_stage(f1, f2, cmul, &stage[j], acc.d, acc.fl);
-    return;
-  }
-  const double i1 = sk_mul(f1, cmul), i2 = sk_mul(f2, cmul);
+__device__ __forceinline__ sk_cplx sk_emit_value(const SkSpec &spec, double f1, double f2, double cmul, double x, long long j,
+                                                 SkAcc &acc, const sk_cplx old) {
+  const double i1 = sk_mul(f1, cmul), i2 = sk_mul(f2, cmul);     // explicit roundings: identical in every code path
   double dd = fabs(sk_add(i2, -i1));
-  spec.backup[j] = old;       // `old` = spec.res[j], loaded early by the caller to hide the latency
-  sk_cplx nw;
-  nw.x = sk_add(old.x, i2);   // ks += I with I = 0 + I2   (src/quadrature.jl:261, src/adaptive.jl:163)
-  nw.y = sk_add(old.y, dd);   // errs += err with err = 0 + |I2-I1|
-  spec.res[j] = nw;
-  if (dd != dd) {
+  sk_cplx out;
+  if (!SPEC) {
+    out.x = i2;
+    out.y = dd;
+  } else {
+    out.x = sk_add(old.x, i2);   // ks += I with I = 0 + I2   (src/quadrature.jl:261, src/adaptive.jl:163)
+    out.y = sk_add(old.y, dd);   // errs += err with err = 0 + |I2-I1|
+  }
+  if (dd != dd) {                                                 // NaN in I1 or I2 (or inf - inf): rare path
     acc.fl |= SK_FLAG_NAND;
     if (i1 != i1) acc.fl |= SK_FLAG_NAN1;
     if (i2 != i2) acc.fl |= SK_FLAG_NAN2;
     dd = 0.0;
   }
   acc.d = fmax(acc.d, dd);
-  const double te = sk_trunc_err(spec.trunc_a, spec.trunc_num, spec.xpow, x, spec.criteria == 0);
-  if (!sk_converged(te, i2, spec.tau, spec.criteria)) {
-    const long long g = spec.lo0 + j;
-    if (g > acc.bad) { acc.bad = g; acc.rb = (unsigned long long)__double_as_longlong(x); }
+  if (SPEC) {
+    bool conv;
+    if (spec.use_xstar) {
+      conv = (x >= spec.xstar) && ((spec.criteria == 1) || (fabs(i2) < spec.tau));
+    } else {
+      const double te = sk_trunc_err(spec.trunc_a, spec.trunc_num, spec.xpow, x, spec.criteria == 0);
+      conv = sk_converged(te, i2, spec.tau, spec.criteria);
+    }
+    if (!conv) {
+      const long long g = spec.lo0 + j;
+      if (g > acc.bad) { acc.bad = g; acc.rb = (unsigned long long)__double_as_longlong(x); }
+    }
   }
+  return out;
+}
+
+// stage (SPEC == false) or commit speculatively (SPEC == true) the target with local index j, distance x
+template <bool SPEC>
+__device__ __forceinline__ void sk_emit(const SkSpec &spec, double f1, double f2, double cmul, double x, long long j,
+                                        sk_cplx *stage, SkAcc &acc, const sk_cplx old) {
+  const sk_cplx out = sk_emit_value<SPEC>(spec, f1, f2, cmul, x, j, acc, old);
+  if (!SPEC) {
+    stage[j] = out;
+  } else {
+    spec.backup[j] = old;       // `old` = spec.res[j], loaded early by the caller to hide the latency
+    spec.res[j] = out;
+  }
+}
+
+// 32-byte global accesses (two (re, im) / (ks, errs) pairs per instruction): a thread that owns adjacent targets moves
+// whole sectors
+__device__ __forceinline__ void sk_ld256(const void *p, double &a, double &b, double &c, double &d) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void sk_st256(void *p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
 // block reduction of SkAcc -> device scalars
@@ -346,10 +384,9 @@ k_interp_session(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkG
 
 // one target from its cell's folded coefficients: Horner, post-phase, Re/Im select (explicit roundings so
 // that the block path and the warp path of k_interp_cells give bit-identical values)
-__device__ __forceinline__ void sk_cell_eval(const double *coef, const sk_cplx *tab, const SkGeom &G, double r, double s,
-                                             int kernel_sin, double *f1, double *f2) {
-  double a[4];
-  sk_cell_horner<4>(coef, s, a);
+// post-phase and Re/Im select of one target from its four Horner sums a = (re1, im1, re2, im2)
+__device__ __forceinline__ void sk_cell_finish(const double *a, const sk_cplx *tab, const SkGeom &G, double r, int kernel_sin,
+                                               double *f1, double *f2) {
   double sn, cs;
   sk_sincos2pi(tab, sk_frac_prod(G.wc, r, 0.0), &sn, &cs);            // post-phase exp(2 pi i wc r)
   if (kernel_sin) {                                                   // Im((a0 + i a1)(cs + i sn))
@@ -359,6 +396,12 @@ __device__ __forceinline__ void sk_cell_eval(const double *coef, const sk_cplx *
     *f1 = sk_fma(a[0], cs, -sk_mul(a[1], sn));
     *f2 = sk_fma(a[2], cs, -sk_mul(a[3], sn));
   }
+}
+__device__ __forceinline__ void sk_cell_eval(const double *coef, const sk_cplx *tab, const SkGeom &G, double r, double s,
+                                             int kernel_sin, double *f1, double *f2) {
+  double a[4];
+  sk_cell_horner<4>(coef, s, a);
+  sk_cell_finish(a, tab, G, r, kernel_sin, f1, f2);
 }
 
 // ---- K4 (cell polynomials) -----------------------------------------------------------------------------
@@ -370,6 +413,9 @@ __device__ __forceinline__ void sk_cell_eval(const double *coef, const sk_cplx *
 // Otherwise (sparse targets) it falls back to per-target taps straight from L2.
 #define SK_TPT 8
 #define SK_TPB (256 * SK_TPT)
+// doubles between the coefficient blocks of consecutive cells: 2 more than SK_NC * 4 = 64, so that the blocks of two
+// neighbouring cells (a warp's 128 adjacent targets often span two) do not start in the same shared-memory bank
+#define SK_CELL_STRIDE (SK_NC * 4 + 2)
 template <int W, bool SPEC, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G, const double *__restrict__ xs,
@@ -382,7 +428,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
   double *sO = sE + (W / 2) * (SK_NC / 2);
   double *sWin = sO + (W / 2) * (SK_NC / 2);            // [(cmax + W)][4]
   double *sQ = sWin + (size_t)(cmax + W) * 4;           // [cmax][4]  deconvolution factor at the 4 Chebyshev nodes
-  double *sCoef = sQ + (size_t)cmax * 4;                // [cmax][SK_NC][4]
+  double *sCoef = sQ + (size_t)cmax * 4;                // [cmax][SK_CELL_STRIDE]: (q, comp) at q * 4 + comp
   __shared__ sk_cplx sTab[65];                          // (cos, sin)(2 pi k / 64) for the post-phase
   const int tpb = 256 * tpt;
   const long long j0 = (long long)blockIdx.x * tpb;
@@ -414,7 +460,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     // B: coefficient (cell, q, comp) = W/2 FMAs
     for (int t = threadIdx.x; t < ncell * SK_NC * 4; t += blockDim.x) {
       const int comp = t & 3, q = (t >> 2) & (SK_NC - 1), cell = t / (SK_NC * 4);
-      sCoef[t] = sk_cell_coef<W>(sE, sO, sWin + cell * 4 + comp, 4, q);
+      sCoef[(size_t)cell * SK_CELL_STRIDE + (t & (SK_NC * 4 - 1))] = sk_cell_coef<W>(sE, sO, sWin + cell * 4 + comp, 4, q);
     }
     __syncthreads();
     // B': fold the deconvolution (a cubic per cell) into the coefficients, one column per thread
@@ -422,39 +468,130 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       const int comp = t & 3, cell = t >> 2;
       double a[4];
       sk_cheb4_to_monomial(sQ + cell * 4, a);
-      sk_cell_fold(sCoef + (size_t)cell * SK_NC * 4 + comp, 4, a);
+      sk_cell_fold(sCoef + (size_t)cell * SK_CELL_STRIDE + comp, 4, a);
     }
     __syncthreads();
-    // C: Horner per target
+    // C: Horner.  A thread takes FOUR ADJACENT targets at a time: sorted targets next to each other nearly always share
+    // their cell (~150 targets per cell at 1e7), so one pair of 16-byte shared-memory loads per coefficient feeds 16
+    // FMAs (4 targets x re/im x two rules) instead of 4, and every thread reads and writes 32 / 64 contiguous bytes of
+    // xs / (ks, errs).  The few quads that straddle a cell boundary (~2 %) would make half of all warps run a second,
+    // divergent pass; their targets are parked in a shared-memory list instead (the window / deconvolution scratch is
+    // free by now) and evaluated one per thread after the loop.  Each target sees exactly the operations of
+    // sk_cell_eval, in the same order, on every route: values do not depend on how targets are grouped (block path,
+    // warp path and the parked targets agree bit for bit).
+    unsigned short *sList = reinterpret_cast<unsigned short *>(sWin);
+    const int list_cap = (int)((((size_t)(cmax + W) * 4 + (size_t)cmax * 4) * sizeof(double)) / sizeof(unsigned short));
+    __shared__ int sListN;
+    if (threadIdx.x == 0) sListN = 0;
+    __syncthreads();                                         // (also: every thread is done with sWin / sQ)
+    const bool aligned32 = (((reinterpret_cast<size_t>(xs + j0)) | reinterpret_cast<size_t>(stage + j0) |
+                             (SPEC ? (reinterpret_cast<size_t>(spec.res + j0) | reinterpret_cast<size_t>(spec.backup + j0)) : 0)) & 31) == 0;
 #pragma unroll 1
     for (int uo = 0; uo < tpt / 4; ++uo) {
-      // issue all global loads of the 4 targets first (distances and, when committing speculatively, the
-      // old (ks, errs) pairs): their latency overlaps the arithmetic
+      const int t0 = (threadIdx.x + uo * 256) * 4;           // first local target of the quad
+      if (t0 >= cnt) continue;
+      const int nq = cnt - t0 < 4 ? cnt - t0 : 4;
       double rr[4];
       sk_cplx old[4];
+      const bool wide = aligned32 && nq == 4;
+      if (wide) {
+        sk_ld256(xs + j0 + t0, rr[0], rr[1], rr[2], rr[3]);
+        if (SPEC) {
+          sk_ld256(spec.res + j0 + t0, old[0].x, old[0].y, old[1].x, old[1].y);
+          sk_ld256(spec.res + j0 + t0 + 2, old[2].x, old[2].y, old[3].x, old[3].y);
+        } else {
 #pragma unroll
-      for (int ui = 0; ui < 4; ++ui) {
-        const int t = threadIdx.x + (uo * 4 + ui) * 256;
-        rr[ui] = 0.0;
-        old[ui].x = old[ui].y = 0.0;
-        if (t < cnt) {
-          rr[ui] = xs[j0 + t];
-          if (SPEC) old[ui] = spec.res[j0 + t];
+          for (int ui = 0; ui < 4; ++ui) old[ui].x = old[ui].y = 0.0;
+        }
+      } else {
+#pragma unroll
+        for (int ui = 0; ui < 4; ++ui) {
+          rr[ui] = ui < nq ? xs[j0 + t0 + ui] : 0.0;
+          old[ui].x = old[ui].y = 0.0;
+          if (SPEC && ui < nq) old[ui] = spec.res[j0 + t0 + ui];
         }
       }
+      int cell[4];
+      double sv[4];
 #pragma unroll
       for (int ui = 0; ui < 4; ++ui) {
-        const int t = threadIdx.x + (uo * 4 + ui) * 256;
-        if (t < cnt) {
-          const double r = rr[ui];
-          const SkTargetCoord tc = sk_target_coord<W>(G, r);
-          int cell = (int)(tc.l0 - l_first);
-          cell = cell < 0 ? 0 : (cell >= ncell ? ncell - 1 : cell);
+        const SkTargetCoord tc = sk_target_coord<W>(G, rr[ui]);
+        int cl = (int)(tc.l0 - l_first);
+        cell[ui] = cl < 0 ? 0 : (cl >= ncell ? ncell - 1 : cl);
+        sv[ui] = tc.s;
+      }
+      if (nq == 4 && cell[0] == cell[3]) {
+        double a[4][4];
+        const double *coef = sCoef + (size_t)cell[0] * SK_CELL_STRIDE;
+        {
+          const double2 c01 = *reinterpret_cast<const double2 *>(coef + (SK_NC - 1) * 4);
+          const double2 c23 = *reinterpret_cast<const double2 *>(coef + (SK_NC - 1) * 4 + 2);
+#pragma unroll
+          for (int ui = 0; ui < 4; ++ui) { a[ui][0] = c01.x; a[ui][1] = c01.y; a[ui][2] = c23.x; a[ui][3] = c23.y; }
+        }
+#pragma unroll
+        for (int q = SK_NC - 2; q >= 0; --q) {
+          const double2 c01 = *reinterpret_cast<const double2 *>(coef + q * 4);
+          const double2 c23 = *reinterpret_cast<const double2 *>(coef + q * 4 + 2);
+#pragma unroll
+          for (int ui = 0; ui < 4; ++ui) {
+            a[ui][0] = sk_fma(a[ui][0], sv[ui], c01.x);
+            a[ui][1] = sk_fma(a[ui][1], sv[ui], c01.y);
+            a[ui][2] = sk_fma(a[ui][2], sv[ui], c23.x);
+            a[ui][3] = sk_fma(a[ui][3], sv[ui], c23.y);
+          }
+        }
+        sk_cplx out[4];
+#pragma unroll
+        for (int ui = 0; ui < 4; ++ui) {
           double f1, f2;
-          sk_cell_eval(sCoef + (size_t)cell * SK_NC * 4, sTab, G, r, tc.s, kernel_sin, &f1, &f2);
-          sk_emit<SPEC>(spec, f1, f2, cmul, r, j0 + t, stage, acc, old[ui]);
+          sk_cell_finish(a[ui], sTab, G, rr[ui], kernel_sin, &f1, &f2);
+          out[ui] = sk_emit_value<SPEC>(spec, f1, f2, cmul, rr[ui], j0 + t0 + ui, acc, old[ui]);
+        }
+        if (wide) {
+          if (SPEC) {
+            sk_st256(spec.backup + j0 + t0, old[0].x, old[0].y, old[1].x, old[1].y);
+            sk_st256(spec.backup + j0 + t0 + 2, old[2].x, old[2].y, old[3].x, old[3].y);
+            sk_st256(spec.res + j0 + t0, out[0].x, out[0].y, out[1].x, out[1].y);
+            sk_st256(spec.res + j0 + t0 + 2, out[2].x, out[2].y, out[3].x, out[3].y);
+          } else {
+            sk_st256(stage + j0 + t0, out[0].x, out[0].y, out[1].x, out[1].y);
+            sk_st256(stage + j0 + t0 + 2, out[2].x, out[2].y, out[3].x, out[3].y);
+          }
+        } else {
+#pragma unroll
+          for (int ui = 0; ui < 4; ++ui) {
+            if (!SPEC) stage[j0 + t0 + ui] = out[ui];
+            else { spec.backup[j0 + t0 + ui] = old[ui]; spec.res[j0 + t0 + ui] = out[ui]; }
+          }
+        }
+      } else {
+        const int at = atomicAdd(&sListN, nq);
+        if (at + nq <= list_cap) {
+          for (int ui = 0; ui < nq; ++ui) sList[at + ui] = (unsigned short)(t0 + ui);
+        } else {                                             // list full (cannot happen at the densities of this path)
+          for (int ui = 0; ui < nq; ++ui) {
+            double f1, f2;
+            sk_cell_eval(sCoef + (size_t)cell[ui] * SK_CELL_STRIDE, sTab, G, rr[ui], sv[ui], kernel_sin, &f1, &f2);
+            sk_emit<SPEC>(spec, f1, f2, cmul, rr[ui], j0 + t0 + ui, stage, acc, old[ui]);
+          }
         }
       }
+    }
+    __syncthreads();
+    const int nlist = sListN < list_cap ? sListN : list_cap;
+    for (int i = threadIdx.x; i < nlist; i += blockDim.x) {  // the parked targets, one per thread
+      const int t = sList[i];
+      const double r = xs[j0 + t];
+      sk_cplx old;
+      old.x = old.y = 0.0;
+      if (SPEC) old = spec.res[j0 + t];
+      const SkTargetCoord tc = sk_target_coord<W>(G, r);
+      int cl = (int)(tc.l0 - l_first);
+      cl = cl < 0 ? 0 : (cl >= ncell ? ncell - 1 : cl);
+      double f1, f2;
+      sk_cell_eval(sCoef + (size_t)cl * SK_CELL_STRIDE, sTab, G, r, tc.s, kernel_sin, &f1, &f2);
+      sk_emit<SPEC>(spec, f1, f2, cmul, r, j0 + t, stage, acc, old);
     }
   } else {
     // Sparse block (more than cmax cells): the same arithmetic, one warp at a time.  The lanes of a warp

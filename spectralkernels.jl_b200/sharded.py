@@ -92,5 +92,16 @@ class LibComm:
     def sum(self, vals):
         return self._r(vals, 2)
 
+    def gather(self, vals):
+        """every rank's values, through ONE sum all-reduce of a one-hot layout (adding zeros is exact)"""
+        vals = list(vals)
+        k = len(vals)
+        if k * self.world_size > 32:
+            raise ValueError("too many values for sk_comm_allreduce")
+        buf = [0.0] * (k * self.world_size)
+        buf[self.rank * k:(self.rank + 1) * k] = vals
+        out = self._r(buf, 2)
+        return [out[r * k:(r + 1) * k] for r in range(self.world_size)]
+
     def close(self):
         self.engine.comm_destroy()
