@@ -393,15 +393,15 @@ int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long lon
   if (!attr_set) {
     cudaFuncSetAttribute(k_interp_cells<W, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_interp_cells<W, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_interp_cells<W, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_interp_cells<W, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_interp_cells<W, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_interp_cells<W, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;
   }
 #define SK_LAUNCH_CELLS(SPECV, MINBV)                                                                                  \
   k_interp_cells<W, SPECV, MINBV><<<nblk(n, tpb), 256, smem, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, cmax, tpt, \
                                                                               c->stage.p + c->lo, spec, c->d_red)
   if (c->interp_mode == 2) {           // A/B variant: 4 resident blocks per SM (<= 64 registers)
-    if (spec.on) SK_LAUNCH_CELLS(true, 4); else SK_LAUNCH_CELLS(false, 4);
+    if (spec.on) SK_LAUNCH_CELLS(true, 3); else SK_LAUNCH_CELLS(false, 3);
   } else {
     if (spec.on) SK_LAUNCH_CELLS(true, 2); else SK_LAUNCH_CELLS(false, 2);
   }
@@ -969,7 +969,7 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
     CK(cudaMemcpyAsync(&c->h_scal->k8, st, sizeof(SkK8State), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaEventRecord(c->k8_ev, c->stream));
   }
-  k_k8_sample<<<std::min<unsigned int>(nblk(n_in, 256), 148u * 2u), 256, 0, c->stream>>>(c->in.p, n_in, st, chist);
+  k_k8_sample<<<std::min<unsigned int>(nblk(n_in, 512), 148u), 512, 0, c->stream>>>(c->in.p, n_in, st, chist);
   LAUNCH_CHECK();
   k_k8_plan<<<1, 1024, 0, c->stream>>>(st, chist, n_in, c->k8_ctab.p);
   LAUNCH_CHECK();

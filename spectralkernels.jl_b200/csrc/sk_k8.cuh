@@ -47,31 +47,43 @@ k_k8_stats(const double *__restrict__ xs, long long n, SkK8State *__restrict__ s
   // neighbouring lane (lane 0 reads it)
   const long long nquad = (n + 3) / 4;
   const int lane_ = threadIdx.x & 31;
-  for (long long q0 = (long long)blockIdx.x * blockDim.x; q0 < nquad; q0 += (long long)gridDim.x * blockDim.x) {
-    const long long q = q0 + threadIdx.x, j = 4 * q;
-    double x[4] = {0.0, 0.0, 0.0, 0.0};
-    int m = 0;
-    if (q < nquad) {
-      if (j + 3 < n) {
-        const double2 a = *reinterpret_cast<const double2 *>(xs + j), b = *reinterpret_cast<const double2 *>(xs + j + 2);
-        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
-        m = 4;
-      } else {
-        for (; j + m < n; ++m) x[m] = xs[j + m];
+  // two quads per thread and step (the second one block-stride further): four 16-byte loads in flight
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q0 = (long long)blockIdx.x * blockDim.x; q0 < nquad; q0 += 2 * stride) {
+    double x[2][4];
+    int m[2];
+    long long jq[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long q = q0 + h * stride + threadIdx.x, j = 4 * q;
+      jq[h] = j;
+      m[h] = 0;
+      x[h][0] = x[h][1] = x[h][2] = x[h][3] = 0.0;
+      if (q < nquad) {
+        if (j + 3 < n) {
+          const double2 a = *reinterpret_cast<const double2 *>(xs + j), b = *reinterpret_cast<const double2 *>(xs + j + 2);
+          x[h][0] = a.x; x[h][1] = a.y; x[h][2] = b.x; x[h][3] = b.y;
+          m[h] = 4;
+        } else {
+          for (; j + m[h] < n; ++m[h]) x[h][m[h]] = xs[j + m[h]];
+        }
       }
     }
-    double prev = __shfl_up_sync(0xffffffffu, x[3], 1);
-    if (lane_ == 0 && m > 0 && j > 0) prev = xs[j - 1];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (i < m) {
-        const unsigned long long k = sk_k8_key(x[i], &bad);
-        if ((j + i > 0) && !(x[i] > prev)) ++nd;             // already sorted and unique? (src/adaptive.jl:113)
-        prev = x[i];
-        if (k == 0ull) ++nz;
-        else {
-          kmin_inv = kmin_inv > ~k ? kmin_inv : ~k;
-          kmax = kmax > k ? kmax : k;
+    for (int h = 0; h < 2; ++h) {
+      double prev = __shfl_up_sync(0xffffffffu, x[h][3], 1);
+      if (lane_ == 0 && m[h] > 0 && jq[h] > 0) prev = xs[jq[h] - 1];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < m[h]) {
+          const unsigned long long k = sk_k8_key(x[h][i], &bad);
+          if ((jq[h] + i > 0) && !(x[h][i] > prev)) ++nd;     // already sorted and unique? (src/adaptive.jl:113)
+          prev = x[h][i];
+          if (k == 0ull) ++nz;
+          else {
+            kmin_inv = kmin_inv > ~k ? kmin_inv : ~k;
+            kmax = kmax > k ? kmax : k;
+          }
         }
       }
     }
@@ -110,7 +122,7 @@ k_k8_stats(const double *__restrict__ xs, long long n, SkK8State *__restrict__ s
 
 // ---- pass 1: coarse histogram of a sample --------------------------------------------------------------
 // One warp per sampled 32-element segment; shared-memory privatised histogram, flushed with global atomics.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_k8_sample(const double *__restrict__ xs, long long n, const SkK8State *__restrict__ st,
             unsigned int *__restrict__ chist) {
   if (!st->ndesc || !st->kmin_inv) return;

@@ -22,13 +22,16 @@ from .sdf import is_builtin
 
 
 def kernel_derivative(cfg: AdaptiveKernelConfig, lags, k0: float, *, reuse_targets: bool = False, **kw):
-    """K'(lag): the sin-kernel run with p + 1 and c * (-2 pi)  (src/adaptive.jl:61-66, src/quadrature.jl:177)."""
+    """K'(lag): the sin-kernel run with p + 1 and c * (-2 pi)  (src/adaptive.jl:61-66, src/quadrature.jl:177).
+    Only the values are used by the callers (`[1]` in src/derivatives.jl:56), so the error estimates stay on the
+    device unless `want_errors=True` is passed; `out_vals` (pinned host memory) avoids the pageable-memory copy."""
     dcfg = gen_derivative_config(cfg)
+    kw.setdefault("want_errors", False)
     return kernel_values(dcfg, lags, k0=k0, reuse_targets=reuse_targets, **kw)[0]
 
 
 def kernel_sdf_derivatives(cfg: AdaptiveKernelConfig, lags, k0: float, *, dsdfs: Optional[List] = None,
-                           reuse_targets: bool = False, **kw) -> List[np.ndarray]:
+                           reuse_targets: bool = False, outs: Optional[List[np.ndarray]] = None, **kw) -> List[np.ndarray]:
     """One adaptive run per spectral-density parameter with f = dS/d theta_j (src/derivatives.jl:63-72).
     For the built-in families the parameter derivatives are device generators (`S.derivative(j)`); for
     other callables pass `dsdfs`, a list of callables."""
@@ -38,10 +41,14 @@ def kernel_sdf_derivatives(cfg: AdaptiveKernelConfig, lags, k0: float, *, dsdfs:
         nparam = {1: 3, 2: 2}[cfg.f.family]
         dsdfs = [cfg.f.derivative(j) for j in range(1, nparam + 1)]
     out = []
+    kw.setdefault("want_errors", False)                                      # only `[1]` is used (src/derivatives.jl:70)
     for j, dS in enumerate(dsdfs):
         cfgj = gen_new_sdf_config(cfg, dS)                                   # drops quadspec etc., as the reference
+        okw = dict(kw)
+        if outs is not None:
+            okw["out_vals"] = outs[j]                                        # e.g. pinned host arrays, one per parameter
         out.append(kernel_values(cfgj, lags, k0=k0, param_derivative=True,
-                                 reuse_targets=reuse_targets or j > 0, **kw)[0])
+                                 reuse_targets=reuse_targets or j > 0, **okw)[0])
     return out
 
 
@@ -50,4 +57,5 @@ def kernel_singularity_derivative(cfg: AdaptiveKernelConfig, lags, k0: float, df
     acfg = AdaptiveKernelConfig(cfg.f, df=df, derivative=False, alpha=cfg.alpha, dim=cfg.dim, logw=True, tol=cfg.tol,
                                 device=cfg.device, nufft_eps=cfg.nufft_eps)
     acfg._engine = cfg._engine
+    kw.setdefault("want_errors", False)
     return kernel_values(acfg, lags, k0=k0, param_derivative=True, reuse_targets=reuse_targets, **kw)[0]
