@@ -159,7 +159,7 @@ struct sk_ctx {
   // targets
   long long n_in = 0, n_unique = 0;
   bool has_zero = false;
-  DevBuf<double> in, uxs, uxs_orig, out_v, out_e;
+  DevBuf<double> in, uxs, uxs_fix, uxs_orig, out_v, out_e;
   bool have_orig = false;                     // uxs_orig holds the unscaled unique distances (sk_targets_scale)
   double in_scale = 1.0;                      // unique distance = input distance * in_scale (sk_targets_scale)
   SkTailList tails;                           // converged tails whose 2 trunc_err is added by the gather (k_gather)
@@ -175,7 +175,7 @@ struct sk_ctx {
   DevBuf<unsigned int> idx, idx_alt, head, uid, inv;
   DevBuf<unsigned char> cub_tmp;
   SkKeyBits *d_kb = nullptr;
-  // K8 (sk_k8.cuh): control block (state, coarse histogram, look-back descriptors, fill counters), the
+  // K8 (sk_k8.cuh): control block (state, coarse histogram, fill counters, offsets, dropped-duplicate counts), the
   // piecewise-linear distribution estimate, and the fine-bin slots
   DevBuf<unsigned char> k8_ctl;
   DevBuf<uint2> k8_ctab;
@@ -940,23 +940,28 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   c->have_targets = false;
   if (n_in > 0x7ffffff0LL) return fail(c, SK_ERR_ARG, "n_in too large");
   const size_t nfine_max = (size_t)(n_in >> SK_K8_TARGET_LOG) + 2;
-  // control block: state | coarse histogram | look-back descriptors | fill counters -- cleared by one memset
-  const size_t off_hist = 256, off_desc = off_hist + sizeof(unsigned int) * SK_K8_NC;
-  const size_t off_fill = off_desc + sizeof(unsigned long long) * nfine_max;
+  // control block: state | coarse histogram | fill counters (one per 32-byte sector) -- cleared by one memset;
+  // then, not cleared: provisional unique offsets | dropped duplicates per bin | their exclusive sums
+  const size_t off_hist = 256, off_fill = off_hist + sizeof(unsigned int) * SK_K8_NC;
   const size_t ctl_bytes = off_fill + sizeof(unsigned int) * nfine_max * SK_K8_FILL_STRIDE;
+  const size_t off_uoff = ctl_bytes, off_dup = off_uoff + sizeof(unsigned int) * nfine_max;
+  const size_t off_dsum = off_dup + sizeof(unsigned int) * nfine_max, all_bytes = off_dsum + sizeof(unsigned int) * nfine_max;
   static_assert(sizeof(SkK8State) <= 256, "control block layout");
-  CK(c->k8_ctl.ensure(ctl_bytes));
+  CK(c->k8_ctl.ensure(all_bytes));
   CK(c->k8_ctab.ensure(SK_K8_NC));
   CK(c->k8_slots.ensure(nfine_max * SK_K8_CAP));
   CK(c->uxs.ensure(n_in));               // sized for the worst case (n_unique <= n_in): no host round trip
+  CK(c->uxs_fix.ensure(n_in));           // the compacted table when duplicates were dropped (k_k8_fix_uxs)
   CK(c->inv.ensure(n_in));
   CK(c->res.ensure(n_in));
   CK(c->pan.ensure(n_in));
   CK(c->stage.ensure(n_in));
   SkK8State *st = (SkK8State *)c->k8_ctl.p;
   unsigned int *chist = (unsigned int *)(c->k8_ctl.p + off_hist);
-  unsigned long long *desc = (unsigned long long *)(c->k8_ctl.p + off_desc);
   unsigned int *fill = (unsigned int *)(c->k8_ctl.p + off_fill);
+  unsigned int *uoffp = (unsigned int *)(c->k8_ctl.p + off_uoff);
+  unsigned int *dup = (unsigned int *)(c->k8_ctl.p + off_dup);
+  unsigned int *dsum = (unsigned int *)(c->k8_ctl.p + off_dsum);
   if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
   CK(cudaMemsetAsync(c->k8_ctl.p, 0, ctl_bytes, c->stream));
   const unsigned int gs = std::min<unsigned int>(nblk(n_in, 256), 148u * 8u);    // grid-stride passes: 2048 threads per SM
@@ -975,11 +980,20 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   LAUNCH_CHECK();
   k_k8_scatter<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->k8_ctab.p, fill, c->k8_slots.p, c->inv.p);
   LAUNCH_CHECK();
-  k_k8_finish<<<(unsigned int)nfine_max, SK_K8_TPB, 0, c->stream>>>(st, fill, c->k8_slots.p, desc, c->uxs.p, c->inv.p);
+  k_k8_scan_bins<<<1, 1024, 0, c->stream>>>(st, fill, SK_K8_FILL_STRIDE, SK_K8_CAP, uoffp, 0);
+  LAUNCH_CHECK();
+  k_k8_finish<<<(unsigned int)nfine_max, SK_K8_TPB, 0, c->stream>>>(st, fill, c->k8_slots.p, uoffp, dup, c->uxs.p, c->inv.p);
+  LAUNCH_CHECK();
+  // only when duplicates were dropped (the three kernels return at once otherwise)
+  k_k8_scan_bins<<<1, 1024, 0, c->stream>>>(st, dup, 1, 0xffffffffu, dsum, 1);
+  LAUNCH_CHECK();
+  k_k8_fix_uxs<<<(unsigned int)nfine_max, 256, 0, c->stream>>>(st, fill, uoffp, dup, dsum, c->uxs.p, c->uxs_fix.p);
+  LAUNCH_CHECK();
+  k_k8_fix_inv<<<gs, 256, 0, c->stream>>>(st, uoffp, dsum, n_in, c->inv.p);
   LAUNCH_CHECK();
   k_k8_identity<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->uxs.p, c->inv.p);
   LAUNCH_CHECK();
-  k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, n_in, c->d_sum);
+  k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, c->uxs_fix.p, n_in, c->d_sum);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
   if (early) {
@@ -1013,6 +1027,7 @@ int targets_finish(sk_ctx *c, long long n_in, sk_target_info *info, bool force_g
   }
   const SkTargetSummary sm = c->h_scal->sum;
   if (sm.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
+  if (!general && sm.fixed) std::swap(c->uxs, c->uxs_fix);        // duplicates were dropped: the compacted table
   if (c->timing) {
     CK(cudaEventRecord(c->ev[1], c->stream));
     CK(cudaEventSynchronize(c->ev[1]));
@@ -1128,7 +1143,7 @@ int sk_ctx_destroy(sk_ctx *c) {
   for (auto &kv : c->fft_plans) cufftDestroy(kv.second);
   DevBuf<double> *dbl[] = {&c->leg_no1, &c->leg_wt1, &c->leg_no2, &c->leg_wt2, &c->jac_no1, &c->jac_wt1, &c->jac_no2,
                            &c->jac_wt2, &c->no1, &c->buf1, &c->no2, &c->buf2, &c->pos_hi1, &c->pos_lo1, &c->pos_hi2,
-                           &c->pos_lo2, &c->imz, &c->in, &c->uxs, &c->uxs_orig, &c->out_v, &c->out_e};
+                           &c->pos_lo2, &c->imz, &c->in, &c->uxs, &c->uxs_fix, &c->uxs_orig, &c->out_v, &c->out_e};
   for (auto *b : dbl) b->release();
   c->cs1.release(); c->cs2.release(); c->fft.release(); c->dsum.release();
   c->res.release(); c->pan.release(); c->stage.release();

@@ -7,9 +7,14 @@
 //   k_k8_plan     one block: scan of the coarse histogram -> piecewise-linear estimate of the key distribution
 //   k_k8_scatter  every element -> its fine bin (~SK_K8_TARGET elements each, SK_K8_CAP slots): one global atomic for
 //                 the slot (one counter per 32-byte sector), one 16-byte (key, index) store; zeros are answered directly
+//   k_k8_offsets  one block: exclusive scan of the bins' fill counts = where each bin's unique values start if no
+//                 distance occurs twice
 //   k_k8_finish   one block per fine bin, in shared memory: counting sort on SK_K8_NSSB sub-bins, exact rank inside
-//                 the (tiny) sub-bin groups, first-of-value flags, block scan; the unique offset of the bin comes from
-//                 a decoupled look-back over the preceding bins; emits the sorted unique table and the inverse map
+//                 the (tiny) sub-bin groups, first-of-value flags, block scan; emits the sorted unique table and the
+//                 inverse map at the bin's offset and records how many duplicates it dropped.  Blocks are independent
+//                 of each other (no look-back, no spinning).
+//   k_k8_fix_*    only when some bin dropped duplicates (all three return at once otherwise): scan of the dropped
+//                 counts, compaction of the unique table into a second buffer, shift of the inverse map
 //   k_k8_summary  n_unique, the two smallest and the largest unique distance, flags -> one read-back
 //
 // HBM traffic per input distance: 8 (stats) + 1 (sample) + 8 + 16 (scatter) + 16 + 8 + 4 (finish) = 61 bytes; the
@@ -29,7 +34,7 @@ struct SkTargetSummary {        // written by k_k8_summary
   unsigned int bad;
   unsigned int overflow;        // the bin scheme did not apply (clustered / heavily duplicated input): general sort
   unsigned int presorted;       // the input was already strictly increasing: no sort at all
-  unsigned int _pad;
+  unsigned int fixed;           // duplicates were dropped: the compacted unique table is in the second buffer
 };
 
 __device__ __forceinline__ unsigned long long sk_k8_key(double x, unsigned int *bad) {
@@ -244,12 +249,49 @@ k_k8_scatter(const double *__restrict__ xs, long long n, SkK8State *__restrict__
   if (__any_sync(0xffffffffu, over) && (threadIdx.x & 31) == 0) atomicOr(&st->overflow, 1u);
 }
 
+// ---- exclusive scan of min(fill, cap) over the bins in use: one block of 1024 threads ---------------------------------
+// src: one value per bin at stride `stride` (the padded fill counters, or the dropped-duplicate counts); dst[b] =
+// sum of the values of bins < b; *total = sum over all bins.  which = 0: provisional unique offsets (always);
+// which = 1: dropped duplicates (only when there are any).
+__global__ void __launch_bounds__(1024)
+k_k8_scan_bins(SkK8State *__restrict__ st, const unsigned int *__restrict__ src, int stride, unsigned int cap,
+               unsigned int *__restrict__ dst, int which) {
+  if (!st->ndesc) return;
+  if (which == 1 && st->ndup == 0ull) return;
+  __shared__ unsigned int s_w[32];
+  __shared__ unsigned int s_run;
+  const unsigned int nb = st->nfine;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_run = 0u;
+  __syncthreads();
+  for (unsigned int b0 = 0; b0 < nb; b0 += 1024u) {
+    const unsigned int b = b0 + threadIdx.x;
+    unsigned int v = 0u;
+    if (b < nb) { v = src[(size_t)b * stride]; v = v < cap ? v : cap; }
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    unsigned int wbase = 0u;
+    for (int w = 0; w < wid; ++w) wbase += s_w[w];
+    const unsigned int base = s_run;
+    if (b < nb) dst[b] = base + wbase + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_run = base + wbase + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && which == 0) st->n_slots = s_run;
+}
+
 // ---- pass 3: finish every fine bin in shared memory ----------------------------------------------------------
-// desc[b]: bits 63..62 = 0 nothing yet, 1 = unique count of bin b, 2 = unique count of bins 0..b; low 32 bits = count
-#define SK_K8_SPIN_LIMIT (1 << 18)
 __global__ void __launch_bounds__(SK_K8_TPB, 4)
 k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, const ulonglong2 *__restrict__ slots,
-            unsigned long long *__restrict__ desc, double *__restrict__ uxs, unsigned int *__restrict__ inv) {
+            const unsigned int *__restrict__ uoffp, unsigned int *__restrict__ dup, double *__restrict__ uxs,
+            unsigned int *__restrict__ inv) {
   if (!st->ndesc) return;
   __shared__ unsigned long long s_key[SK_K8_CAP];        // placed order, later final (sorted) order
   __shared__ int s_off[SK_K8_NSSB + 1];                  // sub-bin counts, then exclusive offsets (+ total)
@@ -257,9 +299,6 @@ k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, c
   __shared__ unsigned char s_head[SK_K8_CAP];
   __shared__ unsigned long long s_lo[8], s_hi[8];
   __shared__ int s_w[8];
-  __shared__ unsigned int s_uoff;
-  // bin = block index: blocks start in index order, so every predecessor the look-back waits for is already running
-  // (the bounded spin below turns a violation of that into the general-sort fall-back, never into a hang)
   const unsigned int bin = blockIdx.x;
   if (bin >= st->nfine) return;
   const unsigned int fl = fill[(size_t)bin * SK_K8_FILL_STRIDE];
@@ -389,49 +428,15 @@ k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, c
 #pragma unroll
     for (int i = 0; i < SK_K8_EPT; ++i) { run += c[i]; s_luid[threadIdx.x * SK_K8_EPT + i] = (unsigned short)run; }
   }
-  // unique offset of this bin: decoupled look-back over the preceding bins, 32 descriptors per step (one warp)
-  if (wid == 0) {
-    const unsigned long long zbase = st->nzero ? 1ull : 0ull;   // unique id 0 is the zero distance when there is one
-    unsigned long long prev = zbase;
-    if (bin > 0) {
-      if (lane == 0) atomicExch(&desc[bin], (1ull << 62) | (unsigned long long)nuniq);
-      prev = 0ull;
-      long long p = (long long)bin - 1;                         // nearest predecessor not yet accounted for
-      for (;;) {
-        const long long q = p - lane;
-        unsigned long long d = 2ull << 62;                       // before bin 0: nothing (bin 0 publishes zbase itself)
-        if (q >= 0) {
-          int spins = 0;
-          for (;;) {
-            d = *((volatile unsigned long long *)&desc[q]);
-            if (d >> 62) break;
-            if (++spins > SK_K8_SPIN_LIMIT) break;
-            __nanosleep(64);
-          }
-        }
-        const unsigned int dead = __ballot_sync(0xffffffffu, (d >> 62) == 0ull);
-        if (dead) {                                              // a predecessor never published: give up, flag it
-          if (lane == 0) atomicExch(&st->overflow, 2u);
-          break;
-        }
-        const unsigned int incl = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
-        const int stop = incl ? __ffs(incl) - 1 : 31;            // nearest predecessor holding an inclusive count
-        unsigned long long v = lane <= stop ? (d & 0xffffffffull) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        prev += v;
-        if (incl) break;
-        p -= 32;
-      }
-    }
-    if (lane == 0) {
-      atomicExch(&desc[bin], (2ull << 62) | (prev + (unsigned long long)nuniq));
-      s_uoff = (unsigned int)prev;
-      if (bin + 1u == st->nfine) st->n_unique_pos = (unsigned int)(prev + (unsigned long long)nuniq - zbase);
-    }
+  // The bin's unique values start where the preceding bins' ELEMENTS end (k_k8_scan_bins): exact when no distance
+  // occurs twice.  Dropped duplicates are recorded; k_k8_fix_* then shift the table and the map (rare path).
+  const unsigned int ndrop = (unsigned int)(cnt - nuniq);
+  if (threadIdx.x == 0) {
+    dup[bin] = ndrop;
+    if (ndrop) atomicAdd(&st->ndup, (unsigned long long)ndrop);
   }
-  __syncthreads();
-  const unsigned int uoff = s_uoff;
+  const unsigned int uoff = (st->nzero ? 1u : 0u) + uoffp[bin];
+  __syncthreads();                                         // s_luid complete
 #pragma unroll
   for (int i = 0; i < SK_K8_EPT; ++i) {
     const int p = threadIdx.x * SK_K8_EPT + i;
@@ -455,18 +460,55 @@ __global__ void k_k8_identity(const double *__restrict__ xs, long long n, const 
   }
 }
 
-__global__ void k_k8_summary(const SkK8State *__restrict__ st, double *__restrict__ uxs, long long n,
-                             SkTargetSummary *__restrict__ out) {
+// ---- duplicates were dropped: compact the unique table and shift the inverse map (all return at once otherwise) -----
+// uxs_out[zbase + uoffp[b] - D[b] + i] = uxs[zbase + uoffp[b] + i], i < fill[b] - dup[b]; one block per bin
+__global__ void __launch_bounds__(256)
+k_k8_fix_uxs(const SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, const unsigned int *__restrict__ uoffp,
+             const unsigned int *__restrict__ dup, const unsigned int *__restrict__ dsum, const double *__restrict__ uxs,
+             double *__restrict__ uxs_out) {
+  if (!st->ndesc || st->ndup == 0ull) return;
+  const unsigned int bin = blockIdx.x;
+  if (bin >= st->nfine) return;
+  const unsigned int zbase = st->nzero ? 1u : 0u;
+  unsigned int cnt = fill[(size_t)bin * SK_K8_FILL_STRIDE];
+  cnt = cnt < (unsigned int)SK_K8_CAP ? cnt : (unsigned int)SK_K8_CAP;
+  const unsigned int nu = cnt - dup[bin], from = zbase + uoffp[bin], to = from - dsum[bin];
+  for (unsigned int i = threadIdx.x; i < nu; i += blockDim.x) uxs_out[to + i] = uxs[from + i];
+  if (bin == 0 && threadIdx.x == 0 && zbase) uxs_out[0] = 0.0;
+}
+// inv[j] -= D[bin of inv[j]]: the bin of a provisional unique id by binary search in the provisional offsets
+__global__ void __launch_bounds__(256)
+k_k8_fix_inv(const SkK8State *__restrict__ st, const unsigned int *__restrict__ uoffp, const unsigned int *__restrict__ dsum,
+             long long n, unsigned int *__restrict__ inv) {
+  if (!st->ndesc || st->ndup == 0ull) return;
+  const unsigned int zbase = st->nzero ? 1u : 0u, nb = st->nfine;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    const unsigned int u = inv[j];
+    if (u < zbase) continue;                                 // the zero distance
+    const unsigned int v = u - zbase;
+    unsigned int a = 0u, b = nb;                             // last bin with uoffp[bin] <= v
+    while (b - a > 1u) {
+      const unsigned int mid = (a + b) >> 1;
+      if (__ldg(&uoffp[mid]) <= v) a = mid; else b = mid;
+    }
+    inv[j] = u - __ldg(&dsum[a]);
+  }
+}
+
+__global__ void k_k8_summary(const SkK8State *__restrict__ st, double *__restrict__ uxs, double *__restrict__ uxs_fix,
+                             long long n, SkTargetSummary *__restrict__ out) {
   const bool presorted = st->ndesc == 0ull;
-  long long nu = presorted ? n : (long long)(st->nzero ? 1 : 0) + (long long)st->n_unique_pos;
+  const bool fixed = !presorted && st->ndup != 0ull;        // the compacted table lives in uxs_fix
+  double *tab = fixed ? uxs_fix : uxs;
+  long long nu = presorted ? n : (long long)(st->nzero ? 1 : 0) + (long long)st->n_slots - (long long)st->ndup;
   if (nu < 1 || nu > n) nu = 1;                // only after an overflow / invalid input (the host then discards this)
-  if (!presorted && st->nzero) uxs[0] = 0.0;
+  if (!presorted && st->nzero) tab[0] = 0.0;
   out->n_unique = nu;
-  out->r0 = uxs[0];
-  out->r1 = nu > 1 ? uxs[1] : 0.0;
-  out->r_last = uxs[nu - 1];
+  out->r0 = tab[0];
+  out->r1 = nu > 1 ? tab[1] : 0.0;
+  out->r_last = tab[nu - 1];
   out->bad = st->bad;
   out->overflow = st->overflow;
   out->presorted = presorted ? 1u : 0u;
-  out->_pad = 0u;
+  out->fixed = fixed ? 1u : 0u;
 }

@@ -33,9 +33,10 @@ struct SkK8State {              // device scalars of one sk_targets_set (zero-in
   unsigned long long mul;       // sk_k8_mul(kmin, kmax)                              (written by k_k8_plan)
   unsigned long long ndesc;     // number of j with x[j] <= x[j-1]; 0: the input is already strictly increasing
   unsigned int bad;             // a distance was NaN / negative / infinite
-  unsigned int overflow;        // 1: a fine bin outgrew its slots; 2: a look-back spin timed out
+  unsigned long long ndup;      // duplicates dropped by k_k8_finish, all bins
+  unsigned int overflow;        // 1: a fine bin outgrew its slots
   unsigned int nfine;           // fine bins in use                                   (written by k_k8_plan)
-  unsigned int n_unique_pos;    // unique positive distances                          (written by k_k8_finish)
+  unsigned int n_slots;         // positive inputs in the bins = sum of the fills       (written by k_k8_scan_bins)
 };
 
 // Coarse bins tile the key range [kmin, kmax] exactly: with M = floor(2^64 SK_K8_NC / (kmax - kmin + 1)) the 128-bit

@@ -1021,7 +1021,7 @@ __global__ void k_target_summary(const double *__restrict__ uxs, const unsigned 
   out->r_last = uxs[nu - 1];
   out->bad = kb->bad;
   out->presorted = 0u;
-  out->_pad = 0u;
+  out->fixed = 0u;
 }
 
 // values and errors back in the ORIGINAL input order (src/adaptive.jl:105-107) from res = (ks, errs): one
