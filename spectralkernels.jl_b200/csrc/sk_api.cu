@@ -151,7 +151,7 @@ struct sk_ctx {
   cudaEvent_t ev_slice[SK_GATHER_SLICES] = {nullptr};
   bool results_sliced = false;
   int last_logw = 0;
-  bool in_group = false;
+  bool in_group = false, early_pending = false, early_global = false;
   long long n_pf_hits = 0, n_pf_issued = 0;
   DevBuf<double> bufb1, bufb2;               // second integrand of the log-weighted origin sub-interval
   bool have_sources = false;
@@ -932,6 +932,39 @@ int targets_sort_general(sk_ctx *c, long long n_in) {
   return SK_OK;
 }
 
+// the key range of the distances being sorted, available as soon as k_k8_stats has run (r_hi = 0: no usable range)
+int targets_early_range(sk_ctx *c, double *r_lo, double *r_hi) {
+  *r_lo = *r_hi = 0.0;
+  if (!c->early_pending) return SK_OK;
+  c->early_pending = false;
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventSynchronize(c->k8_ev));
+  unsigned long long kmin_inv, kmax, bad;
+  if (c->early_global) {
+    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(c->h_scal->hv);
+    kmin_inv = w[0]; kmax = w[1]; bad = w[2];
+  } else {
+    const SkK8State &k8 = c->h_scal->k8;
+    kmin_inv = k8.kmin_inv; kmax = k8.kmax; bad = k8.bad;
+  }
+  if (bad || kmin_inv == 0ull || kmax == 0ull) return SK_OK;
+  const unsigned long long kmin = ~kmin_inv;
+  std::memcpy(r_lo, &kmin, sizeof(double));
+  std::memcpy(r_hi, &kmax, sizeof(double));
+  return SK_OK;
+}
+// source side of the first panel (0, m k / (2 r_hi)) (src/adaptive.jl:152) over the distance range [r_lo, r_hi], on the
+// prefetch stream, while the sort is still running
+int targets_early_prefetch(sk_ctx *c, double r_lo, double r_hi) {
+  CK(cudaSetDevice(c->device));
+  const double b1 = 0.0 + (double)((long long)c->m * c->k) / (2 * r_hi);
+  SkGeom G1;
+  if (!(std::isfinite(b1) && b1 > 0.0) || sk_make_geom(c->plan, 0.0, b1, r_lo, r_hi, &G1) != 0) return SK_OK;
+  SkPanelSpec S1;
+  make_panel_spec(c, 0.0, b1, c->last_logw, &S1);
+  return prefetch_sources(c, S1, G1);
+}
+
 // K8 (sk_k8.cuh): c->in holds the n_in raw distances -> sorted unique table c->uxs, inverse map c->inv.  One host
 // synchronisation, at the end (the summary); an already strictly increasing input is detected on the device and
 // costs one read pass.  Two halves like transform_and_stage (a device group sorts all chunks concurrently).
@@ -969,9 +1002,27 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   LAUNCH_CHECK();
   // the first panel is (0, quadm / (2 r_max)) (src/adaptive.jl:152) and r_max is known after this first pass: fetch the
   // key range now, and start the panel's source side on the prefetch stream while the sort runs
-  const bool early = c->prefetch_on && !c->in_group && c->have_rule && c->family != SK_SDF_HOST && n_in >= 65536 && c->plan.w > 0;
+  // (a rank of a process-per-GPU run does not know the global distance range yet: no early prefetch there; a device
+  //  group issues it for all its devices once every chunk's range is in: sk_group_targets_set)
+  const bool early = c->prefetch_on && c->have_rule && c->family != SK_SDF_HOST && c->plan.w > 0 &&
+                     (c->in_group || c->comm || n_in >= 65536);
+  c->early_pending = early;
+  c->early_global = false;
   if (early) {
-    CK(cudaMemcpyAsync(&c->h_scal->k8, st, sizeof(SkK8State), cudaMemcpyDeviceToHost, c->stream));
+    if (c->comm) {
+      // process-per-GPU run: the panels are built from the GLOBAL distance range, so the ranks reduce their key
+      // ranges here (one 3-word MAX all-reduce behind the first pass; every rank takes this branch or none does:
+      // the condition above holds no rank-local quantity)
+      NcclApi *N = nccl_api();
+      unsigned long long *w = reinterpret_cast<unsigned long long *>(c->d_hv);
+      k_k8_pack_range<<<1, 1, 0, c->stream>>>(st, w);
+      LAUNCH_CHECK();
+      NCK(N->AllReduce(w, w, 3, ncclUint64, ncclMax, c->comm, c->stream));
+      CK(cudaMemcpyAsync(c->h_scal->hv, w, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      c->early_global = true;
+    } else {
+      CK(cudaMemcpyAsync(&c->h_scal->k8, st, sizeof(SkK8State), cudaMemcpyDeviceToHost, c->stream));
+    }
     CK(cudaEventRecord(c->k8_ev, c->stream));
   }
   k_k8_sample<<<std::min<unsigned int>(nblk(n_in, 512), 148u), 512, 0, c->stream>>>(c->in.p, n_in, st, chist);
@@ -996,22 +1047,13 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, c->uxs_fix.p, n_in, c->d_sum);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
-  if (early) {
-    CK(cudaEventSynchronize(c->k8_ev));
-    const SkK8State &k8 = c->h_scal->k8;
-    if (!k8.bad && k8.kmin_inv != 0ull && k8.kmax != 0ull) {
-      double r_lo, r_hi;
-      const unsigned long long kmin = ~k8.kmin_inv;
-      std::memcpy(&r_lo, &kmin, sizeof(double));
-      std::memcpy(&r_hi, &k8.kmax, sizeof(double));
-      const double b1 = 0.0 + (double)((long long)c->m * c->k) / (2 * r_hi);
-      SkGeom G1;
-      if (std::isfinite(b1) && b1 > 0.0 && sk_make_geom(c->plan, 0.0, b1, r_lo, r_hi, &G1) == 0) {
-        SkPanelSpec S1;
-        make_panel_spec(c, 0.0, b1, c->last_logw, &S1);
-        int rc = prefetch_sources(c, S1, G1);
-        if (rc != SK_OK) return rc;
-      }
+  if (early && !c->in_group) {
+    double r_lo = 0, r_hi = 0;
+    int rc = targets_early_range(c, &r_lo, &r_hi);
+    if (rc != SK_OK) return rc;
+    if (r_hi > 0.0) {
+      rc = targets_early_prefetch(c, r_lo, r_hi);
+      if (rc != SK_OK) return rc;
     }
   }
   return SK_OK;
@@ -2273,6 +2315,27 @@ int sk_group_targets_set(sk_group *g, const double *xs_host, int64_t n_in, sk_ta
     }
     int rc = targets_enqueue(c, g->cnt[i]);
     if (rc != SK_OK) return gfail(g, i, rc);
+  }
+  {
+    // every chunk's key range is in long before its sort ends: the first panel's source side -- built from the GLOBAL
+    // range, as sk_panel_set_range will ask for -- starts on every device while the sorts run
+    double lo_g = 0.0, hi_g = 0.0;
+    long long n_tot = 0;
+    for (int i = 0; i < g->nuse; ++i) {
+      double lo = 0, hi = 0;
+      int rc = targets_early_range(g->ctx[i], &lo, &hi);
+      if (rc != SK_OK) return gfail(g, i, rc);
+      if (hi > 0.0) {
+        if (lo_g == 0.0 || lo < lo_g) lo_g = lo;
+        if (hi > hi_g) hi_g = hi;
+      }
+      n_tot += g->cnt[i];
+    }
+    if (hi_g > 0.0 && n_tot >= 65536)
+      for (int i = 0; i < g->nuse; ++i) {
+        int rc = targets_early_prefetch(g->ctx[i], lo_g, hi_g);
+        if (rc != SK_OK) return gfail(g, i, rc);
+      }
   }
   g->has_zero = false;
   g->r_min_pos = 0.0;

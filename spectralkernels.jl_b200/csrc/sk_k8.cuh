@@ -449,6 +449,13 @@ k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, c
   }
 }
 
+// (process-per-GPU runs) the local key range as two words for a MAX all-reduce: ~kmin and kmax
+__global__ void k_k8_pack_range(const SkK8State *__restrict__ st, unsigned long long *__restrict__ out) {
+  out[0] = st->kmin_inv;
+  out[1] = st->kmax;
+  out[2] = st->bad ? 1ull : 0ull;
+}
+
 // already sorted and unique input: the unique table is the input itself and the inverse map is the identity
 __global__ void k_k8_identity(const double *__restrict__ xs, long long n, const SkK8State *__restrict__ st,
                               double *__restrict__ uxs, unsigned int *__restrict__ inv) {
