@@ -69,7 +69,7 @@ def parse():
     ap.add_argument("--n", type=int, default=10_000_000, help="distances per GPU")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000, help="distances in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--interp-mode", type=int, default=0, help="0 cells (default), 1 per-target taps, 2 cells @4 blocks/SM")
+    ap.add_argument("--interp-mode", type=int, default=0, help="0 cell polynomials (default), 1 per-target taps (A/B reference)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: n distances per GPU (the headline line); strong: the n distances of the BASELINE workload "
                          "split over the GPUs.  The weak line always carries the strong-scaling leg as well (key 'strong')")

@@ -241,7 +241,9 @@ int sk_subinterval_host(sk_ctx *ctx, double a, double b, const double *no1, cons
  * I_k = (I0 - Re A_k + 2 pi x Im B_k) / denom * cmul like sk_subinterval.
  * With opts->kernel == SK_KERNEL_BESSEL (dim >= 2, :204-221) the two transforms are Bessel sums of orders
  * opts->nu = dim/2-1 (A) and opts->nu + 1 (B), I0 carries J_nu(2 pi b x) and the result is divided by
- * x^xdiv_pow: I_k = (I0 - A_k + 2 pi x B_k) / denom * cmul / x^(dim/2-1). */
+ * x^xdiv_pow: I_k = (I0 - A_k + 2 pi x B_k) / denom * cmul / x^(dim/2-1).
+ * All six array pointers NULL: a built-in density is set (sk_sdf_builtin, deriv_index 0) and the device evaluates both
+ * integrands itself (dS/dw of the shipped families is closed-form): nothing is evaluated on or uploaded from the host. */
 int sk_subinterval_logw_host(sk_ctx *ctx, double a, double b, const double *no1, const double *bufa1,
                              const double *bufb1, const double *no2, const double *bufa2, const double *bufb2,
                              const sk_subinterval_opts *opts, double i0_coef, double denom, double *max_abs_diff);

@@ -197,19 +197,27 @@ function kernel_values(config::AdaptiveKernelConfig{<:OnB200}, xs::AbstractVecto
         dim <= 2 || error("singularity derivative not implemented in d > 2")                      # :222-223
         s.group && error("the log-weighted origin sub-interval takes a single context")
         (f, df) = (config.f, config.df)
-        (no1, ba1, no2, ba2) = updatequadbufs!(config.buffers, config.legrule, config.jacrule,
-                                               w -> f(w) + w*log(w)*df(w), _a, _b; p=config.p)
-        (no1, ra1, no2, ra2) = (copy(no1), real.(ba1), copy(no2), real.(ba2))
-        (_, bb1, _, bb2)     = updatequadbufs!(config.buffers, config.legrule, config.jacrule,
-                                               w -> w*log(w)*f(w), _a, _b; p=config.p)
-        (rb1, rb2) = (real.(bb1), real.(bb2))
         i0   = _b^(dim/2 + 1 - config.alpha)*log(_b)*f(_b)                                          # :189
         lopt = Ref(SubintervalOpts(config.c, config.p, dim == 1 ? SK_KERNEL_COS : SK_KERNEL_BESSEL, 1,
                                    dim == 1 ? 0 : Int64(dim/2 - 1), 0, dim/2 - 1, C_NULL))
-        GC.@preserve no1 ra1 rb1 no2 ra2 rb2 ck(s, ccall((:sk_subinterval_logw_host, libsk), Cint,
-            (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-             Ptr{Float64}, Ref{SubintervalOpts}, Float64, Float64, Ref{Float64}),
-            s.h, _a, _b, no1, ra1, rb1, no2, ra2, rb2, lopt, i0, dim - config.alpha, mx))
+        if !isnothing(builtin) && builtin[3] == 0
+          # a shipped family: dS/dw is closed-form, the device evaluates both integrands itself (all pointers NULL)
+          ck(s, ccall((:sk_subinterval_logw_host, libsk), Cint,
+              (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+               Ptr{Float64}, Ref{SubintervalOpts}, Float64, Float64, Ref{Float64}),
+              s.h, _a, _b, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, lopt, i0, dim - config.alpha, mx))
+        else
+          (no1, ba1, no2, ba2) = updatequadbufs!(config.buffers, config.legrule, config.jacrule,
+                                                 w -> f(w) + w*log(w)*df(w), _a, _b; p=config.p)
+          (no1, ra1, no2, ra2) = (copy(no1), real.(ba1), copy(no2), real.(ba2))
+          (_, bb1, _, bb2)     = updatequadbufs!(config.buffers, config.legrule, config.jacrule,
+                                                 w -> w*log(w)*f(w), _a, _b; p=config.p)
+          (rb1, rb2) = (real.(bb1), real.(bb2))
+          GC.@preserve no1 ra1 rb1 no2 ra2 rb2 ck(s, ccall((:sk_subinterval_logw_host, libsk), Cint,
+              (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+               Ptr{Float64}, Ref{SubintervalOpts}, Float64, Float64, Ref{Float64}),
+              s.h, _a, _b, no1, ra1, rb1, no2, ra2, rb2, lopt, i0, dim - config.alpha, mx))
+        end
       elseif isnothing(builtin)
         origin = (_a == 0.0 && config.p != 0.0)
         f = origin ? config.f : (w -> w^config.p * (config.logw ? log(w) : 1) * config.f(w))

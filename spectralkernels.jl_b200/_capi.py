@@ -402,8 +402,12 @@ class Session:
                               kernel: int = SK_KERNEL_COS, nu: int = 0, xdiv_pow: float = 0.0) -> float:
         o = SubintervalOpts(float(cmul), float(p), int(kernel), 1, int(nu), 0, float(xdiv_pow), None)
         out = c_double()
-        arrs = [_f64(x) for x in (no1, bufa1, bufb1, no2, bufa2, bufb2)]
-        self._ck(self._L.sk_subinterval_logw_host(self._h, float(a), float(b), *[_p(x) for x in arrs], byref(o),
+        if no1 is None:          # built-in density: both integrands are evaluated on the device
+            ptrs = [None] * 6
+        else:
+            arrs = [_f64(x) for x in (no1, bufa1, bufb1, no2, bufa2, bufb2)]
+            ptrs = [_p(x) for x in arrs]
+        self._ck(self._L.sk_subinterval_logw_host(self._h, float(a), float(b), *ptrs, byref(o),
                                                   float(i0_coef), float(denom), byref(out)))
         return out.value
 

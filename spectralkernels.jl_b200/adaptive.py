@@ -290,12 +290,16 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
                 if cfg.dim not in (1, 2):
                     raise NotImplementedError("singularity derivative not implemented in d > 2")   # :222-223
                 f, df = cfg.f, cfg.df
-                if df is None:
-                    raise TypeError("logw=true needs df (the derivative of the spectral density)")
-                ga = lambda w: f(w) + w * np.log(w) * df(w)                      # :192, :210
-                gb = lambda w: w * np.log(w) * f(w)                              # :198, :216
-                no1, ba1, no2, ba2 = _host_strengths(cfg, eng, _a, _b, True, integrand=ga)
-                _, bb1, _, bb2 = _host_strengths(cfg, eng, _a, _b, True, integrand=gb)
+                if builtin and getattr(f, "deriv", 0) == 0 and (df is None or getattr(df, "__self__", None) is f):
+                    # a shipped family and its own closed-form dS/dw: both integrands are evaluated on the device
+                    no1 = ba1 = bb1 = no2 = ba2 = bb2 = None
+                else:
+                    if df is None:
+                        raise TypeError("logw=true needs df (the derivative of the spectral density)")
+                    ga = lambda w: f(w) + w * np.log(w) * df(w)                  # :192, :210
+                    gb = lambda w: w * np.log(w) * f(w)                          # :198, :216
+                    no1, ba1, no2, ba2 = _host_strengths(cfg, eng, _a, _b, True, integrand=ga)
+                    _, bb1, _, bb2 = _host_strengths(cfg, eng, _a, _b, True, integrand=gb)
                 i0 = _b ** (cfg.dim / 2 + 1 - cfg.alpha) * math.log(_b) * _f_scalar(f, _b)      # :189
                 if cfg.dim == 1:
                     mx = eng.subinterval_logw_host(_a, _b, no1, ba1, bb1, no2, ba2, bb2, cfg.c, cfg.p, i0,

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <tuple>
@@ -125,7 +126,7 @@ struct sk_ctx {
   std::vector<double> h_rule[8];
   // generated rules, kept for the life of the context: (n, p) -> (nodes, weights).  Derivative configs flip
   // between p = 0 and p = 1 (src/adaptive.jl:42), and a generation costs ~0.3 s of host time at n = 8192
-  std::map<std::pair<int, double>, std::pair<std::vector<double>, std::vector<double>>> rule_cache;
+  // (the generated rules themselves are cached process-wide: rule_cache() below)
 
   // integrand
   int family = SK_SDF_HOST, deriv = 0, nparam = 0;
@@ -393,18 +394,12 @@ int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long lon
   if (!attr_set) {
     cudaFuncSetAttribute(k_interp_cells<W, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_interp_cells<W, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_interp_cells<W, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_interp_cells<W, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;
   }
 #define SK_LAUNCH_CELLS(SPECV, MINBV)                                                                                  \
   k_interp_cells<W, SPECV, MINBV><<<nblk(n, tpb), 256, smem, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, cmax, tpt, \
                                                                               c->stage.p + c->lo, spec, c->d_red)
-  if (c->interp_mode == 2) {           // A/B variant: 4 resident blocks per SM (<= 64 registers)
-    if (spec.on) SK_LAUNCH_CELLS(true, 3); else SK_LAUNCH_CELLS(false, 3);
-  } else {
-    if (spec.on) SK_LAUNCH_CELLS(true, 2); else SK_LAUNCH_CELLS(false, 2);
-  }
+  if (spec.on) SK_LAUNCH_CELLS(true, 2); else SK_LAUNCH_CELLS(false, 2);
 #undef SK_LAUNCH_CELLS
   return 0;
 }
@@ -840,50 +835,88 @@ int rollback_speculation(sk_ctx *c) {
   return SK_OK;
 }
 
-// Rules are generated on the device (k_gauss_rules, double-double Newton) and kept for the life of the
-// context; the host long-double generator (sk_plan_gauss_rule) remains as the cross-check in the tests.
-int cached_gauss_rule(sk_ctx *c, int n, double p, std::vector<double> &no, std::vector<double> &wt) {
-  auto key = std::make_pair(n, p);
-  auto it = c->rule_cache.find(key);
-  if (it == c->rule_cache.end()) {
-    std::vector<double> hA(2 * (size_t)n), hB(2 * (size_t)n), hC(2 * (size_t)n), x(n), w(n);
-    if (sk_plan_jacobi_coeffs(n, p, hA.data(), hB.data(), hC.data()) != 0) return -1;
-    double *dA = nullptr, *dNo = nullptr;
-    SkRuleJob *dJob = nullptr;
-    const size_t cb = sizeof(double) * 2 * (size_t)n;
-    bool ok = cudaMalloc((void **)&dA, 3 * cb) == cudaSuccess && cudaMalloc((void **)&dNo, sizeof(double) * 2 * (size_t)n) == cudaSuccess &&
-              cudaMalloc((void **)&dJob, sizeof(SkRuleJob)) == cudaSuccess;
-    if (ok) {
-      SkRuleJob J;
-      J.n = n;
-      J.p = p;
-      J.A = (const sk_dd *)dA;
-      J.B = (const sk_dd *)((char *)dA + cb);
-      J.C = (const sk_dd *)((char *)dA + 2 * cb);
-      J.no = dNo;
-      J.wt = dNo + n;
-      ok = cudaMemcpyAsync((void *)J.A, hA.data(), cb, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
-           cudaMemcpyAsync((void *)J.B, hB.data(), cb, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
-           cudaMemcpyAsync((void *)J.C, hC.data(), cb, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
-           cudaMemcpyAsync(dJob, &J, sizeof(J), cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+// Rules are generated on the device (k_gauss_rules: Newton in double, then double-double) and kept for the life of
+// the context; the host long-double generator (sk_plan_gauss_rule) remains as the cross-check in the tests.  All
+// rules a configuration needs that are not cached yet -- up to four: (m, 2m) x (Legendre, Jacobi) -- are generated by
+// ONE launch (blockIdx.y = rule): their Newton iterations are long serial recurrences, so they cost the time of the
+// largest one, not the sum.
+typedef std::map<std::pair<int, double>, std::pair<std::vector<double>, std::vector<double>>> RuleCache;
+RuleCache &rule_cache() {          // process-wide: every context of a device group, every Session of a fit shares it
+  static RuleCache cache;
+  return cache;
+}
+std::mutex &rule_cache_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+
+int ensure_gauss_rules(sk_ctx *c, const std::vector<std::pair<int, double>> &want) {
+  std::lock_guard<std::mutex> lock(rule_cache_mutex());
+  std::vector<std::pair<int, double>> todo;
+  for (const auto &k : want)
+    if (rule_cache().find(k) == rule_cache().end() && std::find(todo.begin(), todo.end(), k) == todo.end()) todo.push_back(k);
+  if (todo.empty()) return 0;
+  const int nj = (int)todo.size();
+  size_t coef_doubles = 0, out_doubles = 0;
+  int nmax = 0;
+  for (const auto &k : todo) { coef_doubles += 6 * (size_t)k.first; out_doubles += 2 * (size_t)k.first; nmax = std::max(nmax, k.first); }
+  std::vector<double> hcoef(coef_doubles), hout(out_doubles);
+  std::vector<SkRuleJob> jobs(nj);
+  double *dcoef = nullptr, *dout = nullptr;
+  SkRuleJob *djobs = nullptr;
+  bool ok = cudaMalloc((void **)&dcoef, sizeof(double) * coef_doubles) == cudaSuccess &&
+            cudaMalloc((void **)&dout, sizeof(double) * out_doubles) == cudaSuccess &&
+            cudaMalloc((void **)&djobs, sizeof(SkRuleJob) * nj) == cudaSuccess;
+  int rc = 0;
+  if (ok) {
+    size_t co = 0, oo = 0;
+    for (int j = 0; j < nj && rc == 0; ++j) {
+      const int n = todo[j].first;
+      if (sk_plan_jacobi_coeffs(n, todo[j].second, &hcoef[co], &hcoef[co + 2 * (size_t)n], &hcoef[co + 4 * (size_t)n]) != 0) rc = -1;
+      jobs[j].n = n;
+      jobs[j].p = todo[j].second;
+      jobs[j].A = (const sk_dd *)(dcoef + co);
+      jobs[j].B = (const sk_dd *)(dcoef + co + 2 * (size_t)n);
+      jobs[j].C = (const sk_dd *)(dcoef + co + 4 * (size_t)n);
+      jobs[j].no = dout + oo;
+      jobs[j].wt = dout + oo + n;
+      co += 6 * (size_t)n;
+      oo += 2 * (size_t)n;
+    }
+    if (rc == 0) {
+      ok = cudaMemcpyAsync(dcoef, hcoef.data(), sizeof(double) * coef_doubles, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+           cudaMemcpyAsync(djobs, jobs.data(), sizeof(SkRuleJob) * nj, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
       if (ok) {
-        dim3 grid((n + 63) / 64, 1);
-        k_gauss_rules<<<grid, 64, 0, c->stream>>>(dJob, 1);
+        dim3 grid((nmax + 63) / 64, nj);
+        k_gauss_rules<<<grid, 64, 0, c->stream>>>(djobs, nj);
         c->stats.kernel_launches++;
         ok = cudaGetLastError() == cudaSuccess &&
-             cudaMemcpyAsync(x.data(), J.no, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
-             cudaMemcpyAsync(w.data(), J.wt, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+             cudaMemcpyAsync(hout.data(), dout, sizeof(double) * out_doubles, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
              cudaStreamSynchronize(c->stream) == cudaSuccess;
       }
     }
-    if (dA) cudaFree(dA);
-    if (dNo) cudaFree(dNo);
-    if (dJob) cudaFree(dJob);
-    if (!ok) return -2;
+  }
+  if (dcoef) cudaFree(dcoef);
+  if (dout) cudaFree(dout);
+  if (djobs) cudaFree(djobs);
+  if (rc != 0) return rc;
+  if (!ok) return -2;
+  size_t oo = 0;
+  for (int j = 0; j < nj; ++j) {
+    const int n = todo[j].first;
+    std::vector<double> x(hout.begin() + oo, hout.begin() + oo + n), w(hout.begin() + oo + n, hout.begin() + oo + 2 * (size_t)n);
+    oo += 2 * (size_t)n;
     for (int i = 1; i < n; ++i)
       if (!(x[i] > x[i - 1])) return -3;                 // Newton landed on a neighbouring zero
-    it = c->rule_cache.emplace(key, std::make_pair(std::move(x), std::move(w))).first;
+    rule_cache().emplace(todo[j], std::make_pair(std::move(x), std::move(w)));
   }
+  return 0;
+}
+
+int cached_gauss_rule(sk_ctx *c, int n, double p, std::vector<double> &no, std::vector<double> &wt) {
+  if (ensure_gauss_rules(c, {{n, p}}) != 0) return -1;
+  std::lock_guard<std::mutex> lock(rule_cache_mutex());
+  const auto it = rule_cache().find(std::make_pair(n, p));
   no = it->second.first;
   wt = it->second.second;
   return 0;
@@ -1451,6 +1484,13 @@ int sk_rule_set(sk_ctx *c, int32_t m, int32_t k, double p, const double *leg_no1
   if (!given_leg && !given_jac && c->have_rule && c->rule_generated && c->m == m && c->k == k && c->p == p) return SK_OK;
   const int sizes[8] = {m, m, 2 * m, 2 * m, m, m, 2 * m, 2 * m};
   for (int i = 0; i < 8; ++i) c->h_rule[i].assign(sizes[i], 0.0);
+  {
+    std::vector<std::pair<int, double>> want;
+    if (!given_leg) { want.push_back({m, 0.0}); want.push_back({2 * m, 0.0}); }
+    if (p != 0.0 && !given_jac) { want.push_back({m, p}); want.push_back({2 * m, p}); }
+    if (!want.empty() && ensure_gauss_rules(c, want) != 0)
+      return fail(c, SK_ERR_ARG, "Gauss rule generation failed for m=%d p=%g", m, p);
+  }
   if (given_leg) {
     const double *src[4] = {leg_no1, leg_wt1, leg_no2, leg_wt2};
     for (int i = 0; i < 4; ++i) std::copy(src[i], src[i] + sizes[i], c->h_rule[i].begin());
@@ -1747,12 +1787,27 @@ static int logw_host_enqueue_local(sk_ctx *c, double a, double b, const double *
   const long long n_act = c->hi - c->lo;
   CK(c->bufb1.ensure(M1));
   CK(c->bufb2.ensure(M2));
-  CK(cudaMemcpyAsync(c->no1.p, no1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->buf1.p, bufa1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->bufb1.p, bufb1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->no2.p, no2, sizeof(double) * M2, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->buf2.p, bufa2, sizeof(double) * M2, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->bufb2.p, bufb2, sizeof(double) * M2, cudaMemcpyHostToDevice, c->stream));
+  c->need_gen = false;
+  c->pf_valid = false;
+  if (no1) {            // host-evaluated integrands (arbitrary closures: Julia owns f and df)
+    CK(cudaMemcpyAsync(c->no1.p, no1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->buf1.p, bufa1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->bufb1.p, bufb1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->no2.p, no2, sizeof(double) * M2, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->buf2.p, bufa2, sizeof(double) * M2, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->bufb2.p, bufb2, sizeof(double) * M2, cudaMemcpyHostToDevice, c->stream));
+  } else {              // built-in family: both integrands of the integration by parts on the device (df is closed-form)
+    SkPanelSpec S;
+    make_panel_spec(c, a, b, 1, &S);
+    S.variant = 1;      // f + w log w f'   (src/quadrature.jl:192, :210)
+    k_gen_sources<<<nblk(3 * M1, 256), 256, 0, c->stream>>>(S, c->leg_no1.p, c->leg_wt1.p, c->leg_no2.p, c->leg_wt2.p, c->jac_no1.p,
+                                                            c->jac_wt1.p, c->jac_no2.p, c->jac_wt2.p, c->no1.p, c->buf1.p, c->no2.p, c->buf2.p);
+    LAUNCH_CHECK();
+    S.variant = 2;      // w log w f        (:198, :216)
+    k_gen_sources<<<nblk(3 * M1, 256), 256, 0, c->stream>>>(S, c->leg_no1.p, c->leg_wt1.p, c->leg_no2.p, c->leg_wt2.p, c->jac_no1.p,
+                                                            c->jac_wt1.p, c->jac_no2.p, c->jac_wt2.p, c->no1.p, c->bufb1.p, c->no2.p, c->bufb2.p);
+    LAUNCH_CHECK();
+  }
   c->have_sources = true;
   CK(cudaMemsetAsync(c->d_red, 0, sizeof(SkReduceOut), c->stream));
   SkLogwArgs L;
@@ -1823,7 +1878,11 @@ int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, c
                              double i0_coef, double denom, double *max_abs_diff) {
   int rc = subinterval_prologue(c, a, b, o);
   if (rc != SK_OK) return rc;
-  if (!no1 || !bufa1 || !bufb1 || !no2 || !bufa2 || !bufb2 || !max_abs_diff) return fail(c, SK_ERR_ARG, "null pointer");
+  if (!max_abs_diff) return fail(c, SK_ERR_ARG, "null pointer");
+  const bool all_null = !no1 && !bufa1 && !bufb1 && !no2 && !bufa2 && !bufb2;
+  if (!all_null && (!no1 || !bufa1 || !bufb1 || !no2 || !bufa2 || !bufb2)) return fail(c, SK_ERR_ARG, "null pointer");
+  if (all_null && (c->family == SK_SDF_HOST || c->deriv != 0))
+    return fail(c, SK_ERR_STATE, "device-evaluated log-weighted integrands need a built-in density (sk_sdf_builtin, deriv_index 0)");
   if (a != 0.0) return fail(c, SK_ERR_ARG, "the integration-by-parts branch applies to a == 0 only");
   const long long n_act = c->hi - c->lo;
   rc = logw_host_enqueue_local(c, a, b, no1, bufa1, bufb1, no2, bufa2, bufb2, o, i0_coef, denom);

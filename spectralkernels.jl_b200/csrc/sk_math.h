@@ -47,6 +47,8 @@ struct SkPanelSpec {     // updatequadbufs! (src/quadrature.jl:49-95) for one su
   int weight_in_f;       // else-branch of src/quadrature.jl:240-247: integrand is w^p [log w] f(w)
   int logw;
   int family, deriv, nparam;
+  int variant;           // integrand: 0 f;  1 f + w log(w) f'(w);  2 w log(w) f(w)   (the two integrands of the
+  int _pad;              //   integration by parts of the log-weighted origin sub-interval, src/quadrature.jl:192, :198)
   double p;
   double jac_scale;      // bmad2[0]^(p+1), src/quadrature.jl:69,73
   double params[SK_NPARAM_MAX];
@@ -162,6 +164,29 @@ SK_HD double sk_sdf_eval(int family, int deriv, const double *q, double w) {
   return 0.0;
 }
 
+// dS/dw of the density itself (the `df` keyword of AdaptiveKernelConfig, needed by logw = true: src/quadrature.jl:192)
+SK_HD double sk_sdf_dw(int family, const double *q, double w) {
+  if (family == 1) {
+    const double phi = q[0], rho = q[1], nu = q[2], d = q[3];
+    const double base = sk_add(sk_mul(rho, rho), sk_mul(w, w));
+    const double ex = -nu - d / 2;
+    return phi * ex * pow(base, ex - 1.0) * 2.0 * w;
+  }
+  if (family == 2) {
+    const double phi = q[0], al = q[1];
+    return -al * (w > 0 ? 1.0 : (w < 0 ? -1.0 : 0.0)) * phi * exp(-al * fabs(w));
+  }
+  return 0.0;
+}
+// the integrand the panel spec asks for (SkPanelSpec::variant)
+SK_HD double sk_integrand(const SkPanelSpec &S, double w) {
+  const double f = sk_sdf_eval(S.family, S.deriv, S.params, w);
+  if (S.variant == 0) return f;
+  const double wl = w * log(w);
+  if (S.variant == 1) return f + wl * sk_sdf_dw(S.family, S.params, w);
+  return wl * f;
+}
+
 // node and (real) strength of source `idx` of rule `rule` (0: m nodes per sub-panel, 1: 2m),
 // following updatequadbufs! operation by operation (src/quadrature.jl:61-92)
 SK_HD void sk_gen_source(const SkPanelSpec &S, int rule, long long idx, const double *leg_no, const double *leg_wt,
@@ -173,10 +198,10 @@ SK_HD void sk_gen_source(const SkPanelSpec &S, int rule, long long idx, const do
   double no, buf;
   if (S.origin_jacobi && i == 0) {
     no = sk_add(sk_mul(bmad2, jac_no[j]), bpad2);                                  // :68,72
-    buf = sk_mul(sk_mul(jac_wt[j], S.jac_scale), sk_sdf_eval(S.family, S.deriv, S.params, no));  // :69,73
+    buf = sk_mul(sk_mul(jac_wt[j], S.jac_scale), sk_integrand(S, no));  // :69,73
   } else {
     no = sk_add(sk_mul(bmad2, leg_no[j]), bpad2);                                  // :85,89
-    const double f = sk_sdf_eval(S.family, S.deriv, S.params, no);
+    const double f = sk_integrand(S, no);
     const double wb = sk_mul(leg_wt[j], bmad2);
     if (S.weight_in_f) {
       // integrand w -> w^p * (logw ? log(w) : 1) * f(w), quadrature rule power 0 (src/quadrature.jl:242, :86)

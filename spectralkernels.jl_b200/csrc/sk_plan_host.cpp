@@ -12,6 +12,9 @@
 
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 typedef __float128 q128;
@@ -66,7 +69,7 @@ static void cheb_fit_series(int n, F f, std::vector<q128> &c) {
   c[0] /= 2;
 }
 
-int sk_plan_make_es(int w, SkEsPlan *out) {
+static int sk_plan_make_es_fit(int w, SkEsPlan *out) {
   if (w < 4 || w > SK_WMAX || (w & 1)) return -1;
   std::memset(out, 0, sizeof(*out));
   out->w = w;
@@ -230,7 +233,7 @@ static void bessel_miller_q(int numax, q128 z, q128 *J) {
   for (int n = 0; n <= numax; ++n) J[n] = keep[n] / sum;
 }
 
-int sk_plan_bessel_table(int numax, int nint, int nc, double *tab) {
+static int sk_plan_bessel_table_fit(int numax, int nint, int nc, double *tab) {
   if (numax < 0 || nint < 1 || nc < 2 || !tab) return -1;
   for (int nu = 0; nu <= numax; ++nu)
     for (int i = 0; i < nint; ++i) {
@@ -242,5 +245,39 @@ int sk_plan_bessel_table(int numax, int nint, int nc, double *tab) {
       }, mono);
       for (int q = 0; q < nc; ++q) tab[((size_t)nu * nint + i) * nc + q] = (double)mono[q];
     }
+  return 0;
+}
+
+// The fits above run in __float128 (~20 ms for a plan, more for the Bessel table): done once per process and width,
+// not once per context -- a device group opens one context per GPU.
+int sk_plan_make_es(int w, SkEsPlan *out) {
+  static std::mutex mu;
+  static std::map<int, SkEsPlan> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(w);
+  if (it == cache.end()) {
+    SkEsPlan P;
+    const int rc = sk_plan_make_es_fit(w, &P);
+    if (rc != 0) return rc;
+    it = cache.emplace(w, P).first;
+  }
+  *out = it->second;
+  return 0;
+}
+
+int sk_plan_bessel_table(int numax, int nint, int nc, double *tab) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int>, std::vector<double>> cache;
+  if (numax < 0 || nint < 1 || nc < 2 || !tab) return -1;
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_tuple(numax, nint, nc);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    std::vector<double> t((size_t)(numax + 1) * nint * nc);
+    const int rc = sk_plan_bessel_table_fit(numax, nint, nc, t.data());
+    if (rc != 0) return rc;
+    it = cache.emplace(key, std::move(t)).first;
+  }
+  std::memcpy(tab, it->second.data(), sizeof(double) * it->second.size());
   return 0;
 }

@@ -75,18 +75,42 @@ SK_HD sk_dd sk_jacobi_deriv_dd(const SkRuleJob &J, sk_dd x, sk_dd pn, sk_dd pm) 
   return dd_div(dd_add(t1, t2), dd_mul(s, omx2));
 }
 
+// P_n and P_{n-1} in plain double (for the first Newton steps only)
+SK_HD void sk_jacobi_eval_d(const SkRuleJob &J, double x, double *pn, double *pm) {
+  double p0 = 1.0, p1 = ((J.p + 2.0) * x - J.p) * 0.5;
+  for (int k = 1; k < J.n; ++k) {
+    const double p2 = (J.A[k].hi * x + J.B[k].hi) * p1 - J.C[k].hi * p0;
+    p0 = p1;
+    p1 = p2;
+  }
+  *pn = p1;
+  *pm = p0;
+}
+
 SK_HD void sk_gauss_node(const SkRuleJob &J, int i) {
   if (J.n == 1 && J.p == 0.0) { J.no[0] = 0.0; J.wt[0] = 2.0; return; }
   const int k = J.n - i;                                   // counted from x = +1 (ascending output)
   const double th = (2.0 * k - 0.5) * 3.141592653589793 / (2.0 * J.n + J.p + 1.0);
-  sk_dd x = dd_make(cos(th));
+  // Newton in plain double down to rounding level (a double-double evaluation of the recurrence costs ~8x more) ...
+  double xd = cos(th);
+  const double nn = (double)J.n, sp = 2.0 * nn + J.p;
+  for (int it = 0; it < 6; ++it) {
+    double pn, pm;
+    sk_jacobi_eval_d(J, xd, &pn, &pm);
+    const double dp = (nn * (-J.p - sp * xd) * pn + 2.0 * nn * (nn + J.p) * pm) / (sp * (1.0 - xd * xd));
+    const double dx = pn / dp;
+    xd -= dx;
+    if (fabs(dx) <= 1e-13 * (1.0 + fabs(xd))) break;
+  }
+  // ... then in double-double: each step squares the error, so one or two steps reach ~1e-30
+  sk_dd x = dd_make(xd);
   for (int it = 0; it < 8; ++it) {
     sk_dd pn, pm;
     sk_jacobi_eval_dd(J, x, &pn, &pm);
     const sk_dd dp = sk_jacobi_deriv_dd(J, x, pn, pm);
     const sk_dd dx = dd_div(pn, dp);
     x = dd_add(x, dd_neg(dx));
-    if (fabs(dx.hi) <= 1e-25 * (1.0 + fabs(x.hi))) break;
+    if (fabs(dx.hi) <= 1e-13 * (1.0 + fabs(x.hi))) break;    // the next correction would be ~dx^2 < 1e-26
   }
   sk_dd pn, pm;
   sk_jacobi_eval_dd(J, x, &pn, &pm);

@@ -231,6 +231,26 @@ def test_singularity_derivative_logw(sk, golden):
     assert np.max(np.abs(v2 - o2)) <= 1e-11 * k0
 
 
+def test_logw_origin_device_integrands_match_host_evaluation(sk, golden):
+    """The two integrands of the integration by parts (src/quadrature.jl:192, :198) evaluated on the device for a
+    shipped family (its dS/dw is closed-form) against the host-evaluated ones (any closure), dim = 1 and dim = 2."""
+    parms = tuple(golden["matern_parms"])
+    xs = golden["sing_r"][5::7]
+    for dim in (1, 2):
+        S = sk.Matern(*parms, d=dim)
+        out = []
+        for df in (S.dw, lambda w: S.dw(w)):               # bound method: device integrands; plain closure: host
+            cfg = sk.AdaptiveKernelConfig(S, df=df, alpha=0.5, logw=True, dim=dim)
+            if dim == 2:
+                cfg.engine.set_hankel_mode(1)
+            k0 = 1.0
+            tr = []
+            v, _ = sk.kernel_values(cfg, xs, k0=k0, param_derivative=True, trace=tr)
+            out.append((v, tr))
+        assert np.max(np.abs(out[0][0] - out[1][0])) <= 1e-12 * max(1.0, float(np.max(np.abs(out[1][0]))))
+        assert _trace_key(out[0][1]) == _trace_key(out[1][1])
+
+
 def test_sdf_param_derivatives_and_target_reuse(sk, golden):
     """test/derivatives/sdf_params.jl (enabled upstream): dK/d(phi, rho, nu) with the device generators of the
     Matern parameter derivatives; the three runs reuse the uploaded / sorted lags (BASELINE config 4 shape)."""
