@@ -16,7 +16,9 @@ value : whole-job K(r) evals/s with the distances already resident in HBM (devic
 e2e   : the same metric through the public kernel_values call with HOST (pinned) buffers: the H2D copy
         of the distances and the D2H copy of values and errors are inside the timed region.
 N > 1 : every rank evaluates its own batch of n distances (weak scaling); the ranks run ONE adaptive
-        loop in lock step through scalar NCCL all-reduces (spectralkernels.jl_b200/sharded.py).
+        loop in lock step through scalar collectives (spectralkernels.jl_b200/sharded.py): single-warp exchange
+        kernels over NVLink peer-mapped mailboxes by default, SK_COMM_TRANSPORT=nccl for in-library NCCL
+        all-reduces, SK_COMM=torch for torch.distributed (A/B references).
 """
 from __future__ import annotations
 
@@ -86,20 +88,54 @@ def make_distances(n: int, rank: int) -> np.ndarray:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and clock-event (throttle) reasons DURING the timed region.  NVML is polled from a thread every 2 ms
+    (the timed region of the default run is 10-30 ms: `nvidia-smi -lms` would deliver at most one sample); nvidia-smi
+    is only the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, cuda_index: int):
+        self.idx, self.rows, self.proc, self.h, self.nv = cuda_index, [], None, None, None
+        self.sm, self.mask, self.mx, self.run = [], 0, None, False
+        if cuda_index < 0:
+            return
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                self.h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(cuda_index).uuid))
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                phys = int(vis.split(",")[cuda_index]) if vis and vis.split(",")[cuda_index].isdigit() else cuda_index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.h = self.nv = None
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         if self.idx < 0:
             return
+        if self.nv is not None:
+            self.run = True
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -110,8 +146,22 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.run = False
+            self.th.join(timeout=1)
+            nv, names = self.nv, []
+            for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                              ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                              ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                              ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                              ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown)):
+                if self.mask & int(bit):
+                    names.append(name)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(names), "samples": len(self.sm), "how": "NVML polled every 2 ms during the timed steps"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"] if self.idx >= 0 else [],
+                    "samples": 0}
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -127,7 +177,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "how": "nvidia-smi -lms 100"}
 
 
 def oracle_cpu_run(n_sample: int, steps: int, warmup: int):
@@ -357,9 +407,12 @@ def run(args):
             "config": {"workload": WORKLOAD,
                        "n_per_gpu": nloc, "k0": "passed (=1.0) in both arms", "nufft_eps": 1e-15,
                        "l2": "inputs + work arrays (>1 GB per step) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": ("target-sharded, scalar NCCL all-reduces only ("
-                                       + ("in-library, on the compute stream" if getattr(comm, "fused", False) else "torch.distributed")
-                                       + ")") if world > 1 else "single GPU",
+                       "parallelism": ("target-sharded, scalar collectives only: "
+                                       + {"peer": "single-warp exchange kernels over NVLink peer-mapped mailboxes "
+                                                  "(k_peer_exchange) on the compute stream, no NCCL on the data path",
+                                          "nccl": "in-library NCCL all-reduces on the compute stream"}.get(
+                                              getattr(comm, "mode", ""), "torch.distributed all-reduces")
+                                       ) if world > 1 else "single GPU",
                        "cpu_affinity": "each rank pinned to its GPU's local CPUs (NVML)" if numa_bound else "default",
                        "panels": [(t["a"], t["b"], t["hi_before"], t["hi_after"]) for t in main_["trace"] if t["kind"] == "panel"]},
             "e2e": {"value": total * K / (e2e_ms * 1e-3), "unit": "evals/s", "ms_per_step": e2e_ms / K,

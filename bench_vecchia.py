@@ -126,9 +126,12 @@ def main():
     setup_warm = time.perf_counter() - ts
     if dist is not None:
         dist.barrier()
+    per = []
     t0 = time.perf_counter()
     for i, b in enumerate(mine):
+        t1 = time.perf_counter()
         k0 = run(hp[b], True, i & 1)                      # the pair list is resident: only the panel loop and the copy
+        per.append(1e3 * (time.perf_counter() - t1))
         # (a consumer -- Vecchia's sparse Cholesky -- would take outs[(i - 1) & 1] here, complete since the wait
         #  inside sk_results_get_async two calls back / the final results_wait)
     eng.results_wait()
@@ -147,6 +150,11 @@ def main():
                                                    f"{args.batch} hyperparameter vectors (Matern, dim={args.dim}, alpha={args.alpha})",
                           "metric": "pair evaluations/s (all GPUs)", "value": args.batch * npairs / dt, "n_gpus": world,
                           "ms_per_vector_per_gpu": 1e3 * dt / len(mine), "seconds": dt, "vectors_per_gpu": len(mine),
+                          # a vector whose octave groups need an FFT size this process has not used yet pays cuFFT's plan
+                          # creation / lazy module load once (tens of ms, up to ~0.6 s for a new kernel family): the median
+                          # is the steady state of a fitting loop, the mean above includes those first uses
+                          "ms_per_vector_median": float(np.median(per)), "ms_per_vector_max": float(np.max(per)),
+                          "value_steady_state": npairs * world / (1e-3 * float(np.median(per))),
                           "n_pairs": npairs, "n_hankel_last": st["n_hankel"], "subintervals_last": st["n_subintervals"],
                           "setup_ms_first_call": 1e3 * setup_first, "setup_plus_one_vector_ms_warm": 1e3 * setup_warm,
                           "scaling": "strong (fixed batch)", "result_copies": "sync" if args.sync_copies else "async (second stream)",

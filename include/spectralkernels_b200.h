@@ -169,6 +169,26 @@ int sk_comm_allreduce(sk_ctx *ctx, double *vals, int32_t n, int32_t op);
 int sk_comm_idle(sk_ctx *ctx, int32_t which);
 int sk_comm_last(sk_ctx *ctx, double *max_abs_diff, double *r_stop, int64_t *n_active_lb);
 
+/* ---- the same collectives over NVLink / NVSwitch PEER MEMORY instead of NCCL ---------------------------------------
+ * Every rank owns a 2 KB mailbox in its HBM which all its peers map through CUDA IPC.  A collective point is then ONE
+ * single-warp kernel on the compute stream behind the kernel that produced the local scalars (k_peer_exchange): it packs
+ * them, stores 64 bytes into every peer's mailbox, waits (bounded: SK_PEER_TIMEOUT_S, default 20 s) for the peers'
+ * words in its own mailbox, reduces them and writes the result into pinned host memory -- no NCCL launch, no pack
+ * kernel, no D2H copy; the host still synchronises once per sub-interval, exactly as on one GPU.  With mailboxes
+ * attached no NCCL communicator is needed at all (sk_comm_init may be skipped); every sk_subinterval*, sk_converge_scan,
+ * sk_comm_idle, sk_comm_allreduce and the early range reduction of sk_targets_set then use the mailboxes.
+ *   sk_comm_peer_export  allocate this rank's mailbox, return its 64-byte cudaIpcMemHandle_t
+ *   (the host all-gathers the handles: torch.distributed / MPI / a file)
+ *   sk_comm_peer_attach  handles = nranks x 64 bytes in rank order; at most 16 ranks, all on one node
+ *   sk_comm_allgather    out[r * k + i] = value i (k <= 7) of rank r; synchronous (the once-per-call range / counts)
+ * sk_comm_peer_selftest runs the protocol with the ranks emulated as blocks of one cooperative launch on ONE device
+ * (out5: per rank maxbits, err, rbits, n_lb, status | epoch << 8) -- a test hook, not part of the path. */
+int sk_comm_peer_export(sk_ctx *ctx, void *handle64);
+int sk_comm_peer_attach(sk_ctx *ctx, const void *handles, int32_t rank, int32_t nranks);
+int sk_comm_allgather(sk_ctx *ctx, const double *vals, int32_t k, double *out);
+int sk_comm_peer_selftest(sk_ctx *ctx, int32_t nranks, int32_t rounds, const uint64_t *maxbits_in, const uint64_t *rbits_in,
+                          const int64_t *top_in, int64_t lo, uint64_t *out5);
+
 /* pinned host memory for callers that want full PCIe rate (Julia: unsafe_wrap the pointer) */
 int sk_host_alloc(size_t bytes, void **out);
 int sk_host_free(void *ptr);

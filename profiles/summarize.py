@@ -34,7 +34,7 @@ def launches(src, dst):
     rows = list(csv.DictReader(lines))
     names = [(r["Kernel Name"], float(r["Metric Value"].replace(",", ""))) for r in rows
              if r["Metric Name"] == "gpu__time_duration.sum"]
-    starts = [i for i, (n, _) in enumerate(names) if "k_make_keys" in n]
+    starts = [i for i, (n, _) in enumerate(names) if "k_k8_stats" in n or "k_make_keys" in n]
     out = [f"source: {src}  ({len(names)} launches captured, {len(starts)} kernel_values steps)",
            "ncu --metrics gpu__time_duration.sum --clock-control none: cold-cache, serialised launches -- compare SHARES",
            ""]
@@ -69,5 +69,25 @@ def kernel(src, dst):
     print("\n".join(out))
 
 
+def traffic(src, dst, units="10000000"):
+    """profiles/r2_traffic.json: DRAM bytes and executed FP64 flops per launch of k_interp_cells (bench.py reads it)."""
+    import json
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(raw.splitlines()))
+    hdr, rows = r[0], [x for x in r[2:] if "k_interp_cells" in x[r[0].index("Kernel Name")]]
+    f = lambda row, m: float(row[hdr.index(m)].replace(",", ""))
+    n, u = len(rows), float(units)
+    dram = sum(f(x, "dram__bytes_read.sum") + f(x, "dram__bytes_write.sum") for x in rows) / n
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[r[1][hdr.index("dram__bytes_read.sum")]]
+    fl = sum(2 * f(x, "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum")
+             + f(x, "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum")
+             + f(x, "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum") for x in rows) / n
+    out = {"interp_cells_dram_bytes_per_launch": dram * scale, "executed_flops_per_unit": fl / u, "launches_captured": n,
+           "units_per_launch": u, "source": f"ncu --set full --clock-control none capture of bench.py ({src.split('/')[-1]}), "
+                                            "dram__bytes_read.sum + dram__bytes_write.sum averaged over the captured launches"}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(out)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "kernel": kernel, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

@@ -79,6 +79,10 @@ SIGNATURES = {
     "sk_comm_allreduce": (c_int, [c_void_p, _dp, c_int32, c_int32]),
     "sk_comm_idle": (c_int, [c_void_p, c_int32]),
     "sk_comm_last": (c_int, [c_void_p, _dp, _dp, POINTER(c_int64)]),
+    "sk_comm_peer_export": (c_int, [c_void_p, c_void_p]),
+    "sk_comm_peer_attach": (c_int, [c_void_p, c_void_p, c_int32, c_int32]),
+    "sk_comm_allgather": (c_int, [c_void_p, _dp, c_int32, _dp]),
+    "sk_comm_peer_selftest": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "sk_host_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "sk_host_free": (c_int, [c_void_p]),
     "sk_nufft1d3": (c_int, [c_void_p, c_int64, _dp, _dp, c_int64, _dp, _dp, c_double]),
@@ -268,6 +272,37 @@ class Session:
 
     def comm_idle(self, which: int):
         self._ck(self._L.sk_comm_idle(self._h, int(which)))
+
+    # -- the same collectives over peer-mapped mailboxes (NVLink / NVSwitch; k_peer_exchange) -------------
+    def comm_peer_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self._L.sk_comm_peer_export(self._h, buf))
+        return buf.raw
+
+    def comm_peer_attach(self, handles, rank: int, nranks: int):
+        blob = b"".join(bytes(h) for h in handles)
+        if len(blob) != 64 * int(nranks):
+            raise ValueError("one 64-byte handle per rank")
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        self._ck(self._L.sk_comm_peer_attach(self._h, buf, int(rank), int(nranks)))
+        self.comm_size = int(nranks)
+
+    def comm_allgather(self, vals, nranks: int):
+        a = _f64(list(vals)).copy()
+        out = np.empty(a.size * int(nranks), dtype=np.float64)
+        self._ck(self._L.sk_comm_allgather(self._h, _p(a), a.size, _p(out)))
+        return out.reshape(int(nranks), a.size).tolist()
+
+    def comm_peer_selftest(self, maxbits, rbits, top, lo: int, rounds: int = 3):
+        """the exchange protocol with len(maxbits) ranks emulated on this one device (test hook)"""
+        n = len(maxbits)
+        mb = np.ascontiguousarray(maxbits, dtype=np.uint64)
+        rb = np.ascontiguousarray(rbits, dtype=np.uint64)
+        tp = np.ascontiguousarray(top, dtype=np.int64)
+        out = np.zeros(5 * n, dtype=np.uint64)
+        self._ck(self._L.sk_comm_peer_selftest(self._h, n, int(rounds), mb.ctypes.data, rb.ctypes.data, tp.ctypes.data, int(lo),
+                                               out.ctypes.data))
+        return out.reshape(n, 5)
 
     def comm_last(self):
         mx, r, n = c_double(), c_double(), c_int64()

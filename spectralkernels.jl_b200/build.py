@@ -23,7 +23,7 @@ GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++")
 CUDA_HOME = os.path.dirname(os.path.dirname(os.path.realpath(NVCC)))
 
 SOURCES = ["sk_api.cu", "sk_plan_host.cpp"]
-HEADERS = ["sk_math.h", "sk_plan.h", "sk_host_util.h", "sk_kernels.cuh", "sk_hankel.h", "sk_hankel.cuh", "sk_rules.cuh",
+HEADERS = ["sk_math.h", "sk_plan.h", "sk_host_util.h", "sk_kernels.cuh", "sk_hankel.h", "sk_hankel.cuh", "sk_rules.cuh", "sk_k8.h", "sk_k8.cuh",
            os.path.join(ROOT, "include", "spectralkernels_b200.h")]
 
 

@@ -203,6 +203,13 @@ struct sk_ctx {
   // target-sharded multi-GPU: scalar NCCL all-reduces on the context's stream
   ncclComm_t comm = nullptr;
   int comm_rank = 0, comm_size = 1;
+  // ... or as single-warp exchange kernels over peer-mapped mailboxes (sk_comm_peer_*; k_peer_exchange)
+  int peer_n = 0;                            // ranks attached (0: no peer exchange)
+  unsigned long long *peer_box = nullptr;    // this rank's mailbox (device memory, exported through CUDA IPC)
+  unsigned long long *peer_map[SK_PEER_MAX] = {nullptr};   // the peers' mailboxes as mapped here
+  unsigned long long peer_epoch = 0;
+  SkPeerOut *peer_out[3] = {nullptr, nullptr, nullptr};    // pinned: sub-interval / scan, early range, host values
+  double peer_timeout_s = 20.0;
   SkGlobalA *d_ga = nullptr;
   SkGlobalB *d_gb = nullptr;
   double *d_hv = nullptr;
@@ -289,8 +296,49 @@ int flush_commit(sk_ctx *c);
 // err != 0: this rank could not evaluate the sub-interval (allocation failure, geometry out of range, ...).  It still
 // joins the collective -- its peers are already waiting in it -- with neutral values and the error word set, so that
 // every rank sees the failure and raises instead of blocking in the all-reduce for ever.
+inline bool sharded(const sk_ctx *c) { return c->comm != nullptr || c->peer_n > 0; }
+void peer_release(sk_ctx *c) {
+  if (c->peer_n > 0 || c->peer_box) {
+    cudaStreamSynchronize(c->stream);
+    for (int r = 0; r < SK_PEER_MAX; ++r) {
+      if (c->peer_map[r] && c->peer_map[r] != c->peer_box) cudaIpcCloseMemHandle(c->peer_map[r]);
+      c->peer_map[r] = nullptr;
+    }
+    if (c->peer_box) cudaFree(c->peer_box);
+    c->peer_box = nullptr;
+    c->peer_n = 0;
+    c->peer_epoch = 0;
+  }
+}
+
+// one exchange over the peer mailboxes (see k_peer_exchange): enqueued on the compute stream, the reduced words land in
+// pinned host memory (slot 0: sub-interval / scan scalars, 1: the early key range, 2: host values)
+int peer_exchange(sk_ctx *c, int slot, int kind, int idle, int err, long long lo, const unsigned long long *imm, int nw,
+                  int raw_op, const SkK8State *k8 = nullptr) {
+  SkPeerArgs a;
+  std::memset(&a, 0, sizeof(a));
+  for (int r = 0; r < c->peer_n; ++r) a.box[r] = c->peer_map[r];
+  a.rank = c->comm_rank;
+  a.n = c->peer_n;
+  a.epoch = ++c->peer_epoch;
+  a.timeout_ns = (unsigned long long)(c->peer_timeout_s * 1e9);
+  a.kind = kind; a.idle = idle; a.err = err; a.raw_op = raw_op; a.lo = lo; a.nw = nw;
+  for (int i = 0; i < 7; ++i) a.imm[i] = (imm && i < nw) ? imm[i] : 0ull;
+  k_peer_exchange<<<1, 32, 0, c->stream>>>(a, c->d_red, k8, c->peer_out[slot]);
+  LAUNCH_CHECK();
+  return SK_OK;
+}
+int peer_check(sk_ctx *c, int slot) {   // after the stream synchronisation
+  if (c->peer_n > 0 && c->peer_out[slot]->status) {
+    c->peer_out[slot]->status = 0;
+    return fail(c, SK_ERR_STATE, "peer exchange timed out: a rank did not reach the collective point within %.0f s", c->peer_timeout_s);
+  }
+  return SK_OK;
+}
+
 int comm_reduce_a(sk_ctx *c, int idle, int err = 0) {
-  if (!c->comm) return SK_OK;
+  if (!sharded(c)) return SK_OK;
+  if (c->peer_n > 0) return peer_exchange(c, 0, SK_PX_A, idle, err, c->lo, nullptr, 0, 0);
   NcclApi *N = nccl_api();
   k_pack_global_a<<<1, 1, 0, c->stream>>>(c->d_red, c->d_ga, (idle || err) ? 1 : 0, err);
   LAUNCH_CHECK();
@@ -302,7 +350,8 @@ int comm_reduce_a(sk_ctx *c, int idle, int err = 0) {
 // the scan's (stopping distance, active count) together, so they travel together; the scan that follows then needs
 // no collective at all.  Idle ranks contribute neutral values.
 int comm_reduce_ab(sk_ctx *c, int idle, int err) {
-  if (!c->comm) return SK_OK;
+  if (!sharded(c)) return SK_OK;
+  if (c->peer_n > 0) return peer_exchange(c, 0, SK_PX_AB, idle, err, c->lo, nullptr, 0, 0);
   NcclApi *N = nccl_api();
   k_pack_global_a<<<1, 1, 0, c->stream>>>(c->d_red, c->d_ga, (idle || err) ? 1 : 0, err);
   LAUNCH_CHECK();
@@ -321,7 +370,11 @@ int comm_reduce_ab(sk_ctx *c, int idle, int err) {
 // collective B (after a scan): MAX of the stopping distance, SUM of the per-rank lower bounds of the
 // number of targets that stay active.  from_red: take the values from d_red (lo = first index of the panel).
 int comm_reduce_b(sk_ctx *c, bool from_red, unsigned long long rbits, long long n_lb) {
-  if (!c->comm) return SK_OK;
+  if (!sharded(c)) return SK_OK;
+  if (c->peer_n > 0) {
+    const unsigned long long imm[2] = {rbits, (unsigned long long)n_lb};
+    return peer_exchange(c, 0, from_red ? SK_PX_B_RED : SK_PX_B_IMM, 0, 0, c->lo, imm, 2, 0);
+  }
   NcclApi *N = nccl_api();
   if (from_red) k_pack_global_b_from_red<<<1, 1, 0, c->stream>>>(c->d_red, c->lo, c->d_gb);
   else k_pack_global_b<<<1, 1, 0, c->stream>>>(c->d_gb, rbits, n_lb);
@@ -333,16 +386,19 @@ int comm_reduce_b(sk_ctx *c, bool from_red, unsigned long long rbits, long long 
   CK(cudaMemcpyAsync(&c->h_scal->gb, c->d_gb, sizeof(SkGlobalB), cudaMemcpyDeviceToHost, c->stream));
   return SK_OK;
 }
+const SkGlobalA &global_a(const sk_ctx *c) { return c->peer_n > 0 ? c->peer_out[0]->ga : c->h_scal->ga; }
+const SkGlobalB &global_b(const sk_ctx *c) { return c->peer_n > 0 ? c->peer_out[0]->gb : c->h_scal->gb; }
 void comm_take_a(sk_ctx *c, unsigned int *fl, double *mx) {   // after the stream sync
-  if (!c->comm) return;
-  const SkGlobalA &g = c->h_scal->ga;
+  if (!sharded(c)) return;
+  const SkGlobalA &g = global_a(c);
   std::memcpy(mx, &g.maxbits, sizeof(double));
   *fl = (g.nan1 ? SK_FLAG_NAN1 : 0u) | (g.nan2 ? SK_FLAG_NAN2 : 0u) | (g.nand ? SK_FLAG_NAND : 0u);
 }
 void comm_take_b(sk_ctx *c) {
-  if (!c->comm) return;
-  std::memcpy(&c->g_r_stop, &c->h_scal->gb.rbits, sizeof(double));
-  c->g_n_lb = c->h_scal->gb.n_lb;
+  if (!sharded(c)) return;
+  const SkGlobalB &g = global_b(c);
+  std::memcpy(&c->g_r_stop, &g.rbits, sizeof(double));
+  c->g_n_lb = g.n_lb;
 }
 
 int width_from_eps(double eps) {
@@ -760,12 +816,12 @@ int transform_and_stage_enqueue(sk_ctx *c, double a, double b, const sk_subinter
     // does this sub-interval speculate (first of its panel, NUFFT branch, scan arguments given)?  Decided from the
     // arguments and the GLOBAL active count only, so that every rank -- also an idle one -- issues the same collectives
     const long long M2 = 2LL * c->m * c->k, n_cut = c->n_act_global > 0 ? c->n_act_global : (c->hi - c->lo);
-    c->pend_ab = c->comm != nullptr && o->kernel != SK_KERNEL_BESSEL && (M2 * n_cut > (1LL << 18)) && n_cut > 1 &&
+    c->pend_ab = sharded(c) && o->kernel != SK_KERNEL_BESSEL && (M2 * n_cut > (1LL << 18)) && n_cut > 1 &&
                  o->speculate != nullptr && c->panel_subs == 0 && o->speculate->criteria >= 0 && o->speculate->criteria <= 2;
   }
   const int rc = transform_and_stage_enqueue_local(c, a, b, o);
   c->pend_rc = rc;
-  if (!c->comm) return rc;
+  if (!sharded(c)) return rc;
   // sharded run: a rank that failed locally still joins the collective (its peers are waiting in it)
   const std::string msg = c->errmsg;
   const int rcc = c->pend_ab ? comm_reduce_ab(c, 0, rc != SK_OK) : comm_reduce_a(c, 0, rc != SK_OK);
@@ -778,9 +834,11 @@ int transform_and_stage_enqueue(sk_ctx *c, double a, double b, const sk_subinter
 int transform_and_stage_finish(sk_ctx *c, double *max_abs_diff, unsigned int *flags_out) {
   const long long n_act = c->hi - c->lo;
   CK(cudaStreamSynchronize(c->stream));
-  if (c->comm) {
+  if (sharded(c)) {
     if (c->pend_rc != SK_OK) return c->pend_rc;                     // this rank's own failure (message already set)
-    if (c->h_scal->ga.err) return fail(c, SK_ERR_STATE, "another rank failed in this sub-interval");
+    const int prc = peer_check(c, 0);
+    if (prc != SK_OK) return prc;
+    if (global_a(c).err) return fail(c, SK_ERR_STATE, "another rank failed in this sub-interval");
   }
   if (c->pend_timed) {
     float ms = 0;
@@ -793,7 +851,7 @@ int transform_and_stage_finish(sk_ctx *c, double *max_abs_diff, unsigned int *fl
   double mx;
   std::memcpy(&mx, &c->h_scal->red.maxbits, sizeof(double));
   comm_take_a(c, &fl, &mx);                 // sharded run: the maximum and the NaN flags over all ranks
-  if (c->comm && c->pend_ab) comm_take_b(c);
+  if (sharded(c) && c->pend_ab) comm_take_b(c);
   if (fl & SK_FLAG_NAND) mx = std::nan("");
   *max_abs_diff = mx;
   c->g_max_abs = mx;
@@ -974,7 +1032,8 @@ int targets_early_range(sk_ctx *c, double *r_lo, double *r_hi) {
   CK(cudaEventSynchronize(c->k8_ev));
   unsigned long long kmin_inv, kmax, bad;
   if (c->early_global) {
-    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(c->h_scal->hv);
+    const unsigned long long *w = c->peer_n > 0 ? c->peer_out[1]->words
+                                                : reinterpret_cast<const unsigned long long *>(c->h_scal->hv);
     kmin_inv = w[0]; kmax = w[1]; bad = w[2];
   } else {
     const SkK8State &k8 = c->h_scal->k8;
@@ -1038,11 +1097,16 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   // (a rank of a process-per-GPU run does not know the global distance range yet: no early prefetch there; a device
   //  group issues it for all its devices once every chunk's range is in: sk_group_targets_set)
   const bool early = c->prefetch_on && c->have_rule && c->family != SK_SDF_HOST && c->plan.w > 0 &&
-                     (c->in_group || c->comm || n_in >= 65536);
+                     (c->in_group || sharded(c) || n_in >= 65536);
   c->early_pending = early;
   c->early_global = false;
   if (early) {
-    if (c->comm) {
+    if (c->peer_n > 0) {
+      // (peer mailboxes: the same 3-word MAX as one exchange kernel; the result lands in pinned memory, slot 1)
+      int rcx = peer_exchange(c, 1, SK_PX_RANGE, 0, 0, 0, nullptr, 0, 0, st);
+      if (rcx != SK_OK) return rcx;
+      c->early_global = true;
+    } else if (c->comm) {
       // process-per-GPU run: the panels are built from the GLOBAL distance range, so the ranks reduce their key
       // ranges here (one 3-word MAX all-reduce behind the first pass; every rank takes this branch or none does:
       // the condition above holds no rank-local quantity)
@@ -1235,6 +1299,8 @@ int sk_ctx_destroy(sk_ctx *c) {
   c->hk_tab.release(); c->hk_vals.release(); c->hk_cheb.release(); c->hk_loc.release(); c->hk_lam1.release(); c->hk_lam2.release();
   c->hk_lev.release(); c->hk_groups.release(); c->hk_grid.release(); c->hk_part.release(); c->hk_modes.release();
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
+  peer_release(c);
+  for (int i = 0; i < 3; ++i) if (c->peer_out[i]) cudaFreeHost(c->peer_out[i]);
   if (c->d_ga) cudaFree(c->d_ga);
   if (c->d_gb) cudaFree(c->d_gb);
   if (c->d_hv) cudaFree(c->d_hv);
@@ -1356,20 +1422,100 @@ int sk_comm_init(sk_ctx *c, const void *id128, int32_t rank, int32_t nranks) {
 
 int sk_comm_destroy(sk_ctx *c) {
   if (!c) return SK_ERR_ARG;
+  cudaSetDevice(c->device);
   if (c->comm) {
     cudaStreamSynchronize(c->stream);
     nccl_api()->CommDestroy(c->comm);
     c->comm = nullptr;
   }
+  peer_release(c);
   c->comm_size = 1;
+  c->comm_rank = 0;
   return SK_OK;
 }
 
-// generic collective on up to 8 host doubles (op: 0 max, 1 min, 2 sum); synchronous.  Used once per
+// ---- peer mailboxes (one process per GPU, NVLink / NVSwitch peer memory; see k_peer_exchange) ------------------
+// sk_comm_peer_export: allocate this rank's mailbox and hand out its 64-byte CUDA IPC handle; the host all-gathers the
+// handles of all ranks (torch.distributed / MPI / files) and passes them to sk_comm_peer_attach.  The all-gather also
+// orders "every mailbox is zeroed" before "any rank writes into a peer's mailbox".
+int sk_comm_peer_export(sk_ctx *c, void *handle64) {
+  if (!c || !handle64) return fail(c, SK_ERR_ARG, "null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CK(cudaSetDevice(c->device));
+  peer_release(c);
+  const size_t bytes = sizeof(unsigned long long) * 2 * SK_PEER_MAX * SK_PEER_WORDS;
+  CK(cudaMalloc((void **)&c->peer_box, bytes));
+  CK(cudaMemset(c->peer_box, 0, bytes));
+  CK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->peer_box));
+  std::memcpy(handle64, &h, sizeof(h));
+  return SK_OK;
+}
+
+int sk_comm_peer_attach(sk_ctx *c, const void *handles, int32_t rank, int32_t nranks) {
+  if (!c || !handles || nranks < 1 || nranks > SK_PEER_MAX || rank < 0 || rank >= nranks)
+    return fail(c, SK_ERR_ARG, "bad peer arguments (at most %d ranks)", SK_PEER_MAX);
+  if (!c->peer_box) return fail(c, SK_ERR_STATE, "sk_comm_peer_export first");
+  CK(cudaSetDevice(c->device));
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) { c->peer_map[r] = c->peer_box; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char *)handles + (size_t)r * sizeof(h), sizeof(h));
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_map[r] = (unsigned long long *)p;
+  }
+  for (int i = 0; i < 3; ++i)
+    if (!c->peer_out[i]) {
+      CK(cudaHostAlloc((void **)&c->peer_out[i], sizeof(SkPeerOut), cudaHostAllocPortable));
+      std::memset(c->peer_out[i], 0, sizeof(SkPeerOut));
+    }
+  c->comm_rank = rank;
+  c->comm_size = nranks;
+  c->peer_n = nranks;
+  c->peer_epoch = 0;
+  if (const char *t = std::getenv("SK_PEER_TIMEOUT_S")) c->peer_timeout_s = std::max(0.001, std::atof(t));
+  return SK_OK;
+}
+
+// every rank's k <= 7 doubles: out[r * k + i] = value i of rank r.  One exchange; synchronous.  (Peer mailboxes only;
+// with an NCCL communicator use sk_comm_allreduce on a one-hot layout.)
+int sk_comm_allgather(sk_ctx *c, const double *vals, int32_t k, double *out) {
+  if (!c || !vals || !out || k < 1 || k > 7) return fail(c, SK_ERR_ARG, "bad allgather arguments");
+  if (c->peer_n <= 0) return fail(c, SK_ERR_STATE, "sk_comm_allgather needs peer mailboxes (sk_comm_peer_attach)");
+  CK(cudaSetDevice(c->device));
+  unsigned long long w[7] = {0, 0, 0, 0, 0, 0, 0};
+  std::memcpy(w, vals, sizeof(double) * k);
+  int rc = peer_exchange(c, 2, SK_PX_GATHER, 0, 0, 0, w, k, 0);
+  if (rc != SK_OK) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  rc = peer_check(c, 2);
+  if (rc != SK_OK) return rc;
+  std::memcpy(out, c->peer_out[2]->words, sizeof(double) * k * c->peer_n);
+  return SK_OK;
+}
+
+// generic collective on up to 32 host doubles (op: 0 max, 1 min, 2 sum); synchronous.  Used once per
 // kernel_values call (global distance range / counts) and for the rare exact count.
 int sk_comm_allreduce(sk_ctx *c, double *vals, int32_t n, int32_t op) {
   if (!c || !vals || n < 1 || n > 32 || op < 0 || op > 2) return fail(c, SK_ERR_ARG, "bad allreduce arguments");
-  if (!c->comm) return SK_OK;
+  if (!sharded(c)) return SK_OK;
+  CK(cudaSetDevice(c->device));
+  if (c->peer_n > 0) {
+    for (int i0 = 0; i0 < n; i0 += 7) {
+      const int nw = std::min(7, n - i0);
+      unsigned long long w[7] = {0, 0, 0, 0, 0, 0, 0};
+      std::memcpy(w, vals + i0, sizeof(double) * nw);
+      int rc = peer_exchange(c, 2, SK_PX_RAW, 0, 0, 0, w, nw, op);
+      if (rc != SK_OK) return rc;
+      CK(cudaStreamSynchronize(c->stream));
+      rc = peer_check(c, 2);
+      if (rc != SK_OK) return rc;
+      std::memcpy(vals + i0, c->peer_out[2]->words, sizeof(double) * nw);
+    }
+    return SK_OK;
+  }
   NcclApi *N = nccl_api();
   for (int i = 0; i < n; ++i) c->h_scal->hv[i] = vals[i];
   CK(cudaMemcpyAsync(c->d_hv, c->h_scal->hv, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
@@ -1381,15 +1527,17 @@ int sk_comm_allreduce(sk_ctx *c, double *vals, int32_t n, int32_t op) {
 }
 
 // a rank without active targets takes part in the collective points of the other ranks' sub-intervals
-// (which = 0) and scans (which = 1) with neutral contributions
+// (which = 0; 2 when the active ranks speculate) and scans (which = 1) with neutral contributions
 int sk_comm_idle(sk_ctx *c, int32_t which) {
   if (!c) return SK_ERR_ARG;
-  if (!c->comm) return SK_OK;
+  if (!sharded(c)) return SK_OK;
   CK(cudaSetDevice(c->device));
   if (which == 0 || which == 2) {
     int rc = which == 2 ? comm_reduce_ab(c, 1, 0) : comm_reduce_a(c, 1);
     if (rc != SK_OK) return rc;
     CK(cudaStreamSynchronize(c->stream));
+    rc = peer_check(c, 0);
+    if (rc != SK_OK) return rc;
     unsigned int fl = 0;
     double mx = 0.0;
     comm_take_a(c, &fl, &mx);
@@ -1397,15 +1545,64 @@ int sk_comm_idle(sk_ctx *c, int32_t which) {
     if (fl & SK_FLAG_NAND) mx = std::nan("");
     c->g_max_abs = mx;
     // the idle rank raises what the active ranks raise, so that all ranks leave the adaptive loop together
-    if (c->h_scal->ga.err) return fail(c, SK_ERR_STATE, "another rank failed in this sub-interval");
+    if (global_a(c).err) return fail(c, SK_ERR_STATE, "another rank failed in this sub-interval");
     if (!(fl & SK_FLAG_NAN1) && (fl & SK_FLAG_NAN2)) return fail(c, SK_ERR_NAN, "NaN detected in panel integral...");
   } else {
     int rc = comm_reduce_b(c, false, 0ull, 0);
     if (rc != SK_OK) return rc;
     CK(cudaStreamSynchronize(c->stream));
+    rc = peer_check(c, 0);
+    if (rc != SK_OK) return rc;
     comm_take_b(c);
   }
   return SK_OK;
+}
+
+// test hook: the exchange protocol with `nranks` ranks emulated as the blocks of one cooperative launch on this
+// context's device (ranks as separate launches must not share a GPU).  kind: 0 A, 1 AB, 6 gather of (base + rank).
+// maxbits_in[r], rbits_in[r], top_in[r]: rank r's local scalars; out: per rank {maxbits, err, rbits, n_lb, status}.
+int sk_comm_peer_selftest(sk_ctx *c, int32_t nranks, int32_t rounds, const uint64_t *maxbits_in, const uint64_t *rbits_in,
+                          const int64_t *top_in, int64_t lo, uint64_t *out5) {
+  if (!c || nranks < 1 || nranks > SK_PEER_MAX || rounds < 1 || !maxbits_in || !rbits_in || !top_in || !out5)
+    return fail(c, SK_ERR_ARG, "bad selftest arguments");
+  CK(cudaSetDevice(c->device));
+  unsigned long long *boxes = nullptr;
+  SkReduceOut *red = nullptr;
+  SkPeerOut *outs = nullptr;
+  const size_t bb = sizeof(unsigned long long) * 2 * SK_PEER_MAX * SK_PEER_WORDS * nranks;
+  CK(cudaMalloc((void **)&boxes, bb));
+  CK(cudaMemset(boxes, 0, bb));
+  CK(cudaMalloc((void **)&red, sizeof(SkReduceOut) * nranks));
+  CK(cudaMalloc((void **)&outs, sizeof(SkPeerOut) * nranks));
+  CK(cudaMemset(outs, 0, sizeof(SkPeerOut) * nranks));
+  std::vector<SkReduceOut> hr(nranks);
+  int rc = SK_OK;
+  for (int it = 1; it <= rounds && rc == SK_OK; ++it) {
+    for (int r = 0; r < nranks; ++r) {
+      std::memset(&hr[r], 0, sizeof(SkReduceOut));
+      hr[r].maxbits = maxbits_in[r] + (unsigned long long)(it - 1);
+      hr[r].rbits = rbits_in[r];
+      hr[r].max_unconv = top_in[r];
+    }
+    cudaMemcpyAsync(red, hr.data(), sizeof(SkReduceOut) * nranks, cudaMemcpyHostToDevice, c->stream);
+    SkPeerArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n = nranks; a.epoch = (unsigned long long)it; a.timeout_ns = 2000000000ull; a.kind = SK_PX_AB; a.lo = lo;
+    void *args[] = {&a, &boxes, &red, &outs};
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)k_peer_exchange_emul, dim3(nranks), dim3(32), args, 0, c->stream);
+    if (e != cudaSuccess) rc = fail(c, SK_ERR_CUDA, "cooperative launch: %s", cudaGetErrorString(e));
+  }
+  if (rc == SK_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, SK_ERR_CUDA, "selftest kernel failed");
+  if (rc == SK_OK) {
+    std::vector<SkPeerOut> ho(nranks);
+    cudaMemcpy(ho.data(), outs, sizeof(SkPeerOut) * nranks, cudaMemcpyDeviceToHost);
+    for (int r = 0; r < nranks; ++r) {
+      out5[5 * r + 0] = ho[r].ga.maxbits; out5[5 * r + 1] = ho[r].ga.err; out5[5 * r + 2] = ho[r].gb.rbits;
+      out5[5 * r + 3] = (uint64_t)ho[r].gb.n_lb; out5[5 * r + 4] = ho[r].status | (ho[r].epoch_done << 8);
+    }
+  }
+  cudaFree(boxes); cudaFree(red); cudaFree(outs);
+  return rc;
 }
 
 // global results of the last collective points: max |I2-I1| over all ranks (last sub-interval), stopping
@@ -1886,13 +2083,15 @@ int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, c
   if (a != 0.0) return fail(c, SK_ERR_ARG, "the integration-by-parts branch applies to a == 0 only");
   const long long n_act = c->hi - c->lo;
   rc = logw_host_enqueue_local(c, a, b, no1, bufa1, bufb1, no2, bufa2, bufb2, o, i0_coef, denom);
-  if (c->comm) {          // a rank that failed locally still joins the collective (its peers are waiting in it)
+  if (sharded(c)) {       // a rank that failed locally still joins the collective (its peers are waiting in it)
     const std::string msg = c->errmsg;
     const int rcc = comm_reduce_a(c, 0, rc != SK_OK);
     if (rcc != SK_OK) return rcc;
     CK(cudaStreamSynchronize(c->stream));
     if (rc != SK_OK) { c->errmsg = msg; return rc; }
-    if (c->h_scal->ga.err) return fail(c, SK_ERR_STATE, "another rank failed in this sub-interval");
+    const int prc = peer_check(c, 0);
+    if (prc != SK_OK) return prc;
+    if (global_a(c).err) return fail(c, SK_ERR_STATE, "another rank failed in this sub-interval");
   } else {
     if (rc != SK_OK) return rc;
     CK(cudaStreamSynchronize(c->stream));
@@ -1983,7 +2182,7 @@ static int converge_scan_enqueue(sk_ctx *c, const sk_scan_args *a) {
                       std::memcmp(&s0.trunc_num, &a->trunc_num, sizeof(double)) == 0 && s0.xpow == a->xpow && s0.tau == a->tau;
     if (!same) return fail(c, SK_ERR_STATE, "scan arguments differ from the ones the panel was speculated with");
     c->scan_from_spec = true;
-    if (c->comm && !c->pend_ab) {   // sharded run: the scan is a collective point for every rank
+    if (sharded(c) && !c->pend_ab) {   // sharded run: the scan is a collective point for every rank
       unsigned long long rb = 0ull;
       std::memcpy(&rb, &c->spec_r, sizeof(double));
       const long long nlb = c->spec_new_hi - c->lo > 0 ? c->spec_new_hi - c->lo : 0;
@@ -2017,8 +2216,10 @@ static int converge_scan_finish(sk_ctx *c, int64_t *new_hi, double *r_at_new_hi)
     if (r_at_new_hi) *r_at_new_hi = c->spec_r;
     c->scan_hi = c->spec_new_hi;
     c->scan_r = c->spec_r;
-    if (c->comm && !c->pend_ab) {
+    if (sharded(c) && !c->pend_ab) {
       CK(cudaStreamSynchronize(c->stream));
+      const int prc = peer_check(c, 0);
+      if (prc != SK_OK) return prc;
       comm_take_b(c);
     }
     return SK_OK;

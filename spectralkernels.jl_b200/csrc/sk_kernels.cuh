@@ -21,6 +21,7 @@
 //       scheme cannot take                                    src/adaptive.jl:99-120
 #pragma once
 #include <cuda_runtime.h>
+#include <math_constants.h>
 
 #include "sk_math.h"
 #include "sk_k8.cuh"
@@ -869,6 +870,160 @@ __global__ void k_pack_global_b_from_red(const SkReduceOut *__restrict__ red, lo
   g->rbits = red->max_unconv >= lo ? red->rbits : 0ull;
   const long long n = red->max_unconv - lo + 1;
   g->n_lb = n > 0 ? n : 0;
+}
+
+// ---- peer exchange: the scalar collectives of a target-sharded run over NVLink peer memory -------------------------
+// One process per GPU.  Every rank owns a 2 KB "mailbox" in its HBM that all its peers have mapped (CUDA IPC,
+// sk_comm_peer_export / sk_comm_peer_attach).  A collective point is ONE single-warp kernel enqueued on the compute
+// stream right behind the kernel that produced the local scalars:
+//   pack the local words  ->  lane r stores them into rank r's mailbox (slot = this rank), fence, then the epoch word
+//   ->  lane r waits for rank r's epoch word in its OWN mailbox  ->  warp-level reduction (u64 MAX; the active count is
+//   an integer SUM)  ->  the reduced words go straight into the pinned host scalars the caller reads after its (single)
+//   stream synchronisation.
+// No NCCL launch, no pack kernel, no D2H copy; the transfer is 64 bytes per peer through the NVSwitch.  Two mailbox
+// halves alternate with the epoch parity: a rank can be at most one exchange ahead of a peer that is still reading.
+// The wait is bounded (timeout_ns of %globaltimer): a lost peer turns into an error word, not a hang.
+constexpr int SK_PEER_MAX = 16;
+constexpr int SK_PEER_WORDS = 8;       // 7 payload words + the epoch word: one 64-byte line per (half, rank)
+enum { SK_PX_A = 0, SK_PX_AB = 1, SK_PX_B_RED = 2, SK_PX_B_IMM = 3, SK_PX_RANGE = 4, SK_PX_RAW = 5, SK_PX_GATHER = 6 };
+struct SkPeerArgs {
+  unsigned long long *box[SK_PEER_MAX];   // box[r]: rank r's mailbox as mapped on this device (box[rank]: the own one)
+  int rank, n;
+  unsigned long long epoch;               // 1, 2, 3, ... identical on all ranks (every rank issues the same exchanges)
+  unsigned long long timeout_ns;
+  int kind, idle, err, raw_op;            // raw_op (SK_PX_RAW, doubles): 0 max, 1 min, 2 sum
+  long long lo;
+  unsigned long long imm[7];              // SK_PX_B_IMM: rbits, n_lb;  SK_PX_RAW / SK_PX_GATHER: the words themselves
+  int nw;
+};
+struct SkPeerOut {                        // pinned host memory, written by the kernel
+  SkGlobalA ga;
+  SkGlobalB gb;
+  unsigned long long words[SK_PEER_MAX * 7];   // RANGE: 3 reduced words; RAW: nw reduced words; GATHER: [rank][nw]
+  unsigned long long status;              // 0 ok, 1 timed out waiting for a peer
+  unsigned long long epoch_done;
+};
+
+__device__ __forceinline__ void sk_st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long sk_ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long sk_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long sk_warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int m = 16; m; m >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m);
+    v = o > v ? o : v;
+  }
+  return v;
+}
+
+// the exchange as seen by ONE rank (a warp); `a` holds that rank's view of the mailboxes
+__device__ __forceinline__ void sk_peer_exchange_warp(const SkPeerArgs &a, const SkReduceOut *__restrict__ red,
+                                                      const SkK8State *__restrict__ k8, SkPeerOut *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long w[7] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+  const bool quiet = a.idle || a.err;
+  if (a.kind == SK_PX_A || a.kind == SK_PX_AB) {
+    const unsigned int fl = quiet ? 0u : red->flags;
+    w[0] = quiet ? 0ull : red->maxbits;
+    w[1] = (fl & SK_FLAG_NAN1) ? 1ull : 0ull;
+    w[2] = (fl & SK_FLAG_NAN2) ? 1ull : 0ull;
+    w[3] = (fl & SK_FLAG_NAND) ? 1ull : 0ull;
+    w[4] = a.err ? 1ull : 0ull;
+  }
+  if ((a.kind == SK_PX_AB && !quiet) || a.kind == SK_PX_B_RED) {
+    const long long top = red->max_unconv;
+    w[5] = top >= a.lo ? red->rbits : 0ull;
+    w[6] = (unsigned long long)(top - a.lo + 1 > 0 ? top - a.lo + 1 : 0);
+  }
+  if (a.kind == SK_PX_B_IMM) { w[5] = a.imm[0]; w[6] = a.imm[1]; }
+  if (a.kind == SK_PX_RANGE) { w[0] = k8->kmin_inv; w[1] = k8->kmax; w[2] = k8->bad ? 1ull : 0ull; }
+  if (a.kind == SK_PX_RAW || a.kind == SK_PX_GATHER) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) w[i] = a.imm[i];
+  }
+  const int half = (int)(a.epoch & 1ull);
+  bool ok = true;
+  if (lane < a.n) {
+    unsigned long long *dst = a.box[lane] + (size_t)(half * SK_PEER_MAX + a.rank) * SK_PEER_WORDS;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) reinterpret_cast<volatile unsigned long long *>(dst)[i] = w[i];
+    __threadfence_system();
+    sk_st_release_sys(dst + 7, a.epoch);
+    // now the words of rank `lane`
+    const unsigned long long *src = a.box[a.rank] + (size_t)(half * SK_PEER_MAX + lane) * SK_PEER_WORDS;
+    const unsigned long long t0 = sk_globaltimer();
+    while (sk_ld_acquire_sys(src + 7) < a.epoch) {
+      if (sk_globaltimer() - t0 > a.timeout_ns) { ok = false; break; }
+    }
+    __threadfence_system();
+#pragma unroll
+    for (int i = 0; i < 7; ++i) w[i] = ok ? reinterpret_cast<const volatile unsigned long long *>(src)[i] : 0ull;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) w[i] = 0ull;       // neutral for MAX over u64 and for the integer SUM
+  }
+  const unsigned int all_ok = __all_sync(0xffffffffu, ok);
+  if (a.kind == SK_PX_GATHER) {
+    if (lane < a.n)
+      for (int i = 0; i < a.nw; ++i) out->words[lane * a.nw + i] = w[i];
+  } else if (a.kind == SK_PX_RAW) {
+    for (int i = 0; i < a.nw; ++i) {
+      double v = __longlong_as_double((long long)w[i]);
+      if (lane >= a.n) v = a.raw_op == 0 ? -CUDART_INF : (a.raw_op == 1 ? CUDART_INF : 0.0);
+#pragma unroll
+      for (int m = 16; m; m >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, v, m);
+        v = a.raw_op == 0 ? fmax(v, o) : (a.raw_op == 1 ? fmin(v, o) : v + o);   // commutative: every lane, every rank agrees
+      }
+      if (lane == 0) out->words[i] = (unsigned long long)__double_as_longlong(v);
+    }
+  } else {
+    unsigned long long r[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r[i] = sk_warp_max_u64(w[i]);
+    long long s = (long long)w[6];
+#pragma unroll
+    for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) {
+      if (a.kind == SK_PX_A || a.kind == SK_PX_AB) {
+        out->ga.maxbits = r[0]; out->ga.nan1 = r[1]; out->ga.nan2 = r[2]; out->ga.nand = r[3]; out->ga.err = r[4];
+      }
+      if (a.kind == SK_PX_AB || a.kind == SK_PX_B_RED || a.kind == SK_PX_B_IMM) { out->gb.rbits = r[5]; out->gb.n_lb = s; }
+      if (a.kind == SK_PX_RANGE) { out->words[0] = r[0]; out->words[1] = r[1]; out->words[2] = r[2]; }
+    }
+  }
+  if (lane == 0) {
+    if (!all_ok) out->status = 1ull;
+    out->epoch_done = a.epoch;
+  }
+}
+
+__global__ void __launch_bounds__(32) k_peer_exchange(SkPeerArgs a, const SkReduceOut *__restrict__ red,
+                                                      const SkK8State *__restrict__ k8, SkPeerOut *__restrict__ out) {
+  sk_peer_exchange_warp(a, red, k8, out);
+}
+
+// The same protocol with the ranks emulated as the blocks of ONE cooperative launch on one device (tests: separate
+// launches that wait for one another must not share a GPU).  boxes: n mailboxes back to back; block b plays rank b with
+// its own local scalars red[b] and its own output outs[b].
+__global__ void __launch_bounds__(32) k_peer_exchange_emul(SkPeerArgs a, unsigned long long *boxes, const SkReduceOut *__restrict__ red,
+                                                           SkPeerOut *__restrict__ outs) {
+  SkPeerArgs mine = a;
+  mine.rank = blockIdx.x;
+  for (int r = 0; r < a.n; ++r) mine.box[r] = boxes + (size_t)r * 2 * SK_PEER_MAX * SK_PEER_WORDS;
+  if (a.kind == SK_PX_RAW || a.kind == SK_PX_GATHER)
+    for (int i = 0; i < 7; ++i) mine.imm[i] = a.imm[i] + (unsigned long long)blockIdx.x * (a.kind == SK_PX_GATHER ? 1ull : 0ull);
+  sk_peer_exchange_warp(mine, red + blockIdx.x, nullptr, outs + blockIdx.x);
 }
 
 // roll a rejected speculative commit back: res = backup (bit for bit)

@@ -57,27 +57,45 @@ class TorchComm:
 
 
 class LibComm:
-    """The scalar reductions of a target-sharded run done INSIDE libsk_b200: NCCL all-reduces enqueued on the
-    context's stream right behind the kernel that produced the local value (sk_comm_init).  The per-sub-interval
-    and per-scan reductions then cost no extra host synchronisation; this object only serves the once-per-call
-    reductions (global distance range, counts) through sk_comm_allreduce.
+    """The scalar reductions of a target-sharded run done INSIDE libsk_b200, enqueued on the context's stream right
+    behind the kernel that produced the local value.  Two transports:
 
-    `LibComm.from_torch(engine)` bootstraps the NCCL communicator through an initialised torch.distributed
-    group (rank 0 creates the unique id and broadcasts it)."""
+    * `mode="peer"` (default on one node): single-warp exchange kernels over peer-mapped mailboxes in the ranks' HBM
+      (NVLink / NVSwitch peer memory through CUDA IPC; sk_comm_peer_export / sk_comm_peer_attach, k_peer_exchange) --
+      no NCCL call on the data path at all;
+    * `mode="nccl"`: NCCL all-reduces on the context's stream (sk_comm_init) -- the A/B reference.
+
+    Either way the per-sub-interval and per-scan reductions cost no extra host synchronisation; this object only serves
+    the once-per-call reductions (global distance range, counts).
+
+    `LibComm.from_torch(engine)` bootstraps through an initialised torch.distributed group (the mailboxes' IPC handles
+    are all-gathered; for NCCL rank 0 creates the unique id and broadcasts it)."""
     fused = True
 
-    def __init__(self, engine, rank: int, world_size: int, uid: bytes):
+    def __init__(self, engine, rank: int, world_size: int, uid: bytes = None, peer_handles=None):
         self.engine, self.rank, self.world_size = engine, int(rank), int(world_size)
-        engine.comm_init(uid, rank, world_size)
+        if peer_handles is not None:
+            engine.comm_peer_attach(peer_handles, rank, world_size)
+            self.mode = "peer"
+        else:
+            engine.comm_init(uid, rank, world_size)
+            self.mode = "nccl"
         self.n_reductions = 0
 
     @classmethod
-    def from_torch(cls, engine, group=None):
+    def from_torch(cls, engine, group=None, mode: str = None):
+        import os
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
+        mode = mode or os.environ.get("SK_COMM_TRANSPORT", "peer")
+        if mode == "peer" and world <= 16:
+            mine = engine.comm_peer_export()
+            handles = [None] * world
+            dist.all_gather_object(handles, mine, group=group)      # also: every mailbox is zeroed before anyone writes
+            return cls(engine, rank, world, peer_handles=handles)
         box = [engine.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0, group=group)
-        return cls(engine, rank, world, box[0])
+        return cls(engine, rank, world, uid=box[0])
 
     def _r(self, vals, op):
         self.n_reductions += 1
@@ -96,6 +114,9 @@ class LibComm:
         """every rank's values, through ONE sum all-reduce of a one-hot layout (adding zeros is exact)"""
         vals = list(vals)
         k = len(vals)
+        if self.mode == "peer" and k <= 7:
+            self.n_reductions += 1
+            return self.engine.comm_allgather(vals, self.world_size)
         if k * self.world_size > 32:
             raise ValueError("too many values for sk_comm_allreduce")
         buf = [0.0] * (k * self.world_size)

@@ -43,6 +43,7 @@ def main():
         tr = []
         v, e = sk.kernel_values(cfg, chunks[rank], k0=k0, comm=comm, trace=tr)
         if flavour == "lib":
+            dist.barrier()
             comm.close()
         # gather everything on rank 0 (padded to the longest chunk)
         m = max(c.size for c in chunks)
@@ -66,7 +67,7 @@ def main():
             same_t = all(k == key1 for k in keys)
             npan = sum(1 for t in tr1 if t["kind"] == "panel")
             print(f"[multi_gpu_check] {name}: world={world} values_bitwise={same_v} errs_bitwise={same_e} "
-                  f"traces_equal={same_t} panels={npan} comm={flavour} host_reductions={comm.n_reductions} "
+                  f"traces_equal={same_t} panels={npan} comm={flavour}/{getattr(comm, "mode", "torch")} host_reductions={comm.n_reductions} "
                   f"max|dv|={np.max(np.abs(vs - v1)):.2e}", flush=True)
             ok = ok and same_v and same_e and same_t
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
