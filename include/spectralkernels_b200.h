@@ -216,6 +216,15 @@ int sk_sdf_builtin(sk_ctx *ctx, int32_t family, const double *params, int32_t np
 /* ---- Level 1: targets, replaces unique/sort/Dict of src/adaptive.jl:99-107, :113-120 ----------- */
 int sk_targets_set(sk_ctx *ctx, const double *xs_host, int64_t n_in, sk_target_info *info);
 int sk_targets_set_device(sk_ctx *ctx, const double *xs_dev, int64_t n_in, sk_target_info *info);
+/* sk_targets_set[_device] in two halves.  _begin enqueues the upload and the sort and returns once the first pass over the
+ * distances has delivered their range (sk_targets_early_range; r_hi = 0: not known before the sort ends).  The first
+ * panel is (0, m k / (2 r_max)) (src/adaptive.jl:152), so the host evaluates estimate_tail_decay (src/adaptive.jl:204-220)
+ * and the scan arguments for it while the device sorts; _end waits for the sort.  The device buffer of _begin_device
+ * must stay valid until _end returns. */
+int sk_targets_begin(sk_ctx *ctx, const double *xs_host, int64_t n_in);
+int sk_targets_begin_device(sk_ctx *ctx, const double *xs_dev, int64_t n_in);
+int sk_targets_early_range(sk_ctx *ctx, double *r_lo, double *r_hi);
+int sk_targets_end(sk_ctx *ctx, sk_target_info *info);
 /* lags of point pairs computed on the device (src/model.jl:53-68 with NoWarping: lag = norm(pts[i] - pts[j])):
  * pts_host is npts x dim row-major; pairs_host holds npairs 0-based (i, j) index pairs, or NULL for all
  * npts (npts-1) / 2 pairs i < j in row-major order of the strict upper triangle.  The results of
@@ -249,6 +258,10 @@ int sk_panel_set_range(sk_ctx *ctx, double r_lo, double r_hi, int64_t n_active_g
  * (updatequadbufs!, :49-95) from the built-in S, transform (fast or direct, :105-128), select
  * Re/Im, scale by cmul, stage I2 and |I2-I1|, and return max|I2-I1| (NaN if any is NaN). */
 int sk_subinterval(sk_ctx *ctx, double a, double b, const sk_subinterval_opts *opts, double *max_abs_diff);
+/* sk_subinterval in two halves: _begin enqueues, _end waits and returns max |I2 - I1|.  In between the host does its
+ * scalar work for the next panel (its ends are known: src/adaptive.jl:152), which then costs no device idle time. */
+int sk_subinterval_begin(sk_ctx *ctx, double a, double b, const sk_subinterval_opts *opts);
+int sk_subinterval_end(sk_ctx *ctx, double *max_abs_diff);
 /* same with host-evaluated nodes and (real) strengths: no1/buf1 length m*k, no2/buf2 length 2*m*k
  * (the buffers of src/adaptive.jl:50-53 after updatequadbufs!) */
 int sk_subinterval_host(sk_ctx *ctx, double a, double b, const double *no1, const double *buf1,

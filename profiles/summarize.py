@@ -79,9 +79,13 @@ def traffic(src, dst, units="10000000"):
     n, u = len(rows), float(units)
     dram = sum(f(x, "dram__bytes_read.sum") + f(x, "dram__bytes_write.sum") for x in rows) / n
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[r[1][hdr.index("dram__bytes_read.sum")]]
-    fl = sum(2 * f(x, "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum")
-             + f(x, "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum")
-             + f(x, "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum") for x in rows) / n
+    def ops(x, op):      # thread-level instruction count (this ncu only exports the per-cycle form of the counter)
+        m = f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum"
+        if m in hdr:
+            return f(x, m)
+        return f(x, m + ".per_cycle_elapsed") * f(x, "smsp__cycles_elapsed.avg" if "smsp__cycles_elapsed.avg" in hdr
+                                                    else "sm__cycles_elapsed.avg")
+    fl = sum(2 * ops(x, "dfma") + ops(x, "dadd") + ops(x, "dmul") for x in rows) / n
     out = {"interp_cells_dram_bytes_per_launch": dram * scale, "executed_flops_per_unit": fl / u, "launches_captured": n,
            "units_per_launch": u, "source": f"ncu --set full --clock-control none capture of bench.py ({src.split('/')[-1]}), "
                                             "dram__bytes_read.sum + dram__bytes_write.sum averaged over the captured launches"}

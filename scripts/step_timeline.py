@@ -7,6 +7,9 @@ import torch
 import spectralkernels_jl_b200 as sk
 from spectralkernels_jl_b200 import adaptive as ad
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
+mode = sys.argv[2] if len(sys.argv) > 2 else "resident"          # resident | e2e
+if len(sys.argv) > 3 and sys.argv[3] == "nooverlap":
+    ad.OVERLAP_HOST_WORK = False
 xs = np.random.default_rng(0).uniform(0, 1, n)
 d_in = torch.from_numpy(xs).cuda()
 d_v = torch.empty_like(d_in); d_e = torch.empty_like(d_in)
@@ -24,8 +27,13 @@ for name in dir(eng):
         try: wrap(eng, name)
         except Exception: pass
 wrap(ad, "estimate_tail_decay", "HOST estimate_tail_decay"); wrap(ad, "_scan_args", "HOST _scan_args")
+hin, hv, he = sk.PinnedArray(n), sk.PinnedArray(n), sk.PinnedArray(n)
+hin.array[:] = xs
 def step():
-    sk.kernel_values(cfg, None, k0=1.0, xs_device=(d_in.data_ptr(), n), out_device=(d_v.data_ptr(), d_e.data_ptr()))
+    if mode == "e2e":
+        sk.kernel_values(cfg, hin.array, k0=1.0, out_vals=hv.array, out_errs=he.array)
+    else:
+        sk.kernel_values(cfg, None, k0=1.0, xs_device=(d_in.data_ptr(), n), out_device=(d_v.data_ptr(), d_e.data_ptr()))
 for _ in range(5): step()
 torch.cuda.synchronize()
 tot = {}
@@ -41,6 +49,6 @@ for _ in range(R):
         tot[name] = tot.get(name, 0) + (t1 - t0); prev = t1
     tot["tail"] = tot.get("tail", 0) + (t_end - prev)
 wall = (time.perf_counter() - T0) / R
-print(f"n = {n}: wall {1e3 * wall:.3f} ms per step; per-step averages (us):")
+print(f"n = {n} {mode} overlap={ad.OVERLAP_HOST_WORK}: wall {1e3 * wall:.3f} ms per step; per-step averages (us):")
 for k, v in tot.items():
     print(f"  {1e6 * v / R:9.1f}  {k}")

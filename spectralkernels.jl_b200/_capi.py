@@ -79,6 +79,12 @@ SIGNATURES = {
     "sk_comm_allreduce": (c_int, [c_void_p, _dp, c_int32, c_int32]),
     "sk_comm_idle": (c_int, [c_void_p, c_int32]),
     "sk_comm_last": (c_int, [c_void_p, _dp, _dp, POINTER(c_int64)]),
+    "sk_targets_begin": (c_int, [c_void_p, _dp, c_int64]),
+    "sk_targets_begin_device": (c_int, [c_void_p, c_void_p, c_int64]),
+    "sk_targets_early_range": (c_int, [c_void_p, _dp, _dp]),
+    "sk_targets_end": (c_int, [c_void_p, c_void_p]),
+    "sk_subinterval_begin": (c_int, [c_void_p, c_double, c_double, c_void_p]),
+    "sk_subinterval_end": (c_int, [c_void_p, _dp]),
     "sk_comm_peer_export": (c_int, [c_void_p, c_void_p]),
     "sk_comm_peer_attach": (c_int, [c_void_p, c_void_p, c_int32, c_int32]),
     "sk_comm_allgather": (c_int, [c_void_p, _dp, c_int32, _dp]),
@@ -387,6 +393,42 @@ class Session:
                                                   pr.ctypes.data_as(POINTER(c_int64)), pr.shape[0], byref(info)))
         self._last_targets = (info, int(info.n_in))
         return info
+
+    # sk_targets_set[_device] in two halves: the host's scalar work for the first panel overlaps the sort
+    def targets_begin(self, xs: np.ndarray):
+        self._begin_keep = xs                      # (the upload is asynchronous: keep the array alive until targets_end)
+        self._ck(self._L.sk_targets_begin(self._h, _p(xs), xs.size))
+
+    def targets_begin_device(self, ptr: int, n: int):
+        self._ck(self._L.sk_targets_begin_device(self._h, c_void_p(ptr), int(n)))
+
+    def targets_early_range(self):
+        lo, hi = c_double(), c_double()
+        self._ck(self._L.sk_targets_early_range(self._h, byref(lo), byref(hi)))
+        return lo.value, hi.value
+
+    def targets_end(self) -> TargetInfo:
+        info = TargetInfo()
+        try:
+            self._ck(self._L.sk_targets_end(self._h, byref(info)))
+        finally:
+            self._begin_keep = None
+        return info
+
+    def subinterval_begin(self, a: float, b: float, cmul: float, p: float, kernel: int, logw: bool, speculate=None,
+                          nu: int = 0, xdiv_pow: float = 0.0):
+        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0, int(nu), 0, float(xdiv_pow),
+                            ctypes.pointer(speculate) if speculate is not None else None)
+        self._sub_keep = (o, speculate)
+        self._ck(self._L.sk_subinterval_begin(self._h, float(a), float(b), byref(o)))
+
+    def subinterval_end(self) -> float:
+        out = c_double()
+        try:
+            self._ck(self._L.sk_subinterval_end(self._h, byref(out)))
+        finally:
+            self._sub_keep = None
+        return out.value
 
     def targets_scale(self, factor: float) -> "TargetInfo":
         """Lags under the linear warping x -> x * factor (range parameter): re-uses the sort of the last targets_set*."""

@@ -187,6 +187,29 @@ def _scan_args(cfg, b, c, d, tau, crit) -> ScanArgs:
     return ScanArgs(ta, tn, (dim + 1) / 2, float(tau), SK_CRIT[crit], 0)
 
 
+# The host's scalar work for the next panel (tail fit, scan arguments) runs while the device sorts / integrates
+# (sk_targets_begin/_end, sk_subinterval_begin/_end).  False: the plain blocking calls (A/B, diagnostics).
+OVERLAP_HOST_WORK = True
+
+
+def _panel_scalars(cfg, a: float, b: float, crit: str, tau: float):
+    """Everything the convergence scan of panel (a, b) needs that depends on the panel ends only: the tail fit
+    (src/adaptive.jl:168-175) and the target-independent pieces of the truncation bound.  Returns
+    (c, d, criteria, message, scan arguments)."""
+    if crit == "panel":                                                          # :168
+        c = d = float("nan")
+    else:
+        c, d = estimate_tail_decay(cfg, a, b, d=cfg.tail)
+    if (math.isnan(c) or math.isnan(d)) and crit != "panel":                     # :170-175
+        msg = "\talgebraic tail estimate failed -- using convergence_criteria = :panel"
+        crit = "panel"
+    elif crit != "panel":
+        msg = f"\talgebraic tail estimate S(w) ≈ {c:.2e} * w^({d:.2f})"
+    else:
+        msg = None
+    return c, d, crit, msg, _scan_args(cfg, b, c, d, tau, crit)
+
+
 class _NoComm:
     """Single-process stand-in for the scalar reductions of a target-sharded run."""
     world_size = 1
@@ -254,10 +277,14 @@ def _host_strengths(cfg: AdaptiveKernelConfig, eng, a: float, b: float, origin: 
 
 def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: float, k0: float, comm, active: bool,
                                verbose: bool = False, trace: Optional[list] = None, speculate=None,
-                               n_act_g: Optional[int] = None, spec_state: Optional[dict] = None):
+                               n_act_g: Optional[int] = None, spec_state: Optional[dict] = None, while_enqueued=None):
     """Scalar control flow of src/quadrature.jl:169-275: LIFO bisection, accept test against
     config.tol*k0 (not the split tolerance), 9:1 tolerance split at the origin.  The per-target work of
-    every pass happens inside sk_subinterval / sk_subinterval_accept."""
+    every pass happens inside sk_subinterval / sk_subinterval_accept.
+
+    `while_enqueued` (callable): host work that does not depend on this panel's outcome (the next panel's tail fit);
+    it runs between sk_subinterval_begin and sk_subinterval_end of the panel's first sub-interval, i.e. while the
+    device integrates."""
     nu, xdiv = 0, 0.0
     if cfg.dim == 1:
         kernel = SK_KERNEL_SIN if cfg.derivative else SK_KERNEL_COS              # :177
@@ -308,6 +335,13 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
                     mx = eng.subinterval_logw_host(_a, _b, no1, ba1, bb1, no2, ba2, bb2, cfg.c, cfg.p, i0,
                                                    cfg.dim - cfg.alpha, kernel=SK_KERNEL_BESSEL,
                                                    nu=int(cfg.dim / 2 - 1), xdiv_pow=cfg.dim / 2 - 1)
+            elif builtin and spec is not None and while_enqueued is not None and OVERLAP_HOST_WORK and \
+                    hasattr(eng, "subinterval_begin"):
+                eng.subinterval_begin(_a, _b, cfg.c, cfg.p, kernel, cfg.logw, speculate=spec, nu=nu, xdiv_pow=xdiv)
+                try:
+                    while_enqueued()
+                finally:
+                    mx = eng.subinterval_end()
             elif builtin:
                 mx = eng.subinterval(_a, _b, cfg.c, cfg.p, kernel, cfg.logw, speculate=spec, nu=nu, xdiv_pow=xdiv)
             else:
@@ -381,18 +415,35 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
     if is_builtin(cfg.f):
         eng.sdf_builtin(cfg.f.family, cfg.f.params, cfg.f.deriv)
     # unique + sort + inverse map on the device (adaptive.jl:99, :113-120)
+    pre = {}         # panel scalars computed ahead of time, keyed by the exact (a, b, criteria) they were computed for
     if reuse_targets and getattr(eng, "_last_targets", None) is not None:
         info, n_in = eng._last_targets
     elif points is not None:
         info = eng.targets_set_pairs(points, pairs)
         n_in = int(info.n_in)
-    elif xs_device is not None:
-        info = eng.targets_set_device(*xs_device)
-        n_in = int(xs_device[1])
     else:
-        xs = np.ascontiguousarray(xs, dtype=np.float64)
-        n_in = xs.size
-        info = eng.targets_set(xs)
+        if xs_device is None:
+            xs = np.ascontiguousarray(xs, dtype=np.float64)
+        n_in = int(xs_device[1]) if xs_device is not None else xs.size
+        if OVERLAP_HOST_WORK and hasattr(eng, "targets_begin") and n_in > 0:
+            # two halves: while the device sorts, the host prepares the first panel (0, m k / (2 r_max)), whose ends
+            # are known as soon as the first pass over the distances has delivered their range
+            if xs_device is not None:
+                eng.targets_begin_device(*xs_device)
+            else:
+                eng.targets_begin(xs)
+            try:
+                _, r_early = eng.targets_early_range()
+                if r_early > 0 and comm.world_size == 1 or (r_early > 0 and getattr(comm, "fused", False)):
+                    b1 = 0.0 + cfg.quadsz / (2 * r_early)
+                    pre[(0.0, b1, cfg.convergence_criteria)] = _panel_scalars(cfg, 0.0, b1, cfg.convergence_criteria,
+                                                                              cfg.tol * abs(k0) / 2)
+            finally:
+                info = eng.targets_end()
+        elif xs_device is not None:
+            info = eng.targets_set_device(*xs_device)
+        else:
+            info = eng.targets_set(xs)
     try:
         eng._last_targets = (info, n_in)
     except AttributeError:
@@ -440,22 +491,23 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
                 eng.panel_set_range(r_lo_g, r_hi_g, n_act_g)
         # The tail fit depends on (a, b) only, so it is evaluated BEFORE the panel is integrated (the
         # reference does it after, src/adaptive.jl:168): the scan arguments can then ride along with the
-        # panel's first sub-interval.
-        if crit == "panel":                                                      # :168
-            c = d = float("nan")
-        else:
-            c, d = estimate_tail_decay(cfg, a, b, d=cfg.tail)
-        if (math.isnan(c) or math.isnan(d)) and crit != "panel":                 # :170-175
-            crit_msg = "\talgebraic tail estimate failed -- using convergence_criteria = :panel"
-            crit = "panel"
-        elif crit != "panel":
-            crit_msg = f"\talgebraic tail estimate S(w) ≈ {c:.2e} * w^({d:.2f})"
-        else:
-            crit_msg = None
-        sargs = _scan_args(cfg, b, c, d, tau, crit)
+        # panel's first sub-interval.  It is usually there already: computed while the device was sorting (first
+        # panel) or integrating the previous panel.
+        key = (a, b, crit)
+        pre_hit = key in pre
+        c, d, crit, crit_msg, sargs = pre.pop(key) if pre_hit else _panel_scalars(cfg, a, b, crit, tau)
+        pre.clear()
+
+        def ahead(a2=b, r=r_hi_g, crit2=crit):
+            # the next panel if this one converges nothing (the usual outcome of a run's first panels): same r_hi
+            b2 = a2 + quadm / (2 * r)
+            if math.isfinite(b2) and b2 > a2:
+                pre[(a2, b2, crit2)] = _panel_scalars(cfg, a2, b2, crit2, tau)
+
         spec_state = {}
         fourier_integrate_interval(cfg, eng, a, b, abs(k0), comm, active, verbose=verbose, trace=trace,
-                                   speculate=sargs, n_act_g=n_act_g, spec_state=spec_state)   # :157-159
+                                   speculate=sargs, n_act_g=n_act_g, spec_state=spec_state,
+                                   while_enqueued=ahead if (ipanel == 0 or pre_hit) else None)         # :157-159
         if active:
             eng.panel_commit()                                                   # :163-164
         if verbose and crit_msg:

@@ -149,6 +149,10 @@ struct sk_ctx {
   cudaStream_t stream_main = nullptr, stream2 = nullptr;
   cudaEvent_t pf_ev = nullptr;
   cudaEvent_t k8_ev = nullptr;
+  // sk_targets_set_device: K8 reads the caller's buffer directly while the library's own copy of the distances (the
+  // final gather reads them again, possibly in a later call) is made on the copy stream next to the sort
+  const double *in_src = nullptr;
+  cudaEvent_t in_ev[2] = {nullptr, nullptr};
   cudaEvent_t ev_slice[SK_GATHER_SLICES] = {nullptr};
   bool results_sliced = false;
   int last_logw = 0;
@@ -189,6 +193,9 @@ struct sk_ctx {
   bool in_panel = false, staged = false, first_accept = true, commit_pending = false;
   long long pend_lo = 0, pend_hi = 0;        // range of the pending (lazy) commit
   double r0 = 0, r1 = 0, r_last = 0;         // smallest, second smallest, largest unique distance
+  double early_lo = 0, early_hi = 0;         // distance range known after the first K8 pass (sk_targets_early_range)
+  long long begin_n = -1;                    // between sk_targets_begin* and sk_targets_end
+  bool sub_open = false;                     // between sk_subinterval_begin and sk_subinterval_end
   long long scan_hi = -1;                    // 1-based index / distance returned by the last scan
   double scan_r = 0;
   int interp_mode = 0;                       // 0: cell polynomials (default), 1: per-target taps
@@ -218,6 +225,9 @@ struct sk_ctx {
   long long g_n_lb = 0;
   // speculative commit of the panel's first sub-interval (see sk_subinterval_opts::speculate)
   bool spec_active = false, spec_accepted = false;
+  // (ks, errs) = 0 at the start of a run (src/adaptive.jl:122) is not written until somebody needs it: the first panel's
+  // speculative commit covers every positive distance and writes the table outright (SkSpec::fresh)
+  bool res_zero_pending = false, zero_lag_written = false, spec_fresh = false;
   bool pend_timed = false, pend_spec = false;  // between transform_and_stage_enqueue and _finish
   bool scan_from_spec = false;                 // between converge_scan_enqueue and _finish
   int pend_rc = 0;                             // local result of transform_and_stage_enqueue in a sharded run
@@ -282,6 +292,7 @@ int fail(sk_ctx *c, int code, const char *fmt, ...) {
 
 inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
 int flush_commit(sk_ctx *c);
+int ensure_res_zero(sk_ctx *c);
 
 #define NCK(call)                                                                                     \
   do {                                                                                                \
@@ -685,7 +696,19 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
                        o->speculate->criteria <= 2;
   SkSpec spec;
   std::memset(&spec, 0, sizeof(spec));
+  c->spec_fresh = false;
   if (spec_on) {
+    // first panel of a run over every positive distance: the table is still (pending) zero -> written outright
+    const bool fresh = c->res_zero_pending && !c->commit_pending && c->lo == (c->has_zero ? 1 : 0) && c->hi == c->n_unique;
+    if (fresh) {
+      c->res_zero_pending = false;
+      if (c->has_zero && !c->zero_lag_written) CK(cudaMemsetAsync(c->res.p, 0, sizeof(sk_cplx), c->stream));
+      c->spec_fresh = true;
+      spec.fresh = 1;
+    } else {
+      int rcz = ensure_res_zero(c);      // the table is read: it must hold its zeros now
+      if (rcz != SK_OK) return rcz;
+    }
     int rc = flush_commit(c);            // res must be current before it is updated in place
     if (rc != SK_OK) return rc;
     spec.on = 1;
@@ -884,8 +907,13 @@ int transform_and_stage(sk_ctx *c, double a, double b, const sk_subinterval_opts
 int rollback_speculation(sk_ctx *c) {
   if (c->spec_active && !c->spec_accepted) {
     const long long n = c->hi - c->lo;
-    k_restore<<<nblk(n, 256), 256, 0, c->stream>>>(c->res.p + c->lo, c->stage.p + c->lo, n);
-    LAUNCH_CHECK();
+    if (c->spec_fresh) {                  // the table was zero before the sub-interval: rolling back = zeroing
+      CK(cudaMemsetAsync(c->res.p + c->lo, 0, sizeof(sk_cplx) * n, c->stream));
+    } else {
+      k_restore<<<nblk(n, 256), 256, 0, c->stream>>>(c->res.p + c->lo, c->stage.p + c->lo, n);
+      LAUNCH_CHECK();
+    }
+    c->spec_fresh = false;
     c->spec_active = false;
     c->staged = false;
     c->stats.n_spec_rollbacks++;
@@ -1063,6 +1091,8 @@ int targets_early_prefetch(sk_ctx *c, double r_lo, double r_hi) {
 int targets_enqueue(sk_ctx *c, long long n_in) {
   NvtxRange nvtx("unique / sort (K8)");
   c->have_targets = false;
+  c->early_lo = c->early_hi = 0.0;
+  const double *src = c->in_src ? c->in_src : c->in.p;      // (the caller's device buffer, or the library's copy)
   if (n_in > 0x7ffffff0LL) return fail(c, SK_ERR_ARG, "n_in too large");
   const size_t nfine_max = (size_t)(n_in >> SK_K8_TARGET_LOG) + 2;
   // control block: state | coarse histogram | fill counters (one per 32-byte sector) -- cleared by one memset;
@@ -1090,7 +1120,7 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
   CK(cudaMemsetAsync(c->k8_ctl.p, 0, ctl_bytes, c->stream));
   const unsigned int gs = std::min<unsigned int>(nblk(n_in, 256), 148u * 8u);    // grid-stride passes: 2048 threads per SM
-  k_k8_stats<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st);
+  k_k8_stats<<<gs, 256, 0, c->stream>>>(src, n_in, st);
   LAUNCH_CHECK();
   // the first panel is (0, quadm / (2 r_max)) (src/adaptive.jl:152) and r_max is known after this first pass: fetch the
   // key range now, and start the panel's source side on the prefetch stream while the sort runs
@@ -1122,11 +1152,11 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
     }
     CK(cudaEventRecord(c->k8_ev, c->stream));
   }
-  k_k8_sample<<<std::min<unsigned int>(nblk(n_in, 512), 148u), 512, 0, c->stream>>>(c->in.p, n_in, st, chist);
+  k_k8_sample<<<std::min<unsigned int>(nblk(n_in, 512), 148u), 512, 0, c->stream>>>(src, n_in, st, chist);
   LAUNCH_CHECK();
   k_k8_plan<<<1, 1024, 0, c->stream>>>(st, chist, n_in, c->k8_ctab.p);
   LAUNCH_CHECK();
-  k_k8_scatter<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->k8_ctab.p, fill, c->k8_slots.p, c->inv.p);
+  k_k8_scatter<<<gs, 256, 0, c->stream>>>(src, n_in, st, c->k8_ctab.p, fill, c->k8_slots.p, c->inv.p);
   LAUNCH_CHECK();
   k_k8_scan_bins<<<1, 1024, 0, c->stream>>>(st, fill, SK_K8_FILL_STRIDE, SK_K8_CAP, uoffp, 0);
   LAUNCH_CHECK();
@@ -1139,15 +1169,18 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   LAUNCH_CHECK();
   k_k8_fix_inv<<<gs, 256, 0, c->stream>>>(st, uoffp, dsum, n_in, c->inv.p);
   LAUNCH_CHECK();
-  k_k8_identity<<<gs, 256, 0, c->stream>>>(c->in.p, n_in, st, c->uxs.p, c->inv.p);
+  k_k8_identity<<<gs, 256, 0, c->stream>>>(src, n_in, st, c->uxs.p, c->inv.p);
   LAUNCH_CHECK();
   k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, c->uxs_fix.p, n_in, c->d_sum);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
+  if (c->in_src) CK(cudaStreamWaitEvent(c->stream, c->in_ev[1], 0));   // the library's copy of the distances is complete
   if (early && !c->in_group) {
     double r_lo = 0, r_hi = 0;
     int rc = targets_early_range(c, &r_lo, &r_hi);
     if (rc != SK_OK) return rc;
+    c->early_lo = r_lo;
+    c->early_hi = r_hi;
     if (r_hi > 0.0) {
       rc = targets_early_prefetch(c, r_lo, r_hi);
       if (rc != SK_OK) return rc;
@@ -1158,6 +1191,7 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
 
 int targets_finish(sk_ctx *c, long long n_in, sk_target_info *info, bool force_general) {
   CK(cudaStreamSynchronize(c->stream));
+  c->in_src = nullptr;                       // the caller's buffer is not referenced any more
   if (c->h_scal->sum.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
   const bool general = force_general || c->h_scal->sum.overflow != 0;
   if (general) {
@@ -1205,9 +1239,24 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   return targets_finish(c, n_in, info, force_general);
 }
 
+// ks = errs = 0 (src/adaptive.jl:122), written only when a consumer needs it (see res_zero_pending); the r = 0 row keeps
+// what sk_zero_lag_set put there
+int ensure_res_zero(sk_ctx *c) {
+  if (!c->res_zero_pending) return SK_OK;
+  c->res_zero_pending = false;
+  const long long first = (c->has_zero && c->zero_lag_written) ? 1 : 0;
+  if (c->n_unique > first)
+    CK(cudaMemsetAsync(c->res.p + first, 0, sizeof(sk_cplx) * (c->n_unique - first), c->stream));
+  return SK_OK;
+}
+
 // the lazy commit of the last panel, when no scan consumed it
 int flush_commit(sk_ctx *c) {
   if (!c->commit_pending) return SK_OK;
+  if (c->res_zero_pending) {
+    int rcz = ensure_res_zero(c);
+    if (rcz != SK_OK) return rcz;
+  }
   const long long n = c->pend_hi - c->pend_lo;
   k_commit<<<nblk(n, 256), 256, 0, c->stream>>>(c->pan.p + c->pend_lo, c->res.p + c->pend_lo, n);
   LAUNCH_CHECK();
@@ -1263,7 +1312,9 @@ int sk_ctx_create(int device, sk_ctx **out) {
   c->stream_main = c->stream;
   if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->pf_ev, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->k8_ev, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&c->k8_ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->in_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->in_ev[1], cudaEventDisableTiming) != cudaSuccess) {
     delete c;
     return SK_ERR_CUDA;
   }
@@ -1312,6 +1363,7 @@ int sk_ctx_destroy(sk_ctx *c) {
   if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
   if (c->pf_ev) cudaEventDestroy(c->pf_ev);
   if (c->k8_ev) cudaEventDestroy(c->k8_ev);
+  for (int i = 0; i < 2; ++i) if (c->in_ev[i]) cudaEventDestroy(c->in_ev[i]);
   for (int i = 0; i < SK_GATHER_SLICES; ++i) if (c->ev_slice[i]) cudaEventDestroy(c->ev_slice[i]);
   c->pf.no1.release(); c->pf.buf1.release(); c->pf.no2.release(); c->pf.buf2.release();
   c->pf.pos_hi1.release(); c->pf.pos_lo1.release(); c->pf.pos_hi2.release(); c->pf.pos_lo2.release();
@@ -1759,8 +1811,72 @@ int sk_targets_set_device(sk_ctx *c, const double *xs_dev, int64_t n_in, sk_targ
   if (!c || !xs_dev || n_in < 1) return fail(c, SK_ERR_ARG, "need at least one distance");
   CK(cudaSetDevice(c->device));
   CK(c->in.ensure(n_in));
-  CK(cudaMemcpyAsync(c->in.p, xs_dev, sizeof(double) * n_in, cudaMemcpyDeviceToDevice, c->stream));
-  return targets_from_device_buffer(c, n_in, info);
+  if (c->stream2) {
+    // K8 reads the caller's buffer; the library's own copy is made on the copy stream, next to the sort (it starts once
+    // everything queued so far -- a previous call's gather reads the old copy -- has drained)
+    CK(cudaEventRecord(c->in_ev[0], c->stream));
+    CK(cudaStreamWaitEvent(c->stream2, c->in_ev[0], 0));
+    CK(cudaMemcpyAsync(c->in.p, xs_dev, sizeof(double) * n_in, cudaMemcpyDeviceToDevice, c->stream2));
+    CK(cudaEventRecord(c->in_ev[1], c->stream2));
+    c->in_src = xs_dev;
+  } else {
+    CK(cudaMemcpyAsync(c->in.p, xs_dev, sizeof(double) * n_in, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  const int rc_t = targets_from_device_buffer(c, n_in, info);
+  c->in_src = nullptr;
+  return rc_t;
+}
+
+// sk_targets_set[_device] in two halves: everything is enqueued by _begin (which returns as soon as the first pass over
+// the distances has delivered their range), the host does its scalar work for the first panel -- the panel is
+// (0, m k / (2 r_max)) (src/adaptive.jl:152), so estimate_tail_decay (:204-220) and the scan arguments can be evaluated
+// while the device sorts -- and _end waits for the sort.
+int sk_targets_begin(sk_ctx *c, const double *xs_host, int64_t n_in) {
+  if (!c || !xs_host || n_in < 1) return fail(c, SK_ERR_ARG, "need at least one distance");
+  CK(cudaSetDevice(c->device));
+  CK(c->in.ensure(n_in));
+  CK(cudaMemcpyAsync(c->in.p, xs_host, sizeof(double) * n_in, cudaMemcpyHostToDevice, c->stream));
+  c->begin_n = -1;
+  int rc = targets_enqueue(c, n_in);
+  if (rc == SK_OK) c->begin_n = n_in;
+  return rc;
+}
+int sk_targets_begin_device(sk_ctx *c, const double *xs_dev, int64_t n_in) {
+  if (!c || !xs_dev || n_in < 1) return fail(c, SK_ERR_ARG, "need at least one distance");
+  CK(cudaSetDevice(c->device));
+  CK(c->in.ensure(n_in));
+  c->begin_n = -1;
+  if (c->stream2) {
+    CK(cudaEventRecord(c->in_ev[0], c->stream));
+    CK(cudaStreamWaitEvent(c->stream2, c->in_ev[0], 0));
+    CK(cudaMemcpyAsync(c->in.p, xs_dev, sizeof(double) * n_in, cudaMemcpyDeviceToDevice, c->stream2));
+    CK(cudaEventRecord(c->in_ev[1], c->stream2));
+    c->in_src = xs_dev;
+  } else {
+    CK(cudaMemcpyAsync(c->in.p, xs_dev, sizeof(double) * n_in, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  int rc = targets_enqueue(c, n_in);
+  if (rc == SK_OK) c->begin_n = n_in;
+  else c->in_src = nullptr;
+  return rc;
+}
+// the distance range [r_lo, r_hi] of the distances being sorted (over all ranks when a communicator / mailboxes are
+// attached); r_hi = 0 when it is not known before the sort ends (small inputs, host-evaluated densities)
+int sk_targets_early_range(sk_ctx *c, double *r_lo, double *r_hi) {
+  if (!c || !r_lo || !r_hi) return SK_ERR_ARG;
+  *r_lo = c->begin_n >= 0 ? c->early_lo : 0.0;
+  *r_hi = c->begin_n >= 0 ? c->early_hi : 0.0;
+  return SK_OK;
+}
+int sk_targets_end(sk_ctx *c, sk_target_info *info) {
+  if (!c) return SK_ERR_ARG;
+  if (c->begin_n < 0) return fail(c, SK_ERR_STATE, "sk_targets_begin first");
+  CK(cudaSetDevice(c->device));
+  const long long n_in = c->begin_n;
+  c->begin_n = -1;
+  const int rc = targets_finish(c, n_in, info, false);
+  c->in_src = nullptr;
+  return rc;
 }
 
 int sk_targets_set_pairs(sk_ctx *c, const double *pts_host, int64_t npts, int32_t dim, const int64_t *pairs_host,
@@ -1847,7 +1963,9 @@ int sk_run_begin(sk_ctx *c) {
   c->stats.timing_enabled = t;
   c->stats.sort_two_level = two;
   c->stats.sort_ms = sort_ms;
-  CK(cudaMemsetAsync(c->res.p, 0, sizeof(sk_cplx) * c->n_unique, c->stream));   // ks = errs = 0, src/adaptive.jl:122
+  c->res_zero_pending = true;               // ks = errs = 0, src/adaptive.jl:122: see ensure_res_zero
+  c->zero_lag_written = false;
+  c->spec_fresh = false;
   c->tails.n = 0;
   c->in_panel = false;
   c->staged = false;
@@ -1862,6 +1980,7 @@ int sk_zero_lag_set(sk_ctx *c, double value) {
   if (!c->has_zero) return SK_OK;
   k_set_zero_lag<<<1, 1, 0, c->stream>>>(c->res.p, value);
   LAUNCH_CHECK();
+  c->zero_lag_written = true;               // (a later ensure_res_zero leaves the row alone)
   return SK_OK;
 }
 
@@ -1948,6 +2067,21 @@ int sk_subinterval(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, 
   if (c && !max_abs_diff) return fail(c, SK_ERR_ARG, "null output");
   int rc = subinterval_builtin_enqueue(c, a, b, o);
   if (rc != SK_OK) return rc;
+  return transform_and_stage_finish(c, max_abs_diff, nullptr);
+}
+
+// sk_subinterval in two halves (built-in densities): _begin enqueues the sub-interval, the host does its scalar work for
+// the NEXT panel (tail fit, scan arguments: they depend on the panel ends only), _end waits and returns max |I2 - I1|.
+int sk_subinterval_begin(sk_ctx *c, double a, double b, const sk_subinterval_opts *o) {
+  if (c) c->sub_open = false;
+  int rc = subinterval_builtin_enqueue(c, a, b, o);
+  if (rc == SK_OK) c->sub_open = true;
+  return rc;
+}
+int sk_subinterval_end(sk_ctx *c, double *max_abs_diff) {
+  if (!c || !max_abs_diff) return fail(c, SK_ERR_ARG, "null pointer");
+  if (!c->sub_open) return fail(c, SK_ERR_STATE, "sk_subinterval_begin first");
+  c->sub_open = false;
   return transform_and_stage_finish(c, max_abs_diff, nullptr);
 }
 
@@ -2202,6 +2336,10 @@ static int converge_scan_enqueue(sk_ctx *c, const sk_scan_args *a) {
     int rc = flush_commit(c);
     if (rc != SK_OK) return rc;
   }
+  {
+    int rcz = ensure_res_zero(c);
+    if (rcz != SK_OK) return rcz;
+  }
   k_commit_scan<<<nblk(n, 256), 256, 0, c->stream>>>(c->uxs.p + c->lo, c->pan.p + c->lo, c->res.p + c->lo, n, c->lo, do_commit,
                                                      a->trunc_a, a->trunc_num, a->xpow, a->tau, a->criteria, c->d_red);
   LAUNCH_CHECK();
@@ -2258,6 +2396,8 @@ int sk_converge_apply(sk_ctx *c, const sk_scan_args *a, int64_t new_hi) {
       t.trunc_a = a->trunc_a; t.trunc_num = a->trunc_num; t.xpow = a->xpow;
       t.criteria = a->criteria; t._pad = 0;
     } else {
+      rc = ensure_res_zero(c);
+      if (rc != SK_OK) return rc;
       k_scan_add<<<nblk(nconv, 256), 256, 0, c->stream>>>(c->uxs.p + new_hi, c->res.p + new_hi, nconv, a->trunc_a, a->trunc_num,
                                                           a->xpow, a->criteria);
       LAUNCH_CHECK();
@@ -2286,6 +2426,8 @@ int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
   if (rc != SK_OK) return rc;
   rc = flush_commit(c);
   if (rc != SK_OK) return rc;
+  rc = ensure_res_zero(c);
+  if (rc != SK_OK) return rc;
   if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
   k_gather<<<nblk(c->n_in, 1024), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, vals_dev, errs_dev, c->in.p, c->in_scale, c->tails);
   LAUNCH_CHECK();
@@ -2307,6 +2449,8 @@ static int results_enqueue(sk_ctx *c, double *vals, double *errs) {
   int rc = rollback_speculation(c);
   if (rc != SK_OK) return rc;
   rc = flush_commit(c);
+  if (rc != SK_OK) return rc;
+  rc = ensure_res_zero(c);
   if (rc != SK_OK) return rc;
   CK(c->out_v.ensure(c->n_in));
   if (errs) CK(c->out_e.ensure(c->n_in));
@@ -2364,6 +2508,8 @@ int sk_results_get_async(sk_ctx *c, double *vals, double *errs) {
   int rc = rollback_speculation(c);
   if (rc != SK_OK) return rc;
   rc = flush_commit(c);
+  if (rc != SK_OK) return rc;
+  rc = ensure_res_zero(c);
   if (rc != SK_OK) return rc;
   if (!c->copy_stream) {
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));

@@ -437,9 +437,11 @@ k_k8_finish(SkK8State *__restrict__ st, const unsigned int *__restrict__ fill, c
   }
   const unsigned int uoff = (st->nzero ? 1u : 0u) + uoffp[bin];
   __syncthreads();                                         // s_luid complete
+  // (positions strided by the block: consecutive lanes read consecutive shared-memory words and write consecutive
+  //  -- or, after a dropped duplicate, nearly consecutive -- table entries)
 #pragma unroll
   for (int i = 0; i < SK_K8_EPT; ++i) {
-    const int p = threadIdx.x * SK_K8_EPT + i;
+    const int p = threadIdx.x + i * SK_K8_TPB;
     if (p < cnt && s_head[p]) uxs[uoff + s_luid[p] - 1u] = __longlong_as_double((long long)s_key[p]);
   }
 #pragma unroll

@@ -53,7 +53,11 @@ struct SkSpec {
   // bound min(trunc_a, trunc_num / (2 pi x)) does not increase with x, and IEEE rounding preserves that): the host
   // finds the smallest double xstar with trunc_err(xstar) < tau by bisection on the SAME function (sk_trunc_err), so
   // "x >= xstar" is the same decision for every double x -- one compare per target instead of a division.
-  int use_xstar, _pad;
+  int use_xstar;
+  // fresh = 1: (ks, errs) are still zero everywhere in the panel (the first panel of a run covers every positive
+  // distance): the old pair is not read (it is (0, 0)), no roll-back copy is written (rolling back = zeroing), and the
+  // run needs no memset of the table at all.  Same additions 0 + I2, 0 + |I2-I1|, so the same bits.
+  int fresh;
   double xstar;
   sk_cplx *res;           // (ks, errs), pre-offset to element 0
   sk_cplx *backup;        // old (ks, errs), pre-offset
@@ -158,7 +162,7 @@ __device__ __forceinline__ void sk_emit(const SkSpec &spec, double f1, double f2
   if (!SPEC) {
     stage[j] = out;
   } else {
-    spec.backup[j] = old;       // `old` = spec.res[j], loaded early by the caller to hide the latency
+    if (!spec.fresh) spec.backup[j] = old;       // `old` = spec.res[j], loaded early by the caller to hide the latency
     spec.res[j] = out;
   }
 }
@@ -375,7 +379,7 @@ k_interp_session(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkG
     const double x = xs[j];
     sk_cplx old;
     old.x = old.y = 0.0;
-    if (SPEC) old = spec.res[j];
+    if (SPEC && !spec.fresh) old = spec.res[j];
     sk_interp_point<W, 2>(P, G, x, grid, fre, fim);
     // kernel == :cos -> real part, :sin -> imaginary part (src/quadrature.jl:130-136); then *c (:250-251)
     sk_emit<SPEC>(spec, kernel_sin ? fim[0] : fre[0], kernel_sin ? fim[1] : fre[1], cmul, x, j, stage, acc, old);
@@ -497,7 +501,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       const bool wide = aligned32 && nq == 4;
       if (wide) {
         sk_ld256(xs + j0 + t0, rr[0], rr[1], rr[2], rr[3]);
-        if (SPEC) {
+        if (SPEC && !spec.fresh) {
           sk_ld256(spec.res + j0 + t0, old[0].x, old[0].y, old[1].x, old[1].y);
           sk_ld256(spec.res + j0 + t0 + 2, old[2].x, old[2].y, old[3].x, old[3].y);
         } else {
@@ -509,7 +513,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
         for (int ui = 0; ui < 4; ++ui) {
           rr[ui] = ui < nq ? xs[j0 + t0 + ui] : 0.0;
           old[ui].x = old[ui].y = 0.0;
-          if (SPEC && ui < nq) old[ui] = spec.res[j0 + t0 + ui];
+          if (SPEC && !spec.fresh && ui < nq) old[ui] = spec.res[j0 + t0 + ui];
         }
       }
       int cell[4];
@@ -551,8 +555,10 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
         }
         if (wide) {
           if (SPEC) {
-            sk_st256(spec.backup + j0 + t0, old[0].x, old[0].y, old[1].x, old[1].y);
-            sk_st256(spec.backup + j0 + t0 + 2, old[2].x, old[2].y, old[3].x, old[3].y);
+            if (!spec.fresh) {
+              sk_st256(spec.backup + j0 + t0, old[0].x, old[0].y, old[1].x, old[1].y);
+              sk_st256(spec.backup + j0 + t0 + 2, old[2].x, old[2].y, old[3].x, old[3].y);
+            }
             sk_st256(spec.res + j0 + t0, out[0].x, out[0].y, out[1].x, out[1].y);
             sk_st256(spec.res + j0 + t0 + 2, out[2].x, out[2].y, out[3].x, out[3].y);
           } else {
@@ -563,7 +569,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
 #pragma unroll
           for (int ui = 0; ui < 4; ++ui) {
             if (!SPEC) stage[j0 + t0 + ui] = out[ui];
-            else { spec.backup[j0 + t0 + ui] = old[ui]; spec.res[j0 + t0 + ui] = out[ui]; }
+            else { if (!spec.fresh) spec.backup[j0 + t0 + ui] = old[ui]; spec.res[j0 + t0 + ui] = out[ui]; }
           }
         }
       } else {
@@ -586,7 +592,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       const double r = xs[j0 + t];
       sk_cplx old;
       old.x = old.y = 0.0;
-      if (SPEC) old = spec.res[j0 + t];
+      if (SPEC && !spec.fresh) old = spec.res[j0 + t];
       const SkTargetCoord tc = sk_target_coord<W>(G, r);
       int cl = (int)(tc.l0 - l_first);
       cl = cl < 0 ? 0 : (cl >= ncell ? ncell - 1 : cl);
@@ -612,7 +618,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       const double r = have ? xs[j0 + t] : 0.0;
       sk_cplx old;
       old.x = old.y = 0.0;
-      if (have && SPEC) old = spec.res[j0 + t];
+      if (have && SPEC && !spec.fresh) old = spec.res[j0 + t];
       SkTargetCoord tc;
       tc.l0 = -1;
       tc.s = 0.0;
