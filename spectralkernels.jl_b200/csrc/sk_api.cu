@@ -455,12 +455,12 @@ int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long lon
   const double span = (c->r_hi - c->r_lo) * G.kap_hi + 1.0;
   const double per_block = span * (double)tpb / (double)n;
   const int cmax = per_block <= 24.0 ? 32 : 96;
-  const size_t smem = sizeof(double) * (size_t)(2 * (W / 2) * (SK_NC / 2) + (cmax + W) * 4 + cmax * 4 + cmax * SK_CELL_STRIDE);
+  const size_t smem = sizeof(double) * (size_t)(2 * (W / 2) * (SK_NC / 2) + (cmax + W) * 4 + cmax * 4 + cmax * SK_CELL_STRIDE + tpb);
   // function attributes are per device: remember per context (one context = one device)
   bool &attr_set = c->smem_attr_set[W];
   if (!attr_set) {
-    cudaFuncSetAttribute(k_interp_cells<W, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_interp_cells<W, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_interp_cells<W, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(k_interp_cells<W, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_set = true;
   }
 #define SK_LAUNCH_CELLS(SPECV, MINBV)                                                                                  \

@@ -167,6 +167,18 @@ __device__ __forceinline__ void sk_emit(const SkSpec &spec, double f1, double f2
   }
 }
 
+// asynchronous global -> shared copies (LDGSTS): the data bypasses the register file and the issuing warp does not wait
+__device__ __forceinline__ void sk_cp_async8(void *smem_dst, const void *gsrc) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void sk_cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void sk_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void sk_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // 32-byte global accesses (two (re, im) / (ks, errs) pairs per instruction): a thread that owns adjacent targets moves
 // whole sectors
 __device__ __forceinline__ void sk_ld256(const void *p, double &a, double &b, double &c, double &d) {
@@ -434,10 +446,24 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
   double *sWin = sO + (W / 2) * (SK_NC / 2);            // [(cmax + W)][4]
   double *sQ = sWin + (size_t)(cmax + W) * 4;           // [cmax][4]  deconvolution factor at the 4 Chebyshev nodes
   double *sCoef = sQ + (size_t)cmax * 4;                // [cmax][SK_CELL_STRIDE]: (q, comp) at q * 4 + comp
+  double *sR = sCoef + (size_t)cmax * SK_CELL_STRIDE;   // [256 * tpt] the block's distances, staged asynchronously
   __shared__ sk_cplx sTab[65];                          // (cos, sin)(2 pi k / 64) for the post-phase
   const int tpb = 256 * tpt;
   const long long j0 = (long long)blockIdx.x * tpb;
   const int cnt = (int)((n - j0) < (long long)tpb ? (n - j0) : (long long)tpb);
+  // The block's distances go to shared memory with asynchronous copies (cp.async -> LDGSTS) issued before anything
+  // else: they land while phases A and B build the cell polynomials, so phase C starts from shared memory instead of
+  // waiting for its first global loads (27 % of the stall samples of the previous version sat on those loads).
+  {
+    const double *src = xs + j0;
+    if ((reinterpret_cast<size_t>(src) & 15) == 0) {
+      for (int t = 2 * threadIdx.x; t + 1 < cnt; t += 512) sk_cp_async16(sR + t, src + t);
+      if ((cnt & 1) && threadIdx.x == 0) sk_cp_async8(sR + cnt - 1, src + cnt - 1);
+    } else {
+      for (int t = threadIdx.x; t < cnt; t += 256) sk_cp_async8(sR + t, src + t);
+    }
+    sk_cp_async_commit();
+  }
   const long long l_first = sk_target_coord<W>(G, xs[j0]).l0;
   const long long l_last = sk_target_coord<W>(G, xs[j0 + cnt - 1]).l0;
   const long long ncell_ll = l_last - l_first + 1;
@@ -475,7 +501,8 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       sk_cheb4_to_monomial(sQ + cell * 4, a);
       sk_cell_fold(sCoef + (size_t)cell * SK_CELL_STRIDE + comp, 4, a);
     }
-    __syncthreads();
+    sk_cp_async_wait_all();                                  // this thread's share of sR has landed ...
+    __syncthreads();                                         // ... and so has everybody else's
     // C: Horner.  A thread takes FOUR ADJACENT targets at a time: sorted targets next to each other nearly always share
     // their cell (~150 targets per cell at 1e7), so one pair of 16-byte shared-memory loads per coefficient feeds 16
     // FMAs (4 targets x re/im x two rules) instead of 4, and every thread reads and writes 32 / 64 contiguous bytes of
@@ -489,7 +516,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     __shared__ int sListN;
     if (threadIdx.x == 0) sListN = 0;
     __syncthreads();                                         // (also: every thread is done with sWin / sQ)
-    const bool aligned32 = (((reinterpret_cast<size_t>(xs + j0)) | reinterpret_cast<size_t>(stage + j0) |
+    const bool aligned32 = ((reinterpret_cast<size_t>(stage + j0) |
                              (SPEC ? (reinterpret_cast<size_t>(spec.res + j0) | reinterpret_cast<size_t>(spec.backup + j0)) : 0)) & 31) == 0;
 #pragma unroll 1
     for (int uo = 0; uo < tpt / 4; ++uo) {
@@ -500,7 +527,10 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       sk_cplx old[4];
       const bool wide = aligned32 && nq == 4;
       if (wide) {
-        sk_ld256(xs + j0 + t0, rr[0], rr[1], rr[2], rr[3]);
+        {
+          const double2 r01 = *reinterpret_cast<const double2 *>(sR + t0), r23 = *reinterpret_cast<const double2 *>(sR + t0 + 2);
+          rr[0] = r01.x; rr[1] = r01.y; rr[2] = r23.x; rr[3] = r23.y;
+        }
         if (SPEC && !spec.fresh) {
           sk_ld256(spec.res + j0 + t0, old[0].x, old[0].y, old[1].x, old[1].y);
           sk_ld256(spec.res + j0 + t0 + 2, old[2].x, old[2].y, old[3].x, old[3].y);
@@ -511,7 +541,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
       } else {
 #pragma unroll
         for (int ui = 0; ui < 4; ++ui) {
-          rr[ui] = ui < nq ? xs[j0 + t0 + ui] : 0.0;
+          rr[ui] = ui < nq ? sR[t0 + ui] : 0.0;
           old[ui].x = old[ui].y = 0.0;
           if (SPEC && !spec.fresh && ui < nq) old[ui] = spec.res[j0 + t0 + ui];
         }
@@ -589,7 +619,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     const int nlist = sListN < list_cap ? sListN : list_cap;
     for (int i = threadIdx.x; i < nlist; i += blockDim.x) {  // the parked targets, one per thread
       const int t = sList[i];
-      const double r = xs[j0 + t];
+      const double r = sR[t];
       sk_cplx old;
       old.x = old.y = 0.0;
       if (SPEC && !spec.fresh) old = spec.res[j0 + t];
@@ -606,6 +636,7 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     // L2, 2 coefficient items per lane, fold by 4 lanes) and then evaluate their targets from it -- bit
     // identical to the block path, whatever the tiling (this is what makes results independent of how
     // the targets are sharded over GPUs).
+    sk_cp_async_wait_all();                                // (sR is not used on this path)
     __syncthreads();                                       // sE / sO / sTab ready
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double *wWin = sCoef + (size_t)wid * (W * 4 + 4 + SK_NC * 4);   // [W][4] window
