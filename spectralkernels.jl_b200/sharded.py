@@ -89,10 +89,25 @@ class LibComm:
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         mode = mode or os.environ.get("SK_COMM_TRANSPORT", "peer")
         if mode == "peer" and world <= 16:
-            mine = engine.comm_peer_export()
+            # every rank must end up on the same transport: a rank that cannot export / map the mailboxes (no peer access,
+            # IPC disabled in a container) makes ALL ranks fall back to the NCCL all-reduces
+            try:
+                mine = engine.comm_peer_export()
+            except Exception:
+                mine = None
             handles = [None] * world
             dist.all_gather_object(handles, mine, group=group)      # also: every mailbox is zeroed before anyone writes
-            return cls(engine, rank, world, peer_handles=handles)
+            comm, ok = None, all(h is not None for h in handles)
+            if ok:
+                try:
+                    comm = cls(engine, rank, world, peer_handles=handles)
+                except Exception:
+                    ok = False
+            flags = [None] * world
+            dist.all_gather_object(flags, bool(ok), group=group)
+            if all(flags):
+                return comm
+            engine.comm_destroy()
         box = [engine.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0, group=group)
         return cls(engine, rank, world, uid=box[0])
