@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SK_ABI_VERSION 1
+#define SK_ABI_VERSION 2
 
 /* status codes */
 #define SK_OK 0
@@ -117,6 +117,8 @@ typedef struct sk_stats {
   int64_t n_prefetch_issued;/* sub-intervals whose source side (nodes, strengths, spread, FFT) was computed ahead on the
                                second stream, since the context was created ...                 */
   int64_t n_prefetch_hits;  /* ... and how many of them the driver then actually asked for      */
+  int64_t n_chained;        /* sub-intervals that were enqueued ahead of time behind the previous panel's
+                               (sk_subinterval_chain) and picked up, since sk_run_begin         */
 } sk_stats;
 
 /* ---- library --------------------------------------------------------------------------------- */
@@ -262,6 +264,16 @@ int sk_subinterval(sk_ctx *ctx, double a, double b, const sk_subinterval_opts *o
  * scalar work for the next panel (its ends are known: src/adaptive.jl:152), which then costs no device idle time. */
 int sk_subinterval_begin(sk_ctx *ctx, double a, double b, const sk_subinterval_opts *opts);
 int sk_subinterval_end(sk_ctx *ctx, double *max_abs_diff);
+/* Between _begin and _end of a panel's speculated first sub-interval: enqueue the NEXT panel's first sub-interval
+ * (a2, b2) = (b, b + m k / (2 r_hi)) (src/adaptive.jl:152) behind it, guarded ON THE DEVICE: the kernel runs only if
+ * this sub-interval turns out accepted -- max |I2-I1| < accept_below = tol * k0, no NaN (src/quadrature.jl:260) -- and
+ * its scan converged nothing (so r_hi, and with it (a2, b2), is what the host will compute); otherwise it returns at
+ * once having touched nothing.  opts.speculate must carry the scan arguments of (a2, b2).  When the host reaches that
+ * panel, its sk_subinterval[_begin] with exactly these arguments finds the work done (sk_stats.n_chained); any other
+ * call discards the launch (and rolls it back if it ran).  *chained = 0: not applicable (sharded run, timing on,
+ * sources of (a2, b2) not prefetched, host-evaluated density, dim >= 2): nothing was enqueued. */
+int sk_subinterval_chain(sk_ctx *ctx, double a2, double b2, const sk_subinterval_opts *opts, double accept_below,
+                         int32_t *chained);
 /* same with host-evaluated nodes and (real) strengths: no1/buf1 length m*k, no2/buf2 length 2*m*k
  * (the buffers of src/adaptive.jl:50-53 after updatequadbufs!) */
 int sk_subinterval_host(sk_ctx *ctx, double a, double b, const double *no1, const double *buf1,

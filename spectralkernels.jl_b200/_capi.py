@@ -49,7 +49,7 @@ class Stats(ctypes.Structure):
                 ("n_fast", c_int64), ("n_direct", c_int64), ("kernel_launches", c_int64), ("last_nf", c_int64),
                 ("last_nf2", c_int64), ("n_speculated", c_int64), ("n_spec_rollbacks", c_int64), ("interp_ms", c_double), ("source_ms", c_double),
                 ("timing_enabled", c_int32), ("sort_two_level", c_int32), ("n_hankel", c_int64), ("sort_ms", c_double),
-                ("gather_ms", c_double), ("n_prefetch_issued", c_int64), ("n_prefetch_hits", c_int64)]
+                ("gather_ms", c_double), ("n_prefetch_issued", c_int64), ("n_prefetch_hits", c_int64), ("n_chained", c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
@@ -85,6 +85,7 @@ SIGNATURES = {
     "sk_targets_end": (c_int, [c_void_p, c_void_p]),
     "sk_subinterval_begin": (c_int, [c_void_p, c_double, c_double, c_void_p]),
     "sk_subinterval_end": (c_int, [c_void_p, _dp]),
+    "sk_subinterval_chain": (c_int, [c_void_p, c_double, c_double, c_void_p, c_double, POINTER(c_int32)]),
     "sk_comm_peer_export": (c_int, [c_void_p, c_void_p]),
     "sk_comm_peer_attach": (c_int, [c_void_p, c_void_p, c_int32, c_int32]),
     "sk_comm_allgather": (c_int, [c_void_p, _dp, c_int32, _dp]),
@@ -421,6 +422,15 @@ class Session:
                             ctypes.pointer(speculate) if speculate is not None else None)
         self._sub_keep = (o, speculate)
         self._ck(self._L.sk_subinterval_begin(self._h, float(a), float(b), byref(o)))
+
+    def subinterval_chain(self, a2: float, b2: float, cmul: float, p: float, kernel: int, logw: bool, speculate,
+                          accept_below: float, nu: int = 0, xdiv_pow: float = 0.0) -> bool:
+        """enqueue the next panel's first sub-interval behind the one in flight, guarded on the device"""
+        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0, int(nu), 0, float(xdiv_pow),
+                            ctypes.pointer(speculate))
+        done = c_int32(0)
+        self._ck(self._L.sk_subinterval_chain(self._h, float(a2), float(b2), byref(o), float(accept_below), byref(done)))
+        return bool(done.value)
 
     def subinterval_end(self) -> float:
         out = c_double()

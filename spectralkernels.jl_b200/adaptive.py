@@ -339,7 +339,13 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
                     hasattr(eng, "subinterval_begin"):
                 eng.subinterval_begin(_a, _b, cfg.c, cfg.p, kernel, cfg.logw, speculate=spec, nu=nu, xdiv_pow=xdiv)
                 try:
-                    while_enqueued()
+                    nxt = while_enqueued()
+                    if nxt is not None and comm.world_size == 1 and hasattr(eng, "subinterval_chain"):
+                        # the next panel's first sub-interval goes in behind this one, guarded on the device: it runs
+                        # only if this one is accepted (:260) and converges nothing (sk_subinterval_chain)
+                        a2, b2, sargs2 = nxt
+                        eng.subinterval_chain(a2, b2, cfg.c, cfg.p, kernel, cfg.logw, sargs2, cfg.tol * k0, nu=nu,
+                                              xdiv_pow=xdiv)
                 finally:
                     mx = eng.subinterval_end()
             elif builtin:
@@ -502,7 +508,11 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
             # the next panel if this one converges nothing (the usual outcome of a run's first panels): same r_hi
             b2 = a2 + quadm / (2 * r)
             if math.isfinite(b2) and b2 > a2:
-                pre[(a2, b2, crit2)] = _panel_scalars(cfg, a2, b2, crit2, tau)
+                ps = _panel_scalars(cfg, a2, b2, crit2, tau)
+                pre[(a2, b2, crit2)] = ps
+                if ps[2] == crit2:              # (a failed tail fit changes the criteria: the host decides that later)
+                    return a2, b2, ps[4]
+            return None
 
         spec_state = {}
         fourier_integrate_interval(cfg, eng, a, b, abs(k0), comm, active, verbose=verbose, trace=trace,

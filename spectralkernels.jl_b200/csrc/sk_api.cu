@@ -142,10 +142,14 @@ struct sk_ctx {
   struct SrcSet {
     DevBuf<double> no1, buf1, no2, buf2, pos_hi1, pos_lo1, pos_hi2, pos_lo2;
     DevBuf<sk_cplx> cs1, cs2, fft;
-  } pf;
+  } pf, pf2;                                 // pf: the next request; pf2: the one after it (promoted when pf is taken)
   bool pf_valid = false, need_gen = false, prefetch_on = true;
   SkPanelSpec pf_S, pend_S;
   SkGeom pf_G;
+  bool pf2_valid = false;
+  SkPanelSpec pf2_S;
+  SkGeom pf2_G;
+  cudaEvent_t pf2_ev = nullptr;
   cudaStream_t stream_main = nullptr, stream2 = nullptr;
   cudaEvent_t pf_ev = nullptr;
   cudaEvent_t k8_ev = nullptr;
@@ -240,6 +244,18 @@ struct sk_ctx {
   SkTargetSummary *d_sum = nullptr;
 
   SkReduceOut *d_red = nullptr;
+  SkReduceOut *red_target = nullptr;         // where the interpolation kernel reduces to (d_red, or the chain's d_red2)
+  // chained launch of the next panel's first sub-interval (sk_subinterval_chain, SkSpec::guard)
+  struct Chain {
+    bool pending = false, adopted = false;
+    double a = 0, b = 0, r_lo = 0, r_hi = 0;
+    long long lo = 0, hi = 0;
+    sk_subinterval_opts o;
+    sk_scan_args sa;
+  } chain;
+  SkGeom chain_G;
+  SkReduceOut *d_red2 = nullptr, *h_red2 = nullptr;
+  cudaEvent_t ev_red = nullptr, ev_red2 = nullptr;
   HostScalars *h_scal = nullptr;  // pinned
 
   // stats / timing
@@ -293,6 +309,7 @@ int fail(sk_ctx *c, int code, const char *fmt, ...) {
 inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
 int flush_commit(sk_ctx *c);
 int ensure_res_zero(sk_ctx *c);
+int chain_discard(sk_ctx *c);
 
 #define NCK(call)                                                                                     \
   do {                                                                                                \
@@ -444,9 +461,9 @@ template <int W>
 int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long long n, double cmul, int ksin, const SkSpec &spec) {
   if (c->interp_mode == 1) {
     if (spec.on)
-      k_interp_session<W, true><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage.p + c->lo, spec, c->d_red);
+      k_interp_session<W, true><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage.p + c->lo, spec, (c->red_target ? c->red_target : c->d_red));
     else
-      k_interp_session<W, false><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage.p + c->lo, spec, c->d_red);
+      k_interp_session<W, false><<<nblk(n, 256), 256, 0, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, c->stage.p + c->lo, spec, (c->red_target ? c->red_target : c->d_red));
     return 0;
   }
   // cells the active targets span -> average targets per cell -> how many cells a block may hold
@@ -465,7 +482,7 @@ int launch_interp_session(sk_ctx *c, const SkGeom &G, const double *xs, long lon
   }
 #define SK_LAUNCH_CELLS(SPECV, MINBV)                                                                                  \
   k_interp_cells<W, SPECV, MINBV><<<nblk(n, tpb), 256, smem, c->stream>>>(c->plan, G, xs, n, c->fft.p, cmul, ksin, cmax, tpt, \
-                                                                              c->stage.p + c->lo, spec, c->d_red)
+                                                                              c->stage.p + c->lo, spec, (c->red_target ? c->red_target : c->d_red))
   if (spec.on) SK_LAUNCH_CELLS(true, 2); else SK_LAUNCH_CELLS(false, 2);
 #undef SK_LAUNCH_CELLS
   return 0;
@@ -679,6 +696,72 @@ int prefetch_sources(sk_ctx *c, const SkPanelSpec &S, const SkGeom &G) {
   return SK_OK;
 }
 
+// the same into the SECOND prefetch set: the request after the next one (both panels of a typical run are known as soon
+// as the distance range is: (0, b1) and (b1, b1 + m k / (2 r_hi)), src/adaptive.jl:152)
+int prefetch_sources_second(sk_ctx *c, const SkPanelSpec &S, const SkGeom &G) {
+  const bool v1 = c->pf_valid;
+  const SkPanelSpec S1 = c->pf_S;
+  const SkGeom G1 = c->pf_G;
+  std::swap(c->pf, c->pf2);
+  std::swap(c->pf_ev, c->pf2_ev);
+  const int rc = prefetch_sources(c, S, G);
+  c->pf2_valid = c->pf_valid;
+  c->pf2_S = c->pf_S;
+  c->pf2_G = c->pf_G;
+  std::swap(c->pf, c->pf2);
+  std::swap(c->pf_ev, c->pf2_ev);
+  c->pf_valid = v1;
+  c->pf_S = S1;
+  c->pf_G = G1;
+  return rc;
+}
+// the first set was just taken (its buffers are the current set now, the old current set sits in pf): the second set moves up
+void promote_second_prefetch(sk_ctx *c) {
+  c->pf_valid = false;
+  if (!c->pf2_valid) return;
+  std::swap(c->pf, c->pf2);
+  std::swap(c->pf_ev, c->pf2_ev);
+  c->pf_S = c->pf2_S;
+  c->pf_G = c->pf2_G;
+  c->pf_valid = true;
+  c->pf2_valid = false;
+}
+
+// the device-side form of the scan arguments a speculated sub-interval carries (SkSpec; `fresh` and the chain guard are
+// set by the caller)
+void fill_spec(sk_ctx *c, const sk_scan_args *sa, SkSpec &spec) {
+  spec.on = 1;
+  spec.criteria = sa->criteria;
+  spec.lo0 = c->lo;
+  spec.trunc_a = sa->trunc_a;
+  spec.trunc_num = sa->trunc_num;
+  spec.xpow = sa->xpow;
+  spec.tau = sa->tau;
+  // exact threshold distance of the truncation half of the predicate (SkSpec::xstar), dim = 1 (x^1: no pow())
+  spec.use_xstar = 0;
+  spec.xstar = 0.0;
+  if (spec.criteria != 0 && spec.xpow == 1.0 && spec.trunc_num > 0.0 && std::isfinite(spec.trunc_num) &&
+      spec.trunc_a == spec.trunc_a && spec.tau == spec.tau) {
+    auto pred = [&](double x) { return sk_trunc_err(spec.trunc_a, spec.trunc_num, 1.0, x, 0) < spec.tau; };
+    const double dmax = 1.7976931348623157e308, dmin = 4.9406564584124654e-324;
+    if (pred(dmin)) { spec.use_xstar = 1; spec.xstar = 0.0; }                 // every positive distance passes
+    else if (!pred(dmax)) { spec.use_xstar = 1; spec.xstar = INFINITY; }      // none does
+    else {
+      unsigned long long lo_b = 1ull, hi_b = 0x7fefffffffffffffull;          // pred(lo) false, pred(hi) true
+      while (hi_b - lo_b > 1ull) {
+        const unsigned long long mid = lo_b + (hi_b - lo_b) / 2;
+        double xm;
+        std::memcpy(&xm, &mid, sizeof(double));
+        if (pred(xm)) hi_b = mid; else lo_b = mid;
+      }
+      std::memcpy(&spec.xstar, &hi_b, sizeof(double));
+      spec.use_xstar = 1;
+    }
+  }
+  spec.res = c->res.p + c->lo;
+  spec.backup = c->stage.p + c->lo;
+}
+
 // transform + stage for the sub-interval whose sources are in no1/buf1/no2/buf2, in two halves: everything that is
 // enqueued on the context's stream, and the read-back of the reduced scalars after the stream has drained.  One
 // context runs the halves back to back (transform_and_stage); a device group (sk_group_*) enqueues on every device
@@ -711,36 +794,7 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
     }
     int rc = flush_commit(c);            // res must be current before it is updated in place
     if (rc != SK_OK) return rc;
-    spec.on = 1;
-    spec.criteria = o->speculate->criteria;
-    spec.lo0 = c->lo;
-    spec.trunc_a = o->speculate->trunc_a;
-    spec.trunc_num = o->speculate->trunc_num;
-    spec.xpow = o->speculate->xpow;
-    spec.tau = o->speculate->tau;
-    // exact threshold distance of the truncation half of the predicate (SkSpec::xstar), dim = 1 (x^1: no pow())
-    spec.use_xstar = 0;
-    spec.xstar = 0.0;
-    if (spec.criteria != 0 && spec.xpow == 1.0 && spec.trunc_num > 0.0 && std::isfinite(spec.trunc_num) &&
-        spec.trunc_a == spec.trunc_a && spec.tau == spec.tau) {
-      auto pred = [&](double x) { return sk_trunc_err(spec.trunc_a, spec.trunc_num, 1.0, x, 0) < spec.tau; };
-      const double dmax = 1.7976931348623157e308, dmin = 4.9406564584124654e-324;
-      if (pred(dmin)) { spec.use_xstar = 1; spec.xstar = 0.0; }                 // every positive distance passes
-      else if (!pred(dmax)) { spec.use_xstar = 1; spec.xstar = INFINITY; }      // none does
-      else {
-        unsigned long long lo_b = 1ull, hi_b = 0x7fefffffffffffffull;          // pred(lo) false, pred(hi) true
-        while (hi_b - lo_b > 1ull) {
-          const unsigned long long mid = lo_b + (hi_b - lo_b) / 2;
-          double xm;
-          std::memcpy(&xm, &mid, sizeof(double));
-          if (pred(xm)) hi_b = mid; else lo_b = mid;
-        }
-        std::memcpy(&spec.xstar, &hi_b, sizeof(double));
-        spec.use_xstar = 1;
-      }
-    }
-    spec.res = c->res.p + c->lo;
-    spec.backup = c->stage.p + c->lo;
+    fill_spec(c, o->speculate, spec);
   }
   SkReduceOut init;
   std::memset(&init, 0, sizeof(init));
@@ -766,13 +820,14 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
       c->n_pf_hits++;
       c->stats.last_nf = G.nf;
       c->stats.last_nf2 = G.nf2;
+      promote_second_prefetch(c);
     } else {
       int rc = launch_gen_sources(c, c->pend_S);
       if (rc != SK_OK) return rc;
     }
     c->have_sources = true;
   }
-  c->pf_valid = false;                       // a prefetch is good for the very next request only
+  if (!served) c->pf_valid = c->pf2_valid = false;   // a prefetch is good for the very request it was made for
   // dim >= 2: the reference calls nufht whenever its NUFFT cutoff holds (src/quadrature.jl:139-143); here the
   // O(N) scheme is taken when it is cheaper than the direct Bessel summation (more than ~4096 active targets)
   int hk_rc = SK_ERR_UNSUPPORTED;
@@ -804,8 +859,12 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
       if (std::isfinite(b2) && b2 > a2 && sk_make_geom(c->plan, a2, b2, c->r_lo, c->r_hi, &G2) == 0) {
         SkPanelSpec S2;
         make_panel_spec(c, a2, b2, o->logw, &S2);
-        int rc = prefetch_sources(c, S2, G2);
-        if (rc != SK_OK) return rc;
+        const bool waiting = c->pf_valid && std::memcmp(&c->pf_S, &S2, sizeof(SkPanelSpec)) == 0 &&
+                             std::memcmp(&c->pf_G, &G2, sizeof(SkGeom)) == 0;      // (prefetched next to the sort already)
+        if (!waiting) {
+          int rc = prefetch_sources(c, S2, G2);
+          if (rc != SK_OK) return rc;
+        }
       }
     }
   } else if (bessel && hk_rc == SK_OK) {
@@ -826,6 +885,7 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
     c->stats.n_direct++;
   }
   CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaEventRecord(c->ev_red, c->stream));
   c->pend_timed = c->timing && (fast || hk_timed);
   c->pend_spec = spec_on;
   if (spec_on) c->spec_args = *o->speculate;
@@ -856,7 +916,29 @@ int transform_and_stage_enqueue(sk_ctx *c, double a, double b, const sk_subinter
 // to the flags of all devices) instead of raising SK_ERR_NAN here
 int transform_and_stage_finish(sk_ctx *c, double *max_abs_diff, unsigned int *flags_out) {
   const long long n_act = c->hi - c->lo;
-  CK(cudaStreamSynchronize(c->stream));
+  if (c->chain.pending && c->chain.adopted) {
+    // this sub-interval was enqueued ahead of time (sk_subinterval_chain): its scalars are in the chain's slot
+    CK(cudaEventSynchronize(c->ev_red2));
+    c->chain.pending = c->chain.adopted = false;
+    if (c->h_red2->flags & SK_FLAG_SKIPPED) {
+      // the guard did not hold after all (cannot happen when the caller follows src/adaptive.jl:149-200, kept for
+      // safety): nothing was touched, evaluate the sub-interval now
+      sk_subinterval_opts o = c->chain.o;
+      o.speculate = &c->chain.sa;
+      make_panel_spec(c, c->chain.a, c->chain.b, o.logw, &c->pend_S);
+      c->need_gen = true;
+      int rc = transform_and_stage_enqueue_local(c, c->chain.a, c->chain.b, &o);
+      if (rc != SK_OK) return rc;
+      CK(cudaStreamSynchronize(c->stream));
+    } else {
+      c->h_scal->red = *c->h_red2;
+      c->stats.n_chained++;
+    }
+  } else if (c->chain.pending) {
+    CK(cudaEventSynchronize(c->ev_red));      // a chained launch is queued behind this sub-interval: do not wait for it
+  } else {
+    CK(cudaStreamSynchronize(c->stream));
+  }
   if (sharded(c)) {
     if (c->pend_rc != SK_OK) return c->pend_rc;                     // this rank's own failure (message already set)
     const int prc = peer_check(c, 0);
@@ -919,6 +1001,27 @@ int rollback_speculation(sk_ctx *c) {
     c->stats.n_spec_rollbacks++;
   }
   return SK_OK;
+}
+
+// a chained launch the host did not pick up: if it ran (its guard held) its speculative commit is rolled back
+int chain_discard(sk_ctx *c) {
+  if (!c->chain.pending) return SK_OK;
+  c->chain.pending = c->chain.adopted = false;
+  CK(cudaEventSynchronize(c->ev_red2));
+  if (!(c->h_red2->flags & SK_FLAG_SKIPPED)) {
+    const long long n = c->chain.hi - c->chain.lo;
+    k_restore<<<nblk(n, 256), 256, 0, c->stream>>>(c->res.p + c->chain.lo, c->stage.p + c->chain.lo, n);
+    LAUNCH_CHECK();
+  }
+  return SK_OK;
+}
+
+bool chain_matches(const sk_ctx *c, double a, double b, const sk_subinterval_opts *o) {
+  const sk_ctx::Chain &h = c->chain;
+  return h.pending && !h.adopted && a == h.a && b == h.b && c->lo == h.lo && c->hi == h.hi && c->r_lo == h.r_lo &&
+         c->r_hi == h.r_hi && c->panel_subs == 0 && !c->timing && o->cmul == h.o.cmul && o->p == h.o.p &&
+         o->kernel == h.o.kernel && o->logw == h.o.logw && o->nu == h.o.nu && o->xdiv_pow == h.o.xdiv_pow &&
+         o->speculate != nullptr && std::memcmp(o->speculate, &h.sa, sizeof(sk_scan_args)) == 0;
 }
 
 // Rules are generated on the device (k_gauss_rules: Newton in double, then double-double) and kept for the life of
@@ -1082,7 +1185,17 @@ int targets_early_prefetch(sk_ctx *c, double r_lo, double r_hi) {
   if (!(std::isfinite(b1) && b1 > 0.0) || sk_make_geom(c->plan, 0.0, b1, r_lo, r_hi, &G1) != 0) return SK_OK;
   SkPanelSpec S1;
   make_panel_spec(c, 0.0, b1, c->last_logw, &S1);
-  return prefetch_sources(c, S1, G1);
+  int rc = prefetch_sources(c, S1, G1);
+  if (rc != SK_OK) return rc;
+  // ... and of the second panel (b1, b1 + m k / (2 r_hi)): the first panel of a run rarely converges anything
+  const double b2 = b1 + (double)((long long)c->m * c->k) / (2 * r_hi);
+  SkGeom G2;
+  if (std::isfinite(b2) && b2 > b1 && sk_make_geom(c->plan, b1, b2, r_lo, r_hi, &G2) == 0) {
+    SkPanelSpec S2;
+    make_panel_spec(c, b1, b2, c->last_logw, &S2);
+    rc = prefetch_sources_second(c, S2, G2);
+  }
+  return rc;
 }
 
 // K8 (sk_k8.cuh): c->in holds the n_in raw distances -> sorted unique table c->uxs, inverse map c->inv.  One host
@@ -1090,6 +1203,10 @@ int targets_early_prefetch(sk_ctx *c, double r_lo, double r_hi) {
 // costs one read pass.  Two halves like transform_and_stage (a device group sorts all chunks concurrently).
 int targets_enqueue(sk_ctx *c, long long n_in) {
   NvtxRange nvtx("unique / sort (K8)");
+  {
+    int rcd = chain_discard(c);
+    if (rcd != SK_OK) return rcd;
+  }
   c->have_targets = false;
   c->early_lo = c->early_hi = 0.0;
   const double *src = c->in_src ? c->in_src : c->in.p;      // (the caller's device buffer, or the library's copy)
@@ -1310,9 +1427,19 @@ int sk_ctx_create(int device, sk_ctx **out) {
   for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
   for (int i = 0; i < 2; ++i) cudaEventCreate(&c->ev_user[i]);
   c->stream_main = c->stream;
-  if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+  // the prefetch / copy stream gets the highest priority: its small source-side kernels (spread, FFT of the NEXT panel)
+  // run next to an interpolation kernel whose thousands of queued blocks would otherwise keep them waiting -- and the
+  // next panel (chained right behind, sk_subinterval_chain) cannot start before they are done
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->pf_ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->pf2_ev, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->k8_ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_red, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_red2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc((void **)&c->d_red2, sizeof(SkReduceOut)) != cudaSuccess ||
+      cudaHostAlloc((void **)&c->h_red2, sizeof(SkReduceOut), cudaHostAllocDefault) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->in_ev[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->in_ev[1], cudaEventDisableTiming) != cudaSuccess) {
     delete c;
@@ -1362,6 +1489,10 @@ int sk_ctx_destroy(sk_ctx *c) {
   c->k8_ctl.release(); c->k8_ctab.release(); c->k8_slots.release();
   if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
   if (c->pf_ev) cudaEventDestroy(c->pf_ev);
+  if (c->pf2_ev) cudaEventDestroy(c->pf2_ev);
+  c->pf2.no1.release(); c->pf2.buf1.release(); c->pf2.no2.release(); c->pf2.buf2.release();
+  c->pf2.pos_hi1.release(); c->pf2.pos_lo1.release(); c->pf2.pos_hi2.release(); c->pf2.pos_lo2.release();
+  c->pf2.cs1.release(); c->pf2.cs2.release(); c->pf2.fft.release();
   if (c->k8_ev) cudaEventDestroy(c->k8_ev);
   for (int i = 0; i < 2; ++i) if (c->in_ev[i]) cudaEventDestroy(c->in_ev[i]);
   for (int i = 0; i < SK_GATHER_SLICES; ++i) if (c->ev_slice[i]) cudaEventDestroy(c->ev_slice[i]);
@@ -1369,6 +1500,10 @@ int sk_ctx_destroy(sk_ctx *c) {
   c->pf.pos_hi1.release(); c->pf.pos_lo1.release(); c->pf.pos_hi2.release(); c->pf.pos_lo2.release();
   c->pf.cs1.release(); c->pf.cs2.release(); c->pf.fft.release();
   if (c->d_red) cudaFree(c->d_red);
+  if (c->d_red2) cudaFree(c->d_red2);
+  if (c->h_red2) cudaFreeHost(c->h_red2);
+  if (c->ev_red) cudaEventDestroy(c->ev_red);
+  if (c->ev_red2) cudaEventDestroy(c->ev_red2);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 2; ++i) if (c->ev_user[i]) cudaEventDestroy(c->ev_user[i]);
@@ -1387,7 +1522,7 @@ int sk_ctx_set_timing(sk_ctx *c, int enabled) {
 int sk_ctx_set_nufft_eps(sk_ctx *c, double eps) {
   if (!c || !(eps > 0) || !(eps < 1)) return fail(c, SK_ERR_ARG, "eps must be in (0,1)");
   c->eps = eps;
-  c->pf_valid = false;
+  c->pf_valid = c->pf2_valid = false;
   if (sk_plan_make_es(width_from_eps(eps), &c->plan) != 0) return fail(c, SK_ERR_ARG, "cannot plan for eps=%g", eps);
   return SK_OK;
 }
@@ -1712,7 +1847,7 @@ int sk_nufft1d3(sk_ctx *c, int64_t M, const double *w, const double *s, int64_t 
   };
   if (rc == SK_OK) rc = body();
   c->plan = saved;
-  c->pf_valid = false;
+  c->pf_valid = c->pf2_valid = false;
   c->have_sources = false;
   c->have_targets = false;  // the target buffer was reused
   return rc;
@@ -1770,7 +1905,7 @@ int sk_rule_set(sk_ctx *c, int32_t m, int32_t k, double p, const double *leg_no1
   CK(c->no1.ensure(M1)); CK(c->buf1.ensure(M1)); CK(c->no2.ensure(2 * M1)); CK(c->buf2.ensure(2 * M1));
   CK(cudaStreamSynchronize(c->stream));
   c->m = m; c->k = k; c->p = p;
-  c->pf_valid = false;
+  c->pf_valid = c->pf2_valid = false;
   c->have_rule = true;
   c->rule_generated = !given_leg && !(c->have_jac && given_jac);
   return SK_OK;
@@ -1956,6 +2091,10 @@ int sk_run_begin(sk_ctx *c) {
   if (!c) return SK_ERR_ARG;
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "sk_targets_set first");
   CK(cudaSetDevice(c->device));
+  {
+    int rcd = chain_discard(c);
+    if (rcd != SK_OK) return rcd;
+  }
   const bool t = c->timing;
   const int two = c->stats.sort_two_level;
   const double sort_ms = c->stats.sort_ms;
@@ -2056,6 +2195,27 @@ static int subinterval_builtin_enqueue(sk_ctx *c, double a, double b, const sk_s
   const bool origin = (a == 0.0 && c->p != 0.0);                    // src/quadrature.jl:185
   if (origin && o->logw)
     return fail(c, SK_ERR_UNSUPPORTED, "log-weighted origin sub-interval needs df: use sk_subinterval_logw_host (src/quadrature.jl:186-228)");
+  if (c->chain.pending) {
+    if (chain_matches(c, a, b, o)) {
+      // this very sub-interval was enqueued ahead of time: nothing to launch, _finish reads the chain's scalars
+      c->chain.adopted = true;
+      c->pend_spec = true;
+      c->pend_timed = false;
+      c->pend_rc = SK_OK;
+      c->pend_ab = false;
+      c->spec_args = c->chain.sa;
+      c->spec_fresh = false;
+      c->need_gen = false;
+      c->have_sources = true;
+      c->last_logw = o->logw ? 1 : 0;
+      c->stats.n_fast++;
+      c->stats.last_nf = c->chain_G.nf;
+      c->stats.last_nf2 = c->chain_G.nf2;
+      return SK_OK;
+    }
+    rc = chain_discard(c);
+    if (rc != SK_OK) return rc;
+  }
   make_panel_spec(c, a, b, o->logw, &c->pend_S);
   c->need_gen = true;                       // generated -- or taken from the prefetch set -- in transform_and_stage
   c->last_logw = o->logw ? 1 : 0;
@@ -2068,6 +2228,65 @@ int sk_subinterval(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, 
   int rc = subinterval_builtin_enqueue(c, a, b, o);
   if (rc != SK_OK) return rc;
   return transform_and_stage_finish(c, max_abs_diff, nullptr);
+}
+
+// Between sk_subinterval_begin and sk_subinterval_end of a panel's speculated first sub-interval: enqueue the NEXT
+// panel's first sub-interval (a2, b2) right behind it, guarded on the device (SkSpec::guard): it runs only if this
+// sub-interval turns out accepted (max |I2-I1| < accept_below, no NaN) with nothing converged.  The host then finds
+// the next panel already integrated when it gets there (its sk_subinterval[_begin] with exactly these arguments picks
+// the launch up) -- the scalar work between two panels costs no device idle time.  *chained = 0: not applicable here
+// (sharded run, timing on, sources not prefetched, ...): nothing was enqueued, carry on as usual.
+int sk_subinterval_chain(sk_ctx *c, double a2, double b2, const sk_subinterval_opts *o, double accept_below, int32_t *chained) {
+  if (!c || !o || !chained) return SK_ERR_ARG;
+  *chained = 0;
+  if (!c->sub_open || !c->pend_spec || c->chain.pending || sharded(c) || c->in_group || c->timing || c->interp_mode != 0 ||
+      c->family == SK_SDF_HOST || o->speculate == nullptr || (o->kernel != SK_KERNEL_COS && o->kernel != SK_KERNEL_SIN) ||
+      o->p != c->p || !(a2 > 0.0) || !(b2 > a2) || !(accept_below > 0.0) || c->pend_rc != SK_OK ||
+      o->speculate->criteria < 0 || o->speculate->criteria > 2)
+    return SK_OK;
+  CK(cudaSetDevice(c->device));
+  const long long n_act = c->hi - c->lo, M2 = 2LL * c->m * c->k;
+  if (!((M2 * n_act > (1LL << 18)) && n_act > 1)) return SK_OK;
+  SkGeom G2;
+  if (sk_make_geom(c->plan, a2, b2, c->r_lo, c->r_hi, &G2) != 0) return SK_OK;
+  SkPanelSpec S2;
+  make_panel_spec(c, a2, b2, o->logw, &S2);
+  if (!c->pf_valid || std::memcmp(&c->pf_S, &S2, sizeof(SkPanelSpec)) != 0 || std::memcmp(&c->pf_G, &G2, sizeof(SkGeom)) != 0)
+    return SK_OK;                                    // the sources of (a2, b2) are not waiting in the prefetch set
+  SkSpec spec;
+  std::memset(&spec, 0, sizeof(spec));
+  fill_spec(c, o->speculate, spec);
+  spec.guard = c->d_red;
+  std::memcpy(&spec.guard_maxbits, &accept_below, sizeof(double));
+  spec.guard_top = c->hi - 1;
+  SkReduceOut init;
+  std::memset(&init, 0, sizeof(init));
+  init.max_unconv = c->lo - 1;
+  *c->h_red2 = init;
+  CK(cudaMemcpyAsync(c->d_red2, c->h_red2, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamWaitEvent(c->stream, c->pf_ev, 0));
+  swap_src_sets(c);                                  // the prefetched sources / grids become the current set
+  c->n_pf_hits++;
+  promote_second_prefetch(c);
+  c->red_target = c->d_red2;
+  const int ksin = o->kernel == SK_KERNEL_SIN;
+#define CALL(WW) launch_interp_session<WW>(c, G2, c->uxs.p + c->lo, n_act, o->cmul, ksin, spec)
+  DISPATCH_W(c->plan.w, CALL)
+#undef CALL
+  c->red_target = nullptr;
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(c->h_red2, c->d_red2, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaEventRecord(c->ev_red2, c->stream));
+  c->chain.pending = true;
+  c->chain.adopted = false;
+  c->chain.a = a2; c->chain.b = b2; c->chain.r_lo = c->r_lo; c->chain.r_hi = c->r_hi;
+  c->chain.lo = c->lo; c->chain.hi = c->hi;
+  c->chain.o = *o;
+  c->chain.sa = *o->speculate;
+  c->chain.o.speculate = nullptr;
+  c->chain_G = G2;
+  *chained = 1;
+  return SK_OK;
 }
 
 // sk_subinterval in two halves (built-in densities): _begin enqueues the sub-interval, the host does its scalar work for
@@ -2088,6 +2307,8 @@ int sk_subinterval_end(sk_ctx *c, double *max_abs_diff) {
 static int subinterval_host_enqueue(sk_ctx *c, double a, double b, const double *no1, const double *buf1, const double *no2,
                                     const double *buf2, const sk_subinterval_opts *o) {
   int rc = subinterval_prologue(c, a, b, o);
+  if (rc != SK_OK) return rc;
+  rc = chain_discard(c);
   if (rc != SK_OK) return rc;
   if (!no1 || !buf1 || !no2 || !buf2) return fail(c, SK_ERR_ARG, "null pointer");
   const long long M1 = (long long)c->m * c->k;
@@ -2119,7 +2340,7 @@ static int logw_host_enqueue_local(sk_ctx *c, double a, double b, const double *
   CK(c->bufb1.ensure(M1));
   CK(c->bufb2.ensure(M2));
   c->need_gen = false;
-  c->pf_valid = false;
+  c->pf_valid = c->pf2_valid = false;
   if (no1) {            // host-evaluated integrands (arbitrary closures: Julia owns f and df)
     CK(cudaMemcpyAsync(c->no1.p, no1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->buf1.p, bufa1, sizeof(double) * M1, cudaMemcpyHostToDevice, c->stream));
@@ -2208,6 +2429,8 @@ int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, c
                              const double *no2, const double *bufa2, const double *bufb2, const sk_subinterval_opts *o,
                              double i0_coef, double denom, double *max_abs_diff) {
   int rc = subinterval_prologue(c, a, b, o);
+  if (rc != SK_OK) return rc;
+  rc = chain_discard(c);
   if (rc != SK_OK) return rc;
   if (!max_abs_diff) return fail(c, SK_ERR_ARG, "null pointer");
   const bool all_null = !no1 && !bufa1 && !bufb1 && !no2 && !bufa2 && !bufb2;
@@ -2424,6 +2647,8 @@ int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
   int rc = rollback_speculation(c);
   if (rc != SK_OK) return rc;
+  rc = chain_discard(c);
+  if (rc != SK_OK) return rc;
   rc = flush_commit(c);
   if (rc != SK_OK) return rc;
   rc = ensure_res_zero(c);
@@ -2447,6 +2672,8 @@ static int results_enqueue(sk_ctx *c, double *vals, double *errs) {
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
   CK(cudaSetDevice(c->device));
   int rc = rollback_speculation(c);
+  if (rc != SK_OK) return rc;
+  rc = chain_discard(c);
   if (rc != SK_OK) return rc;
   rc = flush_commit(c);
   if (rc != SK_OK) return rc;
@@ -2506,6 +2733,8 @@ int sk_results_get_async(sk_ctx *c, double *vals, double *errs) {
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
   CK(cudaSetDevice(c->device));
   int rc = rollback_speculation(c);
+  if (rc != SK_OK) return rc;
+  rc = chain_discard(c);
   if (rc != SK_OK) return rc;
   rc = flush_commit(c);
   if (rc != SK_OK) return rc;

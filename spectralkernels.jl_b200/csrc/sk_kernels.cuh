@@ -29,6 +29,7 @@
 #define SK_FLAG_NAN1 1u
 #define SK_FLAG_NAN2 2u
 #define SK_FLAG_NAND 4u
+#define SK_FLAG_SKIPPED 8u    // a chained launch whose guard did not hold: nothing was touched
 
 struct SkReduceOut {            // device scalars written by the reductions
   unsigned long long maxbits;   // bit pattern of max |I2-I1| (non-negative doubles order like integers)
@@ -61,7 +62,23 @@ struct SkSpec {
   double xstar;
   sk_cplx *res;           // (ks, errs), pre-offset to element 0
   sk_cplx *backup;        // old (ks, errs), pre-offset
+  // Chained launch (sk_subinterval_chain): the NEXT panel's first sub-interval is enqueued behind this panel's before the
+  // host has seen this panel's outcome.  It runs only if that outcome is the one the host predicted -- the previous
+  // sub-interval accepted (max |I2-I1| below the accept threshold, no NaN: src/quadrature.jl:260) and the scan
+  // converged nothing (highest unconverged index = top of the panel, so r_hi and with it the next panel's ends are
+  // unchanged: src/adaptive.jl:152) -- and otherwise returns at once with SK_FLAG_SKIPPED, having touched nothing.
+  const SkReduceOut *guard;          // nullptr: no guard
+  unsigned long long guard_maxbits;  // run only if guard->maxbits < guard_maxbits ...
+  long long guard_top;               // ... and guard->max_unconv == guard_top and guard->flags == 0
 };
+
+__device__ __forceinline__ bool sk_chain_guard_holds(const SkSpec &spec) {
+  if (spec.guard == nullptr) return true;
+  const unsigned long long mb = __ldcg(&spec.guard->maxbits);
+  const unsigned int fl = __ldcg(&spec.guard->flags);
+  const long long top = __ldcg(&spec.guard->max_unconv);
+  return mb < spec.guard_maxbits && fl == 0u && top == spec.guard_top;
+}
 
 __device__ __forceinline__ double sk_warp_max(double v) {
 #pragma unroll
@@ -440,6 +457,10 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
                sk_cplx *__restrict__ stage, const __grid_constant__ SkSpec spec, SkReduceOut *__restrict__ red) {
   // tpt (4 or 8) targets per thread: 2048-target blocks amortise the per-cell work best; smaller launches use
   // 1024-target blocks so that the grid still fills the 148 SMs several times over
+  if (SPEC && !sk_chain_guard_holds(spec)) {           // chained launch whose prediction failed: touch nothing
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&red->flags, SK_FLAG_SKIPPED);
+    return;
+  }
   extern __shared__ __align__(16) double smem[];
   double *sE = smem;                                   // [W/2][SK_NC/2]
   double *sO = sE + (W / 2) * (SK_NC / 2);

@@ -26,7 +26,7 @@ def test_header_symbols_exported(sk):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(sk._capi.SIGNATURES), declared ^ set(sk._capi.SIGNATURES)
-    assert lib.sk_abi_version() == 1
+    assert lib.sk_abi_version() == 2
 
 
 def test_no_cpu_fallback(sk):

@@ -725,3 +725,37 @@ def test_config2_full_size_properties(sk):
     assert np.max(np.abs(vs[::4] - vo)) <= 1e-11
     st = cfg.engine.stats()
     assert st["n_fast"] == st["n_subintervals"] and st["units"] >= 2000
+
+
+def test_overlapped_host_work_and_chained_panels_are_bitwise_neutral(sk):
+    """sk_targets_begin/_end, sk_subinterval_begin/_end and the device-guarded chained launch of the next panel
+    (sk_subinterval_chain) only move WHEN work is enqueued: values, error estimates and the trace must equal the plain
+    blocking call sequence bit for bit -- when the prediction holds (second panel picked up: n_chained = 1), when the
+    first panel converges part of the targets (guard fails on the device: the launch is skipped) and when a panel is
+    rejected and bisected (the chained launch is discarded)."""
+    from spectralkernels_jl_b200 import adaptive as ad
+    rng = np.random.default_rng(11)
+    cases = [
+        ("two panels, nothing converges in the first", sk.Matern(1 / (np.pi / 2), 1.0, 1.5), rng.uniform(0, 1, 300_000), 1.0, {}, 1),
+        ("shrinking active set", sk.Matern(1.0, 0.5, 0.55), 10 ** rng.uniform(-4, 0, 200_000), 5.9, {}, None),
+        ("bisection", sk.Matern(1.0, 0.05, 0.8), rng.uniform(0, 3, 100_000), None, {"quadspec": (256, 4)}, None),
+    ]
+    key = lambda tr: [(t["kind"], t["a"], t["b"], t.get("accepted"), t.get("hi_after"), t.get("criteria")) for t in tr]
+    for name, S, xs, k0, kw, want_chained in cases:
+        out = []
+        for overlap in (False, True):
+            ad.OVERLAP_HOST_WORK = overlap
+            try:
+                cfg = sk.AdaptiveKernelConfig(S, **kw)
+                tr = []
+                v, e = sk.kernel_values(cfg, xs, k0=k0, trace=tr)
+                out.append((v, e, key(tr), cfg.engine.stats()))
+            finally:
+                ad.OVERLAP_HOST_WORK = True
+        (v0, e0, t0, s0), (v1, e1, t1, s1) = out
+        assert np.array_equal(v0, v1), name
+        assert np.array_equal(np.nan_to_num(e0, nan=-1.0), np.nan_to_num(e1, nan=-1.0)), name
+        assert t0 == t1, name
+        assert s0["n_chained"] == 0
+        if want_chained is not None:
+            assert s1["n_chained"] == want_chained, (name, s1)
