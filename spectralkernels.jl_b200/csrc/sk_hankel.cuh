@@ -499,11 +499,14 @@ k_hankel_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkHan
   long long cur_l0 = -1;
   double d = 0.0;
   unsigned int fl = 0;
+  // the distance of the NEXT 32-target step is loaded one step ahead: its latency hides behind this step's work
+  double x_next = (base + lane < n) ? xs[base + lane] : 0.0;
 #pragma unroll 1
   for (int u = 0; u < SK_HK_CT; ++u) {
     const long long j = base + (long long)u * 32 + lane;
     const bool have = j < n;
-    const double x = have ? xs[j] : 0.0;
+    const double x = x_next;
+    if (u + 1 < SK_HK_CT) x_next = (j + 32 < n) ? xs[j + 32] : 0.0;
     double f[2] = {0.0, 0.0}, lo[2] = {0.0, 0.0};
     int gi = -1;
     SkTargetCoord tc;

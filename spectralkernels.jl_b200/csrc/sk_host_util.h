@@ -11,7 +11,7 @@
 // sigma = 2 for both the spread and the inner type-2 step.
 // Returns 0, or -1 if the grid would be unreasonably large.
 static inline int sk_make_geom(const SkEsPlan &P, double w_lo, double w_hi, double r_lo, double r_hi, SkGeom *G,
-                               bool force_center = false) {
+                               bool force_center = false, bool pow2_only = false) {
   const double sigma = 2.0;
   const double PI = 3.14159265358979323846;
   double X = 0.5 * (w_hi - w_lo);
@@ -48,7 +48,10 @@ static inline int sk_make_geom(const SkEsPlan &P, double w_lo, double w_hi, doub
   const long long need = (long long)std::ceil(1.999 * (double)nf);
   long long pow2 = 2;
   while (pow2 < need) pow2 <<= 1;
-  G->nf2 = (pow2 >= 8 && 3 * (pow2 / 4) >= need) ? 3 * (pow2 / 4) : pow2;
+  // (pow2_only: the octave groups of the Hankel transform come in many sizes that move with every hyperparameter
+  //  vector of a fit; powers of two keep them to one cuFFT kernel family and ~10 plans -- the first use of a
+  //  3*2^k size made cuFFT load another module, 0.6-1 s, in the middle of a fitting loop)
+  G->nf2 = (!pow2_only && pow2 >= 8 && 3 * (pow2 / 4) >= need) ? 3 * (pow2 / 4) : pow2;
   const double n2 = (double)G->nf2;
   G->kap_hi = n2 / G->inv_hu;
   G->kap_lo = -std::fma(G->kap_hi, G->inv_hu, -n2) / G->inv_hu;
@@ -109,7 +112,7 @@ static inline long long sk_hk_make_plan(const SkEsPlan &P, int nu, double a, dou
     SkHankelGroup &g = groups[ng];
     std::memset(&g, 0, sizeof(g));
     if (share) g.G = *share;
-    else if (sk_make_geom(P, w_lo, b, rl, rh, &g.G, center) != 0) return false;
+    else if (sk_make_geom(P, w_lo, b, rl, rh, &g.G, center, true) != 0) return false;
     g.w_ref = w_ref;
     g.q_cut = q_cut;
     g.q_from = q_cut;
@@ -134,7 +137,7 @@ static inline long long sk_hk_make_plan(const SkEsPlan &P, int nu, double a, dou
   if (sharing) {
     w_ref_s = std::ldexp(H->wT, t_share + 1);
     const double rl = std::fmax(r_lo, std::ldexp(r_hi, -(t_end + 1)));
-    if (sk_make_geom(P, w_ref_s, b, rl, std::ldexp(r_hi, -t_share), &Gs, false) != 0) return -1;
+    if (sk_make_geom(P, w_ref_s, b, rl, std::ldexp(r_hi, -t_share), &Gs, false, true) != 0) return -1;
   }
   for (int t = t_first; t <= t_end; ++t) {
     if (sharing && t >= t_share) {
