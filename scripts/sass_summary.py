@@ -23,7 +23,7 @@ CLASSES = [
     ("mufu/f2f", re.compile(r"^(MUFU|F2F|F2I|I2F|FRND|I2I)")),
     ("shared ld/st", re.compile(r"^(LDS|STS|LDSM)")),
     ("shared atom", re.compile(r"^ATOMS")),
-    ("global ld/st", re.compile(r"^(LDG|STG|LD\b|ST\b)")),
+    ("global ld/st", re.compile(r"^(LDG(?!STS)|STG|LD\b|ST\b)")),
     ("global atom/red", re.compile(r"^(ATOMG|ATOM\b|RED)")),
     ("local ld/st", re.compile(r"^(LDL|STL)")),
     ("const ld", re.compile(r"^(LDC|ULDC)")),
