@@ -158,7 +158,7 @@ class ClockSampler:
                 if self.mask & int(bit):
                     names.append(name)
             return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
-                    "reasons": sorted(names), "samples": len(self.sm), "how": "NVML polled every 2 ms during the timed steps"}
+                    "reasons": sorted(names), "samples": len(self.sm), "how": "NVML polled every 2 ms from the warm-up through the timed resident and end-to-end steps"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"] if self.idx >= 0 else [],
                     "samples": 0}
@@ -301,17 +301,19 @@ def run(args):
             sk.kernel_values(cfg, host_in.array, k0=k0, comm=comm, out_vals=host_v.array, out_errs=host_e.array)
 
         trace = []
+        # clocks and throttle reasons are sampled from the warm-up through the last timed step (resident, per-stage and
+        # end-to-end loops: the GPU is under load throughout), so that the short timed region is well covered
+        sampler = ClockSampler(local_rank if (rank == 0 and sample_clocks) else -1)
+        sampler.start()
         step_resident(trace)
         for _ in range(W - 1):
             step_resident()
         eng.set_timing(True)
         gc.collect()
         gc.disable()                  # no collector pauses inside the timed regions (ranks wait for each other)
-        sampler = ClockSampler(local_rank if (rank == 0 and sample_clocks) else -1)   # nvidia-smi takes a driver lock
         agg = {"units": 0, "interp_ms": 0.0, "source_ms": 0.0, "sort_ms": 0.0, "gather_ms": 0.0, "launches": 0,
                "subintervals": 0}
         barrier()
-        sampler.start()
         t0 = time.perf_counter()
         eng.timer_begin()
         for _ in range(K):
@@ -323,7 +325,6 @@ def run(args):
         dev_ms = eng.timer_end()
         barrier()
         wall_ms = 1e3 * (time.perf_counter() - t0)
-        clocks = sampler.stop()
         eng.set_timing(False)
         # the per-stage timers add event synchronisations to the step: time the same K steps once more without them
         barrier()
@@ -341,6 +342,7 @@ def run(args):
             step_e2e()
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0)
+        clocks = sampler.stop()
         gc.enable()
         if world > 1:
             t = torch.tensor([res_ms, e2e_ms, wall_ms, dev_ms], dtype=torch.float64, device=d_in.device)

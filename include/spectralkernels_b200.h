@@ -227,6 +227,14 @@ int sk_targets_begin(sk_ctx *ctx, const double *xs_host, int64_t n_in);
 int sk_targets_begin_device(sk_ctx *ctx, const double *xs_dev, int64_t n_in);
 int sk_targets_early_range(sk_ctx *ctx, double *r_lo, double *r_hi);
 int sk_targets_end(sk_ctx *ctx, sk_target_info *info);
+/* Between _begin and _end: enqueue the FIRST panel's first sub-interval (0, b1), b1 = m k / (2 r_max)
+ * (src/adaptive.jl:152), behind the sort -- its ends, its transform geometry and whether there is an r = 0 row are known
+ * after the first pass; the number of unique distances is read by the kernel from the sort's device-side summary.
+ * opts.speculate must carry the scan arguments of (0, b1).  The sk_run_begin / sk_panel_begin / sk_subinterval[_begin]
+ * (0, b1, opts) that follow sk_targets_end find the panel already being integrated (sk_stats.n_chained); anything
+ * else discards the launch.  *queued = 0: not applicable (sharded run, timing on, host-evaluated density, dim >= 2,
+ * small input): nothing was enqueued. */
+int sk_first_panel_early(sk_ctx *ctx, double a, double b, const sk_subinterval_opts *opts, int32_t *queued);
 /* lags of point pairs computed on the device (src/model.jl:53-68 with NoWarping: lag = norm(pts[i] - pts[j])):
  * pts_host is npts x dim row-major; pairs_host holds npairs 0-based (i, j) index pairs, or NULL for all
  * npts (npts-1) / 2 pairs i < j in row-major order of the strict upper triangle.  The results of

@@ -83,6 +83,7 @@ SIGNATURES = {
     "sk_targets_begin_device": (c_int, [c_void_p, c_void_p, c_int64]),
     "sk_targets_early_range": (c_int, [c_void_p, _dp, _dp]),
     "sk_targets_end": (c_int, [c_void_p, c_void_p]),
+    "sk_first_panel_early": (c_int, [c_void_p, c_double, c_double, c_void_p, POINTER(c_int32)]),
     "sk_subinterval_begin": (c_int, [c_void_p, c_double, c_double, c_void_p]),
     "sk_subinterval_end": (c_int, [c_void_p, _dp]),
     "sk_subinterval_chain": (c_int, [c_void_p, c_double, c_double, c_void_p, c_double, POINTER(c_int32)]),
@@ -407,6 +408,13 @@ class Session:
         lo, hi = c_double(), c_double()
         self._ck(self._L.sk_targets_early_range(self._h, byref(lo), byref(hi)))
         return lo.value, hi.value
+
+    def first_panel_early(self, a: float, b: float, cmul: float, p: float, kernel: int, logw: bool, speculate) -> bool:
+        """between targets_begin* and targets_end: enqueue the first panel's first sub-interval behind the sort"""
+        o = SubintervalOpts(float(cmul), float(p), int(kernel), 1 if logw else 0, 0, 0, 0.0, ctypes.pointer(speculate))
+        done = c_int32(0)
+        self._ck(self._L.sk_first_panel_early(self._h, float(a), float(b), byref(o), byref(done)))
+        return bool(done.value)
 
     def targets_end(self) -> TargetInfo:
         info = TargetInfo()

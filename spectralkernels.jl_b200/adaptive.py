@@ -442,8 +442,14 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
                 _, r_early = eng.targets_early_range()
                 if r_early > 0 and comm.world_size == 1 or (r_early > 0 and getattr(comm, "fused", False)):
                     b1 = 0.0 + cfg.quadsz / (2 * r_early)
-                    pre[(0.0, b1, cfg.convergence_criteria)] = _panel_scalars(cfg, 0.0, b1, cfg.convergence_criteria,
-                                                                              cfg.tol * abs(k0) / 2)
+                    ps = _panel_scalars(cfg, 0.0, b1, cfg.convergence_criteria, cfg.tol * abs(k0) / 2)
+                    pre[(0.0, b1, cfg.convergence_criteria)] = ps
+                    if comm.world_size == 1 and cfg.dim == 1 and is_builtin(cfg.f) and ps[2] == cfg.convergence_criteria \
+                            and hasattr(eng, "first_panel_early"):
+                        # the first panel goes in behind the sort (sk_first_panel_early): its kernel takes the number
+                        # of unique distances from the sort's device-side summary
+                        eng.first_panel_early(0.0, b1, cfg.c, cfg.p, SK_KERNEL_SIN if cfg.derivative else SK_KERNEL_COS,
+                                              cfg.logw, ps[4])
             finally:
                 info = eng.targets_end()
         elif xs_device is not None:

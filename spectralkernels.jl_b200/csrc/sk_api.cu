@@ -254,6 +254,16 @@ struct sk_ctx {
     sk_scan_args sa;
   } chain;
   SkGeom chain_G;
+  // the FIRST panel's first sub-interval enqueued behind the sort (sk_first_panel_early; SkSpec::dyn)
+  struct Early {
+    bool pending = false, adopted = false;
+    double a = 0, b = 0, r_lo = 0, r_hi = 0;
+    long long lo = 0, n_in = 0;
+    sk_subinterval_opts o;
+    sk_scan_args sa;
+    SkGeom G;
+  } early1;
+  cudaEvent_t ev_sum = nullptr;              // behind the D2H copy of the sort's summary
   SkReduceOut *d_red2 = nullptr, *h_red2 = nullptr;
   cudaEvent_t ev_red = nullptr, ev_red2 = nullptr;
   HostScalars *h_scal = nullptr;  // pinned
@@ -310,6 +320,7 @@ inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1)
 int flush_commit(sk_ctx *c);
 int ensure_res_zero(sk_ctx *c);
 int chain_discard(sk_ctx *c);
+int early_discard(sk_ctx *c);
 
 #define NCK(call)                                                                                     \
   do {                                                                                                \
@@ -944,6 +955,26 @@ int transform_and_stage_finish(sk_ctx *c, double *max_abs_diff, unsigned int *fl
   } else {
     CK(cudaStreamSynchronize(c->stream));
   }
+  if (c->early1.pending && c->early1.adopted) {
+    c->early1.pending = c->early1.adopted = false;
+    if (c->h_scal->red.flags & SK_FLAG_SKIPPED) {
+      // the launch behind the sort skipped itself (the sort fell back to the general path, or the active set is too
+      // small for the NUFFT branch): evaluate the sub-interval now, the ordinary way
+      int rc = chain_discard(c);              // (a launch chained behind it saw the flag and skipped itself too)
+      if (rc != SK_OK) return rc;
+      sk_subinterval_opts o = c->early1.o;
+      o.speculate = &c->early1.sa;
+      c->res_zero_pending = true;
+      c->spec_fresh = false;
+      make_panel_spec(c, c->early1.a, c->early1.b, o.logw, &c->pend_S);
+      c->need_gen = true;
+      rc = transform_and_stage_enqueue_local(c, c->early1.a, c->early1.b, &o);
+      if (rc != SK_OK) return rc;
+      CK(cudaStreamSynchronize(c->stream));
+    } else {
+      c->stats.n_chained++;
+    }
+  }
   if (sharded(c)) {
     if (c->pend_rc != SK_OK) return c->pend_rc;                     // this rank's own failure (message already set)
     const int prc = peer_check(c, 0);
@@ -1019,6 +1050,23 @@ int chain_discard(sk_ctx *c) {
     LAUNCH_CHECK();
   }
   return SK_OK;
+}
+
+// the first-panel launch queued behind the sort that the host did not pick up: if it ran, the table holds its commit
+int early_discard(sk_ctx *c) {
+  if (!c->early1.pending) return SK_OK;
+  c->early1.pending = c->early1.adopted = false;
+  CK(cudaEventSynchronize(c->ev_red));
+  if (!(c->h_scal->red.flags & SK_FLAG_SKIPPED) && c->n_unique > c->early1.lo)
+    CK(cudaMemsetAsync(c->res.p + c->early1.lo, 0, sizeof(sk_cplx) * (c->n_unique - c->early1.lo), c->stream));
+  return SK_OK;
+}
+bool early_matches(const sk_ctx *c, double a, double b, const sk_subinterval_opts *o) {
+  const sk_ctx::Early &h = c->early1;
+  return h.pending && !h.adopted && a == h.a && b == h.b && c->lo == h.lo && c->hi == c->n_unique && c->r_lo == h.r_lo &&
+         c->r_hi == h.r_hi && c->panel_subs == 0 && !c->timing && c->res_zero_pending && !c->commit_pending &&
+         o->cmul == h.o.cmul && o->p == h.o.p && o->kernel == h.o.kernel && o->logw == h.o.logw && o->nu == h.o.nu &&
+         o->xdiv_pow == h.o.xdiv_pow && o->speculate != nullptr && std::memcmp(o->speculate, &h.sa, sizeof(sk_scan_args)) == 0;
 }
 
 bool chain_matches(const sk_ctx *c, double a, double b, const sk_subinterval_opts *o) {
@@ -1210,6 +1258,7 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   NvtxRange nvtx("unique / sort (K8)");
   {
     int rcd = chain_discard(c);
+    if (rcd == SK_OK) rcd = early_discard(c);
     if (rcd != SK_OK) return rcd;
   }
   c->have_targets = false;
@@ -1297,6 +1346,7 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
   if (c->in_src) CK(cudaStreamWaitEvent(c->stream, c->in_ev[1], 0));   // the library's copy of the distances is complete
+  CK(cudaEventRecord(c->ev_sum, c->stream));
   if (early && !c->in_group) {
     double r_lo = 0, r_hi = 0;
     int rc = targets_early_range(c, &r_lo, &r_hi);
@@ -1312,7 +1362,8 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
 }
 
 int targets_finish(sk_ctx *c, long long n_in, sk_target_info *info, bool force_general) {
-  CK(cudaStreamSynchronize(c->stream));
+  if (c->early1.pending) CK(cudaEventSynchronize(c->ev_sum));   // the first panel is queued behind the sort: do not wait for it
+  else CK(cudaStreamSynchronize(c->stream));
   c->in_src = nullptr;                       // the caller's buffer is not referenced any more
   if (c->h_scal->sum.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
   const bool general = force_general || c->h_scal->sum.overflow != 0;
@@ -1443,6 +1494,7 @@ int sk_ctx_create(int device, sk_ctx **out) {
       cudaEventCreateWithFlags(&c->k8_ev, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_red, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_red2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_sum, cudaEventDisableTiming) != cudaSuccess ||
       cudaMalloc((void **)&c->d_red2, sizeof(SkReduceOut)) != cudaSuccess ||
       cudaHostAlloc((void **)&c->h_red2, sizeof(SkReduceOut), cudaHostAllocDefault) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->in_ev[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -1509,6 +1561,7 @@ int sk_ctx_destroy(sk_ctx *c) {
   if (c->h_red2) cudaFreeHost(c->h_red2);
   if (c->ev_red) cudaEventDestroy(c->ev_red);
   if (c->ev_red2) cudaEventDestroy(c->ev_red2);
+  if (c->ev_sum) cudaEventDestroy(c->ev_sum);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 2; ++i) if (c->ev_user[i]) cudaEventDestroy(c->ev_user[i]);
@@ -2200,6 +2253,29 @@ static int subinterval_builtin_enqueue(sk_ctx *c, double a, double b, const sk_s
   const bool origin = (a == 0.0 && c->p != 0.0);                    // src/quadrature.jl:185
   if (origin && o->logw)
     return fail(c, SK_ERR_UNSUPPORTED, "log-weighted origin sub-interval needs df: use sk_subinterval_logw_host (src/quadrature.jl:186-228)");
+  if (c->early1.pending) {
+    if (early_matches(c, a, b, o)) {
+      // this very sub-interval has been running since the sort ended (sk_first_panel_early)
+      c->early1.adopted = true;
+      c->res_zero_pending = false;                       // the launch writes the table outright (SkSpec::fresh)
+      if (c->has_zero && !c->zero_lag_written) CK(cudaMemsetAsync(c->res.p, 0, sizeof(sk_cplx), c->stream));
+      c->spec_fresh = true;
+      c->pend_spec = true;
+      c->pend_timed = false;
+      c->pend_rc = SK_OK;
+      c->pend_ab = false;
+      c->spec_args = c->early1.sa;
+      c->need_gen = false;
+      c->have_sources = true;
+      c->last_logw = o->logw ? 1 : 0;
+      c->stats.n_fast++;
+      c->stats.last_nf = c->early1.G.nf;
+      c->stats.last_nf2 = c->early1.G.nf2;
+      return SK_OK;
+    }
+    rc = early_discard(c);
+    if (rc != SK_OK) return rc;
+  }
   if (c->chain.pending) {
     if (chain_matches(c, a, b, o)) {
       // this very sub-interval was enqueued ahead of time: nothing to launch, _finish reads the chain's scalars
@@ -2233,6 +2309,72 @@ int sk_subinterval(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, 
   int rc = subinterval_builtin_enqueue(c, a, b, o);
   if (rc != SK_OK) return rc;
   return transform_and_stage_finish(c, max_abs_diff, nullptr);
+}
+
+// Between sk_targets_begin* and sk_targets_end: enqueue the FIRST panel's first sub-interval (0, b1) behind the sort.
+// Everything the launch needs is known after the first pass over the distances (their range -> panel ends and transform
+// geometry; whether there is an r = 0 row) except the number of unique distances and the buffer the unique table ends up
+// in: the kernel reads those from the sort's device-side summary (SkSpec::dyn) and skips itself if the sort did not
+// deliver.  The host's sk_run_begin / sk_panel_begin / sk_subinterval[_begin](0, b1, opts) that follow sk_targets_end then
+// find the panel already being integrated.  *queued = 0: not applicable, nothing was enqueued.
+int sk_first_panel_early(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, int32_t *queued) {
+  if (!c || !o || !queued) return SK_ERR_ARG;
+  *queued = 0;
+  if (c->begin_n < 0 || c->early1.pending || c->chain.pending || sharded(c) || c->in_group || c->timing ||
+      c->interp_mode != 0 || c->family == SK_SDF_HOST || !c->have_rule || o->speculate == nullptr ||
+      (o->kernel != SK_KERNEL_COS && o->kernel != SK_KERNEL_SIN) || o->p != c->p || a != 0.0 || !(b > 0.0) ||
+      (c->p != 0.0 && o->logw) || o->speculate->criteria < 0 || o->speculate->criteria > 2 || c->early_global ||
+      !(c->early_hi > 0.0) || c->plan.w <= 0)
+    return SK_OK;
+  CK(cudaSetDevice(c->device));
+  const SkK8State &k8 = c->h_scal->k8;              // fetched behind the first pass (targets_early_range)
+  if (k8.bad) return SK_OK;
+  const long long n_in = c->begin_n, lo = k8.nzero ? 1 : 0, M2 = 2LL * c->m * c->k;
+  const long long min_n = std::max<long long>(1, (1LL << 18) / M2);         // NUFFT branch: M2 n > 2^18 and n > 1
+  if (n_in - lo <= min_n) return SK_OK;
+  SkGeom G;
+  if (sk_make_geom(c->plan, a, b, c->early_lo, c->early_hi, &G) != 0) return SK_OK;
+  SkPanelSpec S;
+  make_panel_spec(c, a, b, o->logw, &S);
+  if (!c->pf_valid || std::memcmp(&c->pf_S, &S, sizeof(SkPanelSpec)) != 0 || std::memcmp(&c->pf_G, &G, sizeof(SkGeom)) != 0)
+    return SK_OK;                                    // its sources are not waiting in the prefetch set
+  CK(c->res.ensure(n_in));
+  CK(c->stage.ensure(n_in));
+  const long long lo_save = c->lo;
+  c->lo = lo;                                        // fill_spec offsets the table pointers by c->lo
+  SkSpec spec;
+  std::memset(&spec, 0, sizeof(spec));
+  fill_spec(c, o->speculate, spec);
+  spec.fresh = 1;
+  spec.dyn = c->d_sum;
+  spec.dyn_xs_alt = c->uxs_fix.p + lo;
+  spec.dyn_lo = lo;
+  spec.dyn_min_n = min_n;
+  SkReduceOut init;
+  std::memset(&init, 0, sizeof(init));
+  init.max_unconv = lo - 1;
+  c->h_scal->red = init;
+  CK(cudaMemcpyAsync(c->d_red, &c->h_scal->red, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamWaitEvent(c->stream, c->pf_ev, 0));
+  swap_src_sets(c);
+  c->n_pf_hits++;
+  promote_second_prefetch(c);
+  const double r_lo_save = c->r_lo, r_hi_save = c->r_hi;
+  c->r_lo = c->early_lo; c->r_hi = c->early_hi;      // (the launch helper sizes its blocks from the distance span)
+  const int ksin = o->kernel == SK_KERNEL_SIN;
+#define CALL(WW) launch_interp_session<WW>(c, G, c->uxs.p + lo, n_in - lo, o->cmul, ksin, spec)
+  DISPATCH_W(c->plan.w, CALL)
+#undef CALL
+  c->lo = lo_save; c->r_lo = r_lo_save; c->r_hi = r_hi_save;
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaEventRecord(c->ev_red, c->stream));
+  sk_ctx::Early &e = c->early1;
+  e.pending = true; e.adopted = false;
+  e.a = a; e.b = b; e.r_lo = c->early_lo; e.r_hi = c->early_hi; e.lo = lo; e.n_in = n_in;
+  e.o = *o; e.sa = *o->speculate; e.o.speculate = nullptr; e.G = G;
+  *queued = 1;
+  return SK_OK;
 }
 
 // Between sk_subinterval_begin and sk_subinterval_end of a panel's speculated first sub-interval: enqueue the NEXT
@@ -2314,6 +2456,8 @@ static int subinterval_host_enqueue(sk_ctx *c, double a, double b, const double 
   int rc = subinterval_prologue(c, a, b, o);
   if (rc != SK_OK) return rc;
   rc = chain_discard(c);
+  if (rc != SK_OK) return rc;
+  rc = early_discard(c);
   if (rc != SK_OK) return rc;
   if (!no1 || !buf1 || !no2 || !buf2) return fail(c, SK_ERR_ARG, "null pointer");
   const long long M1 = (long long)c->m * c->k;
@@ -2436,6 +2580,8 @@ int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, c
   int rc = subinterval_prologue(c, a, b, o);
   if (rc != SK_OK) return rc;
   rc = chain_discard(c);
+  if (rc != SK_OK) return rc;
+  rc = early_discard(c);
   if (rc != SK_OK) return rc;
   if (!max_abs_diff) return fail(c, SK_ERR_ARG, "null pointer");
   const bool all_null = !no1 && !bufa1 && !bufb1 && !no2 && !bufa2 && !bufb2;
@@ -2654,6 +2800,8 @@ int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
   if (rc != SK_OK) return rc;
   rc = chain_discard(c);
   if (rc != SK_OK) return rc;
+  rc = early_discard(c);
+  if (rc != SK_OK) return rc;
   rc = flush_commit(c);
   if (rc != SK_OK) return rc;
   rc = ensure_res_zero(c);
@@ -2679,6 +2827,8 @@ static int results_enqueue(sk_ctx *c, double *vals, double *errs) {
   int rc = rollback_speculation(c);
   if (rc != SK_OK) return rc;
   rc = chain_discard(c);
+  if (rc != SK_OK) return rc;
+  rc = early_discard(c);
   if (rc != SK_OK) return rc;
   rc = flush_commit(c);
   if (rc != SK_OK) return rc;
@@ -2740,6 +2890,8 @@ int sk_results_get_async(sk_ctx *c, double *vals, double *errs) {
   int rc = rollback_speculation(c);
   if (rc != SK_OK) return rc;
   rc = chain_discard(c);
+  if (rc != SK_OK) return rc;
+  rc = early_discard(c);
   if (rc != SK_OK) return rc;
   rc = flush_commit(c);
   if (rc != SK_OK) return rc;

@@ -70,6 +70,13 @@ struct SkSpec {
   const SkReduceOut *guard;          // nullptr: no guard
   unsigned long long guard_maxbits;  // run only if guard->maxbits < guard_maxbits ...
   long long guard_top;               // ... and guard->max_unconv == guard_top and guard->flags == 0
+  // First panel enqueued behind the SORT (sk_first_panel_early): the number of unique distances and the buffer the
+  // unique table ended up in are not known to the host yet -- the kernel takes them from the sort's device-side summary
+  // (lo = 0 / 1, the r = 0 row, is known from the first pass).  It skips itself if the sort did not deliver (bad input,
+  // bin overflow -> general sort on the host) or if the active set is too small for the NUFFT branch.
+  const SkTargetSummary *dyn;        // nullptr: n and xs are the kernel arguments
+  const double *dyn_xs_alt;          // the table when duplicates were dropped (pre-offset like xs)
+  long long dyn_lo, dyn_min_n;
 };
 
 __device__ __forceinline__ bool sk_chain_guard_holds(const SkSpec &spec) {
@@ -452,14 +459,27 @@ __device__ __forceinline__ void sk_cell_eval(const double *coef, const sk_cplx *
 #define SK_CELL_STRIDE (SK_NC * 4 + 2)
 template <int W, bool SPEC, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G, const double *__restrict__ xs,
-               long long n, const sk_cplx *__restrict__ grid, double cmul, int kernel_sin, int cmax, int tpt,
+k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeom G, const double *__restrict__ xs_arg,
+               long long n_arg, const sk_cplx *__restrict__ grid, double cmul, int kernel_sin, int cmax, int tpt,
                sk_cplx *__restrict__ stage, const __grid_constant__ SkSpec spec, SkReduceOut *__restrict__ red) {
   // tpt (4 or 8) targets per thread: 2048-target blocks amortise the per-cell work best; smaller launches use
   // 1024-target blocks so that the grid still fills the 148 SMs several times over
   if (SPEC && !sk_chain_guard_holds(spec)) {           // chained launch whose prediction failed: touch nothing
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&red->flags, SK_FLAG_SKIPPED);
     return;
+  }
+  const double *xs = xs_arg;
+  long long n = n_arg;
+  if (SPEC && spec.dyn != nullptr) {                   // enqueued behind the sort: its summary says what there is
+    const long long nu = __ldcg(&spec.dyn->n_unique);
+    const unsigned int bad = __ldcg(&spec.dyn->bad), over = __ldcg(&spec.dyn->overflow), fixed = __ldcg(&spec.dyn->fixed);
+    n = nu - spec.dyn_lo;
+    if (bad || over || n <= spec.dyn_min_n) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&red->flags, SK_FLAG_SKIPPED);
+      return;
+    }
+    if (fixed) xs = spec.dyn_xs_alt;
+    if ((long long)blockIdx.x * 256 * tpt >= n) return;          // the grid was sized for the number of INPUT distances
   }
   extern __shared__ __align__(16) double smem[];
   double *sE = smem;                                   // [W/2][SK_NC/2]

@@ -730,13 +730,14 @@ def test_config2_full_size_properties(sk):
 def test_overlapped_host_work_and_chained_panels_are_bitwise_neutral(sk):
     """sk_targets_begin/_end, sk_subinterval_begin/_end and the device-guarded chained launch of the next panel
     (sk_subinterval_chain) only move WHEN work is enqueued: values, error estimates and the trace must equal the plain
-    blocking call sequence bit for bit -- when the prediction holds (second panel picked up: n_chained = 1), when the
+    blocking call sequence bit for bit -- when the predictions hold (first panel enqueued behind the sort and second
+    panel behind the first, both picked up: n_chained = 2), when the
     first panel converges part of the targets (guard fails on the device: the launch is skipped) and when a panel is
     rejected and bisected (the chained launch is discarded)."""
     from spectralkernels_jl_b200 import adaptive as ad
     rng = np.random.default_rng(11)
     cases = [
-        ("two panels, nothing converges in the first", sk.Matern(1 / (np.pi / 2), 1.0, 1.5), rng.uniform(0, 1, 300_000), 1.0, {}, 1),
+        ("two panels, nothing converges in the first", sk.Matern(1 / (np.pi / 2), 1.0, 1.5), rng.uniform(0, 1, 300_000), 1.0, {}, 2),
         ("shrinking active set", sk.Matern(1.0, 0.5, 0.55), 10 ** rng.uniform(-4, 0, 200_000), 5.9, {}, None),
         ("bisection", sk.Matern(1.0, 0.05, 0.8), rng.uniform(0, 3, 100_000), None, {"quadspec": (256, 4)}, None),
     ]
