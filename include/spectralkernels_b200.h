@@ -282,6 +282,11 @@ int sk_subinterval_end(sk_ctx *ctx, double *max_abs_diff);
  * sources of (a2, b2) not prefetched, host-evaluated density, dim >= 2): nothing was enqueued. */
 int sk_subinterval_chain(sk_ctx *ctx, double a2, double b2, const sk_subinterval_opts *opts, double accept_below,
                          int32_t *chained);
+/* Right after a successful sk_subinterval_chain: enqueue the final gather of sk_results_get_device behind the chained panel,
+ * guarded on the device: it runs only if that panel is accepted and converges EVERY target, i.e. if it turns out to be the
+ * last panel of the run (src/adaptive.jl:149).  sk_results_get_device(vals, errs) with the same arrays then finds the
+ * results in place; otherwise it gathers as usual.  *queued = 0: nothing was enqueued. */
+int sk_results_chain_device(sk_ctx *ctx, double *vals_dev, double *errs_dev, double accept_below, int32_t *queued);
 /* same with host-evaluated nodes and (real) strengths: no1/buf1 length m*k, no2/buf2 length 2*m*k
  * (the buffers of src/adaptive.jl:50-53 after updatequadbufs!) */
 int sk_subinterval_host(sk_ctx *ctx, double a, double b, const double *no1, const double *buf1,

@@ -87,6 +87,7 @@ SIGNATURES = {
     "sk_subinterval_begin": (c_int, [c_void_p, c_double, c_double, c_void_p]),
     "sk_subinterval_end": (c_int, [c_void_p, _dp]),
     "sk_subinterval_chain": (c_int, [c_void_p, c_double, c_double, c_void_p, c_double, POINTER(c_int32)]),
+    "sk_results_chain_device": (c_int, [c_void_p, c_void_p, c_void_p, c_double, POINTER(c_int32)]),
     "sk_comm_peer_export": (c_int, [c_void_p, c_void_p]),
     "sk_comm_peer_attach": (c_int, [c_void_p, c_void_p, c_int32, c_int32]),
     "sk_comm_allgather": (c_int, [c_void_p, _dp, c_int32, _dp]),
@@ -363,9 +364,12 @@ class Session:
         return no, wt
 
     def sdf_builtin(self, family: int, params, deriv_index: int = 0):
+        key = (int(family), tuple(float(v) for v in params), int(deriv_index))
+        if key == self.sdf_key:                    # unchanged since the last call on this context
+            return
         pr = _f64(params)
         self._ck(self._L.sk_sdf_builtin(self._h, int(family), _p(pr) if pr.size else None, pr.size, int(deriv_index)))
-        self.sdf_key = (int(family), tuple(pr.tolist()), int(deriv_index))
+        self.sdf_key = key
 
     def targets_set(self, xs: np.ndarray) -> TargetInfo:
         xs = _f64(xs)
@@ -438,6 +442,13 @@ class Session:
                             ctypes.pointer(speculate))
         done = c_int32(0)
         self._ck(self._L.sk_subinterval_chain(self._h, float(a2), float(b2), byref(o), float(accept_below), byref(done)))
+        return bool(done.value)
+
+    def results_chain_device(self, vals_ptr: int, errs_ptr: int, accept_below: float) -> bool:
+        """enqueue the final gather behind the chained panel, guarded on the device (it runs if that panel is the last)"""
+        done = c_int32(0)
+        self._ck(self._L.sk_results_chain_device(self._h, c_void_p(vals_ptr), c_void_p(errs_ptr) if errs_ptr else None,
+                                                 float(accept_below), byref(done)))
         return bool(done.value)
 
     def subinterval_end(self) -> float:

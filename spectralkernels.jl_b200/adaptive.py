@@ -277,7 +277,8 @@ def _host_strengths(cfg: AdaptiveKernelConfig, eng, a: float, b: float, origin: 
 
 def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: float, k0: float, comm, active: bool,
                                verbose: bool = False, trace: Optional[list] = None, speculate=None,
-                               n_act_g: Optional[int] = None, spec_state: Optional[dict] = None, while_enqueued=None):
+                               n_act_g: Optional[int] = None, spec_state: Optional[dict] = None, while_enqueued=None,
+                               chain_out: Optional[Tuple[int, int]] = None):
     """Scalar control flow of src/quadrature.jl:169-275: LIFO bisection, accept test against
     config.tol*k0 (not the split tolerance), 9:1 tolerance split at the origin.  The per-target work of
     every pass happens inside sk_subinterval / sk_subinterval_accept.
@@ -344,8 +345,10 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
                         # the next panel's first sub-interval goes in behind this one, guarded on the device: it runs
                         # only if this one is accepted (:260) and converges nothing (sk_subinterval_chain)
                         a2, b2, sargs2 = nxt
-                        eng.subinterval_chain(a2, b2, cfg.c, cfg.p, kernel, cfg.logw, sargs2, cfg.tol * k0, nu=nu,
-                                              xdiv_pow=xdiv)
+                        if eng.subinterval_chain(a2, b2, cfg.c, cfg.p, kernel, cfg.logw, sargs2, cfg.tol * k0, nu=nu,
+                                                 xdiv_pow=xdiv) and chain_out is not None:
+                            # ... and behind it the final gather, which runs if that panel ends the loop (:149)
+                            eng.results_chain_device(chain_out[0], chain_out[1], cfg.tol * k0)
                 finally:
                     mx = eng.subinterval_end()
             elif builtin:
@@ -523,7 +526,8 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
         spec_state = {}
         fourier_integrate_interval(cfg, eng, a, b, abs(k0), comm, active, verbose=verbose, trace=trace,
                                    speculate=sargs, n_act_g=n_act_g, spec_state=spec_state,
-                                   while_enqueued=ahead if (ipanel == 0 or pre_hit) else None)         # :157-159
+                                   while_enqueued=ahead if (ipanel == 0 or pre_hit) else None,
+                                   chain_out=out_device if (out_device is not None and not async_results) else None)  # :157-159
         if active:
             eng.panel_commit()                                                   # :163-164
         if verbose and crit_msg:

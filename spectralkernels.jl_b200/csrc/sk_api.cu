@@ -264,6 +264,13 @@ struct sk_ctx {
     SkGeom G;
   } early1;
   cudaEvent_t ev_sum = nullptr;              // behind the D2H copy of the sort's summary
+  // the final gather enqueued behind a chained last panel (sk_results_chain_device; SkGatherGuard)
+  struct GatherChain {
+    bool pending = false;
+    double *vals = nullptr, *errs = nullptr;
+    SkTailList tails;
+  } gchain;
+  unsigned int *d_gran = nullptr, *h_gran = nullptr;
   SkReduceOut *d_red2 = nullptr, *h_red2 = nullptr;
   cudaEvent_t ev_red = nullptr, ev_red2 = nullptr;
   HostScalars *h_scal = nullptr;  // pinned
@@ -1041,6 +1048,7 @@ int rollback_speculation(sk_ctx *c) {
 
 // a chained launch the host did not pick up: if it ran (its guard held) its speculative commit is rolled back
 int chain_discard(sk_ctx *c) {
+  c->gchain.pending = false;                 // (a gather chained behind it wrote, at most, into the caller's output arrays)
   if (!c->chain.pending) return SK_OK;
   c->chain.pending = c->chain.adopted = false;
   CK(cudaEventSynchronize(c->ev_red2));
@@ -1333,13 +1341,8 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   LAUNCH_CHECK();
   k_k8_finish<<<(unsigned int)nfine_max, SK_K8_TPB, 0, c->stream>>>(st, fill, c->k8_slots.p, uoffp, dup, c->uxs.p, c->inv.p);
   LAUNCH_CHECK();
-  // only when duplicates were dropped (the three kernels return at once otherwise)
-  k_k8_scan_bins<<<1, 1024, 0, c->stream>>>(st, dup, 1, 0xffffffffu, dsum, 1);
-  LAUNCH_CHECK();
-  k_k8_fix_uxs<<<(unsigned int)nfine_max, 256, 0, c->stream>>>(st, fill, uoffp, dup, dsum, c->uxs.p, c->uxs_fix.p);
-  LAUNCH_CHECK();
-  k_k8_fix_inv<<<gs, 256, 0, c->stream>>>(st, uoffp, dsum, n_in, c->inv.p);
-  LAUNCH_CHECK();
+  // (duplicates dropped by a bin: the compaction of the table and the shift of the inverse map are launched by
+  //  targets_finish when the summary says so -- three launches less on the common path)
   k_k8_identity<<<gs, 256, 0, c->stream>>>(src, n_in, st, c->uxs.p, c->inv.p);
   LAUNCH_CHECK();
   k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, c->uxs_fix.p, n_in, c->d_sum);
@@ -1370,6 +1373,27 @@ int targets_finish(sk_ctx *c, long long n_in, sk_target_info *info, bool force_g
   if (general) {
     int rc = targets_sort_general(c, n_in);
     if (rc != SK_OK) return rc;
+  } else if (c->h_scal->sum.fixed) {
+    // some bin dropped duplicates: compact the unique table into the second buffer, shift the inverse map, and take
+    // the summary again from the compacted table (same layout of the control block as targets_enqueue)
+    const size_t nfine_max = (size_t)(n_in >> SK_K8_TARGET_LOG) + 2;
+    const size_t off_fill = 256 + sizeof(unsigned int) * SK_K8_NC;
+    const size_t off_uoff = off_fill + sizeof(unsigned int) * nfine_max * SK_K8_FILL_STRIDE;
+    const size_t off_dup = off_uoff + sizeof(unsigned int) * nfine_max, off_dsum = off_dup + sizeof(unsigned int) * nfine_max;
+    SkK8State *st = (SkK8State *)c->k8_ctl.p;
+    unsigned int *fill = (unsigned int *)(c->k8_ctl.p + off_fill), *uoffp = (unsigned int *)(c->k8_ctl.p + off_uoff);
+    unsigned int *dup = (unsigned int *)(c->k8_ctl.p + off_dup), *dsum = (unsigned int *)(c->k8_ctl.p + off_dsum);
+    const unsigned int gs = std::min<unsigned int>(nblk(n_in, 256), 148u * 8u);
+    k_k8_scan_bins<<<1, 1024, 0, c->stream>>>(st, dup, 1, 0xffffffffu, dsum, 1);
+    LAUNCH_CHECK();
+    k_k8_fix_uxs<<<(unsigned int)nfine_max, 256, 0, c->stream>>>(st, fill, uoffp, dup, dsum, c->uxs.p, c->uxs_fix.p);
+    LAUNCH_CHECK();
+    k_k8_fix_inv<<<gs, 256, 0, c->stream>>>(st, uoffp, dsum, n_in, c->inv.p);
+    LAUNCH_CHECK();
+    k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, c->uxs_fix.p, n_in, c->d_sum);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
   }
   const SkTargetSummary sm = c->h_scal->sum;
   if (sm.bad) return fail(c, SK_ERR_INPUT, "distances must be finite and >= 0");
@@ -1495,6 +1519,8 @@ int sk_ctx_create(int device, sk_ctx **out) {
       cudaEventCreateWithFlags(&c->ev_red, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_red2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_sum, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc((void **)&c->d_gran, sizeof(unsigned int)) != cudaSuccess ||
+      cudaHostAlloc((void **)&c->h_gran, sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess ||
       cudaMalloc((void **)&c->d_red2, sizeof(SkReduceOut)) != cudaSuccess ||
       cudaHostAlloc((void **)&c->h_red2, sizeof(SkReduceOut), cudaHostAllocDefault) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->in_ev[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -1562,6 +1588,8 @@ int sk_ctx_destroy(sk_ctx *c) {
   if (c->ev_red) cudaEventDestroy(c->ev_red);
   if (c->ev_red2) cudaEventDestroy(c->ev_red2);
   if (c->ev_sum) cudaEventDestroy(c->ev_sum);
+  if (c->d_gran) cudaFree(c->d_gran);
+  if (c->h_gran) cudaFreeHost(c->h_gran);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 2; ++i) if (c->ev_user[i]) cudaEventDestroy(c->ev_user[i]);
@@ -2347,7 +2375,6 @@ int sk_first_panel_early(sk_ctx *c, double a, double b, const sk_subinterval_opt
   fill_spec(c, o->speculate, spec);
   spec.fresh = 1;
   spec.dyn = c->d_sum;
-  spec.dyn_xs_alt = c->uxs_fix.p + lo;
   spec.dyn_lo = lo;
   spec.dyn_min_n = min_n;
   SkReduceOut init;
@@ -2433,6 +2460,41 @@ int sk_subinterval_chain(sk_ctx *c, double a2, double b2, const sk_subinterval_o
   c->chain.o.speculate = nullptr;
   c->chain_G = G2;
   *chained = 1;
+  return SK_OK;
+}
+
+// Right after a successful sk_subinterval_chain: enqueue the final gather (sk_results_get_device) behind the chained panel,
+// guarded on the device -- it runs only if that panel is accepted and converges EVERY target, i.e. if it is the last panel
+// of the run (src/adaptive.jl:149); its truncation segment [lo, hi) (src/adaptive.jl:194) is the one sk_converge_apply will
+// register.  The host's sk_results_get_device(vals, errs) then finds the results in place.  *queued = 0: nothing enqueued.
+int sk_results_chain_device(sk_ctx *c, double *vals_dev, double *errs_dev, double accept_below, int32_t *queued) {
+  if (!c || !vals_dev || !queued) return SK_ERR_ARG;
+  *queued = 0;
+  if (!c->chain.pending || c->chain.adopted || c->gchain.pending || c->timing || c->tails.n != 0 || !(accept_below > 0.0))
+    return SK_OK;
+  CK(cudaSetDevice(c->device));
+  sk_ctx::GatherChain &g = c->gchain;
+  std::memset(&g.tails, 0, sizeof(g.tails));
+  if (c->chain.sa.criteria != SK_CRIT_PANEL) {
+    SkTailSeg &t = g.tails.seg[0];
+    t.lo = c->chain.lo; t.hi = c->chain.hi;
+    t.trunc_a = c->chain.sa.trunc_a; t.trunc_num = c->chain.sa.trunc_num; t.xpow = c->chain.sa.xpow;
+    t.criteria = c->chain.sa.criteria; t._pad = 0;
+    g.tails.n = 1;
+  }
+  SkGatherGuard gg;
+  gg.red = c->d_red2;
+  std::memcpy(&gg.maxbits, &accept_below, sizeof(double));
+  gg.top = c->chain.lo - 1;
+  gg.ran = c->d_gran;
+  CK(cudaMemsetAsync(c->d_gran, 0, sizeof(unsigned int), c->stream));
+  k_gather<<<nblk(c->n_in, 1024), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, vals_dev, errs_dev, c->in.p, c->in_scale,
+                                                       g.tails, gg);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(c->h_gran, c->d_gran, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  g.vals = vals_dev; g.errs = errs_dev;
+  g.pending = true;
+  *queued = 1;
   return SK_OK;
 }
 
@@ -2796,6 +2858,20 @@ int sk_target_upper_index(sk_ctx *c, double r, int64_t *idx) {
 int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
   if (!c || !vals_dev) return SK_ERR_ARG;
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
+  if (c->gchain.pending) {
+    // a gather was enqueued behind the last panel (sk_results_chain_device): if it ran and is the gather this call would
+    // do -- same arrays, same truncation segments, nothing pending -- the results are already in place
+    c->gchain.pending = false;
+    const bool same = vals_dev == c->gchain.vals && errs_dev == c->gchain.errs && !c->chain.pending && !c->early1.pending &&
+                      !c->commit_pending && !c->res_zero_pending && !(c->spec_active && !c->spec_accepted) && !c->timing &&
+                      c->tails.n == c->gchain.tails.n &&
+                      std::memcmp(c->tails.seg, c->gchain.tails.seg, sizeof(SkTailSeg) * (size_t)c->tails.n) == 0;
+    CK(cudaStreamSynchronize(c->stream));
+    if (same && *c->h_gran == 1u) {
+      c->stats.n_chained++;
+      return SK_OK;
+    }
+  }
   int rc = rollback_speculation(c);
   if (rc != SK_OK) return rc;
   rc = chain_discard(c);

@@ -73,9 +73,9 @@ struct SkSpec {
   // First panel enqueued behind the SORT (sk_first_panel_early): the number of unique distances and the buffer the
   // unique table ended up in are not known to the host yet -- the kernel takes them from the sort's device-side summary
   // (lo = 0 / 1, the r = 0 row, is known from the first pass).  It skips itself if the sort did not deliver (bad input,
-  // bin overflow -> general sort on the host) or if the active set is too small for the NUFFT branch.
-  const SkTargetSummary *dyn;        // nullptr: n and xs are the kernel arguments
-  const double *dyn_xs_alt;          // the table when duplicates were dropped (pre-offset like xs)
+  // bin overflow -> general sort on the host, duplicates dropped -> the host still compacts the table) or if the active
+  // set is too small for the NUFFT branch.
+  const SkTargetSummary *dyn;        // nullptr: n is the kernel argument
   long long dyn_lo, dyn_min_n;
 };
 
@@ -474,11 +474,11 @@ k_interp_cells(const __grid_constant__ SkEsPlan P, const __grid_constant__ SkGeo
     const long long nu = __ldcg(&spec.dyn->n_unique);
     const unsigned int bad = __ldcg(&spec.dyn->bad), over = __ldcg(&spec.dyn->overflow), fixed = __ldcg(&spec.dyn->fixed);
     n = nu - spec.dyn_lo;
-    if (bad || over || n <= spec.dyn_min_n) {
+    // (fixed: some bin dropped duplicates -- the host still has to compact the table: not this time)
+    if (bad || over || fixed || n <= spec.dyn_min_n) {
       if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&red->flags, SK_FLAG_SKIPPED);
       return;
     }
-    if (fixed) xs = spec.dyn_xs_alt;
     if ((long long)blockIdx.x * 256 * tpt >= n) return;          // the grid was sized for the number of INPUT distances
   }
   extern __shared__ __align__(16) double smem[];
@@ -1276,10 +1276,26 @@ struct SkTailList {
   int n, _pad;
   SkTailSeg seg[SK_MAX_TAILS];
 };
+// A gather can be enqueued ahead of time behind a chained last panel (sk_results_chain_device): it then runs only if that
+// panel turned out accepted (max |I2-I1| below the accept threshold, no NaN, not skipped) with EVERY target converged
+// (guard->max_unconv == gtop = lo - 1: the adaptive loop ends, src/adaptive.jl:149), and says so in *ran.
+struct SkGatherGuard {
+  const SkReduceOut *red;            // nullptr: unconditional
+  unsigned long long maxbits;
+  long long top;
+  unsigned int *ran;
+};
 __global__ void __launch_bounds__(256)
 k_gather(const unsigned int *__restrict__ inv, const sk_cplx *__restrict__ res, long long n,
          double *__restrict__ out_v, double *__restrict__ out_e, const double *__restrict__ xin, double xscale,
-         const __grid_constant__ SkTailList T) {
+         const __grid_constant__ SkTailList T, const SkGatherGuard gg = SkGatherGuard{nullptr, 0ull, 0, nullptr}) {
+  if (gg.red != nullptr) {
+    const unsigned long long mb = __ldcg(&gg.red->maxbits);
+    const unsigned int fl = __ldcg(&gg.red->flags);
+    const long long top = __ldcg(&gg.red->max_unconv);
+    if (!(mb < gg.maxbits && fl == 0u && top == gg.top)) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *gg.ran = 1u;
+  }
   // 4 independent random reads in flight per thread (the kernel is bound by the latency of the 16-byte reads)
   const long long j0 = ((long long)blockIdx.x * blockDim.x) * 4 + threadIdx.x;
   unsigned int u[4];

@@ -760,3 +760,39 @@ def test_overlapped_host_work_and_chained_panels_are_bitwise_neutral(sk):
         assert s0["n_chained"] == 0
         if want_chained is not None:
             assert s1["n_chained"] == want_chained, (name, s1)
+
+
+def test_chained_gather_device_resident_run(sk):
+    """device pointers in and out: the first panel queued behind the sort, the second behind the first and the final gather
+    behind the second (sk_results_chain_device) are all picked up (n_chained = 3) and the values / error estimates equal
+    the blocking call sequence bit for bit; with duplicated distances the launch behind the sort skips itself (the host
+    still has to compact the unique table) and the run falls back to the ordinary sequence; with a shrinking active set
+    the guards fail on the device and nothing changes"""
+    import torch
+    from spectralkernels_jl_b200 import adaptive as ad
+    rng = np.random.default_rng(5)
+    for name, S, xs, k0, want in (("all predictions hold", sk.Matern(1 / (np.pi / 2), 1.0, 1.5), rng.uniform(0, 1, 400_000), 1.0, 3),
+                                  ("zero lags and duplicates", sk.Matern(1 / (np.pi / 2), 1.0, 1.5),
+                                   np.concatenate([[0.0, 0.0], np.repeat(rng.uniform(0, 1, 150_000), 2)]), 1.0, 0),
+                                  ("shrinking active set", sk.Matern(1.0, 0.5, 0.55), 10 ** rng.uniform(-4, 0, 200_000), 5.9, None)):
+        d_in = torch.from_numpy(xs).cuda()
+        outs = []
+        for overlap in (False, True):
+            ad.OVERLAP_HOST_WORK = overlap
+            try:
+                cfg = sk.AdaptiveKernelConfig(S)
+                d_v = torch.full_like(d_in, -7.0)
+                d_e = torch.full_like(d_in, -7.0)
+                sk.kernel_values(cfg, None, k0=k0, xs_device=(d_in.data_ptr(), xs.size), out_device=(d_v.data_ptr(), d_e.data_ptr()))
+                torch.cuda.synchronize()
+                outs.append((d_v.cpu().numpy(), d_e.cpu().numpy(), cfg.engine.stats()["n_chained"]))
+            finally:
+                ad.OVERLAP_HOST_WORK = True
+        (v0, e0, c0), (v1, e1, c1) = outs
+        assert np.array_equal(v0, v1), name
+        assert np.array_equal(np.nan_to_num(e0, nan=-1.0), np.nan_to_num(e1, nan=-1.0)), name
+        assert c0 == 0, name
+        if want is not None:
+            assert c1 == want, (name, c1)
+        ref, _ = sk.kernel_values(sk.AdaptiveKernelConfig(S), xs, k0=k0)
+        assert np.array_equal(ref, v1), name
