@@ -188,6 +188,12 @@ int sk_comm_last(sk_ctx *ctx, double *max_abs_diff, double *r_stop, int64_t *n_a
 int sk_comm_peer_export(sk_ctx *ctx, void *handle64);
 int sk_comm_peer_attach(sk_ctx *ctx, const void *handles, int32_t rank, int32_t nranks);
 int sk_comm_allgather(sk_ctx *ctx, const double *vals, int32_t k, double *out);
+/* With mailboxes attached, sk_targets_set* / sk_targets_end also deliver what the ranks exchange at the start of a run
+ * (src/adaptive.jl:123, :152): the smallest positive and the largest distance over all ranks and the summed number of
+ * positive unique distances -- sent behind the sort's summary kernel, so it costs no synchronisation of its own.
+ * *valid = 0: not available (some rank's sort took a path whose summary the host recomputes); every rank sees the same
+ * answer and then exchanges the three numbers with sk_comm_allgather. */
+int sk_comm_summary(sk_ctx *ctx, int32_t *valid, double *r_lo, double *r_hi, int64_t *n_active);
 int sk_comm_peer_selftest(sk_ctx *ctx, int32_t nranks, int32_t rounds, const uint64_t *maxbits_in, const uint64_t *rbits_in,
                           const int64_t *top_in, int64_t lo, uint64_t *out5);
 

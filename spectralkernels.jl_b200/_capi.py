@@ -91,6 +91,7 @@ SIGNATURES = {
     "sk_comm_peer_export": (c_int, [c_void_p, c_void_p]),
     "sk_comm_peer_attach": (c_int, [c_void_p, c_void_p, c_int32, c_int32]),
     "sk_comm_allgather": (c_int, [c_void_p, _dp, c_int32, _dp]),
+    "sk_comm_summary": (c_int, [c_void_p, POINTER(c_int32), _dp, _dp, POINTER(c_int64)]),
     "sk_comm_peer_selftest": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "sk_host_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "sk_host_free": (c_int, [c_void_p]),
@@ -301,6 +302,12 @@ class Session:
         out = np.empty(a.size * int(nranks), dtype=np.float64)
         self._ck(self._L.sk_comm_allgather(self._h, _p(a), a.size, _p(out)))
         return out.reshape(int(nranks), a.size).tolist()
+
+    def comm_summary(self):
+        """(valid, r_lo, r_hi, n_active) over all ranks, delivered behind the last targets_set* (peer mailboxes)"""
+        ok, lo, hi, n = c_int32(0), c_double(), c_double(), c_int64()
+        self._ck(self._L.sk_comm_summary(self._h, byref(ok), byref(lo), byref(hi), byref(n)))
+        return bool(ok.value), lo.value, hi.value, n.value
 
     def comm_peer_selftest(self, maxbits, rbits, top, lo: int, rounds: int = 3):
         """the exchange protocol with len(maxbits) ranks emulated on this one device (test hook)"""

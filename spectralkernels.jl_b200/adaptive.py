@@ -486,11 +486,18 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
     fused = getattr(comm, "fused", False)
     rmin_local = info.r_min_pos if info.r_min_pos > 0 else math.inf
     # (+-inf would turn into NaN in a one-hot sum: a rank without positive distances sends the largest double)
-    g0 = comm.gather([rmin_local if math.isfinite(rmin_local) else 1.7976931348623157e308, r_hi_local,
-                      float(max(n - ix1 + 1, 0))])
-    r_lo_g = min(v[0] for v in g0)
-    r_hi_g = max(v[1] for v in g0)
-    n_act_g = int(sum(v[2] for v in g0))
+    summ = eng.comm_summary() if (fused and not reuse_targets and getattr(comm, "mode", "") == "peer"
+                                  and hasattr(eng, "comm_summary")) else (False,)
+    if summ[0]:
+        # the three numbers went round behind the sort's summary kernel (sk_comm_summary): no collective of their own
+        r_lo_g = summ[1] if summ[1] > 0 else 1.7976931348623157e308
+        r_hi_g, n_act_g = summ[2], int(summ[3])
+    else:
+        g0 = comm.gather([rmin_local if math.isfinite(rmin_local) else 1.7976931348623157e308, r_hi_local,
+                          float(max(n - ix1 + 1, 0))])
+        r_lo_g = min(v[0] for v in g0)
+        r_hi_g = max(v[1] for v in g0)
+        n_act_g = int(sum(v[2] for v in g0))
     m2 = 2 * cfg.quadsz
     ipanel = 0
     tau = cfg.tol * abs(k0) / 2                                                  # :191

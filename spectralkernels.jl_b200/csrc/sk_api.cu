@@ -219,7 +219,8 @@ struct sk_ctx {
   unsigned long long *peer_box = nullptr;    // this rank's mailbox (device memory, exported through CUDA IPC)
   unsigned long long *peer_map[SK_PEER_MAX] = {nullptr};   // the peers' mailboxes as mapped here
   unsigned long long peer_epoch = 0;
-  SkPeerOut *peer_out[3] = {nullptr, nullptr, nullptr};    // pinned: sub-interval / scan, early range, host values
+  SkPeerOut *peer_out[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned: sub-interval / scan, early range, host values, run summary
+  bool peer_summary_sent = false;            // the sort's summary went out behind it (sk_comm_summary)
   double peer_timeout_s = 20.0;
   SkGlobalA *d_ga = nullptr;
   SkGlobalB *d_gb = nullptr;
@@ -360,7 +361,7 @@ void peer_release(sk_ctx *c) {
 // one exchange over the peer mailboxes (see k_peer_exchange): enqueued on the compute stream, the reduced words land in
 // pinned host memory (slot 0: sub-interval / scan scalars, 1: the early key range, 2: host values)
 int peer_exchange(sk_ctx *c, int slot, int kind, int idle, int err, long long lo, const unsigned long long *imm, int nw,
-                  int raw_op, const SkK8State *k8 = nullptr) {
+                  int raw_op, const SkK8State *k8 = nullptr, const SkTargetSummary *sum = nullptr) {
   SkPeerArgs a;
   std::memset(&a, 0, sizeof(a));
   for (int r = 0; r < c->peer_n; ++r) a.box[r] = c->peer_map[r];
@@ -370,7 +371,7 @@ int peer_exchange(sk_ctx *c, int slot, int kind, int idle, int err, long long lo
   a.timeout_ns = (unsigned long long)(c->peer_timeout_s * 1e9);
   a.kind = kind; a.idle = idle; a.err = err; a.raw_op = raw_op; a.lo = lo; a.nw = nw;
   for (int i = 0; i < 7; ++i) a.imm[i] = (imm && i < nw) ? imm[i] : 0ull;
-  k_peer_exchange<<<1, 32, 0, c->stream>>>(a, c->d_red, k8, c->peer_out[slot]);
+  k_peer_exchange<<<1, 32, 0, c->stream>>>(a, c->d_red, k8, c->peer_out[slot], sum);
   LAUNCH_CHECK();
   return SK_OK;
 }
@@ -1348,6 +1349,15 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, c->uxs_fix.p, n_in, c->d_sum);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
+  c->peer_summary_sent = false;
+  if (c->peer_n > 0 && !c->in_group) {
+    // process-per-GPU run over peer mailboxes: what the ranks exchange at the start of a run (global distance range, global
+    // active count) goes out right behind the summary -- the host finds it when the sort's synchronisation returns
+    // (sk_comm_summary) instead of paying for a synchronous gather
+    int rcx = peer_exchange(c, 3, SK_PX_SUMMARY, 0, 0, 0, nullptr, 0, 0, nullptr, c->d_sum);
+    if (rcx != SK_OK) return rcx;
+    c->peer_summary_sent = true;
+  }
   if (c->in_src) CK(cudaStreamWaitEvent(c->stream, c->in_ev[1], 0));   // the library's copy of the distances is complete
   CK(cudaEventRecord(c->ev_sum, c->stream));
   if (early && !c->in_group) {
@@ -1561,7 +1571,7 @@ int sk_ctx_destroy(sk_ctx *c) {
   c->hk_lev.release(); c->hk_groups.release(); c->hk_grid.release(); c->hk_part.release(); c->hk_modes.release();
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   peer_release(c);
-  for (int i = 0; i < 3; ++i) if (c->peer_out[i]) cudaFreeHost(c->peer_out[i]);
+  for (int i = 0; i < 4; ++i) if (c->peer_out[i]) cudaFreeHost(c->peer_out[i]);
   if (c->d_ga) cudaFree(c->d_ga);
   if (c->d_gb) cudaFree(c->d_gb);
   if (c->d_hv) cudaFree(c->d_hv);
@@ -1739,7 +1749,7 @@ int sk_comm_peer_attach(sk_ctx *c, const void *handles, int32_t rank, int32_t nr
     CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     c->peer_map[r] = (unsigned long long *)p;
   }
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 4; ++i)
     if (!c->peer_out[i]) {
       CK(cudaHostAlloc((void **)&c->peer_out[i], sizeof(SkPeerOut), cudaHostAllocPortable));
       std::memset(c->peer_out[i], 0, sizeof(SkPeerOut));
@@ -1766,6 +1776,27 @@ int sk_comm_allgather(sk_ctx *c, const double *vals, int32_t k, double *out) {
   rc = peer_check(c, 2);
   if (rc != SK_OK) return rc;
   std::memcpy(out, c->peer_out[2]->words, sizeof(double) * k * c->peer_n);
+  return SK_OK;
+}
+
+// what the ranks exchange at the start of a run, as delivered behind the last sk_targets_set* / sk_targets_end (peer
+// mailboxes only): smallest positive and largest distance over all ranks (0 when no rank has one) and the number of
+// positive unique distances summed over the ranks.  *valid = 0: not available (no mailboxes, or some rank's sort took a
+// path whose summary the host recomputes): every rank then exchanges them with sk_comm_allgather / sk_comm_allreduce.
+int sk_comm_summary(sk_ctx *c, int32_t *valid, double *r_lo, double *r_hi, int64_t *n_active) {
+  if (!c || !valid || !r_lo || !r_hi || !n_active) return SK_ERR_ARG;
+  *valid = 0; *r_lo = 0.0; *r_hi = 0.0; *n_active = 0;
+  if (c->peer_n <= 0 || !c->peer_summary_sent) return SK_OK;
+  c->peer_summary_sent = false;
+  int rc = peer_check(c, 3);
+  if (rc != SK_OK) return rc;
+  const unsigned long long *w = c->peer_out[3]->words;
+  if (w[2]) return SK_OK;
+  const unsigned long long kmin = ~w[0];
+  if (w[0]) std::memcpy(r_lo, &kmin, sizeof(double));
+  std::memcpy(r_hi, &w[1], sizeof(double));
+  *n_active = (int64_t)w[3];
+  *valid = 1;
   return SK_OK;
 }
 

@@ -963,7 +963,8 @@ __global__ void k_pack_global_b_from_red(const SkReduceOut *__restrict__ red, lo
 // The wait is bounded (timeout_ns of %globaltimer): a lost peer turns into an error word, not a hang.
 constexpr int SK_PEER_MAX = 16;
 constexpr int SK_PEER_WORDS = 8;       // 7 payload words + the epoch word: one 64-byte line per (half, rank)
-enum { SK_PX_A = 0, SK_PX_AB = 1, SK_PX_B_RED = 2, SK_PX_B_IMM = 3, SK_PX_RANGE = 4, SK_PX_RAW = 5, SK_PX_GATHER = 6 };
+enum { SK_PX_A = 0, SK_PX_AB = 1, SK_PX_B_RED = 2, SK_PX_B_IMM = 3, SK_PX_RANGE = 4, SK_PX_RAW = 5, SK_PX_GATHER = 6,
+       SK_PX_SUMMARY = 7 };
 struct SkPeerArgs {
   unsigned long long *box[SK_PEER_MAX];   // box[r]: rank r's mailbox as mapped on this device (box[rank]: the own one)
   int rank, n;
@@ -1006,7 +1007,8 @@ __device__ __forceinline__ unsigned long long sk_warp_max_u64(unsigned long long
 
 // the exchange as seen by ONE rank (a warp); `a` holds that rank's view of the mailboxes
 __device__ __forceinline__ void sk_peer_exchange_warp(const SkPeerArgs &a, const SkReduceOut *__restrict__ red,
-                                                      const SkK8State *__restrict__ k8, SkPeerOut *__restrict__ out) {
+                                                      const SkK8State *__restrict__ k8, SkPeerOut *__restrict__ out,
+                                                      const SkTargetSummary *__restrict__ sum = nullptr) {
   const int lane = threadIdx.x & 31;
   unsigned long long w[7] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
   const bool quiet = a.idle || a.err;
@@ -1025,6 +1027,18 @@ __device__ __forceinline__ void sk_peer_exchange_warp(const SkPeerArgs &a, const
   }
   if (a.kind == SK_PX_B_IMM) { w[5] = a.imm[0]; w[6] = a.imm[1]; }
   if (a.kind == SK_PX_RANGE) { w[0] = k8->kmin_inv; w[1] = k8->kmax; w[2] = k8->bad ? 1ull : 0ull; }
+  if (a.kind == SK_PX_SUMMARY) {
+    // what every rank contributes to the start of a run (src/adaptive.jl:123, :152): its smallest positive and its largest
+    // unique distance and the number of positive unique distances -- straight from the sort's summary; w[2] flags a
+    // summary the host still has to redo (general sort, duplicates to compact): then every rank falls back to a gather
+    const long long nu = sum->n_unique;
+    const long long lo = sum->r0 == 0.0 ? 1 : 0, cnt = nu - lo > 0 ? nu - lo : 0;
+    const double rmin = lo ? sum->r1 : sum->r0;
+    w[0] = cnt > 0 ? ~(unsigned long long)__double_as_longlong(rmin) : 0ull;
+    w[1] = cnt > 0 ? (unsigned long long)__double_as_longlong(sum->r_last) : 0ull;
+    w[2] = (sum->bad || sum->overflow || sum->fixed) ? 1ull : 0ull;
+    w[6] = (unsigned long long)cnt;
+  }
   if (a.kind == SK_PX_RAW || a.kind == SK_PX_GATHER) {
 #pragma unroll
     for (int i = 0; i < 7; ++i) w[i] = a.imm[i];
@@ -1078,6 +1092,7 @@ __device__ __forceinline__ void sk_peer_exchange_warp(const SkPeerArgs &a, const
       }
       if (a.kind == SK_PX_AB || a.kind == SK_PX_B_RED || a.kind == SK_PX_B_IMM) { out->gb.rbits = r[5]; out->gb.n_lb = s; }
       if (a.kind == SK_PX_RANGE) { out->words[0] = r[0]; out->words[1] = r[1]; out->words[2] = r[2]; }
+      if (a.kind == SK_PX_SUMMARY) { out->words[0] = r[0]; out->words[1] = r[1]; out->words[2] = r[2]; out->words[3] = (unsigned long long)s; }
     }
   }
   if (lane == 0) {
@@ -1087,8 +1102,9 @@ __device__ __forceinline__ void sk_peer_exchange_warp(const SkPeerArgs &a, const
 }
 
 __global__ void __launch_bounds__(32) k_peer_exchange(SkPeerArgs a, const SkReduceOut *__restrict__ red,
-                                                      const SkK8State *__restrict__ k8, SkPeerOut *__restrict__ out) {
-  sk_peer_exchange_warp(a, red, k8, out);
+                                                      const SkK8State *__restrict__ k8, SkPeerOut *__restrict__ out,
+                                                      const SkTargetSummary *__restrict__ sum) {
+  sk_peer_exchange_warp(a, red, k8, out, sum);
 }
 
 // The same protocol with the ranks emulated as the blocks of ONE cooperative launch on one device (tests: separate
