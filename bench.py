@@ -409,6 +409,11 @@ def run(args):
             "config": {"workload": WORKLOAD,
                        "n_per_gpu": nloc, "k0": "passed (=1.0) in both arms", "nufft_eps": 1e-15,
                        "l2": "inputs + work arrays (>1 GB per step) exceed the 126 MB L2; no explicit flush",
+                       "launch_chaining": ("device-guarded: first panel queued behind the sort, second behind the first, gather "
+                                           "behind the second (sk_first_panel_early / sk_subinterval_chain / "
+                                           "sk_results_chain_device); host scalar work overlapped") if world == 1 else
+                                          "host scalar work overlapped with device work (begin/end halves); no chained launches "
+                                          "in sharded runs",
                        "parallelism": ("target-sharded, scalar collectives only: "
                                        + {"peer": "single-warp exchange kernels over NVLink peer-mapped mailboxes "
                                                   "(k_peer_exchange) on the compute stream, no NCCL on the data path",

@@ -21,6 +21,12 @@
 # `kernel_sdf_derivatives` / `kernel_warping_gradients` / `kernel_singularity_derivative` (src/derivatives.jl:51-81),
 # the ForwardDiff and ChainRules extensions (ext/SpectralKernelsForwardDiffExt.jl:7-22) and the Vecchia extension
 # (ext/SpectralKernelsVecchiaExt.jl:19-27).
+#
+# This file uses the plain blocking entry points (sk_targets_set, sk_subinterval, sk_results_get).  The ABI also offers
+# them in two halves plus device-guarded chained launches (sk_targets_begin/_early_range/_end, sk_first_panel_early,
+# sk_subinterval_begin/_chain/_end, sk_results_chain_device: INTEGRATION.md) so that `estimate_tail_decay` for the next
+# panel runs while the device works and consecutive panels run back to back; adaptive.py shows the call order.  They only
+# move WHEN work is enqueued -- values, error estimates and traces are bit-identical -- so adopting them is optional.
 module SpectralKernelsB200
 
 using SpectralKernels
