@@ -259,39 +259,32 @@ k_k8_scan_bins(SkK8State *__restrict__ st, const unsigned int *__restrict__ src,
   if (!st->ndesc) return;
   if (which == 1 && st->ndup == 0ull) return;
   __shared__ unsigned int s_w[32];
+  __shared__ unsigned int s_run;
   const unsigned int nb = st->nfine;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  // one pass: thread t owns the `per` consecutive bins [t * per, (t + 1) * per) -- a serial sum over them, ONE block-level
-  // scan of the 1024 partial sums, then the bins' offsets (the chunked version looped over the block scan ~10 times)
-  const unsigned int per = (nb + 1023u) / 1024u;
-  const unsigned int b_lo = threadIdx.x * per, b_hi = b_lo + per < nb ? b_lo + per : nb;
-  unsigned int sum = 0u;
-  for (unsigned int b = b_lo; b < b_hi; ++b) {
-    unsigned int v = src[(size_t)b * stride];
-    sum += v < cap ? v : cap;
-  }
-  unsigned int inc = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) s_w[wid] = inc;
+  if (threadIdx.x == 0) s_run = 0u;
   __syncthreads();
-  unsigned int wbase = 0u, total = 0u;
-  for (int w = 0; w < 32; ++w) {
-    const unsigned int x = s_w[w];
-    if (w < wid) wbase += x;
-    total += x;
+  for (unsigned int b0 = 0; b0 < nb; b0 += 1024u) {
+    const unsigned int b = b0 + threadIdx.x;
+    unsigned int v = 0u;
+    if (b < nb) { v = src[(size_t)b * stride]; v = v < cap ? v : cap; }
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    unsigned int wbase = 0u;
+    for (int w = 0; w < wid; ++w) wbase += s_w[w];
+    const unsigned int base = s_run;
+    if (b < nb) dst[b] = base + wbase + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_run = base + wbase + inc;
+    __syncthreads();
   }
-  unsigned int run = wbase + inc - sum;
-  for (unsigned int b = b_lo; b < b_hi; ++b) {
-    unsigned int v = src[(size_t)b * stride];
-    v = v < cap ? v : cap;
-    dst[b] = run;
-    run += v;
-  }
-  if (threadIdx.x == 0 && which == 0) st->n_slots = total;
+  if (threadIdx.x == 0 && which == 0) st->n_slots = s_run;
 }
 
 // ---- pass 3: finish every fine bin in shared memory ----------------------------------------------------------
