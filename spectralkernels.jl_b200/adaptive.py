@@ -192,6 +192,12 @@ def _scan_args(cfg, b, c, d, tau, crit) -> ScanArgs:
 OVERLAP_HOST_WORK = True
 
 
+def _may_chain(comm) -> bool:
+    """Chained launches (sk_first_panel_early, sk_subinterval_chain): single-GPU runs, and sharded runs whose collectives
+    go over peer mailboxes (the guards then read the global scalars; the library refuses them otherwise anyway)."""
+    return comm.world_size == 1 or (getattr(comm, "fused", False) and getattr(comm, "mode", "") == "peer")
+
+
 def _panel_scalars(cfg, a: float, b: float, crit: str, tau: float):
     """Everything the convergence scan of panel (a, b) needs that depends on the panel ends only: the tail fit
     (src/adaptive.jl:168-175) and the target-independent pieces of the truncation bound.  Returns
@@ -341,7 +347,7 @@ def fourier_integrate_interval(cfg: AdaptiveKernelConfig, eng, a: float, b: floa
                 eng.subinterval_begin(_a, _b, cfg.c, cfg.p, kernel, cfg.logw, speculate=spec, nu=nu, xdiv_pow=xdiv)
                 try:
                     nxt = while_enqueued()
-                    if nxt is not None and comm.world_size == 1 and hasattr(eng, "subinterval_chain"):
+                    if nxt is not None and _may_chain(comm) and hasattr(eng, "subinterval_chain"):
                         # the next panel's first sub-interval goes in behind this one, guarded on the device: it runs
                         # only if this one is accepted (:260) and converges nothing (sk_subinterval_chain)
                         a2, b2, sargs2 = nxt
@@ -447,7 +453,7 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
                     b1 = 0.0 + cfg.quadsz / (2 * r_early)
                     ps = _panel_scalars(cfg, 0.0, b1, cfg.convergence_criteria, cfg.tol * abs(k0) / 2)
                     pre[(0.0, b1, cfg.convergence_criteria)] = ps
-                    if comm.world_size == 1 and cfg.dim == 1 and is_builtin(cfg.f) and ps[2] == cfg.convergence_criteria \
+                    if _may_chain(comm) and cfg.dim == 1 and is_builtin(cfg.f) and ps[2] == cfg.convergence_criteria \
                             and hasattr(eng, "first_panel_early"):
                         # the first panel goes in behind the sort (sk_first_panel_early): its kernel takes the number
                         # of unique distances from the sort's device-side summary
@@ -534,7 +540,10 @@ def kernel_values(cfg: AdaptiveKernelConfig, xs, *, k0: Optional[float] = None, 
         fourier_integrate_interval(cfg, eng, a, b, abs(k0), comm, active, verbose=verbose, trace=trace,
                                    speculate=sargs, n_act_g=n_act_g, spec_state=spec_state,
                                    while_enqueued=ahead if (ipanel == 0 or pre_hit) else None,
-                                   chain_out=out_device if (out_device is not None and not async_results) else None)  # :157-159
+                                   # (the gather is chained in single-GPU runs only: behind a sharded panel's exchange
+                                   #  kernel it measured 28 us SLOWER than launching it from the host)
+                                   chain_out=out_device if (out_device is not None and not async_results
+                                                            and comm.world_size == 1) else None)             # :157-159
         if active:
             eng.panel_commit()                                                   # :163-164
         if verbose and crit_msg:

@@ -219,7 +219,12 @@ struct sk_ctx {
   unsigned long long *peer_box = nullptr;    // this rank's mailbox (device memory, exported through CUDA IPC)
   unsigned long long *peer_map[SK_PEER_MAX] = {nullptr};   // the peers' mailboxes as mapped here
   unsigned long long peer_epoch = 0;
-  SkPeerOut *peer_out[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned: sub-interval / scan, early range, host values, run summary
+  SkPeerOut *peer_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // pinned: sub-interval / scan, early range, host values,
+                                                                           // run summary, chained sub-interval
+  SkPeerOut *d_gout[2] = {nullptr, nullptr}; // device mirrors of slots 0 and 4 (the guards of chained launches read them)
+  int peer_slot = 0;                         // where the scalars of the sub-interval being finished are: 0, or 4 (chained)
+  const SkReduceOut *cur_red = nullptr;      // its local reduction slot (d_red, or d_red2 for an adopted chained launch)
+  bool sharded_chain = true;                 // chained launches in sharded runs (SK_SHARDED_CHAIN=0 switches them off)
   bool peer_summary_sent = false;            // the sort's summary went out behind it (sk_comm_summary)
   double peer_timeout_s = 20.0;
   SkGlobalA *d_ga = nullptr;
@@ -361,7 +366,8 @@ void peer_release(sk_ctx *c) {
 // one exchange over the peer mailboxes (see k_peer_exchange): enqueued on the compute stream, the reduced words land in
 // pinned host memory (slot 0: sub-interval / scan scalars, 1: the early key range, 2: host values)
 int peer_exchange(sk_ctx *c, int slot, int kind, int idle, int err, long long lo, const unsigned long long *imm, int nw,
-                  int raw_op, const SkK8State *k8 = nullptr, const SkTargetSummary *sum = nullptr) {
+                  int raw_op, const SkK8State *k8 = nullptr, const SkTargetSummary *sum = nullptr,
+                  const SkReduceOut *red = nullptr) {
   SkPeerArgs a;
   std::memset(&a, 0, sizeof(a));
   for (int r = 0; r < c->peer_n; ++r) a.box[r] = c->peer_map[r];
@@ -371,7 +377,8 @@ int peer_exchange(sk_ctx *c, int slot, int kind, int idle, int err, long long lo
   a.timeout_ns = (unsigned long long)(c->peer_timeout_s * 1e9);
   a.kind = kind; a.idle = idle; a.err = err; a.raw_op = raw_op; a.lo = lo; a.nw = nw;
   for (int i = 0; i < 7; ++i) a.imm[i] = (imm && i < nw) ? imm[i] : 0ull;
-  k_peer_exchange<<<1, 32, 0, c->stream>>>(a, c->d_red, k8, c->peer_out[slot], sum);
+  SkPeerOut *dout = slot == 0 ? c->d_gout[0] : (slot == 4 ? c->d_gout[1] : nullptr);
+  k_peer_exchange<<<1, 32, 0, c->stream>>>(a, red ? red : c->d_red, k8, c->peer_out[slot], sum, dout);
   LAUNCH_CHECK();
   return SK_OK;
 }
@@ -433,8 +440,11 @@ int comm_reduce_b(sk_ctx *c, bool from_red, unsigned long long rbits, long long 
   CK(cudaMemcpyAsync(&c->h_scal->gb, c->d_gb, sizeof(SkGlobalB), cudaMemcpyDeviceToHost, c->stream));
   return SK_OK;
 }
-const SkGlobalA &global_a(const sk_ctx *c) { return c->peer_n > 0 ? c->peer_out[0]->ga : c->h_scal->ga; }
-const SkGlobalB &global_b(const sk_ctx *c) { return c->peer_n > 0 ? c->peer_out[0]->gb : c->h_scal->gb; }
+const SkGlobalA &global_a(const sk_ctx *c) { return c->peer_n > 0 ? c->peer_out[c->peer_slot]->ga : c->h_scal->ga; }
+const SkGlobalB &global_b(const sk_ctx *c) { return c->peer_n > 0 ? c->peer_out[c->peer_slot]->gb : c->h_scal->gb; }
+// a void exchange (some rank's chained launch skipped itself, k_peer_exchange) does not count: every rank issues the
+// exchange again -- with the same local scalars, or after evaluating the sub-interval it had skipped
+inline bool peer_void(const sk_ctx *c) { return c->peer_n > 0 && c->peer_out[c->peer_slot]->void_flag != 0ull; }
 void comm_take_a(sk_ctx *c, unsigned int *fl, double *mx) {   // after the stream sync
   if (!sharded(c)) return;
   const SkGlobalA &g = global_a(c);
@@ -931,9 +941,36 @@ int transform_and_stage_enqueue(sk_ctx *c, double a, double b, const sk_subinter
   if (!sharded(c)) return rc;
   // sharded run: a rank that failed locally still joins the collective (its peers are waiting in it)
   const std::string msg = c->errmsg;
+  c->peer_slot = 0;
+  c->cur_red = c->d_red;
   const int rcc = c->pend_ab ? comm_reduce_ab(c, 0, rc != SK_OK) : comm_reduce_a(c, 0, rc != SK_OK);
   if (rc != SK_OK) c->errmsg = msg;
+  if (rcc == SK_OK) cudaEventRecord(c->ev_red, c->stream);      // (behind the exchange: _finish may wait on the event only)
   return rcc != SK_OK ? rcc : SK_OK;                     // a local failure is reported by _finish, after the collective
+}
+
+// chained launches in a sharded run need the mailboxes (their guards read the global scalars the exchange kernels leave
+// in device memory, and a skipped launch turns its exchange void); with NCCL all-reduces they stay off
+inline bool chain_allowed(const sk_ctx *c) {
+  return !sharded(c) || (c->peer_n > 0 && c->comm == nullptr && c->sharded_chain);
+}
+
+// sharded run over mailboxes: while the exchange just read back is void (some rank's chained launch skipped itself),
+// issue it again with this rank's local scalars; every rank does the same, so the exchanges stay paired
+int peer_resend_while_void(sk_ctx *c) {
+  int guard = 0;
+  while (peer_void(c)) {
+    if (++guard > 8) return fail(c, SK_ERR_STATE, "peer exchange: too many void rounds");
+    c->peer_slot = 0;
+    const long long lo = c->lo;
+    int rc = peer_exchange(c, 0, c->pend_ab ? SK_PX_AB : SK_PX_A, 0, c->pend_rc != SK_OK, lo, nullptr, 0, 0, nullptr, nullptr,
+                           c->cur_red);
+    if (rc != SK_OK) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    rc = peer_check(c, 0);
+    if (rc != SK_OK) return rc;
+  }
+  return SK_OK;
 }
 
 // flags_out != nullptr: hand the NaN flags to the caller (a device group applies the rule of src/quadrature.jl:165
@@ -951,12 +988,14 @@ int transform_and_stage_finish(sk_ctx *c, double *max_abs_diff, unsigned int *fl
       o.speculate = &c->chain.sa;
       make_panel_spec(c, c->chain.a, c->chain.b, o.logw, &c->pend_S);
       c->need_gen = true;
-      int rc = transform_and_stage_enqueue_local(c, c->chain.a, c->chain.b, &o);
+      int rc = sharded(c) ? transform_and_stage_enqueue(c, c->chain.a, c->chain.b, &o)      // (with its exchange)
+                          : transform_and_stage_enqueue_local(c, c->chain.a, c->chain.b, &o);
       if (rc != SK_OK) return rc;
       CK(cudaStreamSynchronize(c->stream));
     } else {
       c->h_scal->red = *c->h_red2;
       c->stats.n_chained++;
+      if (sharded(c)) { c->peer_slot = 4; c->cur_red = c->d_red2; }
     }
   } else if (c->chain.pending) {
     CK(cudaEventSynchronize(c->ev_red));      // a chained launch is queued behind this sub-interval: do not wait for it
@@ -976,7 +1015,8 @@ int transform_and_stage_finish(sk_ctx *c, double *max_abs_diff, unsigned int *fl
       c->spec_fresh = false;
       make_panel_spec(c, c->early1.a, c->early1.b, o.logw, &c->pend_S);
       c->need_gen = true;
-      rc = transform_and_stage_enqueue_local(c, c->early1.a, c->early1.b, &o);
+      rc = sharded(c) ? transform_and_stage_enqueue(c, c->early1.a, c->early1.b, &o)
+                      : transform_and_stage_enqueue_local(c, c->early1.a, c->early1.b, &o);
       if (rc != SK_OK) return rc;
       CK(cudaStreamSynchronize(c->stream));
     } else {
@@ -985,7 +1025,9 @@ int transform_and_stage_finish(sk_ctx *c, double *max_abs_diff, unsigned int *fl
   }
   if (sharded(c)) {
     if (c->pend_rc != SK_OK) return c->pend_rc;                     // this rank's own failure (message already set)
-    const int prc = peer_check(c, 0);
+    int prc = peer_check(c, c->peer_slot);
+    if (prc != SK_OK) return prc;
+    prc = peer_resend_while_void(c);                                // (some other rank's chained launch skipped itself)
     if (prc != SK_OK) return prc;
     if (global_a(c).err) return fail(c, SK_ERR_STATE, "another rank failed in this sub-interval");
   }
@@ -1315,6 +1357,7 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
       // (peer mailboxes: the same 3-word MAX as one exchange kernel; the result lands in pinned memory, slot 1)
       int rcx = peer_exchange(c, 1, SK_PX_RANGE, 0, 0, 0, nullptr, 0, 0, st);
       if (rcx != SK_OK) return rcx;
+      CK(cudaMemcpyAsync(&c->h_scal->k8, st, sizeof(SkK8State), cudaMemcpyDeviceToHost, c->stream));   // (this rank's zeros)
       c->early_global = true;
     } else if (c->comm) {
       // process-per-GPU run: the panels are built from the GLOBAL distance range, so the ranks reduce their key
@@ -1571,7 +1614,8 @@ int sk_ctx_destroy(sk_ctx *c) {
   c->hk_lev.release(); c->hk_groups.release(); c->hk_grid.release(); c->hk_part.release(); c->hk_modes.release();
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   peer_release(c);
-  for (int i = 0; i < 4; ++i) if (c->peer_out[i]) cudaFreeHost(c->peer_out[i]);
+  for (int i = 0; i < 5; ++i) if (c->peer_out[i]) cudaFreeHost(c->peer_out[i]);
+  for (int i = 0; i < 2; ++i) if (c->d_gout[i]) cudaFree(c->d_gout[i]);
   if (c->d_ga) cudaFree(c->d_ga);
   if (c->d_gb) cudaFree(c->d_gb);
   if (c->d_hv) cudaFree(c->d_hv);
@@ -1749,11 +1793,18 @@ int sk_comm_peer_attach(sk_ctx *c, const void *handles, int32_t rank, int32_t nr
     CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     c->peer_map[r] = (unsigned long long *)p;
   }
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 5; ++i)
     if (!c->peer_out[i]) {
       CK(cudaHostAlloc((void **)&c->peer_out[i], sizeof(SkPeerOut), cudaHostAllocPortable));
       std::memset(c->peer_out[i], 0, sizeof(SkPeerOut));
     }
+  for (int i = 0; i < 2; ++i)
+    if (!c->d_gout[i]) {
+      CK(cudaMalloc((void **)&c->d_gout[i], sizeof(SkPeerOut)));
+      CK(cudaMemset(c->d_gout[i], 0, sizeof(SkPeerOut)));
+    }
+  if (const char *sc = std::getenv("SK_SHARDED_CHAIN")) c->sharded_chain = std::atoi(sc) != 0;
+  c->peer_slot = 0;
   c->comm_rank = rank;
   c->comm_size = nranks;
   c->peer_n = nranks;
@@ -1770,11 +1821,16 @@ int sk_comm_allgather(sk_ctx *c, const double *vals, int32_t k, double *out) {
   CK(cudaSetDevice(c->device));
   unsigned long long w[7] = {0, 0, 0, 0, 0, 0, 0};
   std::memcpy(w, vals, sizeof(double) * k);
-  int rc = peer_exchange(c, 2, SK_PX_GATHER, 0, 0, 0, w, k, 0);
-  if (rc != SK_OK) return rc;
-  CK(cudaStreamSynchronize(c->stream));
-  rc = peer_check(c, 2);
-  if (rc != SK_OK) return rc;
+  int rc = SK_OK;
+  for (int round = 0;; ++round) {             // (again while void: it met another rank's skipped chained launch)
+    if (round > 8) return fail(c, SK_ERR_STATE, "peer exchange: too many void rounds");
+    rc = peer_exchange(c, 2, SK_PX_GATHER, 0, 0, 0, w, k, 0);
+    if (rc != SK_OK) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    rc = peer_check(c, 2);
+    if (rc != SK_OK) return rc;
+    if (!c->peer_out[2]->void_flag) break;
+  }
   std::memcpy(out, c->peer_out[2]->words, sizeof(double) * k * c->peer_n);
   return SK_OK;
 }
@@ -1811,11 +1867,16 @@ int sk_comm_allreduce(sk_ctx *c, double *vals, int32_t n, int32_t op) {
       const int nw = std::min(7, n - i0);
       unsigned long long w[7] = {0, 0, 0, 0, 0, 0, 0};
       std::memcpy(w, vals + i0, sizeof(double) * nw);
-      int rc = peer_exchange(c, 2, SK_PX_RAW, 0, 0, 0, w, nw, op);
-      if (rc != SK_OK) return rc;
-      CK(cudaStreamSynchronize(c->stream));
-      rc = peer_check(c, 2);
-      if (rc != SK_OK) return rc;
+      int rc = SK_OK;
+      for (int round = 0;; ++round) {
+        if (round > 8) return fail(c, SK_ERR_STATE, "peer exchange: too many void rounds");
+        rc = peer_exchange(c, 2, SK_PX_RAW, 0, 0, 0, w, nw, op);
+        if (rc != SK_OK) return rc;
+        CK(cudaStreamSynchronize(c->stream));
+        rc = peer_check(c, 2);
+        if (rc != SK_OK) return rc;
+        if (!c->peer_out[2]->void_flag) break;
+      }
       std::memcpy(vals + i0, c->peer_out[2]->words, sizeof(double) * nw);
     }
     return SK_OK;
@@ -1837,11 +1898,17 @@ int sk_comm_idle(sk_ctx *c, int32_t which) {
   if (!sharded(c)) return SK_OK;
   CK(cudaSetDevice(c->device));
   if (which == 0 || which == 2) {
-    int rc = which == 2 ? comm_reduce_ab(c, 1, 0) : comm_reduce_a(c, 1);
-    if (rc != SK_OK) return rc;
-    CK(cudaStreamSynchronize(c->stream));
-    rc = peer_check(c, 0);
-    if (rc != SK_OK) return rc;
+    c->peer_slot = 0;
+    int rc = SK_OK;
+    for (int round = 0;; ++round) {           // (again while the exchange is void: an active rank's chained launch skipped)
+      if (round > 8) return fail(c, SK_ERR_STATE, "peer exchange: too many void rounds");
+      rc = which == 2 ? comm_reduce_ab(c, 1, 0) : comm_reduce_a(c, 1);
+      if (rc != SK_OK) return rc;
+      CK(cudaStreamSynchronize(c->stream));
+      rc = peer_check(c, 0);
+      if (rc != SK_OK) return rc;
+      if (!peer_void(c)) break;
+    }
     unsigned int fl = 0;
     double mx = 0.0;
     comm_take_a(c, &fl, &mx);
@@ -2322,7 +2389,9 @@ static int subinterval_builtin_enqueue(sk_ctx *c, double a, double b, const sk_s
       c->pend_spec = true;
       c->pend_timed = false;
       c->pend_rc = SK_OK;
-      c->pend_ab = false;
+      c->pend_ab = sharded(c);
+      c->peer_slot = 0;
+      c->cur_red = c->d_red;
       c->spec_args = c->early1.sa;
       c->need_gen = false;
       c->have_sources = true;
@@ -2342,7 +2411,7 @@ static int subinterval_builtin_enqueue(sk_ctx *c, double a, double b, const sk_s
       c->pend_spec = true;
       c->pend_timed = false;
       c->pend_rc = SK_OK;
-      c->pend_ab = false;
+      c->pend_ab = sharded(c);               // (sharded: its exchange carried the scan's scalars)
       c->spec_args = c->chain.sa;
       c->spec_fresh = false;
       c->need_gen = false;
@@ -2379,11 +2448,11 @@ int sk_subinterval(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, 
 int sk_first_panel_early(sk_ctx *c, double a, double b, const sk_subinterval_opts *o, int32_t *queued) {
   if (!c || !o || !queued) return SK_ERR_ARG;
   *queued = 0;
-  if (c->begin_n < 0 || c->early1.pending || c->chain.pending || sharded(c) || c->in_group || c->timing ||
+  if (c->begin_n < 0 || c->early1.pending || c->chain.pending || !chain_allowed(c) || c->in_group || c->timing ||
       c->interp_mode != 0 || c->family == SK_SDF_HOST || !c->have_rule || o->speculate == nullptr ||
       (o->kernel != SK_KERNEL_COS && o->kernel != SK_KERNEL_SIN) || o->p != c->p || a != 0.0 || !(b > 0.0) ||
-      (c->p != 0.0 && o->logw) || o->speculate->criteria < 0 || o->speculate->criteria > 2 || c->early_global ||
-      !(c->early_hi > 0.0) || c->plan.w <= 0)
+      (c->p != 0.0 && o->logw) || o->speculate->criteria < 0 || o->speculate->criteria > 2 ||
+      (c->early_global && !(c->peer_n > 0)) || !(c->early_hi > 0.0) || c->plan.w <= 0)
     return SK_OK;
   CK(cudaSetDevice(c->device));
   const SkK8State &k8 = c->h_scal->k8;              // fetched behind the first pass (targets_early_range)
@@ -2426,6 +2495,12 @@ int sk_first_panel_early(sk_ctx *c, double a, double b, const sk_subinterval_opt
   c->lo = lo_save; c->r_lo = r_lo_save; c->r_hi = r_hi_save;
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  if (sharded(c)) {
+    // sharded run: the sub-interval's exchange (max |I2-I1| and the scan's scalars over all ranks) goes out behind it; a
+    // launch that skipped itself makes it void and every rank then evaluates the panel the ordinary way
+    int rcx = peer_exchange(c, 0, SK_PX_AB, 0, 0, lo, nullptr, 0, 0, nullptr, nullptr, c->d_red);
+    if (rcx != SK_OK) return rcx;
+  }
   CK(cudaEventRecord(c->ev_red, c->stream));
   sk_ctx::Early &e = c->early1;
   e.pending = true; e.adopted = false;
@@ -2444,7 +2519,8 @@ int sk_first_panel_early(sk_ctx *c, double a, double b, const sk_subinterval_opt
 int sk_subinterval_chain(sk_ctx *c, double a2, double b2, const sk_subinterval_opts *o, double accept_below, int32_t *chained) {
   if (!c || !o || !chained) return SK_ERR_ARG;
   *chained = 0;
-  if (!c->sub_open || !c->pend_spec || c->chain.pending || sharded(c) || c->in_group || c->timing || c->interp_mode != 0 ||
+  if (!c->sub_open || !c->pend_spec || c->chain.pending || !chain_allowed(c) || (sharded(c) && !c->pend_ab) || c->in_group ||
+      c->timing || c->interp_mode != 0 ||
       c->family == SK_SDF_HOST || o->speculate == nullptr || (o->kernel != SK_KERNEL_COS && o->kernel != SK_KERNEL_SIN) ||
       o->p != c->p || !(a2 > 0.0) || !(b2 > a2) || !(accept_below > 0.0) || c->pend_rc != SK_OK ||
       o->speculate->criteria < 0 || o->speculate->criteria > 2)
@@ -2464,6 +2540,11 @@ int sk_subinterval_chain(sk_ctx *c, double a2, double b2, const sk_subinterval_o
   spec.guard = c->d_red;
   std::memcpy(&spec.guard_maxbits, &accept_below, sizeof(double));
   spec.guard_top = c->hi - 1;
+  if (sharded(c)) {                                  // the GLOBAL scalars of the sub-interval in flight (its exchange is queued)
+    spec.guard = nullptr;
+    spec.gguard = c->d_gout[0];
+    std::memcpy(&spec.gguard_rbits, &c->r_hi, sizeof(double));
+  }
   SkReduceOut init;
   std::memset(&init, 0, sizeof(init));
   init.max_unconv = c->lo - 1;
@@ -2481,6 +2562,11 @@ int sk_subinterval_chain(sk_ctx *c, double a2, double b2, const sk_subinterval_o
   c->red_target = nullptr;
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(c->h_red2, c->d_red2, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  if (sharded(c)) {
+    // its exchange goes out behind it (slot 4): void if the guard did not hold -- on every rank alike, the guard is global
+    int rcx = peer_exchange(c, 4, SK_PX_AB, 0, 0, c->lo, nullptr, 0, 0, nullptr, nullptr, c->d_red2);
+    if (rcx != SK_OK) return rcx;
+  }
   CK(cudaEventRecord(c->ev_red2, c->stream));
   c->chain.pending = true;
   c->chain.adopted = false;
@@ -2518,6 +2604,7 @@ int sk_results_chain_device(sk_ctx *c, double *vals_dev, double *errs_dev, doubl
   std::memcpy(&gg.maxbits, &accept_below, sizeof(double));
   gg.top = c->chain.lo - 1;
   gg.ran = c->d_gran;
+  gg.gl = sharded(c) ? c->d_gout[1] : nullptr;       // (the chained panel's exchange is queued in front of this launch)
   CK(cudaMemsetAsync(c->d_gran, 0, sizeof(unsigned int), c->stream));
   k_gather<<<nblk(c->n_in, 1024), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, vals_dev, errs_dev, c->in.p, c->in_scale,
                                                        g.tails, gg);
@@ -2686,11 +2773,17 @@ int sk_subinterval_logw_host(sk_ctx *c, double a, double b, const double *no1, c
   rc = logw_host_enqueue_local(c, a, b, no1, bufa1, bufb1, no2, bufa2, bufb2, o, i0_coef, denom);
   if (sharded(c)) {       // a rank that failed locally still joins the collective (its peers are waiting in it)
     const std::string msg = c->errmsg;
+    c->peer_slot = 0;
+    c->cur_red = c->d_red;
+    c->pend_ab = false;
+    c->pend_rc = rc;
     const int rcc = comm_reduce_a(c, 0, rc != SK_OK);
     if (rcc != SK_OK) return rcc;
     CK(cudaStreamSynchronize(c->stream));
     if (rc != SK_OK) { c->errmsg = msg; return rc; }
-    const int prc = peer_check(c, 0);
+    int prc = peer_check(c, 0);
+    if (prc != SK_OK) return prc;
+    prc = peer_resend_while_void(c);
     if (prc != SK_OK) return prc;
     if (global_a(c).err) return fail(c, SK_ERR_STATE, "another rank failed in this sub-interval");
   } else {

@@ -45,6 +45,7 @@ struct SkReduceOut {            // device scalars written by the reductions
 // (ks, errs) pair in `backup` so that a rejected sub-interval can be rolled back bit for bit) and
 // evaluates the convergence predicate of src/adaptive.jl:185-197 on panel_ks = I2, so that no separate
 // pass over the targets is needed for src/quadrature.jl:261-262, src/adaptive.jl:163-164 and :183-198.
+struct SkPeerOut;
 struct SkSpec {
   int on;
   int criteria;
@@ -70,6 +71,12 @@ struct SkSpec {
   const SkReduceOut *guard;          // nullptr: no guard
   unsigned long long guard_maxbits;  // run only if guard->maxbits < guard_maxbits ...
   long long guard_top;               // ... and guard->max_unconv == guard_top and guard->flags == 0
+  // target-sharded run (peer mailboxes): the same guard on the GLOBAL scalars the previous sub-interval's exchange kernel
+  // left in device memory -- max |I2-I1| over all ranks below the threshold, no NaN / error / void on any rank, and the
+  // global stopping distance still the global r_hi (nothing converged anywhere).  Every rank sees the same words, so
+  // every chained launch of a step takes the same decision.
+  const SkPeerOut *gguard;           // nullptr: the local form above
+  unsigned long long gguard_rbits;   // bit pattern of the global r_hi
   // First panel enqueued behind the SORT (sk_first_panel_early): the number of unique distances and the buffer the
   // unique table ended up in are not known to the host yet -- the kernel takes them from the sort's device-side summary
   // (lo = 0 / 1, the r = 0 row, is known from the first pass).  It skips itself if the sort did not deliver (bad input,
@@ -79,13 +86,7 @@ struct SkSpec {
   long long dyn_lo, dyn_min_n;
 };
 
-__device__ __forceinline__ bool sk_chain_guard_holds(const SkSpec &spec) {
-  if (spec.guard == nullptr) return true;
-  const unsigned long long mb = __ldcg(&spec.guard->maxbits);
-  const unsigned int fl = __ldcg(&spec.guard->flags);
-  const long long top = __ldcg(&spec.guard->max_unconv);
-  return mb < spec.guard_maxbits && fl == 0u && top == spec.guard_top;
-}
+__device__ __forceinline__ bool sk_chain_guard_holds(const SkSpec &spec);
 
 __device__ __forceinline__ double sk_warp_max(double v) {
 #pragma unroll
@@ -981,7 +982,25 @@ struct SkPeerOut {                        // pinned host memory, written by the 
   unsigned long long words[SK_PEER_MAX * 7];   // RANGE: 3 reduced words; RAW: nw reduced words; GATHER: [rank][nw]
   unsigned long long status;              // 0 ok, 1 timed out waiting for a peer
   unsigned long long epoch_done;
+  unsigned long long void_flag;           // 1: some rank marked this exchange void -- it does not count, whatever its kind
 };
+#define SK_PX_VOID (~0ull)                  // maxbits of a void sub-interval exchange (fails every guard's "<" test)
+#define SK_PX_VOID_BIT (1ull << 63)         // ... and the mark in the epoch word, which every kind of exchange carries
+
+__device__ __forceinline__ bool sk_chain_guard_holds(const SkSpec &spec) {
+  if (spec.gguard != nullptr) {
+    const unsigned long long mb = __ldcg(&spec.gguard->ga.maxbits);
+    const unsigned long long bad = __ldcg(&spec.gguard->ga.nan1) | __ldcg(&spec.gguard->ga.nan2) |
+                                   __ldcg(&spec.gguard->ga.nand) | __ldcg(&spec.gguard->ga.err);
+    const unsigned long long rb = __ldcg(&spec.gguard->gb.rbits);
+    return mb < spec.guard_maxbits && bad == 0ull && rb == spec.gguard_rbits;      // (SK_PX_VOID fails the first test)
+  }
+  if (spec.guard == nullptr) return true;
+  const unsigned long long mb = __ldcg(&spec.guard->maxbits);
+  const unsigned int fl = __ldcg(&spec.guard->flags);
+  const long long top = __ldcg(&spec.guard->max_unconv);
+  return mb < spec.guard_maxbits && fl == 0u && top == spec.guard_top;
+}
 
 __device__ __forceinline__ void sk_st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -1008,7 +1027,8 @@ __device__ __forceinline__ unsigned long long sk_warp_max_u64(unsigned long long
 // the exchange as seen by ONE rank (a warp); `a` holds that rank's view of the mailboxes
 __device__ __forceinline__ void sk_peer_exchange_warp(const SkPeerArgs &a, const SkReduceOut *__restrict__ red,
                                                       const SkK8State *__restrict__ k8, SkPeerOut *__restrict__ out,
-                                                      const SkTargetSummary *__restrict__ sum = nullptr) {
+                                                      const SkTargetSummary *__restrict__ sum = nullptr,
+                                                      SkPeerOut *__restrict__ dout = nullptr) {
   const int lane = threadIdx.x & 31;
   unsigned long long w[7] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
   const bool quiet = a.idle || a.err;
@@ -1020,7 +1040,12 @@ __device__ __forceinline__ void sk_peer_exchange_warp(const SkPeerArgs &a, const
     w[3] = (fl & SK_FLAG_NAND) ? 1ull : 0ull;
     w[4] = a.err ? 1ull : 0ull;
   }
-  if ((a.kind == SK_PX_AB && !quiet) || a.kind == SK_PX_B_RED) {
+  // void: this rank's sub-interval was enqueued ahead of time under a device-side guard and skipped itself (its reduction
+  // slot carries SK_FLAG_SKIPPED).  The exchange still takes place -- the ranks stay paired -- but the all-ones word wins
+  // the MAX on every rank: nobody counts this exchange, every rank issues the next one in its place.
+  const bool is_void = (a.kind == SK_PX_A || a.kind == SK_PX_AB) && !quiet && (red->flags & SK_FLAG_SKIPPED) != 0u;
+  if (is_void) { w[0] = SK_PX_VOID; w[1] = w[2] = w[3] = 0ull; }
+  if (((a.kind == SK_PX_AB && !quiet) || a.kind == SK_PX_B_RED) && !is_void) {
     const long long top = red->max_unconv;
     w[5] = top >= a.lo ? red->rbits : 0ull;
     w[6] = (unsigned long long)(top - a.lo + 1 > 0 ? top - a.lo + 1 : 0);
@@ -1044,19 +1069,21 @@ __device__ __forceinline__ void sk_peer_exchange_warp(const SkPeerArgs &a, const
     for (int i = 0; i < 7; ++i) w[i] = a.imm[i];
   }
   const int half = (int)(a.epoch & 1ull);
-  bool ok = true;
+  bool ok = true, vseen = false;
   if (lane < a.n) {
     unsigned long long *dst = a.box[lane] + (size_t)(half * SK_PEER_MAX + a.rank) * SK_PEER_WORDS;
 #pragma unroll
     for (int i = 0; i < 7; ++i) reinterpret_cast<volatile unsigned long long *>(dst)[i] = w[i];
     __threadfence_system();
-    sk_st_release_sys(dst + 7, a.epoch);
+    sk_st_release_sys(dst + 7, a.epoch | (is_void ? SK_PX_VOID_BIT : 0ull));
     // now the words of rank `lane`
     const unsigned long long *src = a.box[a.rank] + (size_t)(half * SK_PEER_MAX + lane) * SK_PEER_WORDS;
     const unsigned long long t0 = sk_globaltimer();
-    while (sk_ld_acquire_sys(src + 7) < a.epoch) {
+    unsigned long long word = 0ull;
+    while (((word = sk_ld_acquire_sys(src + 7)) & ~SK_PX_VOID_BIT) < a.epoch) {
       if (sk_globaltimer() - t0 > a.timeout_ns) { ok = false; break; }
     }
+    vseen = ok && (word & SK_PX_VOID_BIT) != 0ull;
     __threadfence_system();
 #pragma unroll
     for (int i = 0; i < 7; ++i) w[i] = ok ? reinterpret_cast<const volatile unsigned long long *>(src)[i] : 0ull;
@@ -1089,22 +1116,28 @@ __device__ __forceinline__ void sk_peer_exchange_warp(const SkPeerArgs &a, const
     if (lane == 0) {
       if (a.kind == SK_PX_A || a.kind == SK_PX_AB) {
         out->ga.maxbits = r[0]; out->ga.nan1 = r[1]; out->ga.nan2 = r[2]; out->ga.nand = r[3]; out->ga.err = r[4];
+        if (dout) { dout->ga.maxbits = r[0]; dout->ga.nan1 = r[1]; dout->ga.nan2 = r[2]; dout->ga.nand = r[3]; dout->ga.err = r[4]; }
       }
-      if (a.kind == SK_PX_AB || a.kind == SK_PX_B_RED || a.kind == SK_PX_B_IMM) { out->gb.rbits = r[5]; out->gb.n_lb = s; }
+      if (a.kind == SK_PX_AB || a.kind == SK_PX_B_RED || a.kind == SK_PX_B_IMM) {
+        out->gb.rbits = r[5]; out->gb.n_lb = s;
+        if (dout) { dout->gb.rbits = r[5]; dout->gb.n_lb = s; }
+      }
       if (a.kind == SK_PX_RANGE) { out->words[0] = r[0]; out->words[1] = r[1]; out->words[2] = r[2]; }
       if (a.kind == SK_PX_SUMMARY) { out->words[0] = r[0]; out->words[1] = r[1]; out->words[2] = r[2]; out->words[3] = (unsigned long long)s; }
     }
   }
+  const unsigned int any_void = __any_sync(0xffffffffu, vseen);
   if (lane == 0) {
     if (!all_ok) out->status = 1ull;
+    out->void_flag = any_void ? 1ull : 0ull;
     out->epoch_done = a.epoch;
   }
 }
 
 __global__ void __launch_bounds__(32) k_peer_exchange(SkPeerArgs a, const SkReduceOut *__restrict__ red,
                                                       const SkK8State *__restrict__ k8, SkPeerOut *__restrict__ out,
-                                                      const SkTargetSummary *__restrict__ sum) {
-  sk_peer_exchange_warp(a, red, k8, out, sum);
+                                                      const SkTargetSummary *__restrict__ sum, SkPeerOut *__restrict__ dout) {
+  sk_peer_exchange_warp(a, red, k8, out, sum, dout);
 }
 
 // The same protocol with the ranks emulated as the blocks of ONE cooperative launch on one device (tests: separate
@@ -1300,16 +1333,22 @@ struct SkGatherGuard {
   unsigned long long maxbits;
   long long top;
   unsigned int *ran;
+  const SkPeerOut *gl;               // sharded run: the accept test is on the GLOBAL scalars of the chained panel's exchange
 };
 __global__ void __launch_bounds__(256)
 k_gather(const unsigned int *__restrict__ inv, const sk_cplx *__restrict__ res, long long n,
          double *__restrict__ out_v, double *__restrict__ out_e, const double *__restrict__ xin, double xscale,
-         const __grid_constant__ SkTailList T, const SkGatherGuard gg = SkGatherGuard{nullptr, 0ull, 0, nullptr}) {
+         const __grid_constant__ SkTailList T, const SkGatherGuard gg = SkGatherGuard{nullptr, 0ull, 0, nullptr, nullptr}) {
   if (gg.red != nullptr) {
-    const unsigned long long mb = __ldcg(&gg.red->maxbits);
+    unsigned long long mb = __ldcg(&gg.red->maxbits);
     const unsigned int fl = __ldcg(&gg.red->flags);
     const long long top = __ldcg(&gg.red->max_unconv);
-    if (!(mb < gg.maxbits && fl == 0u && top == gg.top)) return;
+    unsigned long long gbad = 0ull;
+    if (gg.gl != nullptr) {          // every rank's max |I2-I1|, NaN / error words (a void exchange fails the "<" test)
+      mb = __ldcg(&gg.gl->ga.maxbits);
+      gbad = __ldcg(&gg.gl->ga.nan1) | __ldcg(&gg.gl->ga.nan2) | __ldcg(&gg.gl->ga.nand) | __ldcg(&gg.gl->ga.err);
+    }
+    if (!(mb < gg.maxbits && fl == 0u && top == gg.top && gbad == 0ull)) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) *gg.ran = 1u;
   }
   // 4 independent random reads in flight per thread (the kernel is bound by the latency of the 16-byte reads)
