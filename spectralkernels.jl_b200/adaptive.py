@@ -14,6 +14,7 @@ the Julia host does, written in Python because the image has no Julia.  There is
 from __future__ import annotations
 
 import math
+import os
 import warnings
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -193,9 +194,11 @@ OVERLAP_HOST_WORK = True
 
 
 def _may_chain(comm) -> bool:
-    """Chained launches (sk_first_panel_early, sk_subinterval_chain): single-GPU runs, and sharded runs whose collectives
-    go over peer mailboxes (the guards then read the global scalars; the library refuses them otherwise anyway)."""
-    return comm.world_size == 1 or (getattr(comm, "fused", False) and getattr(comm, "mode", "") == "peer")
+    """Chained launches (sk_first_panel_early, sk_subinterval_chain): single-GPU runs; sharded runs whose collectives go
+    over peer mailboxes only on request (SK_SHARDED_CHAIN=1: the guards then read the global scalars and a skipped launch
+    makes its exchange void -- it pays on 2 GPUs, not on 8, see sk_ctx::sharded_chain)."""
+    return comm.world_size == 1 or (getattr(comm, "fused", False) and getattr(comm, "mode", "") == "peer"
+                                    and os.environ.get("SK_SHARDED_CHAIN", "0") == "1")
 
 
 def _panel_scalars(cfg, a: float, b: float, crit: str, tau: float):
