@@ -184,7 +184,8 @@ int sk_comm_last(sk_ctx *ctx, double *max_abs_diff, double *r_stop, int64_t *n_a
  *   sk_comm_peer_attach  handles = nranks x 64 bytes in rank order; at most 16 ranks, all on one node
  *   sk_comm_allgather    out[r * k + i] = value i (k <= 7) of rank r; synchronous (the once-per-call range / counts)
  * sk_comm_peer_selftest runs the protocol with the ranks emulated as blocks of one cooperative launch on ONE device
- * (out5: per rank maxbits, err, rbits, n_lb, status | epoch << 8) -- a test hook, not part of the path. */
+ * (out5: per rank maxbits, err, rbits, n_lb, status | void << 1 | epoch << 8; skip_rank >= 0: that rank's last exchange is
+ * that of a chained launch which skipped itself, so every rank must see it void) -- a test hook, not part of the path. */
 int sk_comm_peer_export(sk_ctx *ctx, void *handle64);
 int sk_comm_peer_attach(sk_ctx *ctx, const void *handles, int32_t rank, int32_t nranks);
 int sk_comm_allgather(sk_ctx *ctx, const double *vals, int32_t k, double *out);
@@ -195,7 +196,7 @@ int sk_comm_allgather(sk_ctx *ctx, const double *vals, int32_t k, double *out);
  * answer and then exchanges the three numbers with sk_comm_allgather. */
 int sk_comm_summary(sk_ctx *ctx, int32_t *valid, double *r_lo, double *r_hi, int64_t *n_active);
 int sk_comm_peer_selftest(sk_ctx *ctx, int32_t nranks, int32_t rounds, const uint64_t *maxbits_in, const uint64_t *rbits_in,
-                          const int64_t *top_in, int64_t lo, uint64_t *out5);
+                          const int64_t *top_in, int64_t lo, int32_t skip_rank, uint64_t *out5);
 
 /* pinned host memory for callers that want full PCIe rate (Julia: unsafe_wrap the pointer) */
 int sk_host_alloc(size_t bytes, void **out);

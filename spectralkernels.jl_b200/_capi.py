@@ -92,7 +92,7 @@ SIGNATURES = {
     "sk_comm_peer_attach": (c_int, [c_void_p, c_void_p, c_int32, c_int32]),
     "sk_comm_allgather": (c_int, [c_void_p, _dp, c_int32, _dp]),
     "sk_comm_summary": (c_int, [c_void_p, POINTER(c_int32), _dp, _dp, POINTER(c_int64)]),
-    "sk_comm_peer_selftest": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "sk_comm_peer_selftest": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "sk_host_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "sk_host_free": (c_int, [c_void_p]),
     "sk_nufft1d3": (c_int, [c_void_p, c_int64, _dp, _dp, c_int64, _dp, _dp, c_double]),
@@ -309,7 +309,7 @@ class Session:
         self._ck(self._L.sk_comm_summary(self._h, byref(ok), byref(lo), byref(hi), byref(n)))
         return bool(ok.value), lo.value, hi.value, n.value
 
-    def comm_peer_selftest(self, maxbits, rbits, top, lo: int, rounds: int = 3):
+    def comm_peer_selftest(self, maxbits, rbits, top, lo: int, rounds: int = 3, skip_rank: int = -1):
         """the exchange protocol with len(maxbits) ranks emulated on this one device (test hook)"""
         n = len(maxbits)
         mb = np.ascontiguousarray(maxbits, dtype=np.uint64)
@@ -317,7 +317,7 @@ class Session:
         tp = np.ascontiguousarray(top, dtype=np.int64)
         out = np.zeros(5 * n, dtype=np.uint64)
         self._ck(self._L.sk_comm_peer_selftest(self._h, n, int(rounds), mb.ctypes.data, rb.ctypes.data, tp.ctypes.data, int(lo),
-                                               out.ctypes.data))
+                                               int(skip_rank), out.ctypes.data))
         return out.reshape(n, 5)
 
     def comm_last(self):

@@ -1936,7 +1936,7 @@ int sk_comm_idle(sk_ctx *c, int32_t which) {
 // context's device (ranks as separate launches must not share a GPU).  kind: 0 A, 1 AB, 6 gather of (base + rank).
 // maxbits_in[r], rbits_in[r], top_in[r]: rank r's local scalars; out: per rank {maxbits, err, rbits, n_lb, status}.
 int sk_comm_peer_selftest(sk_ctx *c, int32_t nranks, int32_t rounds, const uint64_t *maxbits_in, const uint64_t *rbits_in,
-                          const int64_t *top_in, int64_t lo, uint64_t *out5) {
+                          const int64_t *top_in, int64_t lo, int32_t skip_rank, uint64_t *out5) {
   if (!c || nranks < 1 || nranks > SK_PEER_MAX || rounds < 1 || !maxbits_in || !rbits_in || !top_in || !out5)
     return fail(c, SK_ERR_ARG, "bad selftest arguments");
   CK(cudaSetDevice(c->device));
@@ -1957,6 +1957,7 @@ int sk_comm_peer_selftest(sk_ctx *c, int32_t nranks, int32_t rounds, const uint6
       hr[r].maxbits = maxbits_in[r] + (unsigned long long)(it - 1);
       hr[r].rbits = rbits_in[r];
       hr[r].max_unconv = top_in[r];
+      if (r == skip_rank && it == rounds) hr[r].flags = SK_FLAG_SKIPPED;     // its (chained) launch skipped itself: void
     }
     cudaMemcpyAsync(red, hr.data(), sizeof(SkReduceOut) * nranks, cudaMemcpyHostToDevice, c->stream);
     SkPeerArgs a;
@@ -1972,7 +1973,8 @@ int sk_comm_peer_selftest(sk_ctx *c, int32_t nranks, int32_t rounds, const uint6
     cudaMemcpy(ho.data(), outs, sizeof(SkPeerOut) * nranks, cudaMemcpyDeviceToHost);
     for (int r = 0; r < nranks; ++r) {
       out5[5 * r + 0] = ho[r].ga.maxbits; out5[5 * r + 1] = ho[r].ga.err; out5[5 * r + 2] = ho[r].gb.rbits;
-      out5[5 * r + 3] = (uint64_t)ho[r].gb.n_lb; out5[5 * r + 4] = ho[r].status | (ho[r].epoch_done << 8);
+      out5[5 * r + 3] = (uint64_t)ho[r].gb.n_lb;
+      out5[5 * r + 4] = ho[r].status | (ho[r].void_flag << 1) | (ho[r].epoch_done << 8);
     }
   }
   cudaFree(boxes); cudaFree(red); cudaFree(outs);

@@ -41,7 +41,14 @@ def test_exchange_protocol_emulated_ranks(sk, nranks):
         assert int(out[r, 1]) == 0
         assert int(out[r, 2]) == want_r
         assert int(out[r, 3]) == want_n
-        assert int(out[r, 4]) & 0xff == 0 and int(out[r, 4]) >> 8 == rounds     # no timeout, last epoch seen
+        assert int(out[r, 4]) & 0xff == 0 and int(out[r, 4]) >> 8 == rounds     # no timeout, not void, last epoch seen
+    if nranks > 1:
+        # one rank's last exchange belongs to a chained launch that skipped itself: EVERY rank must see the exchange void
+        # (mark in the epoch word) and the all-ones word in place of max |I2-I1| (fails every guard's "<" test)
+        out = eng.comm_peer_selftest(maxbits, dist.view(np.uint64), top, lo, rounds=rounds, skip_rank=nranks - 1)
+        for r in range(nranks):
+            assert int(out[r, 0]) == 0xFFFFFFFFFFFFFFFF
+            assert (int(out[r, 4]) >> 1) & 1 == 1 and int(out[r, 4]) & 1 == 0 and int(out[r, 4]) >> 8 == rounds
 
 
 def test_world_size_one_mailbox_run_is_bitwise_identical(sk):
