@@ -280,6 +280,7 @@ struct sk_ctx {
     SkTailList tails;
   } gchain;
   unsigned int *d_gran = nullptr, *h_gran = nullptr;
+  unsigned int gran_gen = 0;                 // generation written by the chained gather that ran
   SkReduceOut *d_red2 = nullptr, *h_red2 = nullptr;
   cudaEvent_t ev_red = nullptr, ev_red2 = nullptr;
   HostScalars *h_scal = nullptr;  // pinned
@@ -335,6 +336,9 @@ int fail(sk_ctx *c, int code, const char *fmt, ...) {
 inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
 int flush_commit(sk_ctx *c);
 int ensure_res_zero(sk_ctx *c);
+// small scalars to / from the device without the copy engine (k_red_init, k_publish: mapped pinned memory)
+int red_init(sk_ctx *c, SkReduceOut *d, long long max_unconv_init);
+int publish(sk_ctx *c, void *host_dst, const void *dev_src, size_t bytes);
 int chain_discard(sk_ctx *c);
 int early_discard(sk_ctx *c);
 
@@ -833,11 +837,10 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
     if (rc != SK_OK) return rc;
     fill_spec(c, o->speculate, spec);
   }
-  SkReduceOut init;
-  std::memset(&init, 0, sizeof(init));
-  init.max_unconv = c->lo - 1;
-  c->h_scal->red = init;
-  CK(cudaMemcpyAsync(c->d_red, &c->h_scal->red, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  {
+    int rci = red_init(c, c->d_red, c->lo - 1);
+    if (rci != SK_OK) return rci;
+  }
   if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
   SkGeom G;
   std::memset(&G, 0, sizeof(G));
@@ -921,7 +924,10 @@ int transform_and_stage_enqueue_local(sk_ctx *c, double a, double b, const sk_su
     LAUNCH_CHECK();
     c->stats.n_direct++;
   }
-  CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  {
+    int rcp = publish(c, &c->h_scal->red, c->d_red, sizeof(SkReduceOut));
+    if (rcp != SK_OK) return rcp;
+  }
   CK(cudaEventRecord(c->ev_red, c->stream));
   c->pend_timed = c->timing && (fast || hk_timed);
   c->pend_spec = spec_on;
@@ -1360,7 +1366,10 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
       // (peer mailboxes: the same 3-word MAX as one exchange kernel; the result lands in pinned memory, slot 1)
       int rcx = peer_exchange(c, 1, SK_PX_RANGE, 0, 0, 0, nullptr, 0, 0, st);
       if (rcx != SK_OK) return rcx;
-      CK(cudaMemcpyAsync(&c->h_scal->k8, st, sizeof(SkK8State), cudaMemcpyDeviceToHost, c->stream));   // (this rank's zeros)
+      {
+        int rcp = publish(c, &c->h_scal->k8, st, sizeof(SkK8State));                                   // (this rank's zeros)
+        if (rcp != SK_OK) return rcp;
+      }
       c->early_global = true;
     } else if (c->comm) {
       // process-per-GPU run: the panels are built from the GLOBAL distance range, so the ranks reduce their key
@@ -1374,7 +1383,8 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
       CK(cudaMemcpyAsync(c->h_scal->hv, w, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
       c->early_global = true;
     } else {
-      CK(cudaMemcpyAsync(&c->h_scal->k8, st, sizeof(SkK8State), cudaMemcpyDeviceToHost, c->stream));
+      int rcp = publish(c, &c->h_scal->k8, st, sizeof(SkK8State));
+      if (rcp != SK_OK) return rcp;
     }
     CK(cudaEventRecord(c->k8_ev, c->stream));
   }
@@ -1394,7 +1404,10 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   LAUNCH_CHECK();
   k_k8_summary<<<1, 1, 0, c->stream>>>(st, c->uxs.p, c->uxs_fix.p, n_in, c->d_sum);
   LAUNCH_CHECK();
-  CK(cudaMemcpyAsync(&c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary), cudaMemcpyDeviceToHost, c->stream));
+  {
+    int rcp = publish(c, &c->h_scal->sum, c->d_sum, sizeof(SkTargetSummary));
+    if (rcp != SK_OK) return rcp;
+  }
   c->peer_summary_sent = false;
   if (c->peer_n > 0 && !c->in_group) {
     // process-per-GPU run over peer mailboxes: what the ranks exchange at the start of a run (global distance range, global
@@ -1492,6 +1505,18 @@ int targets_from_device_buffer(sk_ctx *c, long long n_in, sk_target_info *info, 
   return targets_finish(c, n_in, info, force_general);
 }
 
+int red_init(sk_ctx *c, SkReduceOut *d, long long max_unconv_init) {
+  k_red_init<<<1, 1, 0, c->stream>>>(d, max_unconv_init);
+  LAUNCH_CHECK();
+  return SK_OK;
+}
+int publish(sk_ctx *c, void *host_dst, const void *dev_src, size_t bytes) {
+  k_publish<<<1, 32, 0, c->stream>>>((unsigned long long *)host_dst, (const unsigned long long *)dev_src, (int)(bytes / 8));
+  LAUNCH_CHECK();
+  return SK_OK;
+}
+static_assert(sizeof(SkReduceOut) % 8 == 0 && sizeof(SkTargetSummary) % 8 == 0 && sizeof(SkK8State) % 8 == 0, "k_publish moves 8-byte words");
+
 // ks = errs = 0 (src/adaptive.jl:122), written only when a consumer needs it (see res_zero_pending); the r = 0 row keeps
 // what sk_zero_lag_set put there
 int ensure_res_zero(sk_ctx *c) {
@@ -1576,7 +1601,7 @@ int sk_ctx_create(int device, sk_ctx **out) {
       cudaEventCreateWithFlags(&c->ev_red2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_sum, cudaEventDisableTiming) != cudaSuccess ||
       cudaMalloc((void **)&c->d_gran, sizeof(unsigned int)) != cudaSuccess ||
-      cudaHostAlloc((void **)&c->h_gran, sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess ||
+      cudaHostAlloc((void **)&c->h_gran, 8, cudaHostAllocDefault) != cudaSuccess ||
       cudaMalloc((void **)&c->d_red2, sizeof(SkReduceOut)) != cudaSuccess ||
       cudaHostAlloc((void **)&c->h_red2, sizeof(SkReduceOut), cudaHostAllocDefault) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->in_ev[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -1588,6 +1613,8 @@ int sk_ctx_create(int device, sk_ctx **out) {
     delete c;
     return SK_ERR_ARG;
   }
+  *c->h_gran = 0u;
+  std::memset(c->h_red2, 0, sizeof(SkReduceOut));
   *out = c;
   return SK_OK;
 }
@@ -2482,11 +2509,10 @@ int sk_first_panel_early(sk_ctx *c, double a, double b, const sk_subinterval_opt
   spec.dyn = c->d_sum;
   spec.dyn_lo = lo;
   spec.dyn_min_n = min_n;
-  SkReduceOut init;
-  std::memset(&init, 0, sizeof(init));
-  init.max_unconv = lo - 1;
-  c->h_scal->red = init;
-  CK(cudaMemcpyAsync(c->d_red, &c->h_scal->red, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  {
+    int rci = red_init(c, c->d_red, lo - 1);
+    if (rci != SK_OK) { c->lo = lo_save; return rci; }
+  }
   CK(cudaStreamWaitEvent(c->stream, c->pf_ev, 0));
   swap_src_sets(c);
   c->n_pf_hits++;
@@ -2499,7 +2525,10 @@ int sk_first_panel_early(sk_ctx *c, double a, double b, const sk_subinterval_opt
 #undef CALL
   c->lo = lo_save; c->r_lo = r_lo_save; c->r_hi = r_hi_save;
   LAUNCH_CHECK();
-  CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  {
+    int rcp = publish(c, &c->h_scal->red, c->d_red, sizeof(SkReduceOut));
+    if (rcp != SK_OK) return rcp;
+  }
   if (sharded(c)) {
     // sharded run: the sub-interval's exchange (max |I2-I1| and the scan's scalars over all ranks) goes out behind it; a
     // launch that skipped itself makes it void and every rank then evaluates the panel the ordinary way
@@ -2550,11 +2579,10 @@ int sk_subinterval_chain(sk_ctx *c, double a2, double b2, const sk_subinterval_o
     spec.gguard = c->d_gout[0];
     std::memcpy(&spec.gguard_rbits, &c->r_hi, sizeof(double));
   }
-  SkReduceOut init;
-  std::memset(&init, 0, sizeof(init));
-  init.max_unconv = c->lo - 1;
-  *c->h_red2 = init;
-  CK(cudaMemcpyAsync(c->d_red2, c->h_red2, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  {
+    int rci = red_init(c, c->d_red2, c->lo - 1);
+    if (rci != SK_OK) return rci;
+  }
   CK(cudaStreamWaitEvent(c->stream, c->pf_ev, 0));
   swap_src_sets(c);                                  // the prefetched sources / grids become the current set
   c->n_pf_hits++;
@@ -2566,7 +2594,10 @@ int sk_subinterval_chain(sk_ctx *c, double a2, double b2, const sk_subinterval_o
 #undef CALL
   c->red_target = nullptr;
   LAUNCH_CHECK();
-  CK(cudaMemcpyAsync(c->h_red2, c->d_red2, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  {
+    int rcp = publish(c, c->h_red2, c->d_red2, sizeof(SkReduceOut));
+    if (rcp != SK_OK) return rcp;
+  }
   if (sharded(c)) {
     // its exchange goes out behind it (slot 4): void if the guard did not hold -- on every rank alike, the guard is global
     int rcx = peer_exchange(c, 4, SK_PX_AB, 0, 0, c->lo, nullptr, 0, 0, nullptr, nullptr, c->d_red2);
@@ -2608,13 +2639,12 @@ int sk_results_chain_device(sk_ctx *c, double *vals_dev, double *errs_dev, doubl
   gg.red = c->d_red2;
   std::memcpy(&gg.maxbits, &accept_below, sizeof(double));
   gg.top = c->chain.lo - 1;
-  gg.ran = c->d_gran;
+  gg.ran = c->h_gran;                                // (mapped pinned memory: no copy back)
+  gg.gen = ++c->gran_gen;
   gg.gl = sharded(c) ? c->d_gout[1] : nullptr;       // (the chained panel's exchange is queued in front of this launch)
-  CK(cudaMemsetAsync(c->d_gran, 0, sizeof(unsigned int), c->stream));
   k_gather<<<nblk(c->n_in, 1024), 256, 0, c->stream>>>(c->inv.p, c->res.p, c->n_in, vals_dev, errs_dev, c->in.p, c->in_scale,
                                                        g.tails, gg);
   LAUNCH_CHECK();
-  CK(cudaMemcpyAsync(c->h_gran, c->d_gran, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
   g.vals = vals_dev; g.errs = errs_dev;
   g.pending = true;
   *queued = 1;
@@ -2996,7 +3026,7 @@ int sk_results_get_device(sk_ctx *c, double *vals_dev, double *errs_dev) {
                       c->tails.n == c->gchain.tails.n &&
                       std::memcmp(c->tails.seg, c->gchain.tails.seg, sizeof(SkTailSeg) * (size_t)c->tails.n) == 0;
     CK(cudaStreamSynchronize(c->stream));
-    if (same && *c->h_gran == 1u) {
+    if (same && *c->h_gran == c->gran_gen) {
       c->stats.n_chained++;
       return SK_OK;
     }

@@ -1153,6 +1153,18 @@ __global__ void __launch_bounds__(32) k_peer_exchange_emul(SkPeerArgs a, unsigne
   sk_peer_exchange_warp(mine, red + blockIdx.x, nullptr, outs + blockIdx.x);
 }
 
+// Small device <-> host traffic on the critical path goes through one-warp kernels and mapped pinned memory instead of
+// cudaMemcpyAsync: a 32-byte copy queued between two dependent kernels costs a trip through the copy engine (~5 us of
+// pipeline bubble), a tiny kernel does not.
+__global__ void k_red_init(SkReduceOut *__restrict__ red, long long max_unconv_init) {
+  red->maxbits = 0ull; red->flags = 0u; red->_pad = 0u; red->max_unconv = max_unconv_init; red->rbits = 0ull;
+}
+__global__ void __launch_bounds__(32) k_publish(unsigned long long *__restrict__ host_dst,
+                                                const unsigned long long *__restrict__ dev_src, int nwords) {
+  for (int i = threadIdx.x; i < nwords; i += 32) host_dst[i] = dev_src[i];
+  __threadfence_system();
+}
+
 // roll a rejected speculative commit back: res = backup (bit for bit)
 __global__ void k_restore(sk_cplx *__restrict__ res, const sk_cplx *__restrict__ backup, long long n) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1332,13 +1344,14 @@ struct SkGatherGuard {
   const SkReduceOut *red;            // nullptr: unconditional
   unsigned long long maxbits;
   long long top;
-  unsigned int *ran;
+  unsigned int *ran;                 // (mapped pinned host memory) receives `gen` when the gather runs
+  unsigned int gen;
   const SkPeerOut *gl;               // sharded run: the accept test is on the GLOBAL scalars of the chained panel's exchange
 };
 __global__ void __launch_bounds__(256)
 k_gather(const unsigned int *__restrict__ inv, const sk_cplx *__restrict__ res, long long n,
          double *__restrict__ out_v, double *__restrict__ out_e, const double *__restrict__ xin, double xscale,
-         const __grid_constant__ SkTailList T, const SkGatherGuard gg = SkGatherGuard{nullptr, 0ull, 0, nullptr, nullptr}) {
+         const __grid_constant__ SkTailList T, const SkGatherGuard gg = SkGatherGuard{nullptr, 0ull, 0, nullptr, 0u, nullptr}) {
   if (gg.red != nullptr) {
     unsigned long long mb = __ldcg(&gg.red->maxbits);
     const unsigned int fl = __ldcg(&gg.red->flags);
@@ -1349,7 +1362,7 @@ k_gather(const unsigned int *__restrict__ inv, const sk_cplx *__restrict__ res, 
       gbad = __ldcg(&gg.gl->ga.nan1) | __ldcg(&gg.gl->ga.nan2) | __ldcg(&gg.gl->ga.nand) | __ldcg(&gg.gl->ga.err);
     }
     if (!(mb < gg.maxbits && fl == 0u && top == gg.top && gbad == 0ull)) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *gg.ran = 1u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *gg.ran = gg.gen; __threadfence_system(); }      // (mapped host memory)
   }
   // 4 independent random reads in flight per thread (the kernel is bound by the latency of the 16-byte reads)
   const long long j0 = ((long long)blockIdx.x * blockDim.x) * 4 + threadIdx.x;
