@@ -1349,7 +1349,9 @@ int targets_enqueue(sk_ctx *c, long long n_in) {
   unsigned int *dup = (unsigned int *)(c->k8_ctl.p + off_dup);
   unsigned int *dsum = (unsigned int *)(c->k8_ctl.p + off_dsum);
   if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
-  CK(cudaMemsetAsync(c->k8_ctl.p, 0, ctl_bytes, c->stream));
+  static_assert((256 + sizeof(unsigned int) * SK_K8_NC) % 8 == 0 && (sizeof(unsigned int) * SK_K8_FILL_STRIDE) % 8 == 0, "8-byte words");
+  k_zero_words<<<148, 256, 0, c->stream>>>((unsigned long long *)c->k8_ctl.p, (long long)(ctl_bytes / 8));   // (a kernel, not a memset node)
+  LAUNCH_CHECK();
   const unsigned int gs = std::min<unsigned int>(nblk(n_in, 256), 148u * 8u);    // grid-stride passes: 2048 threads per SM
   k_k8_stats<<<gs, 256, 0, c->stream>>>(src, n_in, st);
   LAUNCH_CHECK();

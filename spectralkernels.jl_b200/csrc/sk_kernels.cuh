@@ -1159,6 +1159,9 @@ __global__ void __launch_bounds__(32) k_peer_exchange_emul(SkPeerArgs a, unsigne
 __global__ void k_red_init(SkReduceOut *__restrict__ red, long long max_unconv_init) {
   red->maxbits = 0ull; red->flags = 0u; red->_pad = 0u; red->max_unconv = max_unconv_init; red->rbits = 0ull;
 }
+__global__ void k_zero_words(unsigned long long *__restrict__ p, long long nwords) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x) p[i] = 0ull;
+}
 __global__ void __launch_bounds__(32) k_publish(unsigned long long *__restrict__ host_dst,
                                                 const unsigned long long *__restrict__ dev_src, int nwords) {
   for (int i = threadIdx.x; i < nwords; i += 32) host_dst[i] = dev_src[i];
