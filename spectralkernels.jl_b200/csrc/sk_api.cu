@@ -2727,7 +2727,10 @@ static int logw_host_enqueue_local(sk_ctx *c, double a, double b, const double *
     LAUNCH_CHECK();
   }
   c->have_sources = true;
-  CK(cudaMemsetAsync(c->d_red, 0, sizeof(SkReduceOut), c->stream));
+  {
+    int rci = red_init(c, c->d_red, 0);
+    if (rci != SK_OK) return rci;
+  }
   SkLogwArgs L;
   L.i0_coef = i0_coef;
   L.denom = denom;
@@ -2787,7 +2790,10 @@ static int logw_host_enqueue_local(sk_ctx *c, double a, double b, const double *
     LAUNCH_CHECK();
     c->stats.n_direct++;
   }
-  CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  {
+    int rcp = publish(c, &c->h_scal->red, c->d_red, sizeof(SkReduceOut));
+    if (rcp != SK_OK) return rcp;
+  }
   return SK_OK;
 }
 
@@ -2923,11 +2929,10 @@ static int converge_scan_enqueue(sk_ctx *c, const sk_scan_args *a) {
     return SK_OK;
   }
   const long long n = c->hi - c->lo;
-  SkReduceOut init;
-  std::memset(&init, 0, sizeof(init));
-  init.max_unconv = c->lo - 1;
-  c->h_scal->red = init;
-  CK(cudaMemcpyAsync(c->d_red, &c->h_scal->red, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  {
+    int rci = red_init(c, c->d_red, c->lo - 1);
+    if (rci != SK_OK) return rci;
+  }
   const int do_commit = (c->commit_pending && c->pend_lo == c->lo && c->pend_hi == c->hi) ? 1 : 0;
   if (c->commit_pending && !do_commit) {
     int rc = flush_commit(c);
@@ -2941,7 +2946,10 @@ static int converge_scan_enqueue(sk_ctx *c, const sk_scan_args *a) {
                                                      a->trunc_a, a->trunc_num, a->xpow, a->tau, a->criteria, c->d_red);
   LAUNCH_CHECK();
   c->commit_pending = false;
-  CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  {
+    int rcp = publish(c, &c->h_scal->red, c->d_red, sizeof(SkReduceOut));
+    if (rcp != SK_OK) return rcp;
+  }
   return comm_reduce_b(c, true, 0ull, 0);
 }
 
@@ -3010,7 +3018,10 @@ int sk_target_upper_index(sk_ctx *c, double r, int64_t *idx) {
   if (!c->have_targets) return fail(c, SK_ERR_STATE, "no targets set");
   k_upper_bound<<<1, 1, 0, c->stream>>>(c->uxs.p, c->n_unique, r, &c->d_red->max_unconv);
   LAUNCH_CHECK();
-  CK(cudaMemcpyAsync(&c->h_scal->red, c->d_red, sizeof(SkReduceOut), cudaMemcpyDeviceToHost, c->stream));
+  {
+    int rcp = publish(c, &c->h_scal->red, c->d_red, sizeof(SkReduceOut));
+    if (rcp != SK_OK) return rcp;
+  }
   CK(cudaStreamSynchronize(c->stream));
   *idx = c->h_scal->red.max_unconv;
   return SK_OK;
