@@ -117,8 +117,10 @@ typedef struct sk_stats {
   int64_t n_prefetch_issued;/* sub-intervals whose source side (nodes, strengths, spread, FFT) was computed ahead on the
                                second stream, since the context was created ...                 */
   int64_t n_prefetch_hits;  /* ... and how many of them the driver then actually asked for      */
-  int64_t n_chained;        /* sub-intervals that were enqueued ahead of time behind the previous panel's
-                               (sk_subinterval_chain) and picked up, since sk_run_begin         */
+  int64_t n_chained;        /* launches that were enqueued ahead of time (sk_first_panel_early, sk_subinterval_chain,
+                               sk_results_chain_device) and picked up, since sk_run_begin      */
+  int64_t launches_total;   /* kernels of this library launched since the context was created (the sort of
+                               sk_targets_set* runs before sk_run_begin resets the other counters) */
 } sk_stats;
 
 /* ---- library --------------------------------------------------------------------------------- */

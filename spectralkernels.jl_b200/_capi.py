@@ -49,7 +49,7 @@ class Stats(ctypes.Structure):
                 ("n_fast", c_int64), ("n_direct", c_int64), ("kernel_launches", c_int64), ("last_nf", c_int64),
                 ("last_nf2", c_int64), ("n_speculated", c_int64), ("n_spec_rollbacks", c_int64), ("interp_ms", c_double), ("source_ms", c_double),
                 ("timing_enabled", c_int32), ("sort_two_level", c_int32), ("n_hankel", c_int64), ("sort_ms", c_double),
-                ("gather_ms", c_double), ("n_prefetch_issued", c_int64), ("n_prefetch_hits", c_int64), ("n_chained", c_int64)]
+                ("gather_ms", c_double), ("n_prefetch_issued", c_int64), ("n_prefetch_hits", c_int64), ("n_chained", c_int64), ("launches_total", c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}

@@ -287,6 +287,7 @@ struct sk_ctx {
 
   // stats / timing
   sk_stats stats;
+  long long launches_total = 0;              // kernels launched since the context was created (sk_stats.launches_total)
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_user[2] = {nullptr, nullptr};
@@ -319,7 +320,7 @@ int fail(sk_ctx *c, int code, const char *fmt, ...) {
     cudaError_t e_ = cudaGetLastError();                                                        \
     if (e_ != cudaSuccess)                                                                      \
       return fail(c, SK_ERR_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
-    c->stats.kernel_launches++;                                                                 \
+    c->stats.kernel_launches++, c->launches_total++;                                                                 \
   } while (0)
 
 #define DISPATCH_W(w, CALL)                \
@@ -568,7 +569,7 @@ int run_source_side(sk_ctx *c, const SkGeom &G, int nrule, long long M1, const d
   if (rc != SK_OK) return rc;
   cufftResult fr = cufftExecZ2Z(h, (cufftDoubleComplex *)fft_out.p, (cufftDoubleComplex *)fft_out.p, CUFFT_INVERSE);
   if (fr != CUFFT_SUCCESS) return fail(c, SK_ERR_CUFFT, "cufftExecZ2Z failed: %d", (int)fr);
-  c->stats.kernel_launches++;
+  c->stats.kernel_launches++, c->launches_total++;
   c->stats.last_nf = G.nf;
   c->stats.last_nf2 = G.nf2;
   return SK_OK;
@@ -660,7 +661,7 @@ int hankel_stage(sk_ctx *c, double a, double b, int nu, const double *sbuf1, con
     if (rc != SK_OK) return rc;
     cufftResult fr = cufftExecZ2Z(h, (cufftDoubleComplex *)dst, (cufftDoubleComplex *)grid_g, CUFFT_INVERSE);   // shared: out of place
     if (fr != CUFFT_SUCCESS) return fail(c, SK_ERR_CUFFT, "cufftExecZ2Z failed: %d", (int)fr);
-    c->stats.kernel_launches++;
+    c->stats.kernel_launches++, c->launches_total++;
     c->stats.last_nf = G.nf;
     c->stats.last_nf2 = G.nf2;
   }
@@ -1191,7 +1192,7 @@ int ensure_gauss_rules(sk_ctx *c, const std::vector<std::pair<int, double>> &wan
       if (ok) {
         dim3 grid((nmax + 63) / 64, nj);
         k_gauss_rules<<<grid, 64, 0, c->stream>>>(djobs, nj);
-        c->stats.kernel_launches++;
+        c->stats.kernel_launches++, c->launches_total++;
         ok = cudaGetLastError() == cudaSuccess &&
              cudaMemcpyAsync(hout.data(), dout, sizeof(double) * out_doubles, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
              cudaStreamSynchronize(c->stream) == cudaSuccess;
@@ -3195,6 +3196,7 @@ int sk_stats_get(sk_ctx *c, sk_stats *out) {
   if (!c || !out) return SK_ERR_ARG;
   c->stats.n_prefetch_issued = c->n_pf_issued;
   c->stats.n_prefetch_hits = c->n_pf_hits;
+  c->stats.launches_total = c->launches_total;
   *out = c->stats;
   return SK_OK;
 }
