@@ -41,6 +41,20 @@ class FakeEngine:
         return types.SimpleNamespace(n_in=xs.size, n_unique=n, has_zero=int(self.uxs[0] == 0),
                                      r_min_pos=float(pos[0]) if pos.size else 0.0, r_max=float(self.uxs[-1]))
 
+    # the two halves of targets_set (sk_targets_begin / _early_range / _end): the host prepares the first panel in between
+    def targets_begin(self, xs):
+        self._pending = np.asarray(xs, dtype=np.float64)
+        self.calls.append(("targets_begin",))
+
+    def targets_early_range(self):
+        pos = self._pending[self._pending > 0]
+        self.calls.append(("targets_early_range",))
+        return (float(pos.min()), float(pos.max())) if pos.size else (0.0, 0.0)
+
+    def targets_end(self):
+        self.calls.append(("targets_end",))
+        return self.targets_set(self._pending)
+
     def run_begin(self):
         n = self.uxs.size
         self.ks, self.errs = np.zeros(n), np.zeros(n)

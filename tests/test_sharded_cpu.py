@@ -122,3 +122,35 @@ def test_driver_with_fake_engine_matches_oracle_driver():
         assert np.array_equal(np.isnan(eg), np.isnan(eo)), kw
         assert np.allclose(np.nan_to_num(eg), np.nan_to_num(eo), rtol=1e-10, atol=0), kw
         assert _key(tg, True) == _key(to, True), kw
+
+
+def test_first_panel_scalars_are_prepared_while_the_targets_are_sorted():
+    """sk_targets_begin / _early_range / _end in the host driver (adaptive.py): the tail fit of the first panel is evaluated
+    between the two halves (while the device sorts), the panel loop then finds it; values, errors and the trace equal the
+    blocking call sequence bit for bit."""
+    import spectralkernels_jl_b200 as sk
+    from spectralkernels_jl_b200 import adaptive as ad
+    from fake_engine import FakeEngine
+    S = lambda w: (1.0 + w ** 2) ** -1.3
+    xs = np.concatenate([[0.0], 10 ** np.random.default_rng(2).uniform(-3, 0, 40)])
+    out = []
+    for overlap in (False, True):
+        eng = FakeEngine()
+        log = []
+        real = ad.estimate_tail_decay
+        ad.OVERLAP_HOST_WORK = overlap
+        ad.estimate_tail_decay = lambda *a, **k: (log.append(len(eng.calls)), real(*a, **k))[1]
+        try:
+            cfg = sk.AdaptiveKernelConfig(S, engine=eng, quadspec=(256, 4))
+            tr = []
+            v, e = sk.kernel_values(cfg, xs, k0=1.9, trace=tr)
+        finally:
+            ad.OVERLAP_HOST_WORK = True
+            ad.estimate_tail_decay = real
+        key = [(t["kind"], t["a"], t["b"], t.get("accepted"), t.get("hi_after"), t.get("criteria")) for t in tr]
+        out.append((v, e, key, [c[0] for c in eng.calls], log))
+    (v0, e0, k0_, c0, l0), (v1, e1, k1_, c1, l1) = out
+    assert np.array_equal(v0, v1) and np.array_equal(np.nan_to_num(e0, nan=-1), np.nan_to_num(e1, nan=-1)) and k0_ == k1_
+    assert "targets_begin" not in c0 and c1[:3] == ["targets_begin", "targets_early_range", "targets_end"]
+    # with the halves, the first tail fit ran after targets_early_range and BEFORE targets_end (2 engine calls logged so far)
+    assert l1[0] == 2 and len(l1) == len(l0)
