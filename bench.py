@@ -415,8 +415,11 @@ def run(args):
                        "launch_chaining": ("device-guarded: first panel queued behind the sort, second behind the first, gather "
                                            "behind the second (sk_first_panel_early / sk_subinterval_chain / "
                                            "sk_results_chain_device); host scalar work overlapped") if world == 1 else
-                                          "host scalar work overlapped with device work (begin/end halves); no chained launches "
-                                          "in sharded runs",
+                                          ("host scalar work overlapped with device work (begin/end halves); chained launches "
+                                           + ("(first panel behind the sort, second behind the first: guards on the global scalars, "
+                                              "void exchanges)" if (world <= 2 or os.environ.get("SK_SHARDED_CHAIN") == "1")
+                                              and os.environ.get("SK_SHARDED_CHAIN") != "0" and getattr(comm, "mode", "") == "peer"
+                                              else "off at this rank count")),
                        "parallelism": ("target-sharded, scalar collectives only: "
                                        + {"peer": "single-warp exchange kernels over NVLink peer-mapped mailboxes "
                                                   "(k_peer_exchange) on the compute stream, no NCCL on the data path",

@@ -195,10 +195,13 @@ OVERLAP_HOST_WORK = True
 
 def _may_chain(comm) -> bool:
     """Chained launches (sk_first_panel_early, sk_subinterval_chain): single-GPU runs; sharded runs whose collectives go
-    over peer mailboxes only on request (SK_SHARDED_CHAIN=1: the guards then read the global scalars and a skipped launch
-    makes its exchange void -- it pays on 2 GPUs, not on 8, see sk_ctx::sharded_chain)."""
-    return comm.world_size == 1 or (getattr(comm, "fused", False) and getattr(comm, "mode", "") == "peer"
-                                    and os.environ.get("SK_SHARDED_CHAIN", "0") == "1")
+    over peer mailboxes with 2 ranks (more on request, SK_SHARDED_CHAIN=1: the guards then read the global scalars and a
+    skipped launch makes its exchange void -- it pays on 2 GPUs, not on 8, see sk_ctx::sharded_chain)."""
+    if comm.world_size == 1:
+        return True
+    env = os.environ.get("SK_SHARDED_CHAIN")
+    on = (env == "1") if env is not None else comm.world_size <= 2          # (same rule as sk_comm_peer_attach)
+    return bool(getattr(comm, "fused", False) and getattr(comm, "mode", "") == "peer" and on)
 
 
 def _panel_scalars(cfg, a: float, b: float, crit: str, tau: float):

@@ -224,9 +224,9 @@ struct sk_ctx {
   SkPeerOut *d_gout[2] = {nullptr, nullptr}; // device mirrors of slots 0 and 4 (the guards of chained launches read them)
   int peer_slot = 0;                         // where the scalars of the sub-interval being finished are: 0, or 4 (chained)
   const SkReduceOut *cur_red = nullptr;      // its local reduction slot (d_red, or d_red2 for an adopted chained launch)
-  // chained launches in sharded runs: opt-in (SK_SHARDED_CHAIN=1).  Measured: 2 GPUs 1.241 -> 1.215 ms per step, 8 GPUs
-  // 1.258 -> 1.270 ms -- a chained panel cannot start before EVERY rank's previous panel has gone through the exchange, so
-  // with more ranks the skew eats what the saved host round trip gives
+  // chained launches in sharded runs: on for 2 ranks, off beyond (SK_SHARDED_CHAIN=0/1 overrides).  Measured: 2 GPUs
+  // 1.234 -> 1.20 ms per step, 8 GPUs 1.258 -> 1.270 ms -- a chained panel cannot start before EVERY rank's previous panel
+  // has gone through the exchange, so with more ranks the skew eats what the saved host round trip gives
   bool sharded_chain = false;
   bool peer_summary_sent = false;            // the sort's summary went out behind it (sk_comm_summary)
   double peer_timeout_s = 20.0;
@@ -1836,6 +1836,7 @@ int sk_comm_peer_attach(sk_ctx *c, const void *handles, int32_t rank, int32_t nr
       CK(cudaMalloc((void **)&c->d_gout[i], sizeof(SkPeerOut)));
       CK(cudaMemset(c->d_gout[i], 0, sizeof(SkPeerOut)));
     }
+  c->sharded_chain = nranks <= 2;
   if (const char *sc = std::getenv("SK_SHARDED_CHAIN")) c->sharded_chain = std::atoi(sc) != 0;
   c->peer_slot = 0;
   c->comm_rank = rank;
